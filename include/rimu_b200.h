@@ -1,0 +1,204 @@
+/*
+ * rimu_b200.h -- C ABI of the B200-native FCIQMC step (librimu_b200.so).
+ *
+ * This is the drop-in boundary for Rimu.jl's hot path.  Every entry point names the
+ * reference interface it replaces (path:line under RimuQMC/Rimu.jl v0.14.0 `src/`).
+ * The Julia-side binding (`ccall`) a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: opaque handles, plain pointers and sizes; no C++/torch types.
+ *   - every function returns an int status: 0 ok; >0 recoverable (caller may regrow and
+ *     retry, the source vector is never modified by a failed step); <0 fatal.
+ *     rimu_last_error() returns a human-readable message for the calling thread.
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - one host thread drives one context; a context owns one GPU, one stream, one working
+ *     table ("working memory", the analogue of PDWorkingMemory) and optionally one NCCL
+ *     communicator.  There is NO CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Address ("key") interchange format: W little-endian uint64 words per address, word 0 least
+ * significant.  BoseFS{N,M}: bit layout of BitStringAddresses/bitstring.jl:464-472 (mode 1 in
+ * the lowest bits, n ones then a 0 separator), B = N+M-1 bits, W = ceil((B+1)/64) <= 2 (one spare
+ * bit is kept so that the all-ones word pattern can mark empty table slots).
+ * FermiFS{N,M}: bit m-1 <-> mode m (bitstring.jl:713-723).  CompositeFS of two FermiFS
+ * (FermiFS2C): component c occupies bits [c*M, (c+1)*M), 2M <= 64.
+ * Julia's BitString stores chunks most-significant first (bitstring.jl:72-75); the shim
+ * reverses chunk order and widens sub-64-bit chunk types.
+ * Values are one 8-byte lane: double (RIMU_VAL_F64) or int64 (RIMU_VAL_I64).
+ */
+#ifndef RIMU_B200_H
+#define RIMU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIMU_MAX_MODES 128
+#define RIMU_MAX_TABLE_MODES 64
+
+/* status codes */
+enum {
+    RIMU_OK = 0,
+    RIMU_ERR_TABLE_FULL = 1,     /* working table too small for this step: grow / raise active slots, retry */
+    RIMU_ERR_VECTOR_FULL = 2,    /* destination vector capacity too small; *needed written where documented */
+    RIMU_ERR_EXCHANGE_FULL = 3,  /* per-peer spawn exchange buffer too small */
+    RIMU_ERR_INVALID = -1,       /* bad argument / unsupported combination (ArgumentError in the reference) */
+    RIMU_ERR_CUDA = -2,
+    RIMU_ERR_NCCL = -3,
+    RIMU_ERR_NO_DEVICE = -4
+};
+
+enum { RIMU_ADDR_BOSE = 0, RIMU_ADDR_FERMI = 1, RIMU_ADDR_FERMI2C = 2 };
+enum { RIMU_HUBBARD_REAL_1D = 0, RIMU_HUBBARD_MOM_1D = 1, RIMU_HUBBARD_REAL_SPACE = 2, RIMU_TRANSCORRELATED_1D = 3 };
+enum { RIMU_VAL_F64 = 0, RIMU_VAL_I64 = 1 };
+/* StochasticStyles/styles.jl: IsDeterministic (:76-105), IsStochasticInteger (:11-25),
+ * IsDynamicSemistochastic (:175-214), IsStochasticWithThreshold (:117-130) */
+enum { RIMU_STYLE_DETERMINISTIC = 0, RIMU_STYLE_INTEGER = 1, RIMU_STYLE_SEMISTOCHASTIC = 2, RIMU_STYLE_WITH_THRESHOLD = 3 };
+enum { RIMU_ANNIHILATE_HASH = 0, RIMU_ANNIHILATE_SORT = 1 };
+
+typedef struct rimu_ctx rimu_ctx;
+typedef struct rimu_ham rimu_ham;
+typedef struct rimu_vec rimu_vec;
+
+/* Hamiltonian descriptor.  Replaces the Julia structs
+ *   HubbardReal1D (Hamiltonians/HubbardReal1D.jl:23-31), HubbardMom1D (HubbardMom1D.jl:43-65),
+ *   HubbardRealSpace (HubbardRealSpace.jl:166-241), Transcorrelated1D (Transcorrelated1D.jl:55-89)
+ * and the address type parameters (BoseFS{N,M}, FermiFS{N,M}, CompositeFS).
+ * Tables (kes, ws, us, potential) are the SVector fields the Julia constructors precompute;
+ * the host shim passes them through unchanged so both sides use identical constants. */
+typedef struct {
+    int32_t model;          /* RIMU_HUBBARD_* / RIMU_TRANSCORRELATED_1D */
+    int32_t addr_kind;      /* RIMU_ADDR_* */
+    int32_t num_modes;      /* M (per component) */
+    int32_t num_components; /* 1 or 2 */
+    int32_t num_particles[2];
+    int32_t ndim;           /* HubbardRealSpace: CubicGrid{D} (geometry.jl:45-54) */
+    int32_t dims[3];
+    int32_t fold[3];        /* periodic flag per dimension */
+    int32_t cutoff;         /* Transcorrelated1D */
+    int32_t three_body_term;
+    int32_t has_potential;  /* potential[] valid (HubbardRealSpace trap) */
+    int32_t reserved;
+    double u, t, v;         /* 1-D models: u,t ; Transcorrelated1D: t,v */
+    double t_comp[2];       /* HubbardRealSpace hopping per component */
+    double u_mat[4];        /* HubbardRealSpace interactions, column major u[i + 2*j] */
+    double kes[RIMU_MAX_TABLE_MODES];
+    double ws[RIMU_MAX_TABLE_MODES];
+    double us[RIMU_MAX_TABLE_MODES];
+    double potential[2 * RIMU_MAX_MODES]; /* potential[c*M + site] */
+} rimu_ham_desc;
+
+/* One FCIQMC step = Interfaces.apply_operator!(wm, target, source, op, boost)
+ * (Interfaces/dictvectors.jl:90-140; PDVec method DictVectors/pdworkingmemory.jl:297-309)
+ * with op = FirstOrderTransitionOperator(H, shift, time_step) (fciqmc.jl:78-112), or op = H
+ * itself when plain_h != 0 (mul!, DictVectors/pdvec.jl:810-822). */
+typedef struct {
+    int32_t style;            /* RIMU_STYLE_* */
+    int32_t plain_h;
+    double shift, time_step, boost;
+    double proj_threshold;    /* on-the-fly projection threshold of the spawning strategy (spawning.jl:9-30) */
+    double rel_threshold;     /* DynamicSemistochastic.rel_threshold (spawning.jl:358-362) */
+    double abs_threshold;     /* DynamicSemistochastic.abs_threshold; +Inf = off */
+    double compress_threshold;/* ThresholdCompression.threshold (compression.jl:8-26); 0 = NoCompression */
+    uint64_t seed;            /* Philox key material: per-step key = f(seed, step) */
+    uint64_t step;
+    uint64_t table_slots;     /* working-table slots to use this step (power of two, <= ctx capacity); 0 = auto */
+} rimu_step_params;
+
+/* step_stats of the styles (styles.jl:14-20,94-96,203-209; compression.jl:16) plus
+ * walkernumber_and_length of the result (pdvec.jl:896-902).  Integer-style quantities are
+ * exact in the i* fields; float styles use the double fields. Sums are GLOBAL over ranks
+ * when a communicator is attached. */
+typedef struct {
+    int64_t exact_steps, inexact_steps, spawn_attempts, len_before, len;
+    double spawns, deaths, clones, zombies, norm1;
+    int64_t ispawns, ideaths, iclones, izombies, inorm1;
+    int64_t local_len;        /* entries stored on this rank */
+    int64_t sent_records;     /* records this rank sent to peers */
+    float ms_spawn, ms_exchange, ms_compact; /* CUDA-event phase timings of this call */
+    float ms_total;
+} rimu_step_stats;
+
+/* ---- context ------------------------------------------------------------ */
+const char *rimu_last_error(void);
+int rimu_version(void);
+/* table_slots: capacity of the working table in slots (rounded up to a power of two);
+ * words: uint64 words per address (1 or 2). */
+int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu_ctx **out);
+int rimu_ctx_destroy(rimu_ctx *ctx);
+int rimu_ctx_synchronize(rimu_ctx *ctx);
+int rimu_ctx_table_slots(rimu_ctx *ctx, uint64_t *out);
+/* reallocate the working table (contents are scratch between calls) */
+int rimu_ctx_resize_table(rimu_ctx *ctx, uint64_t table_slots);
+/* raw cudaStream_t of the context, for callers that want to time with their own events */
+int rimu_ctx_stream(rimu_ctx *ctx, void **stream_out);
+
+/* ---- multi-GPU: replaces DictVectors/communicators.jl AllToAll (:546-606),
+ * mpi_exchange_alltoall! (:475-498) and merge_remote_reductions (:56) ------ */
+int rimu_comm_unique_id(void *id128);               /* ncclGetUniqueId; broadcast by the host launcher */
+int rimu_comm_init(rimu_ctx *ctx, const void *id128, int rank, int nranks, uint64_t exchange_records_per_peer);
+int rimu_comm_rank(rimu_ctx *ctx, int *rank, int *nranks);
+int rimu_comm_allreduce_f64(rimu_ctx *ctx, double *host_inout, int n);
+/* owner rank of an address: communicators.jl:77-81 target_segment */
+int rimu_addr_owner(const uint64_t *key, int words, int nranks);
+uint64_t rimu_addr_hash(const uint64_t *key, int words);
+
+/* ---- Hamiltonian (Interfaces/hamiltonians.jl:143-201,350-370) ------------ */
+int rimu_ham_create(const rimu_ham_desc *desc, rimu_ham **out);
+int rimu_ham_destroy(rimu_ham *ham);
+int rimu_ham_words(const rimu_ham *ham);
+/* element-wise hooks evaluated by the DEVICE code, host buffers in/out:
+ * diagonal_element(h, addr), num_offdiagonals(h, addr), get_offdiagonal(h, addr, chosen) for
+ * chosen = first..first+count-1 (1-based as in the reference). */
+int rimu_ham_diagonal(rimu_ctx *ctx, const rimu_ham *ham, const uint64_t *keys, int64_t n, double *out);
+int rimu_ham_num_offdiagonals(rimu_ctx *ctx, const rimu_ham *ham, const uint64_t *keys, int64_t n, int64_t *out);
+int rimu_ham_offdiagonals(rimu_ctx *ctx, const rimu_ham *ham, const uint64_t *key, int64_t first, int64_t count,
+                          uint64_t *keys_out, double *vals_out);
+
+/* ---- walker vector: replaces DVec (DictVectors/dvec.jl:44-47) / PDVec (pdvec.jl:156-163)
+ * storage; dense (keys, values) arrays resident in HBM ---------------------- */
+int rimu_vec_create(rimu_ctx *ctx, int val_type, uint64_t capacity, rimu_vec **out);
+int rimu_vec_destroy(rimu_vec *v);
+int rimu_vec_reserve(rimu_vec *v, uint64_t capacity);      /* grow, keeping contents */
+int rimu_vec_clear(rimu_vec *v);                           /* zerovector!/empty! */
+int rimu_vec_length(rimu_vec *v, int64_t *out);            /* length(localpart(v)) */
+int rimu_vec_capacity(rimu_vec *v, uint64_t *out);
+/* DVec(pairs...): duplicates are summed, zeros dropped (dvec.jl:62-100); with a communicator
+ * attached, keys not owned by this rank are dropped (pdvec.jl:336-349) */
+int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n);
+/* pairs(localpart(v)) in unspecified order; n_out = length */
+int rimu_vec_download(rimu_vec *v, uint64_t *keys_out, void *vals_out, int64_t cap, int64_t *n_out);
+int rimu_vec_copy(rimu_vec *dst, rimu_vec *src);           /* copy!/copyto! */
+/* raw copyto! of n distinct non-zero pairs (e.g. a previous download); no deduplication */
+int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n);
+int rimu_vec_get(rimu_vec *v, const uint64_t *key, void *val_out); /* getindex, 0 if absent */
+/* norm(v, p) p in {1, 2, inf(0)} (abstractdvec.jl:200-256); walkernumber = p=1; global with comm */
+int rimu_vec_norm(rimu_vec *v, int p, double *out);
+int rimu_vec_scale(rimu_vec *v, double alpha);             /* scale!/lmul! (pdvec.jl:714-729) */
+/* dot(x, y) (pdvec.jl:760-796); also serves FrozenDVec dot for projected energy */
+int rimu_vec_dot(rimu_vec *x, rimu_vec *y, double *out);
+/* out = alpha*x + beta*y (add!/axpy!/axpby!, pdvec.jl:731-758); out may alias x or y */
+int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *y, rimu_vec *out);
+
+/* annihilation of a given spawn list (the "sum by key, drop zeros" core of
+ * collect_local!/move_and_compress!, pdworkingmemory.jl:228-273).
+ * method: RIMU_ANNIHILATE_HASH (open-addressing HBM table) or RIMU_ANNIHILATE_SORT
+ * (radix sort + segmented reduce; deterministic summation order). Host arrays in. */
+int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *vals, int64_t n, int method);
+/* same with the spawn list already resident in HBM (device pointers), for measurement */
+int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, const void *d_vals, int64_t n, int method,
+                           float *ms_out);
+
+/* ---- the step ------------------------------------------------------------ */
+int rimu_step(rimu_ctx *ctx, const rimu_ham *ham, const rimu_step_params *params,
+              rimu_vec *src, rimu_vec *dst, rimu_step_stats *stats_out);
+
+/* per-step Philox key derivation, exported so hosts/oracles can reproduce streams */
+void rimu_step_key(uint64_t seed, uint64_t step, uint32_t key_out[2]);
+void rimu_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIMU_B200_H */

@@ -1,0 +1,27 @@
+"""rimu.jl_b200 -- B200-native FCIQMC step behind the Rimu.jl API.
+
+Python host mirror of the reference's operator/vector interface for the hot path
+(ProjectorMonteCarloProblem/solve, the Hamiltonian interface, Fock addresses, DVec/PDVec and the
+StochasticStyles) over a C-ABI CUDA library (include/rimu_b200.h).  Import as `rimu_b200`
+(root shim) -- the directory name contains a dot and cannot be imported directly.
+"""
+from . import _lib
+from ._lib import RimuB200Error, build
+from .addresses import (AddressType, BoseFS, CompositeFS, FermiFS, FermiFS2C, near_uniform, near_uniform_onr,
+                        num_modes, num_particles, onr)
+from .hamiltonians import (AbstractHamiltonian, Context, CubicGrid, HardwallBoundaries, HubbardMom1D, HubbardReal1D,
+                           HubbardRealSpace, LadderBoundaries, PeriodicBoundaries, Transcorrelated1D,
+                           continuum_dispersion, diagonal_element, dimension, get_context, get_offdiagonal,
+                           hubbard_dispersion, num_offdiagonals, offdiagonals, random_offdiagonal, reset_contexts,
+                           starting_address)
+from .stochasticstyles import (IsDeterministic, IsDynamicSemistochastic, IsStochasticInteger,
+                               IsStochasticWithThreshold, NoCompression, StochasticStyle, ThresholdCompression,
+                               default_style, step_stats)
+from .dictvectors import (DVec, FirstOrderTransitionOperator, GPUDVec, PDVec, WorkingMemory, apply_operator, dot, mul,
+                          walkernumber_and_length, working_memory)
+from .fciqmc import (DataFrame, DontUpdate, DoubleLogUpdate, DoubleLogUpdateAfterTargetWalkers, LogUpdate,
+                     PMCSimulation, ProjectedEnergy, Projector, ProjectorMonteCarloProblem, ShiftParameters,
+                     SingleState, Timer, default_starting_vector, init, solve, solve_, step_)
+from .statstools import blocking_analysis, projected_energy, ratio_of_means, shift_estimator
+from .lanczos import eigsolve_lanczos
+from .distributed import init_distributed

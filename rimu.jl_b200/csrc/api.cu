@@ -1,0 +1,877 @@
+// api.cu -- C ABI (include/rimu_b200.h) over the kernels in kernels.cuh.
+// Host-side orchestration of one FCIQMC step = apply_operator! (pdworkingmemory.jl:297-309):
+//   perform_spawns!  -> diag_count_kernel + scan_blocks_kernel + spawn_kernel
+//   collect_local!   -> implicit (all deposits accumulate in the one working table)
+//   synchronize_remote! -> count all-gather + grouped ncclSend/ncclRecv + insert_records_kernel
+//   move_and_compress!  -> compact_kernel (also walkernumber_and_length)
+#include "../../include/rimu_b200.h"
+#include "kernels.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RIMU_ERR_NO_DEVICE : RIMU_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+    } while (0)
+#define TRY(x)              \
+    do {                    \
+        int r_ = (x);       \
+        if (r_ != 0) return r_; \
+    } while (0)
+
+extern "C" const char *rimu_last_error(void) { return g_err.c_str(); }
+extern "C" int rimu_version(void) { return 100; }
+
+// ---------------------------------------------------------------- NCCL (resolved lazily; same soname as torch's bundled copy)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclInt64 = 4, ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMax = 2 };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *);
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    const char *(*GetErrorString)(int);
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(RIMU_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                   \
+    *(void **)(&g_nccl.field) = dlsym(lib, name);                                          \
+    if (!g_nccl.field) return fail(RIMU_ERR_NCCL, "libnccl lacks symbol %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllGather, "ncclAllGather"); SYM(AllReduce, "ncclAllReduce"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = lib;
+    return 0;
+}
+#define NCCL_TRY(x)                                                                              \
+    do {                                                                                         \
+        int e_ = (x);                                                                            \
+        if (e_ != 0) return fail(RIMU_ERR_NCCL, "%s failed: %s", #x, g_nccl.GetErrorString(e_)); \
+    } while (0)
+
+// ---------------------------------------------------------------- handles
+struct rimu_ctx {
+    int device, W, sm_count;
+    cudaStream_t stream;
+    u64 *table;
+    u64 table_slots; // capacity (power of two)
+    StatsDev *d_stats, *h_stats, *h_stats_local;
+    u64 *local_off, *block_tot, *block_base;
+    u64 scratch_parents;
+    cudaEvent_t ev[4];
+    // staging for host <-> device transfers
+    u64 *stage_keys; void *stage_vals; u64 stage_cap;
+    // comm
+    ncclComm_t comm;
+    int rank, nranks;
+    ExchangeDev xch;
+    u64 *recv_keys, *recv_vals, recv_cap;
+    u64 *d_allcounts, *h_allcounts;
+    double *d_reduce;
+};
+struct rimu_ham {
+    rimu_ham_desc desc;
+    int hk, W, device;
+    HamDev dev;
+    double *d_tables;
+    unsigned char *d_nbr;
+};
+struct rimu_vec {
+    rimu_ctx *ctx;
+    int vt;
+    u64 cap;
+    i64 n;
+    u64 *keys;
+    void *vals;
+};
+
+static u64 next_pow2(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
+static int grid_for(i64 n, int sm_count, int per_sm = 8) {
+    i64 g = (n + RIMU_TPB - 1) / RIMU_TPB;
+    i64 cap = (i64)sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------- context
+static int table_fill(rimu_ctx *c, u64 slots) {
+    table_fill_empty_kernel<<<grid_for((i64)slots, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(c->table, slots, c->W);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu_ctx **out) {
+    if (!out || (words != 1 && words != 2)) return fail(RIMU_ERR_INVALID, "rimu_ctx_create: words must be 1 or 2");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(RIMU_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(RIMU_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    rimu_ctx *c = new rimu_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device; c->W = words; c->nranks = 1; c->rank = 0;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->table_slots = next_pow2(table_slots < 1024 ? 1024 : table_slots);
+    CUDA_TRY(cudaMalloc(&c->table, c->table_slots * (words == 1 ? 16 : 32)));
+    CUDA_TRY(cudaMalloc(&c->d_stats, sizeof(StatsDev)));
+    CUDA_TRY(cudaMallocHost(&c->h_stats, sizeof(StatsDev)));
+    CUDA_TRY(cudaMallocHost(&c->h_stats_local, sizeof(StatsDev)));
+    CUDA_TRY(cudaMalloc(&c->d_reduce, 64 * sizeof(double)));
+    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+    TRY(table_fill(c, c->table_slots));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.lib) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->table); cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFreeHost(c->h_stats_local);
+    cudaFree(c->local_off); cudaFree(c->block_tot); cudaFree(c->block_base);
+    cudaFree(c->stage_keys); cudaFree(c->stage_vals);
+    cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->xch.counts);
+    cudaFree(c->recv_keys); cudaFree(c->recv_vals); cudaFree(c->d_allcounts); cudaFreeHost(c->h_allcounts);
+    cudaFree(c->d_reduce);
+    for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+extern "C" int rimu_ctx_synchronize(rimu_ctx *c) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
+extern "C" int rimu_ctx_table_slots(rimu_ctx *c, uint64_t *out) { *out = c->table_slots; return 0; }
+extern "C" int rimu_ctx_stream(rimu_ctx *c, void **s) { *s = (void *)c->stream; return 0; }
+extern "C" int rimu_ctx_resize_table(rimu_ctx *c, uint64_t table_slots) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    u64 slots = next_pow2(table_slots < 1024 ? 1024 : table_slots);
+    if (slots == c->table_slots) return 0;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->table);
+    c->table = nullptr; c->table_slots = 0;
+    CUDA_TRY(cudaMalloc(&c->table, slots * (c->W == 1 ? 16 : 32)));
+    c->table_slots = slots;
+    TRY(table_fill(c, slots));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int ensure_scratch(rimu_ctx *c, u64 parents) {
+    if (parents <= c->scratch_parents) return 0;
+    u64 cap = parents + parents / 4 + 1024;
+    cudaFree(c->local_off); cudaFree(c->block_tot); cudaFree(c->block_base);
+    c->local_off = c->block_tot = c->block_base = nullptr; c->scratch_parents = 0;
+    u64 nblk = (cap + RIMU_TPB - 1) / RIMU_TPB;
+    CUDA_TRY(cudaMalloc(&c->local_off, cap * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->block_tot, nblk * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->block_base, (nblk + 1) * sizeof(u64)));
+    c->scratch_parents = cap;
+    return 0;
+}
+static int ensure_stage(rimu_ctx *c, u64 n) {
+    if (n <= c->stage_cap) return 0;
+    u64 cap = n + n / 4 + 1024;
+    cudaFree(c->stage_keys); cudaFree(c->stage_vals);
+    c->stage_keys = nullptr; c->stage_vals = nullptr; c->stage_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->stage_keys, cap * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->stage_vals, cap * sizeof(u64)));
+    c->stage_cap = cap;
+    return 0;
+}
+
+// ---------------------------------------------------------------- communicator
+extern "C" int rimu_comm_unique_id(void *id128) {
+    TRY(nccl_load());
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return 0;
+}
+extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nranks, uint64_t per_peer) {
+    if (nranks < 1 || nranks > RIMU_MAX_RANKS || rank < 0 || rank >= nranks) return fail(RIMU_ERR_INVALID, "bad rank/nranks");
+    if (c->comm) return fail(RIMU_ERR_INVALID, "communicator already attached");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->rank = rank; c->nranks = nranks;
+    if (nranks == 1) return 0;
+    TRY(nccl_load());
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    if (per_peer < 1024) per_peer = 1024;
+    c->xch.cap = per_peer;
+    CUDA_TRY(cudaMalloc(&c->xch.keys, (u64)nranks * per_peer * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->xch.vals, (u64)nranks * per_peer * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->xch.counts, RIMU_MAX_RANKS * sizeof(u64)));
+    CUDA_TRY(cudaMemset(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64)));
+    c->recv_cap = (u64)nranks * per_peer;
+    CUDA_TRY(cudaMalloc(&c->recv_keys, c->recv_cap * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->recv_vals, c->recv_cap * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->d_allcounts, (u64)nranks * nranks * sizeof(u64)));
+    CUDA_TRY(cudaMallocHost(&c->h_allcounts, (u64)nranks * nranks * sizeof(u64)));
+    return 0;
+}
+extern "C" int rimu_comm_rank(rimu_ctx *c, int *rank, int *nranks) { *rank = c->rank; *nranks = c->nranks; return 0; }
+extern "C" int rimu_comm_allreduce_f64(rimu_ctx *c, double *buf, int n) {
+    if (c->nranks == 1) return 0;
+    if (n > 64) return fail(RIMU_ERR_INVALID, "allreduce of at most 64 doubles");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->d_reduce, buf, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(c->d_reduce, c->d_reduce, n, ncclFloat64, ncclSum, c->comm, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(buf, c->d_reduce, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" uint64_t rimu_addr_hash(const uint64_t *key, int words) {
+    return words == 1 ? addr_hash<1>((const u64 *)key) : addr_hash<2>((const u64 *)key);
+}
+extern "C" int rimu_addr_owner(const uint64_t *key, int words, int nranks) {
+    return addr_owner(rimu_addr_hash(key, words), nranks);
+}
+extern "C" void rimu_step_key(uint64_t seed, uint64_t step, uint32_t key_out[2]) {
+    u64 k = splitmix64(seed ^ splitmix64(step));
+    key_out[0] = (u32)k; key_out[1] = (u32)(k >> 32);
+}
+extern "C" void rimu_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    philox4x32_10(ctr, key[0], key[1], out);
+}
+
+// ---------------------------------------------------------------- Hamiltonian
+static int neighbor_site_host(const rimu_ham_desc *d, int mode, int chosen) { // geometry.jl:161-175,232-235
+    int D = d->ndim, idx = mode - 1, x[3];
+    for (int k = 0; k < D; k++) { x[k] = idx % d->dims[k] + 1; idx /= d->dims[k]; }
+    if (chosen <= D) x[chosen - 1] += 1; else x[chosen - D - 1] -= 1;
+    for (int k = 0; k < D; k++) {
+        if (d->fold[k]) { x[k] = ((x[k] - 1) % d->dims[k] + d->dims[k]) % d->dims[k] + 1; }
+        else if (x[k] < 1 || x[k] > d->dims[k]) return 0;
+    }
+    int lin = 0, stride = 1;
+    for (int k = 0; k < D; k++) { lin += (x[k] - 1) * stride; stride *= d->dims[k]; }
+    return lin + 1;
+}
+
+extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
+    if (!d || !out) return fail(RIMU_ERR_INVALID, "null argument");
+    const int M = d->num_modes, kind = d->addr_kind, model = d->model;
+    if (M < 1 || M > RIMU_MAX_MODES) return fail(RIMU_ERR_INVALID, "num_modes %d unsupported (1..%d)", M, RIMU_MAX_MODES);
+    int hk = -1, bits = 0;
+    if (kind == RIMU_ADDR_BOSE) {
+        if (d->num_components != 1) return fail(RIMU_ERR_INVALID, "BoseFS must have one component");
+        bits = d->num_particles[0] + M - 1;
+        if (bits + 1 > 128) return fail(RIMU_ERR_INVALID, "BoseFS{%d,%d} needs %d bits; at most 127 supported", d->num_particles[0], M, bits);
+        if (model == RIMU_HUBBARD_REAL_1D) hk = HK_REAL1D_BOSE;
+        else if (model == RIMU_HUBBARD_MOM_1D) hk = HK_MOM1D_BOSE;
+        else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_BOSE;
+    } else if (kind == RIMU_ADDR_FERMI) {
+        if (d->num_components != 1) return fail(RIMU_ERR_INVALID, "FermiFS must have one component");
+        bits = M;
+        if (M > 63) return fail(RIMU_ERR_INVALID, "FermiFS with more than 63 modes unsupported");
+        if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_FERMI;
+    } else if (kind == RIMU_ADDR_FERMI2C) {
+        if (d->num_components != 2) return fail(RIMU_ERR_INVALID, "FermiFS2C must have two components");
+        bits = 2 * M;
+        if (M > 32) return fail(RIMU_ERR_INVALID, "two-component fermions with more than 32 modes unsupported");
+        if (d->num_particles[0] == M && d->num_particles[1] == M && M == 32)
+            return fail(RIMU_ERR_INVALID, "completely filled 32-mode two-component address collides with the empty-slot sentinel");
+        if (model == RIMU_HUBBARD_MOM_1D) hk = HK_MOM1D_F2C;
+        else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_F2C;
+        else if (model == RIMU_TRANSCORRELATED_1D) hk = HK_TC_F2C;
+    }
+    if (hk < 0)
+        return fail(RIMU_ERR_INVALID, "model %d is not implemented for address kind %d (no CPU fallback exists)", model, kind);
+    if ((hk == HK_MOM1D_BOSE || hk == HK_MOM1D_F2C || hk == HK_TC_F2C) && M > RIMU_MAX_TABLE_MODES)
+        return fail(RIMU_ERR_INVALID, "momentum-space models support at most %d modes", RIMU_MAX_TABLE_MODES);
+    if (hk == HK_MOM1D_BOSE && M < 3) return fail(RIMU_ERR_INVALID, "HubbardMom1D needs at least 3 modes");
+    rimu_ham *h = new rimu_ham();
+    memset(h, 0, sizeof(*h));
+    h->desc = *d; h->hk = hk;
+    h->W = (kind == RIMU_ADDR_BOSE) ? ((bits + 1 + 63) / 64) : 1;
+    CUDA_TRY(cudaGetDevice(&h->device));
+    HamDev &v = h->dev;
+    v.hk = hk; v.M = M; v.N0 = d->num_particles[0]; v.N1 = d->num_particles[1];
+    v.ndim = d->ndim; v.nnb = 2 * d->ndim; v.cutoff = d->cutoff; v.three_body = d->three_body_term; v.has_pot = d->has_potential;
+    v.u = d->u; v.t = d->t; v.v = d->v; v.tc0 = d->t_comp[0]; v.tc1 = d->t_comp[1];
+    v.u00 = d->u_mat[0]; v.u10 = d->u_mat[1];
+    int nz = 0;
+    for (int i = 0; i < d->num_components * d->num_components; i++) nz += d->u_mat[(i % d->num_components) + 2 * (i / d->num_components)] != 0.0;
+    v.umat_zero = nz == 0;
+    // device tables: kes | ws | us | pot
+    std::vector<double> tab(3 * RIMU_MAX_TABLE_MODES + 2 * RIMU_MAX_MODES);
+    memcpy(&tab[0], d->kes, sizeof(d->kes));
+    memcpy(&tab[RIMU_MAX_TABLE_MODES], d->ws, sizeof(d->ws));
+    memcpy(&tab[2 * RIMU_MAX_TABLE_MODES], d->us, sizeof(d->us));
+    memcpy(&tab[3 * RIMU_MAX_TABLE_MODES], d->potential, sizeof(d->potential));
+    CUDA_TRY(cudaMalloc(&h->d_tables, tab.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    v.kes = h->d_tables; v.ws = h->d_tables + RIMU_MAX_TABLE_MODES; v.us = h->d_tables + 2 * RIMU_MAX_TABLE_MODES;
+    v.pot = h->d_tables + 3 * RIMU_MAX_TABLE_MODES;
+    if (model == RIMU_HUBBARD_REAL_SPACE) {
+        if (d->ndim < 1 || d->ndim > 3) { delete h; return fail(RIMU_ERR_INVALID, "geometry must have 1..3 dimensions"); }
+        int prod = 1;
+        for (int k = 0; k < d->ndim; k++) prod *= d->dims[k];
+        if (prod != M) { delete h; return fail(RIMU_ERR_INVALID, "`geometry` does not have the correct number of sites"); }
+        std::vector<unsigned char> nbr((size_t)M * v.nnb);
+        for (int s = 1; s <= M; s++)
+            for (int c = 1; c <= v.nnb; c++) nbr[(size_t)(s - 1) * v.nnb + (c - 1)] = (unsigned char)neighbor_site_host(d, s, c);
+        CUDA_TRY(cudaMalloc(&h->d_nbr, nbr.size()));
+        CUDA_TRY(cudaMemcpy(h->d_nbr, nbr.data(), nbr.size(), cudaMemcpyHostToDevice));
+        v.nbr = h->d_nbr;
+    }
+    *out = h;
+    return 0;
+}
+extern "C" int rimu_ham_destroy(rimu_ham *h) {
+    if (!h) return 0;
+    cudaFree(h->d_tables); cudaFree(h->d_nbr);
+    delete h;
+    return 0;
+}
+extern "C" int rimu_ham_words(const rimu_ham *h) { return h->W; }
+
+// compile-time dispatch over (HamKind, W)
+template <int HK, int W> struct HkTag { static constexpr int hk = HK; static constexpr int w = W; };
+template <class F> static int dispatch_ham(const rimu_ham *h, F &&f) {
+    switch (h->hk) {
+    case HK_REAL1D_BOSE: return h->W == 1 ? f(HkTag<HK_REAL1D_BOSE, 1>()) : f(HkTag<HK_REAL1D_BOSE, 2>());
+    case HK_MOM1D_BOSE: return h->W == 1 ? f(HkTag<HK_MOM1D_BOSE, 1>()) : f(HkTag<HK_MOM1D_BOSE, 2>());
+    case HK_MOM1D_F2C: return f(HkTag<HK_MOM1D_F2C, 1>());
+    case HK_RS_BOSE: return h->W == 1 ? f(HkTag<HK_RS_BOSE, 1>()) : f(HkTag<HK_RS_BOSE, 2>());
+    case HK_RS_FERMI: return f(HkTag<HK_RS_FERMI, 1>());
+    case HK_RS_F2C: return f(HkTag<HK_RS_F2C, 1>());
+    case HK_TC_F2C: return f(HkTag<HK_TC_F2C, 1>());
+    }
+    return fail(RIMU_ERR_INVALID, "unknown Hamiltonian kind");
+}
+
+static int check_ctx_ham(rimu_ctx *c, const rimu_ham *h) {
+    if (!c || !h) return fail(RIMU_ERR_INVALID, "null handle");
+    if (c->W != h->W) return fail(RIMU_ERR_INVALID, "context built for %d-word addresses, Hamiltonian needs %d", c->W, h->W);
+    if (c->device != h->device) return fail(RIMU_ERR_INVALID, "Hamiltonian tables live on device %d, context on %d", h->device, c->device);
+    CUDA_TRY(cudaSetDevice(c->device));
+    return 0;
+}
+
+extern "C" int rimu_ham_diagonal(rimu_ctx *c, const rimu_ham *h, const uint64_t *keys, int64_t n, double *out) {
+    TRY(check_ctx_ham(c, h));
+    if (n <= 0) return 0;
+    TRY(ensure_stage(c, (u64)n));
+    CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    double *d_out = (double *)c->stage_vals;
+    TRY(dispatch_ham(h, [&](auto tag) {
+        ham_diag_kernel<decltype(tag)::hk, decltype(tag)::w><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(h->dev, c->stage_keys, n, d_out, nullptr);
+        return 0;
+    }));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int rimu_ham_num_offdiagonals(rimu_ctx *c, const rimu_ham *h, const uint64_t *keys, int64_t n, int64_t *out) {
+    TRY(check_ctx_ham(c, h));
+    if (n <= 0) return 0;
+    TRY(ensure_stage(c, (u64)n));
+    CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    i64 *d_out = (i64 *)c->stage_vals;
+    TRY(dispatch_ham(h, [&](auto tag) {
+        ham_diag_kernel<decltype(tag)::hk, decltype(tag)::w><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(h->dev, c->stage_keys, n, nullptr, d_out);
+        return 0;
+    }));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, n * sizeof(i64), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int rimu_ham_offdiagonals(rimu_ctx *c, const rimu_ham *h, const uint64_t *key, int64_t first, int64_t count,
+                                     uint64_t *keys_out, double *vals_out) {
+    TRY(check_ctx_ham(c, h));
+    if (count <= 0) return 0;
+    if (first < 1) return fail(RIMU_ERR_INVALID, "off-diagonal indices are 1-based");
+    TRY(ensure_stage(c, (u64)count + 1));
+    u64 *d_key = c->stage_keys + (u64)count * c->W;
+    CUDA_TRY(cudaMemcpyAsync(d_key, key, c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    double *d_vals = (double *)c->stage_vals;
+    TRY(dispatch_ham(h, [&](auto tag) {
+        ham_offdiag_kernel<decltype(tag)::hk, decltype(tag)::w><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(
+            h->dev, d_key, first - 1, count, c->stage_keys, d_vals);
+        return 0;
+    }));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(keys_out, c->stage_keys, count * c->W * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(vals_out, d_vals, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------- vectors
+extern "C" int rimu_vec_create(rimu_ctx *c, int val_type, uint64_t capacity, rimu_vec **out) {
+    if (!c || !out) return fail(RIMU_ERR_INVALID, "null argument");
+    if (val_type != RIMU_VAL_F64 && val_type != RIMU_VAL_I64) return fail(RIMU_ERR_INVALID, "bad value type");
+    CUDA_TRY(cudaSetDevice(c->device));
+    rimu_vec *v = new rimu_vec();
+    v->ctx = c; v->vt = val_type; v->n = 0; v->cap = capacity < 256 ? 256 : capacity;
+    v->keys = nullptr; v->vals = nullptr;
+    CUDA_TRY(cudaMalloc(&v->keys, v->cap * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&v->vals, v->cap * sizeof(u64)));
+    *out = v;
+    return 0;
+}
+extern "C" int rimu_vec_destroy(rimu_vec *v) {
+    if (!v) return 0;
+    cudaSetDevice(v->ctx->device);
+    cudaStreamSynchronize(v->ctx->stream);
+    cudaFree(v->keys); cudaFree(v->vals);
+    delete v;
+    return 0;
+}
+extern "C" int rimu_vec_reserve(rimu_vec *v, uint64_t capacity) {
+    if (capacity <= v->cap) return 0;
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    u64 *nk = nullptr; void *nv = nullptr;
+    CUDA_TRY(cudaMalloc(&nk, capacity * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&nv, capacity * sizeof(u64)));
+    if (v->n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(nk, v->keys, v->n * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(nv, v->vals, v->n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(v->keys); cudaFree(v->vals);
+    v->keys = nk; v->vals = nv; v->cap = capacity;
+    return 0;
+}
+extern "C" int rimu_vec_clear(rimu_vec *v) { v->n = 0; return 0; }
+extern "C" int rimu_vec_length(rimu_vec *v, int64_t *out) { *out = v->n; return 0; }
+extern "C" int rimu_vec_capacity(rimu_vec *v, uint64_t *out) { *out = v->cap; return 0; }
+
+static StepDev null_step(rimu_ctx *c) {
+    StepDev p;
+    memset(&p, 0, sizeof(p));
+    p.rank = c->rank; p.nranks = c->nranks;
+    return p;
+}
+
+// drain the working table into dst (no compression); returns RIMU_ERR_VECTOR_FULL after growing is impossible
+template <int W, class VT> static int compact_into(rimu_ctx *c, rimu_vec *dst, u64 slots, const StepDev &p) {
+    TableDev tab{c->table, slots - 1};
+    compact_kernel<W, VT><<<grid_for((i64)slots, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
+        tab, p, dst->keys, (VT *)dst->vals, dst->cap, c->d_stats);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <class F> static int dispatch_wv(int W, int vt, F &&f) {
+    if (W == 1) return vt == RIMU_VAL_F64 ? f(HkTag<0, 1>(), double()) : f(HkTag<0, 1>(), i64());
+    return vt == RIMU_VAL_F64 ? f(HkTag<0, 2>(), double()) : f(HkTag<0, 2>(), i64());
+}
+
+static u64 pick_slots(rimu_ctx *c, u64 expected_entries) {
+    u64 s = next_pow2(expected_entries * 2 + 1024);
+    if (s > c->table_slots) s = c->table_slots;
+    return s;
+}
+
+// build dst from device-resident records (sum by key, drop zeros) via the working table.
+// Retries with more slots on table overflow; grows dst when needed.
+static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
+                          const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    u64 slots = pick_slots(c, (u64)(n + n2));
+    for (;;) {
+        CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
+        TableDev tab{c->table, slots - 1};
+        TRY(dispatch_wv(c->W, dst->vt, [&](auto tag, auto vtag) {
+            typedef decltype(vtag) VT;
+            constexpr int W = decltype(tag)::w;
+            if (n > 0)
+                insert_records_kernel<W, VT><<<grid_for(n, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                    d_keys, (const VT *)d_vals, n, a1, use_scale, c->rank, c->nranks, tab, c->d_stats);
+            if (n2 > 0)
+                insert_records_kernel<W, VT><<<grid_for(n2, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                    d_keys2, (const VT *)d_vals2, n2, a2, use_scale, c->rank, c->nranks, tab, c->d_stats);
+            return compact_into<W, VT>(c, dst, slots, null_step(c));
+        }));
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (c->h_stats->overflow_table) {
+            if (slots >= c->table_slots)
+                return fail(RIMU_ERR_TABLE_FULL, "working table (%llu slots) too small for %lld records", (unsigned long long)c->table_slots, (long long)(n + n2));
+            slots = slots * 4 > c->table_slots ? c->table_slots : slots * 4;
+            continue;
+        }
+        if (c->h_stats->out_count > dst->cap) {
+            // the table has been drained; grow and redo (inputs are untouched unless dst aliases them)
+            if ((const u64 *)dst->keys == d_keys || (const u64 *)dst->keys == d_keys2)
+                return fail(RIMU_ERR_VECTOR_FULL, "destination (aliasing an input) too small: need %llu", (unsigned long long)c->h_stats->out_count);
+            dst->n = 0;
+            TRY(rimu_vec_reserve(dst, c->h_stats->out_count + c->h_stats->out_count / 4));
+            continue;
+        }
+        dst->n = (i64)c->h_stats->out_count;
+        return 0;
+    }
+}
+
+extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n <= 0) { v->n = 0; return 0; }
+    TRY(ensure_stage(c, (u64)n));
+    CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->stage_vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    return records_to_vec(c, v, c->stage_keys, c->stage_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0);
+}
+extern "C" int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n < 0) return fail(RIMU_ERR_INVALID, "negative length");
+    if ((u64)n > v->cap) { v->n = 0; TRY(rimu_vec_reserve(v, (u64)n)); }
+    if (n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(v->keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(v->vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    }
+    v->n = n;
+    return 0;
+}
+extern "C" int rimu_vec_download(rimu_vec *v, uint64_t *keys_out, void *vals_out, int64_t cap, int64_t *n_out) {
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_out) *n_out = v->n;
+    if (cap < v->n) return fail(RIMU_ERR_VECTOR_FULL, "download buffer too small: need %lld", (long long)v->n);
+    if (v->n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(keys_out, v->keys, v->n * c->W * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(vals_out, v->vals, v->n * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int rimu_vec_copy(rimu_vec *dst, rimu_vec *src) {
+    if (dst == src) return 0;
+    rimu_ctx *c = src->ctx;
+    if (dst->ctx != c) return fail(RIMU_ERR_INVALID, "copy between vectors of different contexts");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if ((u64)src->n > dst->cap) { dst->n = 0; TRY(rimu_vec_reserve(dst, (u64)src->n)); }
+    if (src->n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(dst->keys, src->keys, src->n * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        if (dst->vt == src->vt) {
+            CUDA_TRY(cudaMemcpyAsync(dst->vals, src->vals, src->n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        } else { // eltype conversion Int64 <-> Float64 on the device
+            if (src->vt == RIMU_VAL_I64) convert_vals_kernel<i64, double><<<grid_for(src->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const i64 *)src->vals, (double *)dst->vals, src->n);
+            else convert_vals_kernel<double, i64><<<grid_for(src->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const double *)src->vals, (i64 *)dst->vals, src->n);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    dst->n = src->n;
+    return 0;
+}
+extern "C" int rimu_vec_get(rimu_vec *v, const uint64_t *key, void *val_out) {
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    u64 *d_out = (u64 *)c->d_reduce;
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(u64), c->stream));
+    if (v->n > 0) {
+        TRY(dispatch_wv(c->W, v->vt, [&](auto tag, auto vtag) {
+            typedef decltype(vtag) VT;
+            find_key_kernel<decltype(tag)::w, VT><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                v->keys, (const VT *)v->vals, v->n, key[0], c->W == 2 ? key[1] : 0, (VT *)d_out);
+            return 0;
+        }));
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(val_out, d_out, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int rimu_vec_norm(rimu_vec *v, int p, double *out) {
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
+    if (v->n > 0) {
+        if (v->vt == RIMU_VAL_F64) norm_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const double *)v->vals, v->n, c->d_stats);
+        else norm_kernel<i64><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const i64 *)v->vals, v->n, c->d_stats);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double r[2] = {c->h_stats->norm1, c->h_stats->norm2};
+    if (c->nranks > 1) {
+        TRY(rimu_comm_allreduce_f64(c, r, 2));
+        if (p == 0) { // max over ranks through NCCL
+            CUDA_TRY(cudaMemcpyAsync(c->d_reduce, &c->h_stats->norminf, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            NCCL_TRY(g_nccl.AllReduce(c->d_reduce, c->d_reduce, 1, ncclFloat64, ncclMax, c->comm, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(&c->h_stats->norminf, c->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+    }
+    if (p == 1) *out = r[0];
+    else if (p == 2) *out = sqrt(r[1]);
+    else if (p == 0) *out = c->h_stats->norminf;
+    else return fail(RIMU_ERR_INVALID, "norm p must be 1, 2 or 0 (=inf)");
+    return 0;
+}
+extern "C" int rimu_vec_scale(rimu_vec *v, double alpha) {
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (alpha == 0.0) { v->n = 0; return 0; } // zero values are never stored
+    if (v->n > 0) {
+        if (v->vt == RIMU_VAL_F64) scale_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((double *)v->vals, v->n, alpha);
+        else scale_kernel<i64><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((i64 *)v->vals, v->n, alpha);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+extern "C" int rimu_vec_dot(rimu_vec *x, rimu_vec *y, double *out) {
+    rimu_ctx *c = x->ctx;
+    if (y->ctx != c || x->vt != y->vt) return fail(RIMU_ERR_INVALID, "dot of incompatible vectors");
+    CUDA_TRY(cudaSetDevice(c->device));
+    rimu_vec *build = x->n <= y->n ? x : y, *probe = x->n <= y->n ? y : x; // table from the shorter one
+    double r = 0.0;
+    if (build->n > 0) {
+        u64 slots = pick_slots(c, (u64)build->n);
+        for (;;) {
+            CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
+            TableDev tab{c->table, slots - 1};
+            TRY(dispatch_wv(c->W, x->vt, [&](auto tag, auto vtag) {
+                typedef decltype(vtag) VT;
+                constexpr int W = decltype(tag)::w;
+                insert_records_kernel<W, VT><<<grid_for(build->n, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                    build->keys, (const VT *)build->vals, build->n, 1.0, 0, 0, 1, tab, c->d_stats);
+                lookup_dot_kernel<W, VT><<<grid_for(probe->n, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                    probe->keys, (const VT *)probe->vals, probe->n, tab, c->d_stats);
+                return 0;
+            }));
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+            // re-empty the table (only the active prefix was touched)
+            TRY(table_fill(c, slots));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            if (c->h_stats->overflow_table) {
+                if (slots >= c->table_slots) return fail(RIMU_ERR_TABLE_FULL, "working table too small for dot");
+                slots = slots * 4 > c->table_slots ? c->table_slots : slots * 4;
+                continue;
+            }
+            r = c->h_stats->dot;
+            break;
+        }
+    }
+    if (c->nranks > 1) TRY(rimu_comm_allreduce_f64(c, &r, 1));
+    *out = r;
+    return 0;
+}
+extern "C" int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *y, rimu_vec *out) {
+    rimu_ctx *c = out->ctx;
+    if (x->ctx != c || y->ctx != c || x->vt != out->vt || y->vt != out->vt) return fail(RIMU_ERR_INVALID, "axpby of incompatible vectors");
+    if (x->n + y->n > 0 && (u64)(x->n + y->n) > out->cap && (out == x || out == y)) TRY(rimu_vec_reserve(out, (u64)(x->n + y->n)));
+    return records_to_vec(c, out, x->keys, x->vals, x->n, y->keys, y->vals, y->n, alpha, beta, 1);
+}
+
+extern "C" int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, const void *d_vals, int64_t n, int method, float *ms_out) {
+    rimu_ctx *c = dst->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (method != RIMU_ANNIHILATE_HASH) return fail(RIMU_ERR_INVALID, "annihilation method %d not available", method);
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    TRY(records_to_vec(c, dst, (const u64 *)d_keys, d_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0));
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev[1]));
+    if (ms_out) CUDA_TRY(cudaEventElapsedTime(ms_out, c->ev[0], c->ev[1]));
+    return 0;
+}
+extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *vals, int64_t n, int method) {
+    rimu_ctx *c = dst->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n <= 0) { dst->n = 0; return 0; }
+    TRY(ensure_stage(c, (u64)n));
+    CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->stage_vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    return rimu_annihilate_device(dst, (const uint64_t *)c->stage_keys, c->stage_vals, n, method, nullptr);
+}
+
+// ---------------------------------------------------------------- the step
+static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out) {
+    const int R = c->nranks, me = c->rank;
+    NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_allcounts, c->d_allcounts, (size_t)R * R * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    u64 worst = 0, total_recv = 0, sent = 0;
+    for (int s = 0; s < R; s++)
+        for (int d = 0; d < R; d++) { u64 n = c->h_allcounts[s * R + d]; if (n > worst) worst = n; }
+    if (worst > c->xch.cap) return RIMU_ERR_EXCHANGE_FULL; // identical decision on every rank
+    for (int s = 0; s < R; s++) if (s != me) total_recv += c->h_allcounts[s * R + me];
+    for (int d = 0; d < R; d++) if (d != me) sent += c->h_allcounts[me * R + d];
+    *sent_out = (i64)sent;
+    NCCL_TRY(g_nccl.GroupStart());
+    u64 off = 0;
+    for (int r = 0; r < R; r++) {
+        if (r == me) continue;
+        u64 ns = c->h_allcounts[me * R + r], nr = c->h_allcounts[r * R + me];
+        if (ns) {
+            NCCL_TRY(g_nccl.Send(c->xch.keys + (u64)r * c->xch.cap * c->W, ns * c->W, ncclUint64, r, c->comm, c->stream));
+            NCCL_TRY(g_nccl.Send(c->xch.vals + (u64)r * c->xch.cap, ns, ncclUint64, r, c->comm, c->stream));
+        }
+        if (nr) {
+            NCCL_TRY(g_nccl.Recv(c->recv_keys + off * c->W, nr * c->W, ncclUint64, r, c->comm, c->stream));
+            NCCL_TRY(g_nccl.Recv(c->recv_vals + off, nr, ncclUint64, r, c->comm, c->stream));
+        }
+        off += nr;
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    if (total_recv) {
+        TableDev tab{c->table, slots - 1};
+        TRY(dispatch_wv(c->W, vt, [&](auto tag, auto vtag) {
+            typedef decltype(vtag) VT;
+            insert_records_kernel<decltype(tag)::w, VT><<<grid_for((i64)total_recv, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, 0, 1, tab, c->d_stats);
+            return 0;
+        }));
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <int HK, int W, class VT>
+static int step_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, u64 slots, i64 *sent) {
+    const i64 n = src->n;
+    TableDev tab{c->table, slots - 1};
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    if (n > 0) {
+        TRY(ensure_scratch(c, (u64)n));
+        const i64 nblk = (n + RIMU_TPB - 1) / RIMU_TPB;
+        diag_count_kernel<HK, W, VT><<<(unsigned)nblk, RIMU_TPB, 0, c->stream>>>(
+            h->dev, p, src->keys, (const VT *)src->vals, n, tab, c->xch, c->local_off, c->block_tot, c->d_stats);
+        scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(c->block_tot, nblk, c->block_base, c->d_stats);
+        spawn_kernel<HK, W, VT><<<c->sm_count * 8, RIMU_TPB, 0, c->stream>>>(
+            h->dev, p, src->keys, (const VT *)src->vals, n, c->block_base, c->local_off, tab, c->xch, c->d_stats);
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    *sent = 0;
+    if (c->nranks > 1) {
+        int r = exchange_spawns(c, dst->vt, slots, sent);
+        if (r) return r;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    TRY((compact_into<W, VT>(c, dst, slots, p)));
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    return 0;
+}
+
+extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params *prm, rimu_vec *src, rimu_vec *dst,
+                         rimu_step_stats *out) {
+    TRY(check_ctx_ham(c, h));
+    if (!prm || !src || !dst) return fail(RIMU_ERR_INVALID, "null argument");
+    if (src == dst) return fail(RIMU_ERR_INVALID, "source and target must not alias (Interfaces/dictvectors.jl:115-117)");
+    if (src->ctx != c || dst->ctx != c) return fail(RIMU_ERR_INVALID, "vectors belong to another context");
+    if (src->vt != dst->vt) return fail(RIMU_ERR_INVALID, "source and target value types differ");
+    const bool is_int = prm->style == RIMU_STYLE_INTEGER;
+    if (is_int != (src->vt == RIMU_VAL_I64))
+        return fail(RIMU_ERR_INVALID, "IsStochasticInteger needs Int64 vectors; the other styles need Float64 vectors");
+    if (prm->style < 0 || prm->style > 3) return fail(RIMU_ERR_INVALID, "unknown stochastic style %d", prm->style);
+    if (is_int && prm->proj_threshold != 0.0) return fail(RIMU_ERR_INVALID, "Thresholding not supported for integer spawns");
+    StepDev p;
+    memset(&p, 0, sizeof(p));
+    p.style = prm->style; p.plain_h = prm->plain_h;
+    p.shift = prm->shift; p.dtau = prm->time_step; p.boost = prm->boost;
+    p.proj_thr = prm->proj_threshold; p.rel_thr = prm->rel_threshold; p.abs_thr = prm->abs_threshold;
+    p.compress_thr = prm->compress_threshold;
+    uint32_t key[2];
+    rimu_step_key(prm->seed, prm->step, key);
+    p.k0 = key[0]; p.k1 = key[1];
+    p.rank = c->rank; p.nranks = c->nranks;
+
+    u64 slots = prm->table_slots ? next_pow2(prm->table_slots) : pick_slots(c, (u64)src->n * 2 + (u64)dst->n);
+    if (slots > c->table_slots) slots = c->table_slots;
+    i64 sent = 0;
+    for (int attempt = 0;; attempt++) {
+        int r = dispatch_ham(h, [&](auto tag) {
+            constexpr int HK = decltype(tag)::hk, W = decltype(tag)::w;
+            if (is_int) return step_once<HK, W, i64>(c, h, p, src, dst, slots, &sent);
+            return step_once<HK, W, double>(c, h, p, src, dst, slots, &sent);
+        });
+        if (r == RIMU_ERR_EXCHANGE_FULL) {
+            // nothing was sent; drain what this rank deposited locally, then report
+            TRY(table_fill(c, slots));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            return fail(RIMU_ERR_EXCHANGE_FULL, "per-peer exchange buffer (%llu records) too small", (unsigned long long)c->xch.cap);
+        }
+        if (r) return r;
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats_local, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+        if (c->nranks > 1) {
+            NCCL_TRY(g_nccl.AllReduce(c->d_stats, c->d_stats, RIMU_STATS_NI64, ncclInt64, ncclSum, c->comm, c->stream));
+            double *dd = (double *)((char *)c->d_stats + RIMU_STATS_NI64 * sizeof(i64));
+            NCCL_TRY(g_nccl.AllReduce(dd, dd, RIMU_STATS_NF64_STEP, ncclFloat64, ncclSum, c->comm, c->stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const StatsDev &g = *c->h_stats, &l = *c->h_stats_local;
+        if (g.overflow_table) { // some rank ran out of probe budget: every rank retries with a larger active table
+            if (slots >= c->table_slots)
+                return fail(RIMU_ERR_TABLE_FULL, "working table (%llu slots) too small for this step", (unsigned long long)c->table_slots);
+            slots = slots * 4 > c->table_slots ? c->table_slots : slots * 4;
+            continue;
+        }
+        // destination capacity: decided globally so that all ranks retry together
+        u64 need_local = l.out_count;
+        double flag = need_local > dst->cap ? 1.0 : 0.0;
+        if (c->nranks > 1) TRY(rimu_comm_allreduce_f64(c, &flag, 1));
+        if (flag > 0.0) {
+            dst->n = 0;
+            if (need_local > dst->cap) TRY(rimu_vec_reserve(dst, need_local + need_local / 4 + 1024));
+            if (attempt > 8) return fail(RIMU_ERR_VECTOR_FULL, "destination vector cannot be grown");
+            continue;
+        }
+        dst->n = (i64)l.out_count;
+        if (out) {
+            memset(out, 0, sizeof(*out));
+            out->exact_steps = g.exact_steps; out->inexact_steps = g.inexact_steps; out->spawn_attempts = g.spawn_attempts;
+            out->len_before = g.len_before; out->len = g.len;
+            out->spawns = g.spawns; out->deaths = g.deaths; out->clones = g.clones; out->zombies = g.zombies; out->norm1 = g.norm1;
+            out->ispawns = g.ispawns; out->ideaths = g.ideaths; out->iclones = g.iclones; out->izombies = g.izombies; out->inorm1 = g.inorm1;
+            out->local_len = (i64)l.out_count; out->sent_records = sent;
+            cudaEventElapsedTime(&out->ms_spawn, c->ev[0], c->ev[1]);
+            cudaEventElapsedTime(&out->ms_exchange, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&out->ms_compact, c->ev[2], c->ev[3]);
+            cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[3]);
+        }
+        return 0;
+    }
+}

@@ -1,0 +1,131 @@
+// common.cuh -- shared device/host primitives: Philox4x32-10, address hashing, bit utilities.
+//
+// RNG design (replaces Julia's task-local Xoshiro256++, pmc_simulation.jl:100-103): every random
+// draw is a pure function of (step key, address hash, attempt index, stream id), so a step's
+// result does not depend on launch geometry or on how determinant space is partitioned over GPUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+typedef unsigned __int128 u128;
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+#else
+#define HD inline
+#define DEV inline
+#endif
+
+HD u32 mulhi32(u32 a, u32 b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * (u64)b) >> 32);
+#endif
+}
+
+HD void philox4x32_10(const u32 ctr[4], u32 k0, u32 k1, u32 out[4]) {
+    u32 c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        u32 hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        u32 hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        u32 n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+HD u64 fmix64(u64 h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 33;
+    return h;
+}
+
+template <int W> HD u64 addr_hash(const u64 *w) {
+    u64 h = 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+    for (int j = 0; j < W; j++) h = fmix64(h ^ w[j]);
+    return h;
+}
+
+// owner rank: fastrange of the high 32 hash bits (reference: fastrange_hash pdvec.jl:6-9,
+// target rank communicators.jl:77-81).  The table slot uses the LOW bits, so the two are independent.
+HD int addr_owner(u64 h, int nranks) { return (int)(((h >> 32) * (u64)nranks) >> 32); }
+
+enum { STREAM_SPAWN = 0, STREAM_DIAG = 1, STREAM_COMPRESS = 2 };
+
+HD double u53(u32 a, u32 b) { return (double)(((u64)a << 21) ^ ((u64)b >> 11)) * (1.0 / 9007199254740992.0); }
+
+HD void rng_draw(u64 h, u64 k, int stream, u32 k0, u32 k1, u32 out[4]) {
+    u32 ctr[4] = {(u32)h, (u32)(h >> 32), (u32)k, ((u32)stream << 28) | (u32)((k >> 32) & 0x0fffffffu)};
+    philox4x32_10(ctr, k0, k1, out);
+}
+
+HD u64 splitmix64(u64 x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    u64 z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// ---------------------------------------------------------------- bit utilities (device)
+#ifdef __CUDACC__
+template <int W> struct BitsT;
+template <> struct BitsT<1> { typedef u64 type; };
+template <> struct BitsT<2> { typedef u128 type; };
+
+DEV int popc_(u64 x) { return __popcll(x); }
+DEV int popc_(u128 x) { return __popcll((u64)x) + __popcll((u64)(x >> 64)); }
+DEV int ctz_(u64 x) { return x ? __ffsll((long long)x) - 1 : 64; }
+DEV int ctz_(u128 x) {
+    u64 lo = (u64)x;
+    if (lo) return __ffsll((long long)lo) - 1;
+    u64 hi = (u64)(x >> 64);
+    return hi ? 64 + __ffsll((long long)hi) - 1 : 128;
+}
+template <class B> DEV int cto_(B x) { return ctz_((B)~x); }
+template <class B> DEV B lowmask(int p) { return (((B)1) << p) - (B)1; }
+
+// position of the k-th (0-based) set bit of a 32-bit word; requires popc(x) > k
+DEV int select32(u32 x, int k) {
+    int pos = 0, c;
+    c = __popc(x & 0xffffu); if (k >= c) { k -= c; pos += 16; x >>= 16; }
+    c = __popc(x & 0xffu);   if (k >= c) { k -= c; pos += 8;  x >>= 8; }
+    c = __popc(x & 0xfu);    if (k >= c) { k -= c; pos += 4;  x >>= 4; }
+    c = __popc(x & 0x3u);    if (k >= c) { k -= c; pos += 2;  x >>= 2; }
+    if (k >= (int)(x & 1u)) pos += 1;
+    return pos;
+}
+DEV int select_(u64 v, int k) {
+    u32 lo = (u32)v;
+    int c = __popc(lo);
+    if (k < c) return select32(lo, k);
+    return 32 + select32((u32)(v >> 32), k - c);
+}
+DEV int select_(u128 v, int k) {
+    u64 lo = (u64)v;
+    int c = __popcll(lo);
+    if (k < c) return select_(lo, k);
+    return 64 + select_((u64)(v >> 64), k - c);
+}
+
+template <int W> DEV typename BitsT<W>::type load_key(const u64 *p);
+template <> DEV u64 load_key<1>(const u64 *p) { return *p; }
+template <> DEV u128 load_key<2>(const u64 *p) {
+    ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+    return ((u128)v.y << 64) | (u128)v.x;
+}
+template <int W> DEV void store_key(u64 *p, typename BitsT<W>::type x);
+template <> DEV void store_key<1>(u64 *p, u64 x) { *p = x; }
+template <> DEV void store_key<2>(u64 *p, u128 x) {
+    *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2((u64)x, (u64)(x >> 64));
+}
+DEV u64 hash_bits(u64 x) { u64 w[1] = {x}; return addr_hash<1>(w); }
+DEV u64 hash_bits(u128 x) { u64 w[2] = {(u64)x, (u64)(x >> 64)}; return addr_hash<2>(w); }
+#endif

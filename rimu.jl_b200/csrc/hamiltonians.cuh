@@ -1,0 +1,387 @@
+// hamiltonians.cuh -- device-side Fock-address arithmetic and the four lattice Hamiltonians.
+//
+// Works directly on the bit-packed addresses (no ONR expansion): occupied-mode lookups are
+// select/ctz/popc chains, boson moves are single-bit delete/insert, fermion signs are popcounts.
+// Semantics follow (path:line under Rimu.jl src/):
+//   BitStringAddresses/bitstring.jl:464-545 (BoseFS bits), :713-792 (FermiFS bits, sign rule)
+//   BitStringAddresses/fockaddress.jl:559-567 (bosonic excitation value)
+//   Hamiltonians/HubbardReal1D.jl:51-62 + BitStringAddresses/bosefs.jl:270-345 (hop enumeration)
+//   Hamiltonians/HubbardMom1D.jl:131-205 + excitations.jl:26-137 (momentum transfer)
+//   Hamiltonians/HubbardRealSpace.jl:18-106,279-391 + geometry.jl:161-175,232-235
+//   Hamiltonians/Transcorrelated1D.jl:113-387 + excitations.jl:199-238
+// Off-diagonal index `i` is 0-based here (= reference's chosen-1); enumeration order is the
+// reference's.  Floating-point expressions are written in the reference's evaluation order and the
+// library is compiled with --fmad=false so that values are bit-identical to an IEEE CPU evaluation.
+#pragma once
+#include "common.cuh"
+
+enum HamKind {
+    HK_REAL1D_BOSE = 0,
+    HK_MOM1D_BOSE = 1,
+    HK_MOM1D_F2C = 2,
+    HK_RS_BOSE = 3,
+    HK_RS_FERMI = 4,
+    HK_RS_F2C = 5,
+    HK_TC_F2C = 6,
+    HK_COUNT = 7
+};
+
+struct HamDev {
+    int hk, M, N0, N1, ndim, nnb, cutoff, three_body, has_pot, umat_zero;
+    double u, t, v, tc0, tc1, u00, u10;
+    const double *kes, *ws, *us, *pot; // device tables
+    const unsigned char *nbr;          // HubbardRealSpace: nbr[(site-1)*nnb + dir] = neighbour site (1-based) or 0
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- boson primitives
+template <class B> DEV int bose_mode_offset(B x, int m) { return m == 1 ? 0 : select_((B)~x, m - 2) + 1; }
+template <class B> DEV B delete_bit(B x, int p) { return (x & lowmask<B>(p)) | ((x >> (p + 1)) << p); }
+template <class B> DEV B insert_one(B x, int p) { return (x & lowmask<B>(p)) | (((B)1) << p) | ((x >> p) << (p + 1)); }
+// a_m: returns occupation before (0 = illegal, x untouched)
+template <class B> DEV int bose_destroy(B &x, int m) {
+    int off = bose_mode_offset(x, m);
+    int n = cto_((B)(x >> off));
+    if (n) x = delete_bit(x, off);
+    return n;
+}
+// a^dagger_m: returns occupation after
+template <class B> DEV int bose_create(B &x, int m) {
+    int off = bose_mode_offset(x, m);
+    int n = cto_((B)(x >> off));
+    x = insert_one(x, off);
+    return n + 1;
+}
+template <class B> DEV int bose_num_occupied(B x) { return popc_((B)(x & ~(x << 1))); }
+template <class B> DEV int bose_num_doubly(B x) { return popc_((B)(x & ~(x << 1) & (x >> 1))); }
+// k-th (0-based) occupied mode in ascending order -> (mode 1-based, occupation)
+template <class B> DEV void bose_kth_occupied(B x, int k, int &mode, int &occ) {
+    int md = 1;
+    for (;;) {
+        int z = ctz_(x);
+        x >>= z; md += z;
+        int n = cto_(x);
+        if (k == 0) { mode = md; occ = n; return; }
+        --k;
+        x >>= n;
+    }
+}
+template <class B> DEV long long bose_interaction(B x) { // sum n(n-1)
+    long long r = 0;
+    while (x != 0) {
+        x >>= ctz_(x);
+        int n = cto_(x);
+        x >>= n;
+        r += (long long)n * (n - 1);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------- fermion primitives (one component in a u64)
+DEV bool fermi_destroy(u64 &f, int m, int &cnt) {
+    u64 bit = 1ull << (m - 1);
+    if (!(f & bit)) return false;
+    cnt += __popcll(f & (bit - 1));
+    f ^= bit;
+    return true;
+}
+DEV bool fermi_create(u64 &f, int m, int &cnt) {
+    u64 bit = 1ull << (m - 1);
+    if (f & bit) return false;
+    cnt += __popcll(f & (bit - 1));
+    f ^= bit;
+    return true;
+}
+DEV double parity_sign(int cnt) { return (cnt & 1) ? -1.0 : 1.0; }
+DEV double kes_sum(const double *kes, u64 f) { // dot(kes, OccupiedModeMap) ascending modes
+    double s = 0.0;
+    while (f) { int b = __ffsll((long long)f) - 1; f &= f - 1; s += kes[b] * 1; }
+    return s;
+}
+
+// ---------------------------------------------------------------- Transcorrelated1D scalar functions
+DEV double tc_n_to_k(int n, int M) { return n * 2.0 * 3.14159265358979323846 / M; }
+DEV double tc_corr(const HamDev &h, int n) {
+    int a = n < 0 ? -n : n;
+    if (a == 0) return 0.0;
+    return (n > 0 ? 1.0 : -1.0) * h.us[a - 1];
+}
+DEV double tc_w(const HamDev &h, int n) { return h.ws[n < 0 ? -n : n]; }
+DEV double tc_t_function(const HamDev &h, int p, int q, int k) {
+    int M = h.M;
+    double k_pi = tc_n_to_k(k, M), pmq_pi = tc_n_to_k(p - q, M), cor_k = tc_corr(h, k);
+    return h.v / M + 2 * h.v / M * (cor_k * k_pi - cor_k * pmq_pi) + 2 * h.v * h.v / h.t * tc_w(h, k);
+}
+DEV double tc_q_function(const HamDev &h, int k, int l) {
+    int M = h.M;
+    return -(h.v * h.v) / (h.t * ((double)M * M)) * tc_corr(h, k) * tc_corr(h, l);
+}
+DEV double tc_three_body_diag(const HamDev &h, u64 fa, int nb) {
+    double value = 0.0;
+    // p over occupied modes ascending, q over those below p (ascending) -- same order as the reference loop
+    u64 fp = fa;
+    while (fp) {
+        int pm = __ffsll((long long)fp); fp &= fp - 1; // 1-based mode
+        u64 fq = fa & ((1ull << (pm - 1)) - 1);
+        while (fq) {
+            int qm = __ffsll((long long)fq); fq &= fq - 1;
+            int k = pm - qm;
+            double qkk = tc_q_function(h, -k, k);
+            value += 2 * qkk * nb;
+        }
+    }
+    return value;
+}
+
+// two-component momentum transfer (excitations.jl:82-119). i is 0-based.
+DEV double mom_transfer_2c(int M, u64 &fa, u64 &fb, int Nb, long long i, bool fold, int &p, int &q, int &mk) {
+    long long per_a = (long long)(M - 1) * Nb;
+    int src_a = (int)(i / per_a);
+    long long rem = i % per_a;
+    int dst_a = (int)(rem / Nb) + 1; // 1..M-1
+    int src_b = (int)(rem % Nb);
+    int src_a_mode = select_(fa, src_a) + 1, src_b_mode = select_(fb, src_b) + 1;
+    if (dst_a >= src_a_mode) dst_a += 1;
+    int mom = dst_a - src_a_mode;
+    int dst_b = src_b_mode - mom;
+    p = src_a_mode; q = src_b_mode; mk = -mom;
+    if (fold) {
+        if (dst_b < 1) dst_b += M; else if (dst_b > M) dst_b -= M;
+    } else if (dst_b < 1 || dst_b > M) return 0.0;
+    u64 ta = fa, tb = fb;
+    int ca = 0, cb = 0;
+    fermi_destroy(ta, src_a_mode, ca);
+    if (!fermi_create(ta, dst_a, ca)) return 0.0;
+    fermi_destroy(tb, src_b_mode, cb);
+    if (!fermi_create(tb, dst_b, cb)) return 0.0;
+    fa = ta; fb = tb;
+    return parity_sign(ca) * parity_sign(cb);
+}
+
+// three-body term (excitations.jl:199-238), fermions. i 0-based; (p,q,s,p_k,q_l) first index fastest.
+DEV double tc_three_body(int M, u64 &fa, u64 &fb, int N1, int N2, long long i, int &k, int &l) {
+    int p = (int)(i % N1); i /= N1;
+    int q = (int)(i % (N1 - 1)); i /= (N1 - 1);
+    int s = (int)(i % N2); i /= N2;
+    int p_k = (int)(i % M) + 1; i /= M;
+    int q_l = (int)(i % M) + 1;
+    if (q >= p) q += 1;
+    int pm = select_(fa, p) + 1, qm = select_(fa, q) + 1, sm = select_(fb, s) + 1;
+    k = pm - p_k; l = q_l - qm;
+    int s_kl = sm + k - l;
+    if (k == 0 || l == 0) return 0.0;
+    if (pm == q_l && qm == p_k) return 0.0;
+    if (s_kl > M || s_kl < 1) return 0.0;
+    u64 ta = fa, tb = fb;
+    int ca = 0, cb = 0;
+    // destructions (q,p) applied last-first: p then q; creations (p_k,q_l): q_l then p_k
+    if (!fermi_destroy(ta, pm, ca)) return 0.0;
+    if (!fermi_destroy(ta, qm, ca)) return 0.0;
+    if (!fermi_create(ta, q_l, ca)) return 0.0;
+    if (!fermi_create(ta, p_k, ca)) return 0.0;
+    if (!fermi_destroy(tb, sm, cb)) return 0.0;
+    if (!fermi_create(tb, s_kl, cb)) return 0.0;
+    fa = ta; fb = tb;
+    return parity_sign(ca) * parity_sign(cb);
+}
+
+// ---------------------------------------------------------------- the Hamiltonian interface
+template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
+    const int M = h.M;
+    if constexpr (HK == HK_REAL1D_BOSE) {
+        return h.u * (double)bose_interaction(x) / 2;
+    } else if constexpr (HK == HK_MOM1D_BOSE) {
+        double ke = 0.0;
+        long long sq = 0, lin = 0, ntot = 0;
+        int md = 1;
+        B y = x;
+        while (y != 0) {
+            int z = ctz_(y); y >>= z; md += z;
+            int n = cto_(y); y >>= n;
+            ke += h.kes[md - 1] * n;
+            lin += (long long)n * (n - 1); sq += (long long)n * n; ntot += n;
+        }
+        long long onproduct = lin + 2 * (ntot * ntot - sq); // sum n(n-1) + 4 sum_{i>j} n_i n_j
+        return ke + h.u / (2 * M) * (double)onproduct;
+    } else if constexpr (HK == HK_MOM1D_F2C) {
+        u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
+        double ka = kes_sum(h.kes, fa), kb = kes_sum(h.kes, fb);
+        return ka + kb + h.u / (2 * M) * (double)(2 * __popcll(fa) * __popcll(fb));
+    } else if constexpr (HK == HK_RS_BOSE) {
+        double interaction = h.umat_zero ? 0.0 : h.u00 * (double)bose_interaction(x) / 2;
+        double pot = 0.0;
+        if (h.has_pot) {
+            int md = 1; B y = x; double pe = 0.0;
+            while (y != 0) {
+                int z = ctz_(y); y >>= z; md += z;
+                int n = cto_(y); y >>= n;
+                pe += n * h.pot[md - 1];
+            }
+            pot += pe;
+        }
+        return interaction + pot;
+    } else if constexpr (HK == HK_RS_FERMI) {
+        double pot = 0.0;
+        if (h.has_pot) {
+            u64 f = (u64)x; double pe = 0.0;
+            while (f) { int b = __ffsll((long long)f) - 1; f &= f - 1; pe += 1 * h.pot[b]; }
+            pot += pe;
+        }
+        return 0.0 + pot;
+    } else if constexpr (HK == HK_RS_F2C) {
+        u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
+        double interaction = h.umat_zero ? 0.0 : (0.0 + h.u10 * (double)__popcll(fa & fb)) + (0.0 + 0.0);
+        double pot = 0.0;
+        if (h.has_pot) {
+            double pe = 0.0; u64 f = fa;
+            while (f) { int b = __ffsll((long long)f) - 1; f &= f - 1; pe += 1 * h.pot[b]; }
+            pot += pe;
+            pe = 0.0; f = fb;
+            while (f) { int b = __ffsll((long long)f) - 1; f &= f - 1; pe += 1 * h.pot[M + b]; }
+            pot += pe;
+        }
+        return interaction + pot;
+    } else { // HK_TC_F2C
+        u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
+        int n1 = __popcll(fa), n2 = __popcll(fb);
+        double k1 = kes_sum(h.kes, fa), k2 = kes_sum(h.kes, fb);
+        double mtd = (double)(2 * n1 * n2) * (h.v / M + 2 * h.v * h.v / h.t * tc_w(h, 0)) / 2;
+        double value = k1 + k2 + mtd;
+        if (h.three_body) value += tc_three_body_diag(h, fa, n2) + tc_three_body_diag(h, fb, n1);
+        return value;
+    }
+}
+
+template <int HK, class B> DEV long long ham_num_offdiagonals(const HamDev &h, B x) {
+    const int M = h.M;
+    if constexpr (HK == HK_REAL1D_BOSE) {
+        return 2LL * bose_num_occupied(x);
+    } else if constexpr (HK == HK_MOM1D_BOSE) {
+        long long s = bose_num_occupied(x), d = bose_num_doubly(x);
+        return s * (s - 1) * (M - 2) + d * (M - 1);
+    } else if constexpr (HK == HK_MOM1D_F2C) {
+        return (long long)h.N0 * h.N1 * (M - 1);
+    } else if constexpr (HK == HK_RS_BOSE) {
+        return (long long)bose_num_occupied(x) * h.nnb;
+    } else if constexpr (HK == HK_RS_FERMI) {
+        return (long long)__popcll((u64)x) * h.nnb;
+    } else if constexpr (HK == HK_RS_F2C) {
+        return (long long)__popcll((u64)x) * h.nnb; // both components
+    } else {
+        long long N1 = h.N0, N2 = h.N1;
+        long long n = N1 * N2 * (M - 1);
+        if (h.three_body) n += N1 * (N1 - 1) * N2 * M * M + N2 * (N2 - 1) * N1 * M * M;
+        return n;
+    }
+}
+
+// returns H_{out,x} for the i-th (0-based) off-diagonal; out == x whenever the value is 0
+template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long long i, B &out) {
+    const int M = h.M;
+    out = x;
+    if constexpr (HK == HK_REAL1D_BOSE) {
+        int mode, occ;
+        bose_kth_occupied(x, (int)(i >> 1), mode, occ);
+        int dst = (i & 1) ? (mode == 1 ? M : mode - 1) : (mode == M ? 1 : mode + 1); // chosen odd <=> i even: hop right
+        B y = x;
+        int ns = bose_destroy(y, mode);
+        int nd = bose_create(y, dst);
+        out = y;
+        return -h.t * sqrt((double)((long long)ns * nd));
+    } else if constexpr (HK == HK_MOM1D_BOSE) {
+        long long s = bose_num_occupied(x);
+        long long dbl = i - s * (s - 1) * (M - 2); // 0-based index into the "same mode" block if >= 0
+        int src0, src1, mom, occ;
+        if (dbl >= 0) {
+            int d = (int)(dbl / (M - 1));
+            mom = (int)(dbl % (M - 1)) + 1;
+            // d-th (0-based) mode with occupation >= 2
+            int md = 1; B y = x;
+            for (;;) {
+                int z = ctz_(y); y >>= z; md += z;
+                int n = cto_(y); y >>= n;
+                if (n >= 2) { if (d == 0) break; --d; }
+            }
+            src0 = src1 = md;
+        } else {
+            long long pair = i / (M - 2);
+            mom = (int)(i % (M - 2)) + 1;
+            int fst = (int)(pair / (s - 1)) + 1, snd = (int)(pair % (s - 1)) + 1; // 1-based as in fldmod1
+            int f_hole, s_hole;
+            if (snd < fst) { f_hole = snd; s_hole = fst; } else { f_hole = fst; s_hole = snd + 1; }
+            bose_kth_occupied(x, f_hole - 1, src0, occ);
+            bose_kth_occupied(x, s_hole - 1, src1, occ);
+            if (mom >= src1 - src0) mom += 1;
+        }
+        int dst0 = src0 + mom, dst1 = src1 - mom;
+        if (dst0 > M) dst0 -= M;
+        if (dst1 < 1) dst1 += M;
+        // excitation(add, dst, src): destroy src[1], src[0]; create dst[1], dst[0]
+        B y = x;
+        long long value = bose_destroy(y, src1);
+        if (value == 0) return 0.0;
+        int n0 = bose_destroy(y, src0);
+        if (n0 == 0) return 0.0;
+        value *= n0;
+        value *= bose_create(y, dst1);
+        value *= bose_create(y, dst0);
+        out = y;
+        return h.u / (2 * M) * sqrt((double)value);
+    } else if constexpr (HK == HK_MOM1D_F2C) {
+        u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
+        int p, q, mk;
+        double val = mom_transfer_2c(M, fa, fb, h.N1, i, true, p, q, mk);
+        if (val != 0.0) out = (B)(fa | (fb << M));
+        return h.u / M * val;
+    } else if constexpr (HK == HK_RS_BOSE) {
+        int particle = (int)(i / h.nnb), neigh = (int)(i % h.nnb);
+        int mode, occ;
+        bose_kth_occupied(x, particle, mode, occ);
+        int dst = h.nbr[(mode - 1) * h.nnb + neigh];
+        if (dst == 0) return 0.0;
+        B y = x;
+        int ns = bose_destroy(y, mode);
+        int nd = bose_create(y, dst);
+        out = y;
+        return -h.tc0 * sqrt((double)((long long)ns * nd));
+    } else if constexpr (HK == HK_RS_FERMI || HK == HK_RS_F2C) {
+        u64 mask = (M >= 64) ? ~0ull : ((1ull << M) - 1);
+        u64 fa = (u64)x & mask, fb = (HK == HK_RS_F2C) ? (((u64)x >> M) & mask) : 0;
+        long long na = (long long)__popcll(fa) * h.nnb;
+        int comp = 0;
+        if (HK == HK_RS_F2C && i >= na) { comp = 1; i -= na; }
+        u64 f = comp ? fb : fa;
+        int particle = (int)(i / h.nnb), neigh = (int)(i % h.nnb);
+        int mode = select_(f, particle) + 1;
+        int dst = h.nbr[(mode - 1) * h.nnb + neigh];
+        if (dst == 0) return 0.0;
+        int cnt = 0;
+        fermi_destroy(f, mode, cnt);
+        if (!fermi_create(f, dst, cnt)) return 0.0;
+        if (comp) fb = f; else fa = f;
+        out = (HK == HK_RS_F2C) ? (B)(fa | (fb << M)) : (B)fa;
+        return -(comp ? h.tc1 : h.tc0) * parity_sign(cnt);
+    } else { // HK_TC_F2C
+        u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
+        long long N1 = h.N0, N2 = h.N1;
+        long long n_mom = N1 * N2 * (M - 1);
+        long long n1 = h.three_body ? N1 * (N1 - 1) * N2 * M * M : 0;
+        double value;
+        if (i < n_mom) {
+            int p, q, mk;
+            value = mom_transfer_2c(M, fa, fb, (int)N2, i, false, p, q, mk);
+            if (value != 0.0) value *= tc_t_function(h, p, q, mk);
+        } else if (i < n_mom + n1) {
+            int k, l;
+            value = tc_three_body(M, fa, fb, (int)N1, (int)N2, i - n_mom, k, l);
+            value *= tc_q_function(h, k, l);
+        } else {
+            int k, l;
+            value = tc_three_body(M, fb, fa, (int)N2, (int)N1, i - n_mom - n1, k, l);
+            value *= tc_q_function(h, k, l);
+        }
+        if (value != 0.0) out = (B)(fa | (fb << M));
+        return value;
+    }
+}
+#endif // __CUDACC__

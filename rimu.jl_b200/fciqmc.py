@@ -1,0 +1,294 @@
+"""FCIQMC driver: host mirror of ProjectorMonteCarloProblem / init / step! / solve.
+
+This is the thin host loop that CALLS the drop-in boundary (`apply_operator`), restated in
+Python because Julia is not available in this image; in a Julia deployment Rimu's own
+`advance!` (fciqmc.jl:126-181) does this job unchanged.  Mirrors
+  ProjectorMonteCarloProblem kwargs/defaults   projector_monte_carlo_problem.jl:150-290
+  PMCSimulation / init / step! / solve!         pmc_simulation.jl:88-174,265-452
+  advance!(::FCIQMC)                            fciqmc.jl:126-181
+  shift strategies                              strategies_and_params/shiftstrategy.jl:100-230
+  ProjectedEnergy / Projector post-steps        strategies_and_params/poststepstrategy.jl:50-121
+  default_starting_vector                       qmc_states.jl:236-260
+Only O(10) scalars per step cross the C ABI; all vector work runs on the GPU.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .dictvectors import (FirstOrderTransitionOperator, GPUDVec, WorkingMemory, apply_operator, dot, mul,
+                          walkernumber_and_length)
+from .hamiltonians import AbstractHamiltonian, starting_address
+from .stochasticstyles import IsDeterministic, IsDynamicSemistochastic, StochasticStyle, default_style
+
+
+# --------------------------------------------------------------------------- shift strategies
+@dataclass
+class ShiftParameters:
+    """DefaultShiftParameters (shiftstrategy.jl:32-38)"""
+    shift: float
+    pnorm: float
+    time_step: float
+    counter: int = 0
+    shift_mode: bool = False
+
+
+@dataclass
+class DontUpdate:
+    target_walkers: float = 1000
+
+    def update(self, sp, tnorm):
+        sp.pnorm = tnorm
+        return {"shift": sp.shift, "norm": tnorm}, True
+
+
+@dataclass
+class LogUpdate:
+    zeta: float = 0.08
+
+    def update(self, sp, tnorm):
+        sp.shift -= self.zeta / sp.time_step * math.log(tnorm / sp.pnorm)
+        sp.pnorm = tnorm
+        return {"shift": sp.shift, "norm": tnorm}, True
+
+
+@dataclass
+class DoubleLogUpdate:
+    """shiftstrategy.jl:160-181"""
+    target_walkers: float = 1000
+    zeta: float = 0.08
+    xi: float | None = None
+
+    def __post_init__(self):
+        if self.xi is None:
+            self.xi = self.zeta ** 2 / 4
+
+    def update(self, sp, tnorm):
+        dt = sp.time_step
+        sp.shift -= self.xi / dt * math.log(tnorm / self.target_walkers) + self.zeta / dt * math.log(tnorm / sp.pnorm)
+        sp.pnorm = tnorm
+        return {"shift": sp.shift, "norm": tnorm}, True
+
+
+@dataclass
+class DoubleLogUpdateAfterTargetWalkers:
+    """shiftstrategy.jl:190-213"""
+    target_walkers: float = 1000
+    zeta: float = 0.08
+    xi: float | None = None
+
+    def __post_init__(self):
+        if self.xi is None:
+            self.xi = self.zeta ** 2 / 4
+
+    def update(self, sp, tnorm):
+        if sp.shift_mode or tnorm > self.target_walkers:
+            sp.shift_mode = True
+            dt = sp.time_step
+            sp.shift -= self.xi / dt * math.log(tnorm / self.target_walkers) + self.zeta / dt * math.log(tnorm / sp.pnorm)
+        sp.pnorm = tnorm
+        return {"shift": sp.shift, "norm": tnorm, "shift_mode": sp.shift_mode}, True
+
+
+# --------------------------------------------------------------------------- post-step strategies
+class ProjectedEnergy:
+    """poststepstrategy.jl:82-121: reports vproj = projector⋅v and hproj = (H' projector)⋅v, or
+    dot(projector, H, v) when the adjoint is unknown (Transcorrelated1D)."""
+
+    def __init__(self, hamiltonian, projector: GPUDVec, vproj="vproj", hproj="hproj"):
+        self.ham, self.vproj_name, self.hproj_name = hamiltonian, vproj, hproj
+        det = IsDeterministic()
+        self.vproj = GPUDVec(style=det, address_type=projector.address_type, ctx=projector.ctx).copy_from(projector)
+        if hamiltonian.hermitian:
+            self.hproj = mul(self.vproj.similar(), hamiltonian, self.vproj)  # H' = H
+        else:
+            self.hproj = None
+
+    def __call__(self, state, step):
+        v = state.v
+        vf = v if v.style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)
+        out = {self.vproj_name: self.vproj.dot(vf)}
+        out[self.hproj_name] = self.hproj.dot(vf) if self.hproj is not None else dot(self.vproj, self.ham, vf)
+        return out
+
+
+class Projector:
+    def __init__(self, **kw):
+        (self.name, proj), = kw.items()
+        self.projector = GPUDVec(style=IsDeterministic(), address_type=proj.address_type, ctx=proj.ctx).copy_from(proj)
+
+    def __call__(self, state, step):
+        v = state.v
+        vf = v if v.style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)
+        return {self.name: self.projector.dot(vf)}
+
+
+class Timer:
+    def __call__(self, state, step):
+        return {"time": time.time()}
+
+
+# --------------------------------------------------------------------------- problem / simulation
+def default_starting_vector(ham_or_address, population=10, style=None):
+    """qmc_states.jl:236-260: `address => population` with the given style."""
+    address = starting_address(ham_or_address) if isinstance(ham_or_address, AbstractHamiltonian) else ham_or_address
+    style = IsDynamicSemistochastic() if style is None else style
+    val = int(population) if style.val_type == _lib.VAL_I64 else float(population)
+    return GPUDVec([(address, val)], style=style)
+
+
+@dataclass
+class SingleState:
+    """qmc_states.jl:20-29"""
+    hamiltonian: AbstractHamiltonian
+    v: GPUDVec
+    pv: GPUDVec
+    wm: WorkingMemory
+    shift_parameters: ShiftParameters
+
+
+class ProjectorMonteCarloProblem:
+    """ProjectorMonteCarloProblem(hamiltonian; kwargs...) with the reference's defaults."""
+
+    def __init__(self, hamiltonian, *, start_at=None, shift=None, style=None, time_step=0.01, starting_step=0,
+                 last_step=100, wall_time=math.inf, target_walkers=1000, zeta=0.08, xi=None, shift_strategy=None,
+                 post_step_strategy=(), max_length=None, random_seed=True, reporting_interval=1, metadata=None,
+                 n_replicas=1, initiator=False):
+        if n_replicas != 1:
+            raise NotImplementedError("replicas are outside the device path (SURVEY.md section 8e)")
+        if initiator:
+            raise NotImplementedError("initiator rules are a NEXT row of the scope table (SURVEY.md section 8f)")
+        self.hamiltonian = hamiltonian
+        self.style = IsDynamicSemistochastic() if style is None else style
+        self.start_at = start_at
+        self.shift, self.time_step = shift, float(time_step)
+        self.starting_step, self.last_step, self.wall_time = starting_step, last_step, wall_time
+        self.shift_strategy = shift_strategy or DoubleLogUpdate(target_walkers, zeta, xi)
+        tw = getattr(self.shift_strategy, "target_walkers", target_walkers)
+        self.max_length = max_length if max_length is not None else round(2 * abs(tw) + 100)
+        self.post_step_strategy = tuple(post_step_strategy) if isinstance(post_step_strategy, (tuple, list)) else (post_step_strategy,)
+        if random_seed is True:
+            random_seed = int.from_bytes(os.urandom(8), "little")
+        elif random_seed is False or random_seed is None:
+            random_seed = 0
+        self.random_seed = int(random_seed) & 0xFFFFFFFFFFFFFFFF
+        self.reporting_interval = reporting_interval
+        self.metadata = dict(metadata or {})
+
+
+class PMCSimulation:
+    """init(problem) (pmc_simulation.jl:88-174)."""
+
+    def __init__(self, problem: ProjectorMonteCarloProblem):
+        self.problem = p = problem
+        ham = p.hamiltonian
+        sa = p.start_at
+        if sa is None:
+            v = default_starting_vector(ham, style=p.style)
+        elif isinstance(sa, GPUDVec):
+            v = sa.copy()
+        elif isinstance(sa, (list, tuple, dict)):
+            v = GPUDVec(sa, style=p.style)
+        else:  # an address
+            v = default_starting_vector(sa, style=p.style)
+        style = v.style
+        if p.shift is None:  # Rayleigh quotient of the starting vector (fciqmc.jl:51-61)
+            vf = v if style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)
+            vdet = vf if isinstance(vf.style, IsDeterministic) else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(vf)
+            shift = dot(vdet, ham, vdet) / vdet.dot(vdet)
+        else:
+            shift = float(p.shift)
+        sp = ShiftParameters(shift, v.walkernumber(), p.time_step)
+        wm = WorkingMemory(v, seed=p.random_seed)
+        self.state = SingleState(ham, v, v.zerovector(), wm, sp)
+        self.step = p.starting_step
+        self.report = {}
+        self.aborted = False
+        self.success = False
+        self.message = ""
+        self.elapsed_time = 0.0
+        self.modified = False
+
+    # ---- one step: advance!(FCIQMC) (fciqmc.jl:126-181)
+    def step_(self):
+        if self.aborted or self.success:
+            return self
+        if self.step >= self.problem.last_step:
+            self.success = True
+            return self
+        self.step += 1
+        st, p = self.state, self.problem
+        sp = st.shift_parameters
+        T = FirstOrderTransitionOperator(st.hamiltonian, sp.shift, sp.time_step)
+        names, values, wm, pv = apply_operator(st.wm, st.pv, st.v, T)
+        st.v, st.pv = pv, st.v
+        stats = wm.last_stats
+        is_int = st.v.style.val_type == _lib.VAL_I64
+        tnorm = float(stats.inorm1) if is_int else stats.norm1
+        length = stats.len
+        shift_stats, proceed = p.shift_strategy.update(sp, tnorm) if length > 0 else ({"shift": sp.shift, "norm": tnorm}, True)
+        if self.step % p.reporting_interval == 0:
+            row = {"step": self.step, "len": length}
+            row.update(shift_stats)
+            row.update(dict(zip(names, values)))
+            for ps in p.post_step_strategy:
+                row.update(ps(st, self.step))
+            for k, val in row.items():
+                self.report.setdefault(k, []).append(val)
+        if length == 0:
+            self.aborted, self.message = True, f"Aborted in step {self.step}."  # dead population
+        elif length > p.max_length:
+            self.aborted, self.message = True, f"Aborted in step {self.step}."  # max_length reached
+        elif not proceed:
+            self.aborted = True
+        elif self.step >= p.last_step:
+            self.success = True
+        self.modified = True
+        return self
+
+    def solve_(self, last_step=None, wall_time=None):
+        if last_step is not None:
+            self.problem.last_step = last_step
+            self.success = self.step >= last_step and not self.aborted
+            if self.step < last_step:
+                self.success = False
+        wt = self.problem.wall_time if wall_time is None else wall_time
+        t0 = time.time()
+        while not self.aborted and not self.success:
+            if time.time() - t0 > wt:
+                self.aborted, self.message = True, "Wall time reached."
+                break
+            self.step_()
+        self.elapsed_time += time.time() - t0
+        return self
+
+    def dataframe(self):
+        import pandas as pd
+        return pd.DataFrame(self.report)
+
+    DataFrame = dataframe
+
+
+def init(problem):
+    return PMCSimulation(problem)
+
+
+def step_(sim):
+    return sim.step_()
+
+
+def solve_(sim, **kw):
+    return sim.solve_(**kw)
+
+
+def solve(problem, **kw):
+    return init(problem).solve_(**kw)
+
+
+def DataFrame(sim):
+    return sim.dataframe()

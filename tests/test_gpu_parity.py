@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Integer/index work must be bit-exact; Float64 within 1e-12 relative (north_star tolerance)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.cases import SPECS, oracle_ham, product_ham, sample_keys
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def sort_kv(keys, vals):
+    keys = np.asarray(keys, dtype=np.uint64).reshape(len(vals), -1)
+    order = np.lexsort(tuple(keys[:, j] for j in range(keys.shape[1])))
+    return keys[order], np.asarray(vals)[order]
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_hamiltonian_elements(built, name):
+    """diagonal_element / num_offdiagonals / get_offdiagonal(i) for every i, element-wise."""
+    oh, ph = oracle_ham(name), product_ham(name)
+    keys = sample_keys(oh, 24, seed=1)
+    d_gpu = ph.diagonal_elements(keys)
+    n_gpu = ph.nums_offdiagonals(keys)
+    for j, key in enumerate(keys):
+        kt = tuple(int(x) for x in key)
+        assert d_gpu[j] == oh.diagonal_element(kt), (name, "diagonal", kt)
+        L = oh.num_offdiagonals(kt)
+        assert n_gpu[j] == L
+        cap = min(L, 3000)
+        ko, vo = ph.offdiagonals_of_key(key, 1, cap)
+        idx = range(1, cap + 1) if L <= 3000 else None
+        for i in range(1, cap + 1):
+            ok, ov = oh.get_offdiagonal(kt, i)
+            assert vo[i - 1] == ov, (name, kt, i, vo[i - 1], ov)
+            if ov != 0.0:
+                assert tuple(int(x) for x in ko[i - 1]) == ok, (name, kt, i)
+        if L > 3000:  # tail block (second three-body segment) spot check
+            first = L - 1999
+            ko, vo = ph.offdiagonals_of_key(key, first, 2000)
+            for i in range(0, 2000, 7):
+                ok, ov = oh.get_offdiagonal(kt, first + i)
+                assert vo[i] == ov
+                if ov != 0.0:
+                    assert tuple(int(x) for x in ko[i]) == ok
+
+
+@pytest.mark.parametrize("name", ["real1d_6", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d", "rs_bose_3d_w2",
+                                  "rs_fermi", "rs_f2c_4x4", "rs_f2c_trap", "tc_7", "tc_8_cut2"])
+def test_deterministic_hv(built, name):
+    """mul!(y, H, x) three times from the starting address: keys exact, values 1e-12 relative."""
+    import rimu_b200 as R
+    oh, ph = oracle_ham(name), product_ham(name)
+    x = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    ok, ov = np.array([oh.start_key], dtype=np.uint64), np.array([1.0])
+    p = orc.make_params(orc.STYLE_DETERMINISTIC, plain_h=True)
+    for it in range(3):
+        y = x.similar()
+        R.mul(y, ph, x)
+        ok, ov, st = oh.step(p, ok, ov)
+        gk, gv = y.download_sorted()
+        assert np.array_equal(gk, ok), (name, it)
+        scale = np.abs(ov).max()
+        assert np.all(np.abs(gv - ov) <= RTOL * np.maximum(np.abs(ov), scale)), (name, it, np.abs(gv - ov).max())
+        x = y
+        if len(ok) > 20000:
+            break
+
+
+@pytest.mark.parametrize("name", ["real1d_6", "real1d_10", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d",
+                                  "rs_bose_3d_w2", "rs_f2c_4x4", "tc_7"])
+def test_integer_walkers_bit_exact(built, name):
+    """IsStochasticInteger FCIQMC steps: same Philox streams => identical vectors and statistics."""
+    import rimu_b200 as R
+    oh, ph = oracle_ham(name), product_ham(name)
+    seed, dtau = 20240917, 0.002 if name.startswith("tc") else 0.01
+    v = R.GPUDVec([(ph.address, 500)], style=R.IsStochasticInteger())
+    wm = R.working_memory(v, seed=seed)
+    ok, ov = np.array([oh.start_key], dtype=np.uint64), np.array([500], dtype=np.int64)
+    shift = oh.diagonal_element(oh.start_key)
+    for step in range(6):
+        T = R.FirstOrderTransitionOperator(ph, shift + 2.0, dtau)
+        out = v.similar()
+        names, vals, _, _ = R.apply_operator(wm, out, v, T)
+        v = out
+        pp = orc.make_params(orc.STYLE_INTEGER, shift=shift + 2.0, dtau=dtau, key=orc.step_key(seed, step))
+        ok, ov, st = oh.step(pp, ok, ov)
+        gk, gv = v.download_sorted()
+        assert np.array_equal(gk, ok), (name, step)
+        assert np.array_equal(gv, ov), (name, step)
+        s = wm.last_stats
+        assert (s.spawn_attempts, s.ispawns, s.ideaths, s.iclones, s.izombies) == \
+            (st.spawn_attempts, st.ispawns, st.ideaths, st.iclones, st.izombies)
+        assert s.len == st.len_after and s.inorm1 == st.inorm1
+        assert names == ("spawn_attempts", "spawns", "deaths", "clones", "zombies")
+
+
+@pytest.mark.parametrize("name", ["real1d_6", "mom1d_bose", "rs_f2c_4x4", "tc_7"])
+def test_semistochastic_step(built, name):
+    """IsDynamicSemistochastic: exact/inexact branch, late ThresholdCompression.  Random decisions are
+    keyed on addresses, so results match the oracle except for Float64 summation order."""
+    import rimu_b200 as R
+    oh, ph = oracle_ham(name), product_ham(name)
+    seed, dtau = 77, 0.002 if name.startswith("tc") else 0.01
+    style = R.IsDynamicSemistochastic()
+    v = R.GPUDVec([(ph.address, 40.0)], style=style)
+    wm = R.working_memory(v, seed=seed)
+    ok, ov = np.array([oh.start_key], dtype=np.uint64), np.array([40.0])
+    shift = oh.diagonal_element(oh.start_key)
+    for step in range(5):
+        T = R.FirstOrderTransitionOperator(ph, shift + 1.0, dtau)
+        out = v.similar()
+        names, vals, _, _ = R.apply_operator(wm, out, v, T)
+        v = out
+        pp = orc.make_params(orc.STYLE_SEMISTOCHASTIC, shift=shift + 1.0, dtau=dtau, compress_threshold=1.0,
+                             key=orc.step_key(seed, step))
+        ok, ov, st = oh.step(pp, ok, ov)
+        gk, gv = v.download_sorted()
+        assert np.array_equal(gk, ok), (name, step)
+        assert np.allclose(gv, ov, rtol=1e-10, atol=0), (name, step)
+        s = wm.last_stats
+        assert (s.exact_steps, s.inexact_steps, s.spawn_attempts, s.len_before, s.len) == \
+            (st.exact_steps, st.inexact_steps, st.spawn_attempts, st.len_before, st.len_after)
+        assert math.isclose(s.spawns, st.spawns, rel_tol=1e-10)
+        assert math.isclose(s.norm1, st.norm1, rel_tol=1e-10)
+        assert names[-1] == "len_before"
+        # feed the GPU result back so that last-bit differences cannot accumulate into branch flips
+        ok, ov = gk, gv
+
+
+def test_with_threshold_style(built):
+    import rimu_b200 as R
+    name = "real1d_6"
+    oh, ph = oracle_ham(name), product_ham(name)
+    style = R.IsStochasticWithThreshold(1.0)
+    v = R.GPUDVec([(ph.address, 25.0)], style=style)
+    wm = R.working_memory(v, seed=5)
+    ok, ov = np.array([oh.start_key], dtype=np.uint64), np.array([25.0])
+    for step in range(4):
+        T = R.FirstOrderTransitionOperator(ph, 1.0, 0.01)
+        out = v.similar()
+        R.apply_operator(wm, out, v, T)
+        v = out
+        pp = orc.make_params(orc.STYLE_WITH_THRESHOLD, shift=1.0, dtau=0.01, proj_threshold=1.0, key=orc.step_key(5, step))
+        ok, ov, st = oh.step(pp, ok, ov)
+        gk, gv = v.download_sorted()
+        assert np.array_equal(gk, ok)
+        assert np.allclose(gv, ov, rtol=1e-10, atol=0)
+        ok, ov = gk, gv
+
+
+@pytest.mark.parametrize("W,dtype", [(1, np.float64), (1, np.int64), (2, np.float64), (2, np.int64)])
+def test_annihilate_given_spawn_list(built, W, dtype):
+    """Annihilation of a given spawn list: bit-exact for Int64, 1e-12 for Float64; includes heavy
+    duplication, exact cancellation, empty input."""
+    import rimu_b200 as R
+    rng = np.random.default_rng(3)
+    at = R.AddressType(R._lib.ADDR_BOSE, (20,) if W == 1 else (60,), 20 if W == 1 else 60)
+    style = R.IsStochasticInteger() if dtype == np.int64 else R.IsDeterministic()
+    for n, distinct in [(0, 1), (1, 1), (1000, 10), (200_000, 5000), (300_000, 300_000)]:
+        pool = rng.integers(0, 2 ** 62, size=(max(distinct, 1), W), dtype=np.uint64)
+        keys = pool[rng.integers(0, max(distinct, 1), size=n)]
+        vals = rng.integers(-3, 4, size=n).astype(np.int64) if dtype == np.int64 else rng.uniform(-1, 1, size=n)
+        if n >= 1000:  # force exact cancellations
+            keys[1], vals[1] = keys[0], -vals[0]
+        v = R.GPUDVec(style=style, address_type=at)
+        R._lib.check(R._lib.lib().rimu_annihilate(v.handle, np.ascontiguousarray(keys).ctypes.data_as(R._lib._u64p),
+                                                  np.ascontiguousarray(vals).ctypes.data_as(R._lib._vp), n, 0))
+        gk, gv = v.download_sorted()
+        ok, ov = orc.annihilate(W, keys, vals)
+        assert np.array_equal(gk, ok)
+        if dtype == np.int64:
+            assert np.array_equal(gv, ov)
+        else:
+            assert np.allclose(gv, ov, rtol=RTOL, atol=1e-15)
+
+
+def test_vector_interface(built):
+    """Subset of test/DictVectors.jl test_dvec_interface that lies on the step path."""
+    import rimu_b200 as R
+    a, b, c = R.BoseFS(3, 2, 1), R.BoseFS(2, 3, 1), R.BoseFS(1, 1, 4)
+    v = R.GPUDVec([(a, 1.5), (b, -2.0), (a, 0.5), (c, 0.0)], style=R.IsDeterministic())
+    assert len(v) == 2 and v[a] == 2.0 and v[b] == -2.0 and v[c] == 0.0
+    v[c] = 4.0
+    assert len(v) == 3 and v[c] == 4.0
+    v[c] = 0.0
+    assert len(v) == 2
+    assert v.norm(1) == 4.0 and math.isclose(v.norm(2), math.sqrt(8.0)) and v.norm(math.inf) == 2.0
+    w = R.GPUDVec([(a, 1.0), (c, 3.0)], style=R.IsDeterministic())
+    assert v.dot(w) == 2.0 and w.dot(v) == 2.0
+    z = v + w
+    assert z.to_dict() == {a: 3.0, b: -2.0, c: 3.0}
+    z = v - v
+    assert len(z) == 0
+    z = 2.0 * v
+    assert z[a] == 4.0
+    v.add_(w, -2.0)
+    assert v.to_dict() == {a: 0.0 + 2.0 - 2.0, b: -2.0, c: -6.0} or v.to_dict() == {b: -2.0, c: -6.0}
+    assert len(v.zerovector()) == 0
+    vi = R.GPUDVec([(a, 3), (b, -2)], style=R.IsStochasticInteger())
+    assert vi.walkernumber() == 5.0 and R.walkernumber_and_length(vi) == (5.0, 2)
+    vf = R.GPUDVec(style=R.IsDeterministic(), address_type=a.address_type).copy_from(vi)
+    assert vf.to_dict() == {a: 3.0, b: -2.0}
+
+
+def test_error_behaviour(built):
+    import rimu_b200 as R
+    a = R.BoseFS(1, 1, 1)
+    H = R.HubbardReal1D(a)
+    v = R.GPUDVec([(a, 1.0)], style=R.IsDynamicSemistochastic())
+    with pytest.raises(ValueError):
+        R.mul(v.similar(), H, v)  # mul! with non-deterministic working memory (pdvec.jl:814-819)
+    with pytest.raises(ValueError):
+        R.apply_operator(R.working_memory(v), v, v, H)  # aliasing
+    with pytest.raises(R.RimuB200Error):
+        vi = R.GPUDVec([(a, 1)], style=R.IsStochasticInteger())
+        R.apply_operator(R.working_memory(v), v.similar(), vi, H)  # style/eltype mismatch
+    with pytest.raises(IndexError):
+        R.get_offdiagonal(H, a, 7)
+
+
+def test_table_growth_retry(built):
+    """A deliberately tiny working table overflows, the step reports it and the retry gives the same result."""
+    import rimu_b200 as R
+    name = "real1d_10"
+    oh, ph = oracle_ham(name), product_ham(name)
+    x = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    for _ in range(5):
+        y = x.similar()
+        R.mul(y, ph, x)
+        x = y
+    ref = x.download_sorted()
+    y = x.similar()
+    wm = R.working_memory(x)
+    R.apply_operator(wm, y, x, ph, table_slots=1024)  # forces internal regrow of the active table
+    z = x.similar()
+    R.apply_operator(wm, z, x, ph)
+    k1, v1 = y.download_sorted()
+    k2, v2 = z.download_sorted()
+    assert np.array_equal(k1, k2) and np.allclose(v1, v2, rtol=1e-12)
+    assert np.array_equal(x.download_sorted()[0], ref[0])  # source untouched
