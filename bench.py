@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native FCIQMC step (contract: see task spec / DESIGN.md).
+
+Metric (BASELINE.json): walker spawn attempts per second (+ annihilation HBM GB/s in `extra`).
+Workload at every N: BASELINE config 2 -- HubbardMom1D, BoseFS{20,20}, IsDynamicSemistochastic,
+1e7 target walkers PER GPU (weak scaling; determinant space hash-partitioned across ranks).
+A "step" is one FCIQMC step (apply_operator! + shift update) on an equilibrated population that the
+sampler itself produced from the starting address (SURVEY.md section 8d "steady-state surrogate").
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  torchrun --nproc-per-node N bench.py --gpus N ...        (driver launches this form)
+  python bench.py --impl reference ...                      CPU arm: oracle port on all host cores
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "spawn_attempts_per_s"
+UNIT = "attempts/s"
+M_SITES, N_PART, U_INT, T_HOP, DTAU = 20, 20, 6.0, 1.0, 1e-4
+START_ONR = tuple(N_PART if i == 9 else 0 for i in range(M_SITES))  # all bosons in mode 10 (k = 0)
+WORKLOAD = "config2: HubbardMom1D BoseFS{20,20} u=6 t=1 dtau=1e-4 IsDynamicSemistochastic"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--walkers", type=float, default=1e7, help="target walkers per GPU")
+    ap.add_argument("--equil", type=int, default=40, help="extra equilibration steps once within 5%% of the target")
+    ap.add_argument("--cpu-walkers", type=float, default=2e5, help="reference arm: walkers of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=1)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm (CPU)
+def reference_arm(args):
+    """The reference (pure Julia) cannot run here: the CPU arm is the oracle port of Rimu's threaded
+    PDVec path (oracle.c orc_step_threaded), all host cores, on a bounded sample of the same workload
+    (same model/style, fewer walkers)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    oh = orc.OracleHam("HubbardMom1D", "bose", START_ONR, u=U_INT, t=T_HOP)
+    target = args.cpu_walkers
+    keys = np.array([oh.start_key], dtype=np.uint64)
+    vals = np.array([10.0])
+    shift0 = oh.diagonal_element(oh.start_key)
+    shift, pnorm, zeta = shift0, 10.0, 0.08
+    xi = zeta ** 2 / 4
+    step = 0
+
+    def one(step, shift):
+        p = orc.make_params(orc.STYLE_SEMISTOCHASTIC, shift=shift, dtau=DTAU, compress_threshold=1.0,
+                            key=orc.step_key(args.seed, step))
+        return oh.step(p, keys, vals, threads=cores)
+
+    # DoubleLogUpdate from the first step, as ProjectorMonteCarloProblem does by default
+    t_budget, settled = time.time(), 0
+    while True:
+        keys, vals, st = one(step, shift)
+        step += 1
+        tnorm = st.norm1
+        shift -= xi / DTAU * math.log(tnorm / target) + zeta / DTAU * math.log(tnorm / pnorm)
+        pnorm = tnorm
+        settled = settled + 1 if abs(tnorm - target) < 0.05 * target else 0
+        if settled >= args.equil or step >= 1500 or time.time() - t_budget > 150:
+            break
+    for _ in range(args.warmup):
+        keys, vals, st = one(step, shift)
+        step += 1
+    attempts, t0 = 0, time.time()
+    for _ in range(args.steps):
+        keys, vals, st = one(step, shift)
+        tnorm = st.norm1
+        shift -= xi / DTAU * math.log(tnorm / target) + zeta / DTAU * math.log(tnorm / pnorm)
+        pnorm = tnorm
+        attempts += st.spawn_attempts
+        step += 1
+    dt = time.time() - t0
+    val = attempts / dt
+    sample = f"{WORKLOAD}, {target:.0e} walkers (bounded sample of the 1e7-walker workload), {len(vals)} determinants"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "walkers_per_gpu": target, "note": "CPU port of Rimu's threaded PDVec path (reference is Julia; not runnable here)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------- our arm (GPU)
+def pinned_array(R, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    R._lib.check(R._lib.lib().rimu_host_alloc(max(n, 8), C.byref(p)))
+    buf = (C.c_char * max(n, 8)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape), p
+
+
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("gloo")
+    per_gpu = args.walkers
+    target = per_gpu * world
+    slots = 1 << max(16, int(math.ceil(math.log2(per_gpu * 3))))
+    ctx = R.init_distributed(1, records_per_peer=int(per_gpu * 1.5), table_slots=slots)
+
+    addr = R.BoseFS(START_ONR)
+    H = R.HubbardMom1D(addr, u=U_INT, t=T_HOP)
+    style = R.IsDynamicSemistochastic()
+    v = R.GPUDVec([(addr, 10.0)], style=style, capacity=int(per_gpu * 1.5))
+    pv = v.similar()
+    R._lib.check(R._lib.lib().rimu_vec_reserve(pv.handle, int(per_gpu * 1.5)))
+    wm = R.working_memory(v, seed=args.seed)
+    shift0 = R.diagonal_element(H, addr)
+    sp = R.ShiftParameters(shift0, 10.0, DTAU)
+    strat = R.DoubleLogUpdate(target_walkers=target)
+
+    def one_step():
+        nonlocal v, pv
+        T = R.FirstOrderTransitionOperator(H, sp.shift, sp.time_step)
+        R.apply_operator(wm, pv, v, T)
+        v, pv = pv, v
+        s = wm.last_stats
+        strat.update(sp, s.norm1)
+        return s
+
+    # DoubleLogUpdate from the first step (the reference's default); stop once the population has
+    # stayed within 5 % of the target for `equil` consecutive steps
+    t0, nsteps, settled = time.time(), 0, 0
+    while True:
+        s = one_step()
+        nsteps += 1
+        settled = settled + 1 if abs(s.norm1 - target) < 0.05 * target else 0
+        if settled >= args.equil or nsteps >= 3000 or time.time() - t0 > 240:
+            break
+    for _ in range(args.warmup):
+        s = one_step()
+
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- timed region: K resident steps
+    launches0 = C.c_uint64()
+    _lib.check(_lib.lib().rimu_ctx_launch_count(ctx.handle, C.byref(launches0)))
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0.record(stream)
+    tw0 = time.time()
+    acc = dict(attempts=0, deposits=0, ms_diag=0.0, ms_spawn=0.0, ms_exch=0.0, ms_compact=0.0, parents=0, len_before=0, len=0)
+    for _ in range(args.steps):
+        parents = len(v)
+        s = one_step()
+        acc["attempts"] += s.spawn_attempts; acc["deposits"] += s.deposits
+        acc["ms_diag"] += s.ms_diag; acc["ms_spawn"] += s.ms_spawn; acc["ms_exch"] += s.ms_exchange; acc["ms_compact"] += s.ms_compact
+        acc["parents"] += parents; acc["len_before"] += s.len_before; acc["len"] += s.len
+    ev1.record(stream)
+    barrier()
+    wall = time.time() - tw0
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches1 = C.c_uint64()
+    _lib.check(_lib.lib().rimu_ctx_launch_count(ctx.handle, C.byref(launches1)))
+    t = torch.tensor([ms], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0])
+    value = acc["attempts"] / (ms_max * 1e-3)  # attempts are already global (all-reduced by the library)
+
+    # ---- e2e: same step through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+    n_in = len(v)
+    hk, hkp = pinned_array(R, (int(per_gpu * 1.5), 1), np.uint64)
+    hv, hvp = pinned_array(R, (int(per_gpu * 1.5),), np.float64)
+    ok, okp = pinned_array(R, (int(per_gpu * 1.5), 1), np.uint64)
+    ov, ovp = pinned_array(R, (int(per_gpu * 1.5),), np.float64)
+    m = C.c_int64()
+    _lib.check(_lib.lib().rimu_vec_download(v.handle, hk.ctypes.data_as(_lib._u64p), hv.ctypes.data_as(C.c_void_p), hk.shape[0], C.byref(m)))
+    e2e_steps = max(3, min(args.steps, 10))
+    src, dst = v.similar(), pv
+    R._lib.check(R._lib.lib().rimu_vec_reserve(src.handle, int(per_gpu * 1.5)))
+    T = R.FirstOrderTransitionOperator(H, sp.shift, sp.time_step)
+    e2e_attempts, h2d, d2h = 0, 0, 0
+    for it in range(2 + e2e_steps):
+        if it == 2:
+            barrier()
+            ev0.record(stream)
+        _lib.check(_lib.lib().rimu_vec_assign(src.handle, hk.ctypes.data_as(_lib._u64p), hv.ctypes.data_as(C.c_void_p), n_in))
+        R.apply_operator(wm, dst, src, T)
+        _lib.check(_lib.lib().rimu_vec_download(dst.handle, ok.ctypes.data_as(_lib._u64p), ov.ctypes.data_as(C.c_void_p), ok.shape[0], C.byref(m)))
+        if it >= 2:
+            e2e_attempts += wm.last_stats.spawn_attempts
+            h2d += n_in * 16
+            d2h += m.value * 16
+    ev1.record(stream)
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = e2e_attempts / (float(t[0]) * 1e-3)
+
+    # ---- roofline of the dominant kernel (CUDA-event durations measured live, per launch averages)
+    K = args.steps
+    E = 16  # bytes per entry: one uint64 address word + one 8-byte value
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # per-rank figures (stats are global -> divide by world for a per-GPU kernel)
+    P = acc["parents"] / K
+    dep_spawn = max(acc["deposits"] / world - acc["parents"], 0) / K
+    spawn_bytes = P * E + P * 8 + 2 * E * dep_spawn            # parents + offsets read; RMW of one slot per deposit
+    compact_bytes = (2 * acc["len_before"] / world + acc["len"] / world) * E / K  # read+reset occupied slots, write survivors
+    kern = {"spawn_kernel": (acc["ms_spawn"] / K, spawn_bytes), "compact_kernel": (acc["ms_compact"] / K, compact_bytes)}
+    dom = max(kern, key=lambda k: kern[k][0])
+    dms, dbytes = kern[dom]
+    achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("walkers_per_gpu") == per_gpu:
+            traffic = tr.get(dom)
+    except Exception:
+        pass
+    annih_bytes = (acc["deposits"] / world + acc["len_before"] / world + acc["len"] / world) * E / K
+    annih_ms = (acc["ms_spawn"] + acc["ms_compact"]) / K
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "walkers_per_gpu": per_gpu, "target_walkers": target, "determinants_per_gpu": P,
+                   "attempts_per_step": acc["attempts"] / K, "l2": "inputs larger than L2 (vector + working table > 126 MB)",
+                   "growth_steps": nsteps, "equil_steps": args.equil, "parallelism": f"hash-partitioned x{world}"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps},
+        "gpu_launches": int(launches1.value - launches0.value),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dbytes, "ms_per_launch": dms},
+        "extra": {"annihilation_gbs": annih_bytes / (annih_ms * 1e-3) / 1e9 if annih_ms > 0 else None,
+                  "phase_ms_per_step": {"diag_count_scan": acc["ms_diag"] / K, "spawn": acc["ms_spawn"] / K,
+                                        "exchange": acc["ms_exch"] / K, "compact": acc["ms_compact"] / K},
+                  "wall_ms_per_step": 1e3 * wall / K, "norm": s.norm1, "shift": sp.shift},
+    }
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample, rank 0, N=1 only
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        cores = os.cpu_count() or 1
+        oh = orc.OracleHam("HubbardMom1D", "bose", START_ONR, u=U_INT, t=T_HOP)
+        p = orc.make_params(orc.STYLE_SEMISTOCHASTIC, shift=sp.shift, dtau=DTAU, compress_threshold=1.0, key=orc.step_key(args.seed, 0))
+        nsample = min(n_in, 20000)
+        t0 = time.time()
+        _, _, st = oh.step(p, hk[:nsample], hv[:nsample], threads=cores)
+        dt = time.time() - t0
+        rate = st.spawn_attempts / dt
+        nsample2 = int(min(n_in, max(nsample, nsample * 15.0 / max(dt, 1e-3))))
+        t0 = time.time()
+        _, _, st = oh.step(p, hk[:nsample2], hv[:nsample2], threads=cores)
+        dt = time.time() - t0
+        line["cpu_baseline"] = {"value": st.spawn_attempts / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"first {nsample2} of {n_in} determinants of the equilibrated GPU vector, one step, {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line))
+    for p in (hkp, hvp, okp, ovp):
+        _lib.lib().rimu_host_free(p)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        ours(a)

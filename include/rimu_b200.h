@@ -116,8 +116,10 @@ typedef struct {
     int64_t ispawns, ideaths, iclones, izombies, inorm1;
     int64_t local_len;        /* entries stored on this rank */
     int64_t sent_records;     /* records this rank sent to peers */
-    float ms_spawn, ms_exchange, ms_compact; /* CUDA-event phase timings of this call */
-    float ms_total;
+    int64_t deposits;         /* non-zero deposits into the working table (diagonal + spawns), global */
+    /* CUDA-event phase timings of this call: diagonal/count+scan, spawn kernel, exchange, compaction */
+    float ms_diag, ms_spawn, ms_exchange, ms_compact;
+    float ms_total, pad_;
 } rimu_step_stats;
 
 /* ---- context ------------------------------------------------------------ */
@@ -133,6 +135,11 @@ int rimu_ctx_table_slots(rimu_ctx *ctx, uint64_t *out);
 int rimu_ctx_resize_table(rimu_ctx *ctx, uint64_t table_slots);
 /* raw cudaStream_t of the context, for callers that want to time with their own events */
 int rimu_ctx_stream(rimu_ctx *ctx, void **stream_out);
+/* number of CUDA kernels this context has launched for rimu_step calls (benchmark bookkeeping) */
+int rimu_ctx_launch_count(rimu_ctx *ctx, uint64_t *out);
+/* pinned host memory for callers that stage vectors across PCIe (cudaMallocHost / cudaFreeHost) */
+int rimu_host_alloc(uint64_t bytes, void **out);
+int rimu_host_free(void *p);
 
 /* ---- multi-GPU: replaces DictVectors/communicators.jl AllToAll (:546-606),
  * mpi_exchange_alltoall! (:475-498) and merge_remote_reductions (:56) ------ */

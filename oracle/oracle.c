@@ -668,12 +668,10 @@ static int rec_cmp1(const void *a, const void *b) {
     return 0;
 }
 
-/* move_and_compress! (pdworkingmemory.jl:262-273, compression.jl:18-26) then export in
- * ascending key order.  Returns number of entries written (<= cap) or -needed. */
-static long map_export(orc_mapv *w, const orc_step_params *p, uint64_t *keys_out, void *vals_out,
-                       long cap, orc_step_stats *st) {
+/* move_and_compress! for one map (pdworkingmemory.jl:262-273, compression.jl:18-26): drops exact
+ * zeros, applies ThresholdCompression, collects survivors (unsorted) and partial statistics. */
+static long map_collect(const orc_mapv *w, const orc_step_params *p, orc_rec *recs, orc_step_stats *st) {
     int W = w->W, is_int = w->is_int;
-    orc_rec *recs = (orc_rec *)malloc(sizeof(orc_rec) * (w->count + 1));
     long n = 0, len_before = 0;
     uint32_t rnd[4];
     for (size_t s = 0; s < w->cap; s++) {
@@ -692,21 +690,32 @@ static long map_export(orc_mapv *w, const orc_step_params *p, uint64_t *keys_out
         recs[n].k[0] = w->keys[s * W]; recs[n].k[1] = W > 1 ? w->keys[s * W + 1] : 0; recs[n].v = v;
         n++;
     }
-    qsort(recs, n, sizeof(orc_rec), rec_cmp1);
     if (st) {
-        st->len_before = len_before; st->len_after = n;
+        st->len_before += len_before; st->len_after += n;
         for (long i = 0; i < n; i++) {
             if (is_int) st->inorm1 += recs[i].v.i < 0 ? -recs[i].v.i : recs[i].v.i;
             else st->norm1 += fabs(recs[i].v.f);
         }
     }
-    if (n > cap) { free(recs); return -n; }
+    return n;
+}
+static long recs_write(const orc_rec *recs, long n, int W, int is_int, uint64_t *keys_out, void *vals_out, long cap) {
+    if (n > cap) return -n;
     for (long i = 0; i < n; i++) {
         for (int j = 0; j < W; j++) keys_out[i * W + j] = recs[i].k[j];
         if (is_int) ((int64_t *)vals_out)[i] = recs[i].v.i; else ((double *)vals_out)[i] = recs[i].v.f;
     }
-    free(recs);
     return n;
+}
+/* serial export in ascending key order (canonical form for parity comparisons) */
+static long map_export(orc_mapv *w, const orc_step_params *p, uint64_t *keys_out, void *vals_out,
+                       long cap, orc_step_stats *st) {
+    orc_rec *recs = (orc_rec *)malloc(sizeof(orc_rec) * (w->count + 1));
+    long n = map_collect(w, p, recs, st);
+    qsort(recs, n, sizeof(orc_rec), rec_cmp1);
+    long r = recs_write(recs, n, w->W, w->is_int, keys_out, vals_out, cap);
+    free(recs);
+    return r;
 }
 
 /* apply_operator! (Interfaces/dictvectors.jl:112-140): serial semantics.
@@ -729,8 +738,10 @@ long orc_step(const orc_ham *h, const orc_step_params *p, long n, const uint64_t
 }
 
 /* Threaded restatement structured like the reference's PDVec path
- * (pdworkingmemory.jl:191-309): T segments by hash, each thread spawns its segment into a
- * private column of T row-maps, rows are merged, then compressed.  Used as cpu_baseline. */
+ * (pdworkingmemory.jl:191-309): the vector lives in T hash segments; thread t spawns segment t into
+ * its private column of T row-maps (perform_spawns!), row r is merged over columns
+ * (collect_local!), then compressed into segment r of the target (move_and_compress!).  Output is
+ * the concatenation of the segments (unsorted, as in the reference).  Used as cpu_baseline. */
 long orc_step_threaded(const orc_ham *h, const orc_step_params *p, long n, const uint64_t *keys,
                        const void *vals, uint64_t *keys_out, void *vals_out, long cap_out,
                        orc_step_stats *st, int T) {
@@ -740,43 +751,70 @@ long orc_step_threaded(const orc_ham *h, const orc_step_params *p, long n, const
     orc_mapv *grid = (orc_mapv *)malloc(sizeof(orc_mapv) * T * T); /* grid[col*T + row] */
     orc_step_stats *sts = (orc_step_stats *)calloc(T, sizeof(orc_step_stats));
     for (int i = 0; i < T * T; i++) mapv_init(&grid[i], W, is_int, (size_t)(n * 2 / (T * T)) + 64);
-    /* perform_spawns!: column t handles parents of segment t */
+    /* segment membership of the source vector (in the reference the PDVec is already stored that way) */
+    int32_t *seg = (int32_t *)malloc(sizeof(int32_t) * (n + 1));
+    long *seg_start = (long *)calloc(T + 1, sizeof(long));
+    long *order = (long *)malloc(sizeof(long) * (n + 1));
+#pragma omp parallel for num_threads(T) schedule(static)
+    for (long i = 0; i < n; i++) seg[i] = addr_owner(addr_hash(keys + i * W, W) << 32, T);
+    for (long i = 0; i < n; i++) seg_start[seg[i] + 1]++;
+    for (int t = 0; t < T; t++) seg_start[t + 1] += seg_start[t];
+    {
+        long *fill = (long *)malloc(sizeof(long) * T);
+        for (int t = 0; t < T; t++) fill[t] = seg_start[t];
+        for (long i = 0; i < n; i++) order[fill[seg[i]]++] = i;
+        free(fill);
+    }
+    /* perform_spawns! */
 #pragma omp parallel for num_threads(T) schedule(static, 1)
     for (int t = 0; t < T; t++) {
         orc_sink sink = {&grid[t * T], T};
-        for (long i = 0; i < n; i++) {
-            const uint64_t *k = keys + i * W;
-            if (addr_owner(addr_hash(k, W) << 32, T) != t) continue; /* segment by low hash bits */
+        for (long q = seg_start[t]; q < seg_start[t + 1]; q++) {
+            long i = order[q];
             orc_val v;
             if (is_int) v.i = ((const int64_t *)vals)[i]; else v.f = ((const double *)vals)[i];
-            apply_column(h, p, &sink, k, v, &sts[t]);
+            apply_column(h, p, &sink, keys + i * W, v, &sts[t]);
         }
     }
-    /* collect_local!: row r <- sum of columns */
+    /* collect_local! + move_and_compress! per row */
+    orc_rec **rows = (orc_rec **)calloc(T, sizeof(orc_rec *));
+    long *rown = (long *)calloc(T, sizeof(long));
+    orc_step_stats *cst = (orc_step_stats *)calloc(T, sizeof(orc_step_stats));
 #pragma omp parallel for num_threads(T) schedule(static, 1)
-    for (int r = 0; r < T; r++)
+    for (int r = 0; r < T; r++) {
         for (int c = 1; c < T; c++) {
             orc_mapv *src = &grid[c * T + r];
             for (size_t s = 0; s < src->cap; s++)
                 if (src->used[s]) mapv_add(&grid[r], src->keys + s * W, src->vals[s]);
         }
-    /* move_and_compress!: concatenate rows of the first column */
-    orc_mapv all; mapv_init(&all, W, is_int, 64);
-    for (int r = 0; r < T; r++) {
-        orc_mapv *src = &grid[r];
-        for (size_t s = 0; s < src->cap; s++) if (src->used[s]) mapv_add(&all, src->keys + s * W, src->vals[s]);
+        rows[r] = (orc_rec *)malloc(sizeof(orc_rec) * (grid[r].count + 1));
+        rown[r] = map_collect(&grid[r], p, rows[r], &cst[r]);
     }
+    long total = 0;
     for (int t = 0; t < T; t++) {
         st->exact_steps += sts[t].exact_steps; st->inexact_steps += sts[t].inexact_steps;
         st->spawn_attempts += sts[t].spawn_attempts;
         st->spawns += sts[t].spawns; st->deaths += sts[t].deaths; st->clones += sts[t].clones; st->zombies += sts[t].zombies;
         st->ispawns += sts[t].ispawns; st->ideaths += sts[t].ideaths; st->iclones += sts[t].iclones; st->izombies += sts[t].izombies;
+        st->len_before += cst[t].len_before; st->len_after += cst[t].len_after;
+        st->norm1 += cst[t].norm1; st->inorm1 += cst[t].inorm1;
+        total += rown[t];
     }
-    long r = map_export(&all, p, keys_out, vals_out, cap_out, st);
-    mapv_free(&all);
+    long ret = total;
+    if (total > cap_out) ret = -total;
+    else {
+        long off = 0;
+        for (int r = 0; r < T; r++) {
+            recs_write(rows[r], rown[r], W, is_int, keys_out + off * W,
+                       is_int ? (void *)((int64_t *)vals_out + off) : (void *)((double *)vals_out + off), rown[r]);
+            off += rown[r];
+        }
+    }
+    for (int r = 0; r < T; r++) free(rows[r]);
+    free(rows); free(rown); free(cst); free(seg); free(seg_start); free(order);
     for (int i = 0; i < T * T; i++) mapv_free(&grid[i]);
     free(grid); free(sts);
-    return r;
+    return ret;
 }
 
 /* annihilation of a given spawn list: sum by key, drop exact zeros, ascending key order */

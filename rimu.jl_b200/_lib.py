@@ -95,7 +95,9 @@ class StepStats(C.Structure):
         ("ispawns", C.c_int64), ("ideaths", C.c_int64), ("iclones", C.c_int64), ("izombies", C.c_int64),
         ("inorm1", C.c_int64),
         ("local_len", C.c_int64), ("sent_records", C.c_int64),
-        ("ms_spawn", C.c_float), ("ms_exchange", C.c_float), ("ms_compact", C.c_float), ("ms_total", C.c_float),
+        ("deposits", C.c_int64),
+        ("ms_diag", C.c_float), ("ms_spawn", C.c_float), ("ms_exchange", C.c_float), ("ms_compact", C.c_float),
+        ("ms_total", C.c_float), ("pad_", C.c_float),
     ]
 
     def asdict(self):
@@ -113,6 +115,9 @@ SYMBOLS = {
     "rimu_ctx_table_slots": (C.c_int, [_vp, _u64p]),
     "rimu_ctx_resize_table": (C.c_int, [_vp, C.c_uint64]),
     "rimu_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "rimu_ctx_launch_count": (C.c_int, [_vp, _u64p]),
+    "rimu_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
+    "rimu_host_free": (C.c_int, [_vp]),
     "rimu_comm_unique_id": (C.c_int, [_vp]),
     "rimu_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64]),
     "rimu_comm_rank": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -91,7 +91,8 @@ struct rimu_ctx {
     StatsDev *d_stats, *h_stats, *h_stats_local;
     u64 *local_off, *block_tot, *block_base;
     u64 scratch_parents;
-    cudaEvent_t ev[4];
+    cudaEvent_t ev[6];
+    unsigned long long launches; // kernels launched by this context (bench bookkeeping)
     // staging for host <-> device transfers
     u64 *stage_keys; void *stage_vals; u64 stage_cap;
     // comm
@@ -156,7 +157,7 @@ extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu
     CUDA_TRY(cudaMallocHost(&c->h_stats, sizeof(StatsDev)));
     CUDA_TRY(cudaMallocHost(&c->h_stats_local, sizeof(StatsDev)));
     CUDA_TRY(cudaMalloc(&c->d_reduce, 64 * sizeof(double)));
-    for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
     TRY(table_fill(c, c->table_slots));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out = c;
@@ -174,7 +175,7 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->xch.counts);
     cudaFree(c->recv_keys); cudaFree(c->recv_vals); cudaFree(c->d_allcounts); cudaFreeHost(c->h_allcounts);
     cudaFree(c->d_reduce);
-    for (int i = 0; i < 4; i++) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -182,6 +183,9 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
 extern "C" int rimu_ctx_synchronize(rimu_ctx *c) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
 extern "C" int rimu_ctx_table_slots(rimu_ctx *c, uint64_t *out) { *out = c->table_slots; return 0; }
 extern "C" int rimu_ctx_stream(rimu_ctx *c, void **s) { *s = (void *)c->stream; return 0; }
+extern "C" int rimu_ctx_launch_count(rimu_ctx *c, uint64_t *out) { *out = c->launches; return 0; }
+extern "C" int rimu_host_alloc(uint64_t bytes, void **out) { CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1)); return 0; }
+extern "C" int rimu_host_free(void *p) { if (p) CUDA_TRY(cudaFreeHost(p)); return 0; }
 extern "C" int rimu_ctx_resize_table(rimu_ctx *c, uint64_t table_slots) {
     CUDA_TRY(cudaSetDevice(c->device));
     u64 slots = next_pow2(table_slots < 1024 ? 1024 : table_slots);
@@ -760,6 +764,7 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out) {
             typedef decltype(vtag) VT;
             insert_records_kernel<decltype(tag)::w, VT><<<grid_for((i64)total_recv, c->sm_count), RIMU_TPB, 0, c->stream>>>(
                 c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, 0, 1, tab, c->d_stats);
+            c->launches += 1;
             return 0;
         }));
         CUDA_TRY(cudaGetLastError());
@@ -779,9 +784,13 @@ static int step_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec 
         diag_count_kernel<HK, W, VT><<<(unsigned)nblk, RIMU_TPB, 0, c->stream>>>(
             h->dev, p, src->keys, (const VT *)src->vals, n, tab, c->xch, c->local_off, c->block_tot, c->d_stats);
         scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(c->block_tot, nblk, c->block_base, c->d_stats);
+        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
         spawn_kernel<HK, W, VT><<<c->sm_count * 8, RIMU_TPB, 0, c->stream>>>(
             h->dev, p, src->keys, (const VT *)src->vals, n, c->block_base, c->local_off, tab, c->xch, c->d_stats);
         CUDA_TRY(cudaGetLastError());
+        c->launches += 3;
+    } else {
+        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
     }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     *sent = 0;
@@ -791,6 +800,7 @@ static int step_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec 
     }
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     TRY((compact_into<W, VT>(c, dst, slots, p)));
+    c->launches += 1;
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
     return 0;
 }
@@ -866,8 +876,9 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             out->len_before = g.len_before; out->len = g.len;
             out->spawns = g.spawns; out->deaths = g.deaths; out->clones = g.clones; out->zombies = g.zombies; out->norm1 = g.norm1;
             out->ispawns = g.ispawns; out->ideaths = g.ideaths; out->iclones = g.iclones; out->izombies = g.izombies; out->inorm1 = g.inorm1;
-            out->local_len = (i64)l.out_count; out->sent_records = sent;
-            cudaEventElapsedTime(&out->ms_spawn, c->ev[0], c->ev[1]);
+            out->local_len = (i64)l.out_count; out->sent_records = sent; out->deposits = g.deposits;
+            cudaEventElapsedTime(&out->ms_diag, c->ev[0], c->ev[4]);
+            cudaEventElapsedTime(&out->ms_spawn, c->ev[4], c->ev[1]);
             cudaEventElapsedTime(&out->ms_exchange, c->ev[1], c->ev[2]);
             cudaEventElapsedTime(&out->ms_compact, c->ev[2], c->ev[3]);
             cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[3]);

@@ -40,7 +40,7 @@ struct StatsDev {
     // block A: 16 x i64, summed over ranks
     i64 exact_steps, inexact_steps, spawn_attempts, len_before, len;
     i64 ispawns, ideaths, iclones, izombies, inorm1;
-    i64 sent;
+    i64 deposits; // non-zero deposits (diagonal + spawns) = table read-modify-writes
     i64 overflow_table, overflow_vec, overflow_xchg;
     u64 out_count;      // entries produced by compaction (may exceed capacity -> overflow_vec)
     u64 total_attempts; // written by the block-total scan
@@ -48,7 +48,7 @@ struct StatsDev {
     double spawns, deaths, clones, zombies, norm1;
     double dot, norm2, norminf; // scratch for dot / norms
 };
-#define RIMU_STATS_NI64 16
+#define RIMU_STATS_NI64 16 /* 'sent' was replaced by 'deposits' */
 #define RIMU_STATS_NF64_STEP 5
 
 struct TableDev {
@@ -205,7 +205,7 @@ diag_count_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
     i64 gid = (i64)blockIdx.x * RIMU_TPB + threadIdx.x;
     u64 cnt = 0;
     double clones = 0, deaths = 0, zombies = 0;
-    i64 exact_steps = 0, inexact_steps = 0;
+    i64 exact_steps = 0, inexact_steps = 0, ndep = 0;
     if (gid < n) {
         B key = load_key<W>(keys + gid * W);
         VT pv = vals[gid];
@@ -222,7 +222,7 @@ diag_count_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
             r = u53(rnd[1], rnd[2]);
         }
         VT res = project_value<VT>(d * val, thr, r);
-        if (res != (VT)0) deposit<W, VT>(tab, xch, p, st, key, res);
+        if (res != (VT)0) { deposit<W, VT>(tab, xch, p, st, key, res); ndep = 1; }
         // clones_deaths_zombies (spawning.jl:79-93)
         double rs = (double)res;
         if (rs > val) clones = fabs(rs - val);
@@ -252,7 +252,7 @@ diag_count_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
     } else {
         stat_add(&st->clones, clones); stat_add(&st->deaths, deaths); stat_add(&st->zombies, zombies);
     }
-    stat_add(&st->exact_steps, exact_steps); stat_add(&st->inexact_steps, inexact_steps);
+    stat_add(&st->exact_steps, exact_steps); stat_add(&st->inexact_steps, inexact_steps); stat_add(&st->deposits, ndep);
 }
 
 // ---------------------------------------------------------------- K2: exclusive scan of block totals (single CTA)
@@ -304,6 +304,7 @@ spawn_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, cons
     const u64 total = st->total_attempts;
     const i64 nblk = (n + RIMU_TPB - 1) / RIMU_TPB;
     double spawns = 0.0;
+    i64 ndep = 0;
     for (u64 tile = blockIdx.x; tile * RIMU_TILE < total; tile += gridDim.x) {
         const u64 t0 = tile * RIMU_TILE;
         const u64 t1 = min(t0 + (u64)RIMU_TILE, total);
@@ -375,7 +376,7 @@ spawn_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, cons
                     }
                     double nv = project_value<double>(val * m, p.proj_thr, r);
                     if (nv != 0.0) {
-                        if constexpr (!is_int) deposit<W, VT>(tab, xch, p, st, child, nv);
+                        if constexpr (!is_int) { deposit<W, VT>(tab, xch, p, st, child, nv); ndep++; }
                         spawns += fabs(nv);
                     }
                 } else { // spawn!(WithReplacement) spawning.jl:232-243
@@ -389,7 +390,7 @@ spawn_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, cons
                     double nv0 = m * magnitude / prob;
                     VT nv = project_value<VT>(nv0, is_int ? 0.0 : p.proj_thr, u53(rnd[1], rnd[2]));
                     if (nv != (VT)0) {
-                        deposit<W, VT>(tab, xch, p, st, child, nv);
+                        deposit<W, VT>(tab, xch, p, st, child, nv); ndep++;
                         spawns += fabs((double)nv);
                     }
                 }
@@ -401,6 +402,7 @@ spawn_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, cons
     }
     if (is_int) stat_add(&st->ispawns, (i64)spawns);
     else stat_add(&st->spawns, spawns);
+    stat_add(&st->deposits, ndep);
 }
 
 // ---------------------------------------------------------------- generic record insertion (exchange receive, upload, axpby)
