@@ -216,6 +216,7 @@ def ours(args):
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
+    torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` captures the timed steps only
     ev0.record(stream)
     tw0 = time.time()
     acc = dict(attempts=0, deposits=0, ms_diag=0.0, ms_spawn=0.0, ms_exch=0.0, ms_compact=0.0, parents=0, len_before=0, len=0)
@@ -227,6 +228,7 @@ def ours(args):
         acc["parents"] += parents; acc["len_before"] += s.len_before; acc["len"] += s.len
     ev1.record(stream)
     barrier()
+    torch.cuda.profiler.stop()
     wall = time.time() - tw0
     clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
