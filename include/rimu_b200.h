@@ -125,6 +125,10 @@ typedef struct {
 /* ---- context ------------------------------------------------------------ */
 const char *rimu_last_error(void);
 int rimu_version(void);
+/* struct sizes as compiled, so that FFI mirrors (Julia `struct`s, ctypes) can assert their layout */
+int rimu_sizeof_ham_desc(void);
+int rimu_sizeof_step_params(void);
+int rimu_sizeof_step_stats(void);
 /* table_slots: capacity of the working table in slots (rounded up to a power of two);
  * words: uint64 words per address (1 or 2). */
 int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu_ctx **out);

@@ -109,6 +109,9 @@ _vp, _u64p, _i64p, _f64p, _u32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C
 SYMBOLS = {
     "rimu_last_error": (C.c_char_p, []),
     "rimu_version": (C.c_int, []),
+    "rimu_sizeof_ham_desc": (C.c_int, []),
+    "rimu_sizeof_step_params": (C.c_int, []),
+    "rimu_sizeof_step_stats": (C.c_int, []),
     "rimu_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.POINTER(_vp)]),
     "rimu_ctx_destroy": (C.c_int, [_vp]),
     "rimu_ctx_synchronize": (C.c_int, [_vp]),

@@ -41,6 +41,9 @@ static int fail(int code, const char *fmt, ...) {
 
 extern "C" const char *rimu_last_error(void) { return g_err.c_str(); }
 extern "C" int rimu_version(void) { return 100; }
+extern "C" int rimu_sizeof_ham_desc(void) { return (int)sizeof(rimu_ham_desc); }
+extern "C" int rimu_sizeof_step_params(void) { return (int)sizeof(rimu_step_params); }
+extern "C" int rimu_sizeof_step_stats(void) { return (int)sizeof(rimu_step_stats); }
 
 // ---------------------------------------------------------------- NCCL (resolved lazily; same soname as torch's bundled copy)
 typedef struct ncclComm *ncclComm_t;
