@@ -55,7 +55,12 @@ enum { RIMU_VAL_F64 = 0, RIMU_VAL_I64 = 1 };
 /* StochasticStyles/styles.jl: IsDeterministic (:76-105), IsStochasticInteger (:11-25),
  * IsDynamicSemistochastic (:175-214), IsStochasticWithThreshold (:117-130) */
 enum { RIMU_STYLE_DETERMINISTIC = 0, RIMU_STYLE_INTEGER = 1, RIMU_STYLE_SEMISTOCHASTIC = 2, RIMU_STYLE_WITH_THRESHOLD = 3 };
-enum { RIMU_ANNIHILATE_HASH = 0, RIMU_ANNIHILATE_SORT = 1 };
+/* annihilation / step methods (north_star: chosen from measured HBM GB/s):
+ *   HASH      one open-addressing table in HBM, CAS claim + RED accumulate per deposit
+ *   SORT      radix sort by address + segmented reduce (deterministic summation order)
+ *   PARTITION spawns are appended to per-bucket record streams (bucket = fastrange of the address hash)
+ *             and every bucket is annihilated in shared memory; all HBM traffic is streaming (default) */
+enum { RIMU_ANNIHILATE_HASH = 0, RIMU_ANNIHILATE_SORT = 1, RIMU_ANNIHILATE_PARTITION = 2 };
 
 typedef struct rimu_ctx rimu_ctx;
 typedef struct rimu_ham rimu_ham;
@@ -120,6 +125,8 @@ typedef struct {
     /* CUDA-event phase timings of this call: diagonal/count+scan, spawn kernel, exchange, compaction */
     float ms_diag, ms_spawn, ms_exchange, ms_compact;
     float ms_total, pad_;
+    int64_t buckets;          /* bucket count of the partitioned step on this rank (0: table method) */
+    int64_t max_bucket_fill;  /* fullest bucket (parents + records) */
 } rimu_step_stats;
 
 /* ---- context ------------------------------------------------------------ */
@@ -141,6 +148,10 @@ int rimu_ctx_resize_table(rimu_ctx *ctx, uint64_t table_slots);
 int rimu_ctx_stream(rimu_ctx *ctx, void **stream_out);
 /* number of CUDA kernels this context has launched for rimu_step calls (benchmark bookkeeping) */
 int rimu_ctx_launch_count(rimu_ctx *ctx, uint64_t *out);
+/* step method of rimu_step: RIMU_ANNIHILATE_PARTITION (default) or RIMU_ANNIHILATE_HASH.  The environment
+ * variable RIMU_B200_METHOD=hash selects the table method at context creation. */
+int rimu_ctx_set_method(rimu_ctx *ctx, int method);
+int rimu_ctx_get_method(rimu_ctx *ctx, int *method);
 /* pinned host memory for callers that stage vectors across PCIe (cudaMallocHost / cudaFreeHost) */
 int rimu_host_alloc(uint64_t bytes, void **out);
 int rimu_host_free(void *p);
@@ -175,6 +186,12 @@ int rimu_vec_reserve(rimu_vec *v, uint64_t capacity);      /* grow, keeping cont
 int rimu_vec_clear(rimu_vec *v);                           /* zerovector!/empty! */
 int rimu_vec_length(rimu_vec *v, int64_t *out);            /* length(localpart(v)) */
 int rimu_vec_capacity(rimu_vec *v, uint64_t *out);
+/* bucket segmentation of the partitioned step: number of buckets the vector is currently
+ * segmented for (0 = none), and an explicit re-segmentation (contents unchanged; order changes) */
+int rimu_vec_buckets(rimu_vec *v, uint32_t *nb_out);
+int rimu_vec_rebucket(rimu_vec *v, uint32_t nb);
+/* copies seg_start[nb] / seg_len[nb] to the host (test hook: every bucket's entries are contiguous) */
+int rimu_vec_segments(rimu_vec *v, uint64_t *start_out, uint32_t *len_out);
 /* DVec(pairs...): duplicates are summed, zeros dropped (dvec.jl:62-100); with a communicator
  * attached, keys not owned by this rank are dropped (pdvec.jl:336-349) */
 int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n);

@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "librimu_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu"]
-HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh"]
+HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "--fmad=false", "-lineinfo",
@@ -31,7 +31,7 @@ ADDR_BOSE, ADDR_FERMI, ADDR_FERMI2C = 0, 1, 2
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3
 VAL_F64, VAL_I64 = 0, 1
 STYLE_DETERMINISTIC, STYLE_INTEGER, STYLE_SEMISTOCHASTIC, STYLE_WITH_THRESHOLD = 0, 1, 2, 3
-ANNIHILATE_HASH, ANNIHILATE_SORT = 0, 1
+ANNIHILATE_HASH, ANNIHILATE_SORT, ANNIHILATE_PARTITION = 0, 1, 2
 
 
 class RimuB200Error(RuntimeError):
@@ -98,6 +98,7 @@ class StepStats(C.Structure):
         ("deposits", C.c_int64),
         ("ms_diag", C.c_float), ("ms_spawn", C.c_float), ("ms_exchange", C.c_float), ("ms_compact", C.c_float),
         ("ms_total", C.c_float), ("pad_", C.c_float),
+        ("buckets", C.c_int64), ("max_bucket_fill", C.c_int64),
     ]
 
     def asdict(self):
@@ -119,6 +120,8 @@ SYMBOLS = {
     "rimu_ctx_resize_table": (C.c_int, [_vp, C.c_uint64]),
     "rimu_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
     "rimu_ctx_launch_count": (C.c_int, [_vp, _u64p]),
+    "rimu_ctx_set_method": (C.c_int, [_vp, C.c_int]),
+    "rimu_ctx_get_method": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rimu_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_vp)]),
     "rimu_host_free": (C.c_int, [_vp]),
     "rimu_comm_unique_id": (C.c_int, [_vp]),
@@ -139,6 +142,9 @@ SYMBOLS = {
     "rimu_vec_clear": (C.c_int, [_vp]),
     "rimu_vec_length": (C.c_int, [_vp, _i64p]),
     "rimu_vec_capacity": (C.c_int, [_vp, _u64p]),
+    "rimu_vec_buckets": (C.c_int, [_vp, C.POINTER(C.c_uint32)]),
+    "rimu_vec_rebucket": (C.c_int, [_vp, C.c_uint32]),
+    "rimu_vec_segments": (C.c_int, [_vp, _u64p, C.POINTER(C.c_uint32)]),
     "rimu_vec_upload": (C.c_int, [_vp, _u64p, _vp, C.c_int64]),
     "rimu_vec_assign": (C.c_int, [_vp, _u64p, _vp, C.c_int64]),
     "rimu_vec_download": (C.c_int, [_vp, _u64p, _vp, C.c_int64, _i64p]),

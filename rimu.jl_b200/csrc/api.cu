@@ -5,7 +5,7 @@
 //   synchronize_remote! -> count all-gather + grouped ncclSend/ncclRecv + insert_records_kernel
 //   move_and_compress!  -> compact_kernel (also walkernumber_and_length)
 #include "../../include/rimu_b200.h"
-#include "kernels.cuh"
+#include "partition.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -105,6 +105,14 @@ struct rimu_ctx {
     u64 *recv_keys, *recv_vals, recv_cap;
     u64 *d_allcounts, *h_allcounts;
     double *d_reduce;
+    // partitioned step (partition.cuh): bucket record streams, heavy-parent queue, re-segmentation scratch
+    int method;              // RIMU_ANNIHILATE_PARTITION (default) or RIMU_ANNIHILATE_HASH
+    PartDev part;
+    u64 part_nb_cap;         // buckets the record streams are allocated for
+    HeavyDev heavy;
+    u32 *bucket_tmp; u64 bucket_tmp_cap; // [2][nb] counts / fill
+    double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
+    u64 last_max_fill;
 };
 struct rimu_ham {
     rimu_ham_desc desc;
@@ -120,6 +128,11 @@ struct rimu_vec {
     i64 n;
     u64 *keys;
     void *vals;
+    // bucket segmentation (partition.cuh); nb == 0: not segmented
+    u32 nb;
+    u64 seg_cap;
+    u64 *seg_start;
+    u32 *seg_len;
 };
 
 static u64 next_pow2(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
@@ -150,6 +163,8 @@ extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu
     rimu_ctx *c = new rimu_ctx();
     memset(c, 0, sizeof(*c));
     c->device = device; c->W = words; c->nranks = 1; c->rank = 0;
+    c->method = RIMU_ANNIHILATE_PARTITION; c->rec_per_parent = 1.5;
+    if (const char *m = getenv("RIMU_B200_METHOD")) { if (!strcmp(m, "hash")) c->method = RIMU_ANNIHILATE_HASH; }
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -178,6 +193,8 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->xch.counts);
     cudaFree(c->recv_keys); cudaFree(c->recv_vals); cudaFree(c->d_allcounts); cudaFreeHost(c->h_allcounts);
     cudaFree(c->d_reduce);
+    cudaFree(c->part.rec_keys); cudaFree(c->part.rec_vals); cudaFree(c->part.rec_count);
+    cudaFree(c->heavy.items); cudaFree(c->heavy.packed); cudaFree(c->bucket_tmp);
     for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -187,6 +204,13 @@ extern "C" int rimu_ctx_synchronize(rimu_ctx *c) { CUDA_TRY(cudaStreamSynchroniz
 extern "C" int rimu_ctx_table_slots(rimu_ctx *c, uint64_t *out) { *out = c->table_slots; return 0; }
 extern "C" int rimu_ctx_stream(rimu_ctx *c, void **s) { *s = (void *)c->stream; return 0; }
 extern "C" int rimu_ctx_launch_count(rimu_ctx *c, uint64_t *out) { *out = c->launches; return 0; }
+extern "C" int rimu_ctx_set_method(rimu_ctx *c, int method) {
+    if (method != RIMU_ANNIHILATE_HASH && method != RIMU_ANNIHILATE_PARTITION)
+        return fail(RIMU_ERR_INVALID, "step method must be RIMU_ANNIHILATE_HASH or RIMU_ANNIHILATE_PARTITION");
+    c->method = method;
+    return 0;
+}
+extern "C" int rimu_ctx_get_method(rimu_ctx *c, int *method) { *method = c->method; return 0; }
 extern "C" int rimu_host_alloc(uint64_t bytes, void **out) { CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1)); return 0; }
 extern "C" int rimu_host_free(void *p) { if (p) CUDA_TRY(cudaFreeHost(p)); return 0; }
 extern "C" int rimu_ctx_resize_table(rimu_ctx *c, uint64_t table_slots) {
@@ -223,6 +247,49 @@ static int ensure_stage(rimu_ctx *c, u64 n) {
     CUDA_TRY(cudaMalloc(&c->stage_keys, cap * c->W * sizeof(u64)));
     CUDA_TRY(cudaMalloc(&c->stage_vals, cap * sizeof(u64)));
     c->stage_cap = cap;
+    return 0;
+}
+
+// ---- partitioned-step working memory
+static int ensure_seg(rimu_vec *v, u32 nb) {
+    if (nb <= v->seg_cap) return 0;
+    u64 cap = (u64)nb + nb / 2 + 64;
+    cudaFree(v->seg_start); cudaFree(v->seg_len);
+    v->seg_start = nullptr; v->seg_len = nullptr; v->seg_cap = 0; v->nb = 0;
+    CUDA_TRY(cudaMalloc(&v->seg_start, cap * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&v->seg_len, cap * sizeof(u32)));
+    v->seg_cap = cap;
+    return 0;
+}
+static u32 part_cap_items(int W) { return W == 1 ? (u32)PartCap<1>::value : (u32)PartCap<2>::value; }
+static size_t part_smem_bytes(int W) { u32 cap = part_cap_items(W); return (size_t)cap * W * 8 + (size_t)cap * 8 + (size_t)cap * 2 * 2; }
+static int ensure_part(rimu_ctx *c, u32 nb) {
+    c->part.rcap = part_cap_items(c->W);
+    if (nb <= c->part_nb_cap) { c->part.nb = nb; return 0; }
+    u64 cap = (u64)nb + nb / 4 + 16;
+    cudaFree(c->part.rec_keys); cudaFree(c->part.rec_vals); cudaFree(c->part.rec_count);
+    c->part.rec_keys = c->part.rec_vals = nullptr; c->part.rec_count = nullptr; c->part_nb_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->part.rec_keys, cap * c->part.rcap * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->part.rec_vals, cap * c->part.rcap * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->part.rec_count, cap * sizeof(u32)));
+    c->part_nb_cap = cap; c->part.nb = nb;
+    return 0;
+}
+static int ensure_heavy(rimu_ctx *c, u64 parents) {
+    if (!c->heavy.packed) CUDA_TRY(cudaMalloc(&c->heavy.packed, sizeof(u64)));
+    if (parents <= c->heavy.cap) return 0;
+    u64 cap = parents + parents / 4 + 1024;
+    cudaFree(c->heavy.items); c->heavy.items = nullptr; c->heavy.cap = 0;
+    CUDA_TRY(cudaMalloc(&c->heavy.items, cap * sizeof(HeavyItem)));
+    c->heavy.cap = cap;
+    return 0;
+}
+static int ensure_bucket_tmp(rimu_ctx *c, u32 nb) {
+    if (nb <= c->bucket_tmp_cap) return 0;
+    u64 cap = (u64)nb + nb / 2 + 64;
+    cudaFree(c->bucket_tmp); c->bucket_tmp = nullptr; c->bucket_tmp_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->bucket_tmp, 2 * cap * sizeof(u32)));
+    c->bucket_tmp_cap = cap;
     return 0;
 }
 
@@ -456,6 +523,7 @@ extern "C" int rimu_vec_create(rimu_ctx *c, int val_type, uint64_t capacity, rim
     rimu_vec *v = new rimu_vec();
     v->ctx = c; v->vt = val_type; v->n = 0; v->cap = capacity < 256 ? 256 : capacity;
     v->keys = nullptr; v->vals = nullptr;
+    v->nb = 0; v->seg_cap = 0; v->seg_start = nullptr; v->seg_len = nullptr;
     CUDA_TRY(cudaMalloc(&v->keys, v->cap * c->W * sizeof(u64)));
     CUDA_TRY(cudaMalloc(&v->vals, v->cap * sizeof(u64)));
     *out = v;
@@ -465,7 +533,7 @@ extern "C" int rimu_vec_destroy(rimu_vec *v) {
     if (!v) return 0;
     cudaSetDevice(v->ctx->device);
     cudaStreamSynchronize(v->ctx->stream);
-    cudaFree(v->keys); cudaFree(v->vals);
+    cudaFree(v->keys); cudaFree(v->vals); cudaFree(v->seg_start); cudaFree(v->seg_len);
     delete v;
     return 0;
 }
@@ -485,7 +553,7 @@ extern "C" int rimu_vec_reserve(rimu_vec *v, uint64_t capacity) {
     v->keys = nk; v->vals = nv; v->cap = capacity;
     return 0;
 }
-extern "C" int rimu_vec_clear(rimu_vec *v) { v->n = 0; return 0; }
+extern "C" int rimu_vec_clear(rimu_vec *v) { v->n = 0; v->nb = 0; return 0; }
 extern "C" int rimu_vec_length(rimu_vec *v, int64_t *out) { *out = v->n; return 0; }
 extern "C" int rimu_vec_capacity(rimu_vec *v, uint64_t *out) { *out = v->cap; return 0; }
 
@@ -521,6 +589,7 @@ static u64 pick_slots(rimu_ctx *c, u64 expected_entries) {
 static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
                           const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
     CUDA_TRY(cudaSetDevice(c->device));
+    dst->nb = 0; // the global-table path produces an unsegmented vector
     u64 slots = pick_slots(c, (u64)(n + n2));
     for (;;) {
         CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
@@ -560,7 +629,7 @@ static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const v
 extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (n <= 0) { v->n = 0; return 0; }
+    if (n <= 0) { v->n = 0; v->nb = 0; return 0; }
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->stage_vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -570,6 +639,7 @@ extern "C" int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *va
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     if (n < 0) return fail(RIMU_ERR_INVALID, "negative length");
+    v->nb = 0;
     if ((u64)n > v->cap) { v->n = 0; TRY(rimu_vec_reserve(v, (u64)n)); }
     if (n > 0) {
         CUDA_TRY(cudaMemcpyAsync(v->keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -607,6 +677,13 @@ extern "C" int rimu_vec_copy(rimu_vec *dst, rimu_vec *src) {
         }
     }
     dst->n = src->n;
+    dst->nb = 0;
+    if (src->nb) { // keep the bucket segmentation
+        TRY(ensure_seg(dst, src->nb));
+        CUDA_TRY(cudaMemcpyAsync(dst->seg_start, src->seg_start, src->nb * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(dst->seg_len, src->seg_len, src->nb * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
+        dst->nb = src->nb;
+    }
     return 0;
 }
 extern "C" int rimu_vec_get(rimu_vec *v, const uint64_t *key, void *val_out) {
@@ -657,7 +734,7 @@ extern "C" int rimu_vec_norm(rimu_vec *v, int p, double *out) {
 extern "C" int rimu_vec_scale(rimu_vec *v, double alpha) {
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (alpha == 0.0) { v->n = 0; return 0; } // zero values are never stored
+    if (alpha == 0.0) { v->n = 0; v->nb = 0; return 0; } // zero values are never stored
     if (v->n > 0) {
         if (v->vt == RIMU_VAL_F64) scale_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((double *)v->vals, v->n, alpha);
         else scale_kernel<i64><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((i64 *)v->vals, v->n, alpha);
@@ -724,7 +801,7 @@ extern "C" int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, con
 extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *vals, int64_t n, int method) {
     rimu_ctx *c = dst->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (n <= 0) { dst->n = 0; return 0; }
+    if (n <= 0) { dst->n = 0; dst->nb = 0; return 0; }
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->stage_vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -732,7 +809,7 @@ extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *
 }
 
 // ---------------------------------------------------------------- the step
-static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out) {
+static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_streams) {
     const int R = c->nranks, me = c->rank;
     NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_allcounts, c->d_allcounts, (size_t)R * R * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
@@ -765,8 +842,12 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out) {
         TableDev tab{c->table, slots - 1};
         TRY(dispatch_wv(c->W, vt, [&](auto tag, auto vtag) {
             typedef decltype(vtag) VT;
-            insert_records_kernel<decltype(tag)::w, VT><<<grid_for((i64)total_recv, c->sm_count), RIMU_TPB, 0, c->stream>>>(
-                c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, 0, 1, tab, c->d_stats);
+            if (to_streams) // partitioned step: received records join this rank's bucket streams
+                append_records_kernel<decltype(tag)::w, VT><<<grid_for((i64)total_recv, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                    c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, c->rank, c->nranks, c->part, c->d_stats);
+            else
+                insert_records_kernel<decltype(tag)::w, VT><<<grid_for((i64)total_recv, c->sm_count), RIMU_TPB, 0, c->stream>>>(
+                    c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, 0, 1, tab, c->d_stats);
             c->launches += 1;
             return 0;
         }));
@@ -798,14 +879,119 @@ static int step_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec 
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     *sent = 0;
     if (c->nranks > 1) {
-        int r = exchange_spawns(c, dst->vt, slots, sent);
+        int r = exchange_spawns(c, dst->vt, slots, sent, false);
         if (r) return r;
     }
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     TRY((compact_into<W, VT>(c, dst, slots, p)));
     c->launches += 1;
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    dst->nb = 0;
     return 0;
+}
+
+// ---- partitioned step (partition.cuh)
+// re-segment a vector for `nb` buckets (count, scan, scatter into fresh arrays); contents are unchanged
+static int rebucket(rimu_vec *v, u32 nb) {
+    rimu_ctx *c = v->ctx;
+    TRY(ensure_seg(v, nb));
+    if (v->n == 0) {
+        CUDA_TRY(cudaMemsetAsync(v->seg_start, 0, nb * sizeof(u64), c->stream));
+        CUDA_TRY(cudaMemsetAsync(v->seg_len, 0, nb * sizeof(u32), c->stream));
+        v->nb = nb;
+        return 0;
+    }
+    TRY(ensure_bucket_tmp(c, nb));
+    u32 *counts = c->bucket_tmp, *fill = c->bucket_tmp + c->bucket_tmp_cap;
+    CUDA_TRY(cudaMemsetAsync(counts, 0, nb * sizeof(u32), c->stream));
+    u64 *nk = nullptr, *nv = nullptr;
+    CUDA_TRY(cudaMalloc(&nk, v->cap * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&nv, v->cap * sizeof(u64)));
+    const int grid = grid_for(v->n, c->sm_count, 16);
+    if (c->W == 1) bucket_count_kernel<1><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, v->n, c->nranks, nb, counts);
+    else bucket_count_kernel<2><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, v->n, c->nranks, nb, counts);
+    bucket_scan_kernel<<<1, 1024, 0, c->stream>>>(counts, nb, v->seg_start, v->seg_len, fill);
+    if (c->W == 1) bucket_scatter_kernel<1><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, (const u64 *)v->vals, v->n, c->nranks, nb, v->seg_start, fill, nk, nv);
+    else bucket_scatter_kernel<2><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, (const u64 *)v->vals, v->n, c->nranks, nb, v->seg_start, fill, nk, nv);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(v->keys); cudaFree(v->vals);
+    v->keys = nk; v->vals = nv; v->nb = nb;
+    return 0;
+}
+
+// testing / tuning hook: re-segment a vector for `nb` buckets (0 drops the segmentation)
+extern "C" int rimu_vec_rebucket(rimu_vec *v, uint32_t nb) {
+    CUDA_TRY(cudaSetDevice(v->ctx->device));
+    if (nb == 0) { v->nb = 0; return 0; }
+    return rebucket(v, nb);
+}
+extern "C" int rimu_vec_buckets(rimu_vec *v, uint32_t *nb) { *nb = v->nb; return 0; }
+extern "C" int rimu_vec_segments(rimu_vec *v, uint64_t *start_out, uint32_t *len_out) {
+    rimu_ctx *c = v->ctx;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (v->nb) {
+        CUDA_TRY(cudaMemcpyAsync(start_out, v->seg_start, v->nb * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(len_out, v->seg_len, v->nb * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+template <int HK, int W, class VT>
+static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, u32 nb, i64 *sent) {
+    const i64 n = src->n;
+    if (src->nb != nb) TRY(rebucket(src, nb));
+    TRY(ensure_seg(dst, nb));
+    TRY(ensure_part(c, nb));
+    TRY(ensure_heavy(c, (u64)n));
+    static bool attr_set[HK_COUNT][3][2] = {};
+    if (!attr_set[HK][W][std::is_integral<VT>::value]) {
+        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
+        attr_set[HK][W][std::is_integral<VT>::value] = true;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->part.rec_count, 0, nb * sizeof(u32), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->heavy.packed, 0, sizeof(u64), c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
+    if (n > 0) {
+        const i64 nchunks = (n + SPAWN_NT - 1) / SPAWN_NT;
+        const int grid = (int)(nchunks < (i64)c->sm_count * 8 ? nchunks : (i64)c->sm_count * 8);
+        spawn_part_kernel<HK, W, VT><<<grid, SPAWN_NT, 0, c->stream>>>(
+            h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->xch, c->heavy, c->d_stats);
+        spawn_heavy_kernel<HK, W, VT><<<c->sm_count * 4, SPAWN_NT, 0, c->stream>>>(
+            h->dev, p, src->keys, (const VT *)src->vals, c->part, c->xch, c->heavy, c->d_stats);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 2;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+    *sent = 0;
+    if (c->nranks > 1) {
+        int r = exchange_spawns(c, dst->vt, 0, sent, true);
+        if (r) return r;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+    SegSrc ss{src->keys, (const u64 *)src->vals, src->seg_start, src->seg_len};
+    SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap};
+    const int mgrid = (int)(nb < (u32)c->sm_count * 16 ? nb : (u32)c->sm_count * 16);
+    merge_kernel<HK, W, VT, 0><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+    return 0;
+}
+
+// bucket count for a step on `n` local parents
+static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src) {
+    const double cap = (double)part_cap_items(c->W);
+    const double expected = (double)src->n * (1.0 + c->rec_per_parent) * 1.15 + 512.0;
+    if (src->nb) { // keep the segmentation while the expected fill stays in a comfortable band
+        double fill = expected / src->nb;
+        if (fill > 0.15 * cap && fill < 0.62 * cap) return src->nb;
+    }
+    double nb = ceil(expected / (0.45 * cap));
+    return nb < 1.0 ? 1u : (u32)nb;
 }
 
 extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params *prm, rimu_vec *src, rimu_vec *dst,
@@ -831,18 +1017,32 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
     p.k0 = key[0]; p.k1 = key[1];
     p.rank = c->rank; p.nranks = c->nranks;
 
+    bool use_part = c->method == RIMU_ANNIHILATE_PARTITION;
     u64 slots = prm->table_slots ? next_pow2(prm->table_slots) : pick_slots(c, (u64)src->n * 2 + (u64)dst->n);
     if (slots > c->table_slots) slots = c->table_slots;
+    u32 nb = use_part ? choose_buckets(c, src) : 0;
+    // record-stream memory budget: beyond it this step falls back to the global HBM table
+    size_t free_b = 0, total_b = 0;
+    const double rec_bytes_per_bucket = (double)part_cap_items(c->W) * (8.0 * c->W + 8.0);
     i64 sent = 0;
     for (int attempt = 0;; attempt++) {
+        if (use_part && nb > c->part_nb_cap) {
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            double have = (double)free_b + (double)c->part_nb_cap * rec_bytes_per_bucket;
+            if ((double)nb * 1.3 * rec_bytes_per_bucket > 0.8 * have) use_part = false;
+        }
         int r = dispatch_ham(h, [&](auto tag) {
             constexpr int HK = decltype(tag)::hk, W = decltype(tag)::w;
+            if (use_part) {
+                if (is_int) return step_part_once<HK, W, i64>(c, h, p, src, dst, nb, &sent);
+                return step_part_once<HK, W, double>(c, h, p, src, dst, nb, &sent);
+            }
             if (is_int) return step_once<HK, W, i64>(c, h, p, src, dst, slots, &sent);
             return step_once<HK, W, double>(c, h, p, src, dst, slots, &sent);
         });
         if (r == RIMU_ERR_EXCHANGE_FULL) {
             // nothing was sent; drain what this rank deposited locally, then report
-            TRY(table_fill(c, slots));
+            if (!use_part) TRY(table_fill(c, slots));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             return fail(RIMU_ERR_EXCHANGE_FULL, "per-peer exchange buffer (%llu records) too small", (unsigned long long)c->xch.cap);
         }
@@ -856,7 +1056,17 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const StatsDev &g = *c->h_stats, &l = *c->h_stats_local;
-        if (g.overflow_table) { // some rank ran out of probe budget: every rank retries with a larger active table
+        if (g.overflow_table) { // some rank ran out of room: every rank retries with more working memory
+            if (attempt > 12) return fail(RIMU_ERR_TABLE_FULL, "step working memory cannot be grown further");
+            if (use_part) {
+                // size the bucket count from what this attempt saw (records are counted even when dropped)
+                const double cap = (double)part_cap_items(c->W);
+                double need = ceil(((double)src->n + (double)l.records) * 1.15 / (0.45 * cap));
+                u32 nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb * 2 + 1);
+                if (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26)) use_part = false; // one address is too hot to pre-sum: use the table
+                nb = nb2;
+                continue;
+            }
             if (slots >= c->table_slots)
                 return fail(RIMU_ERR_TABLE_FULL, "working table (%llu slots) too small for this step", (unsigned long long)c->table_slots);
             slots = slots * 4 > c->table_slots ? c->table_slots : slots * 4;
@@ -867,12 +1077,17 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         double flag = need_local > dst->cap ? 1.0 : 0.0;
         if (c->nranks > 1) TRY(rimu_comm_allreduce_f64(c, &flag, 1));
         if (flag > 0.0) {
-            dst->n = 0;
+            dst->n = 0; dst->nb = 0;
             if (need_local > dst->cap) TRY(rimu_vec_reserve(dst, need_local + need_local / 4 + 1024));
-            if (attempt > 8) return fail(RIMU_ERR_VECTOR_FULL, "destination vector cannot be grown");
+            if (attempt > 12) return fail(RIMU_ERR_VECTOR_FULL, "destination vector cannot be grown");
             continue;
         }
         dst->n = (i64)l.out_count;
+        dst->nb = use_part ? nb : 0;
+        if (use_part) {
+            if (src->n > 0) c->rec_per_parent = 0.5 * c->rec_per_parent + 0.5 * ((double)l.records / (double)src->n);
+            c->last_max_fill = l.max_fill;
+        }
         if (out) {
             memset(out, 0, sizeof(*out));
             out->exact_steps = g.exact_steps; out->inexact_steps = g.inexact_steps; out->spawn_attempts = g.spawn_attempts;
@@ -885,6 +1100,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             cudaEventElapsedTime(&out->ms_exchange, c->ev[1], c->ev[2]);
             cudaEventElapsedTime(&out->ms_compact, c->ev[2], c->ev[3]);
             cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[3]);
+            out->buckets = use_part ? (int64_t)nb : 0; out->max_bucket_fill = (int64_t)l.max_fill;
         }
         return 0;
     }

@@ -50,6 +50,12 @@ template <int W> HD u64 addr_hash(const u64 *w) {
     u64 h = 0x9E3779B97F4A7C15ULL;
 #pragma unroll
     for (int j = 0; j < W; j++) h = fmix64(h ^ w[j]);
+#ifdef __CUDA_ARCH__
+    // nvcc 12.9 (sm_100a, -O3) miscompiles `(u32)(h >> 32) * m` when it fuses it into the final 64-bit
+    // multiply of fmix64 (scratch/t_hash.cu reproduces it: the fused form drops the cross terms of the
+    // product).  Materialising h in a register pair keeps the hash and its consumers separate.
+    asm volatile("" : "+l"(h));
+#endif
     return h;
 }
 

@@ -47,6 +47,9 @@ struct StatsDev {
     // block B: 8 x double (first 5 summed over ranks by the step)
     double spawns, deaths, clones, zombies, norm1;
     double dot, norm2, norminf; // scratch for dot / norms
+    // block C: local bookkeeping of the partitioned step (never reduced over ranks)
+    u64 max_fill;       // fullest bucket (parents + records) seen by merge_kernel
+    u64 records;        // spawn records appended to this rank's bucket streams
 };
 #define RIMU_STATS_NI64 16 /* 'sent' was replaced by 'deposits' */
 #define RIMU_STATS_NF64_STEP 5

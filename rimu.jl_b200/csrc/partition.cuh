@@ -1,0 +1,504 @@
+// partition.cuh -- the partitioned FCIQMC step: bucket streams in HBM + shared-memory annihilation.
+//
+// Why (profiles/r1_baseline_ncu_summary.md): random read-modify-writes into one big HBM hash table are
+// latency-bound (10-20 % of DRAM throughput) and move 4x the algorithmic bytes.  Here every HBM access is
+// a stream:
+//
+//   walker vector : dense SoA (keys[n][W], vals[n]) that is SEGMENTED by bucket: the entries of bucket b
+//                   are contiguous at [seg_start[b], seg_start[b]+seg_len[b]).  bucket(addr) is a fastrange
+//                   of the address hash, so a determinant always lives in the same bucket.
+//   K1 spawn      : one CTA per chunk of 256 parents; attempt counts are scanned inside the CTA and the
+//                   attempts are spread over its threads (one thread per spawn attempt).  Every non-zero
+//                   spawn is appended to the record stream of the CHILD's bucket (one 16/24-byte store and
+//                   one counter atomic).  Parents with more than HEAVY_T attempts go to a queue.
+//   K2 heavy      : queue items are cut into tiles of HEAVY_TILE attempts, one CTA per tile; stochastic
+//                   spawns of one parent are pre-summed per off-diagonal index in shared memory, so a
+//                   determinant with 10^6 walkers emits at most L records per tile.
+//   K3 merge      : one CTA per bucket stages the bucket's parents (applying the diagonal step,
+//                   spawning.jl:73-93) and its spawn records in shared memory, annihilates them there
+//                   (open addressing on 16-bit item indices, claimed by plain stores in barrier-separated
+//                   rounds -- no 64-bit shared atomics except for genuine duplicates), applies
+//                   ThresholdCompression (compression.jl:18-26) and appends the survivors to the target
+//                   vector, which is thereby segmented again.  walkernumber/length and the step statistics
+//                   are reduced in the same pass (pdvec.jl:896-902).
+//
+// Algorithmic HBM bytes per step with P parents, A' records, U survivors, E = 8W+8:
+//   K1: P*E read + A'*E written;  K3: P*E + A'*E read, U*E written.
+#pragma once
+#include "kernels.cuh"
+
+#define PART_NT 512        // threads of a merge CTA
+#define SPAWN_NT 256       // threads (= parents per chunk) of a spawn CTA
+#define HEAVY_T 1024       // parents with more attempts than this are queued for K2
+#define HEAVY_TILE 8192    // attempts per K2 work item
+#define ACC_MAX 4096       // K2 pre-sums per off-diagonal index when L <= ACC_MAX
+
+template <int W> struct PartCap { static constexpr int value = W == 1 ? 4096 : 2048; };
+
+struct PartDev {       // bucket record streams (working memory of the partitioned step)
+    u32 nb;            // buckets on this rank
+    u32 rcap;          // records per bucket stream
+    u64 *rec_keys;     // [nb][rcap][W]
+    u64 *rec_vals;     // [nb][rcap]
+    u32 *rec_count;    // [nb]
+};
+struct SegSrc {        // a segmented vector, read side
+    const u64 *keys; const u64 *vals; const u64 *seg_start; const u32 *seg_len;
+};
+struct SegDst {        // a segmented vector, write side
+    u64 *keys; u64 *vals; u64 *seg_start; u32 *seg_len; u64 cap;
+};
+struct HeavyItem { i64 parent; u64 nattempts; u64 tile_base; u64 exact; };
+struct HeavyDev { HeavyItem *items; u64 *packed; /* (count << 32) | tiles */ u64 cap; };
+
+#ifdef __CUDACC__
+// local bucket of an address hash.  The owner rank is the integer part of x*R/2^32 (addr_owner); the
+// bucket is a fastrange of the fractional part, so it is uniform within every rank's share.
+DEV u32 bucket_of(u64 h, int nranks, u32 nb) {
+    u32 x = (u32)(h >> 32);
+    u32 y = nranks > 1 ? x * (u32)nranks : x;
+    return __umulhi(y, nb);
+}
+
+template <int W, class VT>
+DEV void append_record(const PartDev &pt, StatsDev *st, typename BitsT<W>::type key, u64 h, int nranks, VT v) {
+    u32 b = bucket_of(h, nranks, pt.nb);
+    u32 pos = atomicAdd(&pt.rec_count[b], 1u);
+    if (pos < pt.rcap) {
+        u64 at = (u64)b * pt.rcap + pos;
+        store_key<W>(pt.rec_keys + at * W, key);
+        union { VT v; u64 b; } cv; cv.v = v;
+        pt.rec_vals[at] = cv.b;
+    } else st->overflow_table = 1;
+}
+
+// route one spawn: the child's bucket stream on this rank, or the owner's exchange segment
+template <int W, class VT>
+DEV void emit_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p, StatsDev *st,
+                     typename BitsT<W>::type key, VT v) {
+    u64 h = hash_bits(key);
+    if (p.nranks > 1) {
+        int owner = addr_owner(h, p.nranks);
+        if (owner != p.rank) {
+            u64 idx = atomicAdd(&x.counts[owner], 1ull);
+            if (idx < x.cap) {
+                store_key<W>(x.keys + ((u64)owner * x.cap + idx) * W, key);
+                union { VT v; u64 b; } cv; cv.v = v;
+                x.vals[(u64)owner * x.cap + idx] = cv.b;
+            } else st->overflow_xchg = 1;
+            return;
+        }
+    }
+    append_record<W, VT>(pt, st, key, h, p.nranks, v);
+}
+
+// one spawn attempt k of a parent (spawning.jl:174-182 Exact, :232-243 WithReplacement).
+// Returns the value to deposit (0 = nothing); ci = off-diagonal index used, child = its address.
+template <int HK, int W, class VT>
+DEV VT spawn_attempt(const HamDev &h, const StepDev &p, typename BitsT<W>::type key, u64 hkey, double val,
+                     long long L, u64 nat, bool exact, u64 k, typename BitsT<W>::type &child, long long &ci,
+                     double &spawned) {
+    typedef typename BitsT<W>::type B;
+    constexpr bool is_int = std::is_integral<VT>::value;
+    if (exact) {
+        ci = (long long)k;
+        double m = ham_offdiagonal<HK, B>(h, key, ci, child);
+        if (!p.plain_h) m = -m * p.dtau;
+        double r = 0.0;
+        if (p.proj_thr > 0.0) {
+            u32 rnd[4];
+            rng_draw(hkey, k, STREAM_SPAWN, p.k0, p.k1, rnd);
+            r = u53(rnd[1], rnd[2]);
+        }
+        double nv = project_value<double>(val * m, p.proj_thr, r);
+        spawned = fabs(nv);
+        if constexpr (is_int) return (VT)0; else return nv;
+    }
+    u32 rnd[4];
+    rng_draw(hkey, k, STREAM_SPAWN, p.k0, p.k1, rnd);
+    ci = (long long)(((u64)rnd[0] * (u64)L) >> 32);
+    double m = ham_offdiagonal<HK, B>(h, key, ci, child);
+    if (!p.plain_h) m = -m * p.dtau;
+    double magnitude = val / (double)nat;
+    double prob = 1.0 / (double)L;
+    double nv0 = m * magnitude / prob;
+    VT nv = project_value<VT>(nv0, is_int ? 0.0 : p.proj_thr, u53(rnd[1], rnd[2]));
+    spawned = fabs((double)nv);
+    return nv;
+}
+
+// ---------------------------------------------------------------- K1: spawning, CTA-local work distribution
+template <int HK, int W, class VT>
+__global__ void __launch_bounds__(SPAWN_NT)
+spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
+                  PartDev pt, ExchangeDev xch, HeavyDev hv, StatsDev *st) {
+    typedef typename BitsT<W>::type B;
+    __shared__ u32 s_off[SPAWN_NT + 1];
+    __shared__ u64 s_keys[SPAWN_NT * W];
+    __shared__ VT s_vals[SPAWN_NT];
+    __shared__ u32 s_warp[SPAWN_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double spawns = 0.0;
+    i64 exact_steps = 0, inexact_steps = 0, attempts = 0;
+    const i64 nchunks = (n + SPAWN_NT - 1) / SPAWN_NT;
+    for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const i64 j = chunk * SPAWN_NT + tid;
+        u32 cnt = 0;
+        if (j < n) {
+            B key = load_key<W>(keys + j * W);
+            VT pv = vals[j];
+            long long L = ham_num_offdiagonals<HK, B>(h, key);
+            u64 c64;
+            bool exact = attempts_for(p, (double)pv, L, c64);
+            if (c64) { if (exact) exact_steps++; else inexact_steps++; }
+            attempts += (i64)c64;
+            if (c64 > HEAVY_T) {
+                u64 ntiles = (c64 + HEAVY_TILE - 1) / HEAVY_TILE;
+                u64 old = atomicAdd(hv.packed, (1ull << 32) | ntiles);
+                u64 idx = old >> 32;
+                if (idx < hv.cap) { HeavyItem it; it.parent = j; it.nattempts = c64; it.tile_base = old & 0xffffffffull; it.exact = exact; hv.items[idx] = it; }
+                else st->overflow_table = 1;
+                c64 = 0;
+            }
+            cnt = (u32)c64;
+            s_keys[tid * W] = (u64)key;
+            if constexpr (W == 2) s_keys[tid * W + 1] = (u64)(key >> 64);
+            s_vals[tid] = pv;
+        }
+        // CTA exclusive scan of cnt
+        u32 incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        u32 base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SPAWN_NT / 32; w++) { u32 t = s_warp[w]; if (w < wid) base += t; total += t; }
+        s_off[tid] = base + incl - cnt;
+        if (tid == 0) s_off[SPAWN_NT] = total;
+        __syncthreads();
+        for (u32 a = tid; a < total; a += SPAWN_NT) {
+            int lo = 0, hi = SPAWN_NT; // last lo with s_off[lo] <= a
+#pragma unroll
+            for (int it = 0; it < 8; it++) { int mid = (lo + hi) >> 1; if (s_off[mid] <= a) lo = mid; else hi = mid; }
+            const u64 k = a - s_off[lo];
+            B key;
+            if constexpr (W == 1) key = s_keys[lo]; else key = ((u128)s_keys[lo * 2 + 1] << 64) | (u128)s_keys[lo * 2];
+            const double val = (double)s_vals[lo];
+            const long long L = ham_num_offdiagonals<HK, B>(h, key);
+            u64 nat;
+            const bool exact = attempts_for(p, val, L, nat);
+            B child; long long ci; double sp;
+            VT nv = spawn_attempt<HK, W, VT>(h, p, key, hash_bits(key), val, L, nat, exact, k, child, ci, sp);
+            spawns += sp;
+            if (nv != (VT)0) emit_record<W, VT>(pt, xch, p, st, child, nv);
+        }
+        __syncthreads();
+    }
+    if (std::is_integral<VT>::value) stat_add(&st->ispawns, (i64)spawns); else stat_add(&st->spawns, spawns);
+    stat_add(&st->exact_steps, exact_steps); stat_add(&st->inexact_steps, inexact_steps);
+    stat_add(&st->spawn_attempts, attempts);
+}
+
+// ---------------------------------------------------------------- K2: heavy parents, one CTA per tile of attempts
+template <int HK, int W, class VT>
+__global__ void __launch_bounds__(SPAWN_NT)
+spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals,
+                   PartDev pt, ExchangeDev xch, HeavyDev hv, StatsDev *st) {
+    typedef typename BitsT<W>::type B;
+    __shared__ u64 acc[ACC_MAX];
+    const u64 packed = *hv.packed;
+    const u64 total = packed & 0xffffffffull;
+    u64 nitems = packed >> 32;
+    if (nitems > hv.cap) nitems = hv.cap;
+    double spawns = 0.0;
+    for (u64 w = blockIdx.x; w < total; w += gridDim.x) {
+        u64 lo = 0, hi = nitems;
+        while (hi - lo > 1) { u64 mid = (lo + hi) >> 1; if (hv.items[mid].tile_base <= w) lo = mid; else hi = mid; }
+        const HeavyItem it = hv.items[lo];
+        const u64 a0 = (w - it.tile_base) * HEAVY_TILE;
+        const u64 a1 = min(a0 + (u64)HEAVY_TILE, it.nattempts);
+        const B key = load_key<W>(keys + it.parent * W);
+        const double val = (double)vals[it.parent];
+        const long long L = ham_num_offdiagonals<HK, B>(h, key);
+        const bool exact = it.exact != 0;
+        const bool agg = !exact && L <= ACC_MAX;
+        const u64 hkey = hash_bits(key);
+        if (agg) { for (int c = threadIdx.x; c < L; c += SPAWN_NT) acc[c] = 0ull; __syncthreads(); }
+        for (u64 a = a0 + threadIdx.x; a < a1; a += SPAWN_NT) {
+            B child; long long ci; double sp;
+            VT nv = spawn_attempt<HK, W, VT>(h, p, key, hkey, val, L, it.nattempts, exact, a, child, ci, sp);
+            spawns += sp;
+            if (nv != (VT)0) {
+                if (agg) atomic_add_val<VT>(&acc[ci], nv);
+                else emit_record<W, VT>(pt, xch, p, st, child, nv);
+            }
+        }
+        if (agg) {
+            __syncthreads();
+            for (int c = threadIdx.x; c < L; c += SPAWN_NT) {
+                union { u64 b; VT v; } cv; cv.b = acc[c];
+                if (cv.v != (VT)0) { B child; ham_offdiagonal<HK, B>(h, key, c, child); emit_record<W, VT>(pt, xch, p, st, child, cv.v); }
+            }
+            __syncthreads();
+        }
+    }
+    if (std::is_integral<VT>::value) stat_add(&st->ispawns, (i64)spawns); else stat_add(&st->spawns, spawns);
+}
+
+// ---------------------------------------------------------------- append a flat record list to the bucket streams
+// (received exchange records, uploads, linear combinations).  Non-local keys are dropped (pdvec.jl:336-349).
+template <int W, class VT>
+__global__ void __launch_bounds__(RIMU_TPB)
+append_records_kernel(const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n, double scale, int use_scale,
+                      int rank, int nranks, PartDev pt, StatsDev *st) {
+    typedef typename BitsT<W>::type B;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        B key = load_key<W>(keys + i * W);
+        VT v = vals[i];
+        if (use_scale) v = (VT)(scale * (double)v);
+        if (v == (VT)0) continue;
+        u64 hh = hash_bits(key);
+        if (nranks > 1 && addr_owner(hh, nranks) != rank) continue;
+        append_record<W, VT>(pt, st, key, hh, nranks, v);
+    }
+}
+
+// ---------------------------------------------------------------- K3: per-bucket annihilation in shared memory
+// MODE 0: FCIQMC step (diagonal step on the parents, compression);  MODE 1: plain sum of records (+ alpha * parents)
+template <int HK, int W, class VT, int MODE>
+__global__ void __launch_bounds__(PART_NT)
+merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st) {
+    typedef typename BitsT<W>::type B;
+    constexpr bool is_int = std::is_integral<VT>::value;
+    constexpr int CAP = PartCap<W>::value;
+    constexpr int R = CAP / PART_NT;
+    constexpr u32 TMASK = 2 * CAP - 1;
+    constexpr u32 NIL = 0xffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *skeys = reinterpret_cast<u64 *>(smem_raw);
+    u64 *svals = skeys + CAP * W;
+    unsigned short *owner = reinterpret_cast<unsigned short *>(svals + CAP);
+    __shared__ u32 s_warp[PART_NT / 32];
+    __shared__ u64 s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double norm1 = 0.0, clones = 0.0, deaths = 0.0, zombies = 0.0;
+    i64 inorm1 = 0, len_before = 0, len = 0, ndep = 0;
+    u32 max_fill = 0;
+    u64 nrec_sum = 0;
+    for (u32 b = blockIdx.x; b < pt.nb; b += gridDim.x) {
+        const u32 np = src.seg_len ? src.seg_len[b] : 0u;
+        const u64 p0 = np ? src.seg_start[b] : 0ull;
+        const u32 nrec = pt.rec_count[b];
+        const u32 n = np + nrec;
+        max_fill = max(max_fill, n);
+        nrec_sum += nrec;
+        if (nrec > pt.rcap || n > (u32)CAP) { // uniform over the CTA: the host retries with more buckets
+            if (tid == 0) { st->overflow_table = 1; dst.seg_len[b] = 0; dst.seg_start[b] = 0; }
+            continue;
+        }
+        for (int i = tid; i < CAP; i += PART_NT) reinterpret_cast<u32 *>(owner)[i] = 0xffffffffu;
+        u32 pend = 0, slot[R];
+        // ---- stage parents (with the diagonal step) and spawn records
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const u32 i = tid + r * PART_NT;
+            slot[r] = 0;
+            if (i >= n) continue;
+            B key; VT v;
+            if (i < np) {
+                key = load_key<W>(src.keys + (p0 + i) * W);
+                union { u64 b; VT v; } cv; cv.b = src.vals[p0 + i];
+                const VT pv = cv.v;
+                if constexpr (MODE == 0) {
+                    // diagonal_step! (spawning.jl:73-77) through FirstOrderTransitionOperator (fciqmc.jl:93-96)
+                    const double val = (double)pv;
+                    const double hd = ham_diagonal<HK, B>(h, key);
+                    const double d = p.plain_h ? hd : 1 - p.dtau * (hd - p.shift);
+                    double rr = 0.0;
+                    const double thr = is_int ? 0.0 : p.proj_thr;
+                    if (is_int || thr > 0.0) {
+                        u32 rnd[4];
+                        rng_draw(hash_bits(key), 0, STREAM_DIAG, p.k0, p.k1, rnd);
+                        rr = u53(rnd[1], rnd[2]);
+                    }
+                    v = project_value<VT>(d * val, thr, rr);
+                    const double rs = (double)v; // clones_deaths_zombies (spawning.jl:79-93)
+                    if (rs > val) clones += fabs(rs - val);
+                    else if (sgn_(rs) != sgn_(val)) { deaths += fabs(val); zombies += fabs(rs); }
+                    else deaths += fabs(rs - val);
+                } else {
+                    v = (VT)(alpha * (double)pv);
+                }
+            } else {
+                const u64 at = (u64)b * pt.rcap + (i - np);
+                key = load_key<W>(pt.rec_keys + at * W);
+                union { u64 b; VT v; } cv; cv.b = pt.rec_vals[at]; v = cv.v;
+            }
+            if (v != (VT)0) {
+                skeys[i * W] = (u64)key;
+                if constexpr (W == 2) skeys[i * W + 1] = (u64)(key >> 64);
+                union { u64 b; VT v; } cv; cv.v = v; svals[i] = cv.b;
+                slot[r] = (u32)hash_bits(key) & TMASK;
+                pend |= 1u << r;
+                ndep++;
+            }
+        }
+        __syncthreads();
+        // ---- placement rounds: read phase | barrier | write phase | barrier
+        u32 own = 0;
+        for (;;) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (!((pend >> r) & 1u)) continue;
+                const u32 i = tid + r * PART_NT;
+                const u64 k0 = skeys[i * W];
+                u64 k1 = 0; if constexpr (W == 2) k1 = skeys[i * W + 1];
+                u32 s = slot[r];
+                for (;;) {
+                    const u32 o = owner[s];
+                    if (o == NIL) break;                              // free: claim it in the write phase
+                    if (o == i) { own |= 1u << r; pend &= ~(1u << r); break; } // my claim of the last round stood
+                    bool eq = skeys[o * W] == k0;
+                    if constexpr (W == 2) eq = eq && skeys[o * W + 1] == k1;
+                    if (eq) {                                         // same address: annihilate into its owner
+                        union { u64 b; VT v; } cv; cv.b = svals[i];
+                        atomic_add_val<VT>(&svals[o], cv.v);
+                        pend &= ~(1u << r);
+                        break;
+                    }
+                    s = (s + 1) & TMASK;
+                }
+                slot[r] = s;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if ((pend >> r) & 1u) owner[slot[r]] = (unsigned short)(tid + r * PART_NT);
+            if (!__syncthreads_or(pend != 0)) break;
+        }
+        // ---- drop zeros, compress, count survivors
+        VT outv[R];
+        u32 keep = 0, cnt = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            outv[r] = (VT)0;
+            if (!((own >> r) & 1u)) continue;
+            const u32 i = tid + r * PART_NT;
+            union { u64 b; VT v; } cv; cv.b = svals[i];
+            VT v = cv.v;
+            if (v == (VT)0) continue; // exact zeros are deleted (pdworkingmemory.jl:25-29)
+            len_before++;
+            if constexpr (!is_int && MODE == 0) {
+                if (p.compress_thr > 0.0) { // ThresholdCompression (compression.jl:18-26)
+                    const double prob = fabs(v) / p.compress_thr;
+                    if (prob < 1) {
+                        B key;
+                        if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
+                        u32 rnd[4];
+                        rng_draw(hash_bits(key), 0, STREAM_COMPRESS, p.k0, p.k1, rnd);
+                        v = (prob > u53(rnd[1], rnd[2])) ? p.compress_thr * sgn_(v) : 0.0;
+                    }
+                }
+            }
+            if (v != (VT)0) {
+                outv[r] = v; keep |= 1u << r; cnt++;
+                if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v); else norm1 += fabs((double)v);
+            }
+        }
+        // ---- CTA scan of survivor counts, one cursor atomic per bucket, write the new segment
+        u32 incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        u32 wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < PART_NT / 32; w++) { u32 t = s_warp[w]; if (w < wid) wbase += t; total += t; }
+        if (tid == 0) {
+            u64 base = total ? atomicAdd(&st->out_count, (u64)total) : 0ull;
+            s_base = base;
+            dst.seg_start[b] = base;
+            dst.seg_len[b] = (base + total <= dst.cap) ? total : 0u;
+        }
+        __syncthreads();
+        const u64 base = s_base;
+        if (base + total <= dst.cap) {
+            u64 at = base + wbase + incl - cnt;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (!((keep >> r) & 1u)) continue;
+                const u32 i = tid + r * PART_NT;
+                dst.keys[at * W] = skeys[i * W];
+                if constexpr (W == 2) dst.keys[at * W + 1] = skeys[i * W + 1];
+                union { u64 b; VT v; } cv; cv.v = outv[r];
+                dst.vals[at] = cv.b;
+                at++;
+            }
+        }
+        len += cnt;
+        __syncthreads(); // shared memory is reused by the next bucket
+    }
+    stat_add(&st->len_before, len_before);
+    stat_add(&st->len, len);
+    stat_add(&st->deposits, ndep);
+    if (is_int) {
+        stat_add(&st->inorm1, inorm1);
+        if (MODE == 0) { stat_add(&st->iclones, (i64)clones); stat_add(&st->ideaths, (i64)deaths); stat_add(&st->izombies, (i64)zombies); }
+    } else {
+        stat_add(&st->norm1, norm1);
+        if (MODE == 0) { stat_add(&st->clones, clones); stat_add(&st->deaths, deaths); stat_add(&st->zombies, zombies); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) max_fill = max(max_fill, __shfl_xor_sync(0xffffffffu, max_fill, o));
+    if (lane == 0) atomicMax(&st->max_fill, (unsigned long long)max_fill);
+    if (tid == 0 && nrec_sum) atomicAdd(&st->records, nrec_sum);
+}
+
+// ---------------------------------------------------------------- re-segmentation of a vector for a new bucket count
+template <int W>
+__global__ void __launch_bounds__(RIMU_TPB)
+bucket_count_kernel(const u64 *__restrict__ keys, i64 n, int nranks, u32 nb, u32 *__restrict__ counts) {
+    typedef typename BitsT<W>::type B;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        B key = load_key<W>(keys + i * W);
+        atomicAdd(&counts[bucket_of(hash_bits(key), nranks, nb)], 1u);
+    }
+}
+// exclusive scan of counts -> seg_start (single CTA; nb is small compared with the vector); fill[] is zeroed
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(const u32 *__restrict__ counts, u32 nb, u64 *__restrict__ seg_start, u32 *__restrict__ seg_len, u32 *__restrict__ fill) {
+    __shared__ u64 warp_tot[32];
+    __shared__ u64 carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (u32 start = 0; start < nb; start += 1024) {
+        u32 i = start + threadIdx.x;
+        u64 v = i < nb ? counts[i] : 0, incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u64 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        u64 base = carry_s, tot = 0;
+        for (int w = 0; w < 32; w++) { u64 t = warp_tot[w]; if (w < wid) base += t; tot += t; }
+        if (i < nb) { seg_start[i] = base + incl - v; seg_len[i] = (u32)v; fill[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += tot;
+        __syncthreads();
+    }
+}
+template <int W>
+__global__ void __launch_bounds__(RIMU_TPB)
+bucket_scatter_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, i64 n, int nranks, u32 nb,
+                      const u64 *__restrict__ seg_start, u32 *__restrict__ fill, u64 *__restrict__ okeys, u64 *__restrict__ ovals) {
+    typedef typename BitsT<W>::type B;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        B key = load_key<W>(keys + i * W);
+        u32 b = bucket_of(hash_bits(key), nranks, nb);
+        u64 at = seg_start[b] + atomicAdd(&fill[b], 1u);
+        store_key<W>(okeys + at * W, key);
+        ovals[at] = vals[i];
+    }
+}
+#endif // __CUDACC__

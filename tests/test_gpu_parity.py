@@ -242,3 +242,34 @@ def test_table_growth_retry(built):
     k2, v2 = z.download_sorted()
     assert np.array_equal(k1, k2) and np.allclose(v1, v2, rtol=1e-12)
     assert np.array_equal(x.download_sorted()[0], ref[0])  # source untouched
+
+
+@pytest.mark.parametrize("W", [1, 2])
+def test_rebucket_preserves_vector(built, W):
+    """Re-segmentation (partition.cuh) is a permutation of the (key, value) pairs, every bucket's entries are
+    contiguous and sit in the bucket the HOST hash function assigns (guards the nvcc hash miscompile that
+    tests/cuda/t_hash_miscompile.cu reproduces)."""
+    import ctypes as C
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+    rng = np.random.default_rng(W)
+    at = R.AddressType(_lib.ADDR_BOSE, (20,) if W == 1 else (60,), 20 if W == 1 else 60)
+    for n in (1, 80, 5000, 300_000):
+        keys = rng.integers(1, 2 ** 62, size=(n, W), dtype=np.uint64)
+        vals = rng.uniform(1, 2, size=n)
+        v = R.GPUDVec(style=R.IsDeterministic(), address_type=at)
+        v.assign(keys, vals)
+        k0, v0 = v.download_sorted()
+        for nb in (1, 5, 64, 1000):
+            _lib.check(_lib.lib().rimu_vec_rebucket(v.handle, nb))
+            k1, v1 = v.download_sorted()
+            assert np.array_equal(k0, k1) and np.array_equal(v0, v1), (W, n, nb)
+            ku, _ = v.download()
+            st, ln = np.zeros(nb, dtype=np.uint64), np.zeros(nb, dtype=np.uint32)
+            _lib.check(_lib.lib().rimu_vec_segments(v.handle, st.ctypes.data_as(_lib._u64p), ln.ctypes.data_as(C.POINTER(C.c_uint32))))
+            assert int(ln.sum()) == n
+            bucket_of_pos = np.repeat(np.arange(nb), ln)[np.argsort(np.repeat(st, ln) + np.concatenate([np.arange(l) for l in ln]) if n else [])] if n else []
+            for pos in rng.integers(0, n, size=min(n, 200)):
+                kk = np.ascontiguousarray(ku[pos])
+                h = _lib.lib().rimu_addr_hash(kk.ctypes.data_as(_lib._u64p), W)
+                assert ((h >> 32) * nb) >> 32 == bucket_of_pos[pos], (W, n, nb, pos)
