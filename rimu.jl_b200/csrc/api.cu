@@ -395,6 +395,14 @@ extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
     if ((hk == HK_MOM1D_BOSE || hk == HK_MOM1D_F2C || hk == HK_TC_F2C) && M > RIMU_MAX_TABLE_MODES)
         return fail(RIMU_ERR_INVALID, "momentum-space models support at most %d modes", RIMU_MAX_TABLE_MODES);
     if (hk == HK_MOM1D_BOSE && M < 3) return fail(RIMU_ERR_INVALID, "HubbardMom1D needs at least 3 modes");
+    { // the device decoders index off-diagonals with 32-bit arithmetic
+        double n1 = d->num_particles[0], n2 = d->num_particles[1], m = M, lmax = 0;
+        if (hk == HK_MOM1D_BOSE) lmax = n1 * (n1 - 1) * (m - 2) + n1 * (m - 1);
+        else if (hk == HK_TC_F2C) lmax = n1 * n2 * (m - 1) + (n1 * (n1 - 1) * n2 + n2 * (n2 - 1) * n1) * m * m;
+        else if (hk == HK_MOM1D_F2C) lmax = n1 * n2 * (m - 1);
+        else lmax = (n1 + n2) * 6;
+        if (lmax >= 2147483648.0) return fail(RIMU_ERR_INVALID, "more than 2^31 off-diagonals per address are unsupported");
+    }
     rimu_ham *h = new rimu_ham();
     memset(h, 0, sizeof(*h));
     h->desc = *d; h->hk = hk;
@@ -941,7 +949,7 @@ extern "C" int rimu_vec_segments(rimu_vec *v, uint64_t *start_out, uint32_t *len
 template <int HK, int W, class VT>
 static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, u32 nb, i64 *sent) {
     const i64 n = src->n;
-    if (src->nb != nb) TRY(rebucket(src, nb));
+    const bool seg = src->nb == nb && n > 0; // parents can be read by bucket segment; else their diagonal deposits go through the streams
     TRY(ensure_seg(dst, nb));
     TRY(ensure_part(c, nb));
     TRY(ensure_heavy(c, (u64)n));
@@ -962,8 +970,13 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
             h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->xch, c->heavy, c->d_stats);
         spawn_heavy_kernel<HK, W, VT><<<c->sm_count * 4, SPAWN_NT, 0, c->stream>>>(
             h->dev, p, src->keys, (const VT *)src->vals, c->part, c->xch, c->heavy, c->d_stats);
-        CUDA_TRY(cudaGetLastError());
         c->launches += 2;
+        if (!seg) {
+            diag_append_kernel<HK, W, VT><<<grid_for(n, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
+                h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->d_stats);
+            c->launches += 1;
+        }
+        CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     *sent = 0;
@@ -972,7 +985,7 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
         if (r) return r;
     }
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    SegSrc ss{src->keys, (const u64 *)src->vals, src->seg_start, src->seg_len};
+    SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr};
     SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap};
     const int mgrid = (int)(nb < (u32)c->sm_count * 16 ? nb : (u32)c->sm_count * 16);
     merge_kernel<HK, W, VT, 0><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
@@ -1061,7 +1074,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             if (use_part) {
                 // size the bucket count from what this attempt saw (records are counted even when dropped)
                 const double cap = (double)part_cap_items(c->W);
-                double need = ceil(((double)src->n + (double)l.records) * 1.15 / (0.45 * cap));
+                double need = ceil(((double)src->n + (double)l.records) * 1.15 / (0.45 * cap)); // (diagonal records may be counted twice: harmless)
                 u32 nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb * 2 + 1);
                 if (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26)) use_part = false; // one address is too hot to pre-sum: use the table
                 nb = nb2;
@@ -1085,7 +1098,10 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         dst->n = (i64)l.out_count;
         dst->nb = use_part ? nb : 0;
         if (use_part) {
-            if (src->n > 0) c->rec_per_parent = 0.5 * c->rec_per_parent + 0.5 * ((double)l.records / (double)src->n);
+            if (src->n > 0) {
+                double rec = (double)l.records - (src->nb == nb ? 0.0 : (double)src->n); // unsegmented sources add one diagonal record per parent
+                c->rec_per_parent = 0.5 * c->rec_per_parent + 0.5 * (rec > 0 ? rec : 0.0) / (double)src->n;
+            }
             c->last_max_fill = l.max_fill;
         }
         if (out) {

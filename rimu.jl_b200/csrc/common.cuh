@@ -88,7 +88,7 @@ template <> struct BitsT<2> { typedef u128 type; };
 
 DEV int popc_(u64 x) { return __popcll(x); }
 DEV int popc_(u128 x) { return __popcll((u64)x) + __popcll((u64)(x >> 64)); }
-DEV int ctz_(u64 x) { return x ? __ffsll((long long)x) - 1 : 64; }
+DEV int ctz_(u64 x) { return __clzll((long long)__brevll(x)); } // 64 for x == 0
 DEV int ctz_(u128 x) {
     u64 lo = (u64)x;
     if (lo) return __ffsll((long long)lo) - 1;

@@ -54,25 +54,33 @@ template <class B> DEV int bose_create(B &x, int m) {
 }
 template <class B> DEV int bose_num_occupied(B x) { return popc_((B)(x & ~(x << 1))); }
 template <class B> DEV int bose_num_doubly(B x) { return popc_((B)(x & ~(x << 1) & (x >> 1))); }
-// k-th (0-based) occupied mode in ascending order -> (mode 1-based, occupation)
+// k-th (0-based) occupied mode in ascending order -> (mode 1-based, occupation, bit offset of its first particle).
+// Occupied modes start where a 1 follows a 0 (or sits at bit 0); the k-th such bit is found with a rank/select
+// step instead of walking the modes (OccupiedModeMap lookups, fockaddress.jl:258-275, in O(1)).
+template <class B> DEV void bose_kth_occupied(B x, int k, int &mode, int &occ, int &off) {
+    const B starts = x & ~(x << 1);
+    off = select_(starts, k);
+    mode = off - popc_((B)(x & lowmask<B>(off))) + 1;
+    occ = cto_((B)(x >> off));
+}
 template <class B> DEV void bose_kth_occupied(B x, int k, int &mode, int &occ) {
-    int md = 1;
-    for (;;) {
-        int z = ctz_(x);
-        x >>= z; md += z;
-        int n = cto_(x);
-        if (k == 0) { mode = md; occ = n; return; }
-        --k;
-        x >>= n;
-    }
+    int off;
+    bose_kth_occupied(x, k, mode, occ, off);
+}
+// d-th (0-based) mode with occupation >= 2
+template <class B> DEV void bose_kth_doubly(B x, int d, int &mode, int &occ, int &off) {
+    const B starts = x & ~(x << 1) & (x >> 1);
+    off = select_(starts, d);
+    mode = off - popc_((B)(x & lowmask<B>(off))) + 1;
+    occ = cto_((B)(x >> off));
 }
 template <class B> DEV long long bose_interaction(B x) { // sum n(n-1)
-    long long r = 0;
+    int r = 0;
     while (x != 0) {
         x >>= ctz_(x);
         int n = cto_(x);
         x >>= n;
-        r += (long long)n * (n - 1);
+        r += n * (n - 1);
     }
     return r;
 }
@@ -134,12 +142,13 @@ DEV double tc_three_body_diag(const HamDev &h, u64 fa, int nb) {
 }
 
 // two-component momentum transfer (excitations.jl:82-119). i is 0-based.
-DEV double mom_transfer_2c(int M, u64 &fa, u64 &fb, int Nb, long long i, bool fold, int &p, int &q, int &mk) {
-    long long per_a = (long long)(M - 1) * Nb;
+DEV double mom_transfer_2c(int M, u64 &fa, u64 &fb, int Nb, long long i64_, bool fold, int &p, int &q, int &mk) {
+    const unsigned i = (unsigned)i64_, nb = (unsigned)Nb; // indices are < 2^31 (checked at rimu_ham_create)
+    const unsigned per_a = (unsigned)(M - 1) * nb;
     int src_a = (int)(i / per_a);
-    long long rem = i % per_a;
-    int dst_a = (int)(rem / Nb) + 1; // 1..M-1
-    int src_b = (int)(rem % Nb);
+    const unsigned rem = i % per_a;
+    int dst_a = (int)(rem / nb) + 1; // 1..M-1
+    int src_b = (int)(rem % nb);
     int src_a_mode = select_(fa, src_a) + 1, src_b_mode = select_(fb, src_b) + 1;
     if (dst_a >= src_a_mode) dst_a += 1;
     int mom = dst_a - src_a_mode;
@@ -159,12 +168,13 @@ DEV double mom_transfer_2c(int M, u64 &fa, u64 &fb, int Nb, long long i, bool fo
 }
 
 // three-body term (excitations.jl:199-238), fermions. i 0-based; (p,q,s,p_k,q_l) first index fastest.
-DEV double tc_three_body(int M, u64 &fa, u64 &fb, int N1, int N2, long long i, int &k, int &l) {
-    int p = (int)(i % N1); i /= N1;
-    int q = (int)(i % (N1 - 1)); i /= (N1 - 1);
-    int s = (int)(i % N2); i /= N2;
-    int p_k = (int)(i % M) + 1; i /= M;
-    int q_l = (int)(i % M) + 1;
+DEV double tc_three_body(int M, u64 &fa, u64 &fb, int N1, int N2, long long i64_, int &k, int &l) {
+    unsigned i = (unsigned)i64_; // indices are < 2^31 (checked at rimu_ham_create)
+    int p = (int)(i % (unsigned)N1); i /= (unsigned)N1;
+    int q = (int)(i % (unsigned)(N1 - 1)); i /= (unsigned)(N1 - 1);
+    int s = (int)(i % (unsigned)N2); i /= (unsigned)N2;
+    int p_k = (int)(i % (unsigned)M) + 1; i /= (unsigned)M;
+    int q_l = (int)(i % (unsigned)M) + 1;
     if (q >= p) q += 1;
     int pm = select_(fa, p) + 1, qm = select_(fa, q) + 1, sm = select_(fb, s) + 1;
     k = pm - p_k; l = q_l - qm;
@@ -192,16 +202,17 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         return h.u * (double)bose_interaction(x) / 2;
     } else if constexpr (HK == HK_MOM1D_BOSE) {
         double ke = 0.0;
-        long long sq = 0, lin = 0, ntot = 0;
-        int md = 1;
+        int lin = 0, md = 0;
         B y = x;
         while (y != 0) {
             int z = ctz_(y); y >>= z; md += z;
             int n = cto_(y); y >>= n;
-            ke += h.kes[md - 1] * n;
-            lin += (long long)n * (n - 1); sq += (long long)n * n; ntot += n;
+            ke += h.kes[md] * n;
+            lin += n * (n - 1);
         }
-        long long onproduct = lin + 2 * (ntot * ntot - sq); // sum n(n-1) + 4 sum_{i>j} n_i n_j
+        // sum n(n-1) + 4 sum_{i>j} n_i n_j with sum n = N and sum n^2 = lin + N
+        const int ntot = h.N0;
+        const long long onproduct = (long long)lin + 2LL * ((long long)ntot * ntot - lin - ntot);
         return ke + h.u / (2 * M) * (double)onproduct;
     } else if constexpr (HK == HK_MOM1D_F2C) {
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
@@ -280,49 +291,42 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
     const int M = h.M;
     out = x;
     if constexpr (HK == HK_REAL1D_BOSE) {
-        int mode, occ;
-        bose_kth_occupied(x, (int)(i >> 1), mode, occ);
+        int mode, ns, off;
+        bose_kth_occupied(x, (int)(i >> 1), mode, ns, off);
         int dst = (i & 1) ? (mode == 1 ? M : mode - 1) : (mode == M ? 1 : mode + 1); // chosen odd <=> i even: hop right
-        B y = x;
-        int ns = bose_destroy(y, mode);
+        B y = delete_bit(x, off);
         int nd = bose_create(y, dst);
         out = y;
-        return -h.t * sqrt((double)((long long)ns * nd));
+        return -h.t * sqrt((double)(ns * nd));
     } else if constexpr (HK == HK_MOM1D_BOSE) {
-        long long s = bose_num_occupied(x);
-        long long dbl = i - s * (s - 1) * (M - 2); // 0-based index into the "same mode" block if >= 0
-        int src0, src1, mom, occ;
-        if (dbl >= 0) {
-            int d = (int)(dbl / (M - 1));
-            mom = (int)(dbl % (M - 1)) + 1;
-            // d-th (0-based) mode with occupation >= 2
-            int md = 1; B y = x;
-            for (;;) {
-                int z = ctz_(y); y >>= z; md += z;
-                int n = cto_(y); y >>= n;
-                if (n >= 2) { if (d == 0) break; --d; }
-            }
-            src0 = src1 = md;
+        const int s = bose_num_occupied(x);
+        const int ndiff = s * (s - 1) * (M - 2);
+        const int ii = (int)i;
+        int src0, src1, off0, off1, n0, n1, mom;
+        if (ii >= ndiff) { // both particles from one mode with n >= 2
+            const unsigned dbl = (unsigned)(ii - ndiff), mm1 = (unsigned)(M - 1);
+            const int d = (int)(dbl / mm1);
+            mom = (int)(dbl % mm1) + 1;
+            bose_kth_doubly(x, d, src0, n0, off0);
+            src1 = src0; off1 = off0; n1 = n0; n0 = n0 - 1; // a_src1 first: n, then a_src0 on the same mode: n - 1
         } else {
-            long long pair = i / (M - 2);
-            mom = (int)(i % (M - 2)) + 1;
-            int fst = (int)(pair / (s - 1)) + 1, snd = (int)(pair % (s - 1)) + 1; // 1-based as in fldmod1
+            const unsigned mm2 = (unsigned)(M - 2), sm1 = (unsigned)(s - 1);
+            const unsigned pair = (unsigned)ii / mm2;
+            mom = (int)((unsigned)ii % mm2) + 1;
+            int fst = (int)(pair / sm1) + 1, snd = (int)(pair % sm1) + 1; // 1-based as in fldmod1
             int f_hole, s_hole;
             if (snd < fst) { f_hole = snd; s_hole = fst; } else { f_hole = fst; s_hole = snd + 1; }
-            bose_kth_occupied(x, f_hole - 1, src0, occ);
-            bose_kth_occupied(x, s_hole - 1, src1, occ);
+            bose_kth_occupied(x, f_hole - 1, src0, n0, off0);
+            bose_kth_occupied(x, s_hole - 1, src1, n1, off1);
             if (mom >= src1 - src0) mom += 1;
         }
         int dst0 = src0 + mom, dst1 = src1 - mom;
         if (dst0 > M) dst0 -= M;
         if (dst1 < 1) dst1 += M;
-        // excitation(add, dst, src): destroy src[1], src[0]; create dst[1], dst[0]
-        B y = x;
-        long long value = bose_destroy(y, src1);
-        if (value == 0) return 0.0;
-        int n0 = bose_destroy(y, src0);
-        if (n0 == 0) return 0.0;
-        value *= n0;
+        // excitation(add, dst, src): destroy src[1], src[0]; create dst[1], dst[0].  off0 <= off1, so removing the
+        // particle at off1 first leaves off0 valid.
+        B y = delete_bit(delete_bit(x, off1), off0);
+        int value = n1 * n0;
         value *= bose_create(y, dst1);
         value *= bose_create(y, dst0);
         out = y;
@@ -334,16 +338,16 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         if (val != 0.0) out = (B)(fa | (fb << M));
         return h.u / M * val;
     } else if constexpr (HK == HK_RS_BOSE) {
-        int particle = (int)(i / h.nnb), neigh = (int)(i % h.nnb);
-        int mode, occ;
-        bose_kth_occupied(x, particle, mode, occ);
+        const unsigned ii = (unsigned)i, nnb = (unsigned)h.nnb;
+        int particle = (int)(ii / nnb), neigh = (int)(ii % nnb);
+        int mode, ns, off;
+        bose_kth_occupied(x, particle, mode, ns, off);
         int dst = h.nbr[(mode - 1) * h.nnb + neigh];
         if (dst == 0) return 0.0;
-        B y = x;
-        int ns = bose_destroy(y, mode);
+        B y = delete_bit(x, off);
         int nd = bose_create(y, dst);
         out = y;
-        return -h.tc0 * sqrt((double)((long long)ns * nd));
+        return -h.tc0 * sqrt((double)(ns * nd));
     } else if constexpr (HK == HK_RS_FERMI || HK == HK_RS_F2C) {
         u64 mask = (M >= 64) ? ~0ull : ((1ull << M) - 1);
         u64 fa = (u64)x & mask, fb = (HK == HK_RS_F2C) ? (((u64)x >> M) & mask) : 0;
@@ -351,7 +355,8 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         int comp = 0;
         if (HK == HK_RS_F2C && i >= na) { comp = 1; i -= na; }
         u64 f = comp ? fb : fa;
-        int particle = (int)(i / h.nnb), neigh = (int)(i % h.nnb);
+        const unsigned ii = (unsigned)i, nnb = (unsigned)h.nnb;
+        int particle = (int)(ii / nnb), neigh = (int)(ii % nnb);
         int mode = select_(f, particle) + 1;
         int dst = h.nbr[(mode - 1) * h.nnb + neigh];
         if (dst == 0) return 0.0;

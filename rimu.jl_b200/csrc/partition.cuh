@@ -136,6 +136,7 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
     __shared__ u32 s_off[SPAWN_NT + 1];
     __shared__ u64 s_keys[SPAWN_NT * W];
     __shared__ VT s_vals[SPAWN_NT];
+    __shared__ u32 s_L[SPAWN_NT];   // off-diagonal count | exact flag in bit 31
     __shared__ u32 s_warp[SPAWN_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double spawns = 0.0;
@@ -161,6 +162,7 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
                 c64 = 0;
             }
             cnt = (u32)c64;
+            s_L[tid] = (u32)L | (exact ? 0x80000000u : 0u);
             s_keys[tid * W] = (u64)key;
             if constexpr (W == 2) s_keys[tid * W + 1] = (u64)(key >> 64);
             s_vals[tid] = pv;
@@ -185,9 +187,10 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
             B key;
             if constexpr (W == 1) key = s_keys[lo]; else key = ((u128)s_keys[lo * 2 + 1] << 64) | (u128)s_keys[lo * 2];
             const double val = (double)s_vals[lo];
-            const long long L = ham_num_offdiagonals<HK, B>(h, key);
-            u64 nat;
-            const bool exact = attempts_for(p, val, L, nat);
+            const u32 Lx = s_L[lo];
+            const long long L = (long long)(Lx & 0x7fffffffu);
+            const bool exact = (Lx >> 31) != 0;
+            const u64 nat = s_off[lo + 1] - s_off[lo]; // light parents only: their attempt count is the scan difference
             B child; long long ci; double sp;
             VT nv = spawn_attempt<HK, W, VT>(h, p, key, hash_bits(key), val, L, nat, exact, k, child, ci, sp);
             spawns += sp;
@@ -262,6 +265,41 @@ append_records_kernel(const u64 *__restrict__ keys, const VT *__restrict__ vals,
         if (nranks > 1 && addr_owner(hh, nranks) != rank) continue;
         append_record<W, VT>(pt, st, key, hh, nranks, v);
     }
+}
+
+// ---------------------------------------------------------------- K0: diagonal step as records
+// Used when the source vector is not segmented for this step's bucket count (fresh uploads, a changed
+// bucket count): the parents' diagonal deposits travel through the bucket streams like spawns, which
+// costs one extra record write + read per parent instead of a re-segmentation pass.
+template <int HK, int W, class VT>
+__global__ void __launch_bounds__(RIMU_TPB)
+diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
+                   PartDev pt, StatsDev *st) {
+    typedef typename BitsT<W>::type B;
+    constexpr bool is_int = std::is_integral<VT>::value;
+    double clones = 0.0, deaths = 0.0, zombies = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const B key = load_key<W>(keys + i * W);
+        const double val = (double)vals[i];
+        const u64 hk = hash_bits(key);
+        const double hd = ham_diagonal<HK, B>(h, key);
+        const double d = p.plain_h ? hd : 1 - p.dtau * (hd - p.shift);
+        double rr = 0.0;
+        const double thr = is_int ? 0.0 : p.proj_thr;
+        if (is_int || thr > 0.0) {
+            u32 rnd[4];
+            rng_draw(hk, 0, STREAM_DIAG, p.k0, p.k1, rnd);
+            rr = u53(rnd[1], rnd[2]);
+        }
+        const VT v = project_value<VT>(d * val, thr, rr);
+        const double rs = (double)v;
+        if (rs > val) clones += fabs(rs - val);
+        else if (sgn_(rs) != sgn_(val)) { deaths += fabs(val); zombies += fabs(rs); }
+        else deaths += fabs(rs - val);
+        if (v != (VT)0) append_record<W, VT>(pt, st, key, hk, p.nranks, v);
+    }
+    if (is_int) { stat_add(&st->iclones, (i64)clones); stat_add(&st->ideaths, (i64)deaths); stat_add(&st->izombies, (i64)zombies); }
+    else { stat_add(&st->clones, clones); stat_add(&st->deaths, deaths); stat_add(&st->zombies, zombies); }
 }
 
 // ---------------------------------------------------------------- K3: per-bucket annihilation in shared memory
