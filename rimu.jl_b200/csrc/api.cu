@@ -120,6 +120,7 @@ struct rimu_ham {
     HamDev dev;
     double *d_tables;
     unsigned char *d_nbr;
+    u64 uid; // identifies this Hamiltonian in the vectors' diagonal-element caches
 };
 struct rimu_vec {
     rimu_ctx *ctx;
@@ -133,6 +134,10 @@ struct rimu_vec {
     u64 seg_cap;
     u64 *seg_start;
     u32 *seg_len;
+    // cache of diagonal_element(H, address) per entry, written by the partitioned step; valid for the
+    // Hamiltonian with uid diag_uid (0 = invalid).  Saves re-evaluating H_aa for every parent every step.
+    double *diag;
+    u64 diag_cap, diag_uid;
 };
 
 static u64 next_pow2(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
@@ -262,7 +267,7 @@ static int ensure_seg(rimu_vec *v, u32 nb) {
     return 0;
 }
 static u32 part_cap_items(int W) { return W == 1 ? (u32)PartCap<1>::value : (u32)PartCap<2>::value; }
-static size_t part_smem_bytes(int W) { u32 cap = part_cap_items(W); return (size_t)cap * W * 8 + (size_t)cap * 8 + (size_t)cap * 2 * 2; }
+static size_t part_smem_bytes(int W) { u32 cap = part_cap_items(W); return (size_t)cap * W * 8 + (size_t)cap * 8 + (size_t)cap * 2 * 4 + (size_t)cap * 2; }
 static int ensure_part(rimu_ctx *c, u32 nb) {
     c->part.rcap = part_cap_items(c->W);
     if (nb <= c->part_nb_cap) { c->part.nb = nb; return 0; }
@@ -406,6 +411,8 @@ extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
     rimu_ham *h = new rimu_ham();
     memset(h, 0, sizeof(*h));
     h->desc = *d; h->hk = hk;
+    static u64 next_uid = 1;
+    h->uid = next_uid++;
     h->W = (kind == RIMU_ADDR_BOSE) ? ((bits + 1 + 63) / 64) : 1;
     CUDA_TRY(cudaGetDevice(&h->device));
     HamDev &v = h->dev;
@@ -532,6 +539,7 @@ extern "C" int rimu_vec_create(rimu_ctx *c, int val_type, uint64_t capacity, rim
     v->ctx = c; v->vt = val_type; v->n = 0; v->cap = capacity < 256 ? 256 : capacity;
     v->keys = nullptr; v->vals = nullptr;
     v->nb = 0; v->seg_cap = 0; v->seg_start = nullptr; v->seg_len = nullptr;
+    v->diag = nullptr; v->diag_cap = 0; v->diag_uid = 0;
     CUDA_TRY(cudaMalloc(&v->keys, v->cap * c->W * sizeof(u64)));
     CUDA_TRY(cudaMalloc(&v->vals, v->cap * sizeof(u64)));
     *out = v;
@@ -541,7 +549,7 @@ extern "C" int rimu_vec_destroy(rimu_vec *v) {
     if (!v) return 0;
     cudaSetDevice(v->ctx->device);
     cudaStreamSynchronize(v->ctx->stream);
-    cudaFree(v->keys); cudaFree(v->vals); cudaFree(v->seg_start); cudaFree(v->seg_len);
+    cudaFree(v->keys); cudaFree(v->vals); cudaFree(v->seg_start); cudaFree(v->seg_len); cudaFree(v->diag);
     delete v;
     return 0;
 }
@@ -556,12 +564,25 @@ extern "C" int rimu_vec_reserve(rimu_vec *v, uint64_t capacity) {
         CUDA_TRY(cudaMemcpyAsync(nk, v->keys, v->n * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(nv, v->vals, v->n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
     }
+    double *nd = nullptr;
+    if (v->diag) {
+        CUDA_TRY(cudaMalloc(&nd, capacity * sizeof(double)));
+        if (v->n > 0 && v->diag_uid) CUDA_TRY(cudaMemcpyAsync(nd, v->diag, v->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(v->keys); cudaFree(v->vals);
+    cudaFree(v->keys); cudaFree(v->vals); cudaFree(v->diag);
     v->keys = nk; v->vals = nv; v->cap = capacity;
+    v->diag = nd; v->diag_cap = nd ? capacity : 0;
     return 0;
 }
-extern "C" int rimu_vec_clear(rimu_vec *v) { v->n = 0; v->nb = 0; return 0; }
+static int ensure_diag(rimu_vec *v) {
+    if (v->diag && v->diag_cap >= v->cap) return 0;
+    cudaFree(v->diag); v->diag = nullptr; v->diag_cap = 0; v->diag_uid = 0;
+    CUDA_TRY(cudaMalloc(&v->diag, v->cap * sizeof(double)));
+    v->diag_cap = v->cap;
+    return 0;
+}
+extern "C" int rimu_vec_clear(rimu_vec *v) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; }
 extern "C" int rimu_vec_length(rimu_vec *v, int64_t *out) { *out = v->n; return 0; }
 extern "C" int rimu_vec_capacity(rimu_vec *v, uint64_t *out) { *out = v->cap; return 0; }
 
@@ -597,7 +618,7 @@ static u64 pick_slots(rimu_ctx *c, u64 expected_entries) {
 static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
                           const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
     CUDA_TRY(cudaSetDevice(c->device));
-    dst->nb = 0; // the global-table path produces an unsegmented vector
+    dst->nb = 0; dst->diag_uid = 0; // the global-table path produces an unsegmented vector
     u64 slots = pick_slots(c, (u64)(n + n2));
     for (;;) {
         CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
@@ -637,7 +658,7 @@ static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const v
 extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (n <= 0) { v->n = 0; v->nb = 0; return 0; }
+    if (n <= 0) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; }
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->stage_vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -647,7 +668,7 @@ extern "C" int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *va
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     if (n < 0) return fail(RIMU_ERR_INVALID, "negative length");
-    v->nb = 0;
+    v->nb = 0; v->diag_uid = 0;
     if ((u64)n > v->cap) { v->n = 0; TRY(rimu_vec_reserve(v, (u64)n)); }
     if (n > 0) {
         CUDA_TRY(cudaMemcpyAsync(v->keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -685,7 +706,12 @@ extern "C" int rimu_vec_copy(rimu_vec *dst, rimu_vec *src) {
         }
     }
     dst->n = src->n;
-    dst->nb = 0;
+    dst->nb = 0; dst->diag_uid = 0;
+    if (src->diag_uid && src->n > 0) { // keep the diagonal-element cache
+        TRY(ensure_diag(dst));
+        CUDA_TRY(cudaMemcpyAsync(dst->diag, src->diag, src->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        dst->diag_uid = src->diag_uid;
+    }
     if (src->nb) { // keep the bucket segmentation
         TRY(ensure_seg(dst, src->nb));
         CUDA_TRY(cudaMemcpyAsync(dst->seg_start, src->seg_start, src->nb * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
@@ -742,7 +768,7 @@ extern "C" int rimu_vec_norm(rimu_vec *v, int p, double *out) {
 extern "C" int rimu_vec_scale(rimu_vec *v, double alpha) {
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (alpha == 0.0) { v->n = 0; v->nb = 0; return 0; } // zero values are never stored
+    if (alpha == 0.0) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; } // zero values are never stored
     if (v->n > 0) {
         if (v->vt == RIMU_VAL_F64) scale_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((double *)v->vals, v->n, alpha);
         else scale_kernel<i64><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((i64 *)v->vals, v->n, alpha);
@@ -809,7 +835,7 @@ extern "C" int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, con
 extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *vals, int64_t n, int method) {
     rimu_ctx *c = dst->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (n <= 0) { dst->n = 0; dst->nb = 0; return 0; }
+    if (n <= 0) { dst->n = 0; dst->nb = 0; dst->diag_uid = 0; return 0; }
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->stage_vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -894,7 +920,7 @@ static int step_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec 
     TRY((compact_into<W, VT>(c, dst, slots, p)));
     c->launches += 1;
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    dst->nb = 0;
+    dst->nb = 0; dst->diag_uid = 0;
     return 0;
 }
 
@@ -925,6 +951,7 @@ static int rebucket(rimu_vec *v, u32 nb) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(v->keys); cudaFree(v->vals);
     v->keys = nk; v->vals = nv; v->nb = nb;
+    v->diag_uid = 0; // entries moved: the diagonal cache no longer lines up
     return 0;
 }
 
@@ -951,6 +978,8 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     const i64 n = src->n;
     const bool seg = src->nb == nb && n > 0; // parents can be read by bucket segment; else their diagonal deposits go through the streams
     TRY(ensure_seg(dst, nb));
+    TRY(ensure_diag(dst));
+    const double *src_diag = (src->diag_uid == h->uid && src->diag) ? src->diag : nullptr;
     TRY(ensure_part(c, nb));
     TRY(ensure_heavy(c, (u64)n));
     static bool attr_set[HK_COUNT][3][2] = {};
@@ -973,7 +1002,7 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
         c->launches += 2;
         if (!seg) {
             diag_append_kernel<HK, W, VT><<<grid_for(n, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
-                h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->d_stats);
+                h->dev, p, src->keys, (const VT *)src->vals, src_diag, n, c->part, c->d_stats);
             c->launches += 1;
         }
         CUDA_TRY(cudaGetLastError());
@@ -985,9 +1014,9 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
         if (r) return r;
     }
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr};
-    SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap};
-    const int mgrid = (int)(nb < (u32)c->sm_count * 16 ? nb : (u32)c->sm_count * 16);
+    SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr, src_diag};
+    SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, dst->diag};
+    const int mgrid = (int)(nb < (u32)c->sm_count * 32 ? nb : (u32)c->sm_count * 32);
     merge_kernel<HK, W, VT, 0><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;
@@ -1097,6 +1126,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         }
         dst->n = (i64)l.out_count;
         dst->nb = use_part ? nb : 0;
+        dst->diag_uid = use_part ? h->uid : 0;
         if (use_part) {
             if (src->n > 0) {
                 double rec = (double)l.records - (src->nb == nb ? 0.0 : (double)src->n); // unsegmented sources add one diagonal record per parent

@@ -27,13 +27,13 @@
 #pragma once
 #include "kernels.cuh"
 
-#define PART_NT 512        // threads of a merge CTA
+#define PART_NT 256        // threads of a merge CTA
 #define SPAWN_NT 256       // threads (= parents per chunk) of a spawn CTA
 #define HEAVY_T 1024       // parents with more attempts than this are queued for K2
 #define HEAVY_TILE 8192    // attempts per K2 work item
 #define ACC_MAX 4096       // K2 pre-sums per off-diagonal index when L <= ACC_MAX
 
-template <int W> struct PartCap { static constexpr int value = W == 1 ? 4096 : 2048; };
+template <int W> struct PartCap { static constexpr int value = 2048; }; // items (parents + records) a bucket may hold
 
 struct PartDev {       // bucket record streams (working memory of the partitioned step)
     u32 nb;            // buckets on this rank
@@ -42,11 +42,11 @@ struct PartDev {       // bucket record streams (working memory of the partition
     u64 *rec_vals;     // [nb][rcap]
     u32 *rec_count;    // [nb]
 };
-struct SegSrc {        // a segmented vector, read side
-    const u64 *keys; const u64 *vals; const u64 *seg_start; const u32 *seg_len;
+struct SegSrc {        // a segmented vector, read side (diag: cached diagonal elements or null)
+    const u64 *keys; const u64 *vals; const u64 *seg_start; const u32 *seg_len; const double *diag;
 };
 struct SegDst {        // a segmented vector, write side
-    u64 *keys; u64 *vals; u64 *seg_start; u32 *seg_len; u64 cap;
+    u64 *keys; u64 *vals; u64 *seg_start; u32 *seg_len; u64 cap; double *diag;
 };
 struct HeavyItem { i64 parent; u64 nattempts; u64 tile_base; u64 exact; };
 struct HeavyDev { HeavyItem *items; u64 *packed; /* (count << 32) | tiles */ u64 cap; };
@@ -273,8 +273,8 @@ append_records_kernel(const u64 *__restrict__ keys, const VT *__restrict__ vals,
 // costs one extra record write + read per parent instead of a re-segmentation pass.
 template <int HK, int W, class VT>
 __global__ void __launch_bounds__(RIMU_TPB)
-diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
-                   PartDev pt, StatsDev *st) {
+diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals,
+                   const double *__restrict__ diag, i64 n, PartDev pt, StatsDev *st) {
     typedef typename BitsT<W>::type B;
     constexpr bool is_int = std::is_integral<VT>::value;
     double clones = 0.0, deaths = 0.0, zombies = 0.0;
@@ -282,7 +282,7 @@ diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
         const B key = load_key<W>(keys + i * W);
         const double val = (double)vals[i];
         const u64 hk = hash_bits(key);
-        const double hd = ham_diagonal<HK, B>(h, key);
+        const double hd = diag ? diag[i] : ham_diagonal<HK, B>(h, key);
         const double d = p.plain_h ? hd : 1 - p.dtau * (hd - p.shift);
         double rr = 0.0;
         const double thr = is_int ? 0.0 : p.proj_thr;
@@ -304,21 +304,30 @@ diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
 
 // ---------------------------------------------------------------- K3: per-bucket annihilation in shared memory
 // MODE 0: FCIQMC step (diagonal step on the parents, compression);  MODE 1: plain sum of records (+ alpha * parents)
+//
+// Shared memory per CTA (CAP items): keys[CAP][W] | vals[CAP] | owner[2*CAP] (u32 item index per table slot) |
+// pidx[CAP] (u16: index of the parent item that was annihilated into this owner, for its cached H_aa).
+// Placement is one pass: an item claims the first free slot of its probe sequence with a 32-bit shared CAS on
+// the owner table; keys are compared through the item index, so nothing has to be published after a claim.
+// After placement the owner table is dead and is reused as the list of survivors that still need H_aa.
 template <int HK, int W, class VT, int MODE>
-__global__ void __launch_bounds__(PART_NT)
+__global__ void __launch_bounds__(PART_NT, 4)
 merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st) {
     typedef typename BitsT<W>::type B;
     constexpr bool is_int = std::is_integral<VT>::value;
     constexpr int CAP = PartCap<W>::value;
     constexpr int R = CAP / PART_NT;
     constexpr u32 TMASK = 2 * CAP - 1;
-    constexpr u32 NIL = 0xffffu;
+    constexpr u32 NIL = 0xffffffffu;
+    constexpr u32 NOPARENT = 0xffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);
     u64 *svals = skeys + CAP * W;
-    unsigned short *owner = reinterpret_cast<unsigned short *>(svals + CAP);
+    u32 *owner = reinterpret_cast<u32 *>(svals + CAP);
+    unsigned short *pidx = reinterpret_cast<unsigned short *>(owner + 2 * CAP);
     __shared__ u32 s_warp[PART_NT / 32];
     __shared__ u64 s_base;
+    __shared__ u32 s_nlist;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double norm1 = 0.0, clones = 0.0, deaths = 0.0, zombies = 0.0;
     i64 inorm1 = 0, len_before = 0, len = 0, ndep = 0;
@@ -335,9 +344,10 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             if (tid == 0) { st->overflow_table = 1; dst.seg_len[b] = 0; dst.seg_start[b] = 0; }
             continue;
         }
-        for (int i = tid; i < CAP; i += PART_NT) reinterpret_cast<u32 *>(owner)[i] = 0xffffffffu;
-        u32 pend = 0, slot[R];
+        for (int i = tid; i < 2 * CAP; i += PART_NT) owner[i] = NIL;
+        if (tid == 0) s_nlist = 0;
         // ---- stage parents (with the diagonal step) and spawn records
+        u32 valid = 0, slot[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const u32 i = tid + r * PART_NT;
@@ -351,7 +361,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 if constexpr (MODE == 0) {
                     // diagonal_step! (spawning.jl:73-77) through FirstOrderTransitionOperator (fciqmc.jl:93-96)
                     const double val = (double)pv;
-                    const double hd = ham_diagonal<HK, B>(h, key);
+                    const double hd = src.diag ? src.diag[p0 + i] : ham_diagonal<HK, B>(h, key);
                     const double d = p.plain_h ? hd : 1 - p.dtau * (hd - p.shift);
                     double rr = 0.0;
                     const double thr = is_int ? 0.0 : p.proj_thr;
@@ -373,48 +383,44 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 key = load_key<W>(pt.rec_keys + at * W);
                 union { u64 b; VT v; } cv; cv.b = pt.rec_vals[at]; v = cv.v;
             }
+            pidx[i] = (unsigned short)NOPARENT;
             if (v != (VT)0) {
                 skeys[i * W] = (u64)key;
                 if constexpr (W == 2) skeys[i * W + 1] = (u64)(key >> 64);
                 union { u64 b; VT v; } cv; cv.v = v; svals[i] = cv.b;
                 slot[r] = (u32)hash_bits(key) & TMASK;
-                pend |= 1u << r;
+                valid |= 1u << r;
                 ndep++;
             }
         }
         __syncthreads();
-        // ---- placement rounds: read phase | barrier | write phase | barrier
+        // ---- placement: claim a slot (CAS) or annihilate into the item that owns this address
         u32 own = 0;
-        for (;;) {
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (!((pend >> r) & 1u)) continue;
-                const u32 i = tid + r * PART_NT;
-                const u64 k0 = skeys[i * W];
-                u64 k1 = 0; if constexpr (W == 2) k1 = skeys[i * W + 1];
-                u32 s = slot[r];
-                for (;;) {
-                    const u32 o = owner[s];
-                    if (o == NIL) break;                              // free: claim it in the write phase
-                    if (o == i) { own |= 1u << r; pend &= ~(1u << r); break; } // my claim of the last round stood
-                    bool eq = skeys[o * W] == k0;
-                    if constexpr (W == 2) eq = eq && skeys[o * W + 1] == k1;
-                    if (eq) {                                         // same address: annihilate into its owner
-                        union { u64 b; VT v; } cv; cv.b = svals[i];
-                        atomic_add_val<VT>(&svals[o], cv.v);
-                        pend &= ~(1u << r);
-                        break;
-                    }
-                    s = (s + 1) & TMASK;
+        for (int r = 0; r < R; r++) {
+            if (!((valid >> r) & 1u)) continue;
+            const u32 i = tid + r * PART_NT;
+            const u64 k0 = skeys[i * W];
+            u64 k1 = 0; if constexpr (W == 2) k1 = skeys[i * W + 1];
+            u32 s = slot[r];
+            for (;;) {
+                u32 o = owner[s];
+                if (o == NIL) {
+                    o = atomicCAS(&owner[s], NIL, i);
+                    if (o == NIL) { own |= 1u << r; break; }
                 }
-                slot[r] = s;
+                bool eq = skeys[o * W] == k0;
+                if constexpr (W == 2) eq = eq && skeys[o * W + 1] == k1;
+                if (eq) {
+                    union { u64 b; VT v; } cv; cv.b = svals[i];
+                    atomic_add_val<VT>(&svals[o], cv.v);
+                    if constexpr (MODE == 0) { if (i < np) pidx[o] = (unsigned short)i; } // its cached H_aa follows the address
+                    break;
+                }
+                s = (s + 1) & TMASK;
             }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < R; r++)
-                if ((pend >> r) & 1u) owner[slot[r]] = (unsigned short)(tid + r * PART_NT);
-            if (!__syncthreads_or(pend != 0)) break;
         }
+        __syncthreads();
         // ---- drop zeros, compress, count survivors
         VT outv[R];
         u32 keep = 0, cnt = 0;
@@ -461,21 +467,41 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         }
         __syncthreads();
         const u64 base = s_base;
-        if (base + total <= dst.cap) {
-            u64 at = base + wbase + incl - cnt;
+        const bool fits = base + total <= dst.cap;
+        if (fits) {
+            u32 rel = wbase + incl - cnt;
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (!((keep >> r) & 1u)) continue;
                 const u32 i = tid + r * PART_NT;
+                const u64 at = base + rel;
                 dst.keys[at * W] = skeys[i * W];
                 if constexpr (W == 2) dst.keys[at * W + 1] = skeys[i * W + 1];
                 union { u64 b; VT v; } cv; cv.v = outv[r];
                 dst.vals[at] = cv.b;
-                at++;
+                if constexpr (MODE == 0) {
+                    // H_aa of the survivor: cached with its parent, or (new determinant) evaluated below
+                    const u32 pi = i < np ? i : (u32)pidx[i];
+                    if (src.diag && pi != NOPARENT) dst.diag[at] = src.diag[p0 + pi];
+                    else owner[atomicAdd(&s_nlist, 1u)] = (i << 16) | rel; // owner table is dead: reuse as the list
+                }
+                rel++;
             }
         }
         len += cnt;
-        __syncthreads(); // shared memory is reused by the next bucket
+        __syncthreads();
+        if constexpr (MODE == 0) {
+            // dense evaluation of H_aa for the gathered survivors (a per-lane evaluation inside the output loop
+            // would cost a full divergent warp pass per new entry)
+            const u32 nl = fits ? s_nlist : 0u;
+            for (u32 j = tid; j < nl; j += PART_NT) {
+                const u32 e = owner[j], i = e >> 16, rel = e & 0xffffu;
+                B key;
+                if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
+                dst.diag[base + rel] = ham_diagonal<HK, B>(h, key);
+            }
+            __syncthreads(); // shared memory is reused by the next bucket
+        }
     }
     stat_add(&st->len_before, len_before);
     stat_add(&st->len, len);
