@@ -1030,9 +1030,9 @@ static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src) {
     const double expected = (double)src->n * (1.0 + c->rec_per_parent) * 1.15 + 512.0;
     if (src->nb) { // keep the segmentation while the expected fill stays in a comfortable band
         double fill = expected / src->nb;
-        if (fill > 0.15 * cap && fill < 0.62 * cap) return src->nb;
+        if (fill > 0.25 * cap && fill < 0.80 * cap) return src->nb;
     }
-    double nb = ceil(expected / (0.45 * cap));
+    double nb = ceil(expected / (0.65 * cap));
     return nb < 1.0 ? 1u : (u32)nb;
 }
 
@@ -1103,7 +1103,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             if (use_part) {
                 // size the bucket count from what this attempt saw (records are counted even when dropped)
                 const double cap = (double)part_cap_items(c->W);
-                double need = ceil(((double)src->n + (double)l.records) * 1.15 / (0.45 * cap)); // (diagonal records may be counted twice: harmless)
+                double need = ceil(((double)src->n + (double)l.records) * 1.15 / (0.6 * cap)); // (diagonal records may be counted twice: harmless)
                 u32 nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb * 2 + 1);
                 if (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26)) use_part = false; // one address is too hot to pre-sum: use the table
                 nb = nb2;

@@ -346,10 +346,12 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         }
         for (int i = tid; i < 2 * CAP; i += PART_NT) owner[i] = NIL;
         if (tid == 0) s_nlist = 0;
+        const int rmax = (int)((n + PART_NT - 1) / PART_NT); // uniform: rounds of PART_NT items this bucket needs
         // ---- stage parents (with the diagonal step) and spawn records
         u32 valid = 0, slot[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
+            if (r >= rmax) break;
             const u32 i = tid + r * PART_NT;
             slot[r] = 0;
             if (i >= n) continue;
@@ -398,6 +400,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         u32 own = 0;
 #pragma unroll
         for (int r = 0; r < R; r++) {
+            if (r >= rmax) break;
             if (!((valid >> r) & 1u)) continue;
             const u32 i = tid + r * PART_NT;
             const u64 k0 = skeys[i * W];
@@ -427,6 +430,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
 #pragma unroll
         for (int r = 0; r < R; r++) {
             outv[r] = (VT)0;
+            if (r >= rmax) break;
             if (!((own >> r) & 1u)) continue;
             const u32 i = tid + r * PART_NT;
             union { u64 b; VT v; } cv; cv.b = svals[i];
@@ -472,6 +476,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             u32 rel = wbase + incl - cnt;
 #pragma unroll
             for (int r = 0; r < R; r++) {
+                if (r >= rmax) break;
                 if (!((keep >> r) & 1u)) continue;
                 const u32 i = tid + r * PART_NT;
                 const u64 at = base + rel;
