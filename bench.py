@@ -271,7 +271,7 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = e2e_attempts / (float(t[0]) * 1e-3)
 
-    # ---- roofline of the dominant kernel (CUDA-event durations measured live, per launch averages)
+    # ---- roofline of the dominant kernel (CUDA-event durations measured live inside rimu_step, per launch averages)
     K = args.steps
     E = 16  # bytes per entry: one uint64 address word + one 8-byte value
     peaks = {}
@@ -281,12 +281,15 @@ def ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    # per-rank figures (stats are global -> divide by world for a per-GPU kernel)
+    # per-rank figures (stats are global -> divide by world for a per-GPU kernel).  Algorithmic bytes:
+    #   spawn_part_kernel: P*E parents read + A'*E records written
+    #   merge_kernel     : P*(E+8) parents + cached H_aa read, A'*E records read, U*(E+8) survivors + H_aa written
     P = acc["parents"] / K
-    dep_spawn = max(acc["deposits"] / world - acc["parents"], 0) / K
-    spawn_bytes = P * E + P * 8 + 2 * E * dep_spawn            # parents + offsets read; RMW of one slot per deposit
-    compact_bytes = (2 * acc["len_before"] / world + acc["len"] / world) * E / K  # read+reset occupied slots, write survivors
-    kern = {"spawn_kernel": (acc["ms_spawn"] / K, spawn_bytes), "compact_kernel": (acc["ms_compact"] / K, compact_bytes)}
+    A1 = max(acc["deposits"] / world - acc["parents"], 0) / K  # non-zero spawn records per step and rank
+    U = acc["len"] / world / K
+    spawn_bytes = P * E + A1 * E
+    merge_bytes = P * (E + 8) + A1 * E + U * (E + 8)
+    kern = {"spawn_part_kernel": (acc["ms_spawn"] / K, spawn_bytes), "merge_kernel": (acc["ms_compact"] / K, merge_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     dms, dbytes = kern[dom]
     achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
@@ -297,15 +300,17 @@ def ours(args):
             traffic = tr.get(dom)
     except Exception:
         pass
-    annih_bytes = (acc["deposits"] / world + acc["len_before"] / world + acc["len"] / world) * E / K
-    annih_ms = (acc["ms_spawn"] + acc["ms_compact"]) / K
+    annih_bytes = merge_bytes
+    annih_ms = acc["ms_compact"] / K
+    step_bytes = spawn_bytes + merge_bytes
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "walkers_per_gpu": per_gpu, "target_walkers": target, "determinants_per_gpu": P,
-                   "attempts_per_step": acc["attempts"] / K, "l2": "inputs larger than L2 (vector + working table > 126 MB)",
+                   "attempts_per_step": acc["attempts"] / K, "method": "partition (bucket streams + shared-memory annihilation)",
+                   "l2": "inputs larger than L2: walker vector + spawn record streams of a step exceed 126 MB",
                    "growth_steps": nsteps, "equil_steps": args.equil, "parallelism": f"hash-partitioned x{world}"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps},
         "gpu_launches": int(launches1.value - launches0.value),
@@ -314,8 +319,8 @@ def ours(args):
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dbytes, "ms_per_launch": dms},
         "extra": {"annihilation_gbs": annih_bytes / (annih_ms * 1e-3) / 1e9 if annih_ms > 0 else None,
-                  "phase_ms_per_step": {"diag_count_scan": acc["ms_diag"] / K, "spawn": acc["ms_spawn"] / K,
-                                        "exchange": acc["ms_exch"] / K, "compact": acc["ms_compact"] / K},
+                  "step_hbm_gbs": step_bytes / (ms_max / K * 1e-3) / 1e9, "step_hbm_frac_of_peak": step_bytes / (ms_max / K * 1e-3) / 1e9 / peak,
+                  "phase_ms_per_step": {"spawn": acc["ms_spawn"] / K, "exchange": acc["ms_exch"] / K, "merge": acc["ms_compact"] / K},
                   "wall_ms_per_step": 1e3 * wall / K, "norm": s.norm1, "shift": sp.shift},
     }
 

@@ -161,6 +161,10 @@ int rimu_host_free(void *p);
 int rimu_comm_unique_id(void *id128);               /* ncclGetUniqueId; broadcast by the host launcher */
 int rimu_comm_init(rimu_ctx *ctx, const void *id128, int rank, int nranks, uint64_t exchange_records_per_peer);
 int rimu_comm_rank(rimu_ctx *ctx, int *rank, int *nranks);
+/* after RIMU_ERR_EXCHANGE_FULL (reported identically on every rank): *needed = largest per-peer record count
+ * seen; every rank then calls rimu_comm_reserve with the same larger size and repeats the step */
+int rimu_comm_capacity(rimu_ctx *ctx, uint64_t *per_peer_out, uint64_t *needed_out);
+int rimu_comm_reserve(rimu_ctx *ctx, uint64_t exchange_records_per_peer);
 int rimu_comm_allreduce_f64(rimu_ctx *ctx, double *host_inout, int n);
 /* owner rank of an address: communicators.jl:77-81 target_segment */
 int rimu_addr_owner(const uint64_t *key, int words, int nranks);

@@ -111,6 +111,7 @@ struct rimu_ctx {
     u64 part_nb_cap;         // buckets the record streams are allocated for
     HeavyDev heavy;
     u32 *bucket_tmp; u64 bucket_tmp_cap; // [2][nb] counts / fill
+    u64 xch_worst;           // largest per-peer record count seen by a failed exchange
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
     u64 last_max_fill;
 };
@@ -327,6 +328,24 @@ extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nran
     CUDA_TRY(cudaMalloc(&c->recv_vals, c->recv_cap * sizeof(u64)));
     CUDA_TRY(cudaMalloc(&c->d_allcounts, (u64)nranks * nranks * sizeof(u64)));
     CUDA_TRY(cudaMallocHost(&c->h_allcounts, (u64)nranks * nranks * sizeof(u64)));
+    return 0;
+}
+// grow the per-peer exchange buffers (every rank must call it with the same size; contents are scratch)
+extern "C" int rimu_comm_reserve(rimu_ctx *c, uint64_t per_peer) {
+    if (c->nranks == 1 || per_peer <= c->xch.cap) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->recv_keys); cudaFree(c->recv_vals);
+    c->xch.keys = c->xch.vals = c->recv_keys = c->recv_vals = nullptr; c->xch.cap = 0; c->recv_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->xch.keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->xch.vals, (u64)c->nranks * per_peer * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->recv_keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
+    CUDA_TRY(cudaMalloc(&c->recv_vals, (u64)c->nranks * per_peer * sizeof(u64)));
+    c->xch.cap = per_peer; c->recv_cap = (u64)c->nranks * per_peer;
+    return 0;
+}
+extern "C" int rimu_comm_capacity(rimu_ctx *c, uint64_t *per_peer, uint64_t *needed) {
+    *per_peer = c->xch.cap; *needed = c->xch_worst;
     return 0;
 }
 extern "C" int rimu_comm_rank(rimu_ctx *c, int *rank, int *nranks) { *rank = c->rank; *nranks = c->nranks; return 0; }
@@ -852,7 +871,10 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool t
     u64 worst = 0, total_recv = 0, sent = 0;
     for (int s = 0; s < R; s++)
         for (int d = 0; d < R; d++) { u64 n = c->h_allcounts[s * R + d]; if (n > worst) worst = n; }
-    if (worst > c->xch.cap) return RIMU_ERR_EXCHANGE_FULL; // identical decision on every rank
+    if (worst > c->xch.cap) { // identical decision on every rank
+        c->xch_worst = worst;
+        return RIMU_ERR_EXCHANGE_FULL;
+    }
     for (int s = 0; s < R; s++) if (s != me) total_recv += c->h_allcounts[s * R + me];
     for (int d = 0; d < R; d++) if (d != me) sent += c->h_allcounts[me * R + d];
     *sent_out = (i64)sent;
@@ -1086,7 +1108,8 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             // nothing was sent; drain what this rank deposited locally, then report
             if (!use_part) TRY(table_fill(c, slots));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
-            return fail(RIMU_ERR_EXCHANGE_FULL, "per-peer exchange buffer (%llu records) too small", (unsigned long long)c->xch.cap);
+            return fail(RIMU_ERR_EXCHANGE_FULL, "per-peer exchange buffer (%llu records) too small: a rank produced %llu records for one peer",
+                        (unsigned long long)c->xch.cap, (unsigned long long)c->xch_worst);
         }
         if (r) return r;
         CUDA_TRY(cudaMemcpyAsync(c->h_stats_local, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));

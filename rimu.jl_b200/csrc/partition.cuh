@@ -72,24 +72,40 @@ DEV void append_record(const PartDev &pt, StatsDev *st, typename BitsT<W>::type 
     } else st->overflow_table = 1;
 }
 
-// route one spawn: the child's bucket stream on this rank, or the owner's exchange segment
+// CTA-collective routing of at most one spawn record per thread: local children go to their bucket stream;
+// records for other ranks are staged per peer -- ranks within the CTA come from a shared-memory counter, ONE
+// global atomic per peer and CTA reserves a contiguous run in that peer's exchange segment (the reference packs
+// per-rank buffers serially, communicators.jl:421-444).  Every thread of the CTA must call this.
+struct RouteSmem { u32 cnt[RIMU_MAX_RANKS]; u64 base[RIMU_MAX_RANKS]; };
 template <int W, class VT>
-DEV void emit_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p, StatsDev *st,
-                     typename BitsT<W>::type key, VT v) {
-    u64 h = hash_bits(key);
-    if (p.nranks > 1) {
-        int owner = addr_owner(h, p.nranks);
-        if (owner != p.rank) {
-            u64 idx = atomicAdd(&x.counts[owner], 1ull);
+DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p, StatsDev *st, RouteSmem &rs,
+                      bool has, typename BitsT<W>::type key, VT v) {
+    u64 h = 0;
+    int owner = p.rank;
+    if (has) {
+        h = hash_bits(key);
+        if (p.nranks > 1) owner = addr_owner(h, p.nranks);
+    }
+    if (p.nranks > 1) { // uniform over the grid
+        if (threadIdx.x < RIMU_MAX_RANKS) rs.cnt[threadIdx.x] = 0;
+        __syncthreads();
+        const bool remote = has && owner != p.rank;
+        u32 lrank = 0;
+        if (remote) lrank = atomicAdd(&rs.cnt[owner], 1u);
+        __syncthreads();
+        if ((int)threadIdx.x < p.nranks && rs.cnt[threadIdx.x])
+            rs.base[threadIdx.x] = atomicAdd(&x.counts[threadIdx.x], (u64)rs.cnt[threadIdx.x]);
+        __syncthreads();
+        if (remote) {
+            const u64 idx = rs.base[owner] + lrank;
             if (idx < x.cap) {
                 store_key<W>(x.keys + ((u64)owner * x.cap + idx) * W, key);
                 union { VT v; u64 b; } cv; cv.v = v;
                 x.vals[(u64)owner * x.cap + idx] = cv.b;
             } else st->overflow_xchg = 1;
-            return;
         }
     }
-    append_record<W, VT>(pt, st, key, h, p.nranks, v);
+    if (has && owner == p.rank) append_record<W, VT>(pt, st, key, h, p.nranks, v);
 }
 
 // one spawn attempt k of a parent (spawning.jl:174-182 Exact, :232-243 WithReplacement).
@@ -138,6 +154,7 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
     __shared__ VT s_vals[SPAWN_NT];
     __shared__ u32 s_L[SPAWN_NT];   // off-diagonal count | exact flag in bit 31
     __shared__ u32 s_warp[SPAWN_NT / 32];
+    __shared__ RouteSmem s_route;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double spawns = 0.0;
     i64 exact_steps = 0, inexact_steps = 0, attempts = 0;
@@ -179,22 +196,27 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
         s_off[tid] = base + incl - cnt;
         if (tid == 0) s_off[SPAWN_NT] = total;
         __syncthreads();
-        for (u32 a = tid; a < total; a += SPAWN_NT) {
-            int lo = 0, hi = SPAWN_NT; // last lo with s_off[lo] <= a
+        for (u32 a0 = 0; a0 < total; a0 += SPAWN_NT) {
+            const u32 a = a0 + tid;
+            B child = 0;
+            VT nv = (VT)0;
+            if (a < total) {
+                int lo = 0, hi = SPAWN_NT; // last lo with s_off[lo] <= a
 #pragma unroll
-            for (int it = 0; it < 8; it++) { int mid = (lo + hi) >> 1; if (s_off[mid] <= a) lo = mid; else hi = mid; }
-            const u64 k = a - s_off[lo];
-            B key;
-            if constexpr (W == 1) key = s_keys[lo]; else key = ((u128)s_keys[lo * 2 + 1] << 64) | (u128)s_keys[lo * 2];
-            const double val = (double)s_vals[lo];
-            const u32 Lx = s_L[lo];
-            const long long L = (long long)(Lx & 0x7fffffffu);
-            const bool exact = (Lx >> 31) != 0;
-            const u64 nat = s_off[lo + 1] - s_off[lo]; // light parents only: their attempt count is the scan difference
-            B child; long long ci; double sp;
-            VT nv = spawn_attempt<HK, W, VT>(h, p, key, hash_bits(key), val, L, nat, exact, k, child, ci, sp);
-            spawns += sp;
-            if (nv != (VT)0) emit_record<W, VT>(pt, xch, p, st, child, nv);
+                for (int it = 0; it < 8; it++) { int mid = (lo + hi) >> 1; if (s_off[mid] <= a) lo = mid; else hi = mid; }
+                const u64 k = a - s_off[lo];
+                B key;
+                if constexpr (W == 1) key = s_keys[lo]; else key = ((u128)s_keys[lo * 2 + 1] << 64) | (u128)s_keys[lo * 2];
+                const double val = (double)s_vals[lo];
+                const u32 Lx = s_L[lo];
+                const long long L = (long long)(Lx & 0x7fffffffu);
+                const bool exact = (Lx >> 31) != 0;
+                const u64 nat = s_off[lo + 1] - s_off[lo]; // light parents only: their attempt count is the scan difference
+                long long ci; double sp;
+                nv = spawn_attempt<HK, W, VT>(h, p, key, hash_bits(key), val, L, nat, exact, k, child, ci, sp);
+                spawns += sp;
+            }
+            route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv);
         }
         __syncthreads();
     }
@@ -210,6 +232,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
                    PartDev pt, ExchangeDev xch, HeavyDev hv, StatsDev *st) {
     typedef typename BitsT<W>::type B;
     __shared__ u64 acc[ACC_MAX];
+    __shared__ RouteSmem s_route;
     const u64 packed = *hv.packed;
     const u64 total = packed & 0xffffffffull;
     u64 nitems = packed >> 32;
@@ -228,20 +251,26 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
         const bool agg = !exact && L <= ACC_MAX;
         const u64 hkey = hash_bits(key);
         if (agg) { for (int c = threadIdx.x; c < L; c += SPAWN_NT) acc[c] = 0ull; __syncthreads(); }
-        for (u64 a = a0 + threadIdx.x; a < a1; a += SPAWN_NT) {
-            B child; long long ci; double sp;
-            VT nv = spawn_attempt<HK, W, VT>(h, p, key, hkey, val, L, it.nattempts, exact, a, child, ci, sp);
-            spawns += sp;
-            if (nv != (VT)0) {
-                if (agg) atomic_add_val<VT>(&acc[ci], nv);
-                else emit_record<W, VT>(pt, xch, p, st, child, nv);
+        for (u64 ab = a0; ab < a1; ab += SPAWN_NT) {
+            const u64 a = ab + threadIdx.x;
+            B child = 0;
+            VT nv = (VT)0;
+            if (a < a1) {
+                long long ci; double sp;
+                nv = spawn_attempt<HK, W, VT>(h, p, key, hkey, val, L, it.nattempts, exact, a, child, ci, sp);
+                spawns += sp;
+                if (agg && nv != (VT)0) { atomic_add_val<VT>(&acc[ci], nv); nv = (VT)0; }
             }
+            if (!agg) route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv);
         }
         if (agg) {
             __syncthreads();
-            for (int c = threadIdx.x; c < L; c += SPAWN_NT) {
-                union { u64 b; VT v; } cv; cv.b = acc[c];
-                if (cv.v != (VT)0) { B child; ham_offdiagonal<HK, B>(h, key, c, child); emit_record<W, VT>(pt, xch, p, st, child, cv.v); }
+            for (int cb = 0; cb < L; cb += SPAWN_NT) {
+                const int c = cb + threadIdx.x;
+                B child = 0;
+                union { u64 b; VT v; } cv; cv.b = 0;
+                if (c < L) { cv.b = acc[c]; if (cv.v != (VT)0) ham_offdiagonal<HK, B>(h, key, c, child); }
+                route_record<W, VT>(pt, xch, p, st, s_route, cv.v != (VT)0, child, cv.v);
             }
             __syncthreads();
         }

@@ -243,6 +243,11 @@ def apply_operator(wm: WorkingMemory, target: GPUDVec, source: GPUDVec, op, boos
         if st == _lib.ERR_TABLE_FULL:
             ctx.resize_table(ctx.table_slots * 4)
             continue
+        if st == _lib.ERR_EXCHANGE_FULL:  # same decision on every rank: grow the per-peer buffers and repeat
+            cap, need = C.c_uint64(), C.c_uint64()
+            _lib.check(_lib.lib().rimu_comm_capacity(ctx.handle, C.byref(cap), C.byref(need)))
+            _lib.check(_lib.lib().rimu_comm_reserve(ctx.handle, max(2 * cap.value, int(1.5 * need.value))))
+            continue
         _lib.check(st)
         break
     wm.counter += 1

@@ -1,0 +1,74 @@
+"""Worker of tests/test_multi_gpu.py: one process per GPU (torchrun).  Runs FCIQMC steps with the NCCL spawn
+exchange and checks the union of the ranks' vectors against the single-rank CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import rimu_b200 as R
+    from oracle import oracle as orc
+    from tests.cases import oracle_ham, product_ham
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    method = os.environ.get("RIMU_B200_METHOD", "partition")
+    for name, style_name in (("real1d_10", "int"), ("rs_bose_3d_w2", "int"), ("mom1d_bose", "semi"), ("rs_f2c_4x4", "int")):
+        oh = oracle_ham(name)
+        R.reset_contexts()
+        ctx = R.init_distributed(oh.W, records_per_peer=1 << 12)  # small on purpose: exercises the grow-and-repeat path
+        ph = product_ham(name)
+        seed, dtau = 99, 0.001 if name == "rs_bose_3d_w2" else 0.01
+        if style_name == "int":
+            style, pop, dtype, ostyle, kw = R.IsStochasticInteger(), 20000, np.int64, orc.STYLE_INTEGER, {}
+        else:
+            style, pop, dtype, ostyle, kw = R.IsDynamicSemistochastic(), 5000.5, np.float64, orc.STYLE_SEMISTOCHASTIC, dict(compress_threshold=1.0)
+        v = R.GPUDVec([(ph.address, pop)], style=style)  # only the owner rank keeps the entry
+        wm = R.working_memory(v, seed=seed)
+        ok, ov = np.array([oh.start_key], dtype=np.uint64), np.array([pop], dtype=dtype)
+        shift = oh.diagonal_element(oh.start_key)
+        for step in range(5):
+            T = R.FirstOrderTransitionOperator(ph, shift, dtau)
+            out = v.similar()
+            R.apply_operator(wm, out, v, T)
+            v = out
+            s = wm.last_stats
+            pp = orc.make_params(ostyle, shift=shift, dtau=dtau, key=orc.step_key(seed, step), **kw)
+            ok, ov, st = oh.step(pp, ok, ov)
+            lk, lv = v.download()
+            parts = [None] * world
+            dist.all_gather_object(parts, (lk, lv))
+            gk = np.concatenate([p[0] for p in parts]).reshape(-1, oh.W)
+            gv = np.concatenate([p[1] for p in parts])
+            order = np.lexsort(tuple(gk[:, j] for j in range(oh.W)))
+            gk, gv = gk[order], gv[order]
+            assert np.array_equal(gk, ok), (name, step, "keys", len(gk), len(ok))
+            # every rank holds exactly the keys it owns
+            for k in lk[:50]:
+                assert orc.addr_owner(k, world) == rank
+            assert s.spawn_attempts == st.spawn_attempts and s.len == st.len_after, (name, step)
+            if style_name == "int":
+                assert np.array_equal(gv, ov), (name, step, "values")
+                assert (s.ispawns, s.ideaths, s.iclones, s.izombies, s.inorm1) == (st.ispawns, st.ideaths, st.iclones, st.izombies, st.inorm1)
+            else:
+                assert np.allclose(gv, ov, rtol=1e-10, atol=0), (name, step)
+                assert abs(s.norm1 - st.norm1) <= 1e-9 * st.norm1
+                # feed the (gathered) GPU values back so that last-bit differences cannot flip branches
+                ok, ov = gk, gv
+            assert all(len(p[1]) > 0 for p in parts) or step == 0, "every rank should own part of the vector"
+            # walkernumber_and_length is global
+            wn, _ = R.walkernumber_and_length(v)
+            assert abs(wn - float(np.abs(ov).sum())) <= 1e-9 * float(np.abs(ov).sum())
+        if rank == 0:
+            print(f"mgpu ok: {name} {style_name} method={method} world={world} len={len(ov)} sent={s.sent_records}", flush=True)
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    main()
