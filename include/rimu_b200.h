@@ -165,6 +165,9 @@ int rimu_comm_rank(rimu_ctx *ctx, int *rank, int *nranks);
  * seen; every rank then calls rimu_comm_reserve with the same larger size and repeats the step */
 int rimu_comm_capacity(rimu_ctx *ctx, uint64_t *per_peer_out, uint64_t *needed_out);
 int rimu_comm_reserve(rimu_ctx *ctx, uint64_t exchange_records_per_peer);
+/* 1 when the spawn exchange goes peer-direct (the spawn kernels store records straight into the owner's receive
+ * buffer through NVLink peer memory mapped with CUDA IPC); 0 = NCCL grouped send/recv (RIMU_B200_P2P=0 forces it) */
+int rimu_comm_p2p(rimu_ctx *ctx, int *enabled_out);
 int rimu_comm_allreduce_f64(rimu_ctx *ctx, double *host_inout, int n);
 /* owner rank of an address: communicators.jl:77-81 target_segment */
 int rimu_addr_owner(const uint64_t *key, int words, int nranks);

@@ -112,6 +112,9 @@ struct rimu_ctx {
     HeavyDev heavy;
     u32 *bucket_tmp; u64 bucket_tmp_cap; // [2][nb] counts / fill
     u64 xch_worst;           // largest per-peer record count seen by a failed exchange
+    int p2p_used;            // the last exchange went peer-direct: counts are read from h_allcounts after the final sync
+    void *peer_open[2][RIMU_MAX_RANKS]; // IPC-opened peer receive buffers (keys, vals)
+    char *d_ipc, *h_ipc;     // all-gather scratch for the IPC handles
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
     u64 last_max_fill;
 };
@@ -188,10 +191,13 @@ extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu
     return 0;
 }
 
+static void p2p_teardown(rimu_ctx *c);
 extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    p2p_teardown(c);
+    cudaFree(c->d_ipc); cudaFreeHost(c->h_ipc);
     if (c->comm && g_nccl.lib) g_nccl.CommDestroy(c->comm);
     cudaFree(c->table); cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFreeHost(c->h_stats_local);
     cudaFree(c->local_off); cudaFree(c->block_tot); cudaFree(c->block_base);
@@ -307,6 +313,58 @@ extern "C" int rimu_comm_unique_id(void *id128) {
     memcpy(id128, &id, 128);
     return 0;
 }
+// ---- peer-direct exchange: map every peer's receive buffers into this process (CUDA IPC over NVLink)
+static void p2p_teardown(rimu_ctx *c) {
+    for (int k = 0; k < 2; k++)
+        for (int r = 0; r < RIMU_MAX_RANKS; r++)
+            if (c->peer_open[k][r]) { cudaIpcCloseMemHandle(c->peer_open[k][r]); c->peer_open[k][r] = nullptr; }
+    c->xch.p2p = 0;
+    memset(c->xch.peer_keys, 0, sizeof(c->xch.peer_keys));
+    memset(c->xch.peer_vals, 0, sizeof(c->xch.peer_vals));
+}
+extern "C" int rimu_comm_allreduce_f64(rimu_ctx *c, double *buf, int n);
+static int p2p_setup(rimu_ctx *c) { // collective
+    p2p_teardown(c);
+    const char *env = getenv("RIMU_B200_P2P");
+    const int R = c->nranks, me = c->rank;
+    const size_t HS = sizeof(cudaIpcMemHandle_t);
+    double bad = (env && !strcmp(env, "0")) ? 1.0 : 0.0;
+    if (!c->d_ipc) {
+        CUDA_TRY(cudaMalloc(&c->d_ipc, (size_t)RIMU_MAX_RANKS * 2 * HS));
+        CUDA_TRY(cudaMallocHost(&c->h_ipc, (size_t)RIMU_MAX_RANKS * 2 * HS));
+    }
+    cudaIpcMemHandle_t mine[2];
+    memset(mine, 0, sizeof(mine));
+    if (bad == 0.0) {
+        if (cudaIpcGetMemHandle(&mine[0], c->recv_keys) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], c->recv_vals) != cudaSuccess) {
+            cudaGetLastError();
+            bad = 1.0;
+        }
+    }
+    TRY(rimu_comm_allreduce_f64(c, &bad, 1));
+    if (bad > 0.0) return 0; // some rank cannot do IPC: everybody keeps the NCCL send/recv exchange
+    CUDA_TRY(cudaMemcpyAsync(c->d_ipc + (size_t)me * 2 * HS, mine, 2 * HS, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(g_nccl.AllGather(c->d_ipc + (size_t)me * 2 * HS, c->d_ipc, 2 * HS, 0 /* ncclInt8 */, c->comm, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_ipc, c->d_ipc, (size_t)R * 2 * HS, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < R && bad == 0.0; r++) {
+        if (r == me) { c->peer_open[0][r] = c->peer_open[1][r] = nullptr; c->xch.peer_keys[r] = c->recv_keys; c->xch.peer_vals[r] = c->recv_vals; continue; }
+        for (int k = 0; k < 2; k++) {
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, c->h_ipc + ((size_t)r * 2 + k) * HS, HS);
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); bad = 1.0; break; }
+            c->peer_open[k][r] = ptr;
+            if (k == 0) c->xch.peer_keys[r] = (u64 *)ptr; else c->xch.peer_vals[r] = (u64 *)ptr;
+        }
+    }
+    TRY(rimu_comm_allreduce_f64(c, &bad, 1));
+    if (bad > 0.0) { p2p_teardown(c); return 0; }
+    c->xch.p2p = 1;
+    return 0;
+}
+extern "C" int rimu_comm_p2p(rimu_ctx *c, int *enabled) { *enabled = c->xch.p2p; return 0; }
+
 extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nranks, uint64_t per_peer) {
     if (nranks < 1 || nranks > RIMU_MAX_RANKS || rank < 0 || rank >= nranks) return fail(RIMU_ERR_INVALID, "bad rank/nranks");
     if (c->comm) return fail(RIMU_ERR_INVALID, "communicator already attached");
@@ -328,13 +386,16 @@ extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nran
     CUDA_TRY(cudaMalloc(&c->recv_vals, c->recv_cap * sizeof(u64)));
     CUDA_TRY(cudaMalloc(&c->d_allcounts, (u64)nranks * nranks * sizeof(u64)));
     CUDA_TRY(cudaMallocHost(&c->h_allcounts, (u64)nranks * nranks * sizeof(u64)));
-    return 0;
+    memset(c->h_allcounts, 0, (size_t)nranks * nranks * sizeof(u64));
+    return p2p_setup(c);
 }
 // grow the per-peer exchange buffers (every rank must call it with the same size; contents are scratch)
 extern "C" int rimu_comm_reserve(rimu_ctx *c, uint64_t per_peer) {
     if (c->nranks == 1 || per_peer <= c->xch.cap) return 0;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    { double zero = 0.0; TRY(rimu_comm_allreduce_f64(c, &zero, 1)); } // nobody is still writing into a peer's old buffer
+    p2p_teardown(c);
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->recv_keys); cudaFree(c->recv_vals);
     c->xch.keys = c->xch.vals = c->recv_keys = c->recv_vals = nullptr; c->xch.cap = 0; c->recv_cap = 0;
     CUDA_TRY(cudaMalloc(&c->xch.keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
@@ -342,7 +403,7 @@ extern "C" int rimu_comm_reserve(rimu_ctx *c, uint64_t per_peer) {
     CUDA_TRY(cudaMalloc(&c->recv_keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
     CUDA_TRY(cudaMalloc(&c->recv_vals, (u64)c->nranks * per_peer * sizeof(u64)));
     c->xch.cap = per_peer; c->recv_cap = (u64)c->nranks * per_peer;
-    return 0;
+    return p2p_setup(c);
 }
 extern "C" int rimu_comm_capacity(rimu_ctx *c, uint64_t *per_peer, uint64_t *needed) {
     *per_peer = c->xch.cap; *needed = c->xch_worst;
@@ -865,6 +926,24 @@ extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *
 static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_streams) {
     const int R = c->nranks, me = c->rank;
     NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
+    c->p2p_used = 0;
+    if (to_streams && c->xch.p2p) {
+        // The payload already sits in this rank's receive regions (peer stores issued by the spawn kernels, complete
+        // before the senders' streams reached the all-gather).  No host round trip: counts are consumed on the device.
+        CUDA_TRY(cudaMemcpyAsync(c->h_allcounts, c->d_allcounts, (size_t)R * R * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64), c->stream));
+        TRY(dispatch_wv(c->W, vt, [&](auto tag, auto vtag) {
+            typedef decltype(vtag) VT;
+            append_recv_kernel<decltype(tag)::w, VT><<<dim3(c->sm_count * 2, R), RIMU_TPB, 0, c->stream>>>(
+                c->recv_keys, (const VT *)c->recv_vals, c->d_allcounts, me, R, c->xch.cap, c->part, c->d_stats);
+            c->launches += 1;
+            return 0;
+        }));
+        CUDA_TRY(cudaGetLastError());
+        c->p2p_used = 1;
+        *sent_out = 0;
+        return 0;
+    }
     CUDA_TRY(cudaMemcpyAsync(c->h_allcounts, c->d_allcounts, (size_t)R * R * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64), c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1121,6 +1200,17 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const StatsDev &g = *c->h_stats, &l = *c->h_stats_local;
+        if (c->nranks > 1 && c->p2p_used) {
+            u64 worst = 0; sent = 0;
+            for (int s_ = 0; s_ < c->nranks; s_++)
+                for (int d_ = 0; d_ < c->nranks; d_++) { u64 n_ = c->h_allcounts[s_ * c->nranks + d_]; if (s_ != d_ && n_ > worst) worst = n_; }
+            for (int d_ = 0; d_ < c->nranks; d_++) if (d_ != c->rank) sent += (i64)c->h_allcounts[c->rank * c->nranks + d_];
+            if (g.overflow_xchg || worst > c->xch.cap) { // identical on every rank (summed flag, gathered counts)
+                c->xch_worst = worst;
+                return fail(RIMU_ERR_EXCHANGE_FULL, "per-peer exchange buffer (%llu records) too small: a rank produced %llu records for one peer",
+                            (unsigned long long)c->xch.cap, (unsigned long long)worst);
+            }
+        }
         if (g.overflow_table) { // some rank ran out of room: every rank retries with more working memory
             if (attempt > 12) return fail(RIMU_ERR_TABLE_FULL, "step working memory cannot be grown further");
             if (use_part) {

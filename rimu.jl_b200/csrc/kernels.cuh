@@ -64,6 +64,11 @@ struct ExchangeDev { // per-peer send staging for multi-GPU spawn exchange
     u64 *vals;       // [nranks][cap]
     u64 *counts;     // [nranks]
     u64 cap;
+    // peer-direct mode (NVLink peer memory, CUDA IPC): records for rank r are stored straight into r's receive
+    // buffer, region [this rank][cap]; only the counts travel through a collective
+    int p2p;
+    u64 *peer_keys[RIMU_MAX_RANKS];
+    u64 *peer_vals[RIMU_MAX_RANKS];
 };
 
 #ifdef __CUDACC__

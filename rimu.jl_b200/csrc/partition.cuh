@@ -99,9 +99,15 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
         if (remote) {
             const u64 idx = rs.base[owner] + lrank;
             if (idx < x.cap) {
-                store_key<W>(x.keys + ((u64)owner * x.cap + idx) * W, key);
                 union { VT v; u64 b; } cv; cv.v = v;
-                x.vals[(u64)owner * x.cap + idx] = cv.b;
+                if (x.p2p) { // straight into the owner's receive region for this rank (NVLink peer store)
+                    const u64 at = (u64)p.rank * x.cap + idx;
+                    store_key<W>(x.peer_keys[owner] + at * W, key);
+                    x.peer_vals[owner][at] = cv.b;
+                } else {
+                    store_key<W>(x.keys + ((u64)owner * x.cap + idx) * W, key);
+                    x.vals[(u64)owner * x.cap + idx] = cv.b;
+                }
             } else st->overflow_xchg = 1;
         }
     }
@@ -293,6 +299,25 @@ append_records_kernel(const u64 *__restrict__ keys, const VT *__restrict__ vals,
         u64 hh = hash_bits(key);
         if (nranks > 1 && addr_owner(hh, nranks) != rank) continue;
         append_record<W, VT>(pt, st, key, hh, nranks, v);
+    }
+}
+
+// peer-direct exchange, receiving side: region [src][cap] of the receive buffer holds allcounts[src][me] records
+template <int W, class VT>
+__global__ void __launch_bounds__(RIMU_TPB)
+append_recv_kernel(const u64 *__restrict__ recv_keys, const VT *__restrict__ recv_vals, const u64 *__restrict__ allcounts,
+                   int me, int R, u64 cap, PartDev pt, StatsDev *st) {
+    typedef typename BitsT<W>::type B;
+    const int src = blockIdx.y;
+    if (src == me) return;
+    u64 n = allcounts[(u64)src * R + me];
+    if (n > cap) n = cap; // the sender raised overflow_xchg
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        const u64 at = (u64)src * cap + i;
+        B key = load_key<W>(recv_keys + at * W);
+        VT v = recv_vals[at];
+        if (v == (VT)0) continue;
+        append_record<W, VT>(pt, st, key, hash_bits(key), R, v);
     }
 }
 

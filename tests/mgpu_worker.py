@@ -66,7 +66,10 @@ def main():
             wn, _ = R.walkernumber_and_length(v)
             assert abs(wn - float(np.abs(ov).sum())) <= 1e-9 * float(np.abs(ov).sum())
         if rank == 0:
-            print(f"mgpu ok: {name} {style_name} method={method} world={world} len={len(ov)} sent={s.sent_records}", flush=True)
+            import ctypes as C
+            p2p = C.c_int()
+            R._lib.check(R._lib.lib().rimu_comm_p2p(ctx.handle, C.byref(p2p)))
+            print(f"mgpu ok: {name} {style_name} method={method} world={world} len={len(ov)} sent={s.sent_records} p2p={p2p.value}", flush=True)
     dist.barrier()
 
 
