@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "librimu_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu"]
+SOURCES = ["api.cu", "sort.cu"]
 HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh"]
 
 NVCC_FLAGS = [

@@ -115,6 +115,7 @@ struct rimu_ctx {
     int p2p_used;            // the last exchange went peer-direct: counts are read from h_allcounts after the final sync
     void *peer_open[2][RIMU_MAX_RANKS]; // IPC-opened peer receive buffers (keys, vals)
     char *d_ipc, *h_ipc;     // all-gather scratch for the IPC handles
+    alignas(16) char sort_scratch[96];   // SortScratch of sort.cu (opaque here)
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
     u64 last_max_fill;
 };
@@ -192,11 +193,17 @@ extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu
 }
 
 static void p2p_teardown(rimu_ctx *c);
+struct SortScratch;
+extern "C" int rimu_sort_scratch_bytes(void);
+extern "C" int rimu_sort_annihilate_w1(cudaStream_t stream, SortScratch *s, const u64 *keys, const u64 *vals, long long n, int is_int,
+                                       int key_bits, u64 *out_keys, u64 *out_vals, u64 out_cap, u64 *d_cursor);
+extern "C" void rimu_sort_scratch_free(SortScratch *s);
 extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     p2p_teardown(c);
+    rimu_sort_scratch_free((SortScratch *)c->sort_scratch);
     cudaFree(c->d_ipc); cudaFreeHost(c->h_ipc);
     if (c->comm && g_nccl.lib) g_nccl.CommDestroy(c->comm);
     cudaFree(c->table); cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFreeHost(c->h_stats_local);
@@ -735,6 +742,79 @@ static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const v
     }
 }
 
+// ---- the same through the partitioned working memory: records -> bucket streams -> shared-memory merge (MODE 1)
+static int ensure_part(rimu_ctx *c, u32 nb);
+static int ensure_seg(rimu_vec *v, u32 nb);
+static u32 part_cap_items(int W);
+static size_t part_smem_bytes(int W);
+static int records_to_vec_part(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
+                               const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
+    CUDA_TRY(cudaSetDevice(c->device));
+    dst->diag_uid = 0; dst->nb = 0;
+    const double cap = (double)part_cap_items(c->W);
+    u32 nb = (u32)ceil(((double)(n + n2) * 1.1 + 256.0) / (0.65 * cap));
+    if (nb < 1) nb = 1;
+    for (int attempt = 0;; attempt++) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        if (nb > c->part_nb_cap && (double)nb * 1.3 * cap * (8.0 * c->W + 8.0) > 0.8 * ((double)free_b + (double)c->part_nb_cap * cap * (8.0 * c->W + 8.0)))
+            return records_to_vec(c, dst, d_keys, d_vals, n, d_keys2, d_vals2, n2, a1, a2, use_scale);
+        TRY(ensure_part(c, nb));
+        TRY(ensure_seg(dst, nb));
+        CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->part.rec_count, 0, nb * sizeof(u32), c->stream));
+        TRY(dispatch_wv(c->W, dst->vt, [&](auto tag, auto vtag) {
+            typedef decltype(vtag) VT;
+            constexpr int W = decltype(tag)::w;
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(merge_kernel<0, W, VT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
+                attr_set = true;
+            }
+            if (n > 0)
+                append_records_kernel<W, VT><<<grid_for(n, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
+                    d_keys, (const VT *)d_vals, n, a1, use_scale, c->rank, c->nranks, c->part, c->d_stats);
+            if (n2 > 0)
+                append_records_kernel<W, VT><<<grid_for(n2, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
+                    d_keys2, (const VT *)d_vals2, n2, a2, use_scale, c->rank, c->nranks, c->part, c->d_stats);
+            HamDev hd; memset(&hd, 0, sizeof(hd));
+            SegSrc ss{nullptr, nullptr, nullptr, nullptr, nullptr};
+            SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, nullptr};
+            const int mgrid = (int)(nb < (u32)c->sm_count * 32 ? nb : (u32)c->sm_count * 32);
+            merge_kernel<0, W, VT, 1><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(hd, null_step(c), ss, 1.0, c->part, sd, c->d_stats);
+            return 0;
+        }));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const StatsDev &l = *c->h_stats;
+        if (l.overflow_table) {
+            if (attempt > 10 || l.max_fill > (u64)(64 * cap)) // one address too hot for a bucket: the table handles it
+                return records_to_vec(c, dst, d_keys, d_vals, n, d_keys2, d_vals2, n2, a1, a2, use_scale);
+            double need = ceil((double)l.records * 1.15 / (0.6 * cap));
+            nb = need > (double)nb * 1.5 ? (u32)need : nb * 2 + 1;
+            continue;
+        }
+        if (l.out_count > dst->cap) {
+            if ((const u64 *)dst->keys == d_keys || (const u64 *)dst->keys == d_keys2)
+                return fail(RIMU_ERR_VECTOR_FULL, "destination (aliasing an input) too small: need %llu", (unsigned long long)l.out_count);
+            dst->n = 0;
+            TRY(rimu_vec_reserve(dst, l.out_count + l.out_count / 4));
+            continue;
+        }
+        dst->n = (i64)l.out_count;
+        dst->nb = nb;
+        return 0;
+    }
+}
+static int records_to_vec_auto(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
+                               const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
+    const bool aliased = (const u64 *)dst->keys == d_keys || (const u64 *)dst->keys == d_keys2;
+    if (c->method == RIMU_ANNIHILATE_PARTITION && !aliased) // (the merge writes dst while it may still be read: aliasing goes through the table, which buffers everything first)
+        return records_to_vec_part(c, dst, d_keys, d_vals, n, d_keys2, d_vals2, n2, a1, a2, use_scale);
+    return records_to_vec(c, dst, d_keys, d_vals, n, d_keys2, d_vals2, n2, a1, a2, use_scale);
+}
+
 extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -742,7 +822,7 @@ extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *va
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->stage_vals, vals, n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-    return records_to_vec(c, v, c->stage_keys, c->stage_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0);
+    return records_to_vec_auto(c, v, c->stage_keys, c->stage_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0);
 }
 extern "C" int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
     rimu_ctx *c = v->ctx;
@@ -898,15 +978,41 @@ extern "C" int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *
     rimu_ctx *c = out->ctx;
     if (x->ctx != c || y->ctx != c || x->vt != out->vt || y->vt != out->vt) return fail(RIMU_ERR_INVALID, "axpby of incompatible vectors");
     if (x->n + y->n > 0 && (u64)(x->n + y->n) > out->cap && (out == x || out == y)) TRY(rimu_vec_reserve(out, (u64)(x->n + y->n)));
-    return records_to_vec(c, out, x->keys, x->vals, x->n, y->keys, y->vals, y->n, alpha, beta, 1);
+    return records_to_vec_auto(c, out, x->keys, x->vals, x->n, y->keys, y->vals, y->n, alpha, beta, 1);
 }
 
 extern "C" int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, const void *d_vals, int64_t n, int method, float *ms_out) {
     rimu_ctx *c = dst->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
-    if (method != RIMU_ANNIHILATE_HASH) return fail(RIMU_ERR_INVALID, "annihilation method %d not available", method);
+    if (method != RIMU_ANNIHILATE_HASH && method != RIMU_ANNIHILATE_SORT && method != RIMU_ANNIHILATE_PARTITION)
+        return fail(RIMU_ERR_INVALID, "annihilation method %d unknown", method);
+    if (method == RIMU_ANNIHILATE_SORT && c->W != 1)
+        return fail(RIMU_ERR_INVALID, "RIMU_ANNIHILATE_SORT is implemented for one-word addresses only");
+    if (method == RIMU_ANNIHILATE_SORT && c->nranks > 1)
+        return fail(RIMU_ERR_INVALID, "RIMU_ANNIHILATE_SORT does not filter by owner rank");
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    TRY(records_to_vec(c, dst, (const u64 *)d_keys, d_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0));
+    if (method == RIMU_ANNIHILATE_HASH) TRY(records_to_vec(c, dst, (const u64 *)d_keys, d_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0));
+    else if (method == RIMU_ANNIHILATE_PARTITION) TRY(records_to_vec_part(c, dst, (const u64 *)d_keys, d_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0));
+    else {
+        dst->nb = 0; dst->diag_uid = 0;
+        if (n <= 0) dst->n = 0;
+        for (int attempt = 0; n > 0; attempt++) {
+            CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
+            if (rimu_sort_annihilate_w1(c->stream, (SortScratch *)c->sort_scratch, (const u64 *)d_keys, (const u64 *)d_vals, n,
+                                        dst->vt == RIMU_VAL_I64, 64, dst->keys, (u64 *)dst->vals, dst->cap, &c->d_stats->out_count))
+                return fail(RIMU_ERR_CUDA, "sort-based annihilation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            if (c->h_stats->out_count > dst->cap) {
+                if (attempt > 2) return fail(RIMU_ERR_VECTOR_FULL, "destination vector cannot be grown");
+                dst->n = 0;
+                TRY(rimu_vec_reserve(dst, c->h_stats->out_count + c->h_stats->out_count / 4));
+                continue;
+            }
+            dst->n = (i64)c->h_stats->out_count;
+            break;
+        }
+    }
     CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
     CUDA_TRY(cudaEventSynchronize(c->ev[1]));
     if (ms_out) CUDA_TRY(cudaEventElapsedTime(ms_out, c->ev[0], c->ev[1]));

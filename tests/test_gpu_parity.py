@@ -152,10 +152,14 @@ def test_with_threshold_style(built):
         ok, ov = gk, gv
 
 
+@pytest.mark.parametrize("method", [0, 1, 2], ids=["hash", "sort", "partition"])
 @pytest.mark.parametrize("W,dtype", [(1, np.float64), (1, np.int64), (2, np.float64), (2, np.int64)])
-def test_annihilate_given_spawn_list(built, W, dtype):
-    """Annihilation of a given spawn list: bit-exact for Int64, 1e-12 for Float64; includes heavy
+def test_annihilate_given_spawn_list(built, W, dtype, method):
+    """Annihilation of a given spawn list with each method (HBM hash table, radix sort + segmented reduce,
+    bucket partition + shared-memory merge): bit-exact for Int64, 1e-12 for Float64; includes heavy
     duplication, exact cancellation, empty input."""
+    if method == 1 and W == 2:
+        pytest.skip("the sort method covers one-word addresses")
     import rimu_b200 as R
     rng = np.random.default_rng(3)
     at = R.AddressType(R._lib.ADDR_BOSE, (20,) if W == 1 else (60,), 20 if W == 1 else 60)
@@ -168,14 +172,18 @@ def test_annihilate_given_spawn_list(built, W, dtype):
             keys[1], vals[1] = keys[0], -vals[0]
         v = R.GPUDVec(style=style, address_type=at)
         R._lib.check(R._lib.lib().rimu_annihilate(v.handle, np.ascontiguousarray(keys).ctypes.data_as(R._lib._u64p),
-                                                  np.ascontiguousarray(vals).ctypes.data_as(R._lib._vp), n, 0))
+                                                  np.ascontiguousarray(vals).ctypes.data_as(R._lib._vp), n, method))
         gk, gv = v.download_sorted()
         ok, ov = orc.annihilate(W, keys, vals)
         assert np.array_equal(gk, ok)
         if dtype == np.int64:
             assert np.array_equal(gv, ov)
         else:
-            assert np.allclose(gv, ov, rtol=RTOL, atol=1e-15)
+            # Float64 sums in a different order: the error bound scales with the magnitude that was summed per address
+            ka, mag = orc.annihilate(W, keys, np.abs(vals))
+            scale = dict(zip(map(tuple, ka.tolist()), mag))
+            bound = np.array([scale[tuple(k)] for k in ok.tolist()]) if len(ok) else np.zeros(0)
+            assert np.all(np.abs(gv - ov) <= RTOL * bound + 1e-300)
 
 
 def test_vector_interface(built):
