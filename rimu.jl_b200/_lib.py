@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "librimu_b200.so")
+LIB_PATH = os.environ.get("RIMU_B200_LIB") or os.path.join(_HERE, "librimu_b200.so")  # override: kernel-tuning builds
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "sort.cu"]
 HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh"]
@@ -50,7 +50,7 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into rimu.jl_b200/librimu_b200.so (in-tree)."""
-    if not force and not _stale():
+    if os.environ.get("RIMU_B200_LIB") or (not force and not _stale()):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \

@@ -546,6 +546,10 @@ extern "C" int rimu_ham_words(const rimu_ham *h) { return h->W; }
 // compile-time dispatch over (HamKind, W)
 template <int HK, int W> struct HkTag { static constexpr int hk = HK; static constexpr int w = W; };
 template <class F> static int dispatch_ham(const rimu_ham *h, F &&f) {
+#ifdef RIMU_TUNE_ONLY_MOM1D // kernel-tuning builds (scratch/): one instantiation, seconds to compile; never shipped
+    if (h->hk == HK_MOM1D_BOSE && h->W == 1) return f(HkTag<HK_MOM1D_BOSE, 1>());
+    return fail(RIMU_ERR_INVALID, "tuning build: only HubbardMom1D/BoseFS one-word addresses are compiled in");
+#else
     switch (h->hk) {
     case HK_REAL1D_BOSE: return h->W == 1 ? f(HkTag<HK_REAL1D_BOSE, 1>()) : f(HkTag<HK_REAL1D_BOSE, 2>());
     case HK_MOM1D_BOSE: return h->W == 1 ? f(HkTag<HK_MOM1D_BOSE, 1>()) : f(HkTag<HK_MOM1D_BOSE, 2>());
@@ -556,6 +560,7 @@ template <class F> static int dispatch_ham(const rimu_ham *h, F &&f) {
     case HK_TC_F2C: return f(HkTag<HK_TC_F2C, 1>());
     }
     return fail(RIMU_ERR_INVALID, "unknown Hamiltonian kind");
+#endif
 }
 
 static int check_ctx_ham(rimu_ctx *c, const rimu_ham *h) {

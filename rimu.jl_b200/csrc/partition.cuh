@@ -27,13 +27,26 @@
 #pragma once
 #include "kernels.cuh"
 
+#ifndef PART_NT
 #define PART_NT 256        // threads of a merge CTA
+#endif
+#ifndef PART_CAP
+#define PART_CAP 2048      // items (parents + records) a bucket may hold
+#endif
+#ifndef PART_MINB
+#define PART_MINB 4        // merge CTAs resident per SM (register cap)
+#endif
+#ifndef SPAWN_NT
 #define SPAWN_NT 256       // threads (= parents per chunk) of a spawn CTA
+#endif
+#ifndef SPAWN_MINB
+#define SPAWN_MINB 4       // spawn CTAs resident per SM (register cap)
+#endif
 #define HEAVY_T 1024       // parents with more attempts than this are queued for K2
 #define HEAVY_TILE 8192    // attempts per K2 work item
 #define ACC_MAX 4096       // K2 pre-sums per off-diagonal index when L <= ACC_MAX
 
-template <int W> struct PartCap { static constexpr int value = 2048; }; // items (parents + records) a bucket may hold
+template <int W> struct PartCap { static constexpr int value = PART_CAP; };
 
 struct PartDev {       // bucket record streams (working memory of the partitioned step)
     u32 nb;            // buckets on this rank
@@ -151,7 +164,7 @@ DEV VT spawn_attempt(const HamDev &h, const StepDev &p, typename BitsT<W>::type 
 
 // ---------------------------------------------------------------- K1: spawning, CTA-local work distribution
 template <int HK, int W, class VT>
-__global__ void __launch_bounds__(SPAWN_NT)
+__global__ void __launch_bounds__(SPAWN_NT, SPAWN_MINB)
 spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
                   PartDev pt, ExchangeDev xch, HeavyDev hv, StatsDev *st) {
     typedef typename BitsT<W>::type B;
@@ -365,7 +378,7 @@ diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
 // the owner table; keys are compared through the item index, so nothing has to be published after a claim.
 // After placement the owner table is dead and is reused as the list of survivors that still need H_aa.
 template <int HK, int W, class VT, int MODE>
-__global__ void __launch_bounds__(PART_NT, 4)
+__global__ void __launch_bounds__(PART_NT, PART_MINB)
 merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st) {
     typedef typename BitsT<W>::type B;
     constexpr bool is_int = std::is_integral<VT>::value;

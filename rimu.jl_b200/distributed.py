@@ -10,16 +10,21 @@ from . import _lib
 from .hamiltonians import Context, _contexts
 
 
-def init_distributed(words: int, records_per_peer: int = 1 << 22, table_slots: int | None = None) -> Context:
-    """Create this rank's context for `words`-word addresses and attach an NCCL communicator."""
+def init_distributed(words: int, records_per_peer: int = 1 << 22, table_slots: int | None = None, fresh: bool = False) -> Context:
+    """Create this rank's context for `words`-word addresses and attach an NCCL communicator.
+    `fresh=True` makes an additional, independent context (own stream, working memory and communicator) --
+    one per replica when several independent vectors are advanced concurrently (n_replicas,
+    projector_monte_carlo_problem.jl:152,205)."""
     import torch
     import torch.distributed as dist
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    ctx = _contexts.get(words)
+    ctx = None if fresh else _contexts.get(words)
     if ctx is None:
-        ctx = _contexts[words] = Context(words, device=local, table_slots=table_slots)
+        ctx = Context(words, device=local, table_slots=table_slots)
+        if not fresh:
+            _contexts[words] = ctx
     if world == 1 or ctx.nranks == world:
         return ctx
     if not dist.is_initialized():

@@ -1,0 +1,187 @@
+"""Physics-level parity on the GPU (north_star's second and third correctness checks):
+
+* ground-state energies from the device matrix-free H*v (Lanczos over `mul!`) agree with exact
+  diagonalisation (oracle BFS basis + dense/sparse eigensolver, the job Rimu's ExactDiagonalization does);
+* stochastic FCIQMC runs reproduce the shift and projected energy within blocking-analysis error bars
+  (+ the known population-control bias allowance), including the reference's own pinned case
+  scripts/BHM-example.jl:157-158 (shift ~ -4.0215, rtol 0.1);
+* size-independent properties at large vector sizes: the two annihilation methods give the same step,
+  H*v is linear, and <x|H y> = <H x|y> for the Hermitian models.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from tests.cases import oracle_ham, product_ham
+
+pytestmark = pytest.mark.gpu
+
+
+def exact_energy(oh):
+    """Oracle ED: dense for small sectors; for larger ones a sparse Lanczos started from the single start
+    determinant (exactly what the reference's `exact_energy` helper does, test/Hamiltonians.jl:13-17)."""
+    basis = oh.bfs_basis()
+    if len(basis) <= 3000:
+        return oh.exact_energy()
+    import scipy.sparse.linalg as spla
+    Hs = oh.sparse_matrix(basis)
+    v0 = np.zeros(len(basis))
+    v0[0] = 1.0
+    w = spla.eigsh(Hs, k=1, which="SA", v0=v0, tol=1e-12)[0]
+    return float(w[0])
+
+
+# --------------------------------------------------------------------------- Lanczos vs ED
+@pytest.mark.parametrize("name", ["real1d_6", "mom1d_bose", "rs_bose_2d", "rs_fermi", "rs_f2c_4x4", "rs_f2c_trap", "mom1d_f2c"])
+def test_lanczos_ground_state_matches_exact_diagonalization(built, name):
+    import rimu_b200 as R
+    oh, ph = oracle_ham(name), product_ham(name)
+    e_exact = exact_energy(oh)  # lowest eigenvalue overlapping the starting address (SURVEY.md 8c lesson 2)
+    start = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    vals, vecs, info = R.eigsolve_lanczos(ph, start, krylovdim=80, tol=1e-10, maxiter=30, full_reorth=True)
+    assert info["converged"], (name, info)
+    assert math.isclose(vals[0], e_exact, rel_tol=1e-9, abs_tol=1e-9), (name, vals[0], e_exact)
+    # Rayleigh quotient of the returned Ritz vector through the three-argument dot (pdvec.jl:866-879)
+    v = vecs[0]
+    rq = R.dot(v, ph, v) / v.dot(v)
+    assert math.isclose(rq, e_exact, rel_tol=1e-8, abs_tol=1e-8), (name, rq, e_exact)
+
+
+def test_bhm_example_pinned_energy(built):
+    """scripts/BHM-example.jl as shipped: 6 sites / 6 bosons, u=6, IsDynamicSemistochastic, 1000 walkers,
+    dtau=0.001, 3000 steps; the script asserts shift ~ -4.0215 (rtol 0.1)."""
+    import rimu_b200 as R
+    addr = R.near_uniform(R.BoseFS, 6, 6)
+    H = R.HubbardReal1D(addr, u=6.0, t=1.0)
+    e_exact = oracle_ham("real1d_6").exact_energy()
+    assert math.isclose(e_exact, -4.0215, abs_tol=1e-3)
+    ref = R.GPUDVec([(addr, 1.0)], style=R.IsDeterministic())
+    prob = R.ProjectorMonteCarloProblem(H, start_at=addr, style=R.IsDynamicSemistochastic(), time_step=0.001,
+                                        last_step=6000, target_walkers=1000, random_seed=17,
+                                        post_step_strategy=(R.ProjectedEnergy(H, ref),))
+    sim = R.solve(prob)
+    assert sim.success
+    df = sim.dataframe()
+    se = R.shift_estimator(df, skip=2000)
+    pe = R.projected_energy(df, skip=2000)
+    assert math.isclose(se.mean, -4.0215, rel_tol=0.1)  # the reference's own assertion
+    # blocking error bars: 5 sigma + population-control bias allowance of 1 %
+    assert abs(se.mean - e_exact) < 5 * se.err + 0.01 * abs(e_exact), (se.mean, se.err, e_exact)
+    assert abs(pe.f - e_exact) < 5 * pe.sigma_f + 0.01 * abs(e_exact), (pe.f, pe.sigma_f, e_exact)
+
+
+@pytest.mark.parametrize("name,style_name,walkers,dtau,steps", [
+    ("real1d_10", "int", 10_000, 0.002, 4000),    # BASELINE config 1
+    ("mom1d_bose", "semi", 2_000, 0.002, 4000),
+    ("rs_f2c_4x4", "semi", 3_000, 0.005, 4000),    # 2D Fermi-Hubbard, 2 up 2 down (sign problem mild at this size)
+])
+def test_fciqmc_energy_within_error_bars(built, name, style_name, walkers, dtau, steps):
+    import rimu_b200 as R
+    oh, ph = oracle_ham(name), product_ham(name)
+    e_exact = exact_energy(oh)
+    style = R.IsStochasticInteger() if style_name == "int" else R.IsDynamicSemistochastic()
+    ref = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=style, time_step=dtau, last_step=steps,
+                                        target_walkers=walkers, random_seed=5, max_length=50 * walkers,
+                                        post_step_strategy=(R.ProjectedEnergy(ph, ref),))
+    sim = R.solve(prob)
+    assert sim.success, sim.message
+    df = sim.dataframe()
+    skip = steps // 3
+    se = R.shift_estimator(df, skip=skip)
+    pe = R.projected_energy(df, skip=skip)
+    tol_bias = 0.01 * abs(e_exact)
+    assert abs(se.mean - e_exact) < 5 * se.err + tol_bias, (name, se.mean, se.err, e_exact)
+    assert abs(pe.f - e_exact) < 5 * pe.sigma_f + tol_bias, (name, pe.f, pe.sigma_f, e_exact)
+    n = np.asarray(df["norm"])[skip:]
+    assert abs(n.mean() - walkers) < 0.1 * walkers  # DoubleLogUpdate holds the population
+
+
+# --------------------------------------------------------------------------- size-independent properties
+def _grow(R, ph, n_target, style):
+    """Deterministic growth of a large vector: repeated H*v from the starting address until it holds
+    at least n_target determinants (values rescaled to O(1))."""
+    x = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    wm = R.working_memory(x)
+    while len(x) < n_target:
+        y = x.similar()
+        R.mul(y, ph, x, wm)
+        y.scale_(1.0 / y.norm(np.inf))
+        x = y
+    if len(x) > 2 * n_target:  # one more hop can overshoot by orders of magnitude: keep a seeded subset
+        keys, vals = x.download_sorted()
+        keep = np.sort(np.random.default_rng(7).choice(len(vals), size=2 * n_target, replace=False))
+        x = R.GPUDVec(style=R.IsDeterministic(), address_type=x.address_type, ctx=x.ctx)
+        x.assign(keys[keep], vals[keep])
+    if style is None:
+        return x
+    keys, vals = x.download()
+    v = R.GPUDVec(style=style, address_type=x.address_type, ctx=x.ctx)
+    if style.val_type == R._lib.VAL_I64:
+        vals = np.where(vals >= 0, 1, -1).astype(np.int64) * np.maximum(1, np.round(np.abs(vals) * 3)).astype(np.int64)
+    else:
+        vals = vals * 3.0
+    v.assign(keys, vals)
+    return v
+
+
+@pytest.mark.parametrize("name,style_name", [("mom1d_bose_20", "semi"), ("rs_bose_3d_w2", "int"), ("tc_32", "semi")])
+def test_methods_agree_at_scale(built, name, style_name):
+    """A step is a pure function of (seed, step, source): the HBM hash-table method and the partitioned
+    method must produce the same vector on >= 3e5 determinants (configs 2, 4, 5 models)."""
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+    ph = product_ham(name)
+    style = R.IsStochasticInteger() if style_name == "int" else R.IsDynamicSemistochastic()
+    v = _grow(R, ph, 300_000, style)
+    shift = R.diagonal_element(ph, ph.address)
+    out = {}
+    for method in (0, 2):  # RIMU_ANNIHILATE_HASH, RIMU_ANNIHILATE_PARTITION
+        _lib.check(_lib.lib().rimu_ctx_set_method(v.ctx.handle, method))
+        wm = R.working_memory(v, seed=99)
+        cur = v
+        for _ in range(2):
+            nxt = cur.similar()
+            R.apply_operator(wm, nxt, cur, R.FirstOrderTransitionOperator(ph, shift, 1e-3))
+            cur = nxt
+        out[method] = cur.download_sorted() + (wm.last_stats.spawn_attempts, wm.last_stats.len)
+    _lib.check(_lib.lib().rimu_ctx_set_method(v.ctx.handle, 2))
+    (k0, v0, a0, l0), (k2, v2, a2, l2) = out[0], out[2]
+    assert a0 == a2 and l0 == l2
+    assert np.array_equal(k0, k2)
+    if style_name == "int":
+        assert np.array_equal(v0, v2)
+    else:
+        assert np.allclose(v0, v2, rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("name", ["mom1d_bose_20", "rs_f2c_half", "rs_bose_3d_w2"])
+def test_hv_linearity_and_symmetry_at_scale(built, name):
+    """H(a x + b y) = a H x + b H y and <x|H y> = <H x|y> on vectors of >= 2e5 determinants (Hermitian models)."""
+    import rimu_b200 as R
+    ph = product_ham(name)
+    x = _grow(R, ph, 200_000, None)
+    wm = R.working_memory(x)
+    y = x.similar()
+    R.mul(y, ph, x, wm)
+    y.scale_(1.0 / y.norm(2))
+    x.scale_(1.0 / x.norm(2))
+    a, b = 0.75, -1.25
+    hx, hy = x.similar(), x.similar()
+    R.mul(hx, ph, x, wm)
+    R.mul(hy, ph, y, wm)
+    # symmetry
+    lhs, rhs = x.dot(hy), hx.dot(y)
+    assert math.isclose(lhs, rhs, rel_tol=1e-10, abs_tol=1e-12), (lhs, rhs)
+    # linearity
+    z = x.copy()
+    z.axpby_(b, y, a)  # z = b*y + a*z
+    hz = z.similar()
+    R.mul(hz, ph, z, wm)
+    comb = hx.copy()
+    comb.axpby_(b, hy, a)
+    diff = hz.copy()
+    diff.add_(comb, -1.0)
+    assert diff.norm(2) <= 1e-12 * max(1.0, hz.norm(2)), (diff.norm(2), hz.norm(2))
