@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -26,12 +27,35 @@ static int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+// cudaMalloc with diagnostics: RIMU_B200_TRACE_ALLOC=1 logs every allocation above 64 MiB; a failure reports the
+// request and the free/total device memory and clears CUDA's "last error" so that it cannot surface at a later,
+// unrelated cudaGetLastError() check
+static size_t g_alloc_fail_bytes = 0;
+template <class T> static cudaError_t rimu_malloc(T **p, size_t bytes) {
+    static const bool trace = getenv("RIMU_B200_TRACE_ALLOC") != nullptr;
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (trace && bytes >= (64u << 20)) {
+        size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+        fprintf(stderr, "[rimu_b200] cudaMalloc %.1f MiB -> %s (free %.1f GiB of %.1f GiB)\n", bytes / 1048576.0,
+                e == cudaSuccess ? "ok" : cudaGetErrorString(e), fr / 1073741824.0, tot / 1073741824.0);
+    }
+    if (e != cudaSuccess) { g_alloc_fail_bytes = bytes; cudaGetLastError(); }
+    return e;
+}
+static std::string oom_note() {
+    size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
+    char b[160];
+    snprintf(b, sizeof(b), " [requested %.1f MiB; device has %.1f GiB free of %.1f GiB]", g_alloc_fail_bytes / 1048576.0,
+             fr / 1073741824.0, tot / 1073741824.0);
+    return b;
+}
 #define CUDA_TRY(x)                                                                                   \
     do {                                                                                              \
         cudaError_t e_ = (x);                                                                         \
         if (e_ != cudaSuccess)                                                                        \
             return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RIMU_ERR_NO_DEVICE : RIMU_ERR_CUDA, \
-                        "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+                        "%s failed: %s (%s:%d)%s", #x, cudaGetErrorString(e_), __FILE__, __LINE__,    \
+                        e_ == cudaErrorMemoryAllocation ? oom_note().c_str() : "");                   \
     } while (0)
 #define TRY(x)              \
     do {                    \
@@ -180,11 +204,11 @@ extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->table_slots = next_pow2(table_slots < 1024 ? 1024 : table_slots);
-    CUDA_TRY(cudaMalloc(&c->table, c->table_slots * (words == 1 ? 16 : 32)));
-    CUDA_TRY(cudaMalloc(&c->d_stats, sizeof(StatsDev)));
+    CUDA_TRY(rimu_malloc(&c->table, c->table_slots * (words == 1 ? 16 : 32)));
+    CUDA_TRY(rimu_malloc(&c->d_stats, sizeof(StatsDev)));
     CUDA_TRY(cudaMallocHost(&c->h_stats, sizeof(StatsDev)));
     CUDA_TRY(cudaMallocHost(&c->h_stats_local, sizeof(StatsDev)));
-    CUDA_TRY(cudaMalloc(&c->d_reduce, 64 * sizeof(double)));
+    CUDA_TRY(rimu_malloc(&c->d_reduce, 64 * sizeof(double)));
     for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
     TRY(table_fill(c, c->table_slots));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -237,9 +261,29 @@ extern "C" int rimu_ctx_resize_table(rimu_ctx *c, uint64_t table_slots) {
     u64 slots = next_pow2(table_slots < 1024 ? 1024 : table_slots);
     if (slots == c->table_slots) return 0;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(c->table);
-    c->table = nullptr; c->table_slots = 0;
-    CUDA_TRY(cudaMalloc(&c->table, slots * (c->W == 1 ? 16 : 32)));
+    if (slots > c->table_slots) { // growing: keep the old table if the new one cannot be allocated
+        u64 *nt = nullptr;
+        size_t fr = 0, tot = 0;
+        CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+        const size_t need = slots * (c->W == 1 ? 16 : 32), have = c->table_slots * (c->W == 1 ? 16 : 32);
+        if (need > fr + have) { g_alloc_fail_bytes = need; return fail(RIMU_ERR_CUDA, "working table of %llu slots does not fit%s", (unsigned long long)slots, oom_note().c_str()); }
+        if (need > fr) { cudaFree(c->table); c->table = nullptr; c->table_slots = 0; } // (contents are scratch; only room matters)
+        cudaError_t e = rimu_malloc(&nt, need);
+        if (e != cudaSuccess) {
+            if (!c->table) { // put a minimal table back so that the context stays usable
+                CUDA_TRY(rimu_malloc(&c->table, 1024 * (c->W == 1 ? 16 : 32)));
+                c->table_slots = 1024;
+                TRY(table_fill(c, 1024));
+            }
+            return fail(RIMU_ERR_CUDA, "working table of %llu slots: %s%s", (unsigned long long)slots, cudaGetErrorString(e), oom_note().c_str());
+        }
+        cudaFree(c->table);
+        c->table = nt;
+    } else {
+        cudaFree(c->table);
+        c->table = nullptr; c->table_slots = 0;
+        CUDA_TRY(rimu_malloc(&c->table, slots * (c->W == 1 ? 16 : 32)));
+    }
     c->table_slots = slots;
     TRY(table_fill(c, slots));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -252,9 +296,9 @@ static int ensure_scratch(rimu_ctx *c, u64 parents) {
     cudaFree(c->local_off); cudaFree(c->block_tot); cudaFree(c->block_base);
     c->local_off = c->block_tot = c->block_base = nullptr; c->scratch_parents = 0;
     u64 nblk = (cap + RIMU_TPB - 1) / RIMU_TPB;
-    CUDA_TRY(cudaMalloc(&c->local_off, cap * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->block_tot, nblk * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->block_base, (nblk + 1) * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->local_off, cap * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->block_tot, nblk * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->block_base, (nblk + 1) * sizeof(u64)));
     c->scratch_parents = cap;
     return 0;
 }
@@ -263,8 +307,8 @@ static int ensure_stage(rimu_ctx *c, u64 n) {
     u64 cap = n + n / 4 + 1024;
     cudaFree(c->stage_keys); cudaFree(c->stage_vals);
     c->stage_keys = nullptr; c->stage_vals = nullptr; c->stage_cap = 0;
-    CUDA_TRY(cudaMalloc(&c->stage_keys, cap * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->stage_vals, cap * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->stage_keys, cap * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->stage_vals, cap * sizeof(u64)));
     c->stage_cap = cap;
     return 0;
 }
@@ -275,8 +319,8 @@ static int ensure_seg(rimu_vec *v, u32 nb) {
     u64 cap = (u64)nb + nb / 2 + 64;
     cudaFree(v->seg_start); cudaFree(v->seg_len);
     v->seg_start = nullptr; v->seg_len = nullptr; v->seg_cap = 0; v->nb = 0;
-    CUDA_TRY(cudaMalloc(&v->seg_start, cap * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&v->seg_len, cap * sizeof(u32)));
+    CUDA_TRY(rimu_malloc(&v->seg_start, cap * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&v->seg_len, cap * sizeof(u32)));
     v->seg_cap = cap;
     return 0;
 }
@@ -288,18 +332,18 @@ static int ensure_part(rimu_ctx *c, u32 nb) {
     u64 cap = (u64)nb + nb / 4 + 16;
     cudaFree(c->part.rec_keys); cudaFree(c->part.rec_vals); cudaFree(c->part.rec_count);
     c->part.rec_keys = c->part.rec_vals = nullptr; c->part.rec_count = nullptr; c->part_nb_cap = 0;
-    CUDA_TRY(cudaMalloc(&c->part.rec_keys, cap * c->part.rcap * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->part.rec_vals, cap * c->part.rcap * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->part.rec_count, cap * sizeof(u32)));
+    CUDA_TRY(rimu_malloc(&c->part.rec_keys, cap * c->part.rcap * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->part.rec_vals, cap * c->part.rcap * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->part.rec_count, cap * sizeof(u32)));
     c->part_nb_cap = cap; c->part.nb = nb;
     return 0;
 }
 static int ensure_heavy(rimu_ctx *c, u64 parents) {
-    if (!c->heavy.packed) CUDA_TRY(cudaMalloc(&c->heavy.packed, sizeof(u64)));
+    if (!c->heavy.packed) CUDA_TRY(rimu_malloc(&c->heavy.packed, sizeof(u64)));
     if (parents <= c->heavy.cap) return 0;
     u64 cap = parents + parents / 4 + 1024;
     cudaFree(c->heavy.items); c->heavy.items = nullptr; c->heavy.cap = 0;
-    CUDA_TRY(cudaMalloc(&c->heavy.items, cap * sizeof(HeavyItem)));
+    CUDA_TRY(rimu_malloc(&c->heavy.items, cap * sizeof(HeavyItem)));
     c->heavy.cap = cap;
     return 0;
 }
@@ -307,7 +351,7 @@ static int ensure_bucket_tmp(rimu_ctx *c, u32 nb) {
     if (nb <= c->bucket_tmp_cap) return 0;
     u64 cap = (u64)nb + nb / 2 + 64;
     cudaFree(c->bucket_tmp); c->bucket_tmp = nullptr; c->bucket_tmp_cap = 0;
-    CUDA_TRY(cudaMalloc(&c->bucket_tmp, 2 * cap * sizeof(u32)));
+    CUDA_TRY(rimu_malloc(&c->bucket_tmp, 2 * cap * sizeof(u32)));
     c->bucket_tmp_cap = cap;
     return 0;
 }
@@ -337,7 +381,7 @@ static int p2p_setup(rimu_ctx *c) { // collective
     const size_t HS = sizeof(cudaIpcMemHandle_t);
     double bad = (env && !strcmp(env, "0")) ? 1.0 : 0.0;
     if (!c->d_ipc) {
-        CUDA_TRY(cudaMalloc(&c->d_ipc, (size_t)RIMU_MAX_RANKS * 2 * HS));
+        CUDA_TRY(rimu_malloc(&c->d_ipc, (size_t)RIMU_MAX_RANKS * 2 * HS));
         CUDA_TRY(cudaMallocHost(&c->h_ipc, (size_t)RIMU_MAX_RANKS * 2 * HS));
     }
     cudaIpcMemHandle_t mine[2];
@@ -384,14 +428,14 @@ extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nran
     NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
     if (per_peer < 1024) per_peer = 1024;
     c->xch.cap = per_peer;
-    CUDA_TRY(cudaMalloc(&c->xch.keys, (u64)nranks * per_peer * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->xch.vals, (u64)nranks * per_peer * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->xch.counts, RIMU_MAX_RANKS * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->xch.keys, (u64)nranks * per_peer * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->xch.vals, (u64)nranks * per_peer * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->xch.counts, RIMU_MAX_RANKS * sizeof(u64)));
     CUDA_TRY(cudaMemset(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64)));
     c->recv_cap = (u64)nranks * per_peer;
-    CUDA_TRY(cudaMalloc(&c->recv_keys, c->recv_cap * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->recv_vals, c->recv_cap * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->d_allcounts, (u64)nranks * nranks * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->recv_keys, c->recv_cap * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->recv_vals, c->recv_cap * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->d_allcounts, (u64)nranks * nranks * sizeof(u64)));
     CUDA_TRY(cudaMallocHost(&c->h_allcounts, (u64)nranks * nranks * sizeof(u64)));
     memset(c->h_allcounts, 0, (size_t)nranks * nranks * sizeof(u64));
     return p2p_setup(c);
@@ -405,10 +449,10 @@ extern "C" int rimu_comm_reserve(rimu_ctx *c, uint64_t per_peer) {
     p2p_teardown(c);
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->recv_keys); cudaFree(c->recv_vals);
     c->xch.keys = c->xch.vals = c->recv_keys = c->recv_vals = nullptr; c->xch.cap = 0; c->recv_cap = 0;
-    CUDA_TRY(cudaMalloc(&c->xch.keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->xch.vals, (u64)c->nranks * per_peer * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->recv_keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&c->recv_vals, (u64)c->nranks * per_peer * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->xch.keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->xch.vals, (u64)c->nranks * per_peer * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->recv_keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->recv_vals, (u64)c->nranks * per_peer * sizeof(u64)));
     c->xch.cap = per_peer; c->recv_cap = (u64)c->nranks * per_peer;
     return p2p_setup(c);
 }
@@ -507,6 +551,7 @@ extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
     v.ndim = d->ndim; v.nnb = 2 * d->ndim; v.cutoff = d->cutoff; v.three_body = d->three_body_term; v.has_pot = d->has_potential;
     v.u = d->u; v.t = d->t; v.v = d->v; v.tc0 = d->t_comp[0]; v.tc1 = d->t_comp[1];
     v.u00 = d->u_mat[0]; v.u10 = d->u_mat[1];
+    v.u_2m = d->u / (2 * M); v.u_m = d->u / M;
     int nz = 0;
     for (int i = 0; i < d->num_components * d->num_components; i++) nz += d->u_mat[(i % d->num_components) + 2 * (i / d->num_components)] != 0.0;
     v.umat_zero = nz == 0;
@@ -516,7 +561,7 @@ extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
     memcpy(&tab[RIMU_MAX_TABLE_MODES], d->ws, sizeof(d->ws));
     memcpy(&tab[2 * RIMU_MAX_TABLE_MODES], d->us, sizeof(d->us));
     memcpy(&tab[3 * RIMU_MAX_TABLE_MODES], d->potential, sizeof(d->potential));
-    CUDA_TRY(cudaMalloc(&h->d_tables, tab.size() * sizeof(double)));
+    CUDA_TRY(rimu_malloc(&h->d_tables, tab.size() * sizeof(double)));
     CUDA_TRY(cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     v.kes = h->d_tables; v.ws = h->d_tables + RIMU_MAX_TABLE_MODES; v.us = h->d_tables + 2 * RIMU_MAX_TABLE_MODES;
     v.pot = h->d_tables + 3 * RIMU_MAX_TABLE_MODES;
@@ -528,7 +573,7 @@ extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
         std::vector<unsigned char> nbr((size_t)M * v.nnb);
         for (int s = 1; s <= M; s++)
             for (int c = 1; c <= v.nnb; c++) nbr[(size_t)(s - 1) * v.nnb + (c - 1)] = (unsigned char)neighbor_site_host(d, s, c);
-        CUDA_TRY(cudaMalloc(&h->d_nbr, nbr.size()));
+        CUDA_TRY(rimu_malloc(&h->d_nbr, nbr.size()));
         CUDA_TRY(cudaMemcpy(h->d_nbr, nbr.data(), nbr.size(), cudaMemcpyHostToDevice));
         v.nbr = h->d_nbr;
     }
@@ -632,8 +677,8 @@ extern "C" int rimu_vec_create(rimu_ctx *c, int val_type, uint64_t capacity, rim
     v->keys = nullptr; v->vals = nullptr;
     v->nb = 0; v->seg_cap = 0; v->seg_start = nullptr; v->seg_len = nullptr;
     v->diag = nullptr; v->diag_cap = 0; v->diag_uid = 0;
-    CUDA_TRY(cudaMalloc(&v->keys, v->cap * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&v->vals, v->cap * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&v->keys, v->cap * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&v->vals, v->cap * sizeof(u64)));
     *out = v;
     return 0;
 }
@@ -650,15 +695,15 @@ extern "C" int rimu_vec_reserve(rimu_vec *v, uint64_t capacity) {
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     u64 *nk = nullptr; void *nv = nullptr;
-    CUDA_TRY(cudaMalloc(&nk, capacity * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&nv, capacity * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&nk, capacity * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&nv, capacity * sizeof(u64)));
     if (v->n > 0) {
         CUDA_TRY(cudaMemcpyAsync(nk, v->keys, v->n * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
         CUDA_TRY(cudaMemcpyAsync(nv, v->vals, v->n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
     }
     double *nd = nullptr;
     if (v->diag) {
-        CUDA_TRY(cudaMalloc(&nd, capacity * sizeof(double)));
+        CUDA_TRY(rimu_malloc(&nd, capacity * sizeof(double)));
         if (v->n > 0 && v->diag_uid) CUDA_TRY(cudaMemcpyAsync(nd, v->diag, v->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -670,7 +715,7 @@ extern "C" int rimu_vec_reserve(rimu_vec *v, uint64_t capacity) {
 static int ensure_diag(rimu_vec *v) {
     if (v->diag && v->diag_cap >= v->cap) return 0;
     cudaFree(v->diag); v->diag = nullptr; v->diag_cap = 0; v->diag_uid = 0;
-    CUDA_TRY(cudaMalloc(&v->diag, v->cap * sizeof(double)));
+    CUDA_TRY(rimu_malloc(&v->diag, v->cap * sizeof(double)));
     v->diag_cap = v->cap;
     return 0;
 }
@@ -712,6 +757,7 @@ static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const v
     CUDA_TRY(cudaSetDevice(c->device));
     dst->nb = 0; dst->diag_uid = 0; // the global-table path produces an unsegmented vector
     u64 slots = pick_slots(c, (u64)(n + n2));
+    const bool aliased = (const u64 *)dst->keys == d_keys || (const u64 *)dst->keys == d_keys2;
     for (;;) {
         CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
         TableDev tab{c->table, slots - 1};
@@ -724,19 +770,32 @@ static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const v
             if (n2 > 0)
                 insert_records_kernel<W, VT><<<grid_for(n2, c->sm_count), RIMU_TPB, 0, c->stream>>>(
                     d_keys2, (const VT *)d_vals2, n2, a2, use_scale, c->rank, c->nranks, tab, c->d_stats);
+            return 0;
+        }));
+        CUDA_TRY(cudaGetLastError());
+        // the table must hold EVERYTHING before it is drained: dst may alias an input, and a partial drain would
+        // overwrite records that the retry still has to read
+        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (c->h_stats->overflow_table) {
+            TRY(table_fill(c, slots)); // forget the partial contents
+            if (slots >= c->table_slots) {
+                if (c->table_slots >= (1ull << 34)) return fail(RIMU_ERR_TABLE_FULL, "working table (%llu slots) too small for %lld records", (unsigned long long)c->table_slots, (long long)(n + n2));
+                TRY(rimu_ctx_resize_table(c, c->table_slots * 4));
+            }
+            slots = slots * 4 > c->table_slots ? c->table_slots : slots * 4;
+            continue;
+        }
+        TRY(dispatch_wv(c->W, dst->vt, [&](auto tag, auto vtag) {
+            typedef decltype(vtag) VT;
+            constexpr int W = decltype(tag)::w;
             return compact_into<W, VT>(c, dst, slots, null_step(c));
         }));
         CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (c->h_stats->overflow_table) {
-            if (slots >= c->table_slots)
-                return fail(RIMU_ERR_TABLE_FULL, "working table (%llu slots) too small for %lld records", (unsigned long long)c->table_slots, (long long)(n + n2));
-            slots = slots * 4 > c->table_slots ? c->table_slots : slots * 4;
-            continue;
-        }
         if (c->h_stats->out_count > dst->cap) {
             // the table has been drained; grow and redo (inputs are untouched unless dst aliases them)
-            if ((const u64 *)dst->keys == d_keys || (const u64 *)dst->keys == d_keys2)
+            if (aliased)
                 return fail(RIMU_ERR_VECTOR_FULL, "destination (aliasing an input) too small: need %llu", (unsigned long long)c->h_stats->out_count);
             dst->n = 0;
             TRY(rimu_vec_reserve(dst, c->h_stats->out_count + c->h_stats->out_count / 4));
@@ -1151,8 +1210,8 @@ static int rebucket(rimu_vec *v, u32 nb) {
     u32 *counts = c->bucket_tmp, *fill = c->bucket_tmp + c->bucket_tmp_cap;
     CUDA_TRY(cudaMemsetAsync(counts, 0, nb * sizeof(u32), c->stream));
     u64 *nk = nullptr, *nv = nullptr;
-    CUDA_TRY(cudaMalloc(&nk, v->cap * c->W * sizeof(u64)));
-    CUDA_TRY(cudaMalloc(&nv, v->cap * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&nk, v->cap * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&nv, v->cap * sizeof(u64)));
     const int grid = grid_for(v->n, c->sm_count, 16);
     if (c->W == 1) bucket_count_kernel<1><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, v->n, c->nranks, nb, counts);
     else bucket_count_kernel<2><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, v->n, c->nranks, nb, counts);

@@ -29,11 +29,16 @@ enum HamKind {
 struct HamDev {
     int hk, M, N0, N1, ndim, nnb, cutoff, three_body, has_pot, umat_zero;
     double u, t, v, tc0, tc1, u00, u10;
+    double u_2m, u_m; // u / (2M), u / M: the same IEEE divisions the reference evaluates per element, done once on the host
     const double *kes, *ws, *us, *pot; // device tables
     const unsigned char *nbr;          // HubbardRealSpace: nbr[(site-1)*nnb + dir] = neighbour site (1-based) or 0
 };
 
 #ifdef __CUDACC__
+// exact x / d for x < 2^21, 0 < d < 2^10 (off-diagonal index decoding): (x + 0.5) / d is at least 0.5/d away from
+// an integer, far more than the float rounding error at these magnitudes, so truncation gives floor(x / d)
+DEV unsigned udiv_small(unsigned x, unsigned d) { return (unsigned)__float2uint_rz(((float)x + 0.5f) * __frcp_rn((float)d)); }
+
 // ---------------------------------------------------------------- boson primitives
 template <class B> DEV int bose_mode_offset(B x, int m) { return m == 1 ? 0 : select_((B)~x, m - 2) + 1; }
 template <class B> DEV B delete_bit(B x, int p) { return (x & lowmask<B>(p)) | ((x >> (p + 1)) << p); }
@@ -145,10 +150,12 @@ DEV double tc_three_body_diag(const HamDev &h, u64 fa, int nb) {
 DEV double mom_transfer_2c(int M, u64 &fa, u64 &fb, int Nb, long long i64_, bool fold, int &p, int &q, int &mk) {
     const unsigned i = (unsigned)i64_, nb = (unsigned)Nb; // indices are < 2^31 (checked at rimu_ham_create)
     const unsigned per_a = (unsigned)(M - 1) * nb;
-    int src_a = (int)(i / per_a);
-    const unsigned rem = i % per_a;
-    int dst_a = (int)(rem / nb) + 1; // 1..M-1
-    int src_b = (int)(rem % nb);
+    const unsigned qa = udiv_small(i, per_a); // i < N1*N2*(M-1) <= 2^15, per_a < 2^10
+    int src_a = (int)qa;
+    const unsigned rem = i - qa * per_a;
+    const unsigned qb = udiv_small(rem, nb);
+    int dst_a = (int)qb + 1; // 1..M-1
+    int src_b = (int)(rem - qb * nb);
     int src_a_mode = select_(fa, src_a) + 1, src_b_mode = select_(fb, src_b) + 1;
     if (dst_a >= src_a_mode) dst_a += 1;
     int mom = dst_a - src_a_mode;
@@ -213,11 +220,11 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         // sum n(n-1) + 4 sum_{i>j} n_i n_j with sum n = N and sum n^2 = lin + N
         const int ntot = h.N0;
         const long long onproduct = (long long)lin + 2LL * ((long long)ntot * ntot - lin - ntot);
-        return ke + h.u / (2 * M) * (double)onproduct;
+        return ke + h.u_2m * (double)onproduct;
     } else if constexpr (HK == HK_MOM1D_F2C) {
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
         double ka = kes_sum(h.kes, fa), kb = kes_sum(h.kes, fb);
-        return ka + kb + h.u / (2 * M) * (double)(2 * __popcll(fa) * __popcll(fb));
+        return ka + kb + h.u_2m * (double)(2 * __popcll(fa) * __popcll(fb));
     } else if constexpr (HK == HK_RS_BOSE) {
         double interaction = h.umat_zero ? 0.0 : h.u00 * (double)bose_interaction(x) / 2;
         double pot = 0.0;
@@ -305,15 +312,16 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         int src0, src1, off0, off1, n0, n1, mom;
         if (ii >= ndiff) { // both particles from one mode with n >= 2
             const unsigned dbl = (unsigned)(ii - ndiff), mm1 = (unsigned)(M - 1);
-            const int d = (int)(dbl / mm1);
-            mom = (int)(dbl % mm1) + 1;
+            const int d = (int)udiv_small(dbl, mm1);
+            mom = (int)(dbl - (unsigned)d * mm1) + 1;
             bose_kth_doubly(x, d, src0, n0, off0);
             src1 = src0; off1 = off0; n1 = n0; n0 = n0 - 1; // a_src1 first: n, then a_src0 on the same mode: n - 1
         } else {
             const unsigned mm2 = (unsigned)(M - 2), sm1 = (unsigned)(s - 1);
-            const unsigned pair = (unsigned)ii / mm2;
-            mom = (int)((unsigned)ii % mm2) + 1;
-            int fst = (int)(pair / sm1) + 1, snd = (int)(pair % sm1) + 1; // 1-based as in fldmod1
+            const unsigned pair = udiv_small((unsigned)ii, mm2);
+            mom = (int)((unsigned)ii - pair * mm2) + 1;
+            const unsigned fq = udiv_small(pair, sm1);
+            int fst = (int)fq + 1, snd = (int)(pair - fq * sm1) + 1; // 1-based as in fldmod1
             int f_hole, s_hole;
             if (snd < fst) { f_hole = snd; s_hole = fst; } else { f_hole = fst; s_hole = snd + 1; }
             bose_kth_occupied(x, f_hole - 1, src0, n0, off0);
@@ -330,16 +338,17 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         value *= bose_create(y, dst1);
         value *= bose_create(y, dst0);
         out = y;
-        return h.u / (2 * M) * sqrt((double)value);
+        return h.u_2m * sqrt((double)value);
     } else if constexpr (HK == HK_MOM1D_F2C) {
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
         int p, q, mk;
         double val = mom_transfer_2c(M, fa, fb, h.N1, i, true, p, q, mk);
         if (val != 0.0) out = (B)(fa | (fb << M));
-        return h.u / M * val;
+        return h.u_m * val;
     } else if constexpr (HK == HK_RS_BOSE) {
         const unsigned ii = (unsigned)i, nnb = (unsigned)h.nnb;
-        int particle = (int)(ii / nnb), neigh = (int)(ii % nnb);
+        const unsigned pq = udiv_small(ii, nnb);
+        int particle = (int)pq, neigh = (int)(ii - pq * nnb);
         int mode, ns, off;
         bose_kth_occupied(x, particle, mode, ns, off);
         int dst = h.nbr[(mode - 1) * h.nnb + neigh];
@@ -356,7 +365,8 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         if (HK == HK_RS_F2C && i >= na) { comp = 1; i -= na; }
         u64 f = comp ? fb : fa;
         const unsigned ii = (unsigned)i, nnb = (unsigned)h.nnb;
-        int particle = (int)(ii / nnb), neigh = (int)(ii % nnb);
+        const unsigned pq = udiv_small(ii, nnb);
+        int particle = (int)pq, neigh = (int)(ii - pq * nnb);
         int mode = select_(f, particle) + 1;
         int dst = h.nbr[(mode - 1) * h.nnb + neigh];
         if (dst == 0) return 0.0;

@@ -73,6 +73,14 @@ DEV u32 bucket_of(u64 h, int nranks, u32 nb) {
     return __umulhi(y, nb);
 }
 
+// bulk L2 prefetch of [p, p + bytes): one instruction per contiguous range (cp.async.bulk.prefetch, 16-byte granules;
+// the range is widened to 16-byte alignment, which stays inside the 256-byte granules cudaMalloc hands out)
+DEV void l2_prefetch(const void *p, u64 bytes) {
+    const u64 a = (u64)p & ~15ull;
+    const u32 sz = (u32)((((u64)p + bytes + 15ull) & ~15ull) - a);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(sz) : "memory");
+}
+
 template <int W, class VT>
 DEV void append_record(const PartDev &pt, StatsDev *st, typename BitsT<W>::type key, u64 h, int nranks, VT v) {
     u32 b = bucket_of(h, nranks, pt.nb);
@@ -178,12 +186,16 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
     double spawns = 0.0;
     i64 exact_steps = 0, inexact_steps = 0, attempts = 0;
     const i64 nchunks = (n + SPAWN_NT - 1) / SPAWN_NT;
+    // the parent of the NEXT chunk is loaded while the current chunk is processed (its HBM latency was the largest
+    // single stall of this kernel: 21 % of the samples in profiles/r1_partition_ncu_summary.md)
+    B nkey = 0; VT npv = (VT)0;
+    { const i64 j0 = (i64)blockIdx.x * SPAWN_NT + tid; if (j0 < n) { nkey = load_key<W>(keys + j0 * W); npv = vals[j0]; } }
     for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const i64 j = chunk * SPAWN_NT + tid;
+        const B key = nkey; const VT pv = npv;
+        { const i64 jn = j + (i64)gridDim.x * SPAWN_NT; if (jn < n) { nkey = load_key<W>(keys + jn * W); npv = vals[jn]; } }
         u32 cnt = 0;
         if (j < n) {
-            B key = load_key<W>(keys + j * W);
-            VT pv = vals[j];
             long long L = ham_num_offdiagonals<HK, B>(h, key);
             u64 c64;
             bool exact = attempts_for(p, (double)pv, L, c64);
@@ -394,16 +406,53 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     unsigned short *pidx = reinterpret_cast<unsigned short *>(owner + 2 * CAP);
     __shared__ u32 s_warp[PART_NT / 32];
     __shared__ u64 s_base;
-    __shared__ u32 s_nlist;
+    __shared__ u32 s_nlist, s_clist;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double norm1 = 0.0, clones = 0.0, deaths = 0.0, zombies = 0.0;
     i64 inorm1 = 0, len_before = 0, len = 0, ndep = 0;
     u32 max_fill = 0;
     u64 nrec_sum = 0;
+    // bucket metadata runs two buckets ahead of the merge and the next bucket's parents and records are pulled into
+    // L2 with bulk prefetches while this one is merged, so that staging sees L2 latency instead of two dependent
+    // HBM round trips (metadata, then data)
+    u32 m_np[2] = {0, 0}, m_nrec[2] = {0, 0};
+    u64 m_p0[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const u64 bq = (u64)blockIdx.x + (u64)q * gridDim.x;
+        if (bq < pt.nb) {
+            m_np[q] = src.seg_len ? src.seg_len[bq] : 0u;
+            m_p0[q] = m_np[q] ? src.seg_start[bq] : 0ull;
+            m_nrec[q] = pt.rec_count[bq];
+        }
+    }
     for (u32 b = blockIdx.x; b < pt.nb; b += gridDim.x) {
-        const u32 np = src.seg_len ? src.seg_len[b] : 0u;
-        const u64 p0 = np ? src.seg_start[b] : 0ull;
-        const u32 nrec = pt.rec_count[b];
+        const u32 np = m_np[0];
+        const u64 p0 = m_p0[0];
+        const u32 nrec = m_nrec[0];
+        m_np[0] = m_np[1]; m_p0[0] = m_p0[1]; m_nrec[0] = m_nrec[1];
+        {
+            const u64 b2 = (u64)b + 2ull * gridDim.x;
+            m_np[1] = 0; m_p0[1] = 0; m_nrec[1] = 0;
+            if (b2 < pt.nb) {
+                m_np[1] = src.seg_len ? src.seg_len[b2] : 0u;
+                m_p0[1] = m_np[1] ? src.seg_start[b2] : 0ull;
+                m_nrec[1] = pt.rec_count[b2];
+            }
+            const u64 b1 = (u64)b + gridDim.x;
+            if (tid == 0 && b1 < pt.nb) {
+                const u32 np1 = m_np[0], nrec1 = m_nrec[0] < pt.rcap ? m_nrec[0] : pt.rcap;
+                if (np1) {
+                    l2_prefetch(src.keys + m_p0[0] * W, (u64)np1 * W * 8);
+                    l2_prefetch(src.vals + m_p0[0], (u64)np1 * 8);
+                    if (src.diag) l2_prefetch(src.diag + m_p0[0], (u64)np1 * 8);
+                }
+                if (nrec1) {
+                    l2_prefetch(pt.rec_keys + b1 * pt.rcap * W, (u64)nrec1 * W * 8);
+                    l2_prefetch(pt.rec_vals + b1 * pt.rcap, (u64)nrec1 * 8);
+                }
+            }
+        }
         const u32 n = np + nrec;
         max_fill = max(max_fill, n);
         nrec_sum += nrec;
@@ -412,7 +461,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             continue;
         }
         for (int i = tid; i < 2 * CAP; i += PART_NT) owner[i] = NIL;
-        if (tid == 0) s_nlist = 0;
+        if (tid == 0) { s_nlist = 0; s_clist = 0; }
         const int rmax = (int)((n + PART_NT - 1) / PART_NT); // uniform: rounds of PART_NT items this bucket needs
         // ---- stage parents (with the diagonal step) and spawn records
         u32 valid = 0, slot[R];
@@ -491,36 +540,59 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             }
         }
         __syncthreads();
-        // ---- drop zeros, compress, count survivors
-        VT outv[R];
+        // ---- ThresholdCompression (compression.jl:18-26) as a dense pass: the owners whose |value| is below the
+        // threshold are gathered into a list (the owner table is dead after placement) so that the Philox draw runs
+        // over full warps instead of once per round for the few lanes that need it
+        if constexpr (!is_int && MODE == 0) {
+            if (p.compress_thr > 0.0) { // uniform
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (r >= rmax) break;
+                    const u32 i = tid + r * PART_NT;
+                    bool need = false;
+                    if ((own >> r) & 1u) {
+                        union { u64 b; double v; } cv; cv.b = svals[i];
+                        if (cv.v != 0.0) { len_before++; need = fabs(cv.v) < p.compress_thr; }
+                    }
+                    const u32 bal = __ballot_sync(0xffffffffu, need);
+                    if (bal) {
+                        u32 wb = 0;
+                        if (lane == 0) wb = atomicAdd(&s_clist, (u32)__popc(bal));
+                        wb = __shfl_sync(0xffffffffu, wb, 0);
+                        if (need) owner[wb + __popc(bal & ((1u << lane) - 1u))] = i;
+                    }
+                }
+                __syncthreads();
+                const u32 ncl = s_clist;
+                for (u32 j = tid; j < ncl; j += PART_NT) {
+                    const u32 i = owner[j];
+                    B key;
+                    if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
+                    union { u64 b; double v; } cv; cv.b = svals[i];
+                    const double prob = p.compress_thr == 1.0 ? fabs(cv.v) : fabs(cv.v) / p.compress_thr; // < 1 for every listed entry (x / 1.0 == x)
+                    u32 rnd[4];
+                    rng_draw(hash_bits(key), 0, STREAM_COMPRESS, p.k0, p.k1, rnd);
+                    cv.v = (prob > u53(rnd[1], rnd[2])) ? p.compress_thr * sgn_(cv.v) : 0.0;
+                    svals[i] = cv.b;
+                }
+                __syncthreads();
+            }
+        }
+        // ---- drop zeros, count survivors
+        const bool compressed = !is_int && MODE == 0 && p.compress_thr > 0.0;
         u32 keep = 0, cnt = 0;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            outv[r] = (VT)0;
             if (r >= rmax) break;
             if (!((own >> r) & 1u)) continue;
             const u32 i = tid + r * PART_NT;
             union { u64 b; VT v; } cv; cv.b = svals[i];
-            VT v = cv.v;
-            if (v == (VT)0) continue; // exact zeros are deleted (pdworkingmemory.jl:25-29)
-            len_before++;
-            if constexpr (!is_int && MODE == 0) {
-                if (p.compress_thr > 0.0) { // ThresholdCompression (compression.jl:18-26)
-                    const double prob = fabs(v) / p.compress_thr;
-                    if (prob < 1) {
-                        B key;
-                        if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
-                        u32 rnd[4];
-                        rng_draw(hash_bits(key), 0, STREAM_COMPRESS, p.k0, p.k1, rnd);
-                        v = (prob > u53(rnd[1], rnd[2])) ? p.compress_thr * sgn_(v) : 0.0;
-                    }
-                }
-            }
-            if (v != (VT)0) {
-                outv[r] = v; keep |= 1u << r; cnt++;
-                if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v); else norm1 += fabs((double)v);
-            }
+            const VT v = cv.v;
+            if (v == (VT)0) continue; // exact zeros are deleted (pdworkingmemory.jl:25-29); so are compressed-away entries
+            keep |= 1u << r; cnt++;
+            if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v); else norm1 += fabs((double)v);
         }
+        if (!compressed) len_before += cnt;
         // ---- CTA scan of survivor counts, one cursor atomic per bucket, write the new segment
         u32 incl = cnt;
 #pragma unroll
@@ -549,8 +621,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 const u64 at = base + rel;
                 dst.keys[at * W] = skeys[i * W];
                 if constexpr (W == 2) dst.keys[at * W + 1] = skeys[i * W + 1];
-                union { u64 b; VT v; } cv; cv.v = outv[r];
-                dst.vals[at] = cv.b;
+                dst.vals[at] = svals[i];
                 if constexpr (MODE == 0) {
                     // H_aa of the survivor: cached with its parent, or (new determinant) evaluated below
                     const u32 pi = i < np ? i : (u32)pidx[i];

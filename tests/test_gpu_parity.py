@@ -321,3 +321,47 @@ def test_heavy_parents(built, name, style_name):
             assert np.allclose(gv, ov, rtol=1e-10, atol=0), (name, step)
             assert math.isclose(s.spawns, st.spawns, rel_tol=1e-10)
             ok, ov = gk, gv
+
+
+@pytest.mark.parametrize("W", [1, 2])
+def test_axpby_in_place_beyond_table_size(built, W):
+    """y <- a*x + b*y in place with more records than the working table holds: the table must be regrown BEFORE
+    anything is drained into the (aliased) destination.  Regression: a partial drain used to overwrite y and the
+    retry then summed a corrupted input."""
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+    at = R.AddressType(_lib.ADDR_BOSE, (20,) if W == 1 else (60,), 20 if W == 1 else 60)
+    ctx = R.Context(W, table_slots=1 << 16)  # own small context so that the overflow path is certain
+    rng = np.random.default_rng(10 + W)
+    n = 400_000
+    pool = np.unique(rng.integers(1, 2 ** 62, size=(int(n * 1.5), W), dtype=np.uint64), axis=0)
+    kx, ky = pool[rng.choice(len(pool), n, replace=False)], pool[rng.choice(len(pool), n, replace=False)]
+    vx, vy = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    x = R.GPUDVec(style=R.IsDeterministic(), address_type=at, ctx=ctx)
+    y = R.GPUDVec(style=R.IsDeterministic(), address_type=at, ctx=ctx)
+    x.assign(kx, vx)
+    y.assign(ky, vy)
+    a, b = 0.75, -1.25
+    y.axpby_(a, x, b)  # y = a*x + b*y
+    gk, gv = y.download_sorted()
+    k = np.concatenate([kx, ky])
+    v = np.concatenate([a * vx, b * vy])
+    order = np.lexsort(tuple(k[:, j] for j in range(W)))
+    k, v = k[order], v[order]
+    first = np.ones(len(v), dtype=bool)
+    first[1:] = np.any(k[1:] != k[:-1], axis=1)
+    ref = np.zeros(int(first.sum()))
+    np.add.at(ref, np.cumsum(first) - 1, v)
+    rk = k[first]
+    rk, ref = sort_kv(rk[ref != 0], ref[ref != 0])
+    assert np.array_equal(gk.reshape(-1, W), rk)
+    assert np.allclose(gv, ref, rtol=1e-12, atol=0)
+    assert math.isclose(x.dot(y), float(np.dot(*_aligned(kx, vx, rk, ref, W))), rel_tol=1e-9)
+    del x, y
+    ctx.close()
+
+
+def _aligned(kx, vx, kr, vr, W):
+    """values of x on the keys of r (0 where absent), for a host-side dot product"""
+    d = {tuple(int(t) for t in key): val for key, val in zip(kr, vr)}
+    return vx, np.array([d.get(tuple(int(t) for t in key), 0.0) for key in kx])
