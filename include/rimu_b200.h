@@ -124,7 +124,7 @@ typedef struct {
     int64_t deposits;         /* non-zero deposits into the working table (diagonal + spawns), global */
     /* CUDA-event phase timings of this call: diagonal/count+scan, spawn kernel, exchange, compaction */
     float ms_diag, ms_spawn, ms_exchange, ms_compact;
-    float ms_total, pad_;
+    float ms_total, ms_reduce; /* ms_reduce: statistics all-reduce + read-back after the merge (multi-GPU) */
     int64_t buckets;          /* bucket count of the partitioned step on this rank (0: table method) */
     int64_t max_bucket_fill;  /* fullest bucket (parents + records) */
 } rimu_step_stats;

@@ -97,7 +97,7 @@ class StepStats(C.Structure):
         ("local_len", C.c_int64), ("sent_records", C.c_int64),
         ("deposits", C.c_int64),
         ("ms_diag", C.c_float), ("ms_spawn", C.c_float), ("ms_exchange", C.c_float), ("ms_compact", C.c_float),
-        ("ms_total", C.c_float), ("pad_", C.c_float),
+        ("ms_total", C.c_float), ("ms_reduce", C.c_float),
         ("buckets", C.c_int64), ("max_bucket_fill", C.c_int64),
     ]
 

@@ -118,7 +118,8 @@ struct rimu_ctx {
     StatsDev *d_stats, *h_stats, *h_stats_local;
     u64 *local_off, *block_tot, *block_base;
     u64 scratch_parents;
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[8];
+    double *d_red = nullptr; // packed statistics for the single all-reduce (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP doubles)
     unsigned long long launches; // kernels launched by this context (bench bookkeeping)
     // staging for host <-> device transfers
     u64 *stage_keys; void *stage_vals; u64 stage_cap;
@@ -209,7 +210,7 @@ extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu
     CUDA_TRY(cudaMallocHost(&c->h_stats, sizeof(StatsDev)));
     CUDA_TRY(cudaMallocHost(&c->h_stats_local, sizeof(StatsDev)));
     CUDA_TRY(rimu_malloc(&c->d_reduce, 64 * sizeof(double)));
-    for (int i = 0; i < 6; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 8; i++) CUDA_TRY(cudaEventCreate(&c->ev[i]));
     TRY(table_fill(c, c->table_slots));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out = c;
@@ -238,8 +239,10 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->d_reduce);
     cudaFree(c->part.rec_keys); cudaFree(c->part.rec_vals); cudaFree(c->part.rec_count);
     cudaFree(c->heavy.items); cudaFree(c->heavy.packed); cudaFree(c->bucket_tmp);
-    for (int i = 0; i < 6; i++) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+    cudaFree(c->d_red);
     cudaStreamDestroy(c->stream);
+    cudaGetLastError(); // teardown is best effort (e.g. closing an IPC mapping whose exporter is already gone): never leave a stale error behind
     delete c;
     return 0;
 }
@@ -369,6 +372,7 @@ static void p2p_teardown(rimu_ctx *c) {
     for (int k = 0; k < 2; k++)
         for (int r = 0; r < RIMU_MAX_RANKS; r++)
             if (c->peer_open[k][r]) { cudaIpcCloseMemHandle(c->peer_open[k][r]); c->peer_open[k][r] = nullptr; }
+    cudaGetLastError();
     c->xch.p2p = 0;
     memset(c->xch.peer_keys, 0, sizeof(c->xch.peer_keys));
     memset(c->xch.peer_vals, 0, sizeof(c->xch.peer_vals));
@@ -1096,6 +1100,7 @@ extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *
 static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_streams) {
     const int R = c->nranks, me = c->rank;
     NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
     c->p2p_used = 0;
     if (to_streams && c->xch.p2p) {
         // The payload already sits in this rank's receive regions (peer stores issued by the spawn kernels, complete
@@ -1104,7 +1109,7 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool t
         CUDA_TRY(cudaMemsetAsync(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64), c->stream));
         TRY(dispatch_wv(c->W, vt, [&](auto tag, auto vtag) {
             typedef decltype(vtag) VT;
-            append_recv_kernel<decltype(tag)::w, VT><<<dim3(c->sm_count * 2, R), RIMU_TPB, 0, c->stream>>>(
+            append_recv_kernel<decltype(tag)::w, VT><<<dim3(c->sm_count * 4, R), RIMU_TPB, 0, c->stream>>>(
                 c->recv_keys, (const VT *)c->recv_vals, c->d_allcounts, me, R, c->xch.cap, c->part, c->d_stats);
             c->launches += 1;
             return 0;
@@ -1363,11 +1368,16 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         if (r) return r;
         CUDA_TRY(cudaMemcpyAsync(c->h_stats_local, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         if (c->nranks > 1) {
-            NCCL_TRY(g_nccl.AllReduce(c->d_stats, c->d_stats, RIMU_STATS_NI64, ncclInt64, ncclSum, c->comm, c->stream));
-            double *dd = (double *)((char *)c->d_stats + RIMU_STATS_NI64 * sizeof(i64));
-            NCCL_TRY(g_nccl.AllReduce(dd, dd, RIMU_STATS_NF64_STEP, ncclFloat64, ncclSum, c->comm, c->stream));
+            // ONE all-reduce per step: the integer block travels as doubles (counts stay far below 2^53, so the sums
+            // are exact) next to the floating-point block (reference: Allreduce of a MultiScalar, pdvec.jl:896-902)
+            if (!c->d_red) CUDA_TRY(rimu_malloc(&c->d_red, (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP) * sizeof(double)));
+            pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 0);
+            NCCL_TRY(g_nccl.AllReduce(c->d_red, c->d_red, RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP, ncclFloat64, ncclSum, c->comm, c->stream));
+            pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 1);
+            CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const StatsDev &g = *c->h_stats, &l = *c->h_stats_local;
         if (c->nranks > 1 && c->p2p_used) {
@@ -1429,6 +1439,13 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             cudaEventElapsedTime(&out->ms_exchange, c->ev[1], c->ev[2]);
             cudaEventElapsedTime(&out->ms_compact, c->ev[2], c->ev[3]);
             cudaEventElapsedTime(&out->ms_total, c->ev[0], c->ev[3]);
+            cudaEventElapsedTime(&out->ms_reduce, c->ev[3], c->ev[5]);
+            static const bool timing = getenv("RIMU_B200_TIMING") != nullptr;
+            if (timing && c->nranks > 1 && (prm->step % 64) == 0) {
+                float g = 0; cudaEventElapsedTime(&g, c->ev[1], c->ev[6]);
+                fprintf(stderr, "[rimu_b200 r%d step %llu] spawn %.3f gather(+skew) %.3f append %.3f merge %.3f reduce(+skew) %.3f ms\n", c->rank,
+                        (unsigned long long)prm->step, out->ms_spawn, g, out->ms_exchange - g, out->ms_compact, out->ms_reduce);
+            }
             out->buckets = use_part ? (int64_t)nb : 0; out->max_bucket_fill = (int64_t)l.max_fill;
         }
         return 0;

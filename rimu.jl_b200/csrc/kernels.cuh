@@ -203,6 +203,15 @@ DEV i64 warp_sum(i64 v) {
 DEV void stat_add(double *dst, double v) { v = warp_sum(v); if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v); }
 DEV void stat_add(i64 *dst, i64 v) { v = warp_sum(v); if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd((u64 *)dst, (u64)v); }
 
+// statistics <-> packed doubles for the single per-step all-reduce (dir 0: pack, 1: unpack)
+__global__ void pack_stats_kernel(StatsDev *st, double *buf, int dir) {
+    const int i = threadIdx.x;
+    i64 *ints = reinterpret_cast<i64 *>(st);
+    double *dbl = reinterpret_cast<double *>(reinterpret_cast<char *>(st) + RIMU_STATS_NI64 * sizeof(i64));
+    if (i < RIMU_STATS_NI64) { if (dir == 0) buf[i] = (double)ints[i]; else ints[i] = (i64)llrint(buf[i]); }
+    if (i < RIMU_STATS_NF64_STEP) { if (dir == 0) buf[RIMU_STATS_NI64 + i] = dbl[i]; else dbl[i] = buf[RIMU_STATS_NI64 + i]; }
+}
+
 // ---------------------------------------------------------------- K1: diagonal step + attempt counts
 template <int HK, int W, class VT>
 __global__ void __launch_bounds__(RIMU_TPB)

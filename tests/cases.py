@@ -32,6 +32,7 @@ SPECS = {
     "rs_fermi": ("HubbardRealSpace", "fermi", _fermi(12, (1, 2, 3)), dict(t=1.0, dims=(3, 4))),
     "rs_fermi_hw": ("HubbardRealSpace", "fermi", _fermi(12, (1, 6, 12)), dict(t=2.0, dims=(4, 3), fold=(False, False))),
     "rs_f2c_4x4": ("HubbardRealSpace", "fermi2c", (_fermi(16, (1, 6)), _fermi(16, (3, 11))), dict(t=(1.0, 1.0), u=((0.0, 4.0), (4.0, 0.0)), dims=(4, 4))),
+    "rs_f2c_3up3dn": ("HubbardRealSpace", "fermi2c", (_fermi(16, (1, 6, 11)), _fermi(16, (2, 8, 13))), dict(t=(1.0, 1.0), u=((0.0, 4.0), (4.0, 0.0)), dims=(4, 4))),  # dim 313 600
     "rs_f2c_half": ("HubbardRealSpace", "fermi2c", (_fermi(16, range(1, 9)), _fermi(16, range(5, 13))), dict(t=(1.0, 1.0), u=((0.0, 1.0), (1.0, 0.0)), dims=(4, 4))),  # config 3
     "rs_f2c_trap": ("HubbardRealSpace", "fermi2c", (_fermi(6, (1, 2, 4, 5)), _fermi(6, (2, 3))), dict(t=(1.0, 2.0), u=((0.0, 0.5), (0.5, 0.0)), dims=(6,), trap=((0.1,), (0.2,)))),
     "tc_7": ("Transcorrelated1D", "fermi2c", (_fermi(7, (3, 5)), _fermi(7, (4,))), dict(t=24.5, v=7.0, cutoff=1, three_body_term=True)),
