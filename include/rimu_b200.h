@@ -141,6 +141,9 @@ int rimu_sizeof_step_stats(void);
 int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu_ctx **out);
 int rimu_ctx_destroy(rimu_ctx *ctx);
 int rimu_ctx_synchronize(rimu_ctx *ctx);
+/* Make the context's GPU the calling thread's current CUDA device (rimu_ham_create places its tables on the current
+ * device; hosts that juggle several devices or libraries call this first). */
+int rimu_ctx_make_current(rimu_ctx *ctx);
 int rimu_ctx_table_slots(rimu_ctx *ctx, uint64_t *out);
 /* reallocate the working table (contents are scratch between calls) */
 int rimu_ctx_resize_table(rimu_ctx *ctx, uint64_t table_slots);

@@ -116,6 +116,7 @@ SYMBOLS = {
     "rimu_ctx_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.POINTER(_vp)]),
     "rimu_ctx_destroy": (C.c_int, [_vp]),
     "rimu_ctx_synchronize": (C.c_int, [_vp]),
+    "rimu_ctx_make_current": (C.c_int, [_vp]),
     "rimu_ctx_table_slots": (C.c_int, [_vp, _u64p]),
     "rimu_ctx_resize_table": (C.c_int, [_vp, C.c_uint64]),
     "rimu_ctx_stream": (C.c_int, [_vp, C.POINTER(_vp)]),

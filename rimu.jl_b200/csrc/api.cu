@@ -132,13 +132,20 @@ struct rimu_ctx {
     double *d_reduce;
     // partitioned step (partition.cuh): bucket record streams, heavy-parent queue, re-segmentation scratch
     int method;              // RIMU_ANNIHILATE_PARTITION (default) or RIMU_ANNIHILATE_HASH
-    PartDev part;
+    PartDev part;            // record streams of the FCIQMC step (direct mode: peers store into them over NVLink)
     u64 part_nb_cap;         // buckets the record streams are allocated for
+    PartDev lpart;           // direct mode only: private streams for local operations (upload, axpby, annihilate), which
+    u64 lpart_nb_cap;        //   run between steps while a faster peer may already be filling the step streams
+    int direct;              // multi-GPU: peers can map each other's streams (CUDA IPC) -> spawned records are stored
+                             //   straight into the owner's bucket sub-streams, no receive pass
+    const rimu_vec *last_dst; u64 last_dst_version; double last_g_len;
+    u32 merge_grid_cap;      // RIMU_B200_MERGE_GRID: cap on merge CTAs (tests force many buckets per CTA with it) // global length of the previous step's result
     HeavyDev heavy;
     u32 *bucket_tmp; u64 bucket_tmp_cap; // [2][nb] counts / fill
     u64 xch_worst;           // largest per-peer record count seen by a failed exchange
+    u64 xch_want;            // per-peer capacity the staging buffers get when they are first needed
     int p2p_used;            // the last exchange went peer-direct: counts are read from h_allcounts after the final sync
-    void *peer_open[2][RIMU_MAX_RANKS]; // IPC-opened peer receive buffers (keys, vals)
+    void *peer_open[2][RIMU_MAX_RANKS]; // IPC-opened peer stream buffers (records, sub-stream fills)
     char *d_ipc, *h_ipc;     // all-gather scratch for the IPC handles
     alignas(16) char sort_scratch[96];   // SortScratch of sort.cu (opaque here)
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
@@ -168,6 +175,7 @@ struct rimu_vec {
     // Hamiltonian with uid diag_uid (0 = invalid).  Saves re-evaluating H_aa for every parent every step.
     double *diag;
     u64 diag_cap, diag_uid;
+    u64 version;             // bumped by every mutating API call (the same call sequence runs on every rank)
 };
 
 static u64 next_pow2(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
@@ -203,6 +211,8 @@ extern "C" int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    c->merge_grid_cap = (u32)c->sm_count * 32;
+    if (const char *g = getenv("RIMU_B200_MERGE_GRID")) { int v = atoi(g); if (v > 0) c->merge_grid_cap = (u32)v; }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->table_slots = next_pow2(table_slots < 1024 ? 1024 : table_slots);
     CUDA_TRY(rimu_malloc(&c->table, c->table_slots * (words == 1 ? 16 : 32)));
@@ -237,7 +247,8 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->xch.counts);
     cudaFree(c->recv_keys); cudaFree(c->recv_vals); cudaFree(c->d_allcounts); cudaFreeHost(c->h_allcounts);
     cudaFree(c->d_reduce);
-    cudaFree(c->part.rec_keys); cudaFree(c->part.rec_vals); cudaFree(c->part.rec_count);
+    cudaFree(c->part.rec); cudaFree(c->part.rcnt); cudaFree(c->part.scnt); cudaFree(c->part.srec);
+    cudaFree(c->lpart.rec); cudaFree(c->lpart.rcnt); cudaFree(c->lpart.scnt);
     cudaFree(c->heavy.items); cudaFree(c->heavy.packed); cudaFree(c->bucket_tmp);
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaFree(c->d_red);
@@ -246,6 +257,7 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     delete c;
     return 0;
 }
+extern "C" int rimu_ctx_make_current(rimu_ctx *c) { if (!c) return fail(RIMU_ERR_INVALID, "null context"); CUDA_TRY(cudaSetDevice(c->device)); return 0; }
 extern "C" int rimu_ctx_synchronize(rimu_ctx *c) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
 extern "C" int rimu_ctx_table_slots(rimu_ctx *c, uint64_t *out) { *out = c->table_slots; return 0; }
 extern "C" int rimu_ctx_stream(rimu_ctx *c, void **s) { *s = (void *)c->stream; return 0; }
@@ -329,18 +341,45 @@ static int ensure_seg(rimu_vec *v, u32 nb) {
 }
 static u32 part_cap_items(int W) { return W == 1 ? (u32)PartCap<1>::value : (u32)PartCap<2>::value; }
 static size_t part_smem_bytes(int W) { u32 cap = part_cap_items(W); return (size_t)cap * W * 8 + (size_t)cap * 8 + (size_t)cap * 2 * 4 + (size_t)cap * 2; }
-static int ensure_part(rimu_ctx *c, u32 nb) {
-    c->part.rcap = part_cap_items(c->W);
-    if (nb <= c->part_nb_cap) { c->part.nb = nb; return 0; }
-    u64 cap = (u64)nb + nb / 4 + 16;
-    cudaFree(c->part.rec_keys); cudaFree(c->part.rec_vals); cudaFree(c->part.rec_count);
-    c->part.rec_keys = c->part.rec_vals = nullptr; c->part.rec_count = nullptr; c->part_nb_cap = 0;
-    CUDA_TRY(rimu_malloc(&c->part.rec_keys, cap * c->part.rcap * c->W * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&c->part.rec_vals, cap * c->part.rcap * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&c->part.rec_count, cap * sizeof(u32)));
-    c->part_nb_cap = cap; c->part.nb = nb;
+static int p2p_setup(rimu_ctx *c);
+static void p2p_teardown(rimu_ctx *c);
+extern "C" int rimu_comm_allreduce_f64(rimu_ctx *c, double *buf, int n);
+// Size the record streams for nb buckets.  shared = the step streams of a multi-GPU context in direct mode: every rank
+// calls this with the same nb (it is derived from all-reduced quantities), so (re)allocation and the exchange of the
+// CUDA IPC handles are collective.  Otherwise: private streams with one sub-stream per bucket.
+static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool shared) {
+    const u32 capi = part_cap_items(c->W);
+    const u32 nsrc = shared ? (u32)c->nranks : 1u;
+    u32 rcap = capi;
+    if (nsrc > 1) { rcap = 2 * capi / nsrc; if (rcap < 128) rcap = 128; }
+    pt.nsrc = nsrc; pt.me = shared ? (u32)c->rank : 0u; pt.rcap = rcap; pt.direct = shared ? 1 : 0;
+    if (nb <= nb_cap) { pt.nb = nb; return 0; }
+    const u64 cap = (u64)nb + nb / 4 + 16;
+    const size_t rw = c->W == 1 ? 2 : 4;
+    if (shared) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        double zero = 0.0;
+        TRY(rimu_comm_allreduce_f64(c, &zero, 1)); // nobody is still storing into a peer's old streams
+        p2p_teardown(c);
+    }
+    cudaFree(pt.rec); cudaFree(pt.rcnt); cudaFree(pt.scnt); cudaFree(pt.srec);
+    pt.rec = nullptr; pt.rcnt = nullptr; pt.scnt = nullptr; pt.srec = nullptr; nb_cap = 0;
+    CUDA_TRY(rimu_malloc(&pt.rec, cap * nsrc * rcap * rw * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&pt.rcnt, (size_t)nsrc * cap * sizeof(u32)));
+    CUDA_TRY(cudaMemsetAsync(pt.rcnt, 0, (size_t)nsrc * cap * sizeof(u32), c->stream));
+    if (shared) {
+        CUDA_TRY(rimu_malloc(&pt.scnt, (size_t)c->nranks * cap * sizeof(u32)));
+        CUDA_TRY(rimu_malloc(&pt.srec, (size_t)c->nranks * cap * rcap * rw * sizeof(u64)));
+    }
+    nb_cap = cap; pt.nb = nb;
+    if (shared) TRY(p2p_setup(c));
     return 0;
 }
+static int ensure_part(rimu_ctx *c, u32 nb) { return ensure_part_impl(c, c->part, c->part_nb_cap, nb, c->nranks > 1 && c->direct); }
+// streams for local record->vector operations
+static PartDev &local_part(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? c->lpart : c->part; }
+static u64 &local_part_cap(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? c->lpart_nb_cap : c->part_nb_cap; }
+static int ensure_local_part(rimu_ctx *c, u32 nb) { return ensure_part_impl(c, local_part(c), local_part_cap(c), nb, false); }
 static int ensure_heavy(rimu_ctx *c, u64 parents) {
     if (!c->heavy.packed) CUDA_TRY(rimu_malloc(&c->heavy.packed, sizeof(u64)));
     if (parents <= c->heavy.cap) return 0;
@@ -373,53 +412,89 @@ static void p2p_teardown(rimu_ctx *c) {
         for (int r = 0; r < RIMU_MAX_RANKS; r++)
             if (c->peer_open[k][r]) { cudaIpcCloseMemHandle(c->peer_open[k][r]); c->peer_open[k][r] = nullptr; }
     cudaGetLastError();
-    c->xch.p2p = 0;
-    memset(c->xch.peer_keys, 0, sizeof(c->xch.peer_keys));
-    memset(c->xch.peer_vals, 0, sizeof(c->xch.peer_vals));
+    memset(c->part.peer_rec, 0, sizeof(c->part.peer_rec));
+    memset(c->part.peer_rcnt, 0, sizeof(c->part.peer_rcnt));
 }
-extern "C" int rimu_comm_allreduce_f64(rimu_ctx *c, double *buf, int n);
-static int p2p_setup(rimu_ctx *c) { // collective
-    p2p_teardown(c);
-    const char *env = getenv("RIMU_B200_P2P");
+// all-gather the CUDA IPC handles of two buffers and map every peer's copy; returns 0 and sets *ok
+static int ipc_map_all(rimu_ctx *c, void *buf0, void *buf1, void *peers0[], void *peers1[], int *ok) {
     const int R = c->nranks, me = c->rank;
     const size_t HS = sizeof(cudaIpcMemHandle_t);
-    double bad = (env && !strcmp(env, "0")) ? 1.0 : 0.0;
+    double bad = 0.0;
     if (!c->d_ipc) {
         CUDA_TRY(rimu_malloc(&c->d_ipc, (size_t)RIMU_MAX_RANKS * 2 * HS));
         CUDA_TRY(cudaMallocHost(&c->h_ipc, (size_t)RIMU_MAX_RANKS * 2 * HS));
     }
     cudaIpcMemHandle_t mine[2];
     memset(mine, 0, sizeof(mine));
-    if (bad == 0.0) {
-        if (cudaIpcGetMemHandle(&mine[0], c->recv_keys) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], c->recv_vals) != cudaSuccess) {
-            cudaGetLastError();
-            bad = 1.0;
-        }
+    if (cudaIpcGetMemHandle(&mine[0], buf0) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], buf1) != cudaSuccess) {
+        cudaGetLastError();
+        bad = 1.0;
     }
     TRY(rimu_comm_allreduce_f64(c, &bad, 1));
-    if (bad > 0.0) return 0; // some rank cannot do IPC: everybody keeps the NCCL send/recv exchange
+    if (bad > 0.0) { *ok = 0; return 0; }
     CUDA_TRY(cudaMemcpyAsync(c->d_ipc + (size_t)me * 2 * HS, mine, 2 * HS, cudaMemcpyHostToDevice, c->stream));
     NCCL_TRY(g_nccl.AllGather(c->d_ipc + (size_t)me * 2 * HS, c->d_ipc, 2 * HS, 0 /* ncclInt8 */, c->comm, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_ipc, c->d_ipc, (size_t)R * 2 * HS, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (int r = 0; r < R && bad == 0.0; r++) {
-        if (r == me) { c->peer_open[0][r] = c->peer_open[1][r] = nullptr; c->xch.peer_keys[r] = c->recv_keys; c->xch.peer_vals[r] = c->recv_vals; continue; }
+        if (r == me) { peers0[r] = buf0; peers1[r] = buf1; continue; }
         for (int k = 0; k < 2; k++) {
             cudaIpcMemHandle_t hnd;
             memcpy(&hnd, c->h_ipc + ((size_t)r * 2 + k) * HS, HS);
             void *ptr = nullptr;
             if (cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); bad = 1.0; break; }
             c->peer_open[k][r] = ptr;
-            if (k == 0) c->xch.peer_keys[r] = (u64 *)ptr; else c->xch.peer_vals[r] = (u64 *)ptr;
+            if (k == 0) peers0[r] = ptr; else peers1[r] = ptr;
         }
     }
     TRY(rimu_comm_allreduce_f64(c, &bad, 1));
-    if (bad > 0.0) { p2p_teardown(c); return 0; }
-    c->xch.p2p = 1;
+    *ok = bad == 0.0;
     return 0;
 }
-extern "C" int rimu_comm_p2p(rimu_ctx *c, int *enabled) { *enabled = c->xch.p2p; return 0; }
+// direct mode: map every rank's step streams (records + sub-stream fills).  Collective.
+static int p2p_setup(rimu_ctx *c) {
+    p2p_teardown(c);
+    int ok = 0;
+    void *pr[RIMU_MAX_RANKS] = {}, *pc[RIMU_MAX_RANKS] = {};
+    TRY(ipc_map_all(c, c->part.rec, c->part.rcnt, pr, pc, &ok));
+    if (!ok) { p2p_teardown(c); return fail(RIMU_ERR_CUDA, "CUDA IPC mapping of the peers' record streams failed (set RIMU_B200_P2P=0 to use NCCL send/recv)"); }
+    for (int r = 0; r < c->nranks; r++) { c->part.peer_rec[r] = (u64 *)pr[r]; c->part.peer_rcnt[r] = (u32 *)pc[r]; }
+    return 0;
+}
+// can the ranks map each other's memory at all?  (decides direct vs staged exchange once, at communicator set-up)
+static int p2p_probe(rimu_ctx *c) {
+    const char *env = getenv("RIMU_B200_P2P");
+    double off = (env && !strcmp(env, "0")) ? 1.0 : 0.0;
+    TRY(rimu_comm_allreduce_f64(c, &off, 1));
+    c->direct = 0;
+    if (off > 0.0) return 0;
+    u64 *probe0 = nullptr, *probe1 = nullptr;
+    CUDA_TRY(rimu_malloc(&probe0, 4096));
+    CUDA_TRY(rimu_malloc(&probe1, 4096));
+    int ok = 0;
+    void *pr[RIMU_MAX_RANKS] = {}, *pc[RIMU_MAX_RANKS] = {};
+    int rc = ipc_map_all(c, probe0, probe1, pr, pc, &ok);
+    p2p_teardown(c);
+    { double zero = 0.0; int rc2 = rimu_comm_allreduce_f64(c, &zero, 1); if (!rc) rc = rc2; } // every mapping is closed before the probes are freed
+    cudaFree(probe0); cudaFree(probe1);
+    if (rc) return rc;
+    c->direct = ok;
+    return 0;
+}
+extern "C" int rimu_comm_p2p(rimu_ctx *c, int *enabled) { *enabled = c->direct; return 0; }
 
+// staging buffers of the NCCL send/recv exchange (staged mode, and the table method in any mode); allocated on first use
+static int ensure_xch(rimu_ctx *c) {
+    if (c->xch.keys) return 0;
+    const u64 per_peer = c->xch_want < 1024 ? 1024 : c->xch_want;
+    CUDA_TRY(rimu_malloc(&c->xch.keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->xch.vals, (u64)c->nranks * per_peer * sizeof(u64)));
+    c->recv_cap = (u64)c->nranks * per_peer;
+    CUDA_TRY(rimu_malloc(&c->recv_keys, c->recv_cap * c->W * sizeof(u64)));
+    CUDA_TRY(rimu_malloc(&c->recv_vals, c->recv_cap * sizeof(u64)));
+    c->xch.cap = per_peer;
+    return 0;
+}
 extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nranks, uint64_t per_peer) {
     if (nranks < 1 || nranks > RIMU_MAX_RANKS || rank < 0 || rank >= nranks) return fail(RIMU_ERR_INVALID, "bad rank/nranks");
     if (c->comm) return fail(RIMU_ERR_INVALID, "communicator already attached");
@@ -431,34 +506,26 @@ extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nran
     memcpy(&id, id128, 128);
     NCCL_TRY(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
     if (per_peer < 1024) per_peer = 1024;
-    c->xch.cap = per_peer;
-    CUDA_TRY(rimu_malloc(&c->xch.keys, (u64)nranks * per_peer * c->W * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&c->xch.vals, (u64)nranks * per_peer * sizeof(u64)));
     CUDA_TRY(rimu_malloc(&c->xch.counts, RIMU_MAX_RANKS * sizeof(u64)));
     CUDA_TRY(cudaMemset(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64)));
-    c->recv_cap = (u64)nranks * per_peer;
-    CUDA_TRY(rimu_malloc(&c->recv_keys, c->recv_cap * c->W * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&c->recv_vals, c->recv_cap * sizeof(u64)));
     CUDA_TRY(rimu_malloc(&c->d_allcounts, (u64)nranks * nranks * sizeof(u64)));
     CUDA_TRY(cudaMallocHost(&c->h_allcounts, (u64)nranks * nranks * sizeof(u64)));
     memset(c->h_allcounts, 0, (size_t)nranks * nranks * sizeof(u64));
-    return p2p_setup(c);
+    c->xch_want = per_peer;
+    TRY(p2p_probe(c));
+    if (!c->direct) TRY(ensure_xch(c)); // staged exchange: per-peer send segments + receive buffer for NCCL send/recv
+    return 0;
 }
 // grow the per-peer exchange buffers (every rank must call it with the same size; contents are scratch)
 extern "C" int rimu_comm_reserve(rimu_ctx *c, uint64_t per_peer) {
     if (c->nranks == 1 || per_peer <= c->xch.cap) return 0;
     CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->xch.keys) { if (per_peer > c->xch_want) c->xch_want = per_peer; return 0; } // not allocated yet (direct mode)
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    { double zero = 0.0; TRY(rimu_comm_allreduce_f64(c, &zero, 1)); } // nobody is still writing into a peer's old buffer
-    p2p_teardown(c);
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->recv_keys); cudaFree(c->recv_vals);
     c->xch.keys = c->xch.vals = c->recv_keys = c->recv_vals = nullptr; c->xch.cap = 0; c->recv_cap = 0;
-    CUDA_TRY(rimu_malloc(&c->xch.keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&c->xch.vals, (u64)c->nranks * per_peer * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&c->recv_keys, (u64)c->nranks * per_peer * c->W * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&c->recv_vals, (u64)c->nranks * per_peer * sizeof(u64)));
-    c->xch.cap = per_peer; c->recv_cap = (u64)c->nranks * per_peer;
-    return p2p_setup(c);
+    c->xch_want = per_peer;
+    return ensure_xch(c);
 }
 extern "C" int rimu_comm_capacity(rimu_ctx *c, uint64_t *per_peer, uint64_t *needed) {
     *per_peer = c->xch.cap; *needed = c->xch_worst;
@@ -723,7 +790,7 @@ static int ensure_diag(rimu_vec *v) {
     v->diag_cap = v->cap;
     return 0;
 }
-extern "C" int rimu_vec_clear(rimu_vec *v) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; }
+extern "C" int rimu_vec_clear(rimu_vec *v) { v->version++; v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; }
 extern "C" int rimu_vec_length(rimu_vec *v, int64_t *out) { *out = v->n; return 0; }
 extern "C" int rimu_vec_capacity(rimu_vec *v, uint64_t *out) { *out = v->cap; return 0; }
 
@@ -825,12 +892,14 @@ static int records_to_vec_part(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, co
     for (int attempt = 0;; attempt++) {
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        if (nb > c->part_nb_cap && (double)nb * 1.3 * cap * (8.0 * c->W + 8.0) > 0.8 * ((double)free_b + (double)c->part_nb_cap * cap * (8.0 * c->W + 8.0)))
+        const double recb = c->W == 1 ? 16.0 : 32.0;
+        if (nb > local_part_cap(c) && (double)nb * 1.3 * cap * recb > 0.8 * ((double)free_b + (double)local_part_cap(c) * cap * recb))
             return records_to_vec(c, dst, d_keys, d_vals, n, d_keys2, d_vals2, n2, a1, a2, use_scale);
-        TRY(ensure_part(c, nb));
+        TRY(ensure_local_part(c, nb));
+        PartDev &lp = local_part(c);
         TRY(ensure_seg(dst, nb));
         CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-        CUDA_TRY(cudaMemsetAsync(c->part.rec_count, 0, nb * sizeof(u32), c->stream));
+        CUDA_TRY(cudaMemsetAsync(lp.rcnt, 0, nb * sizeof(u32), c->stream));
         TRY(dispatch_wv(c->W, dst->vt, [&](auto tag, auto vtag) {
             typedef decltype(vtag) VT;
             constexpr int W = decltype(tag)::w;
@@ -841,15 +910,15 @@ static int records_to_vec_part(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, co
             }
             if (n > 0)
                 append_records_kernel<W, VT><<<grid_for(n, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
-                    d_keys, (const VT *)d_vals, n, a1, use_scale, c->rank, c->nranks, c->part, c->d_stats);
+                    d_keys, (const VT *)d_vals, n, a1, use_scale, c->rank, c->nranks, lp, 0u, c->d_stats);
             if (n2 > 0)
                 append_records_kernel<W, VT><<<grid_for(n2, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
-                    d_keys2, (const VT *)d_vals2, n2, a2, use_scale, c->rank, c->nranks, c->part, c->d_stats);
+                    d_keys2, (const VT *)d_vals2, n2, a2, use_scale, c->rank, c->nranks, lp, 0u, c->d_stats);
             HamDev hd; memset(&hd, 0, sizeof(hd));
             SegSrc ss{nullptr, nullptr, nullptr, nullptr, nullptr};
             SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, nullptr};
-            const int mgrid = (int)(nb < (u32)c->sm_count * 32 ? nb : (u32)c->sm_count * 32);
-            merge_kernel<0, W, VT, 1><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(hd, null_step(c), ss, 1.0, c->part, sd, c->d_stats);
+            const int mgrid = (int)(nb < c->merge_grid_cap ? nb : c->merge_grid_cap);
+            merge_kernel<0, W, VT, 1><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(hd, null_step(c), ss, 1.0, lp, sd, c->d_stats);
             return 0;
         }));
         CUDA_TRY(cudaGetLastError());
@@ -884,6 +953,7 @@ static int records_to_vec_auto(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, co
 }
 
 extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
+    if (v) v->version++;
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     if (n <= 0) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; }
@@ -893,6 +963,7 @@ extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *va
     return records_to_vec_auto(c, v, c->stage_keys, c->stage_vals, n, nullptr, nullptr, 0, 1.0, 1.0, 0);
 }
 extern "C" int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
+    if (v) v->version++;
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     if (n < 0) return fail(RIMU_ERR_INVALID, "negative length");
@@ -918,6 +989,7 @@ extern "C" int rimu_vec_download(rimu_vec *v, uint64_t *keys_out, void *vals_out
     return 0;
 }
 extern "C" int rimu_vec_copy(rimu_vec *dst, rimu_vec *src) {
+    if (dst) dst->version++;
     if (dst == src) return 0;
     rimu_ctx *c = src->ctx;
     if (dst->ctx != c) return fail(RIMU_ERR_INVALID, "copy between vectors of different contexts");
@@ -994,6 +1066,7 @@ extern "C" int rimu_vec_norm(rimu_vec *v, int p, double *out) {
     return 0;
 }
 extern "C" int rimu_vec_scale(rimu_vec *v, double alpha) {
+    if (v) v->version++;
     rimu_ctx *c = v->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     if (alpha == 0.0) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; } // zero values are never stored
@@ -1043,6 +1116,7 @@ extern "C" int rimu_vec_dot(rimu_vec *x, rimu_vec *y, double *out) {
     return 0;
 }
 extern "C" int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *y, rimu_vec *out) {
+    if (out) out->version++;
     rimu_ctx *c = out->ctx;
     if (x->ctx != c || y->ctx != c || x->vt != out->vt || y->vt != out->vt) return fail(RIMU_ERR_INVALID, "axpby of incompatible vectors");
     if (x->n + y->n > 0 && (u64)(x->n + y->n) > out->cap && (out == x || out == y)) TRY(rimu_vec_reserve(out, (u64)(x->n + y->n)));
@@ -1050,6 +1124,7 @@ extern "C" int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *
 }
 
 extern "C" int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, const void *d_vals, int64_t n, int method, float *ms_out) {
+    if (dst) dst->version++;
     rimu_ctx *c = dst->ctx;
     CUDA_TRY(cudaSetDevice(c->device));
     if (method != RIMU_ANNIHILATE_HASH && method != RIMU_ANNIHILATE_SORT && method != RIMU_ANNIHILATE_PARTITION)
@@ -1099,26 +1174,30 @@ extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *
 // ---------------------------------------------------------------- the step
 static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_streams) {
     const int R = c->nranks, me = c->rank;
-    NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
     c->p2p_used = 0;
-    if (to_streams && c->xch.p2p) {
-        // The payload already sits in this rank's receive regions (peer stores issued by the spawn kernels, complete
-        // before the senders' streams reached the all-gather).  No host round trip: counts are consumed on the device.
+    if (to_streams && c->direct) {
+        // Direct mode: the spawn kernels bucketed the records for every peer in local memory; one kernel now ships them
+        // as coalesced runs straight into the owners' bucket sub-streams (peer stores over NVLink) together with the
+        // sub-stream fills.  The all-gather of the per-destination totals is the barrier that orders all of this
+        // before anybody's merge.  No receive pass, no host round trip.
+        u32 gx = (c->part.nb + (RIMU_TPB / 32) - 1) / (RIMU_TPB / 32); // one warp per (destination, bucket) run
+        const u32 gmax = (u32)(c->sm_count * 16 / (R > 1 ? R - 1 : 1)) + 1;
+        if (gx > gmax) gx = gmax;
+        if (c->W == 1) push_records_kernel<2><<<dim3(gx, R), RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
+        else push_records_kernel<4><<<dim3(gx, R), RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
+        CUDA_TRY(cudaGetLastError());
+        c->launches += 1;
+        NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->h_allcounts, c->d_allcounts, (size_t)R * R * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemsetAsync(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64), c->stream));
-        TRY(dispatch_wv(c->W, vt, [&](auto tag, auto vtag) {
-            typedef decltype(vtag) VT;
-            append_recv_kernel<decltype(tag)::w, VT><<<dim3(c->sm_count * 4, R), RIMU_TPB, 0, c->stream>>>(
-                c->recv_keys, (const VT *)c->recv_vals, c->d_allcounts, me, R, c->xch.cap, c->part, c->d_stats);
-            c->launches += 1;
-            return 0;
-        }));
-        CUDA_TRY(cudaGetLastError());
         c->p2p_used = 1;
         *sent_out = 0;
         return 0;
     }
+    TRY(ensure_xch(c));
+    NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_allcounts, c->d_allcounts, (size_t)R * R * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64), c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1154,7 +1233,7 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool t
             typedef decltype(vtag) VT;
             if (to_streams) // partitioned step: received records join this rank's bucket streams
                 append_records_kernel<decltype(tag)::w, VT><<<grid_for((i64)total_recv, c->sm_count), RIMU_TPB, 0, c->stream>>>(
-                    c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, c->rank, c->nranks, c->part, c->d_stats);
+                    c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, c->rank, c->nranks, c->part, c->part.me, c->d_stats);
             else
                 insert_records_kernel<decltype(tag)::w, VT><<<grid_for((i64)total_recv, c->sm_count), RIMU_TPB, 0, c->stream>>>(
                     c->recv_keys, (const VT *)c->recv_vals, (i64)total_recv, 1.0, 0, 0, 1, tab, c->d_stats);
@@ -1233,6 +1312,7 @@ static int rebucket(rimu_vec *v, u32 nb) {
 
 // testing / tuning hook: re-segment a vector for `nb` buckets (0 drops the segmentation)
 extern "C" int rimu_vec_rebucket(rimu_vec *v, uint32_t nb) {
+    if (v) v->version++;
     CUDA_TRY(cudaSetDevice(v->ctx->device));
     if (nb == 0) { v->nb = 0; return 0; }
     return rebucket(v, nb);
@@ -1264,7 +1344,8 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
         attr_set[HK][W][std::is_integral<VT>::value] = true;
     }
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->part.rec_count, 0, nb * sizeof(u32), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->part.rcnt + (size_t)c->part.me * nb, 0, nb * sizeof(u32), c->stream)); // own sub-stream fills
+    if (c->part.direct) CUDA_TRY(cudaMemsetAsync(c->part.scnt, 0, (size_t)c->nranks * nb * sizeof(u32), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->heavy.packed, 0, sizeof(u64), c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
@@ -1292,7 +1373,7 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
     SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr, src_diag};
     SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, dst->diag};
-    const int mgrid = (int)(nb < (u32)c->sm_count * 32 ? nb : (u32)c->sm_count * 32);
+    const int mgrid = (int)(nb < c->merge_grid_cap ? nb : c->merge_grid_cap);
     merge_kernel<HK, W, VT, 0><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;
@@ -1301,9 +1382,10 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
 }
 
 // bucket count for a step on `n` local parents
-static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src) {
+// `parents` = local parents (one rank) or the per-rank share of the global length (multi-GPU: the same number on every rank)
+static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
     const double cap = (double)part_cap_items(c->W);
-    const double expected = (double)src->n * (1.0 + c->rec_per_parent) * 1.15 + 512.0;
+    const double expected = parents * (1.0 + c->rec_per_parent) * 1.15 + 512.0;
     if (src->nb) { // keep the segmentation while the expected fill stays in a comfortable band
         double fill = expected / src->nb;
         if (fill > 0.25 * cap && fill < 0.80 * cap) return src->nb;
@@ -1338,17 +1420,28 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
     bool use_part = c->method == RIMU_ANNIHILATE_PARTITION;
     u64 slots = prm->table_slots ? next_pow2(prm->table_slots) : pick_slots(c, (u64)src->n * 2 + (u64)dst->n);
     if (slots > c->table_slots) slots = c->table_slots;
-    u32 nb = use_part ? choose_buckets(c, src) : 0;
+    // multi-GPU: the bucket count must be the same on every rank (peers store into each other's sub-streams), so it
+    // is derived from the GLOBAL vector length: known from the previous step's statistics when `src` is that step's
+    // untouched result, otherwise all-reduced here
+    double parents = (double)src->n, g_len = (double)src->n;
+    if (c->nranks > 1) {
+        if (c->last_dst == src && c->last_dst_version == src->version) g_len = c->last_g_len;
+        else TRY(rimu_comm_allreduce_f64(c, &g_len, 1));
+        parents = ceil(g_len / c->nranks * 1.02) + 64.0;
+    }
+    u32 nb = use_part ? choose_buckets(c, src, parents) : 0;
+    const bool multi = c->nranks > 1;
     // record-stream memory budget: beyond it this step falls back to the global HBM table
     size_t free_b = 0, total_b = 0;
-    const double rec_bytes_per_bucket = (double)part_cap_items(c->W) * (8.0 * c->W + 8.0);
+    const double rec_bytes_per_bucket = (double)part_cap_items(c->W) * (c->W == 1 ? 16.0 : 32.0);
     i64 sent = 0;
     for (int attempt = 0;; attempt++) {
-        if (use_part && nb > c->part_nb_cap) {
+        if (use_part && nb > c->part_nb_cap && !multi) { // (multi-GPU: a per-rank fallback would desynchronise the ranks)
             CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
             double have = (double)free_b + (double)c->part_nb_cap * rec_bytes_per_bucket;
             if ((double)nb * 1.3 * rec_bytes_per_bucket > 0.8 * have) use_part = false;
         }
+        if (multi && !(use_part && c->direct)) TRY(ensure_xch(c)); // staged exchange buffers (table method / no peer access)
         int r = dispatch_ham(h, [&](auto tag) {
             constexpr int HK = decltype(tag)::hk, W = decltype(tag)::w;
             if (use_part) {
@@ -1370,9 +1463,9 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         if (c->nranks > 1) {
             // ONE all-reduce per step: the integer block travels as doubles (counts stay far below 2^53, so the sums
             // are exact) next to the floating-point block (reference: Allreduce of a MultiScalar, pdvec.jl:896-902)
-            if (!c->d_red) CUDA_TRY(rimu_malloc(&c->d_red, (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP) * sizeof(double)));
+            if (!c->d_red) CUDA_TRY(rimu_malloc(&c->d_red, (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP + 1) * sizeof(double)));
             pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 0);
-            NCCL_TRY(g_nccl.AllReduce(c->d_red, c->d_red, RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP, ncclFloat64, ncclSum, c->comm, c->stream));
+            NCCL_TRY(g_nccl.AllReduce(c->d_red, c->d_red, RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP + 1, ncclFloat64, ncclSum, c->comm, c->stream));
             pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 1);
             CUDA_TRY(cudaGetLastError());
         }
@@ -1380,25 +1473,20 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const StatsDev &g = *c->h_stats, &l = *c->h_stats_local;
-        if (c->nranks > 1 && c->p2p_used) {
-            u64 worst = 0; sent = 0;
-            for (int s_ = 0; s_ < c->nranks; s_++)
-                for (int d_ = 0; d_ < c->nranks; d_++) { u64 n_ = c->h_allcounts[s_ * c->nranks + d_]; if (s_ != d_ && n_ > worst) worst = n_; }
+        if (c->nranks > 1 && c->p2p_used) { // direct mode: per-destination totals of every rank arrived with the barrier all-gather
+            sent = 0;
             for (int d_ = 0; d_ < c->nranks; d_++) if (d_ != c->rank) sent += (i64)c->h_allcounts[c->rank * c->nranks + d_];
-            if (g.overflow_xchg || worst > c->xch.cap) { // identical on every rank (summed flag, gathered counts)
-                c->xch_worst = worst;
-                return fail(RIMU_ERR_EXCHANGE_FULL, "per-peer exchange buffer (%llu records) too small: a rank produced %llu records for one peer",
-                            (unsigned long long)c->xch.cap, (unsigned long long)worst);
-            }
         }
         if (g.overflow_table) { // some rank ran out of room: every rank retries with more working memory
             if (attempt > 12) return fail(RIMU_ERR_TABLE_FULL, "step working memory cannot be grown further");
             if (use_part) {
                 // size the bucket count from what this attempt saw (records are counted even when dropped)
                 const double cap = (double)part_cap_items(c->W);
-                double need = ceil(((double)src->n + (double)l.records) * 1.15 / (0.6 * cap)); // (diagonal records may be counted twice: harmless)
+                const double recs = multi ? (double)g.records / c->nranks * 1.02 : (double)l.records; // g.records: summed over ranks
+                double need = ceil((parents + recs) * 1.15 / (0.6 * cap)); // (diagonal records may be counted twice: harmless)
                 u32 nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb * 2 + 1);
-                if (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26)) use_part = false; // one address is too hot to pre-sum: use the table
+                if (!multi && (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26))) use_part = false; // one address is too hot to pre-sum: use the table
+                if (multi && nb2 > (1u << 26)) return fail(RIMU_ERR_TABLE_FULL, "bucket streams cannot be grown further");
                 nb = nb2;
                 continue;
             }
@@ -1420,10 +1508,13 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         dst->n = (i64)l.out_count;
         dst->nb = use_part ? nb : 0;
         dst->diag_uid = use_part ? h->uid : 0;
+        dst->version++;
+        c->last_dst = dst; c->last_dst_version = dst->version; c->last_g_len = (double)g.len;
         if (use_part) {
-            if (src->n > 0) {
-                double rec = (double)l.records - (src->nb == nb ? 0.0 : (double)src->n); // unsegmented sources add one diagonal record per parent
-                c->rec_per_parent = 0.5 * c->rec_per_parent + 0.5 * (rec > 0 ? rec : 0.0) / (double)src->n;
+            const double rec_all = multi ? (double)g.records : (double)l.records, par_all = multi ? g_len : (double)src->n;
+            if (par_all > 0) { // identical on every rank in multi-GPU runs (all-reduced inputs)
+                double rec = rec_all - (src->nb == nb ? 0.0 : par_all); // unsegmented sources add one diagonal record per parent
+                c->rec_per_parent = 0.5 * c->rec_per_parent + 0.5 * (rec > 0 ? rec : 0.0) / par_all;
             }
             c->last_max_fill = l.max_fill;
         }

@@ -64,11 +64,6 @@ struct ExchangeDev { // per-peer send staging for multi-GPU spawn exchange
     u64 *vals;       // [nranks][cap]
     u64 *counts;     // [nranks]
     u64 cap;
-    // peer-direct mode (NVLink peer memory, CUDA IPC): records for rank r are stored straight into r's receive
-    // buffer, region [this rank][cap]; only the counts travel through a collective
-    int p2p;
-    u64 *peer_keys[RIMU_MAX_RANKS];
-    u64 *peer_vals[RIMU_MAX_RANKS];
 };
 
 #ifdef __CUDACC__
@@ -210,6 +205,10 @@ __global__ void pack_stats_kernel(StatsDev *st, double *buf, int dir) {
     double *dbl = reinterpret_cast<double *>(reinterpret_cast<char *>(st) + RIMU_STATS_NI64 * sizeof(i64));
     if (i < RIMU_STATS_NI64) { if (dir == 0) buf[i] = (double)ints[i]; else ints[i] = (i64)llrint(buf[i]); }
     if (i < RIMU_STATS_NF64_STEP) { if (dir == 0) buf[RIMU_STATS_NI64 + i] = dbl[i]; else dbl[i] = buf[RIMU_STATS_NI64 + i]; }
+    if (i == 31) { // spawn records appended (block C): summed so that every rank sizes the next bucket count identically
+        const int at = RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP;
+        if (dir == 0) buf[at] = (double)st->records; else st->records = (u64)llrint(buf[at]);
+    }
 }
 
 // ---------------------------------------------------------------- K1: diagonal step + attempt counts

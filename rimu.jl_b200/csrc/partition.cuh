@@ -49,12 +49,23 @@
 template <int W> struct PartCap { static constexpr int value = PART_CAP; };
 
 struct PartDev {       // bucket record streams (working memory of the partitioned step)
-    u32 nb;            // buckets on this rank
-    u32 rcap;          // records per bucket stream
-    u64 *rec_keys;     // [nb][rcap][W]
-    u64 *rec_vals;     // [nb][rcap]
-    u32 *rec_count;    // [nb]
+    u32 nb;            // buckets per rank (identical on all ranks of a step)
+    u32 rcap;          // records per (bucket, source rank) sub-stream
+    u32 nsrc;          // sub-streams per bucket: 1, or the number of ranks in direct (peer-store) mode
+    u32 me;            // this rank's sub-stream (0 when nsrc == 1)
+    u64 *rec;          // [nb][nsrc][rcap] records, array of structures: W=1 {key, value} (16 B), W=2 {k0, k1, value, pad} (32 B)
+    u32 *rcnt;         // [nsrc][nb] fill of every sub-stream; slot `me` is counted locally, the others are pushed by their senders
+    // direct mode (multi-GPU, CUDA IPC peer memory): a spawned record is stored straight into sub-stream [bucket][this rank] of
+    // its OWNER's streams over NVLink; the slot comes from a LOCAL counter, so no remote atomics and no receive pass
+    int direct;
+    u32 *scnt;                       // [nranks][nb] records this rank produced for rank d's bucket b (d != me)
+    u64 *srec;                       // [nranks][nb][rcap] ... staged here, bucketed, in LOCAL memory (L2 write-combined 16-byte
+                                     //   appends), then shipped by push_records_kernel as coalesced runs: fine-grained peer
+                                     //   stores were measured at ~10 G packets/s, 3x slower than the bulk copy
+    u64 *peer_rec[RIMU_MAX_RANKS];   // rec of every rank ([me] = rec)
+    u32 *peer_rcnt[RIMU_MAX_RANKS];  // rcnt of every rank
 };
+template <int W> struct RecWords { static constexpr int value = W == 1 ? 2 : 4; };
 struct SegSrc {        // a segmented vector, read side (diag: cached diagonal elements or null)
     const u64 *keys; const u64 *vals; const u64 *seg_start; const u32 *seg_len; const double *diag;
 };
@@ -81,22 +92,38 @@ DEV void l2_prefetch(const void *p, u64 bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(sz) : "memory");
 }
 
+template <int W> DEV void store_rec(u64 *p, typename BitsT<W>::type key, u64 vbits);
+template <> DEV void store_rec<1>(u64 *p, u64 key, u64 vbits) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(key, vbits); }
+template <> DEV void store_rec<2>(u64 *p, u128 key, u64 vbits) {
+    reinterpret_cast<ulonglong2 *>(p)[0] = make_ulonglong2((u64)key, (u64)(key >> 64));
+    reinterpret_cast<ulonglong2 *>(p)[1] = make_ulonglong2(vbits, 0ull);
+}
+template <int W> DEV void load_rec(const u64 *p, typename BitsT<W>::type &key, u64 &vbits);
+template <> DEV void load_rec<1>(const u64 *p, u64 &key, u64 &vbits) {
+    const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(p); key = r.x; vbits = r.y;
+}
+template <> DEV void load_rec<2>(const u64 *p, u128 &key, u64 &vbits) {
+    const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(p)[0]; key = ((u128)a.y << 64) | (u128)a.x;
+    vbits = p[2];
+}
+
+// append to sub-stream `slot` of the LOCAL bucket of hash h
 template <int W, class VT>
-DEV void append_record(const PartDev &pt, StatsDev *st, typename BitsT<W>::type key, u64 h, int nranks, VT v) {
-    u32 b = bucket_of(h, nranks, pt.nb);
-    u32 pos = atomicAdd(&pt.rec_count[b], 1u);
+DEV void append_record(const PartDev &pt, StatsDev *st, typename BitsT<W>::type key, u64 h, int nranks, VT v, u32 slot) {
+    const u32 b = bucket_of(h, nranks, pt.nb);
+    const u32 pos = atomicAdd(&pt.rcnt[(u64)slot * pt.nb + b], 1u);
     if (pos < pt.rcap) {
-        u64 at = (u64)b * pt.rcap + pos;
-        store_key<W>(pt.rec_keys + at * W, key);
         union { VT v; u64 b; } cv; cv.v = v;
-        pt.rec_vals[at] = cv.b;
+        store_rec<W>(pt.rec + (((u64)b * pt.nsrc + slot) * pt.rcap + pos) * RecWords<W>::value, key, cv.b);
     } else st->overflow_table = 1;
 }
 
-// CTA-collective routing of at most one spawn record per thread: local children go to their bucket stream;
-// records for other ranks are staged per peer -- ranks within the CTA come from a shared-memory counter, ONE
-// global atomic per peer and CTA reserves a contiguous run in that peer's exchange segment (the reference packs
-// per-rank buffers serially, communicators.jl:421-444).  Every thread of the CTA must call this.
+// CTA-collective routing of at most one spawn record per thread.  Every thread of the CTA must call this.
+//  * one rank, or direct mode: the record goes straight into sub-stream [bucket][this rank] of its owner's streams -- a
+//    local counter atomic and one 16/32-byte store (a peer store over NVLink when the owner is another GPU);
+//  * staged mode (no peer access): records for other ranks are staged per peer -- ranks within the CTA come from a
+//    shared-memory counter, ONE global atomic per peer and CTA reserves a contiguous run in that peer's exchange segment
+//    (the reference packs per-rank buffers serially, communicators.jl:421-444); NCCL send/recv moves the segments.
 struct RouteSmem { u32 cnt[RIMU_MAX_RANKS]; u64 base[RIMU_MAX_RANKS]; };
 template <int W, class VT>
 DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p, StatsDev *st, RouteSmem &rs,
@@ -107,7 +134,16 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
         h = hash_bits(key);
         if (p.nranks > 1) owner = addr_owner(h, p.nranks);
     }
-    if (p.nranks > 1) { // uniform over the grid
+    if (p.nranks > 1 && pt.direct) { // uniform over the grid
+        if (has && owner != p.rank) {
+            const u32 b = bucket_of(h, p.nranks, pt.nb);
+            const u32 pos = atomicAdd(&pt.scnt[(u64)owner * pt.nb + b], 1u);
+            if (pos < pt.rcap) {
+                union { VT v; u64 b; } cv; cv.v = v;
+                store_rec<W>(pt.srec + (((u64)owner * pt.nb + b) * pt.rcap + pos) * RecWords<W>::value, key, cv.b);
+            } else st->overflow_table = 1;
+        }
+    } else if (p.nranks > 1) {
         if (threadIdx.x < RIMU_MAX_RANKS) rs.cnt[threadIdx.x] = 0;
         __syncthreads();
         const bool remote = has && owner != p.rank;
@@ -121,18 +157,40 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
             const u64 idx = rs.base[owner] + lrank;
             if (idx < x.cap) {
                 union { VT v; u64 b; } cv; cv.v = v;
-                if (x.p2p) { // straight into the owner's receive region for this rank (NVLink peer store)
-                    const u64 at = (u64)p.rank * x.cap + idx;
-                    store_key<W>(x.peer_keys[owner] + at * W, key);
-                    x.peer_vals[owner][at] = cv.b;
-                } else {
-                    store_key<W>(x.keys + ((u64)owner * x.cap + idx) * W, key);
-                    x.vals[(u64)owner * x.cap + idx] = cv.b;
-                }
+                store_key<W>(x.keys + ((u64)owner * x.cap + idx) * W, key);
+                x.vals[(u64)owner * x.cap + idx] = cv.b;
             } else st->overflow_xchg = 1;
         }
     }
-    if (has && owner == p.rank) append_record<W, VT>(pt, st, key, h, p.nranks, v);
+    if (has && owner == p.rank) append_record<W, VT>(pt, st, key, h, p.nranks, v, pt.me);
+}
+
+// direct mode: after the spawn kernels, ship to every peer d the records staged for each of its buckets -- one warp per
+// (destination, bucket) run, 16 bytes per lane, straight into sub-stream [bucket][this rank] of d's streams over NVLink --
+// together with the fill of that sub-stream, and total the records per destination for the statistics
+template <int RW>
+__global__ void __launch_bounds__(RIMU_TPB) push_records_kernel(PartDev pt, int me, int R, u64 *__restrict__ totals) {
+    const int d = blockIdx.y;
+    if (d == me) return;
+    const int lane = threadIdx.x & 31;
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    u32 *dcnt = pt.peer_rcnt[d] + (u64)me * pt.nb;
+    const u32 *scnt = pt.scnt + (u64)d * pt.nb;
+    u64 sum = 0;
+    for (u32 b = warp; b < pt.nb; b += nwarps) {
+        const u32 c0 = scnt[b], c = c0 < pt.rcap ? c0 : pt.rcap;
+        if (lane == 0) { dcnt[b] = c; sum += c0; }
+        const ulonglong2 *from = reinterpret_cast<const ulonglong2 *>(pt.srec + (((u64)d * pt.nb + b) * pt.rcap) * RW);
+        ulonglong2 *to = reinterpret_cast<ulonglong2 *>(pt.peer_rec[d] + (((u64)b * pt.nsrc + me) * pt.rcap) * RW);
+        const u32 units = c * (RW / 2);
+        u32 i = lane;
+        for (; i + 96 < units; i += 128) { // four 16-byte loads in flight per lane
+            const ulonglong2 a0 = from[i], a1 = from[i + 32], a2 = from[i + 64], a3 = from[i + 96];
+            to[i] = a0; to[i + 32] = a1; to[i + 64] = a2; to[i + 96] = a3;
+        }
+        for (; i < units; i += 32) to[i] = from[i];
+    }
+    if (lane == 0 && sum) atomicAdd(&totals[d], sum);
 }
 
 // one spawn attempt k of a parent (spawning.jl:174-182 Exact, :232-243 WithReplacement).
@@ -314,7 +372,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
 template <int W, class VT>
 __global__ void __launch_bounds__(RIMU_TPB)
 append_records_kernel(const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n, double scale, int use_scale,
-                      int rank, int nranks, PartDev pt, StatsDev *st) {
+                      int rank, int nranks, PartDev pt, u32 slot, StatsDev *st) {
     typedef typename BitsT<W>::type B;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         B key = load_key<W>(keys + i * W);
@@ -323,47 +381,7 @@ append_records_kernel(const u64 *__restrict__ keys, const VT *__restrict__ vals,
         if (v == (VT)0) continue;
         u64 hh = hash_bits(key);
         if (nranks > 1 && addr_owner(hh, nranks) != rank) continue;
-        append_record<W, VT>(pt, st, key, hh, nranks, v);
-    }
-}
-
-// peer-direct exchange, receiving side: region [src][cap] of the receive buffer holds allcounts[src][me] records
-template <int W, class VT>
-__global__ void __launch_bounds__(RIMU_TPB)
-append_recv_kernel(const u64 *__restrict__ recv_keys, const VT *__restrict__ recv_vals, const u64 *__restrict__ allcounts,
-                   int me, int R, u64 cap, PartDev pt, StatsDev *st) {
-    typedef typename BitsT<W>::type B;
-    const int src = blockIdx.y;
-    if (src == me) return;
-    u64 n = allcounts[(u64)src * R + me];
-    if (n > cap) n = cap; // the sender raised overflow_xchg
-    // four records per thread and iteration: the four counter atomics are in flight together (the kernel is bound by
-    // their round-trip latency, not by bytes)
-    constexpr int U = 4;
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
-        B key[U]; VT v[U]; u32 bk[U], pos[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const u64 i = i0 + (u64)u * stride;
-            v[u] = (VT)0; key[u] = 0;
-            if (i < n) { const u64 at = (u64)src * cap + i; key[u] = load_key<W>(recv_keys + at * W); v[u] = recv_vals[at]; }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            pos[u] = 0xffffffffu; bk[u] = 0;
-            if (v[u] != (VT)0) { bk[u] = bucket_of(hash_bits(key[u]), R, pt.nb); pos[u] = atomicAdd(&pt.rec_count[bk[u]], 1u); }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (v[u] == (VT)0) continue;
-            if (pos[u] < pt.rcap) {
-                const u64 at = (u64)bk[u] * pt.rcap + pos[u];
-                store_key<W>(pt.rec_keys + at * W, key[u]);
-                union { VT v; u64 b; } cv; cv.v = v[u];
-                pt.rec_vals[at] = cv.b;
-            } else st->overflow_table = 1;
-        }
+        append_record<W, VT>(pt, st, key, hh, nranks, v, slot);
     }
 }
 
@@ -396,7 +414,7 @@ diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
         if (rs > val) clones += fabs(rs - val);
         else if (sgn_(rs) != sgn_(val)) { deaths += fabs(val); zombies += fabs(rs); }
         else deaths += fabs(rs - val);
-        if (v != (VT)0) append_record<W, VT>(pt, st, key, hk, p.nranks, v);
+        if (v != (VT)0) append_record<W, VT>(pt, st, key, hk, p.nranks, v, pt.me);
     }
     if (is_int) { stat_add(&st->iclones, (i64)clones); stat_add(&st->ideaths, (i64)deaths); stat_add(&st->izombies, (i64)zombies); }
     else { stat_add(&st->clones, clones); stat_add(&st->deaths, deaths); stat_add(&st->zombies, zombies); }
@@ -433,10 +451,13 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     i64 inorm1 = 0, len_before = 0, len = 0, ndep = 0;
     u32 max_fill = 0;
     u64 nrec_sum = 0;
-    // bucket metadata runs two buckets ahead of the merge and the next bucket's parents and records are pulled into
-    // L2 with bulk prefetches while this one is merged, so that staging sees L2 latency instead of two dependent
-    // HBM round trips (metadata, then data)
-    u32 m_np[2] = {0, 0}, m_nrec[2] = {0, 0};
+    // Bucket metadata (segment of parents, fill of every source's sub-stream) runs two buckets ahead of the merge, and
+    // the next bucket's parents and records are pulled into L2 with bulk prefetches while this one is merged, so that
+    // staging sees L2 latency instead of two dependent HBM round trips (metadata, then data).
+    constexpr int RW = RecWords<W>::value;
+    __shared__ u32 s_cnt[3][RIMU_MAX_RANKS]; // ring: sub-stream fills of this bucket, the next, the one after
+    const u32 nsrc = pt.nsrc;
+    u32 m_np[2] = {0, 0};
     u64 m_p0[2] = {0, 0};
 #pragma unroll
     for (int q = 0; q < 2; q++) {
@@ -444,41 +465,47 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         if (bq < pt.nb) {
             m_np[q] = src.seg_len ? src.seg_len[bq] : 0u;
             m_p0[q] = m_np[q] ? src.seg_start[bq] : 0ull;
-            m_nrec[q] = pt.rec_count[bq];
         }
+        if ((u32)tid < nsrc) s_cnt[q][tid] = bq < pt.nb ? pt.rcnt[(u64)tid * pt.nb + bq] : 0u;
     }
-    for (u32 b = blockIdx.x; b < pt.nb; b += gridDim.x) {
+    __syncthreads();
+    u32 ring = 0;
+    for (u32 b = blockIdx.x; b < pt.nb; b += gridDim.x, ring = ring == 2 ? 0 : ring + 1) {
+        const u32 cur = ring, nxt = ring == 2 ? 0 : ring + 1, nn = nxt == 2 ? 0 : nxt + 1;
         const u32 np = m_np[0];
         const u64 p0 = m_p0[0];
-        const u32 nrec = m_nrec[0];
-        m_np[0] = m_np[1]; m_p0[0] = m_p0[1]; m_nrec[0] = m_nrec[1];
+        m_np[0] = m_np[1]; m_p0[0] = m_p0[1];
+        u32 pending_cnt = 0; // fill of sub-stream `tid` two buckets ahead; stored to the ring at the end of this iteration
         {
             const u64 b2 = (u64)b + 2ull * gridDim.x;
-            m_np[1] = 0; m_p0[1] = 0; m_nrec[1] = 0;
+            m_np[1] = 0; m_p0[1] = 0;
             if (b2 < pt.nb) {
                 m_np[1] = src.seg_len ? src.seg_len[b2] : 0u;
                 m_p0[1] = m_np[1] ? src.seg_start[b2] : 0ull;
-                m_nrec[1] = pt.rec_count[b2];
+                if ((u32)tid < nsrc) pending_cnt = pt.rcnt[(u64)tid * pt.nb + b2];
             }
             const u64 b1 = (u64)b + gridDim.x;
-            if (tid == 0 && b1 < pt.nb) {
-                const u32 np1 = m_np[0], nrec1 = m_nrec[0] < pt.rcap ? m_nrec[0] : pt.rcap;
-                if (np1) {
-                    l2_prefetch(src.keys + m_p0[0] * W, (u64)np1 * W * 8);
-                    l2_prefetch(src.vals + m_p0[0], (u64)np1 * 8);
-                    if (src.diag) l2_prefetch(src.diag + m_p0[0], (u64)np1 * 8);
-                }
-                if (nrec1) {
-                    l2_prefetch(pt.rec_keys + b1 * pt.rcap * W, (u64)nrec1 * W * 8);
-                    l2_prefetch(pt.rec_vals + b1 * pt.rcap, (u64)nrec1 * 8);
+            if (b1 < pt.nb) {
+                if ((u32)tid < nsrc) {
+                    const u32 c1 = s_cnt[nxt][tid] < pt.rcap ? s_cnt[nxt][tid] : pt.rcap;
+                    if (c1) l2_prefetch(pt.rec + ((b1 * nsrc + tid) * pt.rcap) * RW, (u64)c1 * RW * 8);
+                } else if (tid == 32 && m_np[0]) {
+                    l2_prefetch(src.keys + m_p0[0] * W, (u64)m_np[0] * W * 8);
+                    l2_prefetch(src.vals + m_p0[0], (u64)m_np[0] * 8);
+                    if (src.diag) l2_prefetch(src.diag + m_p0[0], (u64)m_np[0] * 8);
                 }
             }
         }
+        u32 nrec = 0;
+        bool sub_over = false;
+        for (u32 q = 0; q < nsrc; q++) { const u32 cq = s_cnt[cur][q]; nrec += cq; sub_over |= cq > pt.rcap; }
         const u32 n = np + nrec;
         max_fill = max(max_fill, n);
         nrec_sum += nrec;
-        if (nrec > pt.rcap || n > (u32)CAP) { // uniform over the CTA: the host retries with more buckets
+        if (sub_over || n > (u32)CAP) { // uniform over the CTA: the host retries with more buckets
             if (tid == 0) { st->overflow_table = 1; dst.seg_len[b] = 0; dst.seg_start[b] = 0; }
+            if ((u32)tid < nsrc) s_cnt[nn][tid] = pending_cnt;
+            __syncthreads();
             continue;
         }
         for (int i = tid; i < 2 * CAP; i += PART_NT) owner[i] = NIL;
@@ -518,9 +545,11 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                     v = (VT)(alpha * (double)pv);
                 }
             } else {
-                const u64 at = (u64)b * pt.rcap + (i - np);
-                key = load_key<W>(pt.rec_keys + at * W);
-                union { u64 b; VT v; } cv; cv.b = pt.rec_vals[at]; v = cv.v;
+                u32 j = i - np, q = 0; // record j of the bucket -> (source sub-stream q, position j)
+                if (nsrc > 1) for (u32 cq = s_cnt[cur][0]; j >= cq; cq = s_cnt[cur][q]) { j -= cq; q++; }
+                union { u64 b; VT v; } cv;
+                load_rec<W>(pt.rec + ((((u64)b * nsrc + q) * pt.rcap) + j) * RW, key, cv.b);
+                v = cv.v;
             }
             pidx[i] = (unsigned short)NOPARENT;
             if (v != (VT)0) {
@@ -653,6 +682,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             }
         }
         len += cnt;
+        if ((u32)tid < nsrc) s_cnt[nn][tid] = pending_cnt; // (loaded at the top of this iteration: its latency is long gone)
         __syncthreads();
         if constexpr (MODE == 0) {
             // dense evaluation of H_aa for the gathered survivors (a per-lane evaluation inside the output loop

@@ -158,7 +158,8 @@ class AbstractHamiltonian:
     @property
     def handle(self):
         if self._handle is None:
-            ctx = self.ctx  # creating the context selects the device
+            ctx = self.ctx
+            _lib.check(_lib.lib().rimu_ctx_make_current(ctx.handle))  # the tables go to the context's GPU
             h = C.c_void_p()
             _lib.check(_lib.lib().rimu_ham_create(C.byref(self.desc), C.byref(h)))
             self._handle = h

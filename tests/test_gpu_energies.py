@@ -195,3 +195,36 @@ def test_hv_linearity_and_symmetry_at_scale(built, name):
     diff = hz.copy()
     diff.add_(comb, -1.0)
     assert diff.norm(2) <= 1e-12 * max(1.0, hz.norm(2)), (diff.norm(2), hz.norm(2))
+
+
+def test_many_buckets_per_merge_cta(built, monkeypatch):
+    """The merge kernel pipelines bucket metadata two buckets ahead through a shared-memory ring; with the default grid
+    (one CTA per bucket up to 32 per SM) small problems never advance the ring.  A context whose merge grid is capped
+    at ONE CTA walks every bucket in that CTA; the step must equal the table method's result."""
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+    monkeypatch.setenv("RIMU_B200_MERGE_GRID", "1")
+    ctx = R.Context(1)
+    monkeypatch.delenv("RIMU_B200_MERGE_GRID")
+    ph = product_ham("mom1d_bose_20")
+    big = _grow(R, ph, 150_000, R.IsDynamicSemistochastic())
+    keys, vals = big.download()
+    v = R.GPUDVec(style=R.IsDynamicSemistochastic(), address_type=big.address_type, ctx=ctx)
+    v.assign(keys, vals)
+    shift = R.diagonal_element(ph, ph.address)
+    out = {}
+    for method in (0, 2):
+        _lib.check(_lib.lib().rimu_ctx_set_method(ctx.handle, method))
+        wm = R.working_memory(v, seed=5)
+        cur = v
+        for _ in range(3):  # the second and third step run on a segmented source
+            nxt = cur.similar()
+            R.apply_operator(wm, nxt, cur, R.FirstOrderTransitionOperator(ph, shift, 1e-3))
+            cur = nxt
+        out[method] = cur.download_sorted() + (wm.last_stats.spawn_attempts, wm.last_stats.len, wm.last_stats.buckets)
+    (k0, v0, a0, l0, _), (k2, v2, a2, l2, nb) = out[0], out[2]
+    assert nb >= 8, nb
+    assert (a0, l0) == (a2, l2)
+    assert np.array_equal(k0, k2) and np.allclose(v0, v2, rtol=1e-10, atol=0)
+    del v, cur, nxt, big
+    ctx.close()
