@@ -1180,11 +1180,12 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool t
         // as coalesced runs straight into the owners' bucket sub-streams (peer stores over NVLink) together with the
         // sub-stream fills.  The all-gather of the per-destination totals is the barrier that orders all of this
         // before anybody's merge.  No receive pass, no host round trip.
-        u32 gx = (c->part.nb + (RIMU_TPB / 32) - 1) / (RIMU_TPB / 32); // one warp per (destination, bucket) run
-        const u32 gmax = (u32)(c->sm_count * 16 / (R > 1 ? R - 1 : 1)) + 1;
-        if (gx > gmax) gx = gmax;
-        if (c->W == 1) push_records_kernel<2><<<dim3(gx, R), RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
-        else push_records_kernel<4><<<dim3(gx, R), RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
+        const u64 nruns = (u64)(R - 1) * c->part.nb; // one warp per (destination, bucket) run
+        u64 gx = (nruns + (RIMU_TPB / 32) - 1) / (RIMU_TPB / 32);
+        if (gx > (u64)c->sm_count * 8) gx = (u64)c->sm_count * 8;
+        if (gx < 1) gx = 1;
+        if (c->W == 1) push_records_kernel<2><<<(unsigned)gx, RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
+        else push_records_kernel<4><<<(unsigned)gx, RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
         CUDA_TRY(cudaGetLastError());
         c->launches += 1;
         NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));

@@ -170,16 +170,19 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
 // together with the fill of that sub-stream, and total the records per destination for the statistics
 template <int RW>
 __global__ void __launch_bounds__(RIMU_TPB) push_records_kernel(PartDev pt, int me, int R, u64 *__restrict__ totals) {
-    const int d = blockIdx.y;
-    if (d == me) return;
     const int lane = threadIdx.x & 31;
-    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    u32 *dcnt = pt.peer_rcnt[d] + (u64)me * pt.nb;
-    const u32 *scnt = pt.scnt + (u64)d * pt.nb;
-    u64 sum = 0;
-    for (u32 b = warp; b < pt.nb; b += nwarps) {
-        const u32 c0 = scnt[b], c = c0 < pt.rcap ? c0 : pt.rcap;
-        if (lane == 0) { dcnt[b] = c; sum += c0; }
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    const u64 nruns = (u64)(R - 1) * pt.nb;
+    // consecutive warps serve different destinations, and rank `me` starts its rotation at me+1: at any moment every
+    // rank is sending to every peer, so no receiver sees an incast while the others idle
+    for (u64 r = warp; r < nruns; r += nwarps) {
+        const int d = (me + 1 + (int)(r % (u64)(R - 1))) % R;
+        const u32 b = (u32)(r / (u64)(R - 1));
+        const u32 c0 = pt.scnt[(u64)d * pt.nb + b], c = c0 < pt.rcap ? c0 : pt.rcap;
+        if (lane == 0) {
+            pt.peer_rcnt[d][(u64)me * pt.nb + b] = c;
+            if (c0) atomicAdd(&totals[d], (u64)c0);
+        }
         const ulonglong2 *from = reinterpret_cast<const ulonglong2 *>(pt.srec + (((u64)d * pt.nb + b) * pt.rcap) * RW);
         ulonglong2 *to = reinterpret_cast<ulonglong2 *>(pt.peer_rec[d] + (((u64)b * pt.nsrc + me) * pt.rcap) * RW);
         const u32 units = c * (RW / 2);
@@ -190,7 +193,6 @@ __global__ void __launch_bounds__(RIMU_TPB) push_records_kernel(PartDev pt, int 
         }
         for (; i < units; i += 32) to[i] = from[i];
     }
-    if (lane == 0 && sum) atomicAdd(&totals[d], sum);
 }
 
 // one spawn attempt k of a parent (spawning.jl:174-182 Exact, :232-243 WithReplacement).
