@@ -510,32 +510,43 @@ static inline void rng_draw(uint64_t h, uint64_t k, int stream, const uint32_t k
 
 /* ------------------------------------------------------------------ accumulation map (the "working memory") */
 typedef union { double f; int64_t i; } orc_val;
-typedef struct { uint64_t *keys; orc_val *vals; uint8_t *used; size_t cap, count; int W, is_int; } orc_mapv;
+/* vals = safe lane (the only one without an initiator rule); vals_u / vals_i = unsafe / initiator lanes of
+ * InitiatorValue (DictVectors/initiators.jl:22-45) */
+typedef struct { uint64_t *keys; orc_val *vals, *vals_u, *vals_i; uint8_t *used; size_t cap, count; int W, is_int; } orc_mapv;
+enum { LANE_SAFE = 0, LANE_UNSAFE = 1, LANE_INIT = 2 };
 
 static void mapv_init(orc_mapv *m, int W, int is_int, size_t cap) {
     size_t c = 64; while (c < cap) c <<= 1;
     m->cap = c; m->count = 0; m->W = W; m->is_int = is_int;
     m->keys = (uint64_t *)malloc(sizeof(uint64_t) * W * c);
     m->vals = (orc_val *)calloc(c, sizeof(orc_val));
+    m->vals_u = (orc_val *)calloc(c, sizeof(orc_val));
+    m->vals_i = (orc_val *)calloc(c, sizeof(orc_val));
     m->used = (uint8_t *)calloc(c, 1);
 }
-static void mapv_free(orc_mapv *m) { free(m->keys); free(m->vals); free(m->used); }
-static void mapv_add(orc_mapv *m, const uint64_t *key, orc_val v);
+static void mapv_free(orc_mapv *m) { free(m->keys); free(m->vals); free(m->vals_u); free(m->vals_i); free(m->used); }
+static void mapv_add_lane(orc_mapv *m, const uint64_t *key, orc_val v, int lane);
+static void mapv_add(orc_mapv *m, const uint64_t *key, orc_val v) { mapv_add_lane(m, key, v, LANE_SAFE); }
 static void mapv_grow(orc_mapv *m) {
     orc_mapv n; mapv_init(&n, m->W, m->is_int, m->cap * 2);
-    for (size_t s = 0; s < m->cap; s++) if (m->used[s]) mapv_add(&n, m->keys + s * m->W, m->vals[s]);
+    for (size_t s = 0; s < m->cap; s++) if (m->used[s]) {
+        mapv_add_lane(&n, m->keys + s * m->W, m->vals[s], LANE_SAFE);
+        mapv_add_lane(&n, m->keys + s * m->W, m->vals_u[s], LANE_UNSAFE);
+        mapv_add_lane(&n, m->keys + s * m->W, m->vals_i[s], LANE_INIT);
+    }
     mapv_free(m); *m = n;
 }
-static void mapv_add(orc_mapv *m, const uint64_t *key, orc_val v) {
+static void mapv_add_lane(orc_mapv *m, const uint64_t *key, orc_val v, int lane) {
     if ((m->count + 1) * 2 > m->cap) mapv_grow(m);
     size_t mask = m->cap - 1, s = (size_t)addr_hash(key, m->W) & mask;
     for (;;) {
         if (!m->used[s]) {
             m->used[s] = 1; memcpy(m->keys + s * m->W, key, sizeof(uint64_t) * m->W);
-            m->vals[s] = v; m->count++; return;
+            m->vals[s].i = 0; m->vals_u[s].i = 0; m->vals_i[s].i = 0; m->count++;
         }
         if (memcmp(m->keys + s * m->W, key, sizeof(uint64_t) * m->W) == 0) {
-            if (m->is_int) m->vals[s].i += v.i; else m->vals[s].f += v.f;
+            orc_val *dst = lane == LANE_SAFE ? &m->vals[s] : lane == LANE_UNSAFE ? &m->vals_u[s] : &m->vals_i[s];
+            if (m->is_int) dst->i += v.i; else dst->f += v.f;
             return;
         }
         s = (s + 1) & mask;
@@ -553,9 +564,9 @@ static int mapv_get(const orc_mapv *m, const uint64_t *key, orc_val *v) {
 /* deposit sink: one map (serial DVec semantics) or T row-maps chosen by target segment
  * (PDWorkingMemory column, pdworkingmemory.jl:21-31) */
 typedef struct { orc_mapv *maps; int T; } orc_sink;
-static inline void sink_add(orc_sink *s, const uint64_t *key, orc_val v) {
+static inline void sink_add(orc_sink *s, const uint64_t *key, orc_val v, int lane) {
     int row = s->T > 1 ? addr_owner(addr_hash(key, s->maps[0].W) << 32, s->T) : 0;
-    mapv_add(&s->maps[row], key, v);
+    mapv_add_lane(&s->maps[row], key, v, lane);
 }
 
 /* ------------------------------------------------------------------ step */
@@ -567,7 +578,35 @@ typedef struct {
     double rel_threshold, abs_threshold; /* DynamicSemistochastic (spawning.jl:358-378) */
     double compress_threshold;           /* ThresholdCompression, 0 = NoCompression */
     uint32_t key[2];        /* Philox key for this step */
+    int32_t initiator_rule; /* 0 NonInitiator, 1 Initiator, 2 SimpleInitiator, 3 CoherentInitiator (initiators.jl:132-236) */
+    int32_t pad_;
+    double initiator_threshold;
 } orc_step_params;
+
+/* to_initiator_value (initiators.jl:142-158): which lane of the child's InitiatorValue a deposit goes to */
+static inline int deposit_lane(const orc_step_params *p, int diagonal, double parent_val) {
+    if (p->initiator_rule == 0) return LANE_SAFE;
+    int is_initiator = fabs(parent_val) > p->initiator_threshold;
+    if (diagonal) return is_initiator ? LANE_INIT : LANE_SAFE;
+    return is_initiator ? LANE_SAFE : LANE_UNSAFE;
+}
+/* from_initiator_value (initiators.jl:136-138, 177-179, 201-207) */
+static inline double from_initiator_f(const orc_step_params *p, double safe, double unsafe, double init) {
+    switch (p ? p->initiator_rule : 0) {
+    case 1: return safe + init + (init != 0.0 ? 1.0 : 0.0) * unsafe;
+    case 2: return safe + init;
+    case 3: return (init != 0.0 || fabs(unsafe) > p->initiator_threshold) ? init + safe + unsafe : init + safe;
+    default: return safe;
+    }
+}
+static inline int64_t from_initiator_i(const orc_step_params *p, int64_t safe, int64_t unsafe, int64_t init) {
+    switch (p ? p->initiator_rule : 0) {
+    case 1: return safe + init + (init != 0 ? 1 : 0) * unsafe;
+    case 2: return safe + init;
+    case 3: return (init != 0 || fabs((double)unsafe) > p->initiator_threshold) ? init + safe + unsafe : init + safe;
+    default: return safe;
+    }
+}
 
 typedef struct {
     int64_t exact_steps, inexact_steps, spawn_attempts, len_before, len_after;
@@ -580,17 +619,17 @@ static inline double sgn(double x) { return (x > 0) - (x < 0); }
 /* projected_deposit! (spawning.jl:9-45): returns deposited value (as double; exact for ints
  * below 2^53) */
 static double projected_deposit(orc_sink *w, int is_int, const uint64_t *key, double val,
-                                double threshold, double r) {
+                                double threshold, double r, int lane) {
     if (is_int) {
         int64_t nv = (int64_t)sgn(val) * (int64_t)floor(fabs(val) + r);
-        if (nv != 0) { orc_val v; v.i = nv; sink_add(w, key, v); }
+        if (nv != 0) { orc_val v; v.i = nv; sink_add(w, key, v, lane); }
         return (double)nv;
     }
     double a = fabs(val);
     if (a < threshold) {
         if (r < a / threshold) val = sgn(val) * threshold; else val = 0.0;
     }
-    if (val != 0.0) { orc_val v; v.f = val; sink_add(w, key, v); }
+    if (val != 0.0) { orc_val v; v.f = val; sink_add(w, key, v, lane); }
     return val;
 }
 
@@ -615,7 +654,7 @@ static void apply_column(const orc_ham *h, const orc_step_params *p, orc_sink *w
     double hd = orc_diagonal_onr(h, &o);
     double d = p->plain_h ? hd : 1 - p->dtau * (hd - p->shift);
     rng_draw(hsh, 0, STREAM_DIAG, p->key, rnd);
-    double res = projected_deposit(w, is_int, key, d * val, is_int ? 0.0 : p->proj_threshold, u53(rnd[1], rnd[2]));
+    double res = projected_deposit(w, is_int, key, d * val, is_int ? 0.0 : p->proj_threshold, u53(rnd[1], rnd[2]), deposit_lane(p, 1, val));
     double cl, de, zo; clones_deaths_zombies(res, val, &cl, &de, &zo);
     if (is_int) { st->iclones += (int64_t)cl; st->ideaths += (int64_t)de; st->izombies += (int64_t)zo; }
     else { st->clones += cl; st->deaths += de; st->zombies += zo; }
@@ -639,7 +678,7 @@ static void apply_column(const orc_ham *h, const orc_step_params *p, orc_sink *w
             double r = 0.0;
             if (p->proj_threshold > 0) { rng_draw(hsh, (uint64_t)(i - 1), STREAM_SPAWN, p->key, rnd); r = u53(rnd[1], rnd[2]); }
             orc_pack(h, &child, ckey);
-            spawns += fabs(projected_deposit(w, 0, ckey, val * m, p->proj_threshold, r));
+            spawns += fabs(projected_deposit(w, 0, ckey, val * m, p->proj_threshold, r, deposit_lane(p, 0, val)));
         }
         st->exact_steps += 1; st->spawn_attempts += L;
     } else { /* spawn!(WithReplacement) spawning.jl:232-243 + random_offdiagonal hamiltonians.jl:361-370 */
@@ -653,7 +692,7 @@ static void apply_column(const orc_ham *h, const orc_step_params *p, orc_sink *w
             if (!p->plain_h) m = -m * p->dtau;
             double nv = m * magnitude / prob;
             orc_pack(h, &child, ckey);
-            spawns += fabs(projected_deposit(w, is_int, ckey, nv, is_int ? 0.0 : p->proj_threshold, u53(rnd[1], rnd[2])));
+            spawns += fabs(projected_deposit(w, is_int, ckey, nv, is_int ? 0.0 : p->proj_threshold, u53(rnd[1], rnd[2]), deposit_lane(p, 0, val)));
         }
         st->inexact_steps += 1; st->spawn_attempts += n;
     }
@@ -677,8 +716,13 @@ static long map_collect(const orc_mapv *w, const orc_step_params *p, orc_rec *re
     for (size_t s = 0; s < w->cap; s++) {
         if (!w->used[s]) continue;
         orc_val v = w->vals[s];
-        if (is_int ? v.i == 0 : v.f == 0.0) continue; /* exact zeros are deleted, pdworkingmemory.jl:25-29 */
+        /* entries whose InitiatorValue is entirely zero are deleted on deposit (pdworkingmemory.jl:25-29); the others
+         * are counted by len_before and converted with from_initiator_value (pdworkingmemory.jl:268-270) */
+        if (is_int ? (v.i == 0 && w->vals_u[s].i == 0 && w->vals_i[s].i == 0) : (v.f == 0.0 && w->vals_u[s].f == 0.0 && w->vals_i[s].f == 0.0)) continue;
         len_before++;
+        if (is_int) v.i = from_initiator_i(p, v.i, w->vals_u[s].i, w->vals_i[s].i);
+        else v.f = from_initiator_f(p, v.f, w->vals_u[s].f, w->vals_i[s].f);
+        if (is_int ? v.i == 0 : v.f == 0.0) continue; /* setindex! of a zero deletes */
         if (!is_int && p && p->compress_threshold > 0) {
             double prob = fabs(v.f) / p->compress_threshold;
             if (prob < 1) {
@@ -785,7 +829,11 @@ long orc_step_threaded(const orc_ham *h, const orc_step_params *p, long n, const
         for (int c = 1; c < T; c++) {
             orc_mapv *src = &grid[c * T + r];
             for (size_t s = 0; s < src->cap; s++)
-                if (src->used[s]) mapv_add(&grid[r], src->keys + s * W, src->vals[s]);
+                if (src->used[s]) {
+                    mapv_add_lane(&grid[r], src->keys + s * W, src->vals[s], LANE_SAFE);
+                    mapv_add_lane(&grid[r], src->keys + s * W, src->vals_u[s], LANE_UNSAFE);
+                    mapv_add_lane(&grid[r], src->keys + s * W, src->vals_i[s], LANE_INIT);
+                }
         }
         rows[r] = (orc_rec *)malloc(sizeof(orc_rec) * (grid[r].count + 1));
         rown[r] = map_collect(&grid[r], p, rows[r], &cst[r]);

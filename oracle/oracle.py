@@ -60,7 +60,13 @@ class StepParams(C.Structure):
         ("proj_threshold", C.c_double), ("rel_threshold", C.c_double), ("abs_threshold", C.c_double),
         ("compress_threshold", C.c_double),
         ("key", C.c_uint32 * 2),
+        ("initiator_rule", C.c_int32), ("pad_", C.c_int32),
+        ("initiator_threshold", C.c_double),
     ]
+
+
+# InitiatorRule ids (DictVectors/initiators.jl:132-236)
+NON_INITIATOR, INITIATOR, SIMPLE_INITIATOR, COHERENT_INITIATOR = 0, 1, 2, 3
 
 
 class StepStats(C.Structure):
@@ -329,13 +335,15 @@ class OracleHam:
 
 
 def make_params(style, shift=0.0, dtau=0.01, boost=1.0, plain_h=False, proj_threshold=0.0,
-                rel_threshold=1.0, abs_threshold=math.inf, compress_threshold=0.0, key=(0, 0)) -> StepParams:
+                rel_threshold=1.0, abs_threshold=math.inf, compress_threshold=0.0, key=(0, 0),
+                initiator_rule=0, initiator_threshold=1.0) -> StepParams:
     p = StepParams()
     p.style, p.plain_h = style, int(plain_h)
     p.shift, p.dtau, p.boost = shift, dtau, boost
     p.proj_threshold, p.rel_threshold, p.abs_threshold = proj_threshold, rel_threshold, abs_threshold
     p.compress_threshold = compress_threshold
     p.key[0], p.key[1] = key
+    p.initiator_rule, p.initiator_threshold = int(initiator_rule), float(initiator_threshold)
     return p
 
 

@@ -393,3 +393,65 @@ def test_philox_known_answer():
     assert orc.philox((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
     assert orc.philox((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+# --------------------------------------------------------------------------- initiator rules
+def test_initiator_rules_hand_computed():
+    """to_initiator_value / from_initiator_value (DictVectors/initiators.jl:132-236) on a two-site Bose-Hubbard
+    model where every number can be done by hand: H = HubbardReal1D(BoseFS(1,1); u=1, t=1), operator = H, threshold 1.
+    Off-diagonals: (1,1) -> (0,2) twice and (2,0) twice with -sqrt(2) each (periodic, M=2); (2,0) -> (1,1) twice with -sqrt(2);
+    diagonal: H(2,0)(2,0) = 1, H(1,1)(1,1) = 0."""
+    oh = orc.OracleHam("HubbardReal1D", "bose", (1, 1), u=1.0, t=1.0)
+    k11, k20, k02 = (oh.pack((1, 1))[0], oh.pack((2, 0))[0], oh.pack((0, 2))[0])
+    r2 = math.sqrt(2.0)
+
+    def run(rule, vec):
+        p = orc.make_params(orc.STYLE_DETERMINISTIC, plain_h=True, initiator_rule=rule, initiator_threshold=1.0)
+        keys = np.array([k for k, _ in vec], dtype=np.uint64)
+        vals = np.array([v for _, v in vec], dtype=np.float64)
+        ko, vo, st = oh.step(p, keys, vals)
+        return {int(k): float(v) for k, v in zip(ko.ravel(), vo)}, st
+
+    # case 1: (1,1) => 2 is an initiator, (2,0) => 0.5 is not.
+    #   (0,2): safe -4 sqrt2;  (2,0): safe -4 sqrt2 + 0.5 (diagonal of a non-initiator is safe);  (1,1): unsafe -sqrt2 only
+    vec = [(k11, 2.0), (k20, 0.5)]
+    base = {k02: 2 * (-r2 * 2.0), k20: 2 * (-r2 * 2.0) + 0.5}
+    for rule, extra in ((orc.NON_INITIATOR, {k11: 2 * (-r2 * 0.5)}), (orc.INITIATOR, {}), (orc.SIMPLE_INITIATOR, {}),
+                        (orc.COHERENT_INITIATOR, {k11: 2 * (-r2 * 0.5)})):  # |unsafe| = 1.41 > threshold: coherent spawns count
+        got, st = run(rule, vec)
+        want = {**base, **extra}
+        assert got.keys() == want.keys(), (rule, got)
+        for k in want:
+            assert math.isclose(got[k], want[k], rel_tol=1e-15), (rule, k, got[k], want[k])
+        assert st.len_before == 3  # the all-unsafe entry is still an entry before from_initiator_value
+
+    # case 2: (2,0) => 3 is an initiator (diagonal deposit 3 goes to the initiator lane), (1,1) => 0.5 is not.
+    #   (2,0): initiator 3, unsafe -sqrt2;  (0,2): unsafe -sqrt2 only;  (1,1): safe -6 sqrt2
+    vec = [(k20, 3.0), (k11, 0.5)]
+    unsafe = 2 * (-r2 * 0.5)
+    for rule, want in ((orc.NON_INITIATOR, {k20: 3.0 + unsafe, k02: unsafe, k11: 2 * (-r2 * 3.0)}),
+                       (orc.INITIATOR, {k20: 3.0 + unsafe, k11: 2 * (-r2 * 3.0)}),          # unsafe counts where an initiator lives
+                       (orc.SIMPLE_INITIATOR, {k20: 3.0, k11: 2 * (-r2 * 3.0)}),           # non-initiators never spawn
+                       (orc.COHERENT_INITIATOR, {k20: 3.0 + unsafe, k02: unsafe, k11: 2 * (-r2 * 3.0)})):  # |unsafe| = 1.41 > 1
+        got, st = run(rule, vec)
+        assert got.keys() == want.keys(), (rule, got)
+        for k in want:
+            assert math.isclose(got[k], want[k], rel_tol=1e-15), (rule, k, got[k], want[k])
+
+
+def test_initiator_rule_zero_is_the_plain_step():
+    """NonInitiator must reproduce the rule-free step bit for bit (integer walkers, several steps)."""
+    oh = orc.OracleHam("HubbardReal1D", "bose", (1, 1, 1, 1, 1, 1), u=6.0, t=1.0)
+    k, v = np.array([oh.start_key], dtype=np.uint64), np.array([50], dtype=np.int64)
+    k2, v2 = k.copy(), v.copy()
+    for step in range(4):
+        key = orc.step_key(3, step)
+        k, v, s1 = oh.step(orc.make_params(orc.STYLE_INTEGER, shift=1.0, dtau=0.02, key=key), k, v)
+        k2, v2, s2 = oh.step(orc.make_params(orc.STYLE_INTEGER, shift=1.0, dtau=0.02, key=key, initiator_rule=0), k2, v2)
+        assert np.array_equal(k, k2) and np.array_equal(v, v2)
+    # and with a rule the population is never larger (spawns from non-initiators onto empty sites are dropped)
+    k3, v3 = np.array([oh.start_key], dtype=np.uint64), np.array([50], dtype=np.int64)
+    for step in range(4):
+        k3, v3, s3 = oh.step(orc.make_params(orc.STYLE_INTEGER, shift=1.0, dtau=0.02, key=orc.step_key(3, step),
+                                             initiator_rule=orc.INITIATOR, initiator_threshold=1.0), k3, v3)
+    assert len(v3) <= len(v)
