@@ -109,7 +109,16 @@ typedef struct {
     uint64_t seed;            /* Philox key material: per-step key = f(seed, step) */
     uint64_t step;
     uint64_t table_slots;     /* working-table slots to use this step (power of two, <= ctx capacity); 0 = auto */
+    /* InitiatorRule of the target vector (DictVectors/initiators.jl:132-236; PDVec(...; initiator=...) pdvec.jl:156-163):
+     * deposits are kept in (safe, unsafe, initiator) lanes during annihilation -- a diagonal deposit of an initiator
+     * (|parent value| > threshold) is "initiator", its spawns are "safe", spawns of non-initiators are "unsafe" -- and
+     * converted back with from_initiator_value before compression.  Partitioned method only. */
+    int32_t initiator_rule;   /* RIMU_INITIATOR_* ; 0 = NonInitiator */
+    int32_t reserved_;
+    double initiator_threshold;
 } rimu_step_params;
+
+enum { RIMU_INITIATOR_NONE = 0, RIMU_INITIATOR = 1, RIMU_INITIATOR_SIMPLE = 2, RIMU_INITIATOR_COHERENT = 3 };
 
 /* step_stats of the styles (styles.jl:14-20,94-96,203-209; compression.jl:16) plus
  * walkernumber_and_length of the result (pdvec.jl:896-902).  Integer-style quantities are

@@ -16,8 +16,9 @@ from .hamiltonians import (AbstractHamiltonian, Context, CubicGrid, HardwallBoun
                            starting_address)
 from .stochasticstyles import (IsDeterministic, IsDynamicSemistochastic, IsStochasticInteger,
                                IsStochasticWithThreshold, NoCompression, StochasticStyle, ThresholdCompression,
-                               default_style, step_stats)
-from .dictvectors import (DVec, FirstOrderTransitionOperator, GPUDVec, PDVec, WorkingMemory, apply_operator, dot, mul,
+                               default_style, step_stats,
+                               CoherentInitiator, Initiator, InitiatorRule, NonInitiator, SimpleInitiator)
+from .dictvectors import (DVec, FirstOrderTransitionOperator, GPUDVec, InitiatorDVec, PDVec, WorkingMemory, apply_operator, dot, mul,
                           walkernumber_and_length, working_memory)
 from .fciqmc import (DataFrame, DontUpdate, DoubleLogUpdate, DoubleLogUpdateAfterTargetWalkers, LogUpdate,
                      PMCSimulation, ProjectedEnergy, Projector, ProjectorMonteCarloProblem, ShiftParameters,

@@ -347,12 +347,15 @@ extern "C" int rimu_comm_allreduce_f64(rimu_ctx *c, double *buf, int n);
 // Size the record streams for nb buckets.  shared = the step streams of a multi-GPU context in direct mode: every rank
 // calls this with the same nb (it is derived from all-reduced quantities), so (re)allocation and the exchange of the
 // CUDA IPC handles are collective.  Otherwise: private streams with one sub-stream per bucket.
-static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool shared) {
+static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool shared, u32 nlane = 1, bool keep_lanes = false) {
     const u32 capi = part_cap_items(c->W);
-    const u32 nsrc = shared ? (u32)c->nranks : 1u;
+    if (keep_lanes && pt.rec && pt.nlane > nlane) nlane = pt.nlane; // local operations reuse a 3-lane layout (lane 0 only)
+    const u32 nranks = shared ? (u32)c->nranks : 1u;
+    const u32 nsrc = nranks * nlane;
     u32 rcap = capi;
-    if (nsrc > 1) { rcap = 2 * capi / nsrc; if (rcap < 128) rcap = 128; }
-    pt.nsrc = nsrc; pt.me = shared ? (u32)c->rank : 0u; pt.rcap = rcap; pt.direct = shared ? 1 : 0;
+    if (nranks > 1) { rcap = 2 * capi / nranks; if (rcap < 128) rcap = 128; }
+    if (pt.nlane != nlane && pt.rec) nb_cap = 0; // the sub-stream layout changes: reallocate (collective in shared mode)
+    pt.nsrc = nsrc; pt.nlane = nlane; pt.me = shared ? (u32)c->rank * nlane : 0u; pt.rcap = rcap; pt.direct = shared ? 1 : 0;
     if (nb <= nb_cap) { pt.nb = nb; return 0; }
     const u64 cap = (u64)nb + nb / 4 + 16;
     const size_t rw = c->W == 1 ? 2 : 4;
@@ -368,18 +371,18 @@ static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool 
     CUDA_TRY(rimu_malloc(&pt.rcnt, (size_t)nsrc * cap * sizeof(u32)));
     CUDA_TRY(cudaMemsetAsync(pt.rcnt, 0, (size_t)nsrc * cap * sizeof(u32), c->stream));
     if (shared) {
-        CUDA_TRY(rimu_malloc(&pt.scnt, (size_t)c->nranks * cap * sizeof(u32)));
-        CUDA_TRY(rimu_malloc(&pt.srec, (size_t)c->nranks * cap * rcap * rw * sizeof(u64)));
+        CUDA_TRY(rimu_malloc(&pt.scnt, (size_t)nsrc * cap * sizeof(u32)));
+        CUDA_TRY(rimu_malloc(&pt.srec, (size_t)nsrc * cap * rcap * rw * sizeof(u64)));
     }
     nb_cap = cap; pt.nb = nb;
     if (shared) TRY(p2p_setup(c));
     return 0;
 }
-static int ensure_part(rimu_ctx *c, u32 nb) { return ensure_part_impl(c, c->part, c->part_nb_cap, nb, c->nranks > 1 && c->direct); }
+static int ensure_part(rimu_ctx *c, u32 nb, u32 nlane = 1) { return ensure_part_impl(c, c->part, c->part_nb_cap, nb, c->nranks > 1 && c->direct, nlane); }
 // streams for local record->vector operations
 static PartDev &local_part(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? c->lpart : c->part; }
 static u64 &local_part_cap(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? c->lpart_nb_cap : c->part_nb_cap; }
-static int ensure_local_part(rimu_ctx *c, u32 nb) { return ensure_part_impl(c, local_part(c), local_part_cap(c), nb, false); }
+static int ensure_local_part(rimu_ctx *c, u32 nb) { return ensure_part_impl(c, local_part(c), local_part_cap(c), nb, false, 1, true); }
 static int ensure_heavy(rimu_ctx *c, u64 parents) {
     if (!c->heavy.packed) CUDA_TRY(rimu_malloc(&c->heavy.packed, sizeof(u64)));
     if (parents <= c->heavy.cap) return 0;
@@ -899,7 +902,7 @@ static int records_to_vec_part(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, co
         PartDev &lp = local_part(c);
         TRY(ensure_seg(dst, nb));
         CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-        CUDA_TRY(cudaMemsetAsync(lp.rcnt, 0, nb * sizeof(u32), c->stream));
+        CUDA_TRY(cudaMemsetAsync(lp.rcnt, 0, (size_t)lp.nsrc * nb * sizeof(u32), c->stream));
         TRY(dispatch_wv(c->W, dst->vt, [&](auto tag, auto vtag) {
             typedef decltype(vtag) VT;
             constexpr int W = decltype(tag)::w;
@@ -1180,7 +1183,7 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool t
         // as coalesced runs straight into the owners' bucket sub-streams (peer stores over NVLink) together with the
         // sub-stream fills.  The all-gather of the per-destination totals is the barrier that orders all of this
         // before anybody's merge.  No receive pass, no host round trip.
-        const u64 nruns = (u64)(R - 1) * c->part.nb; // one warp per (destination, bucket) run
+        const u64 nruns = (u64)(R - 1) * c->part.nb * c->part.nlane; // one warp per (destination, lane, bucket) run
         u64 gx = (nruns + (RIMU_TPB / 32) - 1) / (RIMU_TPB / 32);
         if (gx > (u64)c->sm_count * 8) gx = (u64)c->sm_count * 8;
         if (gx < 1) gx = 1;
@@ -1337,16 +1340,18 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     TRY(ensure_seg(dst, nb));
     TRY(ensure_diag(dst));
     const double *src_diag = (src->diag_uid == h->uid && src->diag) ? src->diag : nullptr;
-    TRY(ensure_part(c, nb));
+    const u32 nlane = p.init_rule ? 3u : 1u;
+    TRY(ensure_part(c, nb, nlane));
     TRY(ensure_heavy(c, (u64)n));
+    const size_t smem_init = (size_t)part_cap_items(W) * 8; // unsafe lane of the initiator rules
     static bool attr_set[HK_COUNT][3][2] = {};
     if (!attr_set[HK][W][std::is_integral<VT>::value]) {
-        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
+        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(part_smem_bytes(W) + smem_init)));
         attr_set[HK][W][std::is_integral<VT>::value] = true;
     }
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->part.rcnt + (size_t)c->part.me * nb, 0, nb * sizeof(u32), c->stream)); // own sub-stream fills
-    if (c->part.direct) CUDA_TRY(cudaMemsetAsync(c->part.scnt, 0, (size_t)c->nranks * nb * sizeof(u32), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->part.rcnt + (size_t)c->part.me * nb, 0, (size_t)nlane * nb * sizeof(u32), c->stream)); // own sub-stream fills
+    if (c->part.direct) CUDA_TRY(cudaMemsetAsync(c->part.scnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream));
     CUDA_TRY(cudaMemsetAsync(c->heavy.packed, 0, sizeof(u64), c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
@@ -1375,7 +1380,7 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr, src_diag};
     SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, dst->diag};
     const int mgrid = (int)(nb < c->merge_grid_cap ? nb : c->merge_grid_cap);
-    merge_kernel<HK, W, VT, 0><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
+    merge_kernel<HK, W, VT, 0><<<mgrid, PART_NT, part_smem_bytes(W) + (p.init_rule ? smem_init : 0), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
@@ -1417,6 +1422,13 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
     rimu_step_key(prm->seed, prm->step, key);
     p.k0 = key[0]; p.k1 = key[1];
     p.rank = c->rank; p.nranks = c->nranks;
+    p.init_rule = prm->initiator_rule; p.init_thr = prm->initiator_threshold;
+    if (p.init_rule < 0 || p.init_rule > 3) return fail(RIMU_ERR_INVALID, "unknown initiator rule %d", p.init_rule);
+    if (p.init_rule && prm->plain_h == 0 && !(p.init_thr >= 0.0)) return fail(RIMU_ERR_INVALID, "initiator threshold must be >= 0");
+    if (p.init_rule && c->method != RIMU_ANNIHILATE_PARTITION)
+        return fail(RIMU_ERR_INVALID, "initiator rules need the partitioned method (the table method has no value lanes)");
+    if (p.init_rule && c->nranks > 1 && !c->direct)
+        return fail(RIMU_ERR_INVALID, "initiator rules on several GPUs need the direct exchange (peer access); the staged NCCL exchange carries no lanes");
 
     bool use_part = c->method == RIMU_ANNIHILATE_PARTITION;
     u64 slots = prm->table_slots ? next_pow2(prm->table_slots) : pick_slots(c, (u64)src->n * 2 + (u64)dst->n);
@@ -1440,7 +1452,10 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         if (use_part && nb > c->part_nb_cap && !multi) { // (multi-GPU: a per-rank fallback would desynchronise the ranks)
             CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
             double have = (double)free_b + (double)c->part_nb_cap * rec_bytes_per_bucket;
-            if ((double)nb * 1.3 * rec_bytes_per_bucket > 0.8 * have) use_part = false;
+            if ((double)nb * 1.3 * rec_bytes_per_bucket * (p.init_rule ? 3.0 : 1.0) > 0.8 * have) {
+                if (p.init_rule) return fail(RIMU_ERR_TABLE_FULL, "record streams of an initiator step do not fit in device memory");
+                use_part = false;
+            }
         }
         if (multi && !(use_part && c->direct)) TRY(ensure_xch(c)); // staged exchange buffers (table method / no peer access)
         int r = dispatch_ham(h, [&](auto tag) {
@@ -1486,7 +1501,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
                 const double recs = multi ? (double)g.records / c->nranks * 1.02 : (double)l.records; // g.records: summed over ranks
                 double need = ceil((parents + recs) * 1.15 / (0.6 * cap)); // (diagonal records may be counted twice: harmless)
                 u32 nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb * 2 + 1);
-                if (!multi && (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26))) use_part = false; // one address is too hot to pre-sum: use the table
+                if (!multi && !p.init_rule && (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26))) use_part = false; // one address is too hot to pre-sum: use the table
                 if (multi && nb2 > (1u << 26)) return fail(RIMU_ERR_TABLE_FULL, "bucket streams cannot be grown further");
                 nb = nb2;
                 continue;

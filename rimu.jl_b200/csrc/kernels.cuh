@@ -34,6 +34,8 @@ struct StepDev {
     double shift, dtau, boost, proj_thr, rel_thr, abs_thr, compress_thr;
     u32 k0, k1;
     int rank, nranks;
+    int init_rule;      // RIMU_INITIATOR_*: 0 = no initiator lanes
+    double init_thr;
 };
 
 struct StatsDev {

@@ -51,8 +51,10 @@ template <int W> struct PartCap { static constexpr int value = PART_CAP; };
 struct PartDev {       // bucket record streams (working memory of the partitioned step)
     u32 nb;            // buckets per rank (identical on all ranks of a step)
     u32 rcap;          // records per (bucket, source rank) sub-stream
-    u32 nsrc;          // sub-streams per bucket: 1, or the number of ranks in direct (peer-store) mode
-    u32 me;            // this rank's sub-stream (0 when nsrc == 1)
+    u32 nsrc;          // sub-streams per bucket = source ranks (1, or all ranks in direct mode) x lanes
+    u32 nlane;         // 1, or 3 with an initiator rule: sub-stream (rank, lane) holds the rank's safe / unsafe / initiator
+                       //   deposits (DictVectors/initiators.jl:22-45) -- the lane travels in the stream index, not in the record
+    u32 me;            // this rank's first sub-stream (rank * nlane; 0 when there is one source)
     u64 *rec;          // [nb][nsrc][rcap] records, array of structures: W=1 {key, value} (16 B), W=2 {k0, k1, value, pad} (32 B)
     u32 *rcnt;         // [nsrc][nb] fill of every sub-stream; slot `me` is counted locally, the others are pushed by their senders
     // direct mode (multi-GPU, CUDA IPC peer memory): a spawned record is stored straight into sub-stream [bucket][this rank] of
@@ -127,7 +129,7 @@ DEV void append_record(const PartDev &pt, StatsDev *st, typename BitsT<W>::type 
 struct RouteSmem { u32 cnt[RIMU_MAX_RANKS]; u64 base[RIMU_MAX_RANKS]; };
 template <int W, class VT>
 DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p, StatsDev *st, RouteSmem &rs,
-                      bool has, typename BitsT<W>::type key, VT v) {
+                      bool has, typename BitsT<W>::type key, VT v, u32 lane) {
     u64 h = 0;
     int owner = p.rank;
     if (has) {
@@ -137,10 +139,11 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
     if (p.nranks > 1 && pt.direct) { // uniform over the grid
         if (has && owner != p.rank) {
             const u32 b = bucket_of(h, p.nranks, pt.nb);
-            const u32 pos = atomicAdd(&pt.scnt[(u64)owner * pt.nb + b], 1u);
+            const u64 sub = (u64)owner * pt.nlane + lane; // staging sub-stream (destination rank, lane)
+            const u32 pos = atomicAdd(&pt.scnt[sub * pt.nb + b], 1u);
             if (pos < pt.rcap) {
                 union { VT v; u64 b; } cv; cv.v = v;
-                store_rec<W>(pt.srec + (((u64)owner * pt.nb + b) * pt.rcap + pos) * RecWords<W>::value, key, cv.b);
+                store_rec<W>(pt.srec + ((sub * pt.nb + b) * pt.rcap + pos) * RecWords<W>::value, key, cv.b);
             } else st->overflow_table = 1;
         }
     } else if (p.nranks > 1) {
@@ -162,7 +165,7 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
             } else st->overflow_xchg = 1;
         }
     }
-    if (has && owner == p.rank) append_record<W, VT>(pt, st, key, h, p.nranks, v, pt.me);
+    if (has && owner == p.rank) append_record<W, VT>(pt, st, key, h, p.nranks, v, pt.me + lane);
 }
 
 // direct mode: after the spawn kernels, ship to every peer d the records staged for each of its buckets -- one warp per
@@ -172,19 +175,22 @@ template <int RW>
 __global__ void __launch_bounds__(RIMU_TPB) push_records_kernel(PartDev pt, int me, int R, u64 *__restrict__ totals) {
     const int lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
-    const u64 nruns = (u64)(R - 1) * pt.nb;
+    const u64 nruns = (u64)(R - 1) * pt.nb * pt.nlane;
     // consecutive warps serve different destinations, and rank `me` starts its rotation at me+1: at any moment every
     // rank is sending to every peer, so no receiver sees an incast while the others idle
     for (u64 r = warp; r < nruns; r += nwarps) {
         const int d = (me + 1 + (int)(r % (u64)(R - 1))) % R;
-        const u32 b = (u32)(r / (u64)(R - 1));
-        const u32 c0 = pt.scnt[(u64)d * pt.nb + b], c = c0 < pt.rcap ? c0 : pt.rcap;
+        const u64 r2 = r / (u64)(R - 1);
+        const u32 lane_ = (u32)(r2 % pt.nlane), b = (u32)(r2 / pt.nlane);
+        const u64 sub = (u64)d * pt.nlane + lane_;            // staging sub-stream here
+        const u64 dsub = (u64)me * pt.nlane + lane_;           // sub-stream (this rank, lane) at the destination
+        const u32 c0 = pt.scnt[sub * pt.nb + b], c = c0 < pt.rcap ? c0 : pt.rcap;
         if (lane == 0) {
-            pt.peer_rcnt[d][(u64)me * pt.nb + b] = c;
+            pt.peer_rcnt[d][dsub * pt.nb + b] = c;
             if (c0) atomicAdd(&totals[d], (u64)c0);
         }
-        const ulonglong2 *from = reinterpret_cast<const ulonglong2 *>(pt.srec + (((u64)d * pt.nb + b) * pt.rcap) * RW);
-        ulonglong2 *to = reinterpret_cast<ulonglong2 *>(pt.peer_rec[d] + (((u64)b * pt.nsrc + me) * pt.rcap) * RW);
+        const ulonglong2 *from = reinterpret_cast<const ulonglong2 *>(pt.srec + ((sub * pt.nb + b) * pt.rcap) * RW);
+        ulonglong2 *to = reinterpret_cast<ulonglong2 *>(pt.peer_rec[d] + (((u64)b * pt.nsrc + dsub) * pt.rcap) * RW);
         const u32 units = c * (RW / 2);
         u32 i = lane;
         for (; i + 96 < units; i += 128) { // four 16-byte loads in flight per lane
@@ -193,6 +199,17 @@ __global__ void __launch_bounds__(RIMU_TPB) push_records_kernel(PartDev pt, int 
         }
         for (; i < units; i += 32) to[i] = from[i];
     }
+}
+
+// lane of a deposit (to_initiator_value, DictVectors/initiators.jl:142-158): diagonal deposits of an initiator
+// (|parent value| > threshold) are "initiator" (2), of anybody else "safe" (0); spawns of an initiator are "safe",
+// of a non-initiator "unsafe" (1).  Without a rule everything is lane 0.
+enum { LANE_SAFE = 0, LANE_UNSAFE = 1, LANE_INIT = 2 };
+DEV u32 deposit_lane(const StepDev &p, bool diagonal, double parent_val) {
+    if (p.init_rule == 0) return LANE_SAFE;
+    const bool is_initiator = fabs(parent_val) > p.init_thr;
+    if (diagonal) return is_initiator ? LANE_INIT : LANE_SAFE;
+    return is_initiator ? LANE_SAFE : LANE_UNSAFE;
 }
 
 // one spawn attempt k of a parent (spawning.jl:174-182 Exact, :232-243 WithReplacement).
@@ -291,6 +308,7 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
             const u32 a = a0 + tid;
             B child = 0;
             VT nv = (VT)0;
+            u32 rlane = 0;
             if (a < total) {
                 int lo = 0, hi = SPAWN_NT; // last lo with s_off[lo] <= a
 #pragma unroll
@@ -306,8 +324,9 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
                 long long ci; double sp;
                 nv = spawn_attempt<HK, W, VT>(h, p, key, hash_bits(key), val, L, nat, exact, k, child, ci, sp);
                 spawns += sp;
+                rlane = deposit_lane(p, false, val);
             }
-            route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv);
+            route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv, rlane);
         }
         __syncthreads();
     }
@@ -341,6 +360,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
         const bool exact = it.exact != 0;
         const bool agg = !exact && L <= ACC_MAX;
         const u64 hkey = hash_bits(key);
+        const u32 rlane = deposit_lane(p, false, val); // one parent per tile: one lane
         if (agg) { for (int c = threadIdx.x; c < L; c += SPAWN_NT) acc[c] = 0ull; __syncthreads(); }
         for (u64 ab = a0; ab < a1; ab += SPAWN_NT) {
             const u64 a = ab + threadIdx.x;
@@ -352,7 +372,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
                 spawns += sp;
                 if (agg && nv != (VT)0) { atomic_add_val<VT>(&acc[ci], nv); nv = (VT)0; }
             }
-            if (!agg) route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv);
+            if (!agg) route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv, rlane);
         }
         if (agg) {
             __syncthreads();
@@ -361,7 +381,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
                 B child = 0;
                 union { u64 b; VT v; } cv; cv.b = 0;
                 if (c < L) { cv.b = acc[c]; if (cv.v != (VT)0) ham_offdiagonal<HK, B>(h, key, c, child); }
-                route_record<W, VT>(pt, xch, p, st, s_route, cv.v != (VT)0, child, cv.v);
+                route_record<W, VT>(pt, xch, p, st, s_route, cv.v != (VT)0, child, cv.v, rlane);
             }
             __syncthreads();
         }
@@ -416,7 +436,7 @@ diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
         if (rs > val) clones += fabs(rs - val);
         else if (sgn_(rs) != sgn_(val)) { deaths += fabs(val); zombies += fabs(rs); }
         else deaths += fabs(rs - val);
-        if (v != (VT)0) append_record<W, VT>(pt, st, key, hk, p.nranks, v, pt.me);
+        if (v != (VT)0) append_record<W, VT>(pt, st, key, hk, p.nranks, v, pt.me + deposit_lane(p, true, val));
     }
     if (is_int) { stat_add(&st->iclones, (i64)clones); stat_add(&st->ideaths, (i64)deaths); stat_add(&st->izombies, (i64)zombies); }
     else { stat_add(&st->clones, clones); stat_add(&st->deaths, deaths); stat_add(&st->zombies, zombies); }
@@ -439,12 +459,17 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     constexpr int R = CAP / PART_NT;
     constexpr u32 TMASK = 2 * CAP - 1;
     constexpr u32 NIL = 0xffffffffu;
-    constexpr u32 NOPARENT = 0xffffu;
+    constexpr u32 NOPARENT = 0x7fffu, IFLAG = 0x8000u; // pidx: parent item index | "initiator lane is non-zero" flag
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);
     u64 *svals = skeys + CAP * W;
     u32 *owner = reinterpret_cast<u32 *>(svals + CAP);
     unsigned short *pidx = reinterpret_cast<unsigned short *>(owner + 2 * CAP);
+    // initiator rule (MODE 0 only): svals accumulates safe + initiator, sunsafe the unsafe lane (CAP more u64 of shared
+    // memory, allocated by the host only for such steps); whether the initiator lane is non-zero is one bit, because
+    // only an address's own parent can deposit there
+    const bool initm = MODE == 0 && p.init_rule != 0;
+    u64 *sunsafe = reinterpret_cast<u64 *>(pidx + CAP);
     __shared__ u32 s_warp[PART_NT / 32];
     __shared__ u64 s_base;
     __shared__ u32 s_nlist, s_clist;
@@ -522,6 +547,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             slot[r] = 0;
             if (i >= n) continue;
             B key; VT v;
+            u32 ilane = LANE_SAFE;
             if (i < np) {
                 key = load_key<W>(src.keys + (p0 + i) * W);
                 union { u64 b; VT v; } cv; cv.b = src.vals[p0 + i];
@@ -539,6 +565,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                         rr = u53(rnd[1], rnd[2]);
                     }
                     v = project_value<VT>(d * val, thr, rr);
+                    ilane = deposit_lane(p, true, val);
                     const double rs = (double)v; // clones_deaths_zombies (spawning.jl:79-93)
                     if (rs > val) clones += fabs(rs - val);
                     else if (sgn_(rs) != sgn_(val)) { deaths += fabs(val); zombies += fabs(rs); }
@@ -552,12 +579,20 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 union { u64 b; VT v; } cv;
                 load_rec<W>(pt.rec + ((((u64)b * nsrc + q) * pt.rcap) + j) * RW, key, cv.b);
                 v = cv.v;
+                if (pt.nlane > 1) ilane = q % pt.nlane;
             }
-            pidx[i] = (unsigned short)NOPARENT;
+            u32 pflag = NOPARENT;
+            if (initm && v != (VT)0) {
+                if (ilane == LANE_INIT) pflag |= IFLAG;
+                union { u64 b; VT v; } cz; cz.v = (VT)0; sunsafe[i] = cz.b;
+            }
+            pidx[i] = (unsigned short)pflag;
             if (v != (VT)0) {
                 skeys[i * W] = (u64)key;
                 if constexpr (W == 2) skeys[i * W + 1] = (u64)(key >> 64);
-                union { u64 b; VT v; } cv; cv.v = v; svals[i] = cv.b;
+                union { u64 b; VT v; } cv; cv.v = v;
+                if (initm && ilane == LANE_UNSAFE) { sunsafe[i] = cv.b; cv.v = (VT)0; }
+                svals[i] = cv.b;
                 slot[r] = (u32)hash_bits(key) & TMASK;
                 valid |= 1u << r;
                 ndep++;
@@ -584,14 +619,40 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 if constexpr (W == 2) eq = eq && skeys[o * W + 1] == k1;
                 if (eq) {
                     union { u64 b; VT v; } cv; cv.b = svals[i];
-                    atomic_add_val<VT>(&svals[o], cv.v);
-                    if constexpr (MODE == 0) { if (i < np) pidx[o] = (unsigned short)i; } // its cached H_aa follows the address
+                    if (cv.v != (VT)0) atomic_add_val<VT>(&svals[o], cv.v);
+                    if (initm) {
+                        union { u64 b; VT v; } cu; cu.b = sunsafe[i];
+                        if (cu.v != (VT)0) atomic_add_val<VT>(&sunsafe[o], cu.v);
+                    }
+                    if constexpr (MODE == 0) {
+                        // the parent's cached H_aa (and its initiator flag) follow the address; an initiator-lane RECORD
+                        // (unsegmented source) only carries the flag.  One writer per address in either case.
+                        if (i < np) pidx[o] = (unsigned short)(i | (pidx[i] & IFLAG));
+                        else if (initm && (pidx[i] & IFLAG)) pidx[o] = (unsigned short)(pidx[o] | IFLAG);
+                    }
                     break;
                 }
                 s = (s + 1) & TMASK;
             }
         }
         __syncthreads();
+        // ---- from_initiator_value (initiators.jl:136-138,177-179,201-207; pdworkingmemory.jl:268-270): collapse the lanes
+        if (initm) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r >= rmax) break;
+                if (!((own >> r) & 1u)) continue;
+                const u32 i = tid + r * PART_NT;
+                union { u64 b; VT v; } ca, cu; ca.b = svals[i]; cu.b = sunsafe[i];
+                const bool fi = (pidx[i] & IFLAG) != 0;
+                if (ca.v == (VT)0 && cu.v == (VT)0 && !fi) continue; // all lanes zero: no entry
+                len_before++;
+                VT out = ca.v;
+                if (p.init_rule == 1) { if (fi) out = ca.v + cu.v; }
+                else if (p.init_rule == 3) { if (fi || fabs((double)cu.v) > p.init_thr) out = ca.v + cu.v; }
+                ca.v = out; svals[i] = ca.b;
+            }
+        }
         // ---- ThresholdCompression (compression.jl:18-26) as a dense pass: the owners whose |value| is below the
         // threshold are gathered into a list (the owner table is dead after placement) so that the Philox draw runs
         // over full warps instead of once per round for the few lanes that need it
@@ -604,7 +665,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                     bool need = false;
                     if ((own >> r) & 1u) {
                         union { u64 b; double v; } cv; cv.b = svals[i];
-                        if (cv.v != 0.0) { len_before++; need = fabs(cv.v) < p.compress_thr; }
+                        if (cv.v != 0.0) { if (!initm) len_before++; need = fabs(cv.v) < p.compress_thr; }
                     }
                     const u32 bal = __ballot_sync(0xffffffffu, need);
                     if (bal) {
@@ -644,7 +705,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             keep |= 1u << r; cnt++;
             if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v); else norm1 += fabs((double)v);
         }
-        if (!compressed) len_before += cnt;
+        if (!compressed && !initm) len_before += cnt;
         // ---- CTA scan of survivor counts, one cursor atomic per bucket, write the new segment
         u32 incl = cnt;
 #pragma unroll
@@ -676,7 +737,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 dst.vals[at] = svals[i];
                 if constexpr (MODE == 0) {
                     // H_aa of the survivor: cached with its parent, or (new determinant) evaluated below
-                    const u32 pi = i < np ? i : (u32)pidx[i];
+                    const u32 pi = i < np ? i : ((u32)pidx[i] & NOPARENT);
                     if (src.diag && pi != NOPARENT) dst.diag[at] = src.diag[p0 + pi];
                     else owner[atomicAdd(&s_nlist, 1u)] = (i << 16) | rel; // owner table is dead: reuse as the list
                 }

@@ -19,7 +19,7 @@ from . import _lib
 from .addresses import AddressType
 from .hamiltonians import AbstractHamiltonian, Context, get_context
 from .stochasticstyles import (IsDeterministic, IsStochasticInteger, StochasticStyle, ThresholdCompression,
-                               default_style, step_stats)
+                               as_initiator_rule, default_style, step_stats)
 
 
 class FirstOrderTransitionOperator:
@@ -33,7 +33,7 @@ class GPUDVec:
     """Dictionary-semantics vector (missing -> 0, zeros never stored) living on the GPU."""
 
     def __init__(self, pairs=None, *, style: StochasticStyle | None = None, address_type: AddressType | None = None,
-                 capacity: int = 1 << 12, ctx: Context | None = None):
+                 capacity: int = 1 << 12, ctx: Context | None = None, initiator=None, initiator_threshold=None):
         items = list(pairs.items()) if isinstance(pairs, dict) else list(pairs or [])
         if address_type is None:
             if not items:
@@ -42,6 +42,7 @@ class GPUDVec:
         if style is None:
             style = default_style(int if items and all(isinstance(v, (int, np.integer)) for _, v in items) else float)
         self.style, self.address_type = style, address_type
+        self.initiator = as_initiator_rule(initiator, initiator_threshold)  # PDVec(...; initiator=...) pdvec.jl:181-199
         self.ctx = ctx or get_context(address_type.words)
         h = C.c_void_p()
         _lib.check(_lib.lib().rimu_vec_create(self.ctx.handle, style.val_type, max(capacity, len(items)), C.byref(h)))
@@ -74,7 +75,8 @@ class GPUDVec:
         return n.value
 
     def similar(self, style=None):
-        return GPUDVec(style=style or self.style, address_type=self.address_type, capacity=max(len(self), 256), ctx=self.ctx)
+        return GPUDVec(style=style or self.style, address_type=self.address_type, capacity=max(len(self), 256), ctx=self.ctx,
+                       initiator=self.initiator)
 
     zerovector = similar
     empty = similar
@@ -202,12 +204,19 @@ DVec = GPUDVec
 PDVec = GPUDVec
 
 
+def InitiatorDVec(pairs=None, *, initiator=None, **kw):
+    """InitiatorDVec(pairs...; initiator=Initiator(1), style, ...) (DictVectors/initiatordvec.jl:42-77)."""
+    from .stochasticstyles import Initiator
+    return GPUDVec(pairs, initiator=Initiator(1.0) if initiator is None else initiator, **kw)
+
+
 class WorkingMemory:
     """working_memory(v) (Interfaces/dictvectors.jl:87, pdworkingmemory.jl:295): the context's
     HBM working table plus the Philox stream position (seed, call counter)."""
 
     def __init__(self, v: GPUDVec, seed: int = 0):
         self.ctx, self.style, self.seed, self.counter = v.ctx, v.style, int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+        self.initiator = v.initiator  # PDWorkingMemory(t).initiator = t.initiator (pdworkingmemory.jl:104-108)
         self.last_stats: _lib.StepStats | None = None
 
 
@@ -236,6 +245,9 @@ def apply_operator(wm: WorkingMemory, target: GPUDVec, source: GPUDVec, op, boos
         raise TypeError("operator must be one of the device Hamiltonians or a FirstOrderTransitionOperator "
                         "(custom Julia/Python operators cannot run on the GPU; there is no CPU fallback)")
     p.boost, p.seed, p.step, p.table_slots = float(boost), wm.seed, wm.counter, int(table_slots)
+    rule = getattr(wm, "initiator", None)
+    if rule is not None and rule.rule_id:
+        p.initiator_rule, p.initiator_threshold = rule.rule_id, float(rule.threshold)
     stats = _lib.StepStats()
     ctx = wm.ctx
     while True:

@@ -134,12 +134,12 @@ class Timer:
 
 
 # --------------------------------------------------------------------------- problem / simulation
-def default_starting_vector(ham_or_address, population=10, style=None):
-    """qmc_states.jl:236-260: `address => population` with the given style."""
+def default_starting_vector(ham_or_address, population=10, style=None, initiator=None):
+    """qmc_states.jl:236-260: `address => population` with the given style (and initiator rule)."""
     address = starting_address(ham_or_address) if isinstance(ham_or_address, AbstractHamiltonian) else ham_or_address
     style = IsDynamicSemistochastic() if style is None else style
     val = int(population) if style.val_type == _lib.VAL_I64 else float(population)
-    return GPUDVec([(address, val)], style=style)
+    return GPUDVec([(address, val)], style=style, initiator=initiator)
 
 
 @dataclass
@@ -161,8 +161,9 @@ class ProjectorMonteCarloProblem:
                  n_replicas=1, initiator=False):
         if n_replicas != 1:
             raise NotImplementedError("replicas are outside the device path (SURVEY.md section 8e)")
-        if initiator:
-            raise NotImplementedError("initiator rules are a NEXT row of the scope table (SURVEY.md section 8f)")
+        # initiator=true -> Initiator(threshold 1) (projector_monte_carlo_problem.jl:156-160); a rule object is taken as is
+        from .stochasticstyles import as_initiator_rule
+        self.initiator = as_initiator_rule(initiator)
         self.hamiltonian = hamiltonian
         self.style = IsDynamicSemistochastic() if style is None else style
         self.start_at = start_at
@@ -189,13 +190,13 @@ class PMCSimulation:
         ham = p.hamiltonian
         sa = p.start_at
         if sa is None:
-            v = default_starting_vector(ham, style=p.style)
+            v = default_starting_vector(ham, style=p.style, initiator=p.initiator)
         elif isinstance(sa, GPUDVec):
-            v = sa.copy()
+            v = sa.copy()  # a vector brings its own style and initiator rule
         elif isinstance(sa, (list, tuple, dict)):
-            v = GPUDVec(sa, style=p.style)
+            v = GPUDVec(sa, style=p.style, initiator=p.initiator)
         else:  # an address
-            v = default_starting_vector(sa, style=p.style)
+            v = default_starting_vector(sa, style=p.style, initiator=p.initiator)
         style = v.style
         if p.shift is None:  # Rayleigh quotient of the starting vector (fciqmc.jl:51-61)
             vf = v if style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)

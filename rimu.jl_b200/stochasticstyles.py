@@ -117,3 +117,48 @@ def step_stats(style):
     if isinstance(getattr(style, "compression", None), ThresholdCompression):
         names = names + ("len_before",)
     return names
+
+
+# --------------------------------------------------------------------------- initiator rules
+# Host mirror of DictVectors/initiators.jl:132-236.  A rule only carries its id and threshold; the lane arithmetic
+# (to_initiator_value / from_initiator_value) runs in the CUDA kernels (partition.cuh).
+@dataclass(frozen=True)
+class InitiatorRule:
+    threshold: float = 1.0
+    rule_id = 0
+
+
+@dataclass(frozen=True)
+class NonInitiator(InitiatorRule):
+    """Disables the approximation (the default of PDVec)."""
+    rule_id = 0
+
+
+@dataclass(frozen=True)
+class Initiator(InitiatorRule):
+    """Initiators (|value| > threshold) spawn anywhere; non-initiators spawn only onto initiators' addresses."""
+    rule_id = 1
+
+
+@dataclass(frozen=True)
+class SimpleInitiator(InitiatorRule):
+    """Initiators spawn anywhere; non-initiators cannot spawn."""
+    rule_id = 2
+
+
+@dataclass(frozen=True)
+class CoherentInitiator(InitiatorRule):
+    """As Initiator, plus: non-initiator spawns onto one address count if together they exceed the threshold."""
+    rule_id = 3
+
+
+def as_initiator_rule(initiator=None, initiator_threshold=None) -> InitiatorRule:
+    """PDVec / InitiatorDVec keyword handling (pdvec.jl:181-199): `initiator=true` or a positive
+    `initiator_threshold` selects Initiator(threshold); a rule object is taken as is."""
+    if isinstance(initiator, InitiatorRule):
+        return initiator
+    if initiator_threshold is not None and initiator_threshold > 0:
+        return Initiator(float(initiator_threshold))
+    if initiator is True:
+        return Initiator(1.0)
+    return NonInitiator()

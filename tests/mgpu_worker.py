@@ -19,7 +19,11 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     method = os.environ.get("RIMU_B200_METHOD", "partition")
-    for name, style_name in (("real1d_10", "int"), ("rs_bose_3d_w2", "int"), ("mom1d_bose", "semi"), ("rs_f2c_4x4", "int")):
+    direct = os.environ.get("RIMU_B200_P2P", "1") != "0"
+    cases = [("real1d_10", "int", 0), ("rs_bose_3d_w2", "int", 0), ("mom1d_bose", "semi", 0), ("rs_f2c_4x4", "int", 0)]
+    if method == "partition" and direct:  # initiator lanes travel in the sub-stream index of the direct exchange
+        cases += [("real1d_10", "int", 1), ("mom1d_bose", "semi", 3)]
+    for name, style_name, irule in cases:
         oh = oracle_ham(name)
         R.reset_contexts()
         ctx = R.init_distributed(oh.W, records_per_peer=1 << 12)  # small on purpose: exercises the grow-and-repeat path
@@ -29,7 +33,8 @@ def main():
             style, pop, dtype, ostyle, kw = R.IsStochasticInteger(), 20000, np.int64, orc.STYLE_INTEGER, {}
         else:
             style, pop, dtype, ostyle, kw = R.IsDynamicSemistochastic(), 5000.5, np.float64, orc.STYLE_SEMISTOCHASTIC, dict(compress_threshold=1.0)
-        v = R.GPUDVec([(ph.address, pop)], style=style)  # only the owner rank keeps the entry
+        rule = {0: None, 1: R.Initiator(1.0), 2: R.SimpleInitiator(1.0), 3: R.CoherentInitiator(1.0)}[irule]
+        v = R.GPUDVec([(ph.address, pop)], style=style, initiator=rule)  # only the owner rank keeps the entry
         wm = R.working_memory(v, seed=seed)
         ok, ov = np.array([oh.start_key], dtype=np.uint64), np.array([pop], dtype=dtype)
         shift = oh.diagonal_element(oh.start_key)
@@ -39,7 +44,8 @@ def main():
             R.apply_operator(wm, out, v, T)
             v = out
             s = wm.last_stats
-            pp = orc.make_params(ostyle, shift=shift, dtau=dtau, key=orc.step_key(seed, step), **kw)
+            pp = orc.make_params(ostyle, shift=shift, dtau=dtau, key=orc.step_key(seed, step), initiator_rule=irule,
+                                 initiator_threshold=1.0, **kw)
             ok, ov, st = oh.step(pp, ok, ov)
             lk, lv = v.download()
             parts = [None] * world
@@ -69,7 +75,7 @@ def main():
             import ctypes as C
             p2p = C.c_int()
             R._lib.check(R._lib.lib().rimu_comm_p2p(ctx.handle, C.byref(p2p)))
-            print(f"mgpu ok: {name} {style_name} method={method} world={world} len={len(ov)} sent={s.sent_records} p2p={p2p.value}", flush=True)
+            print(f"mgpu ok: {name} {style_name} initiator={irule} method={method} world={world} len={len(ov)} sent={s.sent_records} p2p={p2p.value}", flush=True)
     dist.barrier()
     # leave without running destructors in arbitrary order against the peers' teardown (NCCL communicators, IPC
     # mappings): every assertion has been evaluated by now
