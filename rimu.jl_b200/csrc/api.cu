@@ -1346,7 +1346,8 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     const size_t smem_init = (size_t)part_cap_items(W) * 8; // unsafe lane of the initiator rules
     static bool attr_set[HK_COUNT][3][2] = {};
     if (!attr_set[HK][W][std::is_integral<VT>::value]) {
-        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(part_smem_bytes(W) + smem_init)));
+        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
+        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(part_smem_bytes(W) + smem_init)));
         attr_set[HK][W][std::is_integral<VT>::value] = true;
     }
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
@@ -1380,7 +1381,8 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr, src_diag};
     SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, dst->diag};
     const int mgrid = (int)(nb < c->merge_grid_cap ? nb : c->merge_grid_cap);
-    merge_kernel<HK, W, VT, 0><<<mgrid, PART_NT, part_smem_bytes(W) + (p.init_rule ? smem_init : 0), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
+    if (p.init_rule) merge_kernel<HK, W, VT, 0, true><<<mgrid, PART_NT, part_smem_bytes(W) + smem_init, c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
+    else merge_kernel<HK, W, VT, 0, false><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;
     CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));

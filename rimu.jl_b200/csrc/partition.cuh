@@ -450,7 +450,7 @@ diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
 // Placement is one pass: an item claims the first free slot of its probe sequence with a 32-bit shared CAS on
 // the owner table; keys are compared through the item index, so nothing has to be published after a claim.
 // After placement the owner table is dead and is reused as the list of survivors that still need H_aa.
-template <int HK, int W, class VT, int MODE>
+template <int HK, int W, class VT, int MODE, bool INIT = false>
 __global__ void __launch_bounds__(PART_NT, PART_MINB)
 merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st) {
     typedef typename BitsT<W>::type B;
@@ -468,30 +468,34 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     // initiator rule (MODE 0 only): svals accumulates safe + initiator, sunsafe the unsafe lane (CAP more u64 of shared
     // memory, allocated by the host only for such steps); whether the initiator lane is non-zero is one bit, because
     // only an address's own parent can deposit there
-    const bool initm = MODE == 0 && p.init_rule != 0;
+    constexpr bool initm = MODE == 0 && INIT; // separate instantiation: the plain step pays nothing for the lanes
     u64 *sunsafe = reinterpret_cast<u64 *>(pidx + CAP);
     __shared__ u32 s_warp[PART_NT / 32];
     __shared__ u64 s_base;
     __shared__ u32 s_nlist, s_clist;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double norm1 = 0.0, clones = 0.0, deaths = 0.0, zombies = 0.0;
-    i64 inorm1 = 0, len_before = 0, len = 0, ndep = 0;
+    i64 inorm1 = 0;
+    u32 len_before = 0, len = 0, ndep = 0; // per-thread counts (32 bits are plenty; registers are the scarce resource here)
     u32 max_fill = 0;
-    u64 nrec_sum = 0;
+    u32 nrec_sum = 0;
     // Bucket metadata (segment of parents, fill of every source's sub-stream) runs two buckets ahead of the merge, and
     // the next bucket's parents and records are pulled into L2 with bulk prefetches while this one is merged, so that
     // staging sees L2 latency instead of two dependent HBM round trips (metadata, then data).
     constexpr int RW = RecWords<W>::value;
-    __shared__ u32 s_cnt[3][RIMU_MAX_RANKS]; // ring: sub-stream fills of this bucket, the next, the one after
+    constexpr int MAXSUB = RIMU_MAX_RANKS * 3;  // sub-streams per bucket: ranks x lanes
+    __shared__ u32 s_cnt[3][MAXSUB];            // ring: sub-stream fills of this bucket, the next, the one after
+    __shared__ u32 s_np[3];                     // ... and the parents' segment (length, start)
+    __shared__ u64 s_p0[3];
     const u32 nsrc = pt.nsrc;
-    u32 m_np[2] = {0, 0};
-    u64 m_p0[2] = {0, 0};
+    const bool meta_thread = tid == PART_NT - 1; // loads the segment metadata; threads 0..nsrc-1 load the fills
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         const u64 bq = (u64)blockIdx.x + (u64)q * gridDim.x;
-        if (bq < pt.nb) {
-            m_np[q] = src.seg_len ? src.seg_len[bq] : 0u;
-            m_p0[q] = m_np[q] ? src.seg_start[bq] : 0ull;
+        if (meta_thread) {
+            const u32 npq = (bq < pt.nb && src.seg_len) ? src.seg_len[bq] : 0u;
+            s_np[q] = npq;
+            s_p0[q] = npq ? src.seg_start[bq] : 0ull;
         }
         if ((u32)tid < nsrc) s_cnt[q][tid] = bq < pt.nb ? pt.rcnt[(u64)tid * pt.nb + bq] : 0u;
     }
@@ -499,16 +503,18 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     u32 ring = 0;
     for (u32 b = blockIdx.x; b < pt.nb; b += gridDim.x, ring = ring == 2 ? 0 : ring + 1) {
         const u32 cur = ring, nxt = ring == 2 ? 0 : ring + 1, nn = nxt == 2 ? 0 : nxt + 1;
-        const u32 np = m_np[0];
-        const u64 p0 = m_p0[0];
-        m_np[0] = m_np[1]; m_p0[0] = m_p0[1];
-        u32 pending_cnt = 0; // fill of sub-stream `tid` two buckets ahead; stored to the ring at the end of this iteration
+        const u32 np = s_np[cur];
+        const u64 p0 = s_p0[cur];
+        // metadata two buckets ahead: loaded now, stored to the ring at the end of this iteration (its latency is hidden)
+        u32 pending_cnt = 0, pending_np = 0;
+        u64 pending_p0 = 0;
         {
             const u64 b2 = (u64)b + 2ull * gridDim.x;
-            m_np[1] = 0; m_p0[1] = 0;
             if (b2 < pt.nb) {
-                m_np[1] = src.seg_len ? src.seg_len[b2] : 0u;
-                m_p0[1] = m_np[1] ? src.seg_start[b2] : 0ull;
+                if (meta_thread) {
+                    pending_np = src.seg_len ? src.seg_len[b2] : 0u;
+                    pending_p0 = pending_np ? src.seg_start[b2] : 0ull;
+                }
                 if ((u32)tid < nsrc) pending_cnt = pt.rcnt[(u64)tid * pt.nb + b2];
             }
             const u64 b1 = (u64)b + gridDim.x;
@@ -516,10 +522,13 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 if ((u32)tid < nsrc) {
                     const u32 c1 = s_cnt[nxt][tid] < pt.rcap ? s_cnt[nxt][tid] : pt.rcap;
                     if (c1) l2_prefetch(pt.rec + ((b1 * nsrc + tid) * pt.rcap) * RW, (u64)c1 * RW * 8);
-                } else if (tid == 32 && m_np[0]) {
-                    l2_prefetch(src.keys + m_p0[0] * W, (u64)m_np[0] * W * 8);
-                    l2_prefetch(src.vals + m_p0[0], (u64)m_np[0] * 8);
-                    if (src.diag) l2_prefetch(src.diag + m_p0[0], (u64)m_np[0] * 8);
+                }
+                if (meta_thread && s_np[nxt]) {
+                    const u32 np1 = s_np[nxt];
+                    const u64 p1 = s_p0[nxt];
+                    l2_prefetch(src.keys + p1 * W, (u64)np1 * W * 8);
+                    l2_prefetch(src.vals + p1, (u64)np1 * 8);
+                    if (src.diag) l2_prefetch(src.diag + p1, (u64)np1 * 8);
                 }
             }
         }
@@ -532,6 +541,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         if (sub_over || n > (u32)CAP) { // uniform over the CTA: the host retries with more buckets
             if (tid == 0) { st->overflow_table = 1; dst.seg_len[b] = 0; dst.seg_start[b] = 0; }
             if ((u32)tid < nsrc) s_cnt[nn][tid] = pending_cnt;
+            if (meta_thread) { s_np[nn] = pending_np; s_p0[nn] = pending_p0; }
             __syncthreads();
             continue;
         }
@@ -746,6 +756,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         }
         len += cnt;
         if ((u32)tid < nsrc) s_cnt[nn][tid] = pending_cnt; // (loaded at the top of this iteration: its latency is long gone)
+        if (meta_thread) { s_np[nn] = pending_np; s_p0[nn] = pending_p0; }
         __syncthreads();
         if constexpr (MODE == 0) {
             // dense evaluation of H_aa for the gathered survivors (a per-lane evaluation inside the output loop
@@ -760,9 +771,9 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             __syncthreads(); // shared memory is reused by the next bucket
         }
     }
-    stat_add(&st->len_before, len_before);
-    stat_add(&st->len, len);
-    stat_add(&st->deposits, ndep);
+    stat_add(&st->len_before, (i64)len_before);
+    stat_add(&st->len, (i64)len);
+    stat_add(&st->deposits, (i64)ndep);
     if (is_int) {
         stat_add(&st->inorm1, inorm1);
         if (MODE == 0) { stat_add(&st->iclones, (i64)clones); stat_add(&st->ideaths, (i64)deaths); stat_add(&st->izombies, (i64)zombies); }
@@ -773,7 +784,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) max_fill = max(max_fill, __shfl_xor_sync(0xffffffffu, max_fill, o));
     if (lane == 0) atomicMax(&st->max_fill, (unsigned long long)max_fill);
-    if (tid == 0 && nrec_sum) atomicAdd(&st->records, nrec_sum);
+    if (tid == 0 && nrec_sum) atomicAdd(&st->records, (u64)nrec_sum);
 }
 
 // ---------------------------------------------------------------- re-segmentation of a vector for a new bucket count
