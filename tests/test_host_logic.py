@@ -134,3 +134,30 @@ def test_problem_defaults(built):
     assert isinstance(p.style, R.IsDynamicSemistochastic)
     with pytest.raises(NotImplementedError):
         R.ProjectorMonteCarloProblem(FakeHam(), n_replicas=2)
+
+
+def test_initiator_rule_keywords(built):
+    """PDVec / InitiatorDVec / ProjectorMonteCarloProblem keyword handling for initiator rules
+    (pdvec.jl:181-199, initiatordvec.jl:42-77, projector_monte_carlo_problem.jl:156-160) and the StepParams the
+    step receives -- host logic only, no device call."""
+    import ctypes as C
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+    from rimu_b200.stochasticstyles import as_initiator_rule
+    assert as_initiator_rule(None) == R.NonInitiator() and as_initiator_rule(False) == R.NonInitiator()
+    assert as_initiator_rule(True) == R.Initiator(1.0)
+    assert as_initiator_rule(None, 2.5) == R.Initiator(2.5)
+    assert as_initiator_rule(R.CoherentInitiator(3.0)) == R.CoherentInitiator(3.0)
+    assert [r.rule_id for r in (R.NonInitiator(), R.Initiator(), R.SimpleInitiator(), R.CoherentInitiator())] == [0, 1, 2, 3]
+    assert (_lib.lib().rimu_sizeof_step_params(), _lib.lib().rimu_sizeof_step_stats()) == (C.sizeof(_lib.StepParams), C.sizeof(_lib.StepStats))
+    names = [f for f, _ in _lib.StepParams._fields_]
+    assert names[-3:] == ["initiator_rule", "reserved_", "initiator_threshold"]
+
+    class FakeHam:
+        pass
+    assert R.ProjectorMonteCarloProblem(FakeHam()).initiator == R.NonInitiator()
+    assert R.ProjectorMonteCarloProblem(FakeHam(), initiator=True).initiator == R.Initiator(1.0)
+    assert R.ProjectorMonteCarloProblem(FakeHam(), initiator=R.SimpleInitiator(2.0)).initiator == R.SimpleInitiator(2.0)
+    # the oracle uses the same rule numbering
+    from oracle import oracle as orc
+    assert (orc.NON_INITIATOR, orc.INITIATOR, orc.SIMPLE_INITIATOR, orc.COHERENT_INITIATOR) == (0, 1, 2, 3)
