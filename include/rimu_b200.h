@@ -225,6 +225,10 @@ int rimu_vec_norm(rimu_vec *v, int p, double *out);
 int rimu_vec_scale(rimu_vec *v, double alpha);             /* scale!/lmul! (pdvec.jl:714-729) */
 /* dot(x, y) (pdvec.jl:760-796); also serves FrozenDVec dot for projected energy */
 int rimu_vec_dot(rimu_vec *x, rimu_vec *y, double *out);
+/* dot(::FrozenDVec, v) (pdvec.jl:773-779; freeze projectors.jl:164): n host-side (key, value) pairs against the device
+ * vector -- the projected-energy reports of every step (poststepstrategy.jl:110-121).  Each key is looked up in its own
+ * bucket segment only (a full scan when the vector is not segmented); global over ranks.  values are Float64. */
+int rimu_vec_dot_sparse(rimu_vec *v, const uint64_t *keys, const double *values, int64_t n, double *out);
 /* out = alpha*x + beta*y (add!/axpy!/axpby!, pdvec.jl:731-758); out may alias x or y */
 int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *y, rimu_vec *out);
 

@@ -158,6 +158,7 @@ SYMBOLS = {
     "rimu_vec_norm": (C.c_int, [_vp, C.c_int, _f64p]),
     "rimu_vec_scale": (C.c_int, [_vp, C.c_double]),
     "rimu_vec_dot": (C.c_int, [_vp, _vp, _f64p]),
+    "rimu_vec_dot_sparse": (C.c_int, [_vp, _u64p, _f64p, C.c_int64, _f64p]),
     "rimu_vec_axpby": (C.c_int, [C.c_double, _vp, C.c_double, _vp, _vp]),
     "rimu_annihilate": (C.c_int, [_vp, _u64p, _vp, C.c_int64, C.c_int]),
     "rimu_annihilate_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),

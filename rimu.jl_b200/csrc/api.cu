@@ -1118,6 +1118,33 @@ extern "C" int rimu_vec_dot(rimu_vec *x, rimu_vec *y, double *out) {
     *out = r;
     return 0;
 }
+extern "C" int rimu_vec_dot_sparse(rimu_vec *v, const uint64_t *keys, const double *values, int64_t n, double *out) {
+    rimu_ctx *c = v->ctx;
+    if (!out || n < 0 || (n > 0 && (!keys || !values))) return fail(RIMU_ERR_INVALID, "dot_sparse: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double r = 0.0;
+    if (n > 0 && v->n > 0) {
+        TRY(ensure_stage(c, (u64)n));
+        CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->stage_vals, values, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemsetAsync(&c->d_stats->dot, 0, sizeof(double), c->stream));
+        const int grid = (int)(n < (i64)c->sm_count * 8 ? n : (i64)c->sm_count * 8);
+        TRY(dispatch_wv(c->W, v->vt, [&](auto tag, auto vtag) {
+            typedef decltype(vtag) VT;
+            dot_sparse_kernel<decltype(tag)::w, VT><<<grid, RIMU_TPB, 0, c->stream>>>(
+                c->stage_keys, (const double *)c->stage_vals, n, v->keys, (const VT *)v->vals, v->n,
+                v->nb ? v->seg_start : nullptr, v->nb ? v->seg_len : nullptr, v->nb, c->rank, c->nranks, &c->d_stats->dot);
+            return 0;
+        }));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&c->h_stats->dot, &c->d_stats->dot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        r = c->h_stats->dot;
+    }
+    if (c->nranks > 1) TRY(rimu_comm_allreduce_f64(c, &r, 1)); // collective even when this rank holds nothing
+    *out = r;
+    return 0;
+}
 extern "C" int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *y, rimu_vec *out) {
     if (out) out->version++;
     rimu_ctx *c = out->ctx;

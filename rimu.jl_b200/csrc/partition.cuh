@@ -787,6 +787,26 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     if (tid == 0 && nrec_sum) atomicAdd(&st->records, (u64)nrec_sum);
 }
 
+// ---------------------------------------------------------------- dot(::FrozenDVec, v): few keys against a big vector
+// One CTA per query key: the key's bucket segment (<= a few thousand entries) is scanned, or the whole vector when it is not
+// segmented.  Keys owned by another rank contribute there.
+template <int W, class VT>
+__global__ void __launch_bounds__(RIMU_TPB)
+dot_sparse_kernel(const u64 *__restrict__ qkeys, const double *__restrict__ qvals, i64 nq, const u64 *__restrict__ keys,
+                  const VT *__restrict__ vals, i64 n, const u64 *__restrict__ seg_start, const u32 *__restrict__ seg_len, u32 nb,
+                  int rank, int nranks, double *__restrict__ out) {
+    typedef typename BitsT<W>::type B;
+    for (i64 q = blockIdx.x; q < nq; q += gridDim.x) {
+        const B key = load_key<W>(qkeys + q * W);
+        const u64 h = hash_bits(key);
+        if (nranks > 1 && addr_owner(h, nranks) != rank) continue;
+        i64 lo = 0, hi = n;
+        if (nb) { const u32 b = bucket_of(h, nranks, nb); lo = (i64)seg_start[b]; hi = lo + (i64)seg_len[b]; }
+        for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x)
+            if (load_key<W>(keys + i * W) == key) atomicAdd(out, qvals[q] * (double)vals[i]); // at most one match per key
+    }
+}
+
 // ---------------------------------------------------------------- re-segmentation of a vector for a new bucket count
 template <int W>
 __global__ void __launch_bounds__(RIMU_TPB)

@@ -167,6 +167,8 @@ class GPUDVec:
         return self.norm(1)
 
     def dot(self, other):
+        if isinstance(other, FrozenDVec):
+            return other.dot(self)
         out = C.c_double()
         self._with_table_retry(lambda: _lib.check(_lib.lib().rimu_vec_dot(self.handle, other.handle, C.byref(out))))
         return out.value
@@ -197,7 +199,30 @@ class GPUDVec:
         return self.copy().add_(other, -1.0)
 
     def freeze(self):
-        return self.copy()
+        """freeze(v) (projectors.jl:164): an immutable list of (address, value) pairs on the HOST; its dot with a device
+        vector looks every address up in its bucket segment (rimu_vec_dot_sparse) instead of building a hash table."""
+        keys, vals = self.download()
+        return FrozenDVec(keys, np.asarray(vals, dtype=np.float64), self.address_type, self.ctx)
+
+
+class FrozenDVec:
+    """FrozenDVec (DictVectors/projectors.jl:141-176): used as the projector of ProjectedEnergy / Projector."""
+
+    def __init__(self, keys, vals, address_type, ctx=None):
+        self.address_type = address_type
+        self.keys = np.ascontiguousarray(np.asarray(keys, dtype=np.uint64).reshape(-1, address_type.words))
+        self.vals = np.ascontiguousarray(np.asarray(vals, dtype=np.float64))
+        self.ctx = ctx
+
+    def __len__(self):
+        return len(self.vals)
+
+    def dot(self, v: "GPUDVec") -> float:
+        """dot(::FrozenDVec, ::PDVec) (pdvec.jl:773-779); global over ranks."""
+        out = C.c_double()
+        _lib.check(_lib.lib().rimu_vec_dot_sparse(v.handle, self.keys.ctypes.data_as(_lib._u64p),
+                                                  self.vals.ctypes.data_as(_lib._f64p), len(self.vals), C.byref(out)))
+        return out.value
 
 
 DVec = GPUDVec
@@ -285,7 +310,7 @@ def mul(y: GPUDVec, op, x: GPUDVec, wm: WorkingMemory | None = None):
 def dot(x: GPUDVec, *args):
     """dot(x, y) or dot(x, op, y) (abstractdvec.jl:286-324, pdvec.jl:833-894)."""
     if len(args) == 1:
-        return x.dot(args[0])
+        return x.dot(args[0])  # either side may be a FrozenDVec
     op, y = args
     tmp = y.similar(style=IsDeterministic())
     yy = y if isinstance(y.style, IsDeterministic) else GPUDVec(style=IsDeterministic(), address_type=y.address_type, ctx=y.ctx).copy_from(y)

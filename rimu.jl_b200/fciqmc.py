@@ -96,36 +96,57 @@ class DoubleLogUpdateAfterTargetWalkers:
 
 
 # --------------------------------------------------------------------------- post-step strategies
+FREEZE_LIMIT = 1 << 16  # projectors up to this many entries are frozen (host pairs + per-key segment lookups)
+
+
+def _frozen_or_device(vec):
+    """(multi-GPU: every rank freezes its local part; both kinds of dot end in exactly one all-reduce, so ranks may differ)"""
+    return vec.freeze() if len(vec) <= FREEZE_LIMIT else vec
+
+
 class ProjectedEnergy:
     """poststepstrategy.jl:82-121: reports vproj = projector⋅v and hproj = (H' projector)⋅v, or
-    dot(projector, H, v) when the adjoint is unknown (Transcorrelated1D)."""
+    dot(projector, H, v) when the adjoint is unknown (Transcorrelated1D).  Both projectors are frozen
+    (`freeze`, projectors.jl:164), so a report costs a few bucket-segment lookups, not a pass over the vector."""
 
     def __init__(self, hamiltonian, projector: GPUDVec, vproj="vproj", hproj="hproj"):
         self.ham, self.vproj_name, self.hproj_name = hamiltonian, vproj, hproj
         det = IsDeterministic()
-        self.vproj = GPUDVec(style=det, address_type=projector.address_type, ctx=projector.ctx).copy_from(projector)
+        self._vdev = GPUDVec(style=det, address_type=projector.address_type, ctx=projector.ctx).copy_from(projector)
+        self.vproj = _frozen_or_device(self._vdev)
         if hamiltonian.hermitian:
-            self.hproj = mul(self.vproj.similar(), hamiltonian, self.vproj)  # H' = H
+            self.hproj = _frozen_or_device(mul(self._vdev.similar(), hamiltonian, self._vdev))  # H' = H
         else:
             self.hproj = None
 
     def __call__(self, state, step):
         v = state.v
-        vf = v if v.style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)
-        out = {self.vproj_name: self.vproj.dot(vf)}
-        out[self.hproj_name] = self.hproj.dot(vf) if self.hproj is not None else dot(self.vproj, self.ham, vf)
+        out = {self.vproj_name: _pdot(self.vproj, v)}
+        if self.hproj is not None:
+            out[self.hproj_name] = _pdot(self.hproj, v)
+        else:
+            vf = v if v.style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)
+            out[self.hproj_name] = dot(self._vdev, self.ham, vf)
         return out
+
+
+def _pdot(projector, v):
+    """projector ⋅ v for a frozen (any value type of v) or device-resident projector (Float64 against Float64)."""
+    from .dictvectors import FrozenDVec
+    if isinstance(projector, FrozenDVec):
+        return projector.dot(v)
+    vf = v if v.style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)
+    return projector.dot(vf)
 
 
 class Projector:
     def __init__(self, **kw):
         (self.name, proj), = kw.items()
-        self.projector = GPUDVec(style=IsDeterministic(), address_type=proj.address_type, ctx=proj.ctx).copy_from(proj)
+        dev = GPUDVec(style=IsDeterministic(), address_type=proj.address_type, ctx=proj.ctx).copy_from(proj)
+        self.projector = _frozen_or_device(dev)
 
     def __call__(self, state, step):
-        v = state.v
-        vf = v if v.style.val_type == _lib.VAL_F64 else GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v)
-        return {self.name: self.projector.dot(vf)}
+        return {self.name: _pdot(self.projector, state.v)}
 
 
 class Timer:

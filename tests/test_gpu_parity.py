@@ -365,3 +365,40 @@ def _aligned(kx, vx, kr, vr, W):
     """values of x on the keys of r (0 where absent), for a host-side dot product"""
     d = {tuple(int(t) for t in key): val for key, val in zip(kr, vr)}
     return vx, np.array([d.get(tuple(int(t) for t in key), 0.0) for key in kx])
+
+
+@pytest.mark.parametrize("name", ["mom1d_bose_20", "rs_bose_3d_w2"])
+def test_frozen_dot_matches_dense_dot(built, name):
+    """dot(::FrozenDVec, v) (pdvec.jl:773-779) through rimu_vec_dot_sparse: per-key lookups in the bucket segment of a
+    segmented vector, full scan of an unsegmented one; Float64 and Int64 vectors; keys that are absent contribute 0."""
+    import rimu_b200 as R
+    ph = product_ham(name)
+    x = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    wm = R.working_memory(x)
+    for _ in range(3 if name == "rs_bose_3d_w2" else 6):
+        y = x.similar()
+        R.mul(y, ph, x, wm)
+        y.scale_(1.0 / y.norm(np.inf))
+        x = y
+    assert len(x) > 2000
+    keys, vals = x.download_sorted()
+    rng = np.random.default_rng(3)
+    pick = np.sort(rng.choice(len(vals), size=500, replace=False))
+    fk = np.concatenate([keys.reshape(len(vals), -1)[pick], np.full((3, keys.reshape(len(vals), -1).shape[1]), 5, dtype=np.uint64)])  # + 3 absent keys
+    fv = np.concatenate([rng.uniform(-1, 1, 500), np.ones(3)])
+    fr = R.FrozenDVec(fk, fv, x.address_type)
+    ref = float(np.dot(fv[:500], vals[pick]))
+    assert math.isclose(fr.dot(x), ref, rel_tol=1e-12)          # segmented (result of a partitioned step)
+    assert math.isclose(x.dot(fr), ref, rel_tol=1e-12)
+    u = R.GPUDVec(style=R.IsDeterministic(), address_type=x.address_type)
+    u.assign(keys, vals)                                          # unsegmented
+    assert math.isclose(fr.dot(u), ref, rel_tol=1e-12)
+    iv = R.GPUDVec(style=R.IsStochasticInteger(), address_type=x.address_type)
+    ivals = np.round(vals * 1000).astype(np.int64)
+    nz = ivals != 0
+    iv.assign(keys.reshape(len(vals), -1)[nz], ivals[nz])
+    assert math.isclose(fr.dot(iv), float(np.dot(fv[:500], ivals[pick])), rel_tol=1e-12)
+    # freeze() of a device vector and the dense dot agree
+    small = R.GPUDVec(style=R.IsDeterministic(), address_type=x.address_type)
+    small.assign(fk[:500], fv[:500])
+    assert math.isclose(small.freeze().dot(x), small.dot(x), rel_tol=1e-12)
