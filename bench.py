@@ -87,6 +87,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------- steady-state detector
+class Settled:
+    """The population counts as equilibrated when, over the last `window` steps, the walker number stayed within 5 % of
+    the target AND drifted by less than 1.5 % of it AND the number of stored determinants changed by less than 3 %.
+    (Staying inside the band alone is not enough: the first passage through it, still growing, can last tens of steps.)"""
+
+    def __init__(self, target, window):
+        self.target, self.window, self.norms, self.lens = float(target), int(window), [], []
+
+    def update(self, norm, length):
+        self.norms.append(float(norm)); self.lens.append(float(length))
+        if len(self.norms) < self.window:
+            return False
+        n, l = self.norms[-self.window:], self.lens[-self.window:]
+        t = self.target
+        return (all(abs(x - t) < 0.05 * t for x in n) and abs(n[-1] - n[0]) < 0.015 * t
+                and abs(l[-1] - l[0]) < 0.03 * max(l[-1], 1.0))
+
+
 # --------------------------------------------------------------------------- reference arm (CPU)
 def reference_arm(args):
     """The reference (pure Julia) cannot run here: the CPU arm is the oracle port of Rimu's threaded
@@ -112,15 +131,14 @@ def reference_arm(args):
         return oh.step(p, keys, vals, threads=cores)
 
     # DoubleLogUpdate from the first step, as ProjectorMonteCarloProblem does by default
-    t_budget, settled = time.time(), 0
+    t_budget, settled = time.time(), Settled(target, args.equil)
     while True:
         keys, vals, st = one(step, shift)
         step += 1
         tnorm = st.norm1
         shift -= xi / DTAU * math.log(tnorm / target) + zeta / DTAU * math.log(tnorm / pnorm)
         pnorm = tnorm
-        settled = settled + 1 if abs(tnorm - target) < 0.05 * target else 0
-        if settled >= args.equil or step >= 1500 or time.time() - t_budget > 150:
+        if settled.update(tnorm, st.len_after) or step >= 1500 or time.time() - t_budget > 150:
             break
     for _ in range(args.warmup):
         keys, vals, st = one(step, shift)
@@ -193,12 +211,11 @@ def ours(args):
 
     # DoubleLogUpdate from the first step (the reference's default); stop once the population has
     # stayed within 5 % of the target for `equil` consecutive steps
-    t0, nsteps, settled = time.time(), 0, 0
+    t0, nsteps, settled = time.time(), 0, Settled(target, args.equil)
     while True:
         s = one_step()
         nsteps += 1
-        settled = settled + 1 if abs(s.norm1 - target) < 0.05 * target else 0
-        if settled >= args.equil or nsteps >= 3000 or time.time() - t0 > 240:
+        if settled.update(s.norm1, s.len) or nsteps >= 3000 or time.time() - t0 > 240:
             break
     for _ in range(args.warmup):
         s = one_step()

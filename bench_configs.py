@@ -77,13 +77,13 @@ def run_stochastic(R, cfg, args, world, rank, dist, torch, peak):
         strat.update(sp, float(s.inorm1) if is_int else s.norm1)
         return s
 
-    t0, nsteps, settled = time.time(), 0, 0
+    from bench import Settled
+    t0, nsteps, settled = time.time(), 0, Settled(target, args.equil)
     while True:
         s = one()
         nsteps += 1
         tn = float(s.inorm1) if is_int else s.norm1
-        settled = settled + 1 if abs(tn - target) < 0.05 * target else 0
-        if settled >= args.equil or nsteps >= args.max_growth or time.time() - t0 > args.growth_seconds:
+        if settled.update(tn, s.len) or nsteps >= args.max_growth or time.time() - t0 > args.growth_seconds:
             break
     for _ in range(3):
         one()
@@ -108,7 +108,7 @@ def run_stochastic(R, cfg, args, world, rank, dist, torch, peak):
     K = args.steps
     E = 8 * W + 8
     P, U = acc["P"] / K, acc["U"] / K
-    A1 = max(acc["dep"] / world - P, 0) / K
+    A1 = max(acc["dep"] / world - acc["P"], 0) / K  # non-zero spawn records per step and rank (deposits = parents' diagonal + records)
     step_bytes = (P * E + A1 * E) + (P * (E + 8) + A1 * E + U * (E + 8))
     tn = float(s.inorm1) if is_int else s.norm1
     return {"config": cfg["name"], "n_gpus": world, "walkers_per_gpu": per_gpu, "norm": tn, "determinants_per_gpu": P,
