@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -248,7 +248,6 @@ def ours(args):
     barrier()
     torch.cuda.profiler.stop()
     wall = time.time() - tw0
-    clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
     launches1 = C.c_uint64()
     _lib.check(_lib.lib().rimu_ctx_launch_count(ctx.handle, C.byref(launches1)))
@@ -336,6 +335,7 @@ def ours(args):
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clk = clocks.stop()  # sampled every 20 ms across BOTH timed regions (resident steps and host-buffer steps)
     e2e_attempts = sum(rep["attempts"] for rep in reps)
     h2d, d2h = sum(rep["h2d"] for rep in reps), sum(rep["d2h"] for rep in reps)
     e2e_total_steps = e2e_steps * nrep
