@@ -50,7 +50,11 @@ enum {
 };
 
 enum { RIMU_ADDR_BOSE = 0, RIMU_ADDR_FERMI = 1, RIMU_ADDR_FERMI2C = 2 };
-enum { RIMU_HUBBARD_REAL_1D = 0, RIMU_HUBBARD_MOM_1D = 1, RIMU_HUBBARD_REAL_SPACE = 2, RIMU_TRANSCORRELATED_1D = 3 };
+enum { RIMU_HUBBARD_REAL_1D = 0, RIMU_HUBBARD_MOM_1D = 1, RIMU_HUBBARD_REAL_SPACE = 2, RIMU_TRANSCORRELATED_1D = 3,
+       RIMU_HUBBARD_REAL_1D_EP = 4,        /* Hamiltonians/HubbardReal1DEP.jl:47-92: potential[] = eps_i, bosons */
+       RIMU_EXTENDED_HUBBARD_REAL_1D = 5   /* Hamiltonians/ExtendedHubbardReal1D.jl:30-135: v = neighbour interaction, bosons */ };
+/* ExtendedHubbardReal1D boundary_condition (real ones; a complex twist angle has no device path) */
+enum { RIMU_BC_PERIODIC = 0, RIMU_BC_HARD_WALL = 1, RIMU_BC_TWISTED = 2 };
 enum { RIMU_VAL_F64 = 0, RIMU_VAL_I64 = 1 };
 /* StochasticStyles/styles.jl: IsDeterministic (:76-105), IsStochasticInteger (:11-25),
  * IsDynamicSemistochastic (:175-214), IsStochasticWithThreshold (:117-130) */
@@ -84,7 +88,7 @@ typedef struct {
     int32_t cutoff;         /* Transcorrelated1D */
     int32_t three_body_term;
     int32_t has_potential;  /* potential[] valid (HubbardRealSpace trap) */
-    int32_t reserved;
+    int32_t boundary_condition; /* RIMU_BC_* (ExtendedHubbardReal1D only) */
     double u, t, v;         /* 1-D models: u,t ; Transcorrelated1D: t,v */
     double t_comp[2];       /* HubbardRealSpace hopping per component */
     double u_mat[4];        /* HubbardRealSpace interactions, column major u[i + 2*j] */

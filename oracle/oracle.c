@@ -41,7 +41,9 @@
 
 enum { ORC_BOSE = 0, ORC_FERMI = 1, ORC_FERMI2C = 2 };
 enum { ORC_HUBBARD_REAL_1D = 0, ORC_HUBBARD_MOM_1D = 1, ORC_HUBBARD_REAL_SPACE = 2,
-       ORC_TRANSCORRELATED_1D = 3 };
+       ORC_TRANSCORRELATED_1D = 3, ORC_HUBBARD_REAL_1D_EP = 4, ORC_EXTENDED_HUBBARD_REAL_1D = 5 };
+/* ExtendedHubbardReal1D boundary_condition (ExtendedHubbardReal1D.jl:12-22), stored in orc_ham.fold[0] */
+enum { ORC_BC_PERIODIC = 0, ORC_BC_HARD_WALL = 1, ORC_BC_TWISTED = 2 };
 enum { ORC_STYLE_DETERMINISTIC = 0, ORC_STYLE_INTEGER = 1, ORC_STYLE_SEMISTOCHASTIC = 2,
        ORC_STYLE_WITH_THRESHOLD = 3 };
 
@@ -218,6 +220,31 @@ double orc_diagonal_onr(const orc_ham *h, const orc_onr *o) {
     switch (h->model) {
     case ORC_HUBBARD_REAL_1D: /* HubbardReal1D.jl:55-57 */
         return h->u * (double)bose_interaction(o->n[0], M) / 2;
+    case ORC_HUBBARD_REAL_1D_EP: { /* HubbardReal1DEP.jl:82-87: sum over occupied modes of u n (n-1) / 2 + ep[mode] n */
+        double s = 0.0; int first = 1;
+        for (int m = 0; m < M; m++) {
+            int n = o->n[0][m];
+            if (!n) continue;
+            double term = h->u * n * (n - 1) / 2 + h->pot[m] * n;
+            s = first ? term : s + term; first = 0;
+        }
+        return s;
+    }
+    case ORC_EXTENDED_HUBBARD_REAL_1D: { /* ExtendedHubbardReal1D.jl:101-126 */
+        orc_map mp; build_map(o->n[0], M, &mp);
+        long ext = 0, reg = 0; int pmode = 0, pocc = 0;
+        for (int i = 0; i < mp.len; i++) {
+            if (pmode == mp.mode[i] - 1) ext += (long)pocc * mp.occ[i]; /* prev starts as the zero index (mode 0, occ 0) */
+            reg += (long)mp.occ[i] * (mp.occ[i] - 1);
+            pmode = mp.mode[i]; pocc = mp.occ[i];
+        }
+        if (h->fold[0] != ORC_BC_HARD_WALL && mp.len > 0) {
+            long last = mp.mode[mp.len - 1] == M ? mp.occ[mp.len - 1] : 0;
+            long firstn = mp.mode[0] == 1 ? mp.occ[0] : 0;
+            ext += last * firstn;
+        }
+        return h->u * (double)reg / 2 + h->v * (double)ext;
+    }
     case ORC_HUBBARD_MOM_1D: { /* HubbardMom1D.jl:163-181, excitations.jl:126-160 */
         orc_map ma; build_map(o->n[0], M, &ma);
         if (h->addr_kind == ORC_BOSE) {
@@ -281,7 +308,8 @@ long orc_num_offdiagonals_onr(const orc_ham *h, const orc_onr *o) {
     orc_map ma, mb; build_map(o->n[0], M, &ma);
     if (h->ncomp == 2) build_map(o->n[1], M, &mb); else mb.len = 0;
     switch (h->model) {
-    case ORC_HUBBARD_REAL_1D: return 2L * ma.len; /* HubbardReal1D.jl:51-53 */
+    case ORC_HUBBARD_REAL_1D: case ORC_HUBBARD_REAL_1D_EP: case ORC_EXTENDED_HUBBARD_REAL_1D:
+        return 2L * ma.len; /* HubbardReal1D.jl:51-53, HubbardReal1DEP.jl:78-80, ExtendedHubbardReal1D.jl:88-90 */
     case ORC_HUBBARD_MOM_1D: /* HubbardMom1D.jl:131-144 */
         if (h->addr_kind == ORC_BOSE) {
             long s = ma.len, d = 0;
@@ -366,12 +394,19 @@ double orc_offdiagonal_onr(const orc_ham *h, const orc_onr *in, long chosen, orc
     orc_map ma, mb; build_map(in->n[0], M, &ma);
     if (h->ncomp == 2) build_map(in->n[1], M, &mb); else mb.len = 0;
     switch (h->model) {
-    case ORC_HUBBARD_REAL_1D: { /* bosefs.jl:270-274,347-353; HubbardReal1D.jl:59-62 */
+    case ORC_HUBBARD_REAL_1D: case ORC_HUBBARD_REAL_1D_EP: case ORC_EXTENDED_HUBBARD_REAL_1D: {
+        /* bosefs.jl:270-274,347-369; HubbardReal1D.jl:59-62, HubbardReal1DEP.jl:89-92, ExtendedHubbardReal1D.jl:128-135 */
         int site = (int)((chosen + 1) >> 1);
         int src = ma.mode[site - 1];
-        int dst = mod1i(src + ((chosen & 1) ? 1 : -1), M);
+        int dir = (chosen & 1) ? 1 : -1;
+        int dst = mod1i(src + dir, M);
         int cre[1] = {dst}, des[1] = {src};
         double val = bose_excite(out->n[0], M, cre, des, 1);
+        if (h->model == ORC_EXTENDED_HUBBARD_REAL_1D) {
+            int on_boundary = (src == 1 && dir == -1) || (src == M && dir == 1);
+            if (on_boundary && h->fold[0] == ORC_BC_TWISTED) val = -val;
+            else if (on_boundary && h->fold[0] == ORC_BC_HARD_WALL) val = 0.0;
+        }
         return -h->t * val;
     }
     case ORC_HUBBARD_MOM_1D: {

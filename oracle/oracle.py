@@ -29,6 +29,8 @@ MAXM = 128
 
 BOSE, FERMI, FERMI2C = 0, 1, 2
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3
+HUBBARD_REAL_1D_EP, EXTENDED_HUBBARD_REAL_1D = 4, 5
+BC_PERIODIC, BC_HARD_WALL, BC_TWISTED = 0, 1, 2
 STYLE_DETERMINISTIC, STYLE_INTEGER, STYLE_SEMISTOCHASTIC, STYLE_WITH_THRESHOLD = 0, 1, 2, 3
 
 
@@ -170,6 +172,13 @@ def trap_potential(dims, v):
     return pot
 
 
+def ep_lattice(M):
+    """shift_lattice(range(-fld(M,2); length=M)) (HubbardReal1DEP.jl:9,55-56): positions with js[0] = 0."""
+    is_ = list(range(-(M // 2), -(M // 2) + M))
+    k = -(-M // 2)  # cld(M, 2)
+    return is_[-k:] + is_[:-k]  # circshift(is, k)
+
+
 class OracleHam:
     """A Hamiltonian of the oracle.
 
@@ -179,11 +188,12 @@ class OracleHam:
     """
 
     MODELS = {"HubbardReal1D": HUBBARD_REAL_1D, "HubbardMom1D": HUBBARD_MOM_1D,
-              "HubbardRealSpace": HUBBARD_REAL_SPACE, "Transcorrelated1D": TRANSCORRELATED_1D}
+              "HubbardRealSpace": HUBBARD_REAL_SPACE, "Transcorrelated1D": TRANSCORRELATED_1D,
+              "HubbardReal1DEP": HUBBARD_REAL_1D_EP, "ExtendedHubbardReal1D": EXTENDED_HUBBARD_REAL_1D}
     KINDS = {"bose": BOSE, "fermi": FERMI, "fermi2c": FERMI2C}
 
     def __init__(self, model, kind, onr, u=1.0, t=1.0, v=1.0, dims=None, fold=None, trap=None,
-                 cutoff=1, three_body_term=True, dispersion="hubbard"):
+                 cutoff=1, three_body_term=True, dispersion="hubbard", v_ho=1.0, boundary_condition="periodic"):
         h = _Ham()
         h.model, h.addr_kind = self.MODELS[model], self.KINDS[kind]
         comps = [tuple(onr)] if kind != "fermi2c" else [tuple(onr[0]), tuple(onr[1])]
@@ -226,6 +236,15 @@ class OracleHam:
             ks, kes, ws, us = tc_tables(M, float(t), int(cutoff))
             for i in range(M):
                 h.ks[i], h.kes[i], h.ws[i], h.us[i] = ks[i], kes[i], ws[i], us[i]
+        elif model == "HubbardReal1DEP":  # HubbardReal1DEP.jl:52-59: eps_i = v_ho * j_i^2, j = shift_lattice(-M//2 .. )
+            h.u, h.t = float(u), float(t)
+            js = ep_lattice(M)
+            h.has_pot = 1
+            for i in range(M):
+                h.pot[i] = float(v_ho) * js[i] ** 2
+        elif model == "ExtendedHubbardReal1D":  # ExtendedHubbardReal1D.jl:54-66
+            h.u, h.t, h.v = float(u), float(t), float(v)
+            h.fold[0] = {"periodic": BC_PERIODIC, "hard_wall": BC_HARD_WALL, "twisted": BC_TWISTED}[boundary_condition]
         else:
             h.u, h.t = float(u), float(t)
         self.h = h

@@ -29,6 +29,8 @@ OK, ERR_TABLE_FULL, ERR_VECTOR_FULL, ERR_EXCHANGE_FULL = 0, 1, 2, 3
 ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = -1, -2, -3, -4
 ADDR_BOSE, ADDR_FERMI, ADDR_FERMI2C = 0, 1, 2
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3
+HUBBARD_REAL_1D_EP, EXTENDED_HUBBARD_REAL_1D = 4, 5
+BC_PERIODIC, BC_HARD_WALL, BC_TWISTED = 0, 1, 2
 VAL_F64, VAL_I64 = 0, 1
 STYLE_DETERMINISTIC, STYLE_INTEGER, STYLE_SEMISTOCHASTIC, STYLE_WITH_THRESHOLD = 0, 1, 2, 3
 ANNIHILATE_HASH, ANNIHILATE_SORT, ANNIHILATE_PARTITION = 0, 1, 2
@@ -68,7 +70,7 @@ class HamDesc(C.Structure):
         ("model", C.c_int32), ("addr_kind", C.c_int32), ("num_modes", C.c_int32), ("num_components", C.c_int32),
         ("num_particles", C.c_int32 * 2),
         ("ndim", C.c_int32), ("dims", C.c_int32 * 3), ("fold", C.c_int32 * 3),
-        ("cutoff", C.c_int32), ("three_body_term", C.c_int32), ("has_potential", C.c_int32), ("reserved", C.c_int32),
+        ("cutoff", C.c_int32), ("three_body_term", C.c_int32), ("has_potential", C.c_int32), ("boundary_condition", C.c_int32),
         ("u", C.c_double), ("t", C.c_double), ("v", C.c_double),
         ("t_comp", C.c_double * 2), ("u_mat", C.c_double * 4),
         ("kes", C.c_double * MAX_TABLE_MODES), ("ws", C.c_double * MAX_TABLE_MODES), ("us", C.c_double * MAX_TABLE_MODES),

@@ -582,7 +582,7 @@ extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
         if (d->num_components != 1) return fail(RIMU_ERR_INVALID, "BoseFS must have one component");
         bits = d->num_particles[0] + M - 1;
         if (bits + 1 > 128) return fail(RIMU_ERR_INVALID, "BoseFS{%d,%d} needs %d bits; at most 127 supported", d->num_particles[0], M, bits);
-        if (model == RIMU_HUBBARD_REAL_1D) hk = HK_REAL1D_BOSE;
+        if (model == RIMU_HUBBARD_REAL_1D || model == RIMU_HUBBARD_REAL_1D_EP || model == RIMU_EXTENDED_HUBBARD_REAL_1D) hk = HK_REAL1D_BOSE;
         else if (model == RIMU_HUBBARD_MOM_1D) hk = HK_MOM1D_BOSE;
         else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_BOSE;
     } else if (kind == RIMU_ADDR_FERMI) {
@@ -626,6 +626,9 @@ extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
     v.u = d->u; v.t = d->t; v.v = d->v; v.tc0 = d->t_comp[0]; v.tc1 = d->t_comp[1];
     v.u00 = d->u_mat[0]; v.u10 = d->u_mat[1];
     v.u_2m = d->u / (2 * M); v.u_m = d->u / M;
+    v.variant = model == RIMU_HUBBARD_REAL_1D_EP ? 1 : model == RIMU_EXTENDED_HUBBARD_REAL_1D ? 2 : 0;
+    v.bc = d->boundary_condition;
+    if (v.variant == 2 && (v.bc < 0 || v.bc > 2)) { delete h; return fail(RIMU_ERR_INVALID, "invalid boundary condition"); }
     int nz = 0;
     for (int i = 0; i < d->num_components * d->num_components; i++) nz += d->u_mat[(i % d->num_components) + 2 * (i / d->num_components)] != 0.0;
     v.umat_zero = nz == 0;

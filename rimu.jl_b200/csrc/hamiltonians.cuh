@@ -28,6 +28,7 @@ enum HamKind {
 
 struct HamDev {
     int hk, M, N0, N1, ndim, nnb, cutoff, three_body, has_pot, umat_zero;
+    int variant, bc; // HK_REAL1D_BOSE: 0 HubbardReal1D, 1 HubbardReal1DEP (pot = eps_i), 2 ExtendedHubbardReal1D (v, bc = RIMU_BC_*)
     double u, t, v, tc0, tc1, u00, u10;
     double u_2m, u_m; // u / (2M), u / M: the same IEEE divisions the reference evaluates per element, done once on the host
     const double *kes, *ws, *us, *pot; // device tables
@@ -206,7 +207,31 @@ DEV double tc_three_body(int M, u64 &fa, u64 &fb, int N1, int N2, long long i64_
 template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
     const int M = h.M;
     if constexpr (HK == HK_REAL1D_BOSE) {
-        return h.u * (double)bose_interaction(x) / 2;
+        if (h.variant == 0) return h.u * (double)bose_interaction(x) / 2;
+        if (h.variant == 1) { // HubbardReal1DEP.jl:82-87: sum over occupied modes (ascending) of u n (n-1) / 2 + eps[mode] n
+            double s = 0.0; bool first = true;
+            int md = 0; B y = x;
+            while (y != 0) {
+                int z = ctz_(y); y >>= z; md += z;
+                int n = cto_(y); y >>= n;
+                const double term = h.u * n * (n - 1) / 2 + h.pot[md] * n;
+                s = first ? term : s + term; first = false;
+            }
+            return s;
+        }
+        // ExtendedHubbardReal1D.jl:101-126: u sum n(n-1) / 2 + v sum n_j n_j+1 (ring unless hard wall)
+        long long ext = 0, reg = 0;
+        int md = 0, pmode = -1, pocc = 0, first_mode = -1, first_occ = 0; B y = x;
+        while (y != 0) {
+            int z = ctz_(y); y >>= z; md += z;      // md = 0-based mode of this occupied block
+            int n = cto_(y); y >>= n;
+            if (pmode == md - 1) ext += (long long)pocc * n;
+            reg += (long long)n * (n - 1);
+            if (first_mode < 0) { first_mode = md; first_occ = n; }
+            pmode = md; pocc = n;
+        }
+        if (h.bc != 1 /* hard wall */ && pmode >= 0) ext += (long long)(pmode == M - 1 ? pocc : 0) * (first_mode == 0 ? first_occ : 0);
+        return h.u * (double)reg / 2 + h.v * (double)ext;
     } else if constexpr (HK == HK_MOM1D_BOSE) {
         double ke = 0.0;
         int lin = 0, md = 0;
@@ -304,7 +329,13 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         B y = delete_bit(x, off);
         int nd = bose_create(y, dst);
         out = y;
-        return -h.t * sqrt((double)(ns * nd));
+        double val = sqrt((double)(ns * nd));
+        if (h.variant == 2) { // hopnextneighbour(b, i, boundary_condition) bosefs.jl:355-369
+            const bool on_boundary = (i & 1) ? mode == 1 : mode == M;
+            if (on_boundary && h.bc == 2) val = -val;
+            else if (on_boundary && h.bc == 1) { val = 0.0; out = x; }
+        }
+        return -h.t * val;
     } else if constexpr (HK == HK_MOM1D_BOSE) {
         const int s = bose_num_occupied(x);
         const int ndiff = s * (s - 1) * (M - 2);

@@ -266,6 +266,63 @@ class HubbardReal1D(AbstractHamiltonian):
         return f"HubbardReal1D({self.address}; u={self.u}, t={self.t})"
 
 
+def shift_lattice(is_):
+    """shift_lattice(is) = circshift(is, cld(length(is), 2)) (HubbardReal1DEP.jl:9)."""
+    is_ = list(is_)
+    k = -(-len(is_) // 2)
+    return is_[-k:] + is_[:-k]
+
+
+def shift_lattice_inv(js):
+    """shift_lattice_inv(js) = circshift(js, fld(length(js), 2)) (HubbardReal1DEP.jl:19)."""
+    js = list(js)
+    k = len(js) // 2
+    return js[-k:] + js[:-k] if k else js
+
+
+class HubbardReal1DEP(AbstractHamiltonian):
+    """HubbardReal1DEP(address; u, t, v_ho) (Hamiltonians/HubbardReal1DEP.jl:47-92): Bose-Hubbard chain with the
+    harmonic potential eps_i = v_ho * j_i^2, j = shift_lattice(-M÷2 : M÷2-1)."""
+
+    def __init__(self, address, u=1.0, t=1.0, v_ho=1.0):
+        if not isinstance(address, BoseFS):
+            raise TypeError("HubbardReal1DEP on the device path needs a BoseFS address")
+        self.u, self.t, self.v_ho = float(u), float(t), float(v_ho)
+        M = address.num_modes
+        js = shift_lattice(range(-(M // 2), -(M // 2) + M))
+        self.ep = np.array([self.v_ho * j ** 2 for j in js], dtype=float)
+        self.desc = _lib.HamDesc()
+        self.desc.model, self.desc.u, self.desc.t, self.desc.has_potential = _lib.HUBBARD_REAL_1D_EP, self.u, self.t, 1
+        for i in range(M):
+            self.desc.potential[i] = self.ep[i]
+        self._finish(address)
+
+    def __repr__(self):
+        return f"HubbardReal1DEP({self.address}; u={self.u}, t={self.t}, v_ho={self.v_ho})"
+
+
+class ExtendedHubbardReal1D(AbstractHamiltonian):
+    """ExtendedHubbardReal1D(address; u, v, t, boundary_condition) (Hamiltonians/ExtendedHubbardReal1D.jl:30-135) for
+    bosons with the real boundary conditions :periodic, :hard_wall, :twisted (a complex twist angle makes the
+    Hamiltonian complex; there is no device path for that and no CPU fallback)."""
+
+    BCS = {"periodic": _lib.BC_PERIODIC, "hard_wall": _lib.BC_HARD_WALL, "twisted": _lib.BC_TWISTED}
+
+    def __init__(self, address, u=1.0, v=1.0, t=1.0, boundary_condition="periodic"):
+        if not isinstance(address, BoseFS):
+            raise TypeError("ExtendedHubbardReal1D on the device path needs a BoseFS address")
+        if boundary_condition not in self.BCS:
+            raise ValueError("invalid boundary condition")  # ArgumentError (ExtendedHubbardReal1D.jl:64)
+        self.u, self.v, self.t, self.boundary_condition = float(u), float(v), float(t), boundary_condition
+        self.desc = _lib.HamDesc()
+        self.desc.model, self.desc.u, self.desc.v, self.desc.t = _lib.EXTENDED_HUBBARD_REAL_1D, self.u, self.v, self.t
+        self.desc.boundary_condition = self.BCS[boundary_condition]
+        self._finish(address)
+
+    def __repr__(self):
+        return f"ExtendedHubbardReal1D({self.address}; u={self.u}, v={self.v}, t={self.t}, boundary_condition=:{self.boundary_condition})"
+
+
 class HubbardMom1D(AbstractHamiltonian):
     def __init__(self, address, u=1.0, t=1.0, dispersion=hubbard_dispersion):
         if not isinstance(address, (BoseFS, CompositeFS)):

@@ -21,6 +21,11 @@ SPECS = {
     "real1d_6": ("HubbardReal1D", "bose", _nu(6, 6), dict(u=6.0, t=1.0)),
     "real1d_10": ("HubbardReal1D", "bose", _nu(10, 10), dict(u=6.0, t=1.0)),             # BASELINE config 1
     "real1d_w2": ("HubbardReal1D", "bose", _nu(40, 40), dict(u=2.0, t=1.0)),             # 79 bits -> 2 words
+    "real1d_ep": ("HubbardReal1DEP", "bose", (1, 2, 3, 4), dict(u=2.0, t=3.0, v_ho=4.0)),              # test/Hamiltonians.jl:392
+    "real1d_ep_w2": ("HubbardReal1DEP", "bose", tuple(1 if i == 0 else 0 for i in range(100)), dict(u=1.0, t=50.0, v_ho=0.005)),  # :1045-1054
+    "ext1d": ("ExtendedHubbardReal1D", "bose", (1, 0, 2, 1), dict(u=1.0, v=2.0, t=3.0)),
+    "ext1d_twisted": ("ExtendedHubbardReal1D", "bose", (2, 0, 1, 1, 0, 1), dict(u=1.5, v=6.0, t=2.0, boundary_condition="twisted")),
+    "ext1d_hw": ("ExtendedHubbardReal1D", "bose", (1, 1, 0, 2, 1), dict(u=1.0, v=6.0, t=2.0, boundary_condition="hard_wall")),
     "mom1d_bose": ("HubbardMom1D", "bose", (0, 0, 0, 6, 0, 0, 0, 0), dict(u=4.0, t=1.0)),
     "mom1d_bose_20": ("HubbardMom1D", "bose", tuple(20 if i == 9 else 0 for i in range(20)), dict(u=6.0, t=1.0)),  # config 2
     "mom1d_odd": ("HubbardMom1D", "bose", (1, 2, 3, 0, 0), dict(u=1.0, t=1.0)),
@@ -59,6 +64,10 @@ def product_ham(name):
         addr = R.FermiFS2C(onr[0], onr[1])
     if model == "HubbardReal1D":
         return R.HubbardReal1D(addr, **p)
+    if model == "HubbardReal1DEP":
+        return R.HubbardReal1DEP(addr, **p)
+    if model == "ExtendedHubbardReal1D":
+        return R.ExtendedHubbardReal1D(addr, **p)
     if model == "HubbardMom1D":
         return R.HubbardMom1D(addr, **p)
     if model == "Transcorrelated1D":

@@ -455,3 +455,55 @@ def test_initiator_rule_zero_is_the_plain_step():
         k3, v3, s3 = oh.step(orc.make_params(orc.STYLE_INTEGER, shift=1.0, dtau=0.02, key=orc.step_key(3, step),
                                              initiator_rule=orc.INITIATOR, initiator_threshold=1.0), k3, v3)
     assert len(v3) <= len(v)
+
+
+# --------------------------------------------------------------------------- 1-D models sharing HubbardReal1D's generator
+def test_hubbard_real1d_ep_pins():
+    """HubbardReal1DEP (Hamiltonians/HubbardReal1DEP.jl): the reference pins it three ways (test/Hamiltonians.jl):
+    :392-396 same energy as HubbardRealSpace with a trap; :1039-1043 shift_lattice; :1045-1054 a single particle in a
+    wide harmonic trap has the oscillator spectrum n + 1/2 (atol 0.005) and sits at zero potential."""
+    assert orc.ep_lattice(3) == [0, 1, -1] and orc.ep_lattice(4) == [0, 1, -2, -1]  # js[1] == 0, circular
+    for M in (3, 4):
+        js = orc.ep_lattice(M)
+        k = M // 2
+        assert (js[-k:] + js[:-k] if k else js) == list(range(-(M // 2), -(M // 2) + M))  # shift_lattice_inv(js) == is
+    a = (1, 2, 3, 4)
+    h1 = orc.OracleHam("HubbardReal1DEP", "bose", a, u=2.0, t=3.0, v_ho=4.0)
+    h2 = orc.OracleHam("HubbardRealSpace", "bose", a, u=2.0, t=3.0, dims=(4,), trap=((4.0,),))
+    assert math.isclose(h1.exact_energy(), h2.exact_energy(), rel_tol=1e-12)
+    m, l0 = 100, 10
+    t, v_ho = 0.5 * l0 ** 2, 0.5 / l0 ** 2
+    h = orc.OracleHam("HubbardReal1DEP", "bose", tuple(1 if i == 0 else 0 for i in range(m)), t=t, v_ho=v_ho)
+    assert h.diagonal_element(h.start_key) == 0.0
+    ev = h.exact_eigenvalues() + 2 * t
+    assert np.allclose(ev[:3], [0.5, 1.5, 2.5], atol=0.005)
+
+
+def test_extended_hubbard_real1d_pins():
+    """ExtendedHubbardReal1D (Hamiltonians/ExtendedHubbardReal1D.jl): hand-computed diagonal; v = 0 is HubbardReal1D;
+    boundary conditions as asserted in test/Hamiltonians.jl:1580-1603 (twisted: boundary hop changes sign, diagonal
+    unchanged; hard wall: boundary hop is 0)."""
+    a = (1, 0, 2, 1)
+    h = orc.OracleHam("ExtendedHubbardReal1D", "bose", a, u=1.0, v=2.0, t=3.0)
+    # sum n(n-1) = 2; neighbours: n3 n4 = 2, ring closure n4 n1 = 1 -> 3
+    assert h.diagonal_element(h.start_key) == 1.0 * 2 / 2 + 2.0 * 3
+    hw = orc.OracleHam("ExtendedHubbardReal1D", "bose", a, u=1.0, v=2.0, t=3.0, boundary_condition="hard_wall")
+    assert hw.diagonal_element(hw.start_key) == 1.0 * 2 / 2 + 2.0 * 2
+    plain = orc.OracleHam("HubbardReal1D", "bose", a, u=1.0, t=3.0)
+    h0 = orc.OracleHam("ExtendedHubbardReal1D", "bose", a, u=1.0, v=0.0, t=3.0)
+    basis = plain.bfs_basis()
+    assert np.array_equal(h0.bfs_basis(), basis)
+    assert (abs(plain.sparse_matrix(basis) - h0.sparse_matrix(basis))).max() == 0.0
+    tw = orc.OracleHam("ExtendedHubbardReal1D", "bose", a, u=1.0, v=2.0, t=3.0, boundary_condition="twisted")
+    key = h.start_key
+    k_per, me = h.get_offdiagonal(key, 2)       # chosen = 2: first occupied mode (site 1) hops LEFT across the boundary
+    k_tw, me_tw = tw.get_offdiagonal(key, 2)
+    k_hw, me_hw = hw.get_offdiagonal(key, 2)
+    assert me != 0.0 and me_tw == -me and k_tw == k_per and me_hw == 0.0
+    assert tw.diagonal_element(key) == h.diagonal_element(key)
+    assert h.get_offdiagonal(key, 1) == tw.get_offdiagonal(key, 1) == hw.get_offdiagonal(key, 1)  # interior hop
+    # Hermitian for all three boundary conditions
+    for ham in (h, tw, hw):
+        b = ham.bfs_basis()
+        mat = ham.sparse_matrix(b)
+        assert abs(mat - mat.T).max() < 1e-14
