@@ -49,6 +49,15 @@ static std::string oom_note() {
              fr / 1073741824.0, tot / 1073741824.0);
     return b;
 }
+// Entry of every API call that touches the device: select the context's GPU and drop any stale, non-sticky error that an
+// earlier benign failure in this thread (ours, NCCL's or the host framework's) left in CUDA's "last error" slot -- otherwise
+// it would be reported by the first cudaGetLastError() after one of OUR launches.  Sticky errors survive this and are
+// still caught by the next call.
+static cudaError_t enter_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    cudaGetLastError();
+    return e;
+}
 #define CUDA_TRY(x)                                                                                   \
     do {                                                                                              \
         cudaError_t e_ = (x);                                                                         \
@@ -107,6 +116,7 @@ static int nccl_load() {
     do {                                                                                         \
         int e_ = (x);                                                                            \
         if (e_ != 0) return fail(RIMU_ERR_NCCL, "%s failed: %s", #x, g_nccl.GetErrorString(e_)); \
+        cudaGetLastError(); /* NCCL succeeded: whatever benign CUDA error it left behind is not ours */ \
     } while (0)
 
 // ---------------------------------------------------------------- handles
@@ -139,7 +149,10 @@ struct rimu_ctx {
     int direct;              // multi-GPU: peers can map each other's streams (CUDA IPC) -> spawned records are stored
                              //   straight into the owner's bucket sub-streams, no receive pass
     const rimu_vec *last_dst; u64 last_dst_version; double last_g_len;
-    u32 merge_grid_cap;      // RIMU_B200_MERGE_GRID: cap on merge CTAs (tests force many buckets per CTA with it) // global length of the previous step's result
+    u32 merge_grid_cap;      // RIMU_B200_MERGE_GRID: cap on merge CTAs (tests force many buckets per CTA with it)
+    int live_vecs;           // vectors created on this context and not yet destroyed
+    int dead;                // rimu_ctx_destroy was called while vectors were alive: the struct (and stream) live on until the
+                             //   last of them is destroyed (host GCs finalise vectors and contexts in arbitrary order) // global length of the previous step's result
     HeavyDev heavy;
     u32 *bucket_tmp; u64 bucket_tmp_cap; // [2][nb] counts / fill
     u64 xch_worst;           // largest per-peer record count seen by a failed exchange
@@ -151,6 +164,12 @@ struct rimu_ctx {
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
     u64 last_max_fill;
 };
+static int enter_ctx(rimu_ctx *c) {
+    if (!c) return fail(RIMU_ERR_INVALID, "null context");
+    if (c->dead) return fail(RIMU_ERR_INVALID, "this context has been destroyed (a vector outlived it)");
+    CUDA_TRY(enter_device(c->device));
+    return 0;
+}
 struct rimu_ham {
     rimu_ham_desc desc;
     int hk, W, device;
@@ -233,8 +252,13 @@ extern "C" int rimu_sort_scratch_bytes(void);
 extern "C" int rimu_sort_annihilate_w1(cudaStream_t stream, SortScratch *s, const u64 *keys, const u64 *vals, long long n, int is_int,
                                        int key_bits, u64 *out_keys, u64 *out_vals, u64 out_cap, u64 *d_cursor);
 extern "C" void rimu_sort_scratch_free(SortScratch *s);
+static void ctx_free_struct(rimu_ctx *c) {
+    cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
 extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
-    if (!c) return 0;
+    if (!c || c->dead) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     p2p_teardown(c);
@@ -252,12 +276,15 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->heavy.items); cudaFree(c->heavy.packed); cudaFree(c->bucket_tmp);
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaFree(c->d_red);
-    cudaStreamDestroy(c->stream);
     cudaGetLastError(); // teardown is best effort (e.g. closing an IPC mapping whose exporter is already gone): never leave a stale error behind
-    delete c;
+    if (c->live_vecs > 0) { // vectors still point at this context: keep the struct and the stream until the last one goes
+        c->dead = 1;
+        return 0;
+    }
+    ctx_free_struct(c);
     return 0;
 }
-extern "C" int rimu_ctx_make_current(rimu_ctx *c) { if (!c) return fail(RIMU_ERR_INVALID, "null context"); CUDA_TRY(cudaSetDevice(c->device)); return 0; }
+extern "C" int rimu_ctx_make_current(rimu_ctx *c) { if (!c) return fail(RIMU_ERR_INVALID, "null context"); TRY(enter_ctx(c)); return 0; }
 extern "C" int rimu_ctx_synchronize(rimu_ctx *c) { CUDA_TRY(cudaStreamSynchronize(c->stream)); return 0; }
 extern "C" int rimu_ctx_table_slots(rimu_ctx *c, uint64_t *out) { *out = c->table_slots; return 0; }
 extern "C" int rimu_ctx_stream(rimu_ctx *c, void **s) { *s = (void *)c->stream; return 0; }
@@ -272,7 +299,7 @@ extern "C" int rimu_ctx_get_method(rimu_ctx *c, int *method) { *method = c->meth
 extern "C" int rimu_host_alloc(uint64_t bytes, void **out) { CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1)); return 0; }
 extern "C" int rimu_host_free(void *p) { if (p) CUDA_TRY(cudaFreeHost(p)); return 0; }
 extern "C" int rimu_ctx_resize_table(rimu_ctx *c, uint64_t table_slots) {
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     u64 slots = next_pow2(table_slots < 1024 ? 1024 : table_slots);
     if (slots == c->table_slots) return 0;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -501,7 +528,7 @@ static int ensure_xch(rimu_ctx *c) {
 extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nranks, uint64_t per_peer) {
     if (nranks < 1 || nranks > RIMU_MAX_RANKS || rank < 0 || rank >= nranks) return fail(RIMU_ERR_INVALID, "bad rank/nranks");
     if (c->comm) return fail(RIMU_ERR_INVALID, "communicator already attached");
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     c->rank = rank; c->nranks = nranks;
     if (nranks == 1) return 0;
     TRY(nccl_load());
@@ -522,7 +549,7 @@ extern "C" int rimu_comm_init(rimu_ctx *c, const void *id128, int rank, int nran
 // grow the per-peer exchange buffers (every rank must call it with the same size; contents are scratch)
 extern "C" int rimu_comm_reserve(rimu_ctx *c, uint64_t per_peer) {
     if (c->nranks == 1 || per_peer <= c->xch.cap) return 0;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (!c->xch.keys) { if (per_peer > c->xch_want) c->xch_want = per_peer; return 0; } // not allocated yet (direct mode)
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->recv_keys); cudaFree(c->recv_vals);
@@ -538,7 +565,7 @@ extern "C" int rimu_comm_rank(rimu_ctx *c, int *rank, int *nranks) { *rank = c->
 extern "C" int rimu_comm_allreduce_f64(rimu_ctx *c, double *buf, int n) {
     if (c->nranks == 1) return 0;
     if (n > 64) return fail(RIMU_ERR_INVALID, "allreduce of at most 64 doubles");
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     CUDA_TRY(cudaMemcpyAsync(c->d_reduce, buf, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     NCCL_TRY(g_nccl.AllReduce(c->d_reduce, c->d_reduce, n, ncclFloat64, ncclSum, c->comm, c->stream));
     CUDA_TRY(cudaMemcpyAsync(buf, c->d_reduce, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -687,9 +714,10 @@ template <class F> static int dispatch_ham(const rimu_ham *h, F &&f) {
 
 static int check_ctx_ham(rimu_ctx *c, const rimu_ham *h) {
     if (!c || !h) return fail(RIMU_ERR_INVALID, "null handle");
+    if (c->dead) return fail(RIMU_ERR_INVALID, "the context of these vectors has been destroyed");
     if (c->W != h->W) return fail(RIMU_ERR_INVALID, "context built for %d-word addresses, Hamiltonian needs %d", c->W, h->W);
     if (c->device != h->device) return fail(RIMU_ERR_INVALID, "Hamiltonian tables live on device %d, context on %d", h->device, c->device);
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     return 0;
 }
 
@@ -748,7 +776,7 @@ extern "C" int rimu_ham_offdiagonals(rimu_ctx *c, const rimu_ham *h, const uint6
 extern "C" int rimu_vec_create(rimu_ctx *c, int val_type, uint64_t capacity, rimu_vec **out) {
     if (!c || !out) return fail(RIMU_ERR_INVALID, "null argument");
     if (val_type != RIMU_VAL_F64 && val_type != RIMU_VAL_I64) return fail(RIMU_ERR_INVALID, "bad value type");
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     rimu_vec *v = new rimu_vec();
     v->ctx = c; v->vt = val_type; v->n = 0; v->cap = capacity < 256 ? 256 : capacity;
     v->keys = nullptr; v->vals = nullptr;
@@ -756,21 +784,25 @@ extern "C" int rimu_vec_create(rimu_ctx *c, int val_type, uint64_t capacity, rim
     v->diag = nullptr; v->diag_cap = 0; v->diag_uid = 0;
     CUDA_TRY(rimu_malloc(&v->keys, v->cap * c->W * sizeof(u64)));
     CUDA_TRY(rimu_malloc(&v->vals, v->cap * sizeof(u64)));
+    c->live_vecs++;
     *out = v;
     return 0;
 }
 extern "C" int rimu_vec_destroy(rimu_vec *v) {
     if (!v) return 0;
-    cudaSetDevice(v->ctx->device);
-    cudaStreamSynchronize(v->ctx->stream);
+    rimu_ctx *c = v->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
     cudaFree(v->keys); cudaFree(v->vals); cudaFree(v->seg_start); cudaFree(v->seg_len); cudaFree(v->diag);
+    cudaGetLastError();
     delete v;
+    if (--c->live_vecs <= 0 && c->dead) ctx_free_struct(c);
     return 0;
 }
 extern "C" int rimu_vec_reserve(rimu_vec *v, uint64_t capacity) {
     if (capacity <= v->cap) return 0;
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     u64 *nk = nullptr; void *nv = nullptr;
     CUDA_TRY(rimu_malloc(&nk, capacity * c->W * sizeof(u64)));
     CUDA_TRY(rimu_malloc(&nv, capacity * sizeof(u64)));
@@ -831,7 +863,7 @@ static u64 pick_slots(rimu_ctx *c, u64 expected_entries) {
 // Retries with more slots on table overflow; grows dst when needed.
 static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
                           const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     dst->nb = 0; dst->diag_uid = 0; // the global-table path produces an unsegmented vector
     u64 slots = pick_slots(c, (u64)(n + n2));
     const bool aliased = (const u64 *)dst->keys == d_keys || (const u64 *)dst->keys == d_keys2;
@@ -890,7 +922,7 @@ static u32 part_cap_items(int W);
 static size_t part_smem_bytes(int W);
 static int records_to_vec_part(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
                                const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     dst->diag_uid = 0; dst->nb = 0;
     const double cap = (double)part_cap_items(c->W);
     u32 nb = (u32)ceil(((double)(n + n2) * 1.1 + 256.0) / (0.65 * cap));
@@ -961,7 +993,7 @@ static int records_to_vec_auto(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, co
 extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
     if (v) v->version++;
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (n <= 0) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; }
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -971,7 +1003,7 @@ extern "C" int rimu_vec_upload(rimu_vec *v, const uint64_t *keys, const void *va
 extern "C" int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *vals, int64_t n) {
     if (v) v->version++;
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (n < 0) return fail(RIMU_ERR_INVALID, "negative length");
     v->nb = 0; v->diag_uid = 0;
     if ((u64)n > v->cap) { v->n = 0; TRY(rimu_vec_reserve(v, (u64)n)); }
@@ -984,7 +1016,7 @@ extern "C" int rimu_vec_assign(rimu_vec *v, const uint64_t *keys, const void *va
 }
 extern "C" int rimu_vec_download(rimu_vec *v, uint64_t *keys_out, void *vals_out, int64_t cap, int64_t *n_out) {
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (n_out) *n_out = v->n;
     if (cap < v->n) return fail(RIMU_ERR_VECTOR_FULL, "download buffer too small: need %lld", (long long)v->n);
     if (v->n > 0) {
@@ -999,7 +1031,7 @@ extern "C" int rimu_vec_copy(rimu_vec *dst, rimu_vec *src) {
     if (dst == src) return 0;
     rimu_ctx *c = src->ctx;
     if (dst->ctx != c) return fail(RIMU_ERR_INVALID, "copy between vectors of different contexts");
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if ((u64)src->n > dst->cap) { dst->n = 0; TRY(rimu_vec_reserve(dst, (u64)src->n)); }
     if (src->n > 0) {
         CUDA_TRY(cudaMemcpyAsync(dst->keys, src->keys, src->n * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
@@ -1028,7 +1060,7 @@ extern "C" int rimu_vec_copy(rimu_vec *dst, rimu_vec *src) {
 }
 extern "C" int rimu_vec_get(rimu_vec *v, const uint64_t *key, void *val_out) {
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     u64 *d_out = (u64 *)c->d_reduce;
     CUDA_TRY(cudaMemsetAsync(d_out, 0, sizeof(u64), c->stream));
     if (v->n > 0) {
@@ -1046,7 +1078,7 @@ extern "C" int rimu_vec_get(rimu_vec *v, const uint64_t *key, void *val_out) {
 }
 extern "C" int rimu_vec_norm(rimu_vec *v, int p, double *out) {
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
     if (v->n > 0) {
         if (v->vt == RIMU_VAL_F64) norm_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const double *)v->vals, v->n, c->d_stats);
@@ -1074,7 +1106,7 @@ extern "C" int rimu_vec_norm(rimu_vec *v, int p, double *out) {
 extern "C" int rimu_vec_scale(rimu_vec *v, double alpha) {
     if (v) v->version++;
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (alpha == 0.0) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; } // zero values are never stored
     if (v->n > 0) {
         if (v->vt == RIMU_VAL_F64) scale_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((double *)v->vals, v->n, alpha);
@@ -1086,7 +1118,7 @@ extern "C" int rimu_vec_scale(rimu_vec *v, double alpha) {
 extern "C" int rimu_vec_dot(rimu_vec *x, rimu_vec *y, double *out) {
     rimu_ctx *c = x->ctx;
     if (y->ctx != c || x->vt != y->vt) return fail(RIMU_ERR_INVALID, "dot of incompatible vectors");
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     rimu_vec *build = x->n <= y->n ? x : y, *probe = x->n <= y->n ? y : x; // table from the shorter one
     double r = 0.0;
     if (build->n > 0) {
@@ -1124,7 +1156,7 @@ extern "C" int rimu_vec_dot(rimu_vec *x, rimu_vec *y, double *out) {
 extern "C" int rimu_vec_dot_sparse(rimu_vec *v, const uint64_t *keys, const double *values, int64_t n, double *out) {
     rimu_ctx *c = v->ctx;
     if (!out || n < 0 || (n > 0 && (!keys || !values))) return fail(RIMU_ERR_INVALID, "dot_sparse: bad arguments");
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     double r = 0.0;
     if (n > 0 && v->n > 0) {
         TRY(ensure_stage(c, (u64)n));
@@ -1159,7 +1191,7 @@ extern "C" int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *
 extern "C" int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, const void *d_vals, int64_t n, int method, float *ms_out) {
     if (dst) dst->version++;
     rimu_ctx *c = dst->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (method != RIMU_ANNIHILATE_HASH && method != RIMU_ANNIHILATE_SORT && method != RIMU_ANNIHILATE_PARTITION)
         return fail(RIMU_ERR_INVALID, "annihilation method %d unknown", method);
     if (method == RIMU_ANNIHILATE_SORT && c->W != 1)
@@ -1196,7 +1228,7 @@ extern "C" int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, con
 }
 extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *vals, int64_t n, int method) {
     rimu_ctx *c = dst->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (n <= 0) { dst->n = 0; dst->nb = 0; dst->diag_uid = 0; return 0; }
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
@@ -1354,7 +1386,7 @@ extern "C" int rimu_vec_rebucket(rimu_vec *v, uint32_t nb) {
 extern "C" int rimu_vec_buckets(rimu_vec *v, uint32_t *nb) { *nb = v->nb; return 0; }
 extern "C" int rimu_vec_segments(rimu_vec *v, uint64_t *start_out, uint32_t *len_out) {
     rimu_ctx *c = v->ctx;
-    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(enter_ctx(c));
     if (v->nb) {
         CUDA_TRY(cudaMemcpyAsync(start_out, v->seg_start, v->nb * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemcpyAsync(len_out, v->seg_len, v->nb * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
