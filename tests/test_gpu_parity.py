@@ -402,3 +402,26 @@ def test_frozen_dot_matches_dense_dot(built, name):
     small = R.GPUDVec(style=R.IsDeterministic(), address_type=x.address_type)
     small.assign(fk[:500], fv[:500])
     assert math.isclose(small.freeze().dot(x), small.dot(x), rel_tol=1e-12)
+
+
+def test_vectors_may_outlive_their_context(built):
+    """Host garbage collectors finalise vectors and contexts in arbitrary order (Julia finalizers, Python __del__):
+    destroying a context first must neither crash nor leave a stale CUDA error behind; using the orphaned vector
+    reports an error instead of touching freed memory."""
+    import rimu_b200 as R
+    a = R.BoseFS((1, 1, 1))
+    H = R.HubbardReal1D(a)
+    ctx = R.Context(1)
+    v = R.GPUDVec([(a, 2.0)], style=R.IsDeterministic(), ctx=ctx)
+    w = v.similar()
+    R.mul(w, H, v)
+    assert len(w) > 1
+    ctx.close()                      # context gone, two vectors still alive
+    with pytest.raises(R.RimuB200Error):
+        v.norm(2)
+    del v, w                         # the last one releases the context's remains
+    # the default context is unaffected and sees no stale error
+    x = R.GPUDVec([(a, 1.0)], style=R.IsDeterministic())
+    y = x.similar()
+    R.mul(y, H, x)
+    assert math.isclose(y.norm(1), sum(abs(val) for val in y.download()[1]))
