@@ -148,7 +148,8 @@ struct rimu_ctx {
     u64 lpart_nb_cap;        //   run between steps while a faster peer may already be filling the step streams
     int direct;              // multi-GPU: peers can map each other's streams (CUDA IPC) -> spawned records are stored
                              //   straight into the owner's bucket sub-streams, no receive pass
-    const rimu_vec *last_dst; u64 last_dst_version; double last_g_len;
+    u64 last_dst_uid, last_dst_version; double last_g_len; // identity (uid, never reused) + state of the previous step's result
+    u64 next_vec_uid;        // vectors are numbered in creation order: the same numbers on every rank (same call sequence)
     u32 merge_grid_cap;      // RIMU_B200_MERGE_GRID: cap on merge CTAs (tests force many buckets per CTA with it)
     int live_vecs;           // vectors created on this context and not yet destroyed
     int dead;                // rimu_ctx_destroy was called while vectors were alive: the struct (and stream) live on until the
@@ -195,6 +196,7 @@ struct rimu_vec {
     double *diag;
     u64 diag_cap, diag_uid;
     u64 version;             // bumped by every mutating API call (the same call sequence runs on every rank)
+    u64 uid;                 // creation number within the context (a freed vector's address may be reused, its uid never is)
 };
 
 static u64 next_pow2(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
@@ -785,6 +787,7 @@ extern "C" int rimu_vec_create(rimu_ctx *c, int val_type, uint64_t capacity, rim
     CUDA_TRY(rimu_malloc(&v->keys, v->cap * c->W * sizeof(u64)));
     CUDA_TRY(rimu_malloc(&v->vals, v->cap * sizeof(u64)));
     c->live_vecs++;
+    v->uid = ++c->next_vec_uid; // (0 = "no vector": last_dst_uid starts at 0)
     *out = v;
     return 0;
 }
@@ -1502,7 +1505,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
     // untouched result, otherwise all-reduced here
     double parents = (double)src->n, g_len = (double)src->n;
     if (c->nranks > 1) {
-        if (c->last_dst == src && c->last_dst_version == src->version) g_len = c->last_g_len;
+        if (c->last_dst_uid == src->uid && c->last_dst_version == src->version) g_len = c->last_g_len;
         else TRY(rimu_comm_allreduce_f64(c, &g_len, 1));
         parents = ceil(g_len / c->nranks * 1.02) + 64.0;
     }
@@ -1589,7 +1592,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         dst->nb = use_part ? nb : 0;
         dst->diag_uid = use_part ? h->uid : 0;
         dst->version++;
-        c->last_dst = dst; c->last_dst_version = dst->version; c->last_g_len = (double)g.len;
+        c->last_dst_uid = dst->uid; c->last_dst_version = dst->version; c->last_g_len = (double)g.len;
         if (use_part) {
             const double rec_all = multi ? (double)g.records : (double)l.records, par_all = multi ? g_len : (double)src->n;
             if (par_all > 0) { // identical on every rank in multi-GPU runs (all-reduced inputs)
