@@ -28,6 +28,13 @@
  *   StochasticStyles/spawning.jl:9-93,152-243,358-385, styles.jl:11-25,76-105,175-214,
  *   StochasticStyles/compression.jl:8-42
  *   Interfaces/dictvectors.jl:112-140, DictVectors/pdworkingmemory.jl:21-31,191-309
+ *   DictVectors/initiators.jl:22-45,132-236  InitiatorValue lanes, to_/from_initiator_value
+ *   Hamiltonians/HubbardReal1DEP.jl:9,47-92, ExtendedHubbardReal1D.jl:30-135, bosefs.jl:355-369
+ *
+ * RNG: the reference draws from Julia's task-local Xoshiro256++; that stream cannot be matched ("parity unpinned" for the
+ * random stream, by design).  Oracle and kernels share a Philox4x32-10 function of (step key, address hash, attempt
+ * index, stream id), pinned by Random123 known answers, so THEIR parity is bit-exact; parity with the reference for
+ * stochastic runs is distributional (blocking analysis, expectation-equality tests).
  */
 #include <math.h>
 #include <stdint.h>
