@@ -6,6 +6,7 @@
 //   move_and_compress!  -> compact_kernel (also walkernumber_and_length)
 #include "../../include/rimu_b200.h"
 #include "partition.cuh"
+#include "ham_host.h"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -589,100 +590,31 @@ extern "C" void rimu_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2],
 }
 
 // ---------------------------------------------------------------- Hamiltonian
-static int neighbor_site_host(const rimu_ham_desc *d, int mode, int chosen) { // geometry.jl:161-175,232-235
-    int D = d->ndim, idx = mode - 1, x[3];
-    for (int k = 0; k < D; k++) { x[k] = idx % d->dims[k] + 1; idx /= d->dims[k]; }
-    if (chosen <= D) x[chosen - 1] += 1; else x[chosen - D - 1] -= 1;
-    for (int k = 0; k < D; k++) {
-        if (d->fold[k]) { x[k] = ((x[k] - 1) % d->dims[k] + d->dims[k]) % d->dims[k] + 1; }
-        else if (x[k] < 1 || x[k] > d->dims[k]) return 0;
-    }
-    int lin = 0, stride = 1;
-    for (int k = 0; k < D; k++) { lin += (x[k] - 1) * stride; stride *= d->dims[k]; }
-    return lin + 1;
-}
-
 extern "C" int rimu_ham_create(const rimu_ham_desc *d, rimu_ham **out) {
     if (!d || !out) return fail(RIMU_ERR_INVALID, "null argument");
-    const int M = d->num_modes, kind = d->addr_kind, model = d->model;
-    if (M < 1 || M > RIMU_MAX_MODES) return fail(RIMU_ERR_INVALID, "num_modes %d unsupported (1..%d)", M, RIMU_MAX_MODES);
-    int hk = -1, bits = 0;
-    if (kind == RIMU_ADDR_BOSE) {
-        if (d->num_components != 1) return fail(RIMU_ERR_INVALID, "BoseFS must have one component");
-        bits = d->num_particles[0] + M - 1;
-        if (bits + 1 > 128) return fail(RIMU_ERR_INVALID, "BoseFS{%d,%d} needs %d bits; at most 127 supported", d->num_particles[0], M, bits);
-        if (model == RIMU_HUBBARD_REAL_1D || model == RIMU_HUBBARD_REAL_1D_EP || model == RIMU_EXTENDED_HUBBARD_REAL_1D) hk = HK_REAL1D_BOSE;
-        else if (model == RIMU_HUBBARD_MOM_1D) hk = HK_MOM1D_BOSE;
-        else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_BOSE;
-    } else if (kind == RIMU_ADDR_FERMI) {
-        if (d->num_components != 1) return fail(RIMU_ERR_INVALID, "FermiFS must have one component");
-        bits = M;
-        if (M > 63) return fail(RIMU_ERR_INVALID, "FermiFS with more than 63 modes unsupported");
-        if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_FERMI;
-    } else if (kind == RIMU_ADDR_FERMI2C) {
-        if (d->num_components != 2) return fail(RIMU_ERR_INVALID, "FermiFS2C must have two components");
-        bits = 2 * M;
-        if (M > 32) return fail(RIMU_ERR_INVALID, "two-component fermions with more than 32 modes unsupported");
-        if (d->num_particles[0] == M && d->num_particles[1] == M && M == 32)
-            return fail(RIMU_ERR_INVALID, "completely filled 32-mode two-component address collides with the empty-slot sentinel");
-        if (model == RIMU_HUBBARD_MOM_1D) hk = HK_MOM1D_F2C;
-        else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_F2C;
-        else if (model == RIMU_TRANSCORRELATED_1D) hk = HK_TC_F2C;
-    }
-    if (hk < 0)
-        return fail(RIMU_ERR_INVALID, "model %d is not implemented for address kind %d (no CPU fallback exists)", model, kind);
-    if ((hk == HK_MOM1D_BOSE || hk == HK_MOM1D_F2C || hk == HK_TC_F2C) && M > RIMU_MAX_TABLE_MODES)
-        return fail(RIMU_ERR_INVALID, "momentum-space models support at most %d modes", RIMU_MAX_TABLE_MODES);
-    if (hk == HK_MOM1D_BOSE && M < 3) return fail(RIMU_ERR_INVALID, "HubbardMom1D needs at least 3 modes");
-    { // the device decoders index off-diagonals with 32-bit arithmetic
-        double n1 = d->num_particles[0], n2 = d->num_particles[1], m = M, lmax = 0;
-        if (hk == HK_MOM1D_BOSE) lmax = n1 * (n1 - 1) * (m - 2) + n1 * (m - 1);
-        else if (hk == HK_TC_F2C) lmax = n1 * n2 * (m - 1) + (n1 * (n1 - 1) * n2 + n2 * (n2 - 1) * n1) * m * m;
-        else if (hk == HK_MOM1D_F2C) lmax = n1 * n2 * (m - 1);
-        else lmax = (n1 + n2) * 6;
-        if (lmax >= 2147483648.0) return fail(RIMU_ERR_INVALID, "more than 2^31 off-diagonals per address are unsupported");
-    }
+    HamHostImage img; // validation + scalars + constant tables: pure host code (ham_host.h), also what the CPU tests check
+    if (ham_build_host(d, &img)) return fail(RIMU_ERR_INVALID, "%s", img.error.c_str());
     rimu_ham *h = new rimu_ham();
     memset(h, 0, sizeof(*h));
-    h->desc = *d; h->hk = hk;
+    h->desc = *d; h->hk = img.hk; h->W = img.W;
     static u64 next_uid = 1;
     h->uid = next_uid++;
-    h->W = (kind == RIMU_ADDR_BOSE) ? ((bits + 1 + 63) / 64) : 1;
-    CUDA_TRY(cudaGetDevice(&h->device));
-    HamDev &v = h->dev;
-    v.hk = hk; v.M = M; v.N0 = d->num_particles[0]; v.N1 = d->num_particles[1];
-    v.ndim = d->ndim; v.nnb = 2 * d->ndim; v.cutoff = d->cutoff; v.three_body = d->three_body_term; v.has_pot = d->has_potential;
-    v.u = d->u; v.t = d->t; v.v = d->v; v.tc0 = d->t_comp[0]; v.tc1 = d->t_comp[1];
-    v.u00 = d->u_mat[0]; v.u10 = d->u_mat[1];
-    v.u_2m = d->u / (2 * M); v.u_m = d->u / M;
-    v.variant = model == RIMU_HUBBARD_REAL_1D_EP ? 1 : model == RIMU_EXTENDED_HUBBARD_REAL_1D ? 2 : 0;
-    v.bc = d->boundary_condition;
-    if (v.variant == 2 && (v.bc < 0 || v.bc > 2)) { delete h; return fail(RIMU_ERR_INVALID, "invalid boundary condition"); }
-    int nz = 0;
-    for (int i = 0; i < d->num_components * d->num_components; i++) nz += d->u_mat[(i % d->num_components) + 2 * (i / d->num_components)] != 0.0;
-    v.umat_zero = nz == 0;
-    // device tables: kes | ws | us | pot
-    std::vector<double> tab(3 * RIMU_MAX_TABLE_MODES + 2 * RIMU_MAX_MODES);
-    memcpy(&tab[0], d->kes, sizeof(d->kes));
-    memcpy(&tab[RIMU_MAX_TABLE_MODES], d->ws, sizeof(d->ws));
-    memcpy(&tab[2 * RIMU_MAX_TABLE_MODES], d->us, sizeof(d->us));
-    memcpy(&tab[3 * RIMU_MAX_TABLE_MODES], d->potential, sizeof(d->potential));
-    CUDA_TRY(rimu_malloc(&h->d_tables, tab.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(h->d_tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-    v.kes = h->d_tables; v.ws = h->d_tables + RIMU_MAX_TABLE_MODES; v.us = h->d_tables + 2 * RIMU_MAX_TABLE_MODES;
-    v.pot = h->d_tables + 3 * RIMU_MAX_TABLE_MODES;
-    if (model == RIMU_HUBBARD_REAL_SPACE) {
-        if (d->ndim < 1 || d->ndim > 3) { delete h; return fail(RIMU_ERR_INVALID, "geometry must have 1..3 dimensions"); }
-        int prod = 1;
-        for (int k = 0; k < d->ndim; k++) prod *= d->dims[k];
-        if (prod != M) { delete h; return fail(RIMU_ERR_INVALID, "`geometry` does not have the correct number of sites"); }
-        std::vector<unsigned char> nbr((size_t)M * v.nnb);
-        for (int s = 1; s <= M; s++)
-            for (int c = 1; c <= v.nnb; c++) nbr[(size_t)(s - 1) * v.nnb + (c - 1)] = (unsigned char)neighbor_site_host(d, s, c);
-        CUDA_TRY(rimu_malloc(&h->d_nbr, nbr.size()));
-        CUDA_TRY(cudaMemcpy(h->d_nbr, nbr.data(), nbr.size(), cudaMemcpyHostToDevice));
-        v.nbr = h->d_nbr;
+    h->dev = img.dev;
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e == cudaSuccess) e = rimu_malloc(&h->d_tables, img.tables.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, img.tables.data(), img.tables.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !img.nbr.empty()) {
+        e = rimu_malloc(&h->d_nbr, img.nbr.size());
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_nbr, img.nbr.data(), img.nbr.size(), cudaMemcpyHostToDevice);
     }
+    if (e != cudaSuccess) {
+        cudaFree(h->d_tables); cudaFree(h->d_nbr);
+        delete h;
+        cudaGetLastError();
+        return fail(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? RIMU_ERR_NO_DEVICE : RIMU_ERR_CUDA,
+                    "rimu_ham_create: %s", cudaGetErrorString(e));
+    }
+    ham_set_tables(&h->dev, h->d_tables, h->d_nbr);
     *out = h;
     return 0;
 }

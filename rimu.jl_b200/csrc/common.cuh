@@ -81,7 +81,9 @@ HD u64 splitmix64(u64 x) {
 }
 
 // ---------------------------------------------------------------- bit utilities (device)
-#ifdef __CUDACC__
+// RIMU_HOST_EMULATION: tests/cuda/host_ham.cpp compiles this section and hamiltonians.cuh with g++ (the CUDA intrinsics are
+// supplied by that file) so that the address arithmetic of the kernels can be checked against the oracle without a GPU.
+#if defined(__CUDACC__) || defined(RIMU_HOST_EMULATION)
 template <int W> struct BitsT;
 template <> struct BitsT<1> { typedef u64 type; };
 template <> struct BitsT<2> { typedef u128 type; };

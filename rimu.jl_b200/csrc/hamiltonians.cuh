@@ -35,7 +35,7 @@ struct HamDev {
     const unsigned char *nbr;          // HubbardRealSpace: nbr[(site-1)*nnb + dir] = neighbour site (1-based) or 0
 };
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(RIMU_HOST_EMULATION)
 // exact x / d for x < 2^21, 0 < d < 2^10 (off-diagonal index decoding): (x + 0.5) / d is at least 0.5/d away from
 // an integer, far more than the float rounding error at these magnitudes, so truncation gives floor(x / d)
 DEV unsigned udiv_small(unsigned x, unsigned d) { return (unsigned)__float2uint_rz(((float)x + 0.5f) * __frcp_rn((float)d)); }

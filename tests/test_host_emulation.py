@@ -1,0 +1,102 @@
+"""The DEVICE address arithmetic checked on the CPU: rimu.jl_b200/csrc/{common,hamiltonians}.cuh and the host half of
+rimu_ham_create (csrc/ham_host.h) are compiled with g++ (tests/cuda/host_ham.cpp supplies the few CUDA intrinsics) and
+compared element by element with the ONR-based oracle -- diagonal_element, num_offdiagonals and EVERY get_offdiagonal(i)
+of sampled addresses for every model case, plus exhaustive checks of the two primitives everything leans on (rank/select,
+float-reciprocal division).  The same comparison runs on the GPU in tests/test_gpu_parity.py::test_hamiltonian_elements;
+this one needs no device, so the kernels' arithmetic is under test in the CPU suite as well.  (Floating point: g++ is run with
+-ffp-contract=off, nvcc with --fmad=false; sqrt and division are IEEE-exact on both.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.cases import SPECS, oracle_ham, product_ham, sample_keys
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so, src = os.path.join(HERE, "libhost_ham.so"), os.path.join(HERE, "host_ham.cpp")
+    deps = [src] + [os.path.join(ROOT, "rimu.jl_b200", "csrc", f) for f in ("common.cuh", "hamiltonians.cuh", "ham_host.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I/usr/local/cuda/include",
+                        src, "-o", so], check=True, capture_output=True)
+    L = C.CDLL(so)
+    u64p = C.POINTER(C.c_uint64)
+    L.emu_ham_create.restype, L.emu_ham_create.argtypes = C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+    L.emu_ham_destroy.argtypes = [C.c_void_p]
+    L.emu_ham_words.restype, L.emu_ham_words.argtypes = C.c_int, [C.c_void_p]
+    L.emu_diagonal.restype, L.emu_diagonal.argtypes = C.c_double, [C.c_void_p, u64p]
+    L.emu_num_offdiagonals.restype, L.emu_num_offdiagonals.argtypes = C.c_longlong, [C.c_void_p, u64p]
+    L.emu_offdiagonal.restype, L.emu_offdiagonal.argtypes = C.c_double, [C.c_void_p, u64p, C.c_longlong, u64p]
+    L.emu_select64.restype, L.emu_select64.argtypes = C.c_int, [C.c_uint64, C.c_int]
+    L.emu_udiv_small.restype, L.emu_udiv_small.argtypes = C.c_uint, [C.c_uint, C.c_uint]
+    return L
+
+
+def test_select_and_small_division_exhaustive(emu):
+    rng = np.random.default_rng(0)
+    words = [0x1, 0x8000000000000000, 0xFFFFFFFFFFFFFFFF, 0x5555555555555555, 0xF0F0F0F00F0F0F0F] + \
+        [int(x) for x in rng.integers(1, 2 ** 63, size=300, dtype=np.uint64)]
+    for w in words:
+        pos = [i for i in range(64) if (w >> i) & 1]
+        for k in range(len(pos)):
+            assert emu.emu_select64(w, k) == pos[k]
+    # udiv_small is specified for x < 2^21, 0 < d < 2^10: all divisors, a dense sweep of dividends including every boundary
+    for d in range(1, 1024):
+        xs = np.unique(np.concatenate([np.arange(0, 4096), np.arange(d - 2 if d > 2 else 0, 2 ** 21, d)[:3000],
+                                       np.arange(d - 1, 2 ** 21, d)[:3000], np.arange(2 ** 21 - 2048, 2 ** 21)]))
+        for x in xs[::7] if d > 64 else xs:
+            assert emu.emu_udiv_small(int(x), d) == int(x) // d, (x, d)
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_device_hamiltonian_code_matches_oracle_on_the_host(built, emu, name):
+    oh, ph = oracle_ham(name), product_ham(name)  # ph only supplies the rimu_ham_desc the product would hand to rimu_ham_create
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    assert emu.emu_ham_create(C.byref(ph.desc), C.byref(h), err, 512) == 0, err.value
+    W = emu.emu_ham_words(h)
+    assert W == oh.W
+    keys = sample_keys(oh, 16, seed=2)
+    u64p = C.POINTER(C.c_uint64)
+    out = (C.c_uint64 * 2)()
+    checked = 0
+    for key in keys:
+        kt = tuple(int(x) for x in key)
+        kin = (C.c_uint64 * 2)(*(list(kt) + [0] * (2 - len(kt))))
+        assert emu.emu_diagonal(h, C.cast(kin, u64p)) == oh.diagonal_element(kt), (name, "diagonal", kt)
+        L = oh.num_offdiagonals(kt)
+        assert emu.emu_num_offdiagonals(h, C.cast(kin, u64p)) == L
+        idx = range(1, L + 1) if L <= 1500 else list(range(1, 700)) + list(range(L - 800, L + 1)) + list(range(700, L - 800, max(1, L // 600)))
+        for i in idx:
+            ok, ov = oh.get_offdiagonal(kt, i)
+            v = emu.emu_offdiagonal(h, C.cast(kin, u64p), i - 1, C.cast(out, u64p))
+            assert v == ov, (name, kt, i, v, ov)
+            if ov != 0.0:
+                assert tuple(int(out[j]) for j in range(W)) == tuple(ok), (name, kt, i)
+            checked += 1
+    assert checked > 0
+    emu.emu_ham_destroy(h)
+
+
+def test_host_validation_errors(emu):
+    """rimu_ham_create's argument checks live in ham_host.h: exercised here without a device."""
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+    h, err = C.c_void_p(), C.create_string_buffer(512)
+    d = _lib.HamDesc()
+    d.model, d.addr_kind, d.num_modes, d.num_components = _lib.TRANSCORRELATED_1D, _lib.ADDR_BOSE, 4, 1
+    d.num_particles[0] = 4
+    assert emu.emu_ham_create(C.byref(d), C.byref(h), err, 512) == _lib.ERR_INVALID and b"not implemented" in err.value
+    d.model, d.num_modes = _lib.HUBBARD_MOM_1D, 2
+    assert emu.emu_ham_create(C.byref(d), C.byref(h), err, 512) == _lib.ERR_INVALID and b"at least 3 modes" in err.value
+    d.model, d.num_modes, d.ndim = _lib.HUBBARD_REAL_SPACE, 6, 2
+    d.dims[0], d.dims[1] = 2, 2
+    assert emu.emu_ham_create(C.byref(d), C.byref(h), err, 512) == _lib.ERR_INVALID and b"correct number of sites" in err.value
+    d.model, d.boundary_condition = _lib.EXTENDED_HUBBARD_REAL_1D, 7
+    assert emu.emu_ham_create(C.byref(d), C.byref(h), err, 512) == _lib.ERR_INVALID and b"boundary" in err.value
