@@ -7,23 +7,30 @@
 //   walker vector : dense SoA (keys[n][W], vals[n]) that is SEGMENTED by bucket: the entries of bucket b
 //                   are contiguous at [seg_start[b], seg_start[b]+seg_len[b]).  bucket(addr) is a fastrange
 //                   of the address hash, so a determinant always lives in the same bucket.
-//   K1 spawn      : one CTA per chunk of 256 parents; attempt counts are scanned inside the CTA and the
-//                   attempts are spread over its threads (one thread per spawn attempt).  Every non-zero
-//                   spawn is appended to the record stream of the CHILD's bucket (one 16/24-byte store and
-//                   one counter atomic).  Parents with more than HEAVY_T attempts go to a queue.
+//   record streams: rec[bucket][sub-stream][rcap] of 16-byte (W=1) / 32-byte (W=2) {address, value} records.  One
+//                   sub-stream per (source rank, initiator lane): a sender owns the positions it writes, and the lane
+//                   of a deposit (DictVectors/initiators.jl:22-45) is the stream index, never part of the record.
+//   K1 spawn      : one CTA per chunk of 256 parents (the next chunk's parents are loaded meanwhile); attempt counts are
+//                   scanned inside the CTA and the attempts are spread over its threads (one thread per spawn attempt).
+//                   Every non-zero spawn is appended to the record stream of the CHILD's bucket: one counter atomic and
+//                   ONE 16-byte store (two for W=2).  Children owned by another GPU are bucketed the same way into local
+//                   staging streams.  Parents with more than HEAVY_T attempts go to a queue.
 //   K2 heavy      : queue items are cut into tiles of HEAVY_TILE attempts, one CTA per tile; stochastic
 //                   spawns of one parent are pre-summed per off-diagonal index in shared memory, so a
 //                   determinant with 10^6 walkers emits at most L records per tile.
+//   push (multi-GPU): one warp per (destination rank, lane, bucket) run copies the staged records into sub-stream
+//                   [bucket][this rank, lane] of the OWNER's streams (peer stores over NVLink) and writes its fill.
 //   K3 merge      : one CTA per bucket stages the bucket's parents (applying the diagonal step,
-//                   spawning.jl:73-93) and its spawn records in shared memory, annihilates them there
-//                   (open addressing on 16-bit item indices, claimed by plain stores in barrier-separated
-//                   rounds -- no 64-bit shared atomics except for genuine duplicates), applies
-//                   ThresholdCompression (compression.jl:18-26) and appends the survivors to the target
-//                   vector, which is thereby segmented again.  walkernumber/length and the step statistics
-//                   are reduced in the same pass (pdvec.jl:896-902).
+//                   spawning.jl:73-93) and the records of all its sub-streams in shared memory (metadata two buckets
+//                   ahead, next bucket bulk-prefetched into L2), annihilates them there (open addressing on item
+//                   indices claimed with 32-bit shared CAS; 64-bit shared adds only for genuine duplicates),
+//                   collapses the initiator lanes (from_initiator_value), applies ThresholdCompression
+//                   (compression.jl:18-26) as a dense pass and appends the survivors to the target vector, which is
+//                   thereby segmented again.  walkernumber/length and the step statistics are reduced in the same
+//                   pass (pdvec.jl:896-902).
 //
 // Algorithmic HBM bytes per step with P parents, A' records, U survivors, E = 8W+8:
-//   K1: P*E read + A'*E written;  K3: P*E + A'*E read, U*E written.
+//   K1: P*E read + A'*E written;  K3: P*(E+8) + A'*E read, U*(E+8) written (+8: cached diagonal elements).
 #pragma once
 #include "kernels.cuh"
 
