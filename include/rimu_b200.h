@@ -152,6 +152,9 @@ int rimu_sizeof_step_stats(void);
 /* table_slots: capacity of the working table in slots (rounded up to a power of two);
  * words: uint64 words per address (1 or 2). */
 int rimu_ctx_create(int device, int words, uint64_t table_slots, rimu_ctx **out);
+/* Frees the working memory.  Vectors created on the context may be destroyed afterwards (host finalizers run in any
+ * order): the context's bookkeeping lives on until the last of them is gone; any other call on such a vector fails with
+ * RIMU_ERR_INVALID. */
 int rimu_ctx_destroy(rimu_ctx *ctx);
 int rimu_ctx_synchronize(rimu_ctx *ctx);
 /* Make the context's GPU the calling thread's current CUDA device (rimu_ham_create places its tables on the current
@@ -177,12 +180,15 @@ int rimu_host_free(void *p);
 int rimu_comm_unique_id(void *id128);               /* ncclGetUniqueId; broadcast by the host launcher */
 int rimu_comm_init(rimu_ctx *ctx, const void *id128, int rank, int nranks, uint64_t exchange_records_per_peer);
 int rimu_comm_rank(rimu_ctx *ctx, int *rank, int *nranks);
-/* after RIMU_ERR_EXCHANGE_FULL (reported identically on every rank): *needed = largest per-peer record count
- * seen; every rank then calls rimu_comm_reserve with the same larger size and repeats the step */
+/* staged exchange only: after RIMU_ERR_EXCHANGE_FULL (reported identically on every rank) *needed = largest per-peer
+ * record count seen; every rank then calls rimu_comm_reserve with the same larger size and repeats the step.  The direct
+ * exchange sizes its streams itself. */
 int rimu_comm_capacity(rimu_ctx *ctx, uint64_t *per_peer_out, uint64_t *needed_out);
 int rimu_comm_reserve(rimu_ctx *ctx, uint64_t exchange_records_per_peer);
-/* 1 when the spawn exchange goes peer-direct (the spawn kernels store records straight into the owner's receive
- * buffer through NVLink peer memory mapped with CUDA IPC); 0 = NCCL grouped send/recv (RIMU_B200_P2P=0 forces it) */
+/* 1 when the spawn exchange is direct: records are bucketed by the sender and pushed straight into the owner's bucket
+ * sub-streams through NVLink peer memory mapped with CUDA IPC (no receive pass); 0 = staged exchange with NCCL grouped
+ * send/recv (RIMU_B200_P2P=0 forces it).  Replaces the choice between the reference's AllToAll / PointToPoint / OneSided
+ * communicators (communicators.jl:107-131). */
 int rimu_comm_p2p(rimu_ctx *ctx, int *enabled_out);
 int rimu_comm_allreduce_f64(rimu_ctx *ctx, double *host_inout, int n);
 /* owner rank of an address: communicators.jl:77-81 target_segment */
@@ -238,8 +244,9 @@ int rimu_vec_axpby(double alpha, rimu_vec *x, double beta, rimu_vec *y, rimu_vec
 
 /* annihilation of a given spawn list (the "sum by key, drop zeros" core of
  * collect_local!/move_and_compress!, pdworkingmemory.jl:228-273).
- * method: RIMU_ANNIHILATE_HASH (open-addressing HBM table) or RIMU_ANNIHILATE_SORT
- * (radix sort + segmented reduce; deterministic summation order). Host arrays in. */
+ * method: RIMU_ANNIHILATE_HASH (open-addressing HBM table), RIMU_ANNIHILATE_SORT (radix sort + segmented reduce;
+ * deterministic summation order; one-word addresses) or RIMU_ANNIHILATE_PARTITION (bucket streams + shared-memory
+ * merge, what rimu_step uses; measured comparison in profiles/r1_annihilation_methods.md). Host arrays in. */
 int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *vals, int64_t n, int method);
 /* same with the spawn list already resident in HBM (device pointers), for measurement */
 int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, const void *d_vals, int64_t n, int method,
