@@ -76,7 +76,9 @@ def test_bhm_example_pinned_energy(built):
 @pytest.mark.parametrize("name,style_name,walkers,dtau,steps", [
     ("real1d_10", "int", 10_000, 0.002, 4000),    # BASELINE config 1
     ("mom1d_bose", "semi", 2_000, 0.002, 4000),
-    ("rs_f2c_4x4", "semi", 3_000, 0.005, 4000),    # 2D Fermi-Hubbard, 2 up 2 down (sign problem mild at this size)
+    ("rs_f2c_4x4", "semi", 20_000, 0.005, 4000),   # 2D Fermi-Hubbard, 2 up 2 down, dim 14 400.  (With 3 000 walkers the shift sits
+                                                    # 1.1 % BELOW E0 -- sign-problem/population bias, measured with the oracle for three
+                                                    # seeds -- which left the 1 % + 5 sigma allowance a margin of only 1.5x.)
 ])
 def test_fciqmc_energy_within_error_bars(built, name, style_name, walkers, dtau, steps):
     import rimu_b200 as R
