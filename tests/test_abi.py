@@ -77,3 +77,19 @@ def test_host_side_helpers_match_oracle(built):
     z4, z2 = (C.c_uint32 * 4)(0, 0, 0, 0), (C.c_uint32 * 2)(0, 0)
     L.rimu_philox4x32_10(z4, z2, out)
     assert tuple(out) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)  # Random123 known answer
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under rimu.jl_b200/ (Python or CUDA sources) may import, link or mention
+    loading it, and the product library must not link the oracle's shared object."""
+    import subprocess
+    pkg = os.path.join(ROOT, "rimu.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            src = open(os.path.join(dirpath, f), errors="ignore").read()
+            assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+    from rimu_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
