@@ -22,6 +22,7 @@ from .stochasticstyles import (IsDeterministic, IsDynamicSemistochastic, IsStoch
 from .dictvectors import (DVec, FirstOrderTransitionOperator, FrozenDVec, GPUDVec, InitiatorDVec, PDVec, WorkingMemory, apply_operator, dot, mul,
                           walkernumber_and_length, working_memory)
 from .fciqmc import (DataFrame, DontUpdate, DoubleLogUpdate, DoubleLogUpdateAfterTargetWalkers, LogUpdate,
+                     LogUpdateAfterTargetWalkers,
                      PMCSimulation, ProjectedEnergy, Projector, ProjectorMonteCarloProblem, ShiftParameters,
                      SingleState, Timer, default_starting_vector, init, solve, solve_, step_)
 from .statstools import blocking_analysis, projected_energy, ratio_of_means, shift_estimator

@@ -58,6 +58,20 @@ class LogUpdate:
 
 
 @dataclass
+class LogUpdateAfterTargetWalkers:
+    """shiftstrategy.jl:100-122: LogUpdate that switches on once the walker number exceeds the target."""
+    target_walkers: float = 1000
+    zeta: float = 0.08
+
+    def update(self, sp, tnorm):
+        if sp.shift_mode or tnorm > self.target_walkers:
+            sp.shift_mode = True
+            sp.shift -= self.zeta / sp.time_step * math.log(tnorm / sp.pnorm)
+        sp.pnorm = tnorm
+        return {"shift": sp.shift, "norm": tnorm, "shift_mode": sp.shift_mode}, True
+
+
+@dataclass
 class DoubleLogUpdate:
     """shiftstrategy.jl:160-181"""
     target_walkers: float = 1000

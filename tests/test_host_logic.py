@@ -97,6 +97,16 @@ def test_shift_strategies(built):
     assert sp.shift == 1.0 and not sp.shift_mode
     st.update(sp, 1500.0)
     assert sp.shift_mode and sp.shift != 1.0
+    # LogUpdateAfterTargetWalkers (shiftstrategy.jl:100-122): frozen shift below the target, LogUpdate afterwards, for good
+    sp = R.ShiftParameters(2.0, 100.0, 0.01)
+    lt = R.LogUpdateAfterTargetWalkers(target_walkers=1000, zeta=0.05)
+    lt.update(sp, 800.0)
+    assert sp.shift == 2.0 and sp.pnorm == 800.0 and not sp.shift_mode
+    lt.update(sp, 1200.0)
+    assert sp.shift_mode and sp.shift == 2.0 - 0.05 / 0.01 * math.log(1200 / 800)
+    before = sp.shift
+    lt.update(sp, 900.0)  # stays in shift mode below the target
+    assert sp.shift == before - 0.05 / 0.01 * math.log(900 / 1200)
 
 
 def test_blocking_analysis(built):
