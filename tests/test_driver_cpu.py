@@ -1,0 +1,175 @@
+"""The host driver above the C ABI -- ProjectorMonteCarloProblem / init / step! / solve, the shift strategies, the report
+assembly and the abort rules (mirror of pmc_simulation.jl:88-174,265-452 and fciqmc.jl:126-181) -- run on the CPU against a
+stand-in for the device: a vector class and an `apply_operator` that execute the ORACLE step.  Nothing of this touches the
+product's compute path (that is what the GPU tests are for); it keeps the driver logic under test in the CPU suite.
+The same runs through the real device are tests/test_gpu_energies.py."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.cases import oracle_ham, product_ham
+
+
+class _Ctx:
+    nranks = 1
+
+
+class FakeDVec:
+    """host stand-in with the GPUDVec surface the driver uses"""
+
+    def __init__(self, pairs=None, *, style=None, address_type=None, capacity=0, ctx=None, initiator=None, initiator_threshold=None):
+        import rimu_b200 as R
+        from rimu_b200.stochasticstyles import as_initiator_rule
+        items = list(pairs or [])
+        self.style = style or R.IsDynamicSemistochastic()
+        self.address_type = address_type or items[0][0].address_type
+        self.ctx, self.initiator = ctx or _Ctx(), as_initiator_rule(initiator, initiator_threshold)
+        self.dtype = np.int64 if self.style.val_type == R._lib.VAL_I64 else np.float64
+        W = self.address_type.words
+        self.keys = np.array([np.atleast_1d(a.key()) for a, _ in items], dtype=np.uint64).reshape(-1, W)
+        self.vals = np.array([v for _, v in items], dtype=self.dtype)
+
+    def __len__(self):
+        return len(self.vals)
+
+    def similar(self, style=None):
+        return FakeDVec(style=style or self.style, address_type=self.address_type, ctx=self.ctx, initiator=self.initiator)
+
+    zerovector = similar
+
+    def copy(self):
+        out = self.similar()
+        out.keys, out.vals = self.keys.copy(), self.vals.copy()
+        return out
+
+    def copy_from(self, other):
+        self.keys, self.vals = other.keys.copy(), other.vals.astype(self.dtype)
+        return self
+
+    def norm(self, p=2):
+        a = np.abs(self.vals.astype(float))
+        return float(a.sum()) if p == 1 else float(np.sqrt((a * a).sum())) if p == 2 else float(a.max(initial=0.0))
+
+    def walkernumber(self):
+        return self.norm(1)
+
+    def dot(self, other):
+        d = {tuple(k): v for k, v in zip(other.keys.tolist(), other.vals.tolist())}
+        return float(sum(v * d.get(tuple(k), 0.0) for k, v in zip(self.keys.tolist(), self.vals.tolist())))
+
+    def freeze(self):
+        return self.copy()
+
+
+@pytest.fixture
+def cpu_device(monkeypatch):
+    """route the driver's vector class and apply_operator to the oracle"""
+    import rimu_b200 as R
+    from rimu_b200 import _lib, dictvectors, fciqmc
+    registry = {}
+
+    def fake_apply_operator(wm, target, source, op, boost=1.0, table_slots=0):
+        assert target is not source
+        if isinstance(op, R.FirstOrderTransitionOperator):
+            ham, plain, shift, dt = op.hamiltonian, False, op.shift, op.time_step
+        else:
+            ham, plain, shift, dt = op, True, 0.0, 0.0
+        oh = registry[id(ham)]
+        p = _lib.StepParams()
+        wm.style.fill(p)
+        rule = wm.initiator
+        pp = orc.make_params(p.style, shift=shift, dtau=dt, boost=boost, plain_h=plain, proj_threshold=p.proj_threshold,
+                             rel_threshold=p.rel_threshold, abs_threshold=p.abs_threshold, compress_threshold=p.compress_threshold,
+                             key=orc.step_key(wm.seed, wm.counter), initiator_rule=rule.rule_id, initiator_threshold=rule.threshold)
+        ko, vo, st = oh.step(pp, source.keys, source.vals)
+        target.keys, target.vals = ko.reshape(len(vo), -1), vo
+        s = _lib.StepStats()
+        for f in ("exact_steps", "inexact_steps", "spawn_attempts", "len_before", "spawns", "deaths", "clones", "zombies", "norm1",
+                  "ispawns", "ideaths", "iclones", "izombies", "inorm1"):
+            setattr(s, f, getattr(st, f))
+        s.len = st.len_after
+        wm.counter += 1
+        wm.last_stats = s
+        names, values = wm.style.stat_names, wm.style.stats(s)
+        if isinstance(getattr(wm.style, "compression", None), R.ThresholdCompression):
+            names, values = names + ("len_before",), values + (s.len_before,)
+        return names, values, wm, target
+
+    def fake_dot(x, *args):
+        if len(args) == 1:
+            return x.dot(args[0])
+        op, y = args
+        oh = registry[id(op)]
+        ko, vo, _ = oh.step(orc.make_params(orc.STYLE_DETERMINISTIC, plain_h=True), y.keys, y.vals.astype(np.float64))
+        tmp = y.similar()
+        tmp.keys, tmp.vals = ko.reshape(len(vo), -1), vo
+        return x.dot(tmp)
+
+    for mod in (fciqmc, dictvectors):
+        monkeypatch.setattr(mod, "GPUDVec", FakeDVec)
+        monkeypatch.setattr(mod, "apply_operator", fake_apply_operator)
+        monkeypatch.setattr(mod, "dot", fake_dot)
+    monkeypatch.setattr(R, "GPUDVec", FakeDVec)
+
+    def make(name):
+        oh, ph = oracle_ham(name), product_ham(name)
+        registry[id(ph)] = oh
+        return oh, ph
+    return make
+
+
+def test_solve_reproduces_the_bhm_example_on_the_cpu(built, cpu_device):
+    """scripts/BHM-example.jl through the Python driver (oracle step underneath): columns, shift mode, energy."""
+    import rimu_b200 as R
+    oh, ph = cpu_device("real1d_6")
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=R.IsDynamicSemistochastic(), time_step=0.001, last_step=3000,
+                                        target_walkers=1000, random_seed=17)
+    sim = R.init(prob)
+    assert sim.state.shift_parameters.shift == oh.diagonal_element(oh.start_key)  # Rayleigh quotient of the start vector (fciqmc.jl:51-61)
+    assert sim.state.shift_parameters.pnorm == 10.0                              # default_starting_vector: address => 10
+    R.step_(sim)
+    assert sim.step == 1 and not sim.success
+    R.solve_(sim)
+    assert sim.success and sim.step == 3000 and not sim.aborted
+    df = sim.dataframe()
+    assert list(df.columns[:4]) == ["step", "len", "shift", "norm"]
+    for col in ("exact_steps", "inexact_steps", "spawn_attempts", "spawns", "len_before"):  # styles.jl:203-209 + compression.jl:16
+        assert col in df.columns
+    assert len(df) == 3000 and df["step"].iloc[-1] == 3000
+    se = R.shift_estimator(df, skip=1000)
+    assert abs(se.mean - (-4.0215)) < 5 * se.err + 0.04
+    assert abs(np.asarray(df["norm"])[1500:].mean() - 1000) < 100
+    # solve! continues when last_step is raised (pmc_simulation.jl:400-452)
+    R.solve_(sim, last_step=3010)
+    assert sim.step == 3010 and len(sim.dataframe()) == 3010
+
+
+def test_driver_options_on_the_cpu(built, cpu_device):
+    import rimu_b200 as R
+    oh, ph = cpu_device("real1d_6")
+    # integer walkers: the norm fed to the shift strategy is the exact integer walker number; reporting_interval thins the report
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=R.IsStochasticInteger(), time_step=0.01, last_step=200,
+                                        target_walkers=500, random_seed=3, reporting_interval=10)
+    sim = R.solve(prob)
+    df = sim.dataframe()
+    assert sim.success and len(df) == 20 and list(df["step"][:3]) == [10, 20, 30]
+    assert all(float(n).is_integer() for n in df["norm"])
+    for col in ("spawn_attempts", "spawns", "deaths", "clones", "zombies"):  # styles.jl:14-20
+        assert col in df.columns
+    # max_length aborts (fciqmc.jl:172-179)
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, time_step=0.01, last_step=500, target_walkers=5000, max_length=20,
+                                        random_seed=3)
+    sim = R.solve(prob)
+    assert sim.aborted and not sim.success and "Aborted in step" in sim.message and sim.step < 500
+    # an explicit shift, DontUpdate and the initiator keyword reach the state
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, shift=-1.5, shift_strategy=R.DontUpdate(), last_step=5, random_seed=1,
+                                        initiator=R.CoherentInitiator(2.0))
+    sim = R.solve(prob)
+    assert set(sim.dataframe()["shift"]) == {-1.5}
+    assert sim.state.v.initiator == R.CoherentInitiator(2.0) and sim.state.wm.initiator == R.CoherentInitiator(2.0)
+    # wall time
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, last_step=10 ** 9, random_seed=1, wall_time=0.2)
+    sim = R.solve(prob)
+    assert sim.aborted and sim.message == "Wall time reached."
