@@ -62,6 +62,19 @@ class FakeDVec:
     def freeze(self):
         return self.copy()
 
+    def scale_(self, alpha):
+        self.vals = self.vals * alpha
+        return self
+
+    def add_(self, other, alpha=1.0):
+        d = {tuple(k): v for k, v in zip(self.keys.tolist(), self.vals.tolist())}
+        for k, v in zip(other.keys.tolist(), other.vals.tolist()):
+            d[tuple(k)] = d.get(tuple(k), 0.0) + alpha * v
+        items = sorted((k, v) for k, v in d.items() if v != 0.0)
+        self.keys = np.array([k for k, _ in items], dtype=np.uint64).reshape(-1, self.address_type.words)
+        self.vals = np.array([v for _, v in items], dtype=self.dtype)
+        return self
+
 
 @pytest.fixture
 def cpu_device(monkeypatch):
@@ -107,6 +120,17 @@ def cpu_device(monkeypatch):
         tmp.keys, tmp.vals = ko.reshape(len(vo), -1), vo
         return x.dot(tmp)
 
+    def fake_mul(y, op, x, wm=None):
+        oh = registry[id(op)]
+        ko, vo, _ = oh.step(orc.make_params(orc.STYLE_DETERMINISTIC, plain_h=True), x.keys, x.vals.astype(np.float64))
+        y.keys, y.vals = ko.reshape(len(vo), -1), vo
+        return y
+
+    from rimu_b200 import lanczos
+    for mod in (lanczos,):
+        monkeypatch.setattr(mod, "GPUDVec", FakeDVec)
+        monkeypatch.setattr(mod, "mul", fake_mul)
+        monkeypatch.setattr(mod, "WorkingMemory", lambda v, seed=0: None)
     for mod in (fciqmc, dictvectors):
         monkeypatch.setattr(mod, "GPUDVec", FakeDVec)
         monkeypatch.setattr(mod, "apply_operator", fake_apply_operator)
@@ -173,3 +197,17 @@ def test_driver_options_on_the_cpu(built, cpu_device):
     prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, last_step=10 ** 9, random_seed=1, wall_time=0.2)
     sim = R.solve(prob)
     assert sim.aborted and sim.message == "Wall time reached."
+
+
+@pytest.mark.parametrize("name", ["real1d_6", "mom1d_bose", "rs_fermi", "ext1d"])
+def test_lanczos_driver_on_the_cpu(built, cpu_device, name):
+    """eigsolve_lanczos (the KrylovKit stand-in of config 3, ext/KrylovKitExt.jl:23-46) over the oracle's H*v: restarts,
+    full reorthogonalisation and the Ritz-vector assembly reproduce the exact-diagonalisation energy."""
+    import rimu_b200 as R
+    from tests.test_gpu_energies import exact_energy
+    oh, ph = cpu_device(name)
+    start = FakeDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    vals, vecs, info = R.eigsolve_lanczos(ph, start, krylovdim=40, tol=1e-10, maxiter=40, full_reorth=True)
+    assert info["converged"], info
+    assert math.isclose(vals[0], exact_energy(oh), rel_tol=1e-9, abs_tol=1e-9)
+    assert math.isclose(vecs[0].norm(2), 1.0, rel_tol=1e-6)
