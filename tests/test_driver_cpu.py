@@ -211,3 +211,20 @@ def test_lanczos_driver_on_the_cpu(built, cpu_device, name):
     assert info["converged"], info
     assert math.isclose(vals[0], exact_energy(oh), rel_tol=1e-9, abs_tol=1e-9)
     assert math.isclose(vecs[0].norm(2), 1.0, rel_tol=1e-6)
+
+
+def test_projected_energy_post_step_on_the_cpu(built, cpu_device):
+    """ProjectedEnergy (poststepstrategy.jl:82-121): vproj = projector . v, hproj = (H projector) . v; their ratio of means
+    estimates the energy (StatsTools/ratio_of_means.jl).  Integer and Float64 walkers."""
+    import rimu_b200 as R
+    oh, ph = cpu_device("real1d_6")
+    for style in (R.IsDynamicSemistochastic(), R.IsStochasticInteger()):
+        ref = FakeDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+        prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=style, time_step=0.002, last_step=2500, target_walkers=800,
+                                            random_seed=9, post_step_strategy=(R.ProjectedEnergy(ph, ref), R.Projector(overlap=ref)))
+        sim = R.solve(prob)
+        df = sim.dataframe()
+        assert {"vproj", "hproj", "overlap"} <= set(df.columns)
+        assert np.array_equal(np.asarray(df["vproj"]), np.asarray(df["overlap"]))  # same projector
+        pe = R.projected_energy(df, skip=800)
+        assert pe.success and abs(pe.f - (-4.0215)) < 5 * pe.sigma_f + 0.04, (pe.f, pe.sigma_f)
