@@ -194,8 +194,9 @@ class ProjectorMonteCarloProblem:
                  last_step=100, wall_time=math.inf, target_walkers=1000, zeta=0.08, xi=None, shift_strategy=None,
                  post_step_strategy=(), max_length=None, random_seed=True, reporting_interval=1, metadata=None,
                  n_replicas=1, initiator=False):
-        if n_replicas != 1:
-            raise NotImplementedError("replicas are outside the device path (SURVEY.md section 8e)")
+        if int(n_replicas) < 1:
+            raise ValueError("n_replicas must be at least 1")
+        self.n_replicas = int(n_replicas)  # independent copies of the walker vector, advanced side by side (qmc_states.jl:89-140)
         # initiator=true -> Initiator(threshold 1) (projector_monte_carlo_problem.jl:156-160); a rule object is taken as is
         from .stochasticstyles import as_initiator_rule
         self.initiator = as_initiator_rule(initiator)
@@ -239,9 +240,15 @@ class PMCSimulation:
             shift = dot(vdet, ham, vdet) / vdet.dot(vdet)
         else:
             shift = float(p.shift)
-        sp = ShiftParameters(shift, v.walkernumber(), p.time_step)
-        wm = WorkingMemory(v, seed=p.random_seed)
-        self.state = SingleState(ham, v, v.zerovector(), wm, sp)
+        # replicas: independent vectors with their own shift parameters and random streams; report columns get the suffix
+        # _1, _2, ... when there is more than one (qmc_states.jl:107-140, pmc_simulation.jl:125-146)
+        self.states = []
+        for r in range(p.n_replicas):
+            vr = v if r == 0 else v.copy()
+            seed = p.random_seed if r == 0 else (p.random_seed + 0x9E3779B97F4A7C15 * r) & 0xFFFFFFFFFFFFFFFF
+            self.states.append(SingleState(ham, vr, vr.zerovector(), WorkingMemory(vr, seed=seed),
+                                           ShiftParameters(shift, vr.walkernumber(), p.time_step)))
+        self.state = self.states[0]
         self.step = p.starting_step
         self.report = {}
         self.aborted = False
@@ -258,29 +265,38 @@ class PMCSimulation:
             self.success = True
             return self
         self.step += 1
-        st, p = self.state, self.problem
-        sp = st.shift_parameters
-        T = FirstOrderTransitionOperator(st.hamiltonian, sp.shift, sp.time_step)
-        names, values, wm, pv = apply_operator(st.wm, st.pv, st.v, T)
-        st.v, st.pv = pv, st.v
-        stats = wm.last_stats
-        is_int = st.v.style.val_type == _lib.VAL_I64
-        tnorm = float(stats.inorm1) if is_int else stats.norm1
-        length = stats.len
-        shift_stats, proceed = p.shift_strategy.update(sp, tnorm) if length > 0 else ({"shift": sp.shift, "norm": tnorm}, True)
-        if self.step % p.reporting_interval == 0:
-            row = {"step": self.step, "len": length}
-            row.update(shift_stats)
-            row.update(dict(zip(names, values)))
-            for ps in p.post_step_strategy:
-                row.update(ps(st, self.step))
+        p = self.problem
+        report_now = self.step % p.reporting_interval == 0
+        row = {"step": self.step}
+        dead = too_long = stop = False
+        for r, st in enumerate(self.states):
+            sfx = f"_{r + 1}" if len(self.states) > 1 else ""
+            sp = st.shift_parameters
+            T = FirstOrderTransitionOperator(st.hamiltonian, sp.shift, sp.time_step)
+            names, values, wm, pv = apply_operator(st.wm, st.pv, st.v, T)
+            st.v, st.pv = pv, st.v
+            stats = wm.last_stats
+            is_int = st.v.style.val_type == _lib.VAL_I64
+            tnorm = float(stats.inorm1) if is_int else stats.norm1
+            length = stats.len
+            shift_stats, proceed = p.shift_strategy.update(sp, tnorm) if length > 0 else ({"shift": sp.shift, "norm": tnorm}, True)
+            if report_now:
+                row["len" + sfx] = length
+                row.update({k + sfx: val for k, val in shift_stats.items()})
+                row.update({k + sfx: val for k, val in zip(names, values)})
+                for ps in p.post_step_strategy:
+                    row.update({k + sfx: val for k, val in ps(st, self.step).items()})
+            dead |= length == 0
+            too_long |= length > p.max_length
+            stop |= not proceed
+        if report_now:
             for k, val in row.items():
                 self.report.setdefault(k, []).append(val)
-        if length == 0:
+        if dead:
             self.aborted, self.message = True, f"Aborted in step {self.step}."  # dead population
-        elif length > p.max_length:
+        elif too_long:
             self.aborted, self.message = True, f"Aborted in step {self.step}."  # max_length reached
-        elif not proceed:
+        elif stop:
             self.aborted = True
         elif self.step >= p.last_step:
             self.success = True

@@ -228,3 +228,23 @@ def test_projected_energy_post_step_on_the_cpu(built, cpu_device):
         assert np.array_equal(np.asarray(df["vproj"]), np.asarray(df["overlap"]))  # same projector
         pe = R.projected_energy(df, skip=800)
         assert pe.success and abs(pe.f - (-4.0215)) < 5 * pe.sigma_f + 0.04, (pe.f, pe.sigma_f)
+
+
+def test_replicas_on_the_cpu(built, cpu_device):
+    """n_replicas > 1 (projector_monte_carlo_problem.jl:152,205; qmc_states.jl:89-140): independent vectors and shift
+    parameters, columns suffixed _1, _2, ...; one replica keeps the plain column names and the single-replica trajectory."""
+    import rimu_b200 as R
+    oh, ph = cpu_device("real1d_6")
+    kw = dict(start_at=ph.address, style=R.IsDynamicSemistochastic(), time_step=0.002, last_step=1500, target_walkers=400, random_seed=4)
+    one = R.solve(R.ProjectorMonteCarloProblem(ph, **kw)).dataframe()
+    three = R.solve(R.ProjectorMonteCarloProblem(ph, n_replicas=3, **kw))
+    df = three.dataframe()
+    assert len(three.states) == 3 and "shift" not in df.columns
+    for r in (1, 2, 3):
+        for col in ("len", "shift", "norm", "spawn_attempts", "len_before"):
+            assert f"{col}_{r}" in df.columns
+    assert np.array_equal(np.asarray(df["shift_1"]), np.asarray(one["shift"]))       # replica 1 = the single-replica run (same seed)
+    assert not np.array_equal(np.asarray(df["shift_1"]), np.asarray(df["shift_2"]))  # independent random streams
+    for r in (1, 2, 3):
+        se = R.blocking_analysis(np.asarray(df[f"shift_{r}"]), skip=500)
+        assert abs(se.mean - (-4.0215)) < 5 * se.err + 0.06

@@ -142,8 +142,9 @@ def test_problem_defaults(built):
     assert p.time_step == 0.01 and p.last_step == 100 and p.max_length == 2 * 1000 + 100
     assert isinstance(p.shift_strategy, R.DoubleLogUpdate) and p.shift_strategy.target_walkers == 1000
     assert isinstance(p.style, R.IsDynamicSemistochastic)
-    with pytest.raises(NotImplementedError):
-        R.ProjectorMonteCarloProblem(FakeHam(), n_replicas=2)
+    assert R.ProjectorMonteCarloProblem(FakeHam(), n_replicas=3).n_replicas == 3
+    with pytest.raises(ValueError):
+        R.ProjectorMonteCarloProblem(FakeHam(), n_replicas=0)
 
 
 def test_initiator_rule_keywords(built):
