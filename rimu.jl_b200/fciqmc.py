@@ -163,6 +163,34 @@ class Projector:
         return {self.name: _pdot(self.projector, state.v)}
 
 
+class AllOverlaps:
+    """AllOverlaps(n_replicas=2; operator=nothing, vecnorm=true) (replicastrategy.jl:60-183): after every step report
+    `c{i}_dot_c{j}` = dot(v_i, v_j) and, for each operator k, `c{i}_Op{k}_c{j}` = dot(v_i, Op_k, v_j) for all replica pairs.
+    Operators are device Hamiltonians (three-argument dot = mul! + dot on the GPU).  Transformed Hamiltonians
+    (`transform=`) are not supported."""
+
+    def __init__(self, n_replicas=2, operator=None, vecnorm=True):
+        if not isinstance(n_replicas, int):
+            raise TypeError("n_replicas must be an integer")
+        self.n_replicas, self.vecnorm = n_replicas, bool(vecnorm)
+        self.operators = () if operator is None else tuple(operator) if isinstance(operator, (tuple, list)) else (operator,)
+
+    def __call__(self, states):
+        out = {}
+        vecs = []
+        for st in states:  # overlaps are Float64 (promote_type of the value types, replicastrategy.jl:165)
+            v = st.v
+            vecs.append(v if v.style.val_type == _lib.VAL_F64 else
+                        GPUDVec(style=IsDeterministic(), address_type=v.address_type, ctx=v.ctx).copy_from(v))
+        for i in range(len(vecs)):
+            for j in range(i + 1, len(vecs)):
+                if self.vecnorm:
+                    out[f"c{i + 1}_dot_c{j + 1}"] = vecs[i].dot(vecs[j])
+                for k, op in enumerate(self.operators):
+                    out[f"c{i + 1}_Op{k + 1}_c{j + 1}"] = dot(vecs[i], op, vecs[j])
+        return out
+
+
 class Timer:
     def __call__(self, state, step):
         return {"time": time.time()}
@@ -193,10 +221,15 @@ class ProjectorMonteCarloProblem:
     def __init__(self, hamiltonian, *, start_at=None, shift=None, style=None, time_step=0.01, starting_step=0,
                  last_step=100, wall_time=math.inf, target_walkers=1000, zeta=0.08, xi=None, shift_strategy=None,
                  post_step_strategy=(), max_length=None, random_seed=True, reporting_interval=1, metadata=None,
-                 n_replicas=1, initiator=False):
+                 n_replicas=1, initiator=False, replica_strategy=None):
         if int(n_replicas) < 1:
             raise ValueError("n_replicas must be at least 1")
         self.n_replicas = int(n_replicas)  # independent copies of the walker vector, advanced side by side (qmc_states.jl:89-140)
+        self.replica_strategy = replica_strategy  # e.g. AllOverlaps: it also fixes the number of replicas (pmc problem :205-215)
+        if replica_strategy is not None:
+            if n_replicas not in (1, replica_strategy.n_replicas):
+                raise ValueError("n_replicas conflicts with the replica strategy")
+            self.n_replicas = replica_strategy.n_replicas
         # initiator=true -> Initiator(threshold 1) (projector_monte_carlo_problem.jl:156-160); a rule object is taken as is
         from .stochasticstyles import as_initiator_rule
         self.initiator = as_initiator_rule(initiator)
@@ -290,6 +323,8 @@ class PMCSimulation:
             too_long |= length > p.max_length
             stop |= not proceed
         if report_now:
+            if p.replica_strategy is not None and not dead:
+                row.update(p.replica_strategy(self.states))
             for k, val in row.items():
                 self.report.setdefault(k, []).append(val)
         if dead:

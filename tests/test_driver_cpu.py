@@ -248,3 +248,31 @@ def test_replicas_on_the_cpu(built, cpu_device):
     for r in (1, 2, 3):
         se = R.blocking_analysis(np.asarray(df[f"shift_{r}"]), skip=500)
         assert abs(se.mean - (-4.0215)) < 5 * se.err + 0.06
+
+
+def test_all_overlaps_on_the_cpu(built, cpu_device):
+    """AllOverlaps (replicastrategy.jl:60-183): column names c{i}_dot_c{j} / c{i}_Op{k}_c{j}, values = dot(v_i, v_j) and
+    dot(v_i, H, v_j); the replica (variational) energy sum c1.H.c2 / sum c1.c2 estimates E0 without the population-control
+    bias of a single vector."""
+    import rimu_b200 as R
+    oh, ph = cpu_device("real1d_6")
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=R.IsDynamicSemistochastic(), time_step=0.002, last_step=1500,
+                                        target_walkers=400, random_seed=6, replica_strategy=R.AllOverlaps(3, operator=ph))
+    sim = R.solve(prob)
+    df = sim.dataframe()
+    assert len(sim.states) == 3
+    pairs = [(1, 2), (1, 3), (2, 3)]
+    for i, j in pairs:
+        assert f"c{i}_dot_c{j}" in df.columns and f"c{i}_Op1_c{j}" in df.columns
+    # the last row against the final vectors
+    v1, v2 = sim.states[0].v, sim.states[1].v
+    assert math.isclose(df["c1_dot_c2"].iloc[-1], v1.dot(v2), rel_tol=1e-12)
+    num = sum(np.asarray(df[f"c{i}_Op1_c{j}"])[500:].sum() for i, j in pairs)
+    den = sum(np.asarray(df[f"c{i}_dot_c{j}"])[500:].sum() for i, j in pairs)
+    assert abs(num / den - (-4.0215)) < 0.05
+    with pytest.raises(ValueError):
+        R.ProjectorMonteCarloProblem(ph, n_replicas=2, replica_strategy=R.AllOverlaps(3))
+    only = R.AllOverlaps(2, vecnorm=False, operator=(ph, ph))
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, last_step=3, random_seed=1, replica_strategy=only)
+    cols = set(R.solve(prob).dataframe().columns)
+    assert {"c1_Op1_c2", "c1_Op2_c2"} <= cols and "c1_dot_c2" not in cols
