@@ -16,6 +16,7 @@ import ctypes as C
 import json
 import math
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -158,7 +159,9 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "walkers_per_gpu": target, "note": "CPU port of Rimu's threaded PDVec path (reference is Julia; not runnable here)"},
+        "config": {"workload": WORKLOAD, "walkers_per_gpu": target,
+                   "note": "CPU port of Rimu's threaded PDVec path (the reference is Julia and cannot run here; probe: julia "
+                           + ("present but Rimu.jl is not installed offline" if shutil.which("julia") else "absent") + ")"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

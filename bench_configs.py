@@ -2,7 +2,7 @@
 """bench_configs.py -- throughput of the FCIQMC step / matrix-free H*v on ALL five BASELINE.json configs
 (bench.py is the contract line on config 2; this script is the per-config evidence table kept in profiles/).
 
-  python bench_configs.py --configs 1,2,4,5 --steps 20          one GPU
+  python bench_configs.py --configs 1,2,4,5 --steps 20          one GPU   (6, 7: the reference's own benchmark workloads)
   torchrun --nproc-per-node N bench_configs.py --configs 4,5    hash-partitioned over N GPUs (weak scaling:
                                                                  --walkers is PER GPU)
 Every line: model, style, walkers, determinants, ms/step (CUDA events on the library's stream, max over ranks),
@@ -51,6 +51,17 @@ def make_config(R, cid, walkers):
         return dict(name="config5 Transcorrelated1D FermiFS2C M=32 3up3down t=1 v=1 cutoff=1 3-body IsDynamicSemistochastic",
                     ham=lambda: R.Transcorrelated1D(a, t=1.0, v=1.0, cutoff=1, three_body_term=True),
                     addr=a, style=R.IsDynamicSemistochastic(), dtau=1e-4, walkers=walkers or 1.25e7, words=1)
+    # the reference's own FCIQMC benchmark workloads (benchmark/benchmarks.jl:56-73), sizes as defined there
+    if cid == 6:
+        a = R.BoseFS(tuple(10 if i == 9 else 0 for i in range(20)))
+        return dict(name="ref-bench (10,20) HubbardMom1D BoseFS{10,20} u=1 IsDynamicSemistochastic initiator=true (benchmark/benchmarks.jl:56-64)",
+                    ham=lambda: R.HubbardMom1D(a, u=1.0, t=1.0), addr=a, style=R.IsDynamicSemistochastic(), dtau=1e-4,
+                    walkers=walkers or 4e4, words=1, initiator=R.Initiator(1.0))
+    if cid == 7:
+        a = R.near_uniform(R.BoseFS, 50, 50)
+        return dict(name="ref-bench (50,50) HubbardReal1D BoseFS{50,50} u=6 IsDynamicSemistochastic (benchmark/benchmarks.jl:66-73)",
+                    ham=lambda: R.HubbardReal1D(a, u=6.0, t=1.0), addr=a, style=R.IsDynamicSemistochastic(), dtau=1e-4,
+                    walkers=walkers or 5e4, words=2)
     raise ValueError(cid)
 
 
@@ -62,7 +73,8 @@ def run_stochastic(R, cfg, args, world, rank, dist, torch, peak):
     H = cfg["ham"]()
     style = cfg["style"]
     is_int = style.val_type == R._lib.VAL_I64
-    v = R.GPUDVec([(cfg["addr"], 10 if is_int else 10.0)], style=style, capacity=int(per_gpu * 1.6) + 4096)
+    v = R.GPUDVec([(cfg["addr"], 10 if is_int else 10.0)], style=style, capacity=int(per_gpu * 1.6) + 4096,
+                  initiator=cfg.get("initiator"))
     pv = v.similar()
     R._lib.check(R._lib.lib().rimu_vec_reserve(pv.handle, int(per_gpu * 1.6) + 4096))
     wm = R.working_memory(v, seed=args.seed)
