@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RIMU_B200_LIB") or os.path.join(_HERE, "librimu_b200.so")  # override: kernel-tuning builds
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "sort.cu"]
-HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h"]
+HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "--fmad=false", "-lineinfo",

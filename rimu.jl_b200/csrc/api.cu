@@ -851,10 +851,6 @@ static int records_to_vec(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const v
 }
 
 // ---- the same through the partitioned working memory: records -> bucket streams -> shared-memory merge (MODE 1)
-static int ensure_part(rimu_ctx *c, u32 nb);
-static int ensure_seg(rimu_vec *v, u32 nb);
-static u32 part_cap_items(int W);
-static size_t part_smem_bytes(int W);
 static int records_to_vec_part(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, const void *d_vals, i64 n,
                                const u64 *d_keys2, const void *d_vals2, i64 n2, double a1, double a2, int use_scale) {
     TRY(enter_ctx(c));

@@ -18,7 +18,7 @@
 // K3 runs ONE THREAD PER ATTEMPT over tiles of the global attempt index space; each tile stages its
 // parents (keys, values, offsets) in shared memory and threads locate their parent by binary search.
 #pragma once
-#include "hamiltonians.cuh"
+#include "step_math.cuh" // StepDev + the per-deposit arithmetic (host-compilable, see tests/cuda/host_ham.cpp)
 #include <type_traits>
 
 #define RIMU_TPB 256
@@ -29,14 +29,6 @@
 
 static const u64 EMPTY_KEY = ~0ull;
 
-struct StepDev {
-    int style, plain_h;
-    double shift, dtau, boost, proj_thr, rel_thr, abs_thr, compress_thr;
-    u32 k0, k1;
-    int rank, nranks;
-    int init_rule;      // RIMU_INITIATOR_*: 0 = no initiator lanes
-    double init_thr;
-};
 
 struct StatsDev {
     // block A: 16 x i64, summed over ranks
@@ -154,36 +146,6 @@ DEV void deposit(const TableDev &t, const ExchangeDev &x, const StepDev &p, Stat
         }
     }
     if (!table_add<W, VT>(t, key, h, v)) st->overflow_table = 1;
-}
-
-DEV double sgn_(double x) { return (double)((x > 0) - (x < 0)); }
-
-// projected_deposit! (spawning.jl:9-45): returns the value actually deposited (0 = nothing)
-template <class VT> DEV VT project_value(double val, double threshold, double r);
-template <> DEV i64 project_value<i64>(double val, double, double r) {
-    return (i64)sgn_(val) * (i64)floor(fabs(val) + r);
-}
-template <> DEV double project_value<double>(double val, double threshold, double r) {
-    double a = fabs(val);
-    if (a < threshold) val = (r < a / threshold) ? sgn_(val) * threshold : 0.0;
-    return val;
-}
-
-// spawn!(::DynamicSemistochastic) decision (spawning.jl:364-378) + attempt count (spawning.jl:234)
-DEV bool attempts_for(const StepDev &p, double val, long long L, u64 &n) {
-    if (L <= 0) { n = 0; return false; }
-    bool exact;
-    if (p.style == 0) exact = true;
-    else if (p.style == 2) {
-        double thresh = fmin(p.abs_thr, (double)L);
-        exact = p.boost * fabs(val) * p.rel_thr >= thresh;
-    } else exact = false;
-    if (exact) n = (u64)L;
-    else {
-        double f = floor(fabs(val) * p.boost);
-        n = f < 1.0 ? 1ull : (u64)f;
-    }
-    return exact;
 }
 
 // block-wide reductions of a few accumulators into StatsDev with one atomic per warp

@@ -208,52 +208,6 @@ __global__ void __launch_bounds__(RIMU_TPB) push_records_kernel(PartDev pt, int 
     }
 }
 
-// lane of a deposit (to_initiator_value, DictVectors/initiators.jl:142-158): diagonal deposits of an initiator
-// (|parent value| > threshold) are "initiator" (2), of anybody else "safe" (0); spawns of an initiator are "safe",
-// of a non-initiator "unsafe" (1).  Without a rule everything is lane 0.
-enum { LANE_SAFE = 0, LANE_UNSAFE = 1, LANE_INIT = 2 };
-DEV u32 deposit_lane(const StepDev &p, bool diagonal, double parent_val) {
-    if (p.init_rule == 0) return LANE_SAFE;
-    const bool is_initiator = fabs(parent_val) > p.init_thr;
-    if (diagonal) return is_initiator ? LANE_INIT : LANE_SAFE;
-    return is_initiator ? LANE_SAFE : LANE_UNSAFE;
-}
-
-// one spawn attempt k of a parent (spawning.jl:174-182 Exact, :232-243 WithReplacement).
-// Returns the value to deposit (0 = nothing); ci = off-diagonal index used, child = its address.
-template <int HK, int W, class VT>
-DEV VT spawn_attempt(const HamDev &h, const StepDev &p, typename BitsT<W>::type key, u64 hkey, double val,
-                     long long L, u64 nat, bool exact, u64 k, typename BitsT<W>::type &child, long long &ci,
-                     double &spawned) {
-    typedef typename BitsT<W>::type B;
-    constexpr bool is_int = std::is_integral<VT>::value;
-    if (exact) {
-        ci = (long long)k;
-        double m = ham_offdiagonal<HK, B>(h, key, ci, child);
-        if (!p.plain_h) m = -m * p.dtau;
-        double r = 0.0;
-        if (p.proj_thr > 0.0) {
-            u32 rnd[4];
-            rng_draw(hkey, k, STREAM_SPAWN, p.k0, p.k1, rnd);
-            r = u53(rnd[1], rnd[2]);
-        }
-        double nv = project_value<double>(val * m, p.proj_thr, r);
-        spawned = fabs(nv);
-        if constexpr (is_int) return (VT)0; else return nv;
-    }
-    u32 rnd[4];
-    rng_draw(hkey, k, STREAM_SPAWN, p.k0, p.k1, rnd);
-    ci = (long long)(((u64)rnd[0] * (u64)L) >> 32);
-    double m = ham_offdiagonal<HK, B>(h, key, ci, child);
-    if (!p.plain_h) m = -m * p.dtau;
-    double magnitude = val / (double)nat;
-    double prob = 1.0 / (double)L;
-    double nv0 = m * magnitude / prob;
-    VT nv = project_value<VT>(nv0, is_int ? 0.0 : p.proj_thr, u53(rnd[1], rnd[2]));
-    spawned = fabs((double)nv);
-    return nv;
-}
-
 // ---------------------------------------------------------------- K1: spawning, CTA-local work distribution
 template <int HK, int W, class VT>
 __global__ void __launch_bounds__(SPAWN_NT, SPAWN_MINB)

@@ -100,3 +100,84 @@ def test_host_validation_errors(emu):
     assert emu.emu_ham_create(C.byref(d), C.byref(h), err, 512) == _lib.ERR_INVALID and b"correct number of sites" in err.value
     d.model, d.boundary_condition = _lib.EXTENDED_HUBBARD_REAL_1D, 7
     assert emu.emu_ham_create(C.byref(d), C.byref(h), err, 512) == _lib.ERR_INVALID and b"boundary" in err.value
+
+
+class _EmuStep(C.Structure):
+    _fields_ = [("style", C.c_int), ("plain_h", C.c_int), ("shift", C.c_double), ("dtau", C.c_double), ("boost", C.c_double),
+                ("proj_thr", C.c_double), ("rel_thr", C.c_double), ("abs_thr", C.c_double), ("k0", C.c_uint32), ("k1", C.c_uint32),
+                ("init_rule", C.c_int), ("init_thr", C.c_double)]
+
+
+STYLES = {  # name -> (oracle style, integer values?, proj_threshold, plain_h)
+    "deterministic_H": (0, False, 0.0, True),
+    "deterministic_T": (0, False, 0.0, False),
+    "integer": (1, True, 0.0, False),
+    "semistochastic": (2, False, 0.0, False),
+    "with_threshold": (3, False, 1.0, False),
+}
+
+
+@pytest.mark.parametrize("style_name", sorted(STYLES))
+@pytest.mark.parametrize("name", ["real1d_10", "real1d_w2", "ext1d_twisted", "real1d_ep", "mom1d_bose", "mom1d_f2c", "rs_bose_2d_hw",
+                                  "rs_bose_3d_w2", "rs_f2c_4x4", "tc_7"])
+def test_device_step_arithmetic_matches_oracle_on_the_host(built, emu, name, style_name):
+    """Everything ONE parent deposits in a step -- the diagonal death/cloning value and every spawn attempt (Philox draw,
+    off-diagonal pick, exact/stochastic decision, projection, initiator lane) -- computed with the kernels' own functions
+    (csrc/step_math.cuh compiled for the host) must reproduce the oracle's step on that single parent: bit-exact for integer
+    walkers, 1e-13 for Float64 (same summation order), including the statistics the step reports."""
+    import math
+    from oracle import oracle as orc
+    style, is_int, proj_thr, plain = STYLES[style_name]
+    oh, ph = oracle_ham(name), product_ham(name)
+    h, err = C.c_void_p(), C.create_string_buffer(512)
+    assert emu.emu_ham_create(C.byref(ph.desc), C.byref(h), err, 512) == 0, err.value
+    emu.emu_parent_deposits.restype = C.c_longlong
+    W = oh.W
+    u64p = C.POINTER(C.c_uint64)
+    shift = oh.diagonal_element(oh.start_key) + 1.5
+    values = [1, 3, -2, 40, 1300] if is_int else [0.3, 1.0, -2.7, 57.4, 1300.5]
+    cap = 200000
+    ck, cv, cl = (C.c_uint64 * (cap * W))(), (C.c_double * cap)(), (C.c_int * cap)()
+    for step, key in enumerate(sample_keys(oh, 6, seed=4)):
+        kt = tuple(int(x) for x in key)
+        for rule in (0, 1, 3):
+            if rule and plain:
+                continue
+            for val in values:
+                k0, k1 = orc.step_key(11, step)
+                pp = orc.make_params(style, shift=shift, dtau=0.01, plain_h=plain, proj_threshold=proj_thr, key=(k0, k1),
+                                     initiator_rule=rule, initiator_threshold=1.0)
+                ko, vo, st = oh.step(pp, np.array([kt], dtype=np.uint64), np.array([val], dtype=np.int64 if is_int else np.float64))
+                want = {tuple(int(t) for t in k): float(v) for k, v in zip(ko.reshape(len(vo), W), vo)}
+                es = _EmuStep(style, int(plain), shift, 0.01, 1.0, proj_thr, 1.0, math.inf, k0, k1, rule, 1.0)
+                kin = (C.c_uint64 * 2)(*(list(kt) + [0] * (2 - len(kt))))
+                dv, dl, att, ex, ssum = C.c_double(), C.c_int(), C.c_longlong(), C.c_int(), C.c_double()
+                n = emu.emu_parent_deposits(h, C.byref(es), C.cast(kin, u64p), C.c_double(float(val)), int(is_int), cap,
+                                            C.cast(ck, u64p), cv, cl, C.byref(dv), C.byref(dl), C.byref(att), C.byref(ex), C.byref(ssum))
+                assert 0 <= n <= cap
+                assert att.value == st.spawn_attempts and ex.value == st.exact_steps, (name, style_name, val)
+                assert math.isclose(ssum.value, float(st.ispawns) if is_int else st.spawns, rel_tol=1e-12, abs_tol=1e-300)
+                # lanes -> (safe + initiator, unsafe, initiator non-zero) per address, then from_initiator_value
+                acc = {}
+                def add(k, v, lane):
+                    a = acc.setdefault(k, [0.0, 0.0, False])
+                    if lane == 1:
+                        a[1] += v
+                    else:
+                        a[0] += v
+                        a[2] |= lane == 2 and v != 0
+                if dv.value != 0.0:
+                    add(kt, dv.value, dl.value)
+                for r in range(n):
+                    add(tuple(int(ck[r * W + j]) for j in range(W)), cv[r], cl[r])
+                got = {}
+                for k, (a, u, fi) in acc.items():
+                    v = a if rule in (0, 2) else (a + u if (fi or (rule == 3 and abs(u) > 1.0)) else a)
+                    if rule == 0:
+                        v = a + u  # without a rule everything is in lane 0 anyway
+                    if v != 0.0:
+                        got[k] = v
+                assert got.keys() == want.keys(), (name, style_name, rule, val, len(got), len(want))
+                for k, v in want.items():
+                    assert (got[k] == v) if is_int else math.isclose(got[k], v, rel_tol=1e-13, abs_tol=1e-300), (name, style_name, rule, val, k, got[k], v)
+    emu.emu_ham_destroy(h)
