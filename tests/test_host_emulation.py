@@ -181,3 +181,56 @@ def test_device_step_arithmetic_matches_oracle_on_the_host(built, emu, name, sty
                 for k, v in want.items():
                     assert (got[k] == v) if is_int else math.isclose(got[k], v, rel_tol=1e-13, abs_tol=1e-300), (name, style_name, rule, val, k, got[k], v)
     emu.emu_ham_destroy(h)
+
+
+def _random_onr(rng, kind, comps, M):
+    """random occupation numbers with the particle numbers of `comps` (edge shapes included)"""
+    out = []
+    for comp in comps:
+        N = sum(comp)
+        if kind == "bose":
+            mode = rng.integers(0, 4)
+            if mode == 0:  # everything in one mode (first, last or random)
+                onr = [0] * M
+                onr[[0, M - 1, int(rng.integers(0, M))][int(rng.integers(0, 3))]] = N
+            else:
+                cuts = np.sort(rng.integers(0, N + 1, size=M - 1))
+                onr = list(np.diff(np.concatenate([[0], cuts, [N]])))
+        else:
+            onr = [0] * M
+            for m in rng.choice(M, size=N, replace=False):
+                onr[int(m)] = 1
+        out.append(tuple(int(x) for x in onr))
+    return out
+
+
+@pytest.mark.parametrize("name", ["real1d_10", "real1d_w2", "real1d_ep_w2", "ext1d_hw", "mom1d_bose_20", "mom1d_odd", "mom1d_f2c",
+                                  "rs_bose_2d_hw", "rs_bose_3d_w2", "rs_fermi_hw", "rs_f2c_trap", "tc_8_cut2", "tc_32"])
+def test_device_hamiltonian_code_on_random_addresses(built, emu, name):
+    """Addresses the BFS walk from the starting address rarely visits: all particles in the first / last mode, random
+    fillings, both address widths.  diagonal, count and a spread of off-diagonals, device code (host build) vs oracle."""
+    oh, ph = oracle_ham(name), product_ham(name)
+    h, err = C.c_void_p(), C.create_string_buffer(512)
+    assert emu.emu_ham_create(C.byref(ph.desc), C.byref(h), err, 512) == 0, err.value
+    W = oh.W
+    u64p = C.POINTER(C.c_uint64)
+    out = (C.c_uint64 * 2)()
+    rng = np.random.default_rng(12345)
+    kind = SPECS[name][1]
+    comps = oh.start_onr
+    for _ in range(60):
+        onrs = _random_onr(rng, "bose" if kind == "bose" else "fermi", comps, oh.M)
+        key = oh.pack(onrs[0] if len(onrs) == 1 else tuple(onrs))
+        kt = tuple(int(x) for x in key) if isinstance(key, (tuple, list)) else tuple(int(x) for x in np.asarray(key, dtype=np.uint64).ravel())
+        kin = (C.c_uint64 * 2)(*(list(kt) + [0] * (2 - len(kt))))
+        assert emu.emu_diagonal(h, C.cast(kin, u64p)) == oh.diagonal_element(kt), (name, onrs)
+        L = oh.num_offdiagonals(kt)
+        assert emu.emu_num_offdiagonals(h, C.cast(kin, u64p)) == L, (name, onrs)
+        idx = range(1, L + 1) if L <= 200 else sorted(set(int(x) for x in rng.integers(1, L + 1, size=200)) | {1, L})
+        for i in idx:
+            ok, ov = oh.get_offdiagonal(kt, i)
+            v = emu.emu_offdiagonal(h, C.cast(kin, u64p), i - 1, C.cast(out, u64p))
+            assert v == ov, (name, onrs, i, v, ov)
+            if ov != 0.0:
+                assert tuple(int(out[j]) for j in range(W)) == (tuple(ok) if isinstance(ok, (tuple, list)) else (int(ok),)), (name, onrs, i)
+    emu.emu_ham_destroy(h)
