@@ -13,13 +13,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RIMU_B200_LIB") or os.path.join(_HERE, "librimu_b200.so")  # override: kernel-tuning builds
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "sort.cu"]
-HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh"]
+SOURCES = ["api.cu", "sort.cu", "step_hk.cu"]   # step_hk.cu is compiled once per HamKind (-DRIMU_HK=n), in parallel
+HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh", "internal.cuh"]
+NUM_HAM_KINDS = 7
+OBJ_DIR = os.path.join(_HERE, "build")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "--fmad=false", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 MAX_MODES = 128
@@ -50,19 +52,42 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into rimu.jl_b200/librimu_b200.so (in-tree)."""
-    if os.environ.get("RIMU_B200_LIB") or (not force and not _stale()):
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None, kinds=None) -> str:
+    """Compile every CUDA source for sm_100a into rimu.jl_b200/librimu_b200.so (in-tree).
+
+    api.cu, sort.cu and one object per Hamiltonian kind (step_hk.cu with -DRIMU_HK=n) are compiled in parallel and linked
+    with nvcc -shared.  `defines`/`out`/`kinds` are for kernel-tuning builds (scratch/)."""
+    target = out or LIB_PATH
+    if out is None and (os.environ.get("RIMU_B200_LIB") or (not force and not _stale())):
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH, "-ldl"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    tag = "" if out is None else "_" + os.path.splitext(os.path.basename(out))[0]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    base = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else [])
+    jobs = []
+    for s in ("api.cu", "sort.cu"):
+        jobs.append((base + ["-c", os.path.join(CSRC, s), "-o", os.path.join(OBJ_DIR, s[:-3] + tag + ".o")]))
+    for hk in (range(NUM_HAM_KINDS) if kinds is None else kinds):
+        jobs.append((base + [f"-DRIMU_HK={hk}", "-c", os.path.join(CSRC, "step_hk.cu"), "-o", os.path.join(OBJ_DIR, f"step_hk{hk}{tag}.o")]))
+
+    def run(cmd):
+        return cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(run, jobs))
+    log = ""
+    for cmd, res in results:
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        log += res.stderr
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + [c[c.index("-o") + 1] for c, _ in results] + ["-o", target, "-ldl"]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
-    return LIB_PATH
+        print(log)
+    return target
 
 
 class HamDesc(C.Structure):

@@ -4,22 +4,11 @@
 //   collect_local!   -> implicit (all deposits accumulate in the one working table)
 //   synchronize_remote! -> count all-gather + grouped ncclSend/ncclRecv + insert_records_kernel
 //   move_and_compress!  -> compact_kernel (also walkernumber_and_length)
-#include "../../include/rimu_b200.h"
-#include "partition.cuh"
-#include "ham_host.h"
-
-#include <dlfcn.h>
-#include <math.h>
-#include <stdarg.h>
-#include <stdio.h>
-#include <stdlib.h>
-#include <string.h>
-#include <string>
-#include <vector>
+#include "internal.cuh"
 
 // ---------------------------------------------------------------- errors
 static thread_local std::string g_err;
-static int fail(int code, const char *fmt, ...) {
+int fail(int code, const char *fmt, ...) {
     char buf[1024];
     va_list ap;
     va_start(ap, fmt);
@@ -28,51 +17,14 @@ static int fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
-// cudaMalloc with diagnostics: RIMU_B200_TRACE_ALLOC=1 logs every allocation above 64 MiB; a failure reports the
-// request and the free/total device memory and clears CUDA's "last error" so that it cannot surface at a later,
-// unrelated cudaGetLastError() check
-static size_t g_alloc_fail_bytes = 0;
-template <class T> static cudaError_t rimu_malloc(T **p, size_t bytes) {
-    static const bool trace = getenv("RIMU_B200_TRACE_ALLOC") != nullptr;
-    cudaError_t e = cudaMalloc((void **)p, bytes);
-    if (trace && bytes >= (64u << 20)) {
-        size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
-        fprintf(stderr, "[rimu_b200] cudaMalloc %.1f MiB -> %s (free %.1f GiB of %.1f GiB)\n", bytes / 1048576.0,
-                e == cudaSuccess ? "ok" : cudaGetErrorString(e), fr / 1073741824.0, tot / 1073741824.0);
-    }
-    if (e != cudaSuccess) { g_alloc_fail_bytes = bytes; cudaGetLastError(); }
-    return e;
-}
-static std::string oom_note() {
+size_t g_alloc_fail_bytes = 0;
+std::string oom_note() {
     size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot);
     char b[160];
     snprintf(b, sizeof(b), " [requested %.1f MiB; device has %.1f GiB free of %.1f GiB]", g_alloc_fail_bytes / 1048576.0,
              fr / 1073741824.0, tot / 1073741824.0);
     return b;
 }
-// Entry of every API call that touches the device: select the context's GPU and drop any stale, non-sticky error that an
-// earlier benign failure in this thread (ours, NCCL's or the host framework's) left in CUDA's "last error" slot -- otherwise
-// it would be reported by the first cudaGetLastError() after one of OUR launches.  Sticky errors survive this and are
-// still caught by the next call.
-static cudaError_t enter_device(int device) {
-    cudaError_t e = cudaSetDevice(device);
-    cudaGetLastError();
-    return e;
-}
-#define CUDA_TRY(x)                                                                                   \
-    do {                                                                                              \
-        cudaError_t e_ = (x);                                                                         \
-        if (e_ != cudaSuccess)                                                                        \
-            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? RIMU_ERR_NO_DEVICE : RIMU_ERR_CUDA, \
-                        "%s failed: %s (%s:%d)%s", #x, cudaGetErrorString(e_), __FILE__, __LINE__,    \
-                        e_ == cudaErrorMemoryAllocation ? oom_note().c_str() : "");                   \
-    } while (0)
-#define TRY(x)              \
-    do {                    \
-        int r_ = (x);       \
-        if (r_ != 0) return r_; \
-    } while (0)
-
 extern "C" const char *rimu_last_error(void) { return g_err.c_str(); }
 extern "C" int rimu_version(void) { return 100; }
 extern "C" int rimu_sizeof_ham_desc(void) { return (int)sizeof(rimu_ham_desc); }
@@ -80,25 +32,8 @@ extern "C" int rimu_sizeof_step_params(void) { return (int)sizeof(rimu_step_para
 extern "C" int rimu_sizeof_step_stats(void) { return (int)sizeof(rimu_step_stats); }
 
 // ---------------------------------------------------------------- NCCL (resolved lazily; same soname as torch's bundled copy)
-typedef struct ncclComm *ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclInt64 = 4, ncclUint64 = 5, ncclFloat64 = 8 };
-enum { ncclSum = 0, ncclMax = 2 };
-struct NcclApi {
-    void *lib = nullptr;
-    int (*GetUniqueId)(ncclUniqueId *);
-    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
-    int (*CommDestroy)(ncclComm_t);
-    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
-    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
-    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
-    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
-    int (*GroupStart)();
-    int (*GroupEnd)();
-    const char *(*GetErrorString)(int);
-};
-static NcclApi g_nccl;
-static int nccl_load() {
+NcclApi g_nccl;
+int nccl_load() {
     if (g_nccl.lib) return 0;
     void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -113,102 +48,12 @@ static int nccl_load() {
     g_nccl.lib = lib;
     return 0;
 }
-#define NCCL_TRY(x)                                                                              \
-    do {                                                                                         \
-        int e_ = (x);                                                                            \
-        if (e_ != 0) return fail(RIMU_ERR_NCCL, "%s failed: %s", #x, g_nccl.GetErrorString(e_)); \
-        cudaGetLastError(); /* NCCL succeeded: whatever benign CUDA error it left behind is not ours */ \
-    } while (0)
-
-// ---------------------------------------------------------------- handles
-struct rimu_ctx {
-    int device, W, sm_count;
-    cudaStream_t stream;
-    u64 *table;
-    u64 table_slots; // capacity (power of two)
-    StatsDev *d_stats, *h_stats, *h_stats_local;
-    u64 *local_off, *block_tot, *block_base;
-    u64 scratch_parents;
-    cudaEvent_t ev[8];
-    double *d_red = nullptr; // packed statistics for the single all-reduce (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP doubles)
-    unsigned long long launches; // kernels launched by this context (bench bookkeeping)
-    // staging for host <-> device transfers
-    u64 *stage_keys; void *stage_vals; u64 stage_cap;
-    // comm
-    ncclComm_t comm;
-    int rank, nranks;
-    ExchangeDev xch;
-    u64 *recv_keys, *recv_vals, recv_cap;
-    u64 *d_allcounts, *h_allcounts;
-    double *d_reduce;
-    // partitioned step (partition.cuh): bucket record streams, heavy-parent queue, re-segmentation scratch
-    int method;              // RIMU_ANNIHILATE_PARTITION (default) or RIMU_ANNIHILATE_HASH
-    PartDev part;            // record streams of the FCIQMC step (direct mode: peers store into them over NVLink)
-    u64 part_nb_cap;         // buckets the record streams are allocated for
-    PartDev lpart;           // direct mode only: private streams for local operations (upload, axpby, annihilate), which
-    u64 lpart_nb_cap;        //   run between steps while a faster peer may already be filling the step streams
-    int direct;              // multi-GPU: peers can map each other's streams (CUDA IPC) -> spawned records are stored
-                             //   straight into the owner's bucket sub-streams, no receive pass
-    u64 last_dst_uid, last_dst_version; double last_g_len; // identity (uid, never reused) + state of the previous step's result
-    u64 next_vec_uid;        // vectors are numbered in creation order: the same numbers on every rank (same call sequence)
-    u32 merge_grid_cap;      // RIMU_B200_MERGE_GRID: cap on merge CTAs (tests force many buckets per CTA with it)
-    int live_vecs;           // vectors created on this context and not yet destroyed
-    int dead;                // rimu_ctx_destroy was called while vectors were alive: the struct (and stream) live on until the
-                             //   last of them is destroyed (host GCs finalise vectors and contexts in arbitrary order) // global length of the previous step's result
-    HeavyDev heavy;
-    u32 *bucket_tmp; u64 bucket_tmp_cap; // [2][nb] counts / fill
-    u64 xch_worst;           // largest per-peer record count seen by a failed exchange
-    u64 xch_want;            // per-peer capacity the staging buffers get when they are first needed
-    int p2p_used;            // the last exchange went peer-direct: counts are read from h_allcounts after the final sync
-    void *peer_open[2][RIMU_MAX_RANKS]; // IPC-opened peer stream buffers (records, sub-stream fills)
-    char *d_ipc, *h_ipc;     // all-gather scratch for the IPC handles
-    alignas(16) char sort_scratch[96];   // SortScratch of sort.cu (opaque here)
-    double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
-    u64 last_max_fill;
-};
-static int enter_ctx(rimu_ctx *c) {
+int enter_ctx(rimu_ctx *c) {
     if (!c) return fail(RIMU_ERR_INVALID, "null context");
     if (c->dead) return fail(RIMU_ERR_INVALID, "this context has been destroyed (a vector outlived it)");
     CUDA_TRY(enter_device(c->device));
     return 0;
 }
-struct rimu_ham {
-    rimu_ham_desc desc;
-    int hk, W, device;
-    HamDev dev;
-    double *d_tables;
-    unsigned char *d_nbr;
-    u64 uid; // identifies this Hamiltonian in the vectors' diagonal-element caches
-};
-struct rimu_vec {
-    rimu_ctx *ctx;
-    int vt;
-    u64 cap;
-    i64 n;
-    u64 *keys;
-    void *vals;
-    // bucket segmentation (partition.cuh); nb == 0: not segmented
-    u32 nb;
-    u64 seg_cap;
-    u64 *seg_start;
-    u32 *seg_len;
-    // cache of diagonal_element(H, address) per entry, written by the partitioned step; valid for the
-    // Hamiltonian with uid diag_uid (0 = invalid).  Saves re-evaluating H_aa for every parent every step.
-    double *diag;
-    u64 diag_cap, diag_uid;
-    u64 version;             // bumped by every mutating API call (the same call sequence runs on every rank)
-    u64 uid;                 // creation number within the context (a freed vector's address may be reused, its uid never is)
-};
-
-static u64 next_pow2(u64 x) { u64 p = 1; while (p < x) p <<= 1; return p; }
-static int grid_for(i64 n, int sm_count, int per_sm = 8) {
-    i64 g = (n + RIMU_TPB - 1) / RIMU_TPB;
-    i64 cap = (i64)sm_count * per_sm;
-    if (g > cap) g = cap;
-    if (g < 1) g = 1;
-    return (int)g;
-}
-
 // ---------------------------------------------------------------- context
 static int table_fill(rimu_ctx *c, u64 slots) {
     table_fill_empty_kernel<<<grid_for((i64)slots, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(c->table, slots, c->W);
@@ -335,7 +180,7 @@ extern "C" int rimu_ctx_resize_table(rimu_ctx *c, uint64_t table_slots) {
     return 0;
 }
 
-static int ensure_scratch(rimu_ctx *c, u64 parents) {
+int ensure_scratch(rimu_ctx *c, u64 parents) {
     if (parents <= c->scratch_parents) return 0;
     u64 cap = parents + parents / 4 + 1024;
     cudaFree(c->local_off); cudaFree(c->block_tot); cudaFree(c->block_base);
@@ -359,7 +204,7 @@ static int ensure_stage(rimu_ctx *c, u64 n) {
 }
 
 // ---- partitioned-step working memory
-static int ensure_seg(rimu_vec *v, u32 nb) {
+int ensure_seg(rimu_vec *v, u32 nb) {
     if (nb <= v->seg_cap) return 0;
     u64 cap = (u64)nb + nb / 2 + 64;
     cudaFree(v->seg_start); cudaFree(v->seg_len);
@@ -369,8 +214,6 @@ static int ensure_seg(rimu_vec *v, u32 nb) {
     v->seg_cap = cap;
     return 0;
 }
-static u32 part_cap_items(int W) { return W == 1 ? (u32)PartCap<1>::value : (u32)PartCap<2>::value; }
-static size_t part_smem_bytes(int W) { u32 cap = part_cap_items(W); return (size_t)cap * W * 8 + (size_t)cap * 8 + (size_t)cap * 2 * 4 + (size_t)cap * 2; }
 static int p2p_setup(rimu_ctx *c);
 static void p2p_teardown(rimu_ctx *c);
 extern "C" int rimu_comm_allreduce_f64(rimu_ctx *c, double *buf, int n);
@@ -408,12 +251,12 @@ static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool 
     if (shared) TRY(p2p_setup(c));
     return 0;
 }
-static int ensure_part(rimu_ctx *c, u32 nb, u32 nlane = 1) { return ensure_part_impl(c, c->part, c->part_nb_cap, nb, c->nranks > 1 && c->direct, nlane); }
+int ensure_part(rimu_ctx *c, u32 nb, u32 nlane) { return ensure_part_impl(c, c->part, c->part_nb_cap, nb, c->nranks > 1 && c->direct, nlane); }
 // streams for local record->vector operations
 static PartDev &local_part(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? c->lpart : c->part; }
 static u64 &local_part_cap(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? c->lpart_nb_cap : c->part_nb_cap; }
 static int ensure_local_part(rimu_ctx *c, u32 nb) { return ensure_part_impl(c, local_part(c), local_part_cap(c), nb, false, 1, true); }
-static int ensure_heavy(rimu_ctx *c, u64 parents) {
+int ensure_heavy(rimu_ctx *c, u64 parents) {
     if (!c->heavy.packed) CUDA_TRY(rimu_malloc(&c->heavy.packed, sizeof(u64)));
     if (parents <= c->heavy.cap) return 0;
     u64 cap = parents + parents / 4 + 1024;
@@ -626,23 +469,24 @@ extern "C" int rimu_ham_destroy(rimu_ham *h) {
 }
 extern "C" int rimu_ham_words(const rimu_ham *h) { return h->W; }
 
-// compile-time dispatch over (HamKind, W)
-template <int HK, int W> struct HkTag { static constexpr int hk = HK; static constexpr int w = W; };
-template <class F> static int dispatch_ham(const rimu_ham *h, F &&f) {
-#ifdef RIMU_TUNE_ONLY_MOM1D // kernel-tuning builds (scratch/): one instantiation, seconds to compile; never shipped
-    if (h->hk == HK_MOM1D_BOSE && h->W == 1) return f(HkTag<HK_MOM1D_BOSE, 1>());
-    return fail(RIMU_ERR_INVALID, "tuning build: only HubbardMom1D/BoseFS one-word addresses are compiled in");
+// per-kind entry points (step_hk.cu)
+static const HkOps *hk_ops(const rimu_ham *h) {
+#ifdef RIMU_TUNE_ONLY_MOM1D // kernel-tuning builds (scratch/): one kind, seconds to compile; never shipped
+    if (h->hk == HK_MOM1D_BOSE && h->W == 1) return rimu_hk_ops_1();
+    fail(RIMU_ERR_INVALID, "tuning build: only HubbardMom1D/BoseFS one-word addresses are compiled in");
+    return nullptr;
 #else
     switch (h->hk) {
-    case HK_REAL1D_BOSE: return h->W == 1 ? f(HkTag<HK_REAL1D_BOSE, 1>()) : f(HkTag<HK_REAL1D_BOSE, 2>());
-    case HK_MOM1D_BOSE: return h->W == 1 ? f(HkTag<HK_MOM1D_BOSE, 1>()) : f(HkTag<HK_MOM1D_BOSE, 2>());
-    case HK_MOM1D_F2C: return f(HkTag<HK_MOM1D_F2C, 1>());
-    case HK_RS_BOSE: return h->W == 1 ? f(HkTag<HK_RS_BOSE, 1>()) : f(HkTag<HK_RS_BOSE, 2>());
-    case HK_RS_FERMI: return f(HkTag<HK_RS_FERMI, 1>());
-    case HK_RS_F2C: return f(HkTag<HK_RS_F2C, 1>());
-    case HK_TC_F2C: return f(HkTag<HK_TC_F2C, 1>());
+    case HK_REAL1D_BOSE: return rimu_hk_ops_0();
+    case HK_MOM1D_BOSE: return rimu_hk_ops_1();
+    case HK_MOM1D_F2C: return rimu_hk_ops_2();
+    case HK_RS_BOSE: return rimu_hk_ops_3();
+    case HK_RS_FERMI: return rimu_hk_ops_4();
+    case HK_RS_F2C: return rimu_hk_ops_5();
+    case HK_TC_F2C: return rimu_hk_ops_6();
     }
-    return fail(RIMU_ERR_INVALID, "unknown Hamiltonian kind");
+    fail(RIMU_ERR_INVALID, "unknown Hamiltonian kind");
+    return nullptr;
 #endif
 }
 
@@ -661,11 +505,9 @@ extern "C" int rimu_ham_diagonal(rimu_ctx *c, const rimu_ham *h, const uint64_t 
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     double *d_out = (double *)c->stage_vals;
-    TRY(dispatch_ham(h, [&](auto tag) {
-        ham_diag_kernel<decltype(tag)::hk, decltype(tag)::w><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(h->dev, c->stage_keys, n, d_out, nullptr);
-        return 0;
-    }));
-    CUDA_TRY(cudaGetLastError());
+    const HkOps *ops = hk_ops(h);
+    if (!ops) return RIMU_ERR_INVALID;
+    TRY(ops->diag(c, h, c->stage_keys, n, d_out, nullptr));
     CUDA_TRY(cudaMemcpyAsync(out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
@@ -676,11 +518,9 @@ extern "C" int rimu_ham_num_offdiagonals(rimu_ctx *c, const rimu_ham *h, const u
     TRY(ensure_stage(c, (u64)n));
     CUDA_TRY(cudaMemcpyAsync(c->stage_keys, keys, n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     i64 *d_out = (i64 *)c->stage_vals;
-    TRY(dispatch_ham(h, [&](auto tag) {
-        ham_diag_kernel<decltype(tag)::hk, decltype(tag)::w><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(h->dev, c->stage_keys, n, nullptr, d_out);
-        return 0;
-    }));
-    CUDA_TRY(cudaGetLastError());
+    const HkOps *ops = hk_ops(h);
+    if (!ops) return RIMU_ERR_INVALID;
+    TRY(ops->diag(c, h, c->stage_keys, n, nullptr, d_out));
     CUDA_TRY(cudaMemcpyAsync(out, d_out, n * sizeof(i64), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
@@ -694,12 +534,9 @@ extern "C" int rimu_ham_offdiagonals(rimu_ctx *c, const rimu_ham *h, const uint6
     u64 *d_key = c->stage_keys + (u64)count * c->W;
     CUDA_TRY(cudaMemcpyAsync(d_key, key, c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
     double *d_vals = (double *)c->stage_vals;
-    TRY(dispatch_ham(h, [&](auto tag) {
-        ham_offdiag_kernel<decltype(tag)::hk, decltype(tag)::w><<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(
-            h->dev, d_key, first - 1, count, c->stage_keys, d_vals);
-        return 0;
-    }));
-    CUDA_TRY(cudaGetLastError());
+    const HkOps *ops = hk_ops(h);
+    if (!ops) return RIMU_ERR_INVALID;
+    TRY(ops->offdiag(c, h, d_key, first - 1, count, c->stage_keys, d_vals));
     CUDA_TRY(cudaMemcpyAsync(keys_out, c->stage_keys, count * c->W * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(vals_out, d_vals, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -756,7 +593,7 @@ extern "C" int rimu_vec_reserve(rimu_vec *v, uint64_t capacity) {
     v->diag = nd; v->diag_cap = nd ? capacity : 0;
     return 0;
 }
-static int ensure_diag(rimu_vec *v) {
+int ensure_diag(rimu_vec *v) {
     if (v->diag && v->diag_cap >= v->cap) return 0;
     cudaFree(v->diag); v->diag = nullptr; v->diag_cap = 0; v->diag_uid = 0;
     CUDA_TRY(rimu_malloc(&v->diag, v->cap * sizeof(double)));
@@ -772,20 +609,6 @@ static StepDev null_step(rimu_ctx *c) {
     memset(&p, 0, sizeof(p));
     p.rank = c->rank; p.nranks = c->nranks;
     return p;
-}
-
-// drain the working table into dst (no compression); returns RIMU_ERR_VECTOR_FULL after growing is impossible
-template <int W, class VT> static int compact_into(rimu_ctx *c, rimu_vec *dst, u64 slots, const StepDev &p) {
-    TableDev tab{c->table, slots - 1};
-    compact_kernel<W, VT><<<grid_for((i64)slots, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
-        tab, p, dst->keys, (VT *)dst->vals, dst->cap, c->d_stats);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-template <class F> static int dispatch_wv(int W, int vt, F &&f) {
-    if (W == 1) return vt == RIMU_VAL_F64 ? f(HkTag<0, 1>(), double()) : f(HkTag<0, 1>(), i64());
-    return vt == RIMU_VAL_F64 ? f(HkTag<0, 2>(), double()) : f(HkTag<0, 2>(), i64());
 }
 
 static u64 pick_slots(rimu_ctx *c, u64 expected_entries) {
@@ -1168,7 +991,7 @@ extern "C" int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *
 }
 
 // ---------------------------------------------------------------- the step
-static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_streams) {
+int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_streams) {
     const int R = c->nranks, me = c->rank;
     c->p2p_used = 0;
     if (to_streams && c->direct) {
@@ -1242,40 +1065,6 @@ static int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool t
     return 0;
 }
 
-template <int HK, int W, class VT>
-static int step_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, u64 slots, i64 *sent) {
-    const i64 n = src->n;
-    TableDev tab{c->table, slots - 1};
-    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    if (n > 0) {
-        TRY(ensure_scratch(c, (u64)n));
-        const i64 nblk = (n + RIMU_TPB - 1) / RIMU_TPB;
-        diag_count_kernel<HK, W, VT><<<(unsigned)nblk, RIMU_TPB, 0, c->stream>>>(
-            h->dev, p, src->keys, (const VT *)src->vals, n, tab, c->xch, c->local_off, c->block_tot, c->d_stats);
-        scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(c->block_tot, nblk, c->block_base, c->d_stats);
-        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-        spawn_kernel<HK, W, VT><<<c->sm_count * 8, RIMU_TPB, 0, c->stream>>>(
-            h->dev, p, src->keys, (const VT *)src->vals, n, c->block_base, c->local_off, tab, c->xch, c->d_stats);
-        CUDA_TRY(cudaGetLastError());
-        c->launches += 3;
-    } else {
-        CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-    }
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    *sent = 0;
-    if (c->nranks > 1) {
-        int r = exchange_spawns(c, dst->vt, slots, sent, false);
-        if (r) return r;
-    }
-    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    TRY((compact_into<W, VT>(c, dst, slots, p)));
-    c->launches += 1;
-    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    dst->nb = 0; dst->diag_uid = 0;
-    return 0;
-}
-
 // ---- partitioned step (partition.cuh)
 // re-segment a vector for `nb` buckets (count, scan, scatter into fresh arrays); contents are unchanged
 static int rebucket(rimu_vec *v, u32 nb) {
@@ -1326,62 +1115,6 @@ extern "C" int rimu_vec_segments(rimu_vec *v, uint64_t *start_out, uint32_t *len
     return 0;
 }
 
-template <int HK, int W, class VT>
-static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, u32 nb, i64 *sent) {
-    const i64 n = src->n;
-    const bool seg = src->nb == nb && n > 0; // parents can be read by bucket segment; else their diagonal deposits go through the streams
-    TRY(ensure_seg(dst, nb));
-    TRY(ensure_diag(dst));
-    const double *src_diag = (src->diag_uid == h->uid && src->diag) ? src->diag : nullptr;
-    const u32 nlane = p.init_rule ? 3u : 1u;
-    TRY(ensure_part(c, nb, nlane));
-    TRY(ensure_heavy(c, (u64)n));
-    const size_t smem_init = (size_t)part_cap_items(W) * 8; // unsafe lane of the initiator rules
-    static bool attr_set[HK_COUNT][3][2] = {};
-    if (!attr_set[HK][W][std::is_integral<VT>::value]) {
-        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
-        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(part_smem_bytes(W) + smem_init)));
-        attr_set[HK][W][std::is_integral<VT>::value] = true;
-    }
-    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->part.rcnt + (size_t)c->part.me * nb, 0, (size_t)nlane * nb * sizeof(u32), c->stream)); // own sub-stream fills
-    if (c->part.direct) CUDA_TRY(cudaMemsetAsync(c->part.scnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->heavy.packed, 0, sizeof(u64), c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-    CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
-    if (n > 0) {
-        const i64 nchunks = (n + SPAWN_NT - 1) / SPAWN_NT;
-        const int grid = (int)(nchunks < (i64)c->sm_count * 8 ? nchunks : (i64)c->sm_count * 8);
-        spawn_part_kernel<HK, W, VT><<<grid, SPAWN_NT, 0, c->stream>>>(
-            h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->xch, c->heavy, c->d_stats);
-        spawn_heavy_kernel<HK, W, VT><<<c->sm_count * 4, SPAWN_NT, 0, c->stream>>>(
-            h->dev, p, src->keys, (const VT *)src->vals, c->part, c->xch, c->heavy, c->d_stats);
-        c->launches += 2;
-        if (!seg) {
-            diag_append_kernel<HK, W, VT><<<grid_for(n, c->sm_count, 16), RIMU_TPB, 0, c->stream>>>(
-                h->dev, p, src->keys, (const VT *)src->vals, src_diag, n, c->part, c->d_stats);
-            c->launches += 1;
-        }
-        CUDA_TRY(cudaGetLastError());
-    }
-    CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-    *sent = 0;
-    if (c->nranks > 1) {
-        int r = exchange_spawns(c, dst->vt, 0, sent, true);
-        if (r) return r;
-    }
-    CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-    SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr, src_diag};
-    SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, dst->diag};
-    const int mgrid = (int)(nb < c->merge_grid_cap ? nb : c->merge_grid_cap);
-    if (p.init_rule) merge_kernel<HK, W, VT, 0, true><<<mgrid, PART_NT, part_smem_bytes(W) + smem_init, c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
-    else merge_kernel<HK, W, VT, 0, false><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
-    CUDA_TRY(cudaGetLastError());
-    c->launches += 1;
-    CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
-    return 0;
-}
-
 // bucket count for a step on `n` local parents
 // `parents` = local parents (one rank) or the per-rank share of the global length (multi-GPU: the same number on every rank)
 static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
@@ -1398,6 +1131,8 @@ static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
 extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params *prm, rimu_vec *src, rimu_vec *dst,
                          rimu_step_stats *out) {
     TRY(check_ctx_ham(c, h));
+    const HkOps *ops = hk_ops(h);
+    if (!ops) return RIMU_ERR_INVALID;
     if (!prm || !src || !dst) return fail(RIMU_ERR_INVALID, "null argument");
     if (src == dst) return fail(RIMU_ERR_INVALID, "source and target must not alias (Interfaces/dictvectors.jl:115-117)");
     if (src->ctx != c || dst->ctx != c) return fail(RIMU_ERR_INVALID, "vectors belong to another context");
@@ -1453,15 +1188,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             }
         }
         if (multi && !(use_part && c->direct)) TRY(ensure_xch(c)); // staged exchange buffers (table method / no peer access)
-        int r = dispatch_ham(h, [&](auto tag) {
-            constexpr int HK = decltype(tag)::hk, W = decltype(tag)::w;
-            if (use_part) {
-                if (is_int) return step_part_once<HK, W, i64>(c, h, p, src, dst, nb, &sent);
-                return step_part_once<HK, W, double>(c, h, p, src, dst, nb, &sent);
-            }
-            if (is_int) return step_once<HK, W, i64>(c, h, p, src, dst, slots, &sent);
-            return step_once<HK, W, double>(c, h, p, src, dst, slots, &sent);
-        });
+        int r = ops->step(c, h, p, src, dst, use_part, is_int, nb, slots, &sent);
         if (r == RIMU_ERR_EXCHANGE_FULL) {
             // nothing was sent; drain what this rank deposited locally, then report
             if (!use_part) TRY(table_fill(c, slots));

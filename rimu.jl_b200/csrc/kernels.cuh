@@ -163,7 +163,7 @@ DEV void stat_add(double *dst, double v) { v = warp_sum(v); if ((threadIdx.x & 3
 DEV void stat_add(i64 *dst, i64 v) { v = warp_sum(v); if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd((u64 *)dst, (u64)v); }
 
 // statistics <-> packed doubles for the single per-step all-reduce (dir 0: pack, 1: unpack)
-__global__ void pack_stats_kernel(StatsDev *st, double *buf, int dir) {
+static __global__ void pack_stats_kernel(StatsDev *st, double *buf, int dir) {
     const int i = threadIdx.x;
     i64 *ints = reinterpret_cast<i64 *>(st);
     double *dbl = reinterpret_cast<double *>(reinterpret_cast<char *>(st) + RIMU_STATS_NI64 * sizeof(i64));
@@ -236,7 +236,7 @@ diag_count_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
 }
 
 // ---------------------------------------------------------------- K2: exclusive scan of block totals (single CTA)
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(const u64 *__restrict__ block_tot, i64 nblocks,
+static __global__ void __launch_bounds__(1024) scan_blocks_kernel(const u64 *__restrict__ block_tot, i64 nblocks,
                                                             u64 *__restrict__ block_base, StatsDev *st) {
     __shared__ u64 warp_tot[32];
     __shared__ u64 carry_s;
@@ -475,7 +475,7 @@ compact_kernel(TableDev tab, const StepDev p, u64 *__restrict__ out_keys, VT *__
     if (is_int) stat_add(&st->inorm1, inorm1); else stat_add(&st->norm1, norm1);
 }
 
-__global__ void table_fill_empty_kernel(u64 *slots, u64 nslots, int W) {
+static __global__ void table_fill_empty_kernel(u64 *slots, u64 nslots, int W) {
     const u64 stride = (u64)gridDim.x * blockDim.x;
     if (W == 1) {
         for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += stride)

@@ -779,7 +779,7 @@ bucket_count_kernel(const u64 *__restrict__ keys, i64 n, int nranks, u32 nb, u32
     }
 }
 // exclusive scan of counts -> seg_start (single CTA; nb is small compared with the vector); fill[] is zeroed
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 bucket_scan_kernel(const u32 *__restrict__ counts, u32 nb, u64 *__restrict__ seg_start, u32 *__restrict__ seg_len, u32 *__restrict__ fill) {
     __shared__ u64 warp_tot[32];
     __shared__ u64 carry_s;

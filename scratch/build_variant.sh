@@ -1,9 +1,11 @@
 #!/bin/bash
-# usage: scratch/build_variant.sh NAME [-DPART_NT=128 ...]   -> scratch/variants/lib_NAME.so (config-2 kernels only)
+# usage: scratch/build_variant.sh NAME [-DPART_NT=128 ...]   -> scratch/variants/lib_NAME.so (config-2 kernels only, ~20 s)
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
-/usr/local/cuda/bin/nvcc -std=c++17 -O3 --fmad=false -lineinfo -gencode arch=compute_100a,code=sm_100a \
-  -Xcompiler -fPIC -shared -DRIMU_TUNE_ONLY_MOM1D "$@" rimu.jl_b200/csrc/api.cu rimu.jl_b200/csrc/sort.cu \
-  -o scratch/variants/lib_$name.so -ldl
-echo built scratch/variants/lib_$name.so
+mkdir -p scratch/variants
+python - "$name" "$@" <<'PY'
+import sys, rimu_b200
+name, defs = sys.argv[1], sys.argv[2:]
+print("built", rimu_b200.build(defines=["-DRIMU_TUNE_ONLY_MOM1D"] + defs, out=f"scratch/variants/lib_{name}.so", kinds=[1]))
+PY
