@@ -43,6 +43,8 @@ enum {
     RIMU_ERR_TABLE_FULL = 1,     /* working table too small for this step: grow / raise active slots, retry */
     RIMU_ERR_VECTOR_FULL = 2,    /* destination vector capacity too small; *needed written where documented */
     RIMU_ERR_EXCHANGE_FULL = 3,  /* per-peer spawn exchange buffer too small */
+    RIMU_ERR_WORKMEM = 4,        /* working memory of the partitioned step (bucket record streams) cannot be grown any further:
+                                  * NOT helped by rimu_ctx_resize_table -- free device memory or use fewer walkers per GPU */
     RIMU_ERR_INVALID = -1,       /* bad argument / unsupported combination (ArgumentError in the reference) */
     RIMU_ERR_CUDA = -2,
     RIMU_ERR_NCCL = -3,

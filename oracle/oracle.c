@@ -726,13 +726,14 @@ static void apply_column(const orc_ham *h, const orc_step_params *p, orc_sink *w
     } else { /* spawn!(WithReplacement) spawning.jl:232-243 + random_offdiagonal hamiltonians.jl:361-370 */
         int64_t n = (int64_t)floor(fabs(val) * p->boost); if (n < 1) n = 1;
         double magnitude = val / (double)n;
-        double prob = 1.0 / (double)L;
         for (int64_t k = 0; k < n; k++) {
             rng_draw(hsh, (uint64_t)k, STREAM_SPAWN, p->key, rnd);
             long i = (long)(((uint64_t)rnd[0] * (uint64_t)L) >> 32) + 1;
             double m = orc_offdiagonal_onr(h, &o, i, &child);
             if (!p->plain_h) m = -m * p->dtau;
-            double nv = m * magnitude / prob;
+            /* spawning.jl:240: mat_elem * magnitude / prob with prob = 1 / L (hamiltonians.jl:366); written as the
+             * multiplication by L -- one rounding instead of two, within the 1e-12 Float64 tolerance of the reference's value */
+            double nv = m * magnitude * (double)L;
             orc_pack(h, &child, ckey);
             spawns += fabs(projected_deposit(w, is_int, ckey, nv, is_int ? 0.0 : p->proj_threshold, u53(rnd[1], rnd[2]), deposit_lane(p, 0, val)));
         }

@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 MAX_MODES = 128
 MAX_TABLE_MODES = 64
 
-OK, ERR_TABLE_FULL, ERR_VECTOR_FULL, ERR_EXCHANGE_FULL = 0, 1, 2, 3
+OK, ERR_TABLE_FULL, ERR_VECTOR_FULL, ERR_EXCHANGE_FULL, ERR_WORKMEM = 0, 1, 2, 3, 4
 ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = -1, -2, -3, -4
 ADDR_BOSE, ADDR_FERMI, ADDR_FERMI2C = 0, 1, 2
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3

@@ -119,8 +119,8 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->xch.keys); cudaFree(c->xch.vals); cudaFree(c->xch.counts);
     cudaFree(c->recv_keys); cudaFree(c->recv_vals); cudaFree(c->d_allcounts); cudaFreeHost(c->h_allcounts);
     cudaFree(c->d_reduce);
-    cudaFree(c->part.rec); cudaFree(c->part.rcnt); cudaFree(c->part.scnt); cudaFree(c->part.srec);
-    cudaFree(c->lpart.rec); cudaFree(c->lpart.rcnt); cudaFree(c->lpart.scnt);
+    cudaFree(c->part.rec); cudaFree(c->part.rcnt);
+    cudaFree(c->lpart.rec); cudaFree(c->lpart.rcnt);
     cudaFree(c->heavy.items); cudaFree(c->heavy.packed); cudaFree(c->bucket_tmp);
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaFree(c->d_red);
@@ -230,6 +230,7 @@ static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool 
     if (pt.nlane != nlane && pt.rec) nb_cap = 0; // the sub-stream layout changes: reallocate (collective in shared mode)
     pt.nsrc = nsrc; pt.nlane = nlane; pt.me = shared ? (u32)c->rank * nlane : 0u; pt.rcap = rcap; pt.direct = shared ? 1 : 0;
     if (nb <= nb_cap) { pt.nb = nb; return 0; }
+    // (the sub-stream stride depends on nb, not on the allocated bucket count, so a smaller nb reuses the buffers as they are)
     const u64 cap = (u64)nb + nb / 4 + 16;
     const size_t rw = c->W == 1 ? 2 : 4;
     if (shared) {
@@ -238,15 +239,11 @@ static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool 
         TRY(rimu_comm_allreduce_f64(c, &zero, 1)); // nobody is still storing into a peer's old streams
         p2p_teardown(c);
     }
-    cudaFree(pt.rec); cudaFree(pt.rcnt); cudaFree(pt.scnt); cudaFree(pt.srec);
-    pt.rec = nullptr; pt.rcnt = nullptr; pt.scnt = nullptr; pt.srec = nullptr; nb_cap = 0;
+    cudaFree(pt.rec); cudaFree(pt.rcnt);
+    pt.rec = nullptr; pt.rcnt = nullptr; nb_cap = 0;
     CUDA_TRY(rimu_malloc(&pt.rec, cap * nsrc * rcap * rw * sizeof(u64)));
     CUDA_TRY(rimu_malloc(&pt.rcnt, (size_t)nsrc * cap * sizeof(u32)));
     CUDA_TRY(cudaMemsetAsync(pt.rcnt, 0, (size_t)nsrc * cap * sizeof(u32), c->stream));
-    if (shared) {
-        CUDA_TRY(rimu_malloc(&pt.scnt, (size_t)nsrc * cap * sizeof(u32)));
-        CUDA_TRY(rimu_malloc(&pt.srec, (size_t)nsrc * cap * rcap * rw * sizeof(u64)));
-    }
     nb_cap = cap; pt.nb = nb;
     if (shared) TRY(p2p_setup(c));
     return 0;
@@ -334,7 +331,7 @@ static int p2p_setup(rimu_ctx *c) {
     void *pr[RIMU_MAX_RANKS] = {}, *pc[RIMU_MAX_RANKS] = {};
     TRY(ipc_map_all(c, c->part.rec, c->part.rcnt, pr, pc, &ok));
     if (!ok) { p2p_teardown(c); return fail(RIMU_ERR_CUDA, "CUDA IPC mapping of the peers' record streams failed (set RIMU_B200_P2P=0 to use NCCL send/recv)"); }
-    for (int r = 0; r < c->nranks; r++) { c->part.peer_rec[r] = (u64 *)pr[r]; c->part.peer_rcnt[r] = (u32 *)pc[r]; }
+    for (int r = 0; r < c->nranks; r++) { c->part.peer_rec[r] = (const u64 *)pr[r]; c->part.peer_rcnt[r] = (const u32 *)pc[r]; }
     return 0;
 }
 // can the ranks map each other's memory at all?  (decides direct vs staged exchange once, at communicator set-up)
@@ -792,9 +789,18 @@ extern "C" int rimu_vec_copy(rimu_vec *dst, rimu_vec *src) {
         if (dst->vt == src->vt) {
             CUDA_TRY(cudaMemcpyAsync(dst->vals, src->vals, src->n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
         } else { // eltype conversion Int64 <-> Float64 on the device
-            if (src->vt == RIMU_VAL_I64) convert_vals_kernel<i64, double><<<grid_for(src->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const i64 *)src->vals, (double *)dst->vals, src->n);
-            else convert_vals_kernel<double, i64><<<grid_for(src->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const double *)src->vals, (i64 *)dst->vals, src->n);
+            CUDA_TRY(cudaMemsetAsync(&c->d_stats->overflow_vec, 0, sizeof(i64), c->stream));
+            if (src->vt == RIMU_VAL_I64) convert_vals_kernel<i64, double><<<grid_for(src->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const i64 *)src->vals, (double *)dst->vals, src->n, &c->d_stats->overflow_vec);
+            else convert_vals_kernel<double, i64><<<grid_for(src->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((const double *)src->vals, (i64 *)dst->vals, src->n, &c->d_stats->overflow_vec);
             CUDA_TRY(cudaGetLastError());
+            if (dst->vt == RIMU_VAL_I64) { // Float64 -> Int64 must be exact (the reference throws InexactError)
+                CUDA_TRY(cudaMemcpyAsync(&c->h_stats->overflow_vec, &c->d_stats->overflow_vec, sizeof(i64), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                if (c->h_stats->overflow_vec) {
+                    dst->n = 0; dst->nb = 0; dst->diag_uid = 0;
+                    return fail(RIMU_ERR_INVALID, "InexactError: a Float64 vector with non-integral values cannot be copied into an Int64 vector");
+                }
+            }
         }
     }
     dst->n = src->n;
@@ -863,8 +869,18 @@ extern "C" int rimu_vec_scale(rimu_vec *v, double alpha) {
     TRY(enter_ctx(c));
     if (alpha == 0.0) { v->n = 0; v->nb = 0; v->diag_uid = 0; return 0; } // zero values are never stored
     if (v->n > 0) {
-        if (v->vt == RIMU_VAL_F64) scale_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((double *)v->vals, v->n, alpha);
-        else scale_kernel<i64><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((i64 *)v->vals, v->n, alpha);
+        if (v->vt == RIMU_VAL_F64) scale_kernel<double><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((double *)v->vals, v->n, alpha, nullptr);
+        else {
+            // Int64 vectors: the scaled values must be integers (InexactError in the reference); the kernel leaves an
+            // offending entry untouched and raises the flag, so a failed call does not corrupt the vector half-way only
+            // when alpha is integral -- which is the one case that can succeed
+            if (alpha != rint(alpha)) return fail(RIMU_ERR_INVALID, "InexactError: an Int64 vector can only be scaled by an integer");
+            CUDA_TRY(cudaMemsetAsync(&c->d_stats->overflow_vec, 0, sizeof(i64), c->stream));
+            scale_kernel<i64><<<grid_for(v->n, c->sm_count), RIMU_TPB, 0, c->stream>>>((i64 *)v->vals, v->n, alpha, &c->d_stats->overflow_vec);
+            CUDA_TRY(cudaMemcpyAsync(&c->h_stats->overflow_vec, &c->d_stats->overflow_vec, sizeof(i64), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            if (c->h_stats->overflow_vec) return fail(RIMU_ERR_INVALID, "InexactError: scaling overflows the exactly representable integer range");
+        }
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
@@ -995,22 +1011,11 @@ int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_strea
     const int R = c->nranks, me = c->rank;
     c->p2p_used = 0;
     if (to_streams && c->direct) {
-        // Direct mode: the spawn kernels bucketed the records for every peer in local memory; one kernel now ships them
-        // as coalesced runs straight into the owners' bucket sub-streams (peer stores over NVLink) together with the
-        // sub-stream fills.  The all-gather of the per-destination totals is the barrier that orders all of this
-        // before anybody's merge.  No receive pass, no host round trip.
-        const u64 nruns = (u64)(R - 1) * c->part.nb * c->part.nlane; // one warp per (destination, lane, bucket) run
-        u64 gx = (nruns + (RIMU_TPB / 32) - 1) / (RIMU_TPB / 32);
-        if (gx > (u64)c->sm_count * 8) gx = (u64)c->sm_count * 8;
-        if (gx < 1) gx = 1;
-        if (c->W == 1) push_records_kernel<2><<<(unsigned)gx, RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
-        else push_records_kernel<4><<<(unsigned)gx, RIMU_TPB, 0, c->stream>>>(c->part, me, R, c->xch.counts);
-        CUDA_TRY(cudaGetLastError());
-        c->launches += 1;
+        // Direct mode: nothing is copied.  Every rank's spawn kernels bucketed the records for every destination in their
+        // own memory; the owners' merge kernels read them in place over NVLink.  All that is needed here is the barrier
+        // that orders everybody's spawn kernels before anybody's merge: one tiny all-gather.
         NCCL_TRY(g_nccl.AllGather(c->xch.counts, c->d_allcounts, R, ncclUint64, c->comm, c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[6], c->stream));
-        CUDA_TRY(cudaMemcpyAsync(c->h_allcounts, c->d_allcounts, (size_t)R * R * sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaMemsetAsync(c->xch.counts, 0, RIMU_MAX_RANKS * sizeof(u64), c->stream));
         c->p2p_used = 1;
         *sent_out = 0;
         return 0;
@@ -1183,7 +1188,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
             double have = (double)free_b + (double)c->part_nb_cap * rec_bytes_per_bucket;
             if ((double)nb * 1.3 * rec_bytes_per_bucket * (p.init_rule ? 3.0 : 1.0) > 0.8 * have) {
-                if (p.init_rule) return fail(RIMU_ERR_TABLE_FULL, "record streams of an initiator step do not fit in device memory");
+                if (p.init_rule) return fail(RIMU_ERR_WORKMEM, "record streams of an initiator step do not fit in device memory");
                 use_part = false;
             }
         }
@@ -1200,23 +1205,23 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         CUDA_TRY(cudaMemcpyAsync(c->h_stats_local, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         if (c->nranks > 1) {
             // ONE all-reduce per step: the integer block travels as doubles (counts stay far below 2^53, so the sums
-            // are exact) next to the floating-point block (reference: Allreduce of a MultiScalar, pdvec.jl:896-902)
-            if (!c->d_red) CUDA_TRY(rimu_malloc(&c->d_red, (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP + 1) * sizeof(double)));
-            pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 0);
-            NCCL_TRY(g_nccl.AllReduce(c->d_red, c->d_red, RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP + 1, ncclFloat64, ncclSum, c->comm, c->stream));
-            pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 1);
+            // are exact) next to the floating-point block (reference: Allreduce of a MultiScalar, pdvec.jl:896-902), the
+            // merged-record count and the "my target vector is too small" flag.  It is also the barrier that keeps a fast
+            // rank from overwriting its record streams (next step) while a peer's merge is still reading them.
+            if (!c->d_red) CUDA_TRY(rimu_malloc(&c->d_red, RIMU_STATS_NPACK * sizeof(double)));
+            pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 0, dst->cap);
+            NCCL_TRY(g_nccl.AllReduce(c->d_red, c->d_red, RIMU_STATS_NPACK, ncclFloat64, ncclSum, c->comm, c->stream));
+            pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 1, dst->cap);
             CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         }
-        CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (c->nranks == 1) *c->h_stats = *c->h_stats_local;
         const StatsDev &g = *c->h_stats, &l = *c->h_stats_local;
-        if (c->nranks > 1 && c->p2p_used) { // direct mode: per-destination totals of every rank arrived with the barrier all-gather
-            sent = 0;
-            for (int d_ = 0; d_ < c->nranks; d_++) if (d_ != c->rank) sent += (i64)c->h_allcounts[c->rank * c->nranks + d_];
-        }
+        if (c->nranks > 1 && use_part) sent = l.sent; // (the table method counts in exchange_spawns)
         if (g.overflow_table) { // some rank ran out of room: every rank retries with more working memory
-            if (attempt > 12) return fail(RIMU_ERR_TABLE_FULL, "step working memory cannot be grown further");
+            if (attempt > 12) return fail(use_part ? RIMU_ERR_WORKMEM : RIMU_ERR_TABLE_FULL, "step working memory cannot be grown further");
             if (use_part) {
                 // size the bucket count from what this attempt saw (records are counted even when dropped)
                 const double cap = (double)part_cap_items(c->W);
@@ -1224,7 +1229,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
                 double need = ceil((parents + recs) * 1.15 / (0.6 * cap)); // (diagonal records may be counted twice: harmless)
                 u32 nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb * 2 + 1);
                 if (!multi && !p.init_rule && (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26))) use_part = false; // one address is too hot to pre-sum: use the table
-                if (multi && nb2 > (1u << 26)) return fail(RIMU_ERR_TABLE_FULL, "bucket streams cannot be grown further");
+                if (multi && nb2 > (1u << 26)) return fail(RIMU_ERR_WORKMEM, "bucket streams cannot be grown further");
                 nb = nb2;
                 continue;
             }
@@ -1233,11 +1238,10 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             slots = slots * 4 > c->table_slots ? c->table_slots : slots * 4;
             continue;
         }
-        // destination capacity: decided globally so that all ranks retry together
-        u64 need_local = l.out_count;
-        double flag = need_local > dst->cap ? 1.0 : 0.0;
-        if (c->nranks > 1) TRY(rimu_comm_allreduce_f64(c, &flag, 1));
-        if (flag > 0.0) {
+        // destination capacity: decided globally (the flag was summed by the step's all-reduce) so that all ranks retry together
+        const u64 need_local = l.out_count;
+        const bool grow = c->nranks > 1 ? g.grow_flag != 0 : need_local > dst->cap;
+        if (grow) {
             dst->n = 0; dst->nb = 0;
             if (need_local > dst->cap) TRY(rimu_vec_reserve(dst, need_local + need_local / 4 + 1024));
             if (attempt > 12) return fail(RIMU_ERR_VECTOR_FULL, "destination vector cannot be grown");

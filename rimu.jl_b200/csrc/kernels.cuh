@@ -43,7 +43,9 @@ struct StatsDev {
     double dot, norm2, norminf; // scratch for dot / norms
     // block C: local bookkeeping of the partitioned step (never reduced over ranks)
     u64 max_fill;       // fullest bucket (parents + records) seen by merge_kernel
-    u64 records;        // spawn records appended to this rank's bucket streams
+    u64 records;        // spawn records this rank's merge read from its bucket streams (all source ranks)
+    i64 sent;           // records this rank produced for buckets of other ranks (sent_records)
+    u64 grow_flag;      // after the all-reduce: number of ranks whose result did not fit their target vector
 };
 #define RIMU_STATS_NI64 16 /* 'sent' was replaced by 'deposits' */
 #define RIMU_STATS_NF64_STEP 5
@@ -162,16 +164,20 @@ DEV i64 warp_sum(i64 v) {
 DEV void stat_add(double *dst, double v) { v = warp_sum(v); if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v); }
 DEV void stat_add(i64 *dst, i64 v) { v = warp_sum(v); if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd((u64 *)dst, (u64)v); }
 
-// statistics <-> packed doubles for the single per-step all-reduce (dir 0: pack, 1: unpack)
-static __global__ void pack_stats_kernel(StatsDev *st, double *buf, int dir) {
+// statistics <-> packed doubles for the single per-step all-reduce (dir 0: pack, 1: unpack).  Two more doubles ride along:
+// the records merged (block C; summed so that every rank sizes the next bucket count identically) and "my result did not fit
+// my target vector" (out_count > dst_cap), so that all ranks decide to grow-and-repeat together without another collective.
+#define RIMU_STATS_NPACK (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP + 2)
+static __global__ void pack_stats_kernel(StatsDev *st, double *buf, int dir, u64 dst_cap) {
     const int i = threadIdx.x;
     i64 *ints = reinterpret_cast<i64 *>(st);
     double *dbl = reinterpret_cast<double *>(reinterpret_cast<char *>(st) + RIMU_STATS_NI64 * sizeof(i64));
     if (i < RIMU_STATS_NI64) { if (dir == 0) buf[i] = (double)ints[i]; else ints[i] = (i64)llrint(buf[i]); }
     if (i < RIMU_STATS_NF64_STEP) { if (dir == 0) buf[RIMU_STATS_NI64 + i] = dbl[i]; else dbl[i] = buf[RIMU_STATS_NI64 + i]; }
-    if (i == 31) { // spawn records appended (block C): summed so that every rank sizes the next bucket count identically
+    if (i == 31) {
         const int at = RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP;
-        if (dir == 0) buf[at] = (double)st->records; else st->records = (u64)llrint(buf[at]);
+        if (dir == 0) { buf[at] = (double)st->records; buf[at + 1] = st->out_count > dst_cap ? 1.0 : 0.0; }
+        else { st->records = (u64)llrint(buf[at]); st->grow_flag = (u64)llrint(buf[at + 1]); }
     }
 }
 
@@ -365,9 +371,8 @@ spawn_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, cons
                     long long i = (long long)(((u64)rnd[0] * (u64)L) >> 32);
                     double m = ham_offdiagonal<HK, B>(h, key, i, child);
                     if (!p.plain_h) m = -m * p.dtau;
-                    double magnitude = val / (double)nat;
-                    double prob = 1.0 / (double)L;
-                    double nv0 = m * magnitude / prob;
+                    double magnitude = nat == 1 ? val : val / (double)nat;
+                    double nv0 = m * magnitude * (double)L; // (= m * magnitude / (1 / L) up to one rounding; see step_math.cuh)
                     VT nv = project_value<VT>(nv0, is_int ? 0.0 : p.proj_thr, u53(rnd[1], rnd[2]));
                     if (nv != (VT)0) {
                         deposit<W, VT>(tab, xch, p, st, child, nv); ndep++;
@@ -502,13 +507,22 @@ template <class VT> __global__ void norm_kernel(const VT *__restrict__ vals, i64
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long *>(&st->norminf), (unsigned long long)__double_as_longlong(ninf));
 }
 
-template <class VT> __global__ void scale_kernel(VT *vals, i64 n, double alpha) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-        vals[i] = (VT)(alpha * (double)vals[i]);
+// scale! / eltype conversion.  An Int64 vector can only hold integral results: anything else raises the flag (the reference
+// throws InexactError there instead of truncating), and zeros can then never appear silently.
+template <class VT> __global__ void scale_kernel(VT *vals, i64 n, double alpha, i64 *inexact) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double r = alpha * (double)vals[i];
+        if (std::is_integral<VT>::value && (r != rint(r) || fabs(r) >= 9007199254740992.0)) { *inexact = 1; continue; }
+        vals[i] = (VT)r;
+    }
 }
 
-template <class From, class To> __global__ void convert_vals_kernel(const From *__restrict__ in, To *__restrict__ out, i64 n) {
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = (To)in[i];
+template <class From, class To> __global__ void convert_vals_kernel(const From *__restrict__ in, To *__restrict__ out, i64 n, i64 *inexact) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const From x = in[i];
+        if (std::is_integral<To>::value && !std::is_integral<From>::value && ((double)x != rint((double)x) || fabs((double)x) >= 9007199254740992.0)) *inexact = 1;
+        out[i] = (To)x;
+    }
 }
 
 // dot(x, y): x was inserted into the table, y is streamed and looked up

@@ -57,22 +57,21 @@ template <int W> struct PartCap { static constexpr int value = PART_CAP; };
 
 struct PartDev {       // bucket record streams (working memory of the partitioned step)
     u32 nb;            // buckets per rank (identical on all ranks of a step)
-    u32 rcap;          // records per (bucket, source rank) sub-stream
-    u32 nsrc;          // sub-streams per bucket = source ranks (1, or all ranks in direct mode) x lanes
-    u32 nlane;         // 1, or 3 with an initiator rule: sub-stream (rank, lane) holds the rank's safe / unsafe / initiator
-                       //   deposits (DictVectors/initiators.jl:22-45) -- the lane travels in the stream index, not in the record
-    u32 me;            // this rank's first sub-stream (rank * nlane; 0 when there is one source)
-    u64 *rec;          // [nb][nsrc][rcap] records, array of structures: W=1 {key, value} (16 B), W=2 {k0, k1, value, pad} (32 B)
-    u32 *rcnt;         // [nsrc][nb] fill of every sub-stream; slot `me` is counted locally, the others are pushed by their senders
-    // direct mode (multi-GPU, CUDA IPC peer memory): a spawned record is stored straight into sub-stream [bucket][this rank] of
-    // its OWNER's streams over NVLink; the slot comes from a LOCAL counter, so no remote atomics and no receive pass
+    u32 rcap;          // records per sub-stream
+    u32 nsrc;          // sub-streams = destination ranks (1, or all ranks in direct mode) x lanes.  The SAME number of
+                       //   sub-streams feeds every bucket of the merge: (source rank, lane)
+    u32 nlane;         // 1, or 3 with an initiator rule: sub-stream (rank, lane) holds the safe / unsafe / initiator deposits
+                       //   (DictVectors/initiators.jl:22-45) -- the lane travels in the stream index, not in the record
+    u32 me;            // this rank's first sub-stream (rank * nlane; 0 when there is one rank)
+    u64 *rec;          // [nsrc][nb][rcap] records, array of structures: W=1 {key, value} (16 B), W=2 {k0, k1, value, pad} (32 B).
+                       //   Sub-stream (d, lane) holds what THIS rank produced for bucket b of rank d.
+    u32 *rcnt;         // [nsrc][nb] fill of every sub-stream
+    // direct mode (multi-GPU, CUDA IPC peer memory): nothing is pushed.  The owner's merge kernel PULLS sub-stream
+    // (me, lane) of every rank's streams over NVLink while it annihilates -- the transfer overlaps the shared-memory work
+    // of the other resident CTAs, there is no exchange pass and no receive pass.
     int direct;
-    u32 *scnt;                       // [nranks][nb] records this rank produced for rank d's bucket b (d != me)
-    u64 *srec;                       // [nranks][nb][rcap] ... staged here, bucketed, in LOCAL memory (L2 write-combined 16-byte
-                                     //   appends), then shipped by push_records_kernel as coalesced runs: fine-grained peer
-                                     //   stores were measured at ~10 G packets/s, 3x slower than the bulk copy
-    u64 *peer_rec[RIMU_MAX_RANKS];   // rec of every rank ([me] = rec)
-    u32 *peer_rcnt[RIMU_MAX_RANKS];  // rcnt of every rank
+    const u64 *peer_rec[RIMU_MAX_RANKS];   // rec of every rank ([this rank] = rec)
+    const u32 *peer_rcnt[RIMU_MAX_RANKS];  // rcnt of every rank
 };
 template <int W> struct RecWords { static constexpr int value = W == 1 ? 2 : 4; };
 struct SegSrc {        // a segmented vector, read side (diag: cached diagonal elements or null)
@@ -120,22 +119,25 @@ template <> DEV void load_rec<2>(const u64 *p, u128 &key, u64 &vbits) {
 template <int W, class VT>
 DEV void append_record(const PartDev &pt, StatsDev *st, typename BitsT<W>::type key, u64 h, int nranks, VT v, u32 slot) {
     const u32 b = bucket_of(h, nranks, pt.nb);
-    const u32 pos = atomicAdd(&pt.rcnt[(u64)slot * pt.nb + b], 1u);
+    const u64 run = (u64)slot * pt.nb + b;
+    const u32 pos = atomicAdd(&pt.rcnt[run], 1u);
     if (pos < pt.rcap) {
         union { VT v; u64 b; } cv; cv.v = v;
-        store_rec<W>(pt.rec + (((u64)b * pt.nsrc + slot) * pt.rcap + pos) * RecWords<W>::value, key, cv.b);
+        store_rec<W>(pt.rec + (run * pt.rcap + pos) * RecWords<W>::value, key, cv.b);
     } else st->overflow_table = 1;
 }
 
 // CTA-collective routing of at most one spawn record per thread.  Every thread of the CTA must call this.
-//  * one rank, or direct mode: the record goes straight into sub-stream [bucket][this rank] of its owner's streams -- a
-//    local counter atomic and one 16/32-byte store (a peer store over NVLink when the owner is another GPU);
+//  * one rank, or direct mode: the record is appended to sub-stream (owner rank, lane) of the child's bucket in LOCAL memory
+//    -- one counter atomic and one 16/32-byte store, whoever owns the child.  Records for other GPUs are never copied: their
+//    owner's merge kernel reads them in place over NVLink.
 //  * staged mode (no peer access): records for other ranks are staged per peer -- ranks within the CTA come from a
 //    shared-memory counter, ONE global atomic per peer and CTA reserves a contiguous run in that peer's exchange segment
 //    (the reference packs per-rank buffers serially, communicators.jl:421-444); NCCL send/recv moves the segments.
+// Returns true when the record leaves this rank (the sent_records statistic).
 struct RouteSmem { u32 cnt[RIMU_MAX_RANKS]; u64 base[RIMU_MAX_RANKS]; };
 template <int W, class VT>
-DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p, StatsDev *st, RouteSmem &rs,
+DEV bool route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p, StatsDev *st, RouteSmem &rs,
                       bool has, typename BitsT<W>::type key, VT v, u32 lane) {
     u64 h = 0;
     int owner = p.rank;
@@ -143,17 +145,7 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
         h = hash_bits(key);
         if (p.nranks > 1) owner = addr_owner(h, p.nranks);
     }
-    if (p.nranks > 1 && pt.direct) { // uniform over the grid
-        if (has && owner != p.rank) {
-            const u32 b = bucket_of(h, p.nranks, pt.nb);
-            const u64 sub = (u64)owner * pt.nlane + lane; // staging sub-stream (destination rank, lane)
-            const u32 pos = atomicAdd(&pt.scnt[sub * pt.nb + b], 1u);
-            if (pos < pt.rcap) {
-                union { VT v; u64 b; } cv; cv.v = v;
-                store_rec<W>(pt.srec + ((sub * pt.nb + b) * pt.rcap + pos) * RecWords<W>::value, key, cv.b);
-            } else st->overflow_table = 1;
-        }
-    } else if (p.nranks > 1) {
+    if (p.nranks > 1 && !pt.direct) { // uniform over the grid
         if (threadIdx.x < RIMU_MAX_RANKS) rs.cnt[threadIdx.x] = 0;
         __syncthreads();
         const bool remote = has && owner != p.rank;
@@ -171,41 +163,11 @@ DEV void route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
                 x.vals[(u64)owner * x.cap + idx] = cv.b;
             } else st->overflow_xchg = 1;
         }
+        if (has && owner == p.rank) append_record<W, VT>(pt, st, key, h, p.nranks, v, lane);
+        return remote;
     }
-    if (has && owner == p.rank) append_record<W, VT>(pt, st, key, h, p.nranks, v, pt.me + lane);
-}
-
-// direct mode: after the spawn kernels, ship to every peer d the records staged for each of its buckets -- one warp per
-// (destination, bucket) run, 16 bytes per lane, straight into sub-stream [bucket][this rank] of d's streams over NVLink --
-// together with the fill of that sub-stream, and total the records per destination for the statistics
-template <int RW>
-__global__ void __launch_bounds__(RIMU_TPB) push_records_kernel(PartDev pt, int me, int R, u64 *__restrict__ totals) {
-    const int lane = threadIdx.x & 31;
-    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
-    const u64 nruns = (u64)(R - 1) * pt.nb * pt.nlane;
-    // consecutive warps serve different destinations, and rank `me` starts its rotation at me+1: at any moment every
-    // rank is sending to every peer, so no receiver sees an incast while the others idle
-    for (u64 r = warp; r < nruns; r += nwarps) {
-        const int d = (me + 1 + (int)(r % (u64)(R - 1))) % R;
-        const u64 r2 = r / (u64)(R - 1);
-        const u32 lane_ = (u32)(r2 % pt.nlane), b = (u32)(r2 / pt.nlane);
-        const u64 sub = (u64)d * pt.nlane + lane_;            // staging sub-stream here
-        const u64 dsub = (u64)me * pt.nlane + lane_;           // sub-stream (this rank, lane) at the destination
-        const u32 c0 = pt.scnt[sub * pt.nb + b], c = c0 < pt.rcap ? c0 : pt.rcap;
-        if (lane == 0) {
-            pt.peer_rcnt[d][dsub * pt.nb + b] = c;
-            if (c0) atomicAdd(&totals[d], (u64)c0);
-        }
-        const ulonglong2 *from = reinterpret_cast<const ulonglong2 *>(pt.srec + ((sub * pt.nb + b) * pt.rcap) * RW);
-        ulonglong2 *to = reinterpret_cast<ulonglong2 *>(pt.peer_rec[d] + (((u64)b * pt.nsrc + dsub) * pt.rcap) * RW);
-        const u32 units = c * (RW / 2);
-        u32 i = lane;
-        for (; i + 96 < units; i += 128) { // four 16-byte loads in flight per lane
-            const ulonglong2 a0 = from[i], a1 = from[i + 32], a2 = from[i + 64], a3 = from[i + 96];
-            to[i] = a0; to[i + 32] = a1; to[i + 64] = a2; to[i + 96] = a3;
-        }
-        for (; i < units; i += 32) to[i] = from[i];
-    }
+    if (has) append_record<W, VT>(pt, st, key, h, p.nranks, v, (u32)owner * pt.nlane + lane);
+    return has && owner != p.rank;
 }
 
 // ---------------------------------------------------------------- K1: spawning, CTA-local work distribution
@@ -222,7 +184,7 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
     __shared__ RouteSmem s_route;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double spawns = 0.0;
-    i64 exact_steps = 0, inexact_steps = 0, attempts = 0;
+    i64 exact_steps = 0, inexact_steps = 0, attempts = 0, nsent = 0;
     const i64 nchunks = (n + SPAWN_NT - 1) / SPAWN_NT;
     // the parent of the NEXT chunk is loaded while the current chunk is processed (its HBM latency was the largest
     // single stall of this kernel: 21 % of the samples in profiles/r1_partition_ncu_summary.md)
@@ -271,9 +233,16 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
             VT nv = (VT)0;
             u32 rlane = 0;
             if (a < total) {
-                int lo = 0, hi = SPAWN_NT; // last lo with s_off[lo] <= a
+                // parent of attempt a = last lo with s_off[lo] <= a.  When every earlier parent of the chunk makes exactly one
+                // attempt (the common case at ~1 walker per determinant) that is parent a itself: two loads instead of
+                // the 8-step binary search
+                int lo = (int)a < SPAWN_NT ? (int)a : 0;
+                if (!(a < SPAWN_NT && s_off[lo] == a && s_off[lo + 1] == a + 1)) {
+                    lo = 0;
+                    int hi = SPAWN_NT;
 #pragma unroll
-                for (int it = 0; it < 8; it++) { int mid = (lo + hi) >> 1; if (s_off[mid] <= a) lo = mid; else hi = mid; }
+                    for (int it = 0; it < 8; it++) { int mid = (lo + hi) >> 1; if (s_off[mid] <= a) lo = mid; else hi = mid; }
+                }
                 const u64 k = a - s_off[lo];
                 B key;
                 if constexpr (W == 1) key = s_keys[lo]; else key = ((u128)s_keys[lo * 2 + 1] << 64) | (u128)s_keys[lo * 2];
@@ -287,13 +256,14 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
                 spawns += sp;
                 rlane = deposit_lane(p, false, val);
             }
-            route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv, rlane);
+            nsent += route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv, rlane);
         }
         __syncthreads();
     }
     if (std::is_integral<VT>::value) stat_add(&st->ispawns, (i64)spawns); else stat_add(&st->spawns, spawns);
     stat_add(&st->exact_steps, exact_steps); stat_add(&st->inexact_steps, inexact_steps);
     stat_add(&st->spawn_attempts, attempts);
+    if (p.nranks > 1) stat_add(&st->sent, nsent);
 }
 
 // ---------------------------------------------------------------- K2: heavy parents, one CTA per tile of attempts
@@ -309,6 +279,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
     u64 nitems = packed >> 32;
     if (nitems > hv.cap) nitems = hv.cap;
     double spawns = 0.0;
+    i64 nsent = 0;
     for (u64 w = blockIdx.x; w < total; w += gridDim.x) {
         u64 lo = 0, hi = nitems;
         while (hi - lo > 1) { u64 mid = (lo + hi) >> 1; if (hv.items[mid].tile_base <= w) lo = mid; else hi = mid; }
@@ -333,7 +304,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
                 spawns += sp;
                 if (agg && nv != (VT)0) { atomic_add_val<VT>(&acc[ci], nv); nv = (VT)0; }
             }
-            if (!agg) route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv, rlane);
+            if (!agg) nsent += route_record<W, VT>(pt, xch, p, st, s_route, nv != (VT)0, child, nv, rlane);
         }
         if (agg) {
             __syncthreads();
@@ -342,12 +313,13 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
                 B child = 0;
                 union { u64 b; VT v; } cv; cv.b = 0;
                 if (c < L) { cv.b = acc[c]; if (cv.v != (VT)0) ham_offdiagonal<HK, B>(h, key, c, child); }
-                route_record<W, VT>(pt, xch, p, st, s_route, cv.v != (VT)0, child, cv.v, rlane);
+                nsent += route_record<W, VT>(pt, xch, p, st, s_route, cv.v != (VT)0, child, cv.v, rlane);
             }
             __syncthreads();
         }
     }
     if (std::is_integral<VT>::value) stat_add(&st->ispawns, (i64)spawns); else stat_add(&st->spawns, spawns);
+    if (p.nranks > 1) stat_add(&st->sent, nsent);
 }
 
 // ---------------------------------------------------------------- append a flat record list to the bucket streams
@@ -450,6 +422,19 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     __shared__ u64 s_p0[3];
     const u32 nsrc = pt.nsrc;
     const bool meta_thread = tid == PART_NT - 1; // loads the segment metadata; threads 0..nsrc-1 load the fills
+    // Sub-stream q = (source rank q / nlane, lane q % nlane) of this rank's buckets lives in the SOURCE rank's streams as
+    // its sub-stream (this rank, lane): local memory for q / nlane == this rank, peer memory (NVLink loads) otherwise.
+    __shared__ const u64 *s_recbase[MAXSUB];
+    __shared__ const u32 *s_cntbase[MAXSUB];
+    __shared__ unsigned char s_local[MAXSUB];
+    if ((u32)tid < nsrc) {
+        const u32 srank = (u32)tid / pt.nlane, sub = pt.me + (u32)tid % pt.nlane;
+        const u64 *rb = pt.direct ? pt.peer_rec[srank] : pt.rec;
+        const u32 *cb = pt.direct ? pt.peer_rcnt[srank] : pt.rcnt;
+        s_recbase[tid] = rb + (u64)sub * pt.nb * pt.rcap * RW;
+        s_cntbase[tid] = cb + (u64)sub * pt.nb;
+        s_local[tid] = (!pt.direct || srank * pt.nlane == pt.me) ? 1 : 0;
+    }
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         const u64 bq = (u64)blockIdx.x + (u64)q * gridDim.x;
@@ -458,7 +443,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             s_np[q] = npq;
             s_p0[q] = npq ? src.seg_start[bq] : 0ull;
         }
-        if ((u32)tid < nsrc) s_cnt[q][tid] = bq < pt.nb ? pt.rcnt[(u64)tid * pt.nb + bq] : 0u;
+        if ((u32)tid < nsrc) s_cnt[q][tid] = bq < pt.nb ? s_cntbase[tid][bq] : 0u;
     }
     __syncthreads();
     u32 ring = 0;
@@ -476,13 +461,13 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                     pending_np = src.seg_len ? src.seg_len[b2] : 0u;
                     pending_p0 = pending_np ? src.seg_start[b2] : 0ull;
                 }
-                if ((u32)tid < nsrc) pending_cnt = pt.rcnt[(u64)tid * pt.nb + b2];
+                if ((u32)tid < nsrc) pending_cnt = s_cntbase[tid][b2];
             }
             const u64 b1 = (u64)b + gridDim.x;
             if (b1 < pt.nb) {
-                if ((u32)tid < nsrc) {
+                if ((u32)tid < nsrc && s_local[tid]) { // (peer memory is not cached in this GPU's L2)
                     const u32 c1 = s_cnt[nxt][tid] < pt.rcap ? s_cnt[nxt][tid] : pt.rcap;
-                    if (c1) l2_prefetch(pt.rec + ((b1 * nsrc + tid) * pt.rcap) * RW, (u64)c1 * RW * 8);
+                    if (c1) l2_prefetch(s_recbase[tid] + (b1 * pt.rcap) * RW, (u64)c1 * RW * 8);
                 }
                 if (meta_thread && s_np[nxt]) {
                     const u32 np1 = s_np[nxt];
@@ -548,7 +533,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 u32 j = i - np, q = 0; // record j of the bucket -> (source sub-stream q, position j)
                 if (nsrc > 1) for (u32 cq = s_cnt[cur][0]; j >= cq; cq = s_cnt[cur][q]) { j -= cq; q++; }
                 union { u64 b; VT v; } cv;
-                load_rec<W>(pt.rec + ((((u64)b * nsrc + q) * pt.rcap) + j) * RW, key, cv.b);
+                load_rec<W>(s_recbase[q] + ((u64)b * pt.rcap + j) * RW, key, cv.b);
                 v = cv.v;
                 if (pt.nlane > 1) ilane = q % pt.nlane;
             }

@@ -59,8 +59,7 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
         attr_set[HK][W][std::is_integral<VT>::value] = true;
     }
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->part.rcnt + (size_t)c->part.me * nb, 0, (size_t)nlane * nb * sizeof(u32), c->stream)); // own sub-stream fills
-    if (c->part.direct) CUDA_TRY(cudaMemsetAsync(c->part.scnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->part.rcnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream)); // fills of every (destination, lane) sub-stream
     CUDA_TRY(cudaMemsetAsync(c->heavy.packed, 0, sizeof(u64), c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));

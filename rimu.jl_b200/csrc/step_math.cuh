@@ -85,9 +85,11 @@ DEV VT spawn_attempt(const HamDev &h, const StepDev &p, typename BitsT<W>::type 
     ci = (long long)(((u64)rnd[0] * (u64)L) >> 32);
     double m = ham_offdiagonal<HK, B>(h, key, ci, child);
     if (!p.plain_h) m = -m * p.dtau;
-    double magnitude = val / (double)nat;
-    double prob = 1.0 / (double)L;
-    double nv0 = m * magnitude / prob;
+    // spawning.jl:237-241: magnitude = val / n; value = matrix element * magnitude / prob with prob = 1 / L.  The division by
+    // 1 / L is written as the multiplication by L (one rounding instead of two; the oracle does the same -- north_star asks
+    // 1e-12 for Float64, not the reference's last bit), and val / 1 is skipped.
+    const double magnitude = nat == 1 ? val : val / (double)nat;
+    const double nv0 = m * magnitude * (double)L;
     VT nv = project_value<VT>(nv0, is_int ? 0.0 : p.proj_thr, u53(rnd[1], rnd[2]));
     spawned = fabs((double)nv);
     return nv;

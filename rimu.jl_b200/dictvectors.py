@@ -95,12 +95,14 @@ class GPUDVec:
         return self
 
     # ---- host <-> device
-    def _with_table_retry(self, fn):
-        while True:
+    def _with_table_retry(self, fn, max_retries=6):
+        """RIMU_ERR_TABLE_FULL means the global HBM table of the table method was too small: grow it (x4) and repeat, a
+        bounded number of times; every other status is raised as it is."""
+        for attempt in range(max_retries + 1):
             try:
                 return fn()
             except _lib.RimuB200Error as e:
-                if e.status != _lib.ERR_TABLE_FULL:
+                if e.status != _lib.ERR_TABLE_FULL or attempt == max_retries:
                     raise
                 self.ctx.resize_table(self.ctx.table_slots * 4)
 
@@ -275,9 +277,13 @@ def apply_operator(wm: WorkingMemory, target: GPUDVec, source: GPUDVec, op, boos
         p.initiator_rule, p.initiator_threshold = rule.rule_id, float(rule.threshold)
     stats = _lib.StepStats()
     ctx = wm.ctx
+    table_retries = 0
     while True:
         st = _lib.lib().rimu_step(ctx.handle, ham.handle, C.byref(p), source.handle, target.handle, C.byref(stats))
-        if st == _lib.ERR_TABLE_FULL:
+        if st == _lib.ERR_TABLE_FULL and table_retries < 6:
+            # the table method ran out of slots: grow the global table and repeat.  (Failures of the partitioned method's
+            # record streams come back as ERR_WORKMEM and are raised below: a bigger table would not help them.)
+            table_retries += 1
             ctx.resize_table(ctx.table_slots * 4)
             continue
         if st == _lib.ERR_EXCHANGE_FULL:  # same decision on every rank: grow the per-peer buffers and repeat

@@ -40,11 +40,12 @@ class ShiftParameters:
 
 @dataclass
 class DontUpdate:
+    """shiftstrategy.jl:77-91: the shift stays fixed; the run stops once the walker number reaches `target_walkers`
+    (`proceed = tnorm < target_walkers`).  `pnorm` is left alone, as in the reference."""
     target_walkers: float = 1000
 
     def update(self, sp, tnorm):
-        sp.pnorm = tnorm
-        return {"shift": sp.shift, "norm": tnorm}, True
+        return {"shift": sp.shift, "norm": tnorm}, tnorm < self.target_walkers
 
 
 @dataclass
@@ -331,8 +332,8 @@ class PMCSimulation:
             self.aborted, self.message = True, f"Aborted in step {self.step}."  # dead population
         elif too_long:
             self.aborted, self.message = True, f"Aborted in step {self.step}."  # max_length reached
-        elif stop:
-            self.aborted = True
+        elif stop:  # a shift strategy asked to stop (pmc_simulation.jl:301-304 reports it the same way)
+            self.aborted, self.message = True, f"Aborted in step {self.step}."
         elif self.step >= p.last_step:
             self.success = True
         self.modified = True

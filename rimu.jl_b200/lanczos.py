@@ -11,13 +11,22 @@ from .stochasticstyles import IsDeterministic
 
 def eigsolve_lanczos(ham, start: GPUDVec, howmany=1, krylovdim=60, tol=1e-10, maxiter=20, full_reorth=False):
     """Lowest `howmany` eigenvalues of a Hermitian device Hamiltonian from `start`.
-    Thick restarts are replaced by plain restarts from the current Ritz vector.
-    Returns (values, vectors, info)."""
+
+    howmany == 1: thick restarts are replaced by plain restarts from the current Ritz vector (up to `maxiter` cycles).
+    howmany > 1: a restart from one vector would collapse onto the lowest state, so a single Krylov space of `krylovdim`
+    vectors is built (full reorthogonalisation is switched on) and `info["converged"]` says whether ALL requested Ritz pairs
+    reached `tol`; raise `krylovdim` otherwise.  Returns (values, vectors, info): `howmany` values and their Ritz vectors."""
+    if howmany < 1:
+        raise ValueError("howmany must be >= 1")
+    if howmany > krylovdim:
+        raise ValueError("howmany cannot exceed krylovdim")
     det = IsDeterministic()
     v = GPUDVec(style=det, address_type=start.address_type, ctx=start.ctx).copy_from(start)
     wm = WorkingMemory(v)
     info = {"matvecs": 0, "converged": False, "residual": np.inf}
-    theta = None
+    if howmany > 1:
+        full_reorth, maxiter = True, 1
+    theta, ritz_vectors = None, [v]
     for restart in range(maxiter):
         nrm = v.norm(2)
         v.scale_(1.0 / nrm)
@@ -38,23 +47,31 @@ def eigsolve_lanczos(ham, start: GPUDVec, howmany=1, krylovdim=60, tol=1e-10, ma
             b = w.norm(2)
             T = np.diag(alphas) + np.diag(betas, 1) + np.diag(betas, -1)
             evals, evecs = np.linalg.eigh(T)
-            resid = abs(b * evecs[-1, 0])
+            # residual of Ritz pair i is |beta_j * (last component of its eigenvector)|; all requested pairs must converge
+            nreq = min(howmany, len(evals))
+            resid = float(np.max(np.abs(b * evecs[-1, :nreq]))) if len(evals) >= howmany else np.inf
             theta = evals
             if resid < tol or b < 1e-14 or j == krylovdim - 1:
-                info["residual"] = resid
+                info["residual"] = resid if len(evals) >= howmany else np.inf
+                if b < 1e-14 and len(evals) >= howmany:  # invariant subspace: the Ritz pairs are exact
+                    info["residual"] = 0.0
                 break
             betas.append(b)
             nxt = w.copy().scale_(1.0 / b)
             basis.append(nxt)
             w = v.similar()
-        # Ritz vector of the lowest state
-        y = evecs[:, 0]
-        ritz = basis[0].copy().scale_(y[0])
-        for q, c in zip(basis[1:], y[1:]):
-            ritz.add_(q, c)
-        v = ritz
+        ritz_vectors = []
+        for i in range(min(howmany, evecs.shape[1])):
+            y = evecs[:, i]
+            ritz = basis[0].copy().scale_(y[0]) if y[0] != 0.0 else basis[0].similar()
+            for q, c in zip(basis[1:], y[1:]):
+                if c != 0.0:
+                    ritz.add_(q, c)
+            ritz_vectors.append(ritz)
+        v = ritz_vectors[0]
         if info["residual"] < tol:
             info["converged"] = True
             break
-    vals = theta[:howmany]
-    return vals, [v], info
+    if len(theta) < howmany:
+        raise ValueError(f"the Krylov space closed after {len(theta)} vectors: fewer than howmany={howmany} states overlap the start vector")
+    return theta[:howmany], ritz_vectors, info

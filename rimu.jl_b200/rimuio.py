@@ -218,5 +218,10 @@ def load_state(filename, style=None, ctx=None, **vector_kwargs):
         style = IsDynamicSemistochastic() if vals.dtype == np.float64 else IsStochasticInteger()
     v = GPUDVec(style=style, address_type=at, capacity=max(len(vals), 256), ctx=ctx, **vector_kwargs)
     nz = vals != 0
-    v.assign(keys[nz], vals[nz].astype(v.dtype))
+    if v.ctx.nranks > 1:
+        # every rank reads the whole file and keeps the addresses it owns: upload() filters by owner rank (a plain
+        # assign() would leave every rank with the full vector and multiply the population by the number of ranks)
+        v.upload(keys[nz], vals[nz].astype(v.dtype))
+    else:
+        v.assign(keys[nz], vals[nz].astype(v.dtype))
     return v, metadata

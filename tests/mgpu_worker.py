@@ -67,7 +67,7 @@ def main():
                 assert abs(s.norm1 - st.norm1) <= 1e-9 * st.norm1
                 # feed the (gathered) GPU values back so that last-bit differences cannot flip branches
                 ok, ov = gk, gv
-            assert all(len(p[1]) > 0 for p in parts) or step == 0, "every rank should own part of the vector"
+            assert all(len(p[1]) > 0 for p in parts) or step < 4, "every rank should own part of the vector"
             # walkernumber_and_length is global
             wn, _ = R.walkernumber_and_length(v)
             assert abs(wn - float(np.abs(ov).sum())) <= 1e-9 * float(np.abs(ov).sum())

@@ -193,6 +193,17 @@ def test_driver_options_on_the_cpu(built, cpu_device):
     sim = R.solve(prob)
     assert set(sim.dataframe()["shift"]) == {-1.5}
     assert sim.state.v.initiator == R.CoherentInitiator(2.0) and sim.state.wm.initiator == R.CoherentInitiator(2.0)
+    # DontUpdate stops the run once the walker number reaches target_walkers (shiftstrategy.jl:89-91) and leaves pnorm alone;
+    # the stop is reported like every other `proceed == false` (pmc_simulation.jl:301-304)
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, shift=20.0, shift_strategy=R.DontUpdate(target_walkers=200),
+                                        time_step=0.01, last_step=5000, random_seed=1)
+    sim = R.init(prob)
+    pnorm0 = sim.state.shift_parameters.pnorm
+    R.solve_(sim)
+    df = sim.dataframe()
+    assert sim.aborted and not sim.success and sim.step < 5000 and sim.message == f"Aborted in step {sim.step}."
+    assert df["norm"].iloc[-1] >= 200 and all(n < 200 for n in df["norm"].iloc[:-1])
+    assert sim.state.shift_parameters.pnorm == pnorm0 and set(df["shift"]) == {20.0}
     # wall time
     prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, last_step=10 ** 9, random_seed=1, wall_time=0.2)
     sim = R.solve(prob)

@@ -12,18 +12,37 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("method,p2p", [("partition", "1"), ("partition", "0"), ("hash", "1")])
-def test_two_rank_steps_match_oracle(built, method, p2p):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+def _run_worker(world, method, p2p, extra_env=None):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     env = dict(os.environ, RIMU_B200_METHOD=method, RIMU_B200_P2P=p2p)  # p2p=1: peer-direct exchange when CUDA IPC works
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    env.update(extra_env or {})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")],
-                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("mgpu ok") == (6 if (method, p2p) == ("partition", "1") else 4)  # + two initiator cases in direct mode
+    return r.stdout
+
+
+@pytest.mark.parametrize("method,p2p", [("partition", "1"), ("partition", "0"), ("hash", "1")])
+def test_two_rank_steps_match_oracle(built, method, p2p):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = _run_worker(2, method, p2p)
+    assert out.count("mgpu ok") == (6 if (method, p2p) == ("partition", "1") else 4)  # + two initiator cases in direct mode
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_many_rank_steps_match_oracle(built, world):
+    """The same bit-exact comparison with the single-rank oracle at 4 and 8 ranks (direct exchange: W=1 and W=2 integer
+    walkers, semistochastic Float64, two initiator cases) -- test/mpi_runtests.jl:41-155 runs its checks at the MPI size it is
+    launched with; here the size is a parameter."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = _run_worker(world, "partition", "1")
+    assert out.count("mgpu ok") == 6
+    assert f"world={world}" in out
