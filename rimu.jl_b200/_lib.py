@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "sort.cu", "step_hk.cu"]   # step_hk.cu is compiled once per HamKind (-DRIMU_HK=n), in parallel
 HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh", "internal.cuh"]
 NUM_HAM_KINDS = 7
-OBJ_DIR = os.path.join(_HERE, "build")
+OBJ_DIR = os.environ.get("RIMU_B200_OBJ_DIR") or os.path.join("/tmp", "rimu_b200_build_" + str(os.getuid()))  # objects stay out of the tree
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "--fmad=false", "-lineinfo",

@@ -80,14 +80,29 @@ template <class B> DEV void bose_kth_doubly(B x, int d, int &mode, int &occ, int
     mode = off - popc_((B)(x & lowmask<B>(off))) + 1;
     occ = cto_((B)(x >> off));
 }
-template <class B> DEV long long bose_interaction(B x) { // sum n(n-1)
-    int r = 0;
-    while (x != 0) {
-        x >>= ctz_(x);
-        int n = cto_(x);
-        x >>= n;
-        r += n * (n - 1);
+// Occupied modes of a bosonic bit string in ascending order: `for (BoseModes<B> it(x); it.next(md, n);)` yields the 0-based
+// mode and its occupation.  The string is bit-reversed ONCE, so that every scan is a count-leading-zeros (one FLO per word)
+// instead of a bit reversal + FLO per scan: these all run on the quarter-rate XU pipe, which the diagonal elements of new
+// determinants kept busy (profiles/r2_merge_ncu.md).
+DEV u64 brev_(u64 x) { return __brevll(x); }
+DEV u128 brev_(u128 x) { return ((u128)__brevll((u64)x) << 64) | (u128)__brevll((u64)(x >> 64)); }
+DEV int clz_(u64 x) { return __clzll((long long)x); } // 64 for x == 0
+DEV int clz_(u128 x) { const u64 hi = (u64)(x >> 64); return hi ? __clzll((long long)hi) : 64 + __clzll((long long)(u64)x); }
+template <class B> struct BoseModes {
+    B yb;   // remaining bits, reversed: the next bit of the string is the most significant one
+    int md; // zeros passed so far = index of the mode the next particle belongs to
+    DEV explicit BoseModes(B x) : yb(brev_(x)), md(0) {}
+    DEV bool next(int &mode, int &n) {
+        if (yb == 0) return false;
+        const int z = clz_(yb); yb <<= z; md += z;
+        n = clz_((B)~yb); yb <<= n; // (a valid address has a spare zero bit, so n < bit width)
+        mode = md;
+        return true;
     }
+};
+template <class B> DEV long long bose_interaction(B x) { // sum n(n-1)
+    int r = 0, md, n;
+    for (BoseModes<B> it(x); it.next(md, n);) r += n * (n - 1);
     return r;
 }
 
@@ -210,10 +225,8 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         if (h.variant == 0) return h.u * (double)bose_interaction(x) / 2;
         if (h.variant == 1) { // HubbardReal1DEP.jl:82-87: sum over occupied modes (ascending) of u n (n-1) / 2 + eps[mode] n
             double s = 0.0; bool first = true;
-            int md = 0; B y = x;
-            while (y != 0) {
-                int z = ctz_(y); y >>= z; md += z;
-                int n = cto_(y); y >>= n;
+            int md, n;
+            for (BoseModes<B> it(x); it.next(md, n);) {
                 const double term = h.u * n * (n - 1) / 2 + h.pot[md] * n;
                 s = first ? term : s + term; first = false;
             }
@@ -221,10 +234,8 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         }
         // ExtendedHubbardReal1D.jl:101-126: u sum n(n-1) / 2 + v sum n_j n_j+1 (ring unless hard wall)
         long long ext = 0, reg = 0;
-        int md = 0, pmode = -1, pocc = 0, first_mode = -1, first_occ = 0; B y = x;
-        while (y != 0) {
-            int z = ctz_(y); y >>= z; md += z;      // md = 0-based mode of this occupied block
-            int n = cto_(y); y >>= n;
+        int md, n, pmode = -1, pocc = 0, first_mode = -1, first_occ = 0;
+        for (BoseModes<B> it(x); it.next(md, n);) { // md = 0-based mode of this occupied block
             if (pmode == md - 1) ext += (long long)pocc * n;
             reg += (long long)n * (n - 1);
             if (first_mode < 0) { first_mode = md; first_occ = n; }
@@ -234,11 +245,8 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         return h.u * (double)reg / 2 + h.v * (double)ext;
     } else if constexpr (HK == HK_MOM1D_BOSE) {
         double ke = 0.0;
-        int lin = 0, md = 0;
-        B y = x;
-        while (y != 0) {
-            int z = ctz_(y); y >>= z; md += z;
-            int n = cto_(y); y >>= n;
+        int lin = 0, md, n;
+        for (BoseModes<B> it(x); it.next(md, n);) {
             ke += h.kes[md] * n;
             lin += n * (n - 1);
         }
@@ -254,12 +262,8 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         double interaction = h.umat_zero ? 0.0 : h.u00 * (double)bose_interaction(x) / 2;
         double pot = 0.0;
         if (h.has_pot) {
-            int md = 1; B y = x; double pe = 0.0;
-            while (y != 0) {
-                int z = ctz_(y); y >>= z; md += z;
-                int n = cto_(y); y >>= n;
-                pe += n * h.pot[md - 1];
-            }
+            int md, n; double pe = 0.0;
+            for (BoseModes<B> it(x); it.next(md, n);) pe += n * h.pot[md];
             pot += pe;
         }
         return interaction + pot;

@@ -382,7 +382,34 @@ diag_append_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
 // pidx[CAP] (u16: index of the parent item that was annihilated into this owner, for its cached H_aa).
 // Placement is one pass: an item claims the first free slot of its probe sequence with a 32-bit shared CAS on
 // the owner table; keys are compared through the item index, so nothing has to be published after a claim.
-// After placement the owner table is dead and is reused as the list of survivors that still need H_aa.
+// After placement the owner table is dead and is reused, one region per warp, for the lists of entries that still need a
+// compression draw or a fresh H_aa -- every warp finishes ITS items with __syncwarp only.  CTA barriers per bucket: after
+// staging, after placement, one for the survivor scan (the last warp to arrive takes the cursor atomic), one at the end.
+//
+// Staging: spawn records need no arithmetic, so they are copied global -> shared with cp.async (LDGSTS): every record
+// load of the bucket is in flight at once, and the copies -- NVLink loads for sub-streams that live on other GPUs -- complete
+// while the parents go through the diagonal step.
+
+DEV void cp_async8(void *smem_dst, const void *gsrc) {
+    const u32 s = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+DEV void cp_async16(void *smem_dst, const void *gsrc) {
+    const u32 s = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// slot of an address in the bucket's shared-memory table.  The items of a bucket are a pseudo-random subset of the addresses
+// (the bucket is a range of the fmix64 hash), so a multiplicative hash of the folded words spreads them; it costs 3 integer
+// multiplies instead of the two 64-bit multiply chains of fmix64, which is kept for what needs avalanche: buckets and RNG.
+template <u32 BITS> DEV u32 slot_hash(u64 k0, u64 k1) {
+    u32 x = (u32)k0 ^ ((u32)(k0 >> 32) * 0x85EBCA6Bu) ^ ((u32)k1 * 0xC2B2AE35u) ^ ((u32)(k1 >> 32) * 0x27D4EB2Fu);
+    return (x * 0x9E3779B1u) >> (32 - BITS);
+}
+template <u32 N> struct Log2 { static constexpr u32 value = 1 + Log2<N / 2>::value; };
+template <> struct Log2<1> { static constexpr u32 value = 0; };
+
 template <int HK, int W, class VT, int MODE, bool INIT = false>
 __global__ void __launch_bounds__(PART_NT, PART_MINB)
 merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st) {
@@ -390,9 +417,14 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     constexpr bool is_int = std::is_integral<VT>::value;
     constexpr int CAP = PartCap<W>::value;
     constexpr int R = CAP / PART_NT;
+    constexpr int NW = PART_NT / 32;
+    constexpr u32 TBITS = Log2<2 * CAP>::value;
     constexpr u32 TMASK = 2 * CAP - 1;
+    constexpr u32 WLIST = 2 * CAP / NW;  // owner-table entries per warp once the table is dead (>= R * 32 items of a warp)
     constexpr u32 NIL = 0xffffffffu;
     constexpr u32 NOPARENT = 0x7fffu, IFLAG = 0x8000u; // pidx: parent item index | "initiator lane is non-zero" flag
+    static_assert((2 * CAP & (2 * CAP - 1)) == 0, "table size must be a power of two");
+    static_assert(WLIST >= (u32)R * 32, "a warp's list region must hold all of its items");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *skeys = reinterpret_cast<u64 *>(smem_raw);
     u64 *svals = skeys + CAP * W;
@@ -403,17 +435,20 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     // only an address's own parent can deposit there
     constexpr bool initm = MODE == 0 && INIT; // separate instantiation: the plain step pays nothing for the lanes
     u64 *sunsafe = reinterpret_cast<u64 *>(pidx + CAP);
-    __shared__ u32 s_warp[PART_NT / 32];
+    __shared__ u32 s_warp[NW];
     __shared__ u64 s_base;
-    __shared__ u32 s_nlist, s_clist;
+    __shared__ u32 s_arrive;
+    __shared__ u32 s_nlist;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    u32 *wlist = owner + wid * WLIST;
     double norm1 = 0.0, clones = 0.0, deaths = 0.0, zombies = 0.0;
     i64 inorm1 = 0;
     u32 len_before = 0, len = 0, ndep = 0; // per-thread counts (32 bits are plenty; registers are the scarce resource here)
     u32 max_fill = 0;
     u32 nrec_sum = 0;
     // Bucket metadata (segment of parents, fill of every source's sub-stream) runs two buckets ahead of the merge, and
-    // the next bucket's parents and records are pulled into L2 with bulk prefetches while this one is merged, so that
+    // the next bucket's parents and local records are pulled into L2 with bulk prefetches while this one is merged, so that
     // staging sees L2 latency instead of two dependent HBM round trips (metadata, then data).
     constexpr int RW = RecWords<W>::value;
     constexpr int MAXSUB = RIMU_MAX_RANKS * 3;  // sub-streams per bucket: ranks x lanes
@@ -435,6 +470,18 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         s_cntbase[tid] = cb + (u64)sub * pt.nb;
         s_local[tid] = (!pt.direct || srank * pt.nlane == pt.me) ? 1 : 0;
     }
+    if (tid == 0) s_arrive = 0;
+    // the kinetic-energy table of the momentum-space models is read once per occupied mode by every H_aa evaluation: keep
+    // it in shared memory (29-cycle loads instead of a trip through L1/L2)
+    __shared__ double s_kes[HK == HK_MOM1D_BOSE || HK == HK_MOM1D_F2C || HK == HK_TC_F2C ? 64 : 1];
+    HamDev hl = h;
+    if constexpr (HK == HK_MOM1D_BOSE || HK == HK_MOM1D_F2C || HK == HK_TC_F2C) {
+        if (h.kes && h.M <= 64) {
+            if (tid < h.M) s_kes[tid] = h.kes[tid];
+            hl.kes = s_kes;
+        }
+    }
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < 2; q++) {
         const u64 bq = (u64)blockIdx.x + (u64)q * gridDim.x;
@@ -492,16 +539,33 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             continue;
         }
         for (int i = tid; i < 2 * CAP; i += PART_NT) owner[i] = NIL;
-        if (tid == 0) { s_nlist = 0; s_clist = 0; }
+        if (tid == 0) s_nlist = 0;
         const int rmax = (int)((n + PART_NT - 1) / PART_NT); // uniform: rounds of PART_NT items this bucket needs
-        // ---- stage parents (with the diagonal step) and spawn records
-        u32 valid = 0, slot[R];
+        // ---- stage the spawn records: asynchronous copies straight into the item arrays (no lanes to sort out)
+        u32 valid = 0;
+        if constexpr (!initm) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r >= rmax) break;
+                const u32 i = tid + r * PART_NT;
+                if (i < np || i >= n) continue;
+                u32 j = i - np, q = 0; // record j of the bucket -> (source sub-stream q, position j)
+                if (nsrc > 1) for (u32 cq = s_cnt[cur][0]; j >= cq; cq = s_cnt[cur][q]) { j -= cq; q++; }
+                const u64 *rp = s_recbase[q] + ((u64)b * pt.rcap + j) * RW;
+                if constexpr (W == 1) { cp_async8(skeys + i, rp); cp_async8(svals + i, rp + 1); }
+                else { cp_async16(skeys + 2 * i, rp); cp_async8(svals + i, rp + 2); }
+                pidx[i] = (unsigned short)NOPARENT;
+                valid |= 1u << r; // spawn kernels append non-zero values only
+                ndep++;
+            }
+        }
+        // ---- stage parents (with the diagonal step); with initiator lanes the records go through registers as well
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (r >= rmax) break;
             const u32 i = tid + r * PART_NT;
-            slot[r] = 0;
             if (i >= n) continue;
+            if (!initm && i >= np) continue;
             B key; VT v;
             u32 ilane = LANE_SAFE;
             if (i < np) {
@@ -511,7 +575,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 if constexpr (MODE == 0) {
                     // diagonal_step! (spawning.jl:73-77) through FirstOrderTransitionOperator (fciqmc.jl:93-96)
                     const double val = (double)pv;
-                    const double hd = src.diag ? src.diag[p0 + i] : ham_diagonal<HK, B>(h, key);
+                    const double hd = src.diag ? src.diag[p0 + i] : ham_diagonal<HK, B>(hl, key);
                     const double d = p.plain_h ? hd : 1 - p.dtau * (hd - p.shift);
                     double rr = 0.0;
                     const double thr = is_int ? 0.0 : p.proj_thr;
@@ -530,7 +594,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                     v = (VT)(alpha * (double)pv);
                 }
             } else {
-                u32 j = i - np, q = 0; // record j of the bucket -> (source sub-stream q, position j)
+                u32 j = i - np, q = 0;
                 if (nsrc > 1) for (u32 cq = s_cnt[cur][0]; j >= cq; cq = s_cnt[cur][q]) { j -= cq; q++; }
                 union { u64 b; VT v; } cv;
                 load_rec<W>(s_recbase[q] + ((u64)b * pt.rcap + j) * RW, key, cv.b);
@@ -549,11 +613,11 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 union { u64 b; VT v; } cv; cv.v = v;
                 if (initm && ilane == LANE_UNSAFE) { sunsafe[i] = cv.b; cv.v = (VT)0; }
                 svals[i] = cv.b;
-                slot[r] = (u32)hash_bits(key) & TMASK;
                 valid |= 1u << r;
                 ndep++;
             }
         }
+        if constexpr (!initm) cp_async_wait_all();
         __syncthreads();
         // ---- placement: claim a slot (CAS) or annihilate into the item that owns this address
         u32 own = 0;
@@ -564,7 +628,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             const u32 i = tid + r * PART_NT;
             const u64 k0 = skeys[i * W];
             u64 k1 = 0; if constexpr (W == 2) k1 = skeys[i * W + 1];
-            u32 s = slot[r];
+            u32 s = slot_hash<TBITS>(k0, k1);
             for (;;) {
                 u32 o = owner[s];
                 if (o == NIL) {
@@ -591,7 +655,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 s = (s + 1) & TMASK;
             }
         }
-        __syncthreads();
+        __syncthreads(); // every sum is complete; the owner table is dead from here on (reused as per-warp lists)
         // ---- from_initiator_value (initiators.jl:136-138,177-179,201-207; pdworkingmemory.jl:268-270): collapse the lanes
         if (initm) {
 #pragma unroll
@@ -609,11 +673,13 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 ca.v = out; svals[i] = ca.b;
             }
         }
-        // ---- ThresholdCompression (compression.jl:18-26) as a dense pass: the owners whose |value| is below the
-        // threshold are gathered into a list (the owner table is dead after placement) so that the Philox draw runs
-        // over full warps instead of once per round for the few lanes that need it
+        // ---- ThresholdCompression (compression.jl:18-26) as a dense pass: the warp gathers ITS owners whose |value| is
+        // below the threshold into its list so that the Philox draw runs over full warps instead of once per round for the
+        // few lanes that need it.  Only this warp touches these entries from here on: __syncwarp is all it takes.
+        const bool compressed = !is_int && MODE == 0 && p.compress_thr > 0.0;
         if constexpr (!is_int && MODE == 0) {
             if (p.compress_thr > 0.0) { // uniform
+                u32 wn = 0;
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     if (r >= rmax) break;
@@ -624,17 +690,12 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                         if (cv.v != 0.0) { if (!initm) len_before++; need = fabs(cv.v) < p.compress_thr; }
                     }
                     const u32 bal = __ballot_sync(0xffffffffu, need);
-                    if (bal) {
-                        u32 wb = 0;
-                        if (lane == 0) wb = atomicAdd(&s_clist, (u32)__popc(bal));
-                        wb = __shfl_sync(0xffffffffu, wb, 0);
-                        if (need) owner[wb + __popc(bal & ((1u << lane) - 1u))] = i;
-                    }
+                    if (need) wlist[wn + __popc(bal & lt_mask)] = i;
+                    wn += __popc(bal);
                 }
-                __syncthreads();
-                const u32 ncl = s_clist;
-                for (u32 j = tid; j < ncl; j += PART_NT) {
-                    const u32 i = owner[j];
+                __syncwarp();
+                for (u32 j = lane; j < wn; j += 32) {
+                    const u32 i = wlist[j];
                     B key;
                     if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
                     union { u64 b; double v; } cv; cv.b = svals[i];
@@ -644,11 +705,10 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                     cv.v = (prob > u53(rnd[1], rnd[2])) ? p.compress_thr * sgn_(cv.v) : 0.0;
                     svals[i] = cv.b;
                 }
-                __syncthreads();
+                __syncwarp();
             }
         }
         // ---- drop zeros, count survivors
-        const bool compressed = !is_int && MODE == 0 && p.compress_thr > 0.0;
         u32 keep = 0, cnt = 0;
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -662,22 +722,30 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v); else norm1 += fabs((double)v);
         }
         if (!compressed && !initm) len_before += cnt;
-        // ---- CTA scan of survivor counts, one cursor atomic per bucket, write the new segment
+        // ---- survivor scan: warp totals meet in shared memory; the LAST warp to arrive reserves the segment with the one
+        // cursor atomic of the bucket while the others already wait at the barrier
         u32 incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { u32 up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-        if (lane == 31) s_warp[wid] = incl;
+        if (lane == 31) {
+            s_warp[wid] = incl;
+            __threadfence_block();
+            if (atomicAdd(&s_arrive, 1u) == (u32)NW - 1u) {
+                __threadfence_block();
+                u32 tot = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) tot += reinterpret_cast<volatile u32 *>(s_warp)[w];
+                const u64 base = tot ? atomicAdd(&st->out_count, (u64)tot) : 0ull;
+                s_base = base;
+                dst.seg_start[b] = base;
+                dst.seg_len[b] = (base + tot <= dst.cap) ? tot : 0u;
+                s_arrive = 0;
+            }
+        }
         __syncthreads();
         u32 wbase = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < PART_NT / 32; w++) { u32 t = s_warp[w]; if (w < wid) wbase += t; total += t; }
-        if (tid == 0) {
-            u64 base = total ? atomicAdd(&st->out_count, (u64)total) : 0ull;
-            s_base = base;
-            dst.seg_start[b] = base;
-            dst.seg_len[b] = (base + total <= dst.cap) ? total : 0u;
-        }
-        __syncthreads();
+        for (int w = 0; w < NW; w++) { u32 t = s_warp[w]; if (w < wid) wbase += t; total += t; }
         const u64 base = s_base;
         const bool fits = base + total <= dst.cap;
         if (fits) {
@@ -685,37 +753,50 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (r >= rmax) break;
-                if (!((keep >> r) & 1u)) continue;
                 const u32 i = tid + r * PART_NT;
-                const u64 at = base + rel;
-                dst.keys[at * W] = skeys[i * W];
-                if constexpr (W == 2) dst.keys[at * W + 1] = skeys[i * W + 1];
-                dst.vals[at] = svals[i];
-                if constexpr (MODE == 0) {
-                    // H_aa of the survivor: cached with its parent, or (new determinant) evaluated below
-                    const u32 pi = i < np ? i : ((u32)pidx[i] & NOPARENT);
-                    if (src.diag && pi != NOPARENT) dst.diag[at] = src.diag[p0 + pi];
-                    else owner[atomicAdd(&s_nlist, 1u)] = (i << 16) | rel; // owner table is dead: reuse as the list
+                bool fresh = false;
+                if ((keep >> r) & 1u) {
+                    const u64 at = base + rel;
+                    dst.keys[at * W] = skeys[i * W];
+                    if constexpr (W == 2) dst.keys[at * W + 1] = skeys[i * W + 1];
+                    dst.vals[at] = svals[i];
+                    if constexpr (MODE == 0) {
+                        // H_aa of the survivor: cached with its parent, or (new determinant) evaluated below
+                        const u32 pi = i < np ? i : ((u32)pidx[i] & NOPARENT);
+                        if (src.diag && pi != NOPARENT) dst.diag[at] = src.diag[p0 + pi];
+                        else fresh = true;
+                    }
                 }
-                rel++;
+                if constexpr (MODE == 0) {
+                    // survivors that need a fresh H_aa are gathered CTA-wide ((item << 16) | position in the segment): the
+                    // evaluation is the most expensive per-entry operation of the kernel and must run over full warps
+                    const u32 bal = __ballot_sync(0xffffffffu, fresh);
+                    if (bal) {
+                        u32 lb = 0;
+                        if (lane == 0) lb = atomicAdd(&s_nlist, (u32)__popc(bal));
+                        lb = __shfl_sync(0xffffffffu, lb, 0);
+                        if (fresh) owner[lb + __popc(bal & lt_mask)] = (i << 16) | rel;
+                    }
+                }
+                if ((keep >> r) & 1u) rel++;
             }
         }
         len += cnt;
         if ((u32)tid < nsrc) s_cnt[nn][tid] = pending_cnt; // (loaded at the top of this iteration: its latency is long gone)
         if (meta_thread) { s_np[nn] = pending_np; s_p0[nn] = pending_p0; }
-        __syncthreads();
         if constexpr (MODE == 0) {
-            // dense evaluation of H_aa for the gathered survivors (a per-lane evaluation inside the output loop
-            // would cost a full divergent warp pass per new entry)
+            // dense evaluation of H_aa for the gathered survivors (a per-lane evaluation inside the output loop would cost
+            // a full divergent warp pass per new entry)
+            __syncthreads();
             const u32 nl = fits ? s_nlist : 0u;
             for (u32 j = tid; j < nl; j += PART_NT) {
                 const u32 e = owner[j], i = e >> 16, rel = e & 0xffffu;
                 B key;
                 if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
-                dst.diag[base + rel] = ham_diagonal<HK, B>(h, key);
+                dst.diag[base + rel] = ham_diagonal<HK, B>(hl, key);
             }
-            __syncthreads(); // shared memory is reused by the next bucket
         }
+        __syncthreads(); // shared memory is reused by the next bucket
     }
     stat_add(&st->len_before, (i64)len_before);
     stat_add(&st->len, (i64)len);
