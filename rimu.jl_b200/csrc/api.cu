@@ -1123,13 +1123,27 @@ extern "C" int rimu_vec_segments(rimu_vec *v, uint64_t *start_out, uint32_t *len
 // bucket count for a step on `n` local parents
 // `parents` = local parents (one rank) or the per-rank share of the global length (multi-GPU: the same number on every rank)
 static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
+    // The merge kernel works through a bucket in rounds of PART_NT items, and a round costs the same whether it is full or
+    // not (measured: 0.586 / 0.656 / 0.544 ms for mean fills of 1157 / 1282 / 1389 items -- the middle one spills a few
+    // items into a sixth round).  So the bucket count aims the MEAN fill just below a round boundary: `rounds` full rounds
+    // minus 2.5 sigma of the Poisson spread.  RIMU_B200_ROUNDS overrides the number of rounds (tuning knob).
+    static const int rounds_env = [] { const char *e = getenv("RIMU_B200_ROUNDS"); return e ? atoi(e) : 0; }();
     const double cap = (double)part_cap_items(c->W);
-    const double expected = parents * (1.0 + c->rec_per_parent) * 1.15 + 512.0;
-    if (src->nb) { // keep the segmentation while the expected fill stays in a comfortable band
+    const int max_rounds = (int)(cap / PART_NT);
+    int rounds = rounds_env > 0 ? rounds_env : (5 * max_rounds) / 8; // 5 of 8 (measured flat between 5 and 7): room for growth and skew
+    if (rounds > max_rounds - 1) rounds = max_rounds - 1;
+    if (rounds < 1) rounds = 1;
+    // `upper` = the largest mean fill whose Poisson spread (1.5 sigma) still fits the rounds.  A fresh segmentation starts at
+    // 0.9 * upper, and the bucket count is kept while the mean stays in [0.7, 1] * upper: a growing population is re-segmented
+    // every ~5 % of growth (one step that carries the diagonal deposits as records), a steady one sits just below the
+    // round boundary, where every round of every bucket is nearly full.
+    const double slots = (double)rounds * PART_NT, upper = slots - 1.5 * sqrt(slots);
+    const double expected = parents * (1.0 + c->rec_per_parent) * 1.02 + 64.0;
+    if (src->nb) {
         double fill = expected / src->nb;
-        if (fill > 0.25 * cap && fill < 0.80 * cap) return src->nb;
+        if (fill >= 0.7 * upper && fill <= upper) return src->nb;
     }
-    double nb = ceil(expected / (0.65 * cap));
+    double nb = ceil(expected / (0.9 * upper));
     return nb < 1.0 ? 1u : (u32)nb;
 }
 

@@ -49,6 +49,9 @@
 #ifndef SPAWN_MINB
 #define SPAWN_MINB 4       // spawn CTAs resident per SM (register cap)
 #endif
+#ifndef PART_BALANCED_TAIL
+#define PART_BALANCED_TAIL 1
+#endif
 #define HEAVY_T 1024       // parents with more attempts than this are queued for K2
 #define HEAVY_TILE 8192    // attempts per K2 work item
 #define ACC_MAX 4096       // K2 pre-sums per off-diagonal index when L <= ACC_MAX
@@ -541,13 +544,24 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         for (int i = tid; i < 2 * CAP; i += PART_NT) owner[i] = NIL;
         if (tid == 0) s_nlist = 0;
         const int rmax = (int)((n + PART_NT - 1) / PART_NT); // uniform: rounds of PART_NT items this bucket needs
+        // Item of this thread in round r: tid + r * PART_NT in the full rounds; the items of the partial last round are dealt
+        // out across ALL warps (lane-major), so that every warp owns the same number of items +-1 and the warps reach the
+        // barriers together (with the plain mapping the low warps did one round more than the high ones)
+        const u32 rfull = n / PART_NT;
+        const u32 tail_item = rfull * PART_NT + (u32)lane * NW + (u32)wid;
+#if PART_BALANCED_TAIL
+        auto item_of = [&](int r) -> u32 { return (u32)r < rfull ? (u32)tid + (u32)r * PART_NT : tail_item; };
+#else
+        (void)rfull; (void)tail_item;
+        auto item_of = [&](int r) -> u32 { return (u32)tid + (u32)r * PART_NT; };
+#endif
         // ---- stage the spawn records: asynchronous copies straight into the item arrays (no lanes to sort out)
         u32 valid = 0;
         if constexpr (!initm) {
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (r >= rmax) break;
-                const u32 i = tid + r * PART_NT;
+                const u32 i = item_of(r);
                 if (i < np || i >= n) continue;
                 u32 j = i - np, q = 0; // record j of the bucket -> (source sub-stream q, position j)
                 if (nsrc > 1) for (u32 cq = s_cnt[cur][0]; j >= cq; cq = s_cnt[cur][q]) { j -= cq; q++; }
@@ -563,7 +577,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (r >= rmax) break;
-            const u32 i = tid + r * PART_NT;
+            const u32 i = item_of(r);
             if (i >= n) continue;
             if (!initm && i >= np) continue;
             B key; VT v;
@@ -625,7 +639,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         for (int r = 0; r < R; r++) {
             if (r >= rmax) break;
             if (!((valid >> r) & 1u)) continue;
-            const u32 i = tid + r * PART_NT;
+            const u32 i = item_of(r);
             const u64 k0 = skeys[i * W];
             u64 k1 = 0; if constexpr (W == 2) k1 = skeys[i * W + 1];
             u32 s = slot_hash<TBITS>(k0, k1);
@@ -662,7 +676,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             for (int r = 0; r < R; r++) {
                 if (r >= rmax) break;
                 if (!((own >> r) & 1u)) continue;
-                const u32 i = tid + r * PART_NT;
+                const u32 i = item_of(r);
                 union { u64 b; VT v; } ca, cu; ca.b = svals[i]; cu.b = sunsafe[i];
                 const bool fi = (pidx[i] & IFLAG) != 0;
                 if (ca.v == (VT)0 && cu.v == (VT)0 && !fi) continue; // all lanes zero: no entry
@@ -683,7 +697,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     if (r >= rmax) break;
-                    const u32 i = tid + r * PART_NT;
+                    const u32 i = item_of(r);
                     bool need = false;
                     if ((own >> r) & 1u) {
                         union { u64 b; double v; } cv; cv.b = svals[i];
@@ -714,7 +728,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         for (int r = 0; r < R; r++) {
             if (r >= rmax) break;
             if (!((own >> r) & 1u)) continue;
-            const u32 i = tid + r * PART_NT;
+            const u32 i = item_of(r);
             union { u64 b; VT v; } cv; cv.b = svals[i];
             const VT v = cv.v;
             if (v == (VT)0) continue; // exact zeros are deleted (pdworkingmemory.jl:25-29); so are compressed-away entries
@@ -753,7 +767,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (r >= rmax) break;
-                const u32 i = tid + r * PART_NT;
+                const u32 i = item_of(r);
                 bool fresh = false;
                 if ((keep >> r) & 1u) {
                     const u64 at = base + rel;

@@ -1,7 +1,5 @@
 #!/bin/bash
-# usage: scratch/sweep.sh name1 name2 ...  -> one compact line per variant (bench.py config 2)
-cd "$(dirname "$0")/.."
-for v in "$@"; do
-  RIMU_B200_LIB=$PWD/scratch/variants/lib_$v.so timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -n 1 | \
-    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$v', 'ms/step %.4f'%d['ms_per_step'], d['extra']['phase_ms_per_step'], 'e2e %.3g'%d['e2e']['value'])" 2>&1 | tail -n 1
+# usage: scratch/sweep.sh NAME...   -- bench.py once per scratch/variants/lib_NAME.so; prints ms/step and the phase split
+for name in "$@"; do
+  RIMU_B200_LIB=$PWD/scratch/variants/lib_$name.so python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-replicas 1 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['ms_per_step'],4), d['extra']['phase_ms_per_step'])"
 done
