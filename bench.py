@@ -167,6 +167,52 @@ def reference_arm(args):
     }))
 
 
+# --------------------------------------------------------------------------- parity preflight (multi-rank arm)
+def parity_preflight(R, rank, world):
+    """Five IsStochasticInteger steps of HubbardReal1D BoseFS{10,10} (BASELINE config 1) on a fresh context spanning all
+    ranks, the union of the ranks' vectors compared bit for bit -- keys, values and every integer statistic -- with the
+    single-rank CPU oracle.  The oracle is used as the checker only (it is never timed here).  Every SCALE record thereby
+    carries its own correctness signal for the exchange path it measures."""
+    import torch.distributed as dist
+    from oracle import oracle as orc
+    onr = (1,) * 10
+    oh = orc.OracleHam("HubbardReal1D", "bose", onr, u=6.0, t=1.0)
+    addr = R.BoseFS(onr)
+    H = R.HubbardReal1D(addr, u=6.0, t=1.0)
+    ctx = R.init_distributed(1, records_per_peer=1 << 12, fresh=True)
+    seed, dtau, pop = 4242, 0.01, 30000
+    v = R.GPUDVec([(addr, pop)], style=R.IsStochasticInteger(), ctx=ctx)
+    wm = R.working_memory(v, seed=seed)
+    ok, ov = np.array([oh.start_key], dtype=np.uint64), np.array([pop], dtype=np.int64)
+    shift = oh.diagonal_element(oh.start_key)
+    verdict = "ok"
+    for step in range(5):
+        out = v.similar()
+        R.apply_operator(wm, out, v, R.FirstOrderTransitionOperator(H, shift, dtau))
+        v = out
+        s = wm.last_stats
+        ok, ov, st = oh.step(orc.make_params(orc.STYLE_INTEGER, shift=shift, dtau=dtau, key=orc.step_key(seed, step)), ok, ov)
+        lk, lv = v.download()
+        parts = [(lk, lv)]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (lk, lv))
+        gk = np.concatenate([p[0] for p in parts]).reshape(-1)
+        gv = np.concatenate([p[1] for p in parts])
+        order = np.argsort(gk, kind="stable")
+        same = (np.array_equal(gk[order], ok.reshape(-1)) and np.array_equal(gv[order], ov)
+                and (s.spawn_attempts, s.len, s.ispawns, s.ideaths, s.iclones, s.izombies, s.inorm1)
+                == (st.spawn_attempts, st.len_after, st.ispawns, st.ideaths, st.iclones, st.izombies, st.inorm1))
+        if not same:
+            verdict = f"MISMATCH at step {step}"
+            break
+    del wm, v, out
+    import gc
+    gc.collect()
+    ctx.close(collective=True)  # every rank, same point: peer mappings are closed before their buffers are freed
+    return verdict
+
+
 # --------------------------------------------------------------------------- our arm (GPU)
 def pinned_array(R, shape, dtype):
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
@@ -191,6 +237,10 @@ def ours(args):
     target = per_gpu * world
     slots = 1 << max(16, int(math.ceil(math.log2(per_gpu * 3))))
     ctx = R.init_distributed(1, records_per_peer=int(per_gpu * 1.5), table_slots=slots)
+
+    preflight = parity_preflight(R, rank, world)  # before anything is timed
+    if preflight != "ok":
+        raise SystemExit(f"parity preflight failed on rank {rank}: {preflight}")
 
     addr = R.BoseFS(START_ONR)
     H = R.HubbardMom1D(addr, u=U_INT, t=T_HOP)
@@ -234,9 +284,10 @@ def ours(args):
     # ---- timed region: K resident steps
     launches0 = C.c_uint64()
     _lib.check(_lib.lib().rimu_ctx_launch_count(ctx.handle, C.byref(launches0)))
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local if world == 1 else ",".join(str(i) for i in range(world)))  # ONE sampler (rank 0) for all GPUs of the job
     barrier()
-    clocks.start()
+    if rank == 0:  # (eight nvidia-smi pollers at 20 ms each contend for the driver's locks with the ranks' own launches)
+        clocks.start()
     torch.cuda.profiler.start()  # cudaProfilerStart: `ncu --profile-from-start off` captures the timed steps only
     ev0.record(stream)
     tw0 = time.time()
@@ -338,7 +389,7 @@ def ours(args):
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    clk = clocks.stop()  # sampled every 20 ms across BOTH timed regions (resident steps and host-buffer steps)
+    clk = clocks.stop() if rank == 0 else None  # sampled every 20 ms across BOTH timed regions (resident steps and host-buffer steps)
     e2e_attempts = sum(rep["attempts"] for rep in reps)
     h2d, d2h = sum(rep["h2d"] for rep in reps), sum(rep["d2h"] for rep in reps)
     e2e_total_steps = e2e_steps * nrep
@@ -389,6 +440,7 @@ def ours(args):
                 "ms_per_step": float(t[0]) / e2e_total_steps, "steps": e2e_total_steps, "replicas_in_flight": nrep,
                 "wall_ms_per_step": 1e3 * e2e_wall / e2e_total_steps},
         "gpu_launches": int(launches1.value - launches0.value),
+        "parity_preflight": preflight,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -396,7 +448,9 @@ def ours(args):
         "extra": {"annihilation_gbs": annih_bytes / (annih_ms * 1e-3) / 1e9 if annih_ms > 0 else None,
                   "step_hbm_gbs": step_bytes / (ms_max / K * 1e-3) / 1e9, "step_hbm_frac_of_peak": step_bytes / (ms_max / K * 1e-3) / 1e9 / peak,
                   "phase_ms_per_step": {"spawn": acc["ms_spawn"] / K, "exchange": acc["ms_exch"] / K, "merge": acc["ms_compact"] / K},
-                  "wall_ms_per_step": 1e3 * wall / K, "norm": s.norm1, "shift": sp.shift},
+                  "wall_ms_per_step": 1e3 * wall / K, "norm": s.norm1, "shift": sp.shift,
+                  "buckets_per_gpu": int(s.buckets), "mean_bucket_fill": (P + A1) / max(int(s.buckets), 1),
+                  "max_bucket_fill": int(s.max_bucket_fill)},
     }
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample, rank 0, N=1 only

@@ -192,6 +192,11 @@ int rimu_comm_reserve(rimu_ctx *ctx, uint64_t exchange_records_per_peer);
  * send/recv (RIMU_B200_P2P=0 forces it).  Replaces the choice between the reference's AllToAll / PointToPoint / OneSided
  * communicators (communicators.jl:107-131). */
 int rimu_comm_p2p(rimu_ctx *ctx, int *enabled_out);
+/* Collective teardown of the peer mappings of a multi-GPU context (call on every rank, in the same order, before
+ * rimu_ctx_destroy): waits until no rank is still reading this rank's record streams, closes every imported mapping, and only
+ * then lets the exporters free their buffers (CUDA requires importers to close first).  No-op on one rank; the context remains
+ * usable afterwards only for local operations.  Reference: MPI.Finalize ordering, mpi_helpers.jl:9-30. */
+int rimu_comm_detach(rimu_ctx *ctx);
 int rimu_comm_allreduce_f64(rimu_ctx *ctx, double *host_inout, int n);
 /* owner rank of an address: communicators.jl:77-81 target_segment */
 int rimu_addr_owner(const uint64_t *key, int words, int nranks);

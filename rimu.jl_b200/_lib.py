@@ -159,6 +159,7 @@ SYMBOLS = {
     "rimu_comm_capacity": (C.c_int, [_vp, _u64p, _u64p]),
     "rimu_comm_reserve": (C.c_int, [_vp, C.c_uint64]),
     "rimu_comm_p2p": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "rimu_comm_detach": (C.c_int, [_vp]),
     "rimu_comm_allreduce_f64": (C.c_int, [_vp, _f64p, C.c_int]),
     "rimu_addr_owner": (C.c_int, [_u64p, C.c_int, C.c_int]),
     "rimu_addr_hash": (C.c_uint64, [_u64p, C.c_int]),

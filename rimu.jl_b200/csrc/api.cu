@@ -122,6 +122,7 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->part.rec); cudaFree(c->part.rcnt);
     cudaFree(c->lpart.rec); cudaFree(c->lpart.rcnt);
     cudaFree(c->heavy.items); cudaFree(c->heavy.packed); cudaFree(c->bucket_tmp);
+    cudaFree(c->spare_keys); cudaFree(c->spare_vals); cudaFree(c->spare_diag);
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaFree(c->d_red);
     cudaGetLastError(); // teardown is best effort (e.g. closing an IPC mapping whose exporter is already gone): never leave a stale error behind
@@ -225,8 +226,18 @@ static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool 
     if (keep_lanes && pt.rec && pt.nlane > nlane) nlane = pt.nlane; // local operations reuse a 3-lane layout (lane 0 only)
     const u32 nranks = shared ? (u32)c->nranks : 1u;
     const u32 nsrc = nranks * nlane;
+    // capacity of a sub-stream.  One rank: a whole bucket.  R ranks: a bucket's records arrive in R sub-streams of ~1/R each;
+    // Poisson spread around the largest mean the bucket-count policy allows (~0.6 * capacity, all of it records in the
+    // worst case) + 8 sigma.  Deliberately NOT a power of two: with 8 ranks the old 2 * cap / R = 512 records (8 KiB
+    // stride, 1 KiB of it used) mapped every open stream onto one seventh of the L2 sets, and the spawn kernel slowed
+    // down from 0.36 to 0.60 ms as 140 000 half-written lines fought over them (profiles/r2_multi_gpu.md).
     u32 rcap = capi;
-    if (nranks > 1) { rcap = 2 * capi / nranks; if (rcap < 128) rcap = 128; }
+    if (nranks > 1) {
+        const double mean = 0.6 * capi / nranks;
+        rcap = (u32)(mean + 8.0 * sqrt(mean) + 16.0);
+        rcap = (rcap + 15u) / 16u * 16u + 16u; // multiple of 16 records, odd multiple of 256 bytes for W = 1
+        if ((rcap / 16u) % 2u == 0) rcap += 16u;
+    }
     if (pt.nlane != nlane && pt.rec) nb_cap = 0; // the sub-stream layout changes: reallocate (collective in shared mode)
     pt.nsrc = nsrc; pt.nlane = nlane; pt.me = shared ? (u32)c->rank * nlane : 0u; pt.rcap = rcap; pt.direct = shared ? 1 : 0;
     if (nb <= nb_cap) { pt.nb = nb; return 0; }
@@ -355,6 +366,19 @@ static int p2p_probe(rimu_ctx *c) {
     return 0;
 }
 extern "C" int rimu_comm_p2p(rimu_ctx *c, int *enabled) { *enabled = c->direct; return 0; }
+extern "C" int rimu_comm_detach(rimu_ctx *c) {
+    if (!c || c->dead || c->nranks == 1 || !c->comm || c->detached) return 0;
+    TRY(enter_ctx(c));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double zero = 0.0;
+    TRY(rimu_comm_allreduce_f64(c, &zero, 1)); // every rank's kernels that read peer streams have finished
+    p2p_teardown(c);                           // close this rank's imports
+    TRY(rimu_comm_allreduce_f64(c, &zero, 1)); // every import is closed: exporters may free
+    cudaFree(c->part.rec); cudaFree(c->part.rcnt);
+    c->part.rec = nullptr; c->part.rcnt = nullptr; c->part_nb_cap = 0;
+    c->detached = 1;
+    return 0;
+}
 
 // staging buffers of the NCCL send/recv exchange (staged mode, and the table method in any mode); allocated on first use
 static int ensure_xch(rimu_ctx *c) {
@@ -1072,7 +1096,7 @@ int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_strea
 
 // ---- partitioned step (partition.cuh)
 // re-segment a vector for `nb` buckets (count, scan, scatter into fresh arrays); contents are unchanged
-static int rebucket(rimu_vec *v, u32 nb) {
+int rebucket(rimu_vec *v, u32 nb) {
     rimu_ctx *c = v->ctx;
     TRY(ensure_seg(v, nb));
     if (v->n == 0) {
@@ -1084,20 +1108,31 @@ static int rebucket(rimu_vec *v, u32 nb) {
     TRY(ensure_bucket_tmp(c, nb));
     u32 *counts = c->bucket_tmp, *fill = c->bucket_tmp + c->bucket_tmp_cap;
     CUDA_TRY(cudaMemsetAsync(counts, 0, nb * sizeof(u32), c->stream));
-    u64 *nk = nullptr, *nv = nullptr;
-    CUDA_TRY(rimu_malloc(&nk, v->cap * c->W * sizeof(u64)));
-    CUDA_TRY(rimu_malloc(&nv, v->cap * sizeof(u64)));
+    const bool keep_diag = v->diag && v->diag_uid != 0 && v->diag_cap >= v->cap;
+    if (c->spare_cap != v->cap || (keep_diag && !c->spare_diag)) { // (re)allocate the ping-pong partner for this capacity
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->spare_keys); cudaFree(c->spare_vals); cudaFree(c->spare_diag);
+        c->spare_keys = c->spare_vals = nullptr; c->spare_diag = nullptr; c->spare_cap = 0;
+        CUDA_TRY(rimu_malloc(&c->spare_keys, v->cap * c->W * sizeof(u64)));
+        CUDA_TRY(rimu_malloc(&c->spare_vals, v->cap * sizeof(u64)));
+        if (v->diag) CUDA_TRY(rimu_malloc(&c->spare_diag, v->cap * sizeof(double)));
+        c->spare_cap = v->cap;
+    }
+    u64 *nk = c->spare_keys, *nv = c->spare_vals;
+    double *nd = keep_diag ? c->spare_diag : nullptr;
     const int grid = grid_for(v->n, c->sm_count, 16);
     if (c->W == 1) bucket_count_kernel<1><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, v->n, c->nranks, nb, counts);
     else bucket_count_kernel<2><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, v->n, c->nranks, nb, counts);
     bucket_scan_kernel<<<1, 1024, 0, c->stream>>>(counts, nb, v->seg_start, v->seg_len, fill);
-    if (c->W == 1) bucket_scatter_kernel<1><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, (const u64 *)v->vals, v->n, c->nranks, nb, v->seg_start, fill, nk, nv);
-    else bucket_scatter_kernel<2><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, (const u64 *)v->vals, v->n, c->nranks, nb, v->seg_start, fill, nk, nv);
+    if (c->W == 1) bucket_scatter_kernel<1><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, (const u64 *)v->vals, keep_diag ? v->diag : nullptr, v->n, c->nranks, nb, v->seg_start, fill, nk, nv, nd);
+    else bucket_scatter_kernel<2><<<grid, RIMU_TPB, 0, c->stream>>>(v->keys, (const u64 *)v->vals, keep_diag ? v->diag : nullptr, v->n, c->nranks, nb, v->seg_start, fill, nk, nv, nd);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    cudaFree(v->keys); cudaFree(v->vals);
+    c->launches += 3;
+    // swap: the vector now lives in the former spare buffers, its old buffers are the next spare (all stream-ordered)
+    c->spare_keys = v->keys; c->spare_vals = (u64 *)v->vals;
     v->keys = nk; v->vals = nv; v->nb = nb;
-    v->diag_uid = 0; // entries moved: the diagonal cache no longer lines up
+    if (keep_diag) { c->spare_diag = v->diag; v->diag = nd; v->diag_cap = v->cap; } // the cached H_aa moved with their entries
+    else v->diag_uid = 0;
     return 0;
 }
 
@@ -1139,11 +1174,19 @@ static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
     // round boundary, where every round of every bucket is nearly full.
     const double slots = (double)rounds * PART_NT, upper = slots - 1.5 * sqrt(slots);
     const double expected = parents * (1.0 + c->rec_per_parent) * 1.02 + 64.0;
-    if (src->nb) {
+    // a count that overflowed is not tried again (nor anything within 20 % of it) until the vector has shrunk by a fifth
+    double floor_nb = 1.0;
+    if (c->ovf_nb) {
+        if (expected >= 0.8 * c->ovf_expected) floor_nb = ceil(1.2 * (double)c->ovf_nb);
+        else c->ovf_nb = 0;
+    }
+    if (src->nb && (double)src->nb >= floor_nb) {
         double fill = expected / src->nb;
         if (fill >= 0.7 * upper && fill <= upper) return src->nb;
+        if (c->ovf_nb && fill <= upper && (double)src->nb <= 1.5 * floor_nb) return src->nb; // the retry's count: keep it
     }
     double nb = ceil(expected / (0.9 * upper));
+    if (nb < floor_nb) nb = floor_nb;
     return nb < 1.0 ? 1u : (u32)nb;
 }
 
@@ -1155,6 +1198,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
     if (!prm || !src || !dst) return fail(RIMU_ERR_INVALID, "null argument");
     if (src == dst) return fail(RIMU_ERR_INVALID, "source and target must not alias (Interfaces/dictvectors.jl:115-117)");
     if (src->ctx != c || dst->ctx != c) return fail(RIMU_ERR_INVALID, "vectors belong to another context");
+    if (c->detached) return fail(RIMU_ERR_INVALID, "this context was detached from its peers (rimu_comm_detach): no further steps");
     if (src->vt != dst->vt) return fail(RIMU_ERR_INVALID, "source and target value types differ");
     const bool is_int = prm->style == RIMU_STYLE_INTEGER;
     if (is_int != (src->vt == RIMU_VAL_I64))
@@ -1241,7 +1285,10 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
                 const double cap = (double)part_cap_items(c->W);
                 const double recs = multi ? (double)g.records / c->nranks * 1.02 : (double)l.records; // g.records: summed over ranks
                 double need = ceil((parents + recs) * 1.15 / (0.6 * cap)); // (diagonal records may be counted twice: harmless)
-                u32 nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb * 2 + 1);
+                // a marginal overflow (Poisson tail, a sub-stream a few records short) needs a quarter more buckets, a gross
+                // one (the estimate of records per parent was off) what the counted records ask for
+                u32 nb2 = need > (double)nb * 1.25 ? (u32)need : (u32)(nb + nb / 4 + 1);
+                c->ovf_nb = nb; c->ovf_expected = parents * (1.0 + c->rec_per_parent) * 1.02 + 64.0;
                 if (!multi && !p.init_rule && (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26))) use_part = false; // one address is too hot to pre-sum: use the table
                 if (multi && nb2 > (1u << 26)) return fail(RIMU_ERR_WORKMEM, "bucket streams cannot be grown further");
                 nb = nb2;

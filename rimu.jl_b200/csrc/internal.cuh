@@ -119,6 +119,7 @@ struct rimu_ctx {
     u64 next_vec_uid;        // vectors are numbered in creation order: the same numbers on every rank (same call sequence)
     u32 merge_grid_cap;      // RIMU_B200_MERGE_GRID: cap on merge CTAs (tests force many buckets per CTA with it)
     int live_vecs;           // vectors created on this context and not yet destroyed
+    int detached;            // rimu_comm_detach ran: the peer mappings are closed, steps are no longer possible
     int dead;                // rimu_ctx_destroy was called while vectors were alive: the struct (and stream) live on until the
                              //   last of them is destroyed (host GCs finalise vectors and contexts in arbitrary order) // global length of the previous step's result
     HeavyDev heavy;
@@ -130,6 +131,12 @@ struct rimu_ctx {
     char *d_ipc, *h_ipc;     // all-gather scratch for the IPC handles
     alignas(16) char sort_scratch[96];   // SortScratch of sort.cu (opaque here)
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
+    u32 ovf_nb; double ovf_expected; // the last bucket count that overflowed and the expected item count it overflowed at:
+                             //   choose_buckets stays above it until the vector has shrunk (no flip-flop between a count
+                             //   that overflows and the retry's larger one)
+    u64 *spare_keys, *spare_vals; double *spare_diag; u64 spare_cap; // ping-pong partner of rebucket(): re-segmenting a
+                             //   vector swaps it into these buffers and keeps the old ones as the next spare (no cudaMalloc,
+                             //   no synchronisation when a host-fed vector is re-segmented every step)
     u64 last_max_fill;
 };
 RIMU_INTERNAL int enter_ctx(rimu_ctx *c);
@@ -176,6 +183,7 @@ RIMU_INTERNAL int ensure_seg(rimu_vec *v, u32 nb);
 RIMU_INTERNAL int ensure_diag(rimu_vec *v);
 RIMU_INTERNAL int ensure_part(rimu_ctx *c, u32 nb, u32 nlane = 1);
 RIMU_INTERNAL int ensure_heavy(rimu_ctx *c, u64 parents);
+RIMU_INTERNAL int rebucket(rimu_vec *v, u32 nb); // re-segment a vector for nb buckets (contents unchanged; cached H_aa follow)
 RIMU_INTERNAL int exchange_spawns(rimu_ctx *c, int vt, u64 slots, i64 *sent_out, bool to_streams);
 static inline u32 part_cap_items(int W) { return W == 1 ? (u32)PartCap<1>::value : (u32)PartCap<2>::value; }
 static inline size_t part_smem_bytes(int W) { u32 cap = part_cap_items(W); return (size_t)cap * W * 8 + (size_t)cap * 8 + (size_t)cap * 2 * 4 + (size_t)cap * 2; }

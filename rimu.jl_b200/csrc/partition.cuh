@@ -883,8 +883,9 @@ bucket_scan_kernel(const u32 *__restrict__ counts, u32 nb, u64 *__restrict__ seg
 }
 template <int W>
 __global__ void __launch_bounds__(RIMU_TPB)
-bucket_scatter_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, i64 n, int nranks, u32 nb,
-                      const u64 *__restrict__ seg_start, u32 *__restrict__ fill, u64 *__restrict__ okeys, u64 *__restrict__ ovals) {
+bucket_scatter_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals, const double *__restrict__ diag, i64 n, int nranks, u32 nb,
+                      const u64 *__restrict__ seg_start, u32 *__restrict__ fill, u64 *__restrict__ okeys, u64 *__restrict__ ovals,
+                      double *__restrict__ odiag) {
     typedef typename BitsT<W>::type B;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
         B key = load_key<W>(keys + i * W);
@@ -892,6 +893,7 @@ bucket_scatter_kernel(const u64 *__restrict__ keys, const u64 *__restrict__ vals
         u64 at = seg_start[b] + atomicAdd(&fill[b], 1u);
         store_key<W>(okeys + at * W, key);
         ovals[at] = vals[i];
+        if (diag) odiag[at] = diag[i]; // the cached diagonal elements move with their entries
     }
 }
 #endif // __CUDACC__

@@ -44,7 +44,12 @@ static int step_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec 
 template <int HK, int W, class VT>
 static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, u32 nb, i64 *sent) {
     const i64 n = src->n;
-    const bool seg = src->nb == nb && n > 0; // parents can be read by bucket segment; else their diagonal deposits go through the streams
+    // Parents are read by bucket segment.  A source that is not segmented for this bucket count (fresh upload, changed count):
+    //  * one rank: its diagonal deposits travel through the bucket streams like spawns (one extra record per parent);
+    //  * several ranks: the sub-streams are sized for 1/R of a bucket's records, so the parents would not fit the one local
+    //    sub-stream -- the source is re-segmented in place instead (count / scan / scatter; the dictionary is unchanged).
+    if (c->nranks > 1 && c->direct && src->nb != nb && n > 0) TRY(rebucket(src, nb));
+    const bool seg = src->nb == nb && n > 0;
     TRY(ensure_seg(dst, nb));
     TRY(ensure_diag(dst));
     const double *src_diag = (src->diag_uid == h->uid && src->diag) ? src->diag : nullptr;

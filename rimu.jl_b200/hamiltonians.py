@@ -67,8 +67,17 @@ class Context:
         _lib.check(_lib.lib().rimu_comm_allreduce_f64(self.handle, arr, len(values)))
         return list(arr)
 
-    def close(self):
+    def detach(self):
+        """Collective (every rank, same order): close the peer mappings before anybody frees the buffers behind them."""
+        if self.handle and self.nranks > 1:
+            _lib.check(_lib.lib().rimu_comm_detach(self.handle))
+
+    def close(self, collective: bool = False):
+        """Destroy the context.  `collective=True` (multi-GPU: called by every rank at the same point) detaches from the peers
+        first; the default is a local, best-effort teardown (finalisers, process exit)."""
         if self.handle:
+            if collective:
+                self.detach()
             _lib.lib().rimu_ctx_destroy(self.handle)
             self.handle = None
 
