@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=float, default=1e7, help="target walkers per GPU")
     ap.add_argument("--equil", type=int, default=40, help="extra equilibration steps once within 5%% of the target")
-    ap.add_argument("--cpu-walkers", type=float, default=2e5, help="reference arm: walkers of the bounded CPU sample")
+    ap.add_argument("--cpu-walkers", type=float, default=0, help="reference arm: walkers of the CPU run (0 = --walkers, the GPU arm's per-GPU workload)")
+    ap.add_argument("--long-steps", type=int, default=200, help="extra resident steps timed after the K contract steps (robust ms/step; 0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--e2e-replicas", type=int, default=3, help="independent replicas in flight in the host-buffer (e2e) measurement")
@@ -118,7 +119,9 @@ def reference_arm(args):
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     oh = orc.OracleHam("HubbardMom1D", "bose", START_ONR, u=U_INT, t=T_HOP)
-    target = args.cpu_walkers
+    # the SAME workload as the GPU arm: 1e7 target walkers (one GPU's share when the job has several), grown on the CPU by
+    # the same DoubleLogUpdate schedule
+    target = args.cpu_walkers or args.walkers
     keys = np.array([oh.start_key], dtype=np.uint64)
     vals = np.array([10.0])
     shift0 = oh.diagonal_element(oh.start_key)
@@ -132,15 +135,16 @@ def reference_arm(args):
         return oh.step(p, keys, vals, threads=cores)
 
     # DoubleLogUpdate from the first step, as ProjectorMonteCarloProblem does by default
-    t_budget, settled = time.time(), Settled(target, args.equil)
+    t_budget, settled = time.time(), Settled(target, min(args.equil, 12))  # (a CPU step at 1e7 walkers takes ~1 s: equilibrate 12 steps, not 40)
     while True:
         keys, vals, st = one(step, shift)
         step += 1
         tnorm = st.norm1
         shift -= xi / DTAU * math.log(tnorm / target) + zeta / DTAU * math.log(tnorm / pnorm)
         pnorm = tnorm
-        if settled.update(tnorm, st.len_after) or step >= 1500 or time.time() - t_budget > 150:
+        if settled.update(tnorm, st.len_after) or step >= 3000 or time.time() - t_budget > 900:
             break
+    grow_s = time.time() - t_budget
     for _ in range(args.warmup):
         keys, vals, st = one(step, shift)
         step += 1
@@ -154,12 +158,16 @@ def reference_arm(args):
         step += 1
     dt = time.time() - t0
     val = attempts / dt
-    sample = f"{WORKLOAD}, {target:.0e} walkers (bounded sample of the 1e7-walker workload), {len(vals)} determinants"
+    world = max(1, args.gpus)
+    sample = (f"{WORKLOAD}, {target:.0e} target walkers grown on the CPU in {step - args.steps - args.warmup} steps ({grow_s:.0f} s), "
+              f"{len(vals)} determinants; every timed step is one full FCIQMC step over that vector"
+              + (f" (= ONE GPU's share of the {world}-GPU job: bounded sample)" if world > 1 else ""))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "walkers_per_gpu": target,
+        "config": {"workload": WORKLOAD, "walkers_per_gpu": target, "target_walkers": target * world,
+                   "parallelism": f"hash-partitioned x{world}",
                    "note": "CPU port of Rimu's threaded PDVec path (the reference is Julia and cannot run here; probe: julia "
                            + ("present but Rimu.jl is not installed offline" if shutil.which("julia") else "absent") + ")"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -305,6 +313,21 @@ def ours(args):
     ms = ev0.elapsed_time(ev1)
     launches1 = C.c_uint64()
     _lib.check(_lib.lib().rimu_ctx_launch_count(ctx.handle, C.byref(launches1)))
+    # the K contract steps last ~20 ms -- one nvidia-smi sample.  A longer run of resident steps (same loop, same events)
+    # gives the clock sampler something to see and a ms/step that does not hinge on 20 steps
+    long_ms = None
+    if args.long_steps > 0:
+        evl0, evl1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        evl0.record(stream)
+        for _ in range(args.long_steps):
+            one_step()
+        evl1.record(stream)
+        barrier()
+        tl = torch.tensor([evl0.elapsed_time(evl1)], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        long_ms = float(tl[0]) / args.long_steps
     t = torch.tensor([ms], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -378,22 +401,39 @@ def ours(args):
             if rep["err"] is not None:
                 raise rep["err"]
 
-    run_all(2, False)  # warm-up: working memory of every replica context sized, pinned pages touched
-    barrier()
-    ev0.record(stream)
-    tw0 = time.time()
-    run_all(e2e_steps, True)  # every thread returns only after its last download has completed (stream-synchronised)
-    ev1.record(stream)
-    barrier()
-    e2e_wall = time.time() - tw0
-    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    clk = clocks.stop() if rank == 0 else None  # sampled every 20 ms across BOTH timed regions (resident steps and host-buffer steps)
-    e2e_attempts = sum(rep["attempts"] for rep in reps)
-    h2d, d2h = sum(rep["h2d"] for rep in reps), sum(rep["d2h"] for rep in reps)
-    e2e_total_steps = e2e_steps * nrep
-    e2e_val = e2e_attempts / (float(t[0]) * 1e-3)
+    def measure_e2e(n_active):
+        """host-buffer steps with the first n_active replicas in flight; returns the e2e record"""
+        nonlocal nrep
+        all_reps, saved = reps[:], nrep
+        del reps[n_active:]
+        nrep = n_active
+        for rep_ in reps:
+            rep_["attempts"] = rep_["h2d"] = rep_["d2h"] = 0
+        try:
+            run_all(2, False)  # warm-up: working memory of every replica context sized, pinned pages touched
+            barrier()
+            ev0.record(stream)
+            tw = time.time()
+            run_all(e2e_steps, True)  # every thread returns only after its last download has completed (stream-synchronised)
+            ev1.record(stream)
+            barrier()
+            wall_ = time.time() - tw
+            tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            att = sum(rep_["attempts"] for rep_ in reps)
+            h2d_, d2h_ = sum(rep_["h2d"] for rep_ in reps), sum(rep_["d2h"] for rep_ in reps)
+            total = e2e_steps * n_active
+            return {"value": att / (float(tt[0]) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_ // total,
+                    "d2h_bytes_per_step": d2h_ // total, "ms_per_step": float(tt[0]) / total, "steps": total,
+                    "replicas_in_flight": n_active, "wall_ms_per_step": 1e3 * wall_ / total}
+        finally:
+            reps[:] = all_reps
+            nrep = saved
+
+    e2e_pipelined = measure_e2e(nrep)            # headline: independent replicas keep both PCIe directions busy
+    e2e_serial = measure_e2e(1) if nrep > 1 else e2e_pipelined  # the plain call sequence: upload, step, download
+    clk = clocks.stop() if rank == 0 else None  # sampled every 20 ms across ALL timed regions (resident steps and host-buffer steps)
 
     # ---- roofline of the dominant kernel (CUDA-event durations measured live inside rimu_step, per launch averages)
     K = args.steps
@@ -436,9 +476,8 @@ def ours(args):
                    "attempts_per_step": acc["attempts"] / K, "method": "partition (bucket streams + shared-memory annihilation)",
                    "l2": "inputs larger than L2: walker vector + spawn record streams of a step exceed 126 MB",
                    "growth_steps": nsteps, "equil_steps": args.equil, "parallelism": f"hash-partitioned x{world}"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_total_steps, "d2h_bytes_per_step": d2h // e2e_total_steps,
-                "ms_per_step": float(t[0]) / e2e_total_steps, "steps": e2e_total_steps, "replicas_in_flight": nrep,
-                "wall_ms_per_step": 1e3 * e2e_wall / e2e_total_steps},
+        "e2e": e2e_pipelined,
+        "e2e_serial": e2e_serial,
         "gpu_launches": int(launches1.value - launches0.value),
         "parity_preflight": preflight,
         "clocks": clk,
@@ -449,6 +488,7 @@ def ours(args):
                   "step_hbm_gbs": step_bytes / (ms_max / K * 1e-3) / 1e9, "step_hbm_frac_of_peak": step_bytes / (ms_max / K * 1e-3) / 1e9 / peak,
                   "phase_ms_per_step": {"spawn": acc["ms_spawn"] / K, "exchange": acc["ms_exch"] / K, "merge": acc["ms_compact"] / K},
                   "wall_ms_per_step": 1e3 * wall / K, "norm": s.norm1, "shift": sp.shift,
+                  "long_run": {"steps": args.long_steps, "ms_per_step": long_ms},
                   "buckets_per_gpu": int(s.buckets), "mean_bucket_fill": (P + A1) / max(int(s.buckets), 1),
                   "max_bucket_fill": int(s.max_bucket_fill)},
     }

@@ -62,6 +62,14 @@ def make_config(R, cid, walkers):
         return dict(name="ref-bench (50,50) HubbardReal1D BoseFS{50,50} u=6 IsDynamicSemistochastic (benchmark/benchmarks.jl:66-73)",
                     ham=lambda: R.HubbardReal1D(a, u=6.0, t=1.0), addr=a, style=R.IsDynamicSemistochastic(), dtau=1e-4,
                     walkers=walkers or 5e4, words=2)
+    # north_star's headline wording: "2D Hubbard at 1e9 walkers" -- no such stochastic config is listed in BASELINE.json
+    # (SURVEY 8g), so it is reported on config 3's model run stochastically: 4x4 Fermi-Hubbard at half filling, 1.25e8
+    # walkers per GPU (= 1e9 on 8 GPUs; the sector has 1.66e8 determinants, so every determinant carries several walkers)
+    if cid == 8:
+        a = R.FermiFS2C(fermi(16, range(1, 9)), fermi(16, range(5, 13)))
+        return dict(name="headline 2D Hubbard: HubbardRealSpace 4x4 FermiFS2C 8+8 u=1 IsDynamicSemistochastic",
+                    ham=lambda: R.HubbardRealSpace(a, geometry=R.PeriodicBoundaries(4, 4), t=(1.0, 1.0), u=((0.0, 1.0), (1.0, 0.0))),
+                    addr=a, style=R.IsDynamicSemistochastic(), dtau=1e-3, walkers=walkers or 1.25e8, words=1)
     raise ValueError(cid)
 
 
@@ -129,7 +137,8 @@ def run_stochastic(R, cfg, args, world, rank, dist, torch, peak):
             "phase_ms": {"spawn": acc["spawn"] / K, "exchange": acc["exch"] / K, "merge": acc["merge"] / K},
             "algorithmic_bytes_per_step_per_gpu": step_bytes, "hbm_gbs": step_bytes / (ms * 1e-3) / 1e9,
             "hbm_frac_of_measured_peak": step_bytes / (ms * 1e-3) / 1e9 / peak, "growth_steps": nsteps, "steps": K,
-            "shift": sp.shift, "dtau": cfg["dtau"], "words": W}
+            "shift": sp.shift, "dtau": cfg["dtau"], "words": W, "buckets_per_gpu": int(s.buckets), "max_bucket_fill": int(s.max_bucket_fill),
+            "sent_records_per_step_per_gpu": int(s.sent_records)}
 
 
 def run_deterministic(R, cfg, args, world, rank, dist, torch, peak):

@@ -42,6 +42,7 @@ SPECS = {
     "rs_f2c_trap": ("HubbardRealSpace", "fermi2c", (_fermi(6, (1, 2, 4, 5)), _fermi(6, (2, 3))), dict(t=(1.0, 2.0), u=((0.0, 0.5), (0.5, 0.0)), dims=(6,), trap=((0.1,), (0.2,)))),
     "tc_7": ("Transcorrelated1D", "fermi2c", (_fermi(7, (3, 5)), _fermi(7, (4,))), dict(t=24.5, v=7.0, cutoff=1, three_body_term=True)),
     "tc_8_cut2": ("Transcorrelated1D", "fermi2c", (_fermi(8, (3, 4, 6)), _fermi(8, (2, 5))), dict(t=1.0, v=1.5, cutoff=2, three_body_term=True)),
+    "tc_12": ("Transcorrelated1D", "fermi2c", (_fermi(12, (5, 6, 7)), _fermi(12, (6, 7))), dict(t=1.0, v=1.0, cutoff=1, three_body_term=True)),  # config 5's model, small enough for ED
     "tc_32": ("Transcorrelated1D", "fermi2c", (_fermi(32, (15, 16, 17)), _fermi(32, (15, 16, 17))), dict(t=1.0, v=1.0, cutoff=1, three_body_term=True)),  # config 5
     "tc_no3b": ("Transcorrelated1D", "fermi2c", (_fermi(6, (2, 3)), _fermi(6, (3, 4))), dict(t=1.0, v=-2.0, cutoff=1, three_body_term=False)),
 }

@@ -9,6 +9,37 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def energy_mode(R, rank, world):
+    """BASELINE config 5's correctness check at the world size this worker runs with: FCIQMC on Transcorrelated1D (M=12,
+    3 up 2 down, three-body term, non-Hermitian) through the full driver -- ProjectorMonteCarloProblem, DoubleLogUpdate,
+    ProjectedEnergy over the AdjointUnknown sweep -- with the vector hash-partitioned over the ranks.  Shift and projected
+    energy must agree with the oracle's exact diagonalisation within blocking-analysis error bars
+    (test/lomc.jl:518-541, test/mpi_runtests.jl:140-155)."""
+    import json
+    from tests.cases import oracle_ham, product_ham
+    oh = oracle_ham("tc_12")
+    e_exact = oh.exact_energy(hermitian=False)
+    R.reset_contexts()
+    R.init_distributed(oh.W, records_per_peer=1 << 14)
+    ph = product_ham("tc_12")
+    ref = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=R.IsDynamicSemistochastic(), time_step=0.002, last_step=5000,
+                                        target_walkers=20_000, random_seed=11, max_length=10 ** 6,
+                                        post_step_strategy=(R.ProjectedEnergy(ph, ref),))
+    sim = R.solve(prob)
+    assert sim.success, sim.message
+    df = sim.dataframe()
+    se = R.shift_estimator(df, skip=1500)
+    pe = R.projected_energy(df, skip=1500)
+    tol_bias = 0.01 * abs(e_exact)
+    ok = abs(se.mean - e_exact) < 5 * se.err + tol_bias and abs(pe.f - e_exact) < 5 * pe.sigma_f + tol_bias
+    if rank == 0:
+        print("mgpu energy " + json.dumps({"model": "Transcorrelated1D M=12 3up2down 3-body", "world": world, "exact": e_exact,
+                                           "shift": se.mean, "shift_err": se.err, "projected": pe.f, "projected_err": pe.sigma_f,
+                                           "walkers": 20000, "steps": 5000, "within_5_sigma_plus_1pct": bool(ok)}), flush=True)
+    assert ok, (se.mean, se.err, pe.f, pe.sigma_f, e_exact)
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -18,6 +49,12 @@ def main():
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    if os.environ.get("RIMU_MGPU_MODE") == "energy":
+        energy_mode(R, rank, world)
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     method = os.environ.get("RIMU_B200_METHOD", "partition")
     direct = os.environ.get("RIMU_B200_P2P", "1") != "0"
     cases = [("real1d_10", "int", 0), ("rs_bose_3d_w2", "int", 0), ("mom1d_bose", "semi", 0), ("rs_f2c_4x4", "int", 0)]

@@ -102,6 +102,28 @@ def test_fciqmc_energy_within_error_bars(built, name, style_name, walkers, dtau,
     assert abs(n.mean() - walkers) < 0.1 * walkers  # DoubleLogUpdate holds the population
 
 
+def test_transcorrelated_energy_within_error_bars(built):
+    """BASELINE config 5's check on a size exact diagonalisation can reach: Transcorrelated1D (non-Hermitian, three-body term)
+    M=12, 3 up 2 down (momentum sector of 1210 determinants).  The projected energy goes through the AdjointUnknown path -- dot(ref, H, v) as an explicit H*v sweep
+    (poststepstrategy.jl:102-115, abstractdvec.jl:313-324) -- and both estimators must bracket the lowest eigenvalue of the
+    momentum sector within blocking-analysis error bars."""
+    import rimu_b200 as R
+    oh, ph = oracle_ham("tc_12"), product_ham("tc_12")
+    e_exact = oh.exact_energy(hermitian=False)
+    ref = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=R.IsDynamicSemistochastic(), time_step=0.002, last_step=6000,
+                                        target_walkers=20_000, random_seed=11, max_length=10 ** 6,
+                                        post_step_strategy=(R.ProjectedEnergy(ph, ref),))
+    sim = R.solve(prob)
+    assert sim.success, sim.message
+    df = sim.dataframe()
+    se = R.shift_estimator(df, skip=2000)
+    pe = R.projected_energy(df, skip=2000)
+    tol_bias = 0.01 * abs(e_exact)
+    assert abs(se.mean - e_exact) < 5 * se.err + tol_bias, (se.mean, se.err, e_exact)
+    assert abs(pe.f - e_exact) < 5 * pe.sigma_f + tol_bias, (pe.f, pe.sigma_f, e_exact)
+
+
 # --------------------------------------------------------------------------- size-independent properties
 def _truncate(R, x, n):
     """One more hop can overshoot by orders of magnitude: keep a seeded subset of at most n entries."""

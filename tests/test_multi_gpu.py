@@ -46,3 +46,14 @@ def test_many_rank_steps_match_oracle(built, world):
     out = _run_worker(world, "partition", "1")
     assert out.count("mgpu ok") == 6
     assert f"world={world}" in out
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_multi_rank_transcorrelated_energy(built, world):
+    """Config 5's blocking-analysis energy check with the walker vector partitioned over `world` GPUs."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = _run_worker(world, "partition", "1", {"RIMU_MGPU_MODE": "energy"})
+    assert "mgpu energy" in out and '"within_5_sigma_plus_1pct": true' in out
+    print(out[out.index("mgpu energy"):].splitlines()[0])
