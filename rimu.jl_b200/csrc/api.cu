@@ -121,10 +121,10 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->d_reduce);
     cudaFree(c->part.rec); cudaFree(c->part.rcnt);
     cudaFree(c->lpart.rec); cudaFree(c->lpart.rcnt);
-    cudaFree(c->heavy.items); cudaFree(c->heavy.packed); cudaFree(c->bucket_tmp);
+    cudaFree(c->heavy.items); cudaFree(c->bucket_tmp);
     cudaFree(c->spare_keys); cudaFree(c->spare_vals); cudaFree(c->spare_diag);
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
-    cudaFree(c->d_red);
+    cudaFree(c->d_red); cudaFreeHost(c->h_red);
     cudaGetLastError(); // teardown is best effort (e.g. closing an IPC mapping whose exporter is already gone): never leave a stale error behind
     if (c->live_vecs > 0) { // vectors still point at this context: keep the struct and the stream until the last one goes
         c->dead = 1;
@@ -255,6 +255,7 @@ static int ensure_part_impl(rimu_ctx *c, PartDev &pt, u64 &nb_cap, u32 nb, bool 
     CUDA_TRY(rimu_malloc(&pt.rec, cap * nsrc * rcap * rw * sizeof(u64)));
     CUDA_TRY(rimu_malloc(&pt.rcnt, (size_t)nsrc * cap * sizeof(u32)));
     CUDA_TRY(cudaMemsetAsync(pt.rcnt, 0, (size_t)nsrc * cap * sizeof(u32), c->stream));
+    if (&pt == &c->part) c->rcnt_clean = 0; // (conservative: the step clears what it uses)
     nb_cap = cap; pt.nb = nb;
     if (shared) TRY(p2p_setup(c));
     return 0;
@@ -265,7 +266,7 @@ static PartDev &local_part(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? 
 static u64 &local_part_cap(rimu_ctx *c) { return (c->nranks > 1 && c->direct) ? c->lpart_nb_cap : c->part_nb_cap; }
 static int ensure_local_part(rimu_ctx *c, u32 nb) { return ensure_part_impl(c, local_part(c), local_part_cap(c), nb, false, 1, true); }
 int ensure_heavy(rimu_ctx *c, u64 parents) {
-    if (!c->heavy.packed) CUDA_TRY(rimu_malloc(&c->heavy.packed, sizeof(u64)));
+    c->heavy.packed = (u64 *)&c->d_stats->heavy_packed; // cleared together with the statistics block
     if (parents <= c->heavy.cap) return 0;
     u64 cap = parents + parents / 4 + 1024;
     cudaFree(c->heavy.items); c->heavy.items = nullptr; c->heavy.cap = 0;
@@ -710,6 +711,7 @@ static int records_to_vec_part(rimu_ctx *c, rimu_vec *dst, const u64 *d_keys, co
             return records_to_vec(c, dst, d_keys, d_vals, n, d_keys2, d_vals2, n2, a1, a2, use_scale);
         TRY(ensure_local_part(c, nb));
         PartDev &lp = local_part(c);
+        if (&lp == &c->part) c->rcnt_clean = 0; // the step's streams are borrowed: the step clears them again itself
         TRY(ensure_seg(dst, nb));
         CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
         CUDA_TRY(cudaMemsetAsync(lp.rcnt, 0, (size_t)lp.nsrc * nb * sizeof(u32), c->stream));
@@ -1268,14 +1270,15 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             // rank from overwriting its record streams (next step) while a peer's merge is still reading them.
             if (!c->d_red) CUDA_TRY(rimu_malloc(&c->d_red, RIMU_STATS_NPACK * sizeof(double)));
             pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 0, dst->cap);
-            NCCL_TRY(g_nccl.AllReduce(c->d_red, c->d_red, RIMU_STATS_NPACK, ncclFloat64, ncclSum, c->comm, c->stream));
-            pack_stats_kernel<<<1, 32, 0, c->stream>>>(c->d_stats, c->d_red, 1, dst->cap);
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+            NCCL_TRY(g_nccl.AllReduce(c->d_red, c->d_red, RIMU_STATS_NPACK, ncclFloat64, ncclSum, c->comm, c->stream));
+            if (!c->h_red) CUDA_TRY(cudaMallocHost(&c->h_red, RIMU_STATS_NPACK * sizeof(double)));
+            CUDA_TRY(cudaMemcpyAsync(c->h_red, c->d_red, RIMU_STATS_NPACK * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         }
         CUDA_TRY(cudaEventRecord(c->ev[5], c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        if (c->nranks == 1) *c->h_stats = *c->h_stats_local;
+        *c->h_stats = *c->h_stats_local;
+        if (c->nranks > 1) unpack_stats_host(c->h_stats, c->h_red); // the summed blocks replace the local ones (host side: no second kernel)
         const StatsDev &g = *c->h_stats, &l = *c->h_stats_local;
         if (c->nranks > 1 && use_part) sent = l.sent; // (the table method counts in exchange_spawns)
         if (g.overflow_table) { // some rank ran out of room: every rank retries with more working memory
@@ -1285,11 +1288,29 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
                 const double cap = (double)part_cap_items(c->W);
                 const double recs = multi ? (double)g.records / c->nranks * 1.02 : (double)l.records; // g.records: summed over ranks
                 double need = ceil((parents + recs) * 1.15 / (0.6 * cap)); // (diagonal records may be counted twice: harmless)
-                // a marginal overflow (Poisson tail, a sub-stream a few records short) needs a quarter more buckets, a gross
-                // one (the estimate of records per parent was off) what the counted records ask for
-                u32 nb2 = need > (double)nb * 1.25 ? (u32)need : (u32)(nb + nb / 4 + 1);
+                u32 nb2;
+                if (!multi) {
+                    // The fullest bucket = the uniform load (mean fill) + whatever a hot address piles on top of it (e.g. the
+                    // reference determinant receiving a record from each of its thousands of neighbours).  More buckets only
+                    // thin out the uniform part: size the retry so that the hot part + the thinned mean fits, and go straight
+                    // to the table method when the hot part alone does not fit a bucket.
+                    const double mean = (parents + recs) / (double)nb;
+                    const double hot = (double)l.max_fill > mean ? (double)l.max_fill - mean : 0.0;
+                    const double room = 0.85 * cap - hot;
+                    if (room < 0.05 * cap) {
+                        if (p.init_rule) return fail(RIMU_ERR_WORKMEM, "one address receives more records in a step (%llu) than a bucket holds; initiator steps cannot fall back to the table method", (unsigned long long)l.max_fill);
+                        use_part = false;
+                        continue;
+                    }
+                    const double fit = ceil((parents + recs) * 1.05 / room);
+                    nb2 = fit > (double)nb * 1.25 ? (u32)fit : (u32)(nb + nb / 4 + 1);
+                    if ((double)nb2 < need) nb2 = (u32)need;
+                } else {
+                    // several ranks: the decision must be identical everywhere, and only summed quantities are
+                    nb2 = need > (double)nb * 1.5 ? (u32)need : (u32)(nb + nb / 2 + 1);
+                }
                 c->ovf_nb = nb; c->ovf_expected = parents * (1.0 + c->rec_per_parent) * 1.02 + 64.0;
-                if (!multi && !p.init_rule && (l.max_fill > (u64)(64 * cap) || nb2 > (1u << 26))) use_part = false; // one address is too hot to pre-sum: use the table
+                if (!multi && nb2 > (1u << 26)) use_part = false;
                 if (multi && nb2 > (1u << 26)) return fail(RIMU_ERR_WORKMEM, "bucket streams cannot be grown further");
                 nb = nb2;
                 continue;
@@ -1308,6 +1329,7 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
             if (attempt > 12) return fail(RIMU_ERR_VECTOR_FULL, "destination vector cannot be grown");
             continue;
         }
+        if (use_part && c->nranks == 1) c->rcnt_clean = 1; // the merge consumed and cleared every counter
         dst->n = (i64)l.out_count;
         dst->nb = use_part ? nb : 0;
         dst->diag_uid = use_part ? h->uid : 0;

@@ -96,7 +96,8 @@ struct rimu_ctx {
     u64 *local_off, *block_tot, *block_base;
     u64 scratch_parents;
     cudaEvent_t ev[8];
-    double *d_red = nullptr; // packed statistics for the single all-reduce (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP doubles)
+    double *d_red = nullptr; // packed statistics for the single all-reduce (RIMU_STATS_NPACK doubles)
+    double *h_red = nullptr; // ... and their pinned host copy
     unsigned long long launches; // kernels launched by this context (bench bookkeeping)
     // staging for host <-> device transfers
     u64 *stage_keys; void *stage_vals; u64 stage_cap;
@@ -131,6 +132,7 @@ struct rimu_ctx {
     char *d_ipc, *h_ipc;     // all-gather scratch for the IPC handles
     alignas(16) char sort_scratch[96];   // SortScratch of sort.cu (opaque here)
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
+    int rcnt_clean;          // one rank: every fill counter of `part` is zero (the last merge cleared what it consumed)
     u32 ovf_nb; double ovf_expected; // the last bucket count that overflowed and the expected item count it overflowed at:
                              //   choose_buckets stays above it until the vector has shrunk (no flip-flop between a count
                              //   that overflows and the retry's larger one)

@@ -46,6 +46,7 @@ struct StatsDev {
     u64 records;        // spawn records this rank's merge read from its bucket streams (all source ranks)
     i64 sent;           // records this rank produced for buckets of other ranks (sent_records)
     u64 grow_flag;      // after the all-reduce: number of ranks whose result did not fit their target vector
+    u64 heavy_packed;   // HeavyDev::packed lives here, so that one memset clears the step's statistics and the heavy-parent queue
 };
 #define RIMU_STATS_NI64 16 /* 'sent' was replaced by 'deposits' */
 #define RIMU_STATS_NF64_STEP 5
@@ -168,19 +169,31 @@ DEV void stat_add(i64 *dst, i64 v) { v = warp_sum(v); if ((threadIdx.x & 31) == 
 // the records merged (block C; summed so that every rank sizes the next bucket count identically) and "my result did not fit
 // my target vector" (out_count > dst_cap), so that all ranks decide to grow-and-repeat together without another collective.
 #define RIMU_STATS_NPACK (RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP + 2)
-static __global__ void pack_stats_kernel(StatsDev *st, double *buf, int dir, u64 dst_cap) {
+static __global__ void pack_stats_kernel(const StatsDev *st, double *buf, int /*dir: pack only*/, u64 dst_cap) {
     const int i = threadIdx.x;
-    i64 *ints = reinterpret_cast<i64 *>(st);
-    double *dbl = reinterpret_cast<double *>(reinterpret_cast<char *>(st) + RIMU_STATS_NI64 * sizeof(i64));
-    if (i < RIMU_STATS_NI64) { if (dir == 0) buf[i] = (double)ints[i]; else ints[i] = (i64)llrint(buf[i]); }
-    if (i < RIMU_STATS_NF64_STEP) { if (dir == 0) buf[RIMU_STATS_NI64 + i] = dbl[i]; else dbl[i] = buf[RIMU_STATS_NI64 + i]; }
+    const i64 *ints = reinterpret_cast<const i64 *>(st);
+    const double *dbl = reinterpret_cast<const double *>(reinterpret_cast<const char *>(st) + RIMU_STATS_NI64 * sizeof(i64));
+    if (i < RIMU_STATS_NI64) buf[i] = (double)ints[i];
+    if (i < RIMU_STATS_NF64_STEP) buf[RIMU_STATS_NI64 + i] = dbl[i];
     if (i == 31) {
         const int at = RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP;
-        if (dir == 0) { buf[at] = (double)st->records; buf[at + 1] = st->out_count > dst_cap ? 1.0 : 0.0; }
-        else { st->records = (u64)llrint(buf[at]); st->grow_flag = (u64)llrint(buf[at + 1]); }
+        buf[at] = (double)st->records;
+        buf[at + 1] = st->out_count > dst_cap ? 1.0 : 0.0;
     }
 }
 
+#endif // __CUDACC__ (the host half of the packing is plain C++)
+// the all-reduced doubles back into the statistics block (host side; mirrors pack_stats_kernel)
+static inline void unpack_stats_host(StatsDev *st, const double *buf) {
+    i64 *ints = reinterpret_cast<i64 *>(st);
+    double *dbl = reinterpret_cast<double *>(reinterpret_cast<char *>(st) + RIMU_STATS_NI64 * sizeof(i64));
+    for (int i = 0; i < RIMU_STATS_NI64; i++) ints[i] = (i64)llrint(buf[i]);
+    for (int i = 0; i < RIMU_STATS_NF64_STEP; i++) dbl[i] = buf[RIMU_STATS_NI64 + i];
+    const int at = RIMU_STATS_NI64 + RIMU_STATS_NF64_STEP;
+    st->records = (u64)llrint(buf[at]);
+    st->grow_flag = (u64)llrint(buf[at + 1]);
+}
+#ifdef __CUDACC__
 // ---------------------------------------------------------------- K1: diagonal step + attempt counts
 template <int HK, int W, class VT>
 __global__ void __launch_bounds__(RIMU_TPB)

@@ -531,6 +531,9 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         u32 nrec = 0;
         bool sub_over = false;
         for (u32 q = 0; q < nsrc; q++) { const u32 cq = s_cnt[cur][q]; nrec += cq; sub_over |= cq > pt.rcap; }
+        // one rank: this CTA is the only reader of the bucket's fill counters (they sit in the ring by now), so it clears
+        // them for the next step -- the host then has no counter array to memset between steps
+        if (!pt.direct && (u32)tid < nsrc) pt.rcnt[(u64)tid * pt.nb + b] = 0u;
         const u32 n = np + nrec;
         max_fill = max(max_fill, n);
         nrec_sum += nrec;

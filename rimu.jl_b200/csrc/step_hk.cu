@@ -63,9 +63,10 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
         CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(part_smem_bytes(W) + smem_init)));
         attr_set[HK][W][std::is_integral<VT>::value] = true;
     }
-    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream));
-    CUDA_TRY(cudaMemsetAsync(c->part.rcnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream)); // fills of every (destination, lane) sub-stream
-    CUDA_TRY(cudaMemsetAsync(c->heavy.packed, 0, sizeof(u64), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream)); // statistics + heavy-parent queue head
+    if (!c->rcnt_clean) // fills of every (destination, lane) sub-stream; on one rank the previous merge has already cleared them
+        CUDA_TRY(cudaMemsetAsync(c->part.rcnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream));
+    c->rcnt_clean = 0; // until this step has merged successfully
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
     if (n > 0) {
