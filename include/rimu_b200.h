@@ -259,6 +259,36 @@ int rimu_annihilate(rimu_vec *dst, const uint64_t *keys, const void *vals, int64
 int rimu_annihilate_device(rimu_vec *dst, const uint64_t *d_keys, const void *d_vals, int64_t n, int method,
                            float *ms_out);
 
+/* ---- dense-indexed deterministic H*v over a complete sector (BASELINE config 3) ----------------------------------------
+ * When a Krylov vector fills a whole particle-number sector, a dictionary is the wrong container: every address is present.
+ * A sector numbers all addresses of the Hamiltonian's address type (BoseFS{N,M}, FermiFS{N,M}, two FermiFS components) by
+ * their combinadic rank; vectors over it are plain arrays of `dim` doubles in HBM (opaque device pointers to the host), and
+ * y = H x is a gather over the off-diagonals of each address -- the same device functions the FCIQMC step uses, no stored
+ * matrix.  Requires a real symmetric H (every model except Transcorrelated1D) and one-word addresses.  This is the device
+ * counterpart of multiplying a basis-ordered coefficient vector in the reference's exact diagonalisation
+ * (ExactDiagonalization/basis_set_representation.jl:35-60; KrylovKit driver ext/KrylovKitExt.jl:23-46) with the matrix-free
+ * mul! of DictVectors/pdvec.jl:810-822 as its operator. */
+typedef struct rimu_sector rimu_sector;
+int rimu_sector_create(rimu_ctx *ctx, const rimu_ham *ham, rimu_sector **out);
+int rimu_sector_destroy(rimu_sector *s);
+int rimu_sector_dim(const rimu_sector *s, uint64_t *dim_out);
+/* rank of n addresses (host keys in, indices out; evaluated by the device code) and the addresses of a range of ranks */
+int rimu_sector_rank(rimu_sector *s, const uint64_t *keys, int64_t n, int64_t *index_out);
+int rimu_sector_keys(rimu_sector *s, int64_t first, int64_t count, uint64_t *keys_out);
+/* dense vectors: device arrays of dim doubles owned by the library */
+int rimu_sector_vec_create(rimu_sector *s, double **d_out);                 /* zero vector */
+int rimu_sector_vec_destroy(rimu_sector *s, double *d);
+int rimu_sector_vec_set(rimu_sector *s, double *d, const int64_t *index, const double *vals, int64_t n); /* zero, then d[index] = vals */
+int rimu_sector_vec_get(rimu_sector *s, const double *d, int64_t first, int64_t count, double *out);
+int rimu_sector_vec_gather(rimu_sector *s, const double *d, const int64_t *index, int64_t n, double *out);
+/* y = H x (mul!, pdvec.jl:810-822, on the complete sector); *ms_out (optional): CUDA-event duration of the kernel */
+int rimu_sector_mul(rimu_sector *s, const double *d_x, double *d_y, float *ms_out);
+int rimu_sector_axpby(rimu_sector *s, double a, const double *d_x, double b, double *d_y);  /* y = a x + b y */
+int rimu_sector_dot(rimu_sector *s, const double *d_x, const double *d_y, double *out);
+/* conversions between the dictionary vector (Float64) and the dense layout */
+int rimu_sector_from_vec(rimu_sector *s, rimu_vec *v, double *d_out);
+int rimu_sector_to_vec(rimu_sector *s, const double *d, rimu_vec *v);
+
 /* ---- the step ------------------------------------------------------------ */
 int rimu_step(rimu_ctx *ctx, const rimu_ham *ham, const rimu_step_params *params,
               rimu_vec *src, rimu_vec *dst, rimu_step_stats *stats_out);

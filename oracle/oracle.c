@@ -978,6 +978,89 @@ long orc_coo_matrix(const orc_ham *h, long dim, const uint64_t *basis, long cap,
     return nnz <= cap ? nnz : -nnz;
 }
 
+/* ------------------------------------------------------------------ dense-indexed rows of y = H x over a complete sector
+ * (SURVEY 8c lesson 3: the independent oracle for config 3 at sizes where no matrix can be built).  The addresses of the
+ * sector -- every bit string with the right number of set bits per component -- are numbered by their combinadic rank
+ * sum_j C(p_j, j) (set bits p_1 < p_2 < ..., j = 1, 2, ...); two components: rank(comp 0) * dim(comp 1) + rank(comp 1).
+ * Everything here is plain loops over a Pascal triangle, independent of the byte tables the device code uses; the
+ * off-diagonals come from the ONR code above. */
+static uint64_t pascal_[65][66];
+static int pascal_ready_ = 0;
+static void pascal_init(void) {
+    if (pascal_ready_) return;
+    for (int n = 0; n <= 64; n++) {
+        pascal_[n][0] = 1;
+        for (int k = 1; k <= 65; k++) pascal_[n][k] = 0;
+        for (int k = 1; k <= n; k++) {
+            uint64_t a = pascal_[n - 1][k - 1], b = k <= n - 1 ? pascal_[n - 1][k] : 0;
+            pascal_[n][k] = (a > ((uint64_t)1 << 62) || b > ((uint64_t)1 << 62)) ? ~(uint64_t)0 : a + b;
+        }
+    }
+    pascal_ready_ = 1;
+}
+static void sector_shape(const orc_ham *h, int *ncomp, int bits[2], int ones[2], int shift[2]) {
+    if (h->addr_kind == ORC_BOSE) { *ncomp = 1; bits[0] = h->N[0] + h->M - 1; ones[0] = h->N[0]; shift[0] = 0; }
+    else if (h->addr_kind == ORC_FERMI) { *ncomp = 1; bits[0] = h->M; ones[0] = h->N[0]; shift[0] = 0; }
+    else { *ncomp = 2; for (int c = 0; c < 2; c++) { bits[c] = h->M; ones[c] = h->N[c]; shift[c] = c * h->M; } }
+}
+long orc_sector_dim(const orc_ham *h) {
+    pascal_init();
+    int nc, bits[2], ones[2], shift[2];
+    sector_shape(h, &nc, bits, ones, shift);
+    uint64_t d = pascal_[bits[0]][ones[0]];
+    if (nc == 2) d *= pascal_[bits[1]][ones[1]];
+    return (long)d;
+}
+long orc_sector_rank(const orc_ham *h, const uint64_t *key) {
+    pascal_init();
+    int nc, bits[2], ones[2], shift[2];
+    sector_shape(h, &nc, bits, ones, shift);
+    uint64_t r = 0;
+    for (int c = 0; c < nc; c++) {
+        uint64_t rc = 0;
+        int j = 0;
+        for (int p = 0; p < bits[c]; p++)
+            if (getbit(key, shift[c] + p)) { j++; rc += pascal_[p][j]; }
+        r = c == 0 ? rc : r * pascal_[bits[1]][ones[1]] + rc;
+    }
+    return (long)r;
+}
+void orc_sector_unrank(const orc_ham *h, long idx, uint64_t *key) {
+    pascal_init();
+    int nc, bits[2], ones[2], shift[2];
+    sector_shape(h, &nc, bits, ones, shift);
+    uint64_t r[2] = {(uint64_t)idx, 0};
+    if (nc == 2) { uint64_t d1 = pascal_[bits[1]][ones[1]]; r[0] = (uint64_t)idx / d1; r[1] = (uint64_t)idx % d1; }
+    key[0] = 0; if (h->words > 1) key[1] = 0;
+    for (int c = 0; c < nc; c++) {
+        uint64_t rem = r[c];
+        int p = bits[c] - 1;
+        for (int j = ones[c]; j >= 1; j--) {
+            while (pascal_[p][j] > rem) p--;
+            rem -= pascal_[p][j];
+            setbit(key, shift[c] + p);
+            p--;
+        }
+    }
+}
+/* y[i] = H_ii x[i] + sum_k H_{c_k, i} x[rank(c_k)] for the n sampled rows idx[] (H real symmetric) */
+void orc_sector_rows(const orc_ham *h, long n, const int64_t *idx, const double *x, double *y_out) {
+    pascal_init();
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long r = 0; r < n; r++) {
+        uint64_t key[2] = {0, 0}, ckey[2];
+        orc_sector_unrank(h, (long)idx[r], key);
+        double acc = orc_diagonal(h, key) * x[idx[r]];
+        long L = orc_num_offdiagonals(h, key);
+        for (long k = 1; k <= L; k++) {
+            ckey[0] = ckey[1] = 0;
+            double m = orc_offdiagonal(h, key, k, ckey);
+            if (m != 0.0) acc += m * x[orc_sector_rank(h, ckey)];
+        }
+        y_out[r] = acc;
+    }
+}
+
 int orc_sizeof_ham(void) { return (int)sizeof(orc_ham); }
 int orc_sizeof_params(void) { return (int)sizeof(orc_step_params); }
 int orc_sizeof_stats(void) { return (int)sizeof(orc_step_stats); }

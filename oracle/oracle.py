@@ -327,6 +327,29 @@ class OracleHam:
             cap = -nnz
         return sp.coo_matrix((vals[:nnz], (rows[:nnz], cols[:nnz])), shape=(dim, dim)).tocsr()
 
+    # -- dense-indexed sector (config 3): combinadic rank / unrank and sampled rows of y = H x
+    def sector_dim(self):
+        lib().orc_sector_dim.restype = C.c_long
+        return int(lib().orc_sector_dim(C.byref(self.h)))
+
+    def sector_rank(self, key):
+        lib().orc_sector_rank.restype = C.c_long
+        k = self._key(key)
+        return int(lib().orc_sector_rank(C.byref(self.h), _p(k, C.c_uint64)))
+
+    def sector_unrank(self, idx):
+        k = np.zeros(self.W, dtype=np.uint64)
+        lib().orc_sector_unrank(C.byref(self.h), C.c_long(int(idx)), _p(k, C.c_uint64))
+        return k
+
+    def sector_rows(self, idx, x):
+        """y[idx] of y = H x for a dense sector vector x (host array of sector_dim doubles)"""
+        idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int64))
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+        out = np.zeros(len(idx), dtype=np.float64)
+        lib().orc_sector_rows(C.byref(self.h), C.c_long(len(idx)), _p(idx, C.c_int64), _p(x, C.c_double), _p(out, C.c_double))
+        return out
+
     def exact_eigenvalues(self, start_key=None, max_dim=200_000, hermitian=True):
         """All eigenvalues of H in the BFS-connected sector of the start address (dense)."""
         basis = self.bfs_basis(start_key, max_dim)

@@ -27,5 +27,6 @@ from .fciqmc import (AllOverlaps, DataFrame, DontUpdate, DoubleLogUpdate, Double
                      SingleState, Timer, default_starting_vector, init, solve, solve_, step_)
 from .statstools import blocking_analysis, projected_energy, ratio_of_means, shift_estimator
 from .lanczos import eigsolve_lanczos
+from .sectors import DenseSectorVec, SectorBasis
 from .rimuio import load_state, save_state
 from .distributed import init_distributed

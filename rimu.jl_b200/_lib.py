@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("RIMU_B200_LIB") or os.path.join(_HERE, "librimu_b200.so")  # override: kernel-tuning builds
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "sort.cu", "step_hk.cu"]   # step_hk.cu is compiled once per HamKind (-DRIMU_HK=n), in parallel
-HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh", "internal.cuh"]
+SOURCES = ["api.cu", "sort.cu", "sector.cu", "step_hk.cu"]   # step_hk.cu is compiled once per HamKind (-DRIMU_HK=n), in parallel
+HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh", "internal.cuh", "sector.cuh"]
 NUM_HAM_KINDS = 7
 OBJ_DIR = os.environ.get("RIMU_B200_OBJ_DIR") or os.path.join("/tmp", "rimu_b200_build_" + str(os.getuid()))  # objects stay out of the tree
 
@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     os.makedirs(OBJ_DIR, exist_ok=True)
     base = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else [])
     jobs = []
-    for s in ("api.cu", "sort.cu"):
+    for s in ("api.cu", "sort.cu", "sector.cu"):
         jobs.append((base + ["-c", os.path.join(CSRC, s), "-o", os.path.join(OBJ_DIR, s[:-3] + tag + ".o")]))
     for hk in (range(NUM_HAM_KINDS) if kinds is None else kinds):
         jobs.append((base + [f"-DRIMU_HK={hk}", "-c", os.path.join(CSRC, "step_hk.cu"), "-o", os.path.join(OBJ_DIR, f"step_hk{hk}{tag}.o")]))
@@ -160,6 +160,21 @@ SYMBOLS = {
     "rimu_comm_reserve": (C.c_int, [_vp, C.c_uint64]),
     "rimu_comm_p2p": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rimu_comm_detach": (C.c_int, [_vp]),
+    "rimu_sector_create": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "rimu_sector_destroy": (C.c_int, [_vp]),
+    "rimu_sector_dim": (C.c_int, [_vp, _u64p]),
+    "rimu_sector_rank": (C.c_int, [_vp, _u64p, C.c_int64, _i64p]),
+    "rimu_sector_keys": (C.c_int, [_vp, C.c_int64, C.c_int64, _u64p]),
+    "rimu_sector_vec_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "rimu_sector_vec_destroy": (C.c_int, [_vp, _vp]),
+    "rimu_sector_vec_set": (C.c_int, [_vp, _vp, _i64p, _f64p, C.c_int64]),
+    "rimu_sector_vec_get": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _f64p]),
+    "rimu_sector_vec_gather": (C.c_int, [_vp, _vp, _i64p, C.c_int64, _f64p]),
+    "rimu_sector_mul": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_float)]),
+    "rimu_sector_axpby": (C.c_int, [_vp, C.c_double, _vp, C.c_double, _vp]),
+    "rimu_sector_dot": (C.c_int, [_vp, _vp, _vp, _f64p]),
+    "rimu_sector_from_vec": (C.c_int, [_vp, _vp, _vp]),
+    "rimu_sector_to_vec": (C.c_int, [_vp, _vp, _vp]),
     "rimu_comm_allreduce_f64": (C.c_int, [_vp, _f64p, C.c_int]),
     "rimu_addr_owner": (C.c_int, [_u64p, C.c_int, C.c_int]),
     "rimu_addr_hash": (C.c_uint64, [_u64p, C.c_int]),

@@ -5,6 +5,7 @@
 #pragma once
 #include "../../include/rimu_b200.h"
 #include "partition.cuh"
+#include "sector.cuh"
 #include "ham_host.h"
 
 #include <dlfcn.h>
@@ -212,6 +213,8 @@ struct HkOps {
     // element-wise hooks on device buffers: diagonal_element / num_offdiagonals, get_offdiagonal(first0 .. first0+count)
     int (*diag)(rimu_ctx *c, const rimu_ham *h, const u64 *d_keys, i64 n, double *d_out, i64 *d_nod);
     int (*offdiag)(rimu_ctx *c, const rimu_ham *h, const u64 *d_key, i64 first0, i64 count, u64 *d_keys_out, double *d_vals);
+    // y = H x over a complete sector in dense (combinadic-rank) indexing: sector.cuh
+    int (*sector_mul)(rimu_ctx *c, const rimu_ham *h, const SectorDev *s, const u64 *d_keys, const double *d_x, double *d_y, u64 dim);
 };
 RIMU_INTERNAL const HkOps *rimu_hk_ops_0();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_1();

@@ -145,5 +145,11 @@ static int HKNAME(offdiag_entry)(rimu_ctx *c, const rimu_ham *h, const u64 *d_ke
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-static const HkOps HKNAME(OPS) = {HKNAME(step_entry), HKNAME(diag_entry), HKNAME(offdiag_entry)};
+static int HKNAME(sector_mul_entry)(rimu_ctx *c, const rimu_ham *h, const SectorDev *s, const u64 *d_keys, const double *d_x, double *d_y, u64 dim) {
+    if (h->W != 1) return fail(RIMU_ERR_INVALID, "dense sectors need one-word addresses");
+    sector_mul_kernel<HKC><<<(unsigned)((dim + 255) / 256), 256, 0, c->stream>>>(h->dev, *s, d_keys, d_x, d_y, dim);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static const HkOps HKNAME(OPS) = {HKNAME(step_entry), HKNAME(diag_entry), HKNAME(offdiag_entry), HKNAME(sector_mul_entry)};
 const HkOps *RIMU_CAT(rimu_hk_ops_, RIMU_HK)() { return &HKNAME(OPS); }

@@ -302,7 +302,9 @@ def apply_operator(wm: WorkingMemory, target: GPUDVec, source: GPUDVec, op, boos
 
 
 def mul(y: GPUDVec, op, x: GPUDVec, wm: WorkingMemory | None = None):
-    """mul!(y, op, x, w) (pdvec.jl:810-822): deterministic y = op * x."""
+    """mul!(y, op, x, w) (pdvec.jl:810-822): deterministic y = op * x.  Dense sector vectors (sectors.py) take the gather path."""
+    if hasattr(y, "mul_from"):
+        return y.mul_from(op, x)
     wm = wm or WorkingMemory(GPUDVec(style=IsDeterministic(), address_type=x.address_type, ctx=x.ctx))
     if not isinstance(wm.style, IsDeterministic):
         raise ValueError("Attempted to use `mul!` with non-deterministic working memory. "

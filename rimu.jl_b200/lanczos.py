@@ -21,8 +21,11 @@ def eigsolve_lanczos(ham, start: GPUDVec, howmany=1, krylovdim=60, tol=1e-10, ma
     if howmany > krylovdim:
         raise ValueError("howmany cannot exceed krylovdim")
     det = IsDeterministic()
-    v = GPUDVec(style=det, address_type=start.address_type, ctx=start.ctx).copy_from(start)
-    wm = WorkingMemory(v)
+    if hasattr(start, "mul_from"):  # dense sector vector (sectors.py): no working memory, same vector operations
+        v, wm = start.copy(), None
+    else:
+        v = GPUDVec(style=det, address_type=start.address_type, ctx=start.ctx).copy_from(start)
+        wm = WorkingMemory(v)
     info = {"matvecs": 0, "converged": False, "residual": np.inf}
     if howmany > 1:
         full_reorth, maxiter = True, 1
