@@ -142,8 +142,32 @@ def run_stochastic(R, cfg, args, world, rank, dist, torch, peak):
 
 
 def run_deterministic(R, cfg, args, world, rank, dist, torch, peak):
-    """config 3: grow x <- H x / |H x| from the starting determinant until the sector is filled (or --max-dim),
-    then time K matrix-free H*v applications (one `mul!` = one Lanczos matvec)."""
+    """config 3: K matrix-free H*v applications (one `mul!` = one Lanczos matvec) over the complete sector in the
+    dense-indexed layout (csrc/sector.cuh: gather, no records).  `--dictionary-hv` times the dictionary path instead
+    (grow x <- H x / |H x| from the starting determinant until the sector is filled or --max-dim)."""
+    if not args.dictionary_hv and world == 1:
+        H = cfg["ham"]()
+        basis = R.SectorBasis(H)
+        x = basis.vector([(cfg["addr"], 1.0)])
+        y = basis.zeros()
+        for _ in range(8):  # fill the sector
+            R.mul(y, H, x)
+            y.scale_(1.0 / y.norm(2))
+            x, y = y, x
+        times = []
+        for _ in range(args.steps):
+            R.mul(y, H, x)
+            times.append(y.last_mul_ms)
+            x, y = y, x
+        ms = float(np.median(times))
+        L = 64  # off-diagonals per address (incl. Pauli-blocked ones): HubbardRealSpace.jl:316-321
+        # algorithmic HBM bytes of the gather: keys + x read once, y written once (neighbour reads hit L2: consecutive
+        # ranks of the last component share their neighbours' cache lines)
+        bytes_ = basis.dim * (8 + 8 + 8)
+        return {"config": cfg["name"] + " (dense-indexed sector)", "n_gpus": 1, "dimension": basis.dim, "ms_per_matvec": ms,
+                "attempts_per_matvec": basis.dim * L, "spawn_attempts_per_s": basis.dim * L / (ms * 1e-3),
+                "algorithmic_bytes_per_matvec": bytes_, "hbm_gbs": bytes_ / (ms * 1e-3) / 1e9,
+                "hbm_frac_of_measured_peak": bytes_ / (ms * 1e-3) / 1e9 / peak, "steps": args.steps, "words": 1}
     W = cfg["words"]
     ctx = R.init_distributed(W, records_per_peer=1 << 22, table_slots=1 << 22)
     H = cfg["ham"]()
@@ -191,6 +215,7 @@ def main():
     ap.add_argument("--growth-seconds", type=float, default=300)
     ap.add_argument("--max-dim", type=float, default=2e8)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--dictionary-hv", action="store_true", help="config 3 through the dictionary path (records + annihilation)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist

@@ -197,6 +197,66 @@ class Timer:
         return {"time": time.time()}
 
 
+# --------------------------------------------------------------------------- spectral strategies
+@dataclass
+class GramSchmidt:
+    """GramSchmidt(S; orthogonalization_interval=1) (strategies_and_params/spectralstrategy.jl:22-35): S spectral states per
+    replica, state i orthogonalised against the states j < i every `orthogonalization_interval` steps (fciqmc.jl:187-202) --
+    on the device `u <- u - (u.v / |v|^2) v` is one dot, one norm and one axpby per pair."""
+    num_spectral_states: int = 1
+    orthogonalization_interval: int = 1
+
+    def orthogonalize(self, states):
+        for i in range(len(states)):
+            for j in range(i):
+                u, v = states[i].v, states[j].v
+                vv = v.dot(v)
+                if vv != 0.0:
+                    u.add_(v, -u.dot(v) / vv)
+
+
+def build_basis(ham, start_address, minimum_size):
+    """build_basis(ham, address; minimum_size) (ExactDiagonalization/basis_breadth_first_search.jl:216-399): breadth-first
+    search from the starting address, level by level, until at least `minimum_size` addresses are known."""
+    from .hamiltonians import offdiagonals
+    basis, seen, frontier = [start_address], {start_address.key()}, [start_address]
+    while frontier and len(basis) < minimum_size:
+        nxt = []
+        for a in frontier:
+            for b, val in offdiagonals(ham, a):
+                if val != 0.0 and b.key() not in seen:
+                    seen.add(b.key())
+                    basis.append(b)
+                    nxt.append(b)
+        frontier = nxt
+    return basis
+
+
+def spectral_starting_vectors(ham, start_address, n_spectral, style, initiator, minimum_size=None):
+    """pmc_simulation.jl:48-63: the lowest `n_spectral` eigenvectors (times 10) of H truncated to a small breadth-first basis
+    around the starting address are the starting vectors of the spectral states."""
+    from .hamiltonians import diagonal_element, offdiagonals
+    basis = build_basis(ham, start_address, minimum_size or 2 * n_spectral)
+    index = {a.key(): i for i, a in enumerate(basis)}
+    mat = np.zeros((len(basis), len(basis)))
+    for i, a in enumerate(basis):
+        mat[i, i] = diagonal_element(ham, a)
+        for b, val in offdiagonals(ham, a):
+            j = index.get(b.key())
+            if j is not None and j != i:
+                mat[j, i] += val
+    w, vecs = np.linalg.eig(mat)
+    order = np.argsort(w.real)
+    out = []
+    for s in range(n_spectral):
+        col = np.real(vecs[:, order[s]])
+        pairs = [(a, 10.0 * c) for a, c in zip(basis, col) if c != 0.0]
+        if style.val_type == _lib.VAL_I64:
+            pairs = [(a, int(round(c))) for a, c in pairs if int(round(c)) != 0]
+        out.append(GPUDVec(pairs, style=style, initiator=initiator))
+    return out
+
+
 # --------------------------------------------------------------------------- problem / simulation
 def default_starting_vector(ham_or_address, population=10, style=None, initiator=None):
     """qmc_states.jl:236-260: `address => population` with the given style (and initiator rule)."""
@@ -222,11 +282,13 @@ class ProjectorMonteCarloProblem:
     def __init__(self, hamiltonian, *, start_at=None, shift=None, style=None, time_step=0.01, starting_step=0,
                  last_step=100, wall_time=math.inf, target_walkers=1000, zeta=0.08, xi=None, shift_strategy=None,
                  post_step_strategy=(), max_length=None, random_seed=True, reporting_interval=1, metadata=None,
-                 n_replicas=1, initiator=False, replica_strategy=None):
+                 n_replicas=1, initiator=False, replica_strategy=None, spectral_strategy=None, minimum_size=None):
         if int(n_replicas) < 1:
             raise ValueError("n_replicas must be at least 1")
         self.n_replicas = int(n_replicas)  # independent copies of the walker vector, advanced side by side (qmc_states.jl:89-140)
         self.replica_strategy = replica_strategy  # e.g. AllOverlaps: it also fixes the number of replicas (pmc problem :205-215)
+        self.spectral_strategy = spectral_strategy or GramSchmidt(1)  # projector_monte_carlo_problem.jl:176
+        self.minimum_size = minimum_size or 2 * self.spectral_strategy.num_spectral_states  # :177
         if replica_strategy is not None:
             if n_replicas not in (1, replica_strategy.n_replicas):
                 raise ValueError("n_replicas conflicts with the replica strategy")
@@ -275,13 +337,36 @@ class PMCSimulation:
         else:
             shift = float(p.shift)
         # replicas: independent vectors with their own shift parameters and random streams; report columns get the suffix
-        # _1, _2, ... when there is more than one (qmc_states.jl:107-140, pmc_simulation.jl:125-146)
-        self.states = []
+        # _1, _2, ... when there is more than one (qmc_states.jl:107-140, pmc_simulation.jl:125-146).  Every replica holds
+        # n_spectral spectral states (suffix _s1, _s2, ...; pmc_simulation.jl:133-146), orthogonalised by the spectral
+        # strategy before they are advanced (fciqmc.jl:187-202).
+        n_spec = p.spectral_strategy.num_spectral_states
+        if n_spec > 1:
+            if isinstance(sa, (list, tuple)) and len(sa) == n_spec and all(isinstance(x, GPUDVec) for x in sa):
+                spec_vectors = [x.copy() for x in sa]  # one starting vector per spectral state
+            else:
+                start = starting_address(ham) if sa is None or isinstance(sa, (GPUDVec, list, tuple, dict)) else sa
+                spec_vectors = spectral_starting_vectors(ham, start, n_spec, style, p.initiator, p.minimum_size)
+        else:
+            spec_vectors = [v]
+        self.states, self.replicas = [], []
+        self.suffixes = []
         for r in range(p.n_replicas):
-            vr = v if r == 0 else v.copy()
-            seed = p.random_seed if r == 0 else (p.random_seed + 0x9E3779B97F4A7C15 * r) & 0xFFFFFFFFFFFFFFFF
-            self.states.append(SingleState(ham, vr, vr.zerovector(), WorkingMemory(vr, seed=seed),
-                                           ShiftParameters(shift, vr.walkernumber(), p.time_step)))
+            rep = []
+            for s_, sv in enumerate(spec_vectors):
+                vr = sv if r == 0 else sv.copy()
+                k = r * n_spec + s_
+                seed = p.random_seed if k == 0 else (p.random_seed + 0x9E3779B97F4A7C15 * k) & 0xFFFFFFFFFFFFFFFF
+                if p.shift is None and n_spec > 1:  # every spectral state starts from its own Rayleigh quotient
+                    vd = GPUDVec(style=IsDeterministic(), address_type=vr.address_type, ctx=vr.ctx).copy_from(vr)
+                    sh = dot(vd, ham, vd) / vd.dot(vd)
+                else:
+                    sh = shift
+                st = SingleState(ham, vr, vr.zerovector(), WorkingMemory(vr, seed=seed), ShiftParameters(sh, vr.walkernumber(), p.time_step))
+                rep.append(st)
+                self.states.append(st)
+                self.suffixes.append((f"_{r + 1}" if p.n_replicas > 1 else "") + (f"_s{s_ + 1}" if n_spec > 1 else ""))
+            self.replicas.append(rep)
         self.state = self.states[0]
         self.step = p.starting_step
         self.report = {}
@@ -303,8 +388,12 @@ class PMCSimulation:
         report_now = self.step % p.reporting_interval == 0
         row = {"step": self.step}
         dead = too_long = stop = False
+        gs = p.spectral_strategy
+        if gs.num_spectral_states > 1 and self.step % gs.orthogonalization_interval == 0:
+            for rep in self.replicas:  # Gram-Schmidt inside every replica (fciqmc.jl:189-197)
+                gs.orthogonalize(rep)
         for r, st in enumerate(self.states):
-            sfx = f"_{r + 1}" if len(self.states) > 1 else ""
+            sfx = self.suffixes[r]
             sp = st.shift_parameters
             T = FirstOrderTransitionOperator(st.hamiltonian, sp.shift, sp.time_step)
             names, values, wm, pv = apply_operator(st.wm, st.pv, st.v, T)
@@ -325,7 +414,7 @@ class PMCSimulation:
             stop |= not proceed
         if report_now:
             if p.replica_strategy is not None and not dead:
-                row.update(p.replica_strategy(self.states))
+                row.update(p.replica_strategy([rep[0] for rep in self.replicas]))  # (first spectral state of every replica)
             for k, val in row.items():
                 self.report.setdefault(k, []).append(val)
         if dead:
