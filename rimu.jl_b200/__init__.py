@@ -21,7 +21,7 @@ from .stochasticstyles import (IsDeterministic, IsDynamicSemistochastic, IsStoch
                                CoherentInitiator, Initiator, InitiatorRule, NonInitiator, SimpleInitiator)
 from .dictvectors import (DVec, FirstOrderTransitionOperator, FrozenDVec, GPUDVec, InitiatorDVec, PDVec, WorkingMemory, apply_operator, dot, mul,
                           walkernumber_and_length, working_memory)
-from .fciqmc import (AllOverlaps, DataFrame, DontUpdate, DoubleLogUpdate, DoubleLogUpdateAfterTargetWalkers, GramSchmidt, LogUpdate,
+from .fciqmc import (AllOverlaps, DataFrame, DontUpdate, DoubleLogUpdate, DoubleLogUpdateAfterTargetWalkers, GramSchmidt, LogUpdate, ReportDFAndInfo, ReportToFile, load_df,
                      LogUpdateAfterTargetWalkers,
                      PMCSimulation, ProjectedEnergy, Projector, ProjectorMonteCarloProblem, ShiftParameters,
                      SingleState, Timer, default_starting_vector, init, solve, solve_, step_)

@@ -197,6 +197,81 @@ class Timer:
         return {"time": time.time()}
 
 
+# --------------------------------------------------------------------------- reporting strategies
+@dataclass
+class ReportDFAndInfo:
+    """reportingstrategy.jl:264-300: the report lives in memory and becomes a DataFrame."""
+    reporting_interval: int = 1
+
+
+class ReportToFile:
+    """ReportToFile(; filename, reporting_interval, chunk_size, save_if, return_df, compress) (reportingstrategy.jl:302-434):
+    the report is written to an Arrow file in chunks of `chunk_size` reported steps and dropped from memory after every
+    chunk; an existing file is never overwritten (`out.arrow` -> `out-1.arrow` -> ...); only the root rank saves."""
+
+    def __init__(self, filename="out.arrow", reporting_interval=1, chunk_size=1000, save_if=None, return_df=False, compress="zstd"):
+        if compress not in (None, "zstd", "lz4"):
+            raise ValueError("compress must be None, 'zstd' or 'lz4'")  # ArgumentError (reportingstrategy.jl:346-350)
+        self.filename, self.reporting_interval, self.chunk_size = str(filename), int(reporting_interval), int(chunk_size)
+        self.save_if = (int(os.environ.get("RANK", "0")) == 0) if save_if is None else bool(save_if)  # is_mpi_root()
+        self.return_df, self.compress = bool(return_df), compress
+        self._writer = self._sink = self._schema = None
+        self.chunks_written = 0
+
+    def refine(self):
+        """refine_reporting_strategy (reportingstrategy.jl:362-381): pick a file name that does not exist yet"""
+        if self.save_if:
+            import re
+            name = self.filename
+            while os.path.isfile(name):
+                base, ext = os.path.splitext(name)
+                m = re.match(r"(.*)-([0-9]+)$", base)
+                name = f"{base}-1{ext}" if m is None else f"{m.group(1)}-{int(m.group(2)) + 1}{ext}"
+            self.filename = name
+        return self
+
+    def _write(self, report, metadata):
+        import pyarrow as pa
+        if not report or not len(next(iter(report.values()))):
+            return
+        table = pa.Table.from_pydict({k: np.asarray(v) for k, v in report.items()})
+        if self._writer is None:
+            md = {str(k).encode(): str(v).encode() for k, v in (metadata or {}).items()}
+            self._schema = table.schema.with_metadata(md)
+            self._sink = pa.OSFile(self.filename, "wb")
+            self._writer = pa.ipc.new_file(self._sink, self._schema, options=pa.ipc.IpcWriteOptions(compression=self.compress))
+        self._writer.write_table(table.cast(self._schema.remove_metadata()).replace_schema_metadata(self._schema.metadata))
+        self.chunks_written += 1
+
+    def after_step(self, step, report, metadata):
+        """report_after_step! (:386-401): flush a full chunk and empty the in-memory report"""
+        if self.save_if and step % (self.chunk_size * self.reporting_interval) == 0:
+            self._write(report, metadata)
+            for v in report.values():
+                v.clear()
+
+    def finalize(self, report, metadata):
+        """finalize_report! (:402-427)"""
+        if self.save_if:
+            self._write(report, metadata)
+            if self._writer is not None:
+                self._writer.close()
+                self._sink.close()
+                self._writer = self._sink = None
+            for v in report.values():
+                v.clear()
+
+
+def load_df(filename):
+    """RimuIO.load_df (RimuIO.jl:27-44): the report file as a DataFrame; the metadata come back in `df.attrs`."""
+    import pyarrow as pa
+    with pa.OSFile(str(filename), "rb") as src:
+        table = pa.ipc.open_file(src).read_all()
+    df = table.to_pandas()
+    df.attrs.update({k.decode(): v.decode() for k, v in (table.schema.metadata or {}).items()})
+    return df
+
+
 # --------------------------------------------------------------------------- spectral strategies
 @dataclass
 class GramSchmidt:
@@ -282,7 +357,8 @@ class ProjectorMonteCarloProblem:
     def __init__(self, hamiltonian, *, start_at=None, shift=None, style=None, time_step=0.01, starting_step=0,
                  last_step=100, wall_time=math.inf, target_walkers=1000, zeta=0.08, xi=None, shift_strategy=None,
                  post_step_strategy=(), max_length=None, random_seed=True, reporting_interval=1, metadata=None,
-                 n_replicas=1, initiator=False, replica_strategy=None, spectral_strategy=None, minimum_size=None):
+                 n_replicas=1, initiator=False, replica_strategy=None, spectral_strategy=None, minimum_size=None,
+                 reporting_strategy=None):
         if int(n_replicas) < 1:
             raise ValueError("n_replicas must be at least 1")
         self.n_replicas = int(n_replicas)  # independent copies of the walker vector, advanced side by side (qmc_states.jl:89-140)
@@ -310,7 +386,9 @@ class ProjectorMonteCarloProblem:
         elif random_seed is False or random_seed is None:
             random_seed = 0
         self.random_seed = int(random_seed) & 0xFFFFFFFFFFFFFFFF
-        self.reporting_interval = reporting_interval
+        # reporting_strategy (ReportDFAndInfo / ReportToFile) carries its own interval (projector_monte_carlo_problem.jl:170-172)
+        self.reporting_strategy = reporting_strategy or ReportDFAndInfo(reporting_interval)
+        self.reporting_interval = self.reporting_strategy.reporting_interval
         self.metadata = dict(metadata or {})
 
 
@@ -323,6 +401,8 @@ class PMCSimulation:
         sa = p.start_at
         if sa is None:
             v = default_starting_vector(ham, style=p.style, initiator=p.initiator)
+        elif isinstance(sa, (list, tuple)) and sa and all(isinstance(x, GPUDVec) for x in sa):
+            v = sa[0].copy()  # one starting vector per spectral state (the matrix form of start_at, pmc_simulation.jl:36-47)
         elif isinstance(sa, GPUDVec):
             v = sa.copy()  # a vector brings its own style and initiator rule
         elif isinstance(sa, (list, tuple, dict)):
@@ -368,6 +448,8 @@ class PMCSimulation:
                 self.suffixes.append((f"_{r + 1}" if p.n_replicas > 1 else "") + (f"_s{s_ + 1}" if n_spec > 1 else ""))
             self.replicas.append(rep)
         self.state = self.states[0]
+        if isinstance(p.reporting_strategy, ReportToFile):
+            p.reporting_strategy.refine()
         self.step = p.starting_step
         self.report = {}
         self.aborted = False
@@ -417,6 +499,8 @@ class PMCSimulation:
                 row.update(p.replica_strategy([rep[0] for rep in self.replicas]))  # (first spectral state of every replica)
             for k, val in row.items():
                 self.report.setdefault(k, []).append(val)
+            if isinstance(p.reporting_strategy, ReportToFile):
+                p.reporting_strategy.after_step(self.step, self.report, self._report_metadata())
         if dead:
             self.aborted, self.message = True, f"Aborted in step {self.step}."  # dead population
         elif too_long:
@@ -442,10 +526,23 @@ class PMCSimulation:
                 break
             self.step_()
         self.elapsed_time += time.time() - t0
+        if (self.aborted or self.success) and isinstance(self.problem.reporting_strategy, ReportToFile):
+            self.problem.reporting_strategy.finalize(self.report, self._report_metadata())
         return self
+
+    def _report_metadata(self):
+        """report_simulation_status_metadata! (pmc_simulation.jl:186-200) + the problem's own metadata"""
+        md = dict(self.problem.metadata)
+        md.update({"modified": self.modified, "aborted": self.aborted, "success": self.success, "message": self.message,
+                   "elapsed_time": self.elapsed_time, "num_replicas": self.problem.n_replicas,
+                   "num_spectral_states": self.problem.spectral_strategy.num_spectral_states})
+        return md
 
     def dataframe(self):
         import pandas as pd
+        rs = self.problem.reporting_strategy
+        if isinstance(rs, ReportToFile) and rs.save_if and rs.chunks_written:
+            return load_df(rs.filename)  # (the in-memory report was emptied after every chunk)
         return pd.DataFrame(self.report)
 
     DataFrame = dataframe

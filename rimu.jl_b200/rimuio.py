@@ -84,8 +84,8 @@ def _key_arrays(keys, at: AddressType):
     return out
 
 
-def write_state_file(filename, keys, values, address_type: AddressType, metadata=None):
-    """Arrow.write(filename, (key=..., value=...); compress=:zstd, metadata) for device-layout keys."""
+def _state_batch(keys, values, address_type: AddressType, metadata=None):
+    """(schema, record batch) of a (key, value) table in the reference's layout"""
     import pyarrow as pa
     values = np.ascontiguousarray(values)
     if values.dtype not in (np.float64, np.int64):
@@ -107,10 +107,53 @@ def write_state_file(filename, keys, values, address_type: AddressType, metadata
     md = {"RIMU_PACKAGE_VERSION": RIMU_PACKAGE_VERSION}
     md.update({str(k): _julia_string(v) for k, v in (metadata or {}).items()})
     schema = pa.schema([key_field, val_field], metadata={k.encode(): v.encode() for k, v in md.items()})
-    batch = pa.record_batch([key_arr, pa.array(values)], schema=schema)
+    return schema, pa.record_batch([key_arr, pa.array(values)], schema=schema)
+
+
+def write_state_file(filename, keys, values, address_type: AddressType, metadata=None):
+    """Arrow.write(filename, (key=..., value=...); compress=:zstd, metadata) for device-layout keys."""
+    import pyarrow as pa
+    schema, batch = _state_batch(keys, values, address_type, metadata)
     with pa.OSFile(str(filename), "wb") as sink:
         with pa.ipc.new_file(sink, schema, options=pa.ipc.IpcWriteOptions(compression="zstd")) as writer:
             writer.write_batch(batch)
+
+
+_EOS = b"\xff\xff\xff\xff\x00\x00\x00\x00"  # end-of-stream marker of the Arrow IPC streaming format
+
+
+def _stream_image(schema, batch):
+    """bytes of an Arrow IPC *stream* holding one record batch -> (schema message, record-batch message(s))"""
+    import pyarrow as pa
+    sink = pa.BufferOutputStream()
+    with pa.ipc.new_stream(sink, schema, options=pa.ipc.IpcWriteOptions(compression="zstd")) as writer:
+        writer.write_batch(batch)
+    raw = sink.getvalue().to_pybytes()
+    assert raw[:4] == b"\xff\xff\xff\xff" and raw.endswith(_EOS)
+    schema_end = 8 + int.from_bytes(raw[4:8], "little")  # a schema message has no body
+    return raw[:schema_end], raw[schema_end:-len(_EOS)]
+
+
+def write_state_stream(filename, keys, values, address_type: AddressType, metadata=None):
+    """rank 0 of a multi-rank save: `Arrow.write(...; file=false)` (RimuIO.jl:113-117) -- the IPC STREAM format, which
+    later ranks can extend"""
+    schema, batch = _state_batch(keys, values, address_type, metadata)
+    head, body = _stream_image(schema, batch)
+    with open(str(filename), "wb") as f:
+        f.write(head + body + _EOS)
+
+
+def append_state_stream(filename, keys, values, address_type: AddressType):
+    """`Arrow.append(filename, table)` (RimuIO.jl:122-126): one more record batch at the end of an IPC stream file"""
+    schema, batch = _state_batch(keys, values, address_type, None)
+    _, body = _stream_image(schema, batch)
+    with open(str(filename), "r+b") as f:
+        f.seek(-len(_EOS), 2)
+        if f.read(len(_EOS)) != _EOS:
+            raise ValueError(f"`{filename}` is not an Arrow IPC stream")
+        f.seek(-len(_EOS), 2)
+        f.truncate()
+        f.write(body + _EOS)
 
 
 def _julia_string(v):
@@ -151,7 +194,11 @@ def read_state_file(filename):
     """-> (keys (n, W) uint64 in the device layout, values, AddressType, metadata dict)"""
     import pyarrow as pa
     with pa.OSFile(str(filename), "rb") as src:
-        tbl = pa.ipc.open_file(src).read_all()
+        try:
+            tbl = pa.ipc.open_file(src).read_all()
+        except pa.ArrowInvalid:  # the streaming format a multi-rank save writes (Arrow.Table reads both)
+            src.seek(0)
+            tbl = pa.ipc.open_stream(src).read_all()
     if tbl.schema.names != ["key", "value"]:
         raise ValueError(f"`{filename}` is not a valid Rimu state file")  # ArgumentError (RimuIO.jl:150-152)
     kf = tbl.schema.field("key")
@@ -202,10 +249,20 @@ def read_state_file(filename):
 def save_state(filename, vector, **kwargs):
     """save_state(filename, vector; kwargs...) (RimuIO.jl:92-105).  One process; with several ranks every rank holds only its
     share of the vector (the reference appends the ranks' record batches to one file, RimuIO.jl:107-135)."""
-    if vector.ctx.nranks > 1:
-        raise NotImplementedError("save_state over several ranks: gather the local parts on one rank first")
     keys, vals = vector.download()
-    write_state_file(filename, keys, vals, vector.address_type, kwargs)
+    ctx = vector.ctx
+    if ctx.nranks == 1:
+        write_state_file(filename, keys, vals, vector.address_type, kwargs)
+        return
+    # _save_state_mpi (RimuIO.jl:107-135): rank 0 creates the file (streaming format + metadata), then the other ranks append
+    # their record batch one after the other, in rank order.  The barrier is the library's own all-reduce.
+    if ctx.rank == 0:
+        write_state_stream(filename, keys, vals, vector.address_type, kwargs)
+    for r in range(1, ctx.nranks):
+        ctx.allreduce([0.0])
+        if ctx.rank == r:
+            append_state_stream(filename, keys, vals, vector.address_type)
+    ctx.allreduce([0.0])
 
 
 def load_state(filename, style=None, ctx=None, **vector_kwargs):

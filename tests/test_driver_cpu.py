@@ -287,3 +287,67 @@ def test_all_overlaps_on_the_cpu(built, cpu_device):
     prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, last_step=3, random_seed=1, replica_strategy=only)
     cols = set(R.solve(prob).dataframe().columns)
     assert {"c1_Op1_c2", "c1_Op2_c2"} <= cols and "c1_dot_c2" not in cols
+
+
+def test_gram_schmidt_spectral_states_on_the_cpu(built, cpu_device):
+    """spectral_strategy=GramSchmidt(2) (fciqmc.jl:187-202, spectralstrategy.jl:22-35): the second spectral state is
+    orthogonalised against the first before every step, so a deterministic run drives its shift to the lowest eigenvalue of the
+    complement that its starting vector overlaps; report columns carry the _s1/_s2 suffixes (pmc_simulation.jl:133-146)."""
+    import rimu_b200 as R
+    oh, ph = cpu_device("real1d_6")
+    basis = oh.bfs_basis()
+    H = oh.sparse_matrix(basis).toarray()
+    w, vecs = np.linalg.eigh(H)
+    index = {int(k[0]): i for i, k in enumerate(basis)}
+    a0 = ph.address
+    k1, _ = oh.get_offdiagonal(oh.start_key, 1)
+    a1 = ph.address_type.from_key(np.atleast_1d(k1))
+    det = R.IsDeterministic()
+    starts = [FakeDVec([(a0, 10.0)], style=det), FakeDVec([(a0, 3.0), (a1, 10.0)], style=det)]
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=starts, style=det, time_step=0.01, last_step=4000, target_walkers=100,
+                                        spectral_strategy=R.GramSchmidt(2), random_seed=1, max_length=10 ** 6)
+    sim = R.solve(prob)
+    assert sim.success, sim.message
+    df = sim.dataframe()
+    for col in ("shift_s1", "shift_s2", "norm_s1", "norm_s2", "len_s1", "len_s2"):
+        assert col in df.columns, df.columns
+    # expected: E0 for the first state; for the second the lowest eigenvalue above E0 that start 2 overlaps
+    s2 = np.zeros(len(basis))
+    s2[index[int(np.atleast_1d(a0.key())[0])]], s2[index[int(np.atleast_1d(a1.key())[0])]] = 3.0, 10.0
+    e1 = next(w[i] for i in range(1, len(w)) if abs(vecs[:, i] @ s2) > 1e-8 and w[i] > w[0] + 1e-9)
+    assert abs(df["shift_s1"].iloc[-500:].mean() - w[0]) < 1e-3 * abs(w[0])
+    assert abs(df["shift_s2"].iloc[-500:].mean() - e1) < 1e-2 * abs(e1), (df["shift_s2"].iloc[-500:].mean(), e1, w[:5])
+    u, v = sim.replicas[0][1].v, sim.replicas[0][0].v
+    R.GramSchmidt(2).orthogonalize(sim.replicas[0])
+    assert abs(u.dot(v)) < 1e-9 * u.norm(2) * v.norm(2)
+
+
+def test_report_to_file_on_the_cpu(built, cpu_device, tmp_path):
+    """ReportToFile (reportingstrategy.jl:302-434): chunks of `chunk_size` reported steps go to an Arrow file, the in-memory
+    report is emptied after every chunk, an existing file gets a numbered sibling, the metadata travel with the file, and
+    load_df returns the same table a ReportDFAndInfo run produces."""
+    import rimu_b200 as R
+    oh, ph = cpu_device("real1d_6")
+    kw = dict(start_at=ph.address, style=R.IsStochasticInteger(), time_step=0.01, last_step=250, target_walkers=200, random_seed=3)
+    ref = R.solve(R.ProjectorMonteCarloProblem(ph, **kw)).dataframe()
+    fn = tmp_path / "out.arrow"
+    rs = R.ReportToFile(filename=fn, chunk_size=100, save_if=True)
+    sim = R.solve(R.ProjectorMonteCarloProblem(ph, reporting_strategy=rs, metadata={"note": "abc"}, **kw))
+    assert sim.success and rs.chunks_written == 3  # 100 + 100 + the last 50 at finalisation
+    assert all(len(v) == 0 for v in sim.report.values())
+    df = R.load_df(rs.filename)
+    assert list(df.columns) == list(ref.columns) and len(df) == 250
+    for col in ref.columns:
+        assert np.array_equal(np.asarray(df[col]), np.asarray(ref[col])), col
+    assert df.attrs["note"] == "abc" and "success" in df.attrs and df.attrs["num_replicas"] == "1"  # (metadata as of the first chunk)
+    assert sim.dataframe().equals(df)
+    # a second run with the same name does not overwrite (reportingstrategy.jl:362-381)
+    rs2 = R.ReportToFile(filename=fn, chunk_size=1000, reporting_interval=10, save_if=True)
+    sim2 = R.solve(R.ProjectorMonteCarloProblem(ph, reporting_strategy=rs2, **kw))
+    assert rs2.filename.endswith("out-1.arrow") and len(R.load_df(rs2.filename)) == 25 and sim2.success
+    # save_if = false: nothing is written
+    rs3 = R.ReportToFile(filename=tmp_path / "none.arrow", save_if=False)
+    R.solve(R.ProjectorMonteCarloProblem(ph, reporting_strategy=rs3, **kw))
+    assert not (tmp_path / "none.arrow").exists()
+    with pytest.raises(ValueError):
+        R.ReportToFile(compress="gzip")

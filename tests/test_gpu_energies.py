@@ -124,6 +124,56 @@ def test_transcorrelated_energy_within_error_bars(built):
     assert abs(pe.f - e_exact) < 5 * pe.sigma_f + tol_bias, (pe.f, pe.sigma_f, e_exact)
 
 
+def test_all_overlaps_on_the_device(built):
+    """AllOverlaps (replicastrategy.jl:60-183) with the device dot / mul!: the c{i}_dot_c{j} and c{i}_Op1_c{j} columns are the
+    device dot products of the replica vectors, and the replica (variational) estimator sum c_i.H.c_j / sum c_i.c_j brackets
+    the exact ground-state energy."""
+    import rimu_b200 as R
+    oh, ph = oracle_ham("real1d_6"), product_ham("real1d_6")
+    e_exact = oh.exact_energy()
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=R.IsDynamicSemistochastic(), time_step=0.002, last_step=3000,
+                                        target_walkers=1000, random_seed=6, replica_strategy=R.AllOverlaps(3, operator=ph))
+    sim = R.solve(prob)
+    assert sim.success, sim.message
+    df = sim.dataframe()
+    pairs = [(1, 2), (1, 3), (2, 3)]
+    for i, j in pairs:
+        assert f"c{i}_dot_c{j}" in df.columns and f"c{i}_Op1_c{j}" in df.columns
+    v1, v2 = sim.states[0].v, sim.states[1].v
+    assert math.isclose(df["c1_dot_c2"].iloc[-1], v1.dot(v2), rel_tol=1e-12)
+    assert math.isclose(df["c1_Op1_c2"].iloc[-1], R.dot(v1, ph, v2), rel_tol=1e-10)
+    # the same overlap from the host: downloaded pairs (independent of the device dot)
+    k1, x1 = v1.download_sorted()
+    k2, x2 = v2.download_sorted()
+    d2 = dict(zip(k2.reshape(-1).tolist(), x2.tolist()))
+    host = sum(x * d2.get(k, 0.0) for k, x in zip(k1.reshape(-1).tolist(), x1.tolist()))
+    assert math.isclose(v1.dot(v2), host, rel_tol=1e-12)
+    num = sum(np.asarray(df[f"c{i}_Op1_c{j}"])[1000:].sum() for i, j in pairs)
+    den = sum(np.asarray(df[f"c{i}_dot_c{j}"])[1000:].sum() for i, j in pairs)
+    assert abs(num / den - e_exact) < 0.01 * abs(e_exact), (num / den, e_exact)
+
+
+def test_gram_schmidt_spectral_states_on_the_device(built):
+    """GramSchmidt(2) (fciqmc.jl:187-202) on the device: starting vectors from the truncated-basis eigenvectors
+    (pmc_simulation.jl:48-63, through the device's element hooks), Gram-Schmidt with the device dot / axpby before every
+    step.  A deterministic run drives the first shift to E0 and keeps the second state orthogonal and above it."""
+    import rimu_b200 as R
+    oh, ph = oracle_ham("real1d_6"), product_ham("real1d_6")
+    w = np.sort(oh.exact_eigenvalues())
+    det = R.IsDeterministic()
+    prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, style=det, time_step=0.01, last_step=3000, target_walkers=100,
+                                        spectral_strategy=R.GramSchmidt(2), random_seed=1, max_length=10 ** 6, minimum_size=6)
+    sim = R.solve(prob)
+    assert sim.success, sim.message
+    df = sim.dataframe()
+    s1, s2 = df["shift_s1"].iloc[-300:].mean(), df["shift_s2"].iloc[-300:].mean()
+    assert abs(s1 - w[0]) < 1e-3 * abs(w[0]), (s1, w[0])
+    assert s2 > w[0] + 0.5 * (w[1] - w[0]) and min(abs(s2 - x) for x in w[1:12]) < 2e-2 * abs(s2), (s2, w[:12])
+    u, v = sim.replicas[0][1].v, sim.replicas[0][0].v
+    R.GramSchmidt(2).orthogonalize(sim.replicas[0])
+    assert abs(u.dot(v)) < 1e-9 * u.norm(2) * v.norm(2)
+
+
 # --------------------------------------------------------------------------- size-independent properties
 def _truncate(R, x, n):
     """One more hop can overshoot by orders of magnitude: keep a seeded subset of at most n entries."""

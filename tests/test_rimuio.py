@@ -138,6 +138,24 @@ def test_save_and_load_state_wrappers(built, tmp_path, monkeypatch):
     assert isinstance(v2.style, R.IsDynamicSemistochastic) and np.array_equal(v2.vals, [0.5, 1.5, -2.0])
     v3, _ = R.load_state(path, style=R.IsDeterministic())
     assert isinstance(v3.style, R.IsDeterministic)
-    src2.ctx.nranks = 2
-    with pytest.raises(NotImplementedError):
-        R.save_state(path, src2)
+    # several ranks (_save_state_mpi, RimuIO.jl:107-135): rank 0 writes the streaming format with the metadata, the others
+    # append their record batch in rank order between barriers; the file reads back as the concatenation in that order
+    class RankCtx:
+        def __init__(self, rank, nranks, log):
+            self.rank, self.nranks, self.log = rank, nranks, log
+
+        def allreduce(self, values):
+            self.log.append(("barrier", self.rank))
+            return values
+
+    path2, log = tmp_path / "ranks.arrow", []
+    shares = [(keys[[0]], np.array([1.0])), (keys[[1]], np.array([2.0])), (keys[[2]], np.array([3.0]))]
+    # the ranks run one after the other here, which is the order the barriers enforce between real processes
+    for r, (k, x) in enumerate(shares):
+        R.save_state(path2, FakeVec(k, x, address_type=addrs[0].address_type, ctx=RankCtx(r, 3, log)), **({"step": 7} if r == 0 else {}))
+    k_all, v_all, at, meta = rimuio.read_state_file(path2)
+    assert np.array_equal(k_all, keys) and np.array_equal(v_all, [1.0, 2.0, 3.0]) and meta["step"] == 7
+    assert sum(1 for e in log if e == ("barrier", 1)) == 3  # one barrier before every appending rank + the final one
+    monkeypatch.setattr(FakeVec, "upload", lambda self, k, x: self.assign(k, x), raising=False)
+    v4, _ = R.load_state(path2, ctx=RankCtx(0, 3, log))  # a multi-rank load goes through upload(), which keeps the owned keys only
+    assert np.array_equal(v4.vals, [1.0, 2.0, 3.0])
