@@ -54,7 +54,11 @@ enum {
 enum { RIMU_ADDR_BOSE = 0, RIMU_ADDR_FERMI = 1, RIMU_ADDR_FERMI2C = 2 };
 enum { RIMU_HUBBARD_REAL_1D = 0, RIMU_HUBBARD_MOM_1D = 1, RIMU_HUBBARD_REAL_SPACE = 2, RIMU_TRANSCORRELATED_1D = 3,
        RIMU_HUBBARD_REAL_1D_EP = 4,        /* Hamiltonians/HubbardReal1DEP.jl:47-92: potential[] = eps_i, bosons */
-       RIMU_EXTENDED_HUBBARD_REAL_1D = 5   /* Hamiltonians/ExtendedHubbardReal1D.jl:30-135: v = neighbour interaction, bosons */ };
+       RIMU_EXTENDED_HUBBARD_REAL_1D = 5,  /* Hamiltonians/ExtendedHubbardReal1D.jl:30-135: v = neighbour interaction, bosons */
+       RIMU_EXTENDED_HUBBARD_MOM_1D = 6,   /* Hamiltonians/ExtendedHubbardMom1D.jl:37-117 (bosons, boundary_condition = 0): u, v, t, kes;
+                                            * ws[q] = cos(q * 2pi / M) (off-diagonals), us[d] = cos(d * (2pi / M)) (diagonal), q, d = 0..M-1 */
+       RIMU_HUBBARD_MOM_1D_EP = 7          /* Hamiltonians/HubbardMom1DEP.jl:68-257 (BoseFS, two FermiFS components): u, t, kes;
+                                            * potential[k] = ep[k+1], the momentum-space harmonic potential */ };
 /* ExtendedHubbardReal1D boundary_condition (real ones; a complex twist angle has no device path) */
 enum { RIMU_BC_PERIODIC = 0, RIMU_BC_HARD_WALL = 1, RIMU_BC_TWISTED = 2 };
 enum { RIMU_VAL_F64 = 0, RIMU_VAL_I64 = 1 };

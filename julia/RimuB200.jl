@@ -25,7 +25,7 @@ using Rimu.BitStringAddresses: BoseFS, FermiFS, CompositeFS, SingleComponentFock
 using Rimu.StochasticStyles: IsDeterministic, IsStochasticInteger, IsDynamicSemistochastic, IsStochasticWithThreshold,
     ThresholdCompression, NoCompression
 using Rimu.DictVectors: Initiator, SimpleInitiator, CoherentInitiator, NonInitiator, InitiatorRule, FrozenDVec, DVec
-using Rimu.Hamiltonians: HubbardReal1D, HubbardReal1DEP, ExtendedHubbardReal1D, HubbardMom1D, HubbardRealSpace,
+using Rimu.Hamiltonians: HubbardReal1D, HubbardReal1DEP, ExtendedHubbardReal1D, HubbardMom1D, HubbardMom1DEP, ExtendedHubbardMom1D, HubbardRealSpace,
     Transcorrelated1D, AbstractHamiltonian
 using Rimu.Interfaces: AbstractDVec, StochasticStyle
 import Rimu.Interfaces: apply_operator!, working_memory, localpart
@@ -226,6 +226,15 @@ function desc(h::ExtendedHubbardReal1D{<:Any,<:Any,U,V,T,BC}) where {U,V,T,BC}  
     return base_desc(5, h.address; u=U, v=V, t=T, bc=BOUNDARY[BC])
 end
 desc(h::HubbardMom1D) = base_desc(1, h.address; u=h.u, t=h.t, kes=h.kes)                            # HubbardMom1D.jl:43-65
+function desc(h::ExtendedHubbardMom1D)                                                              # ExtendedHubbardMom1D.jl:37-57
+    h.address isa BoseFS || throw(ArgumentError("ExtendedHubbardMom1D has a device path for BoseFS addresses only"))
+    h.boundary_condition == 0 || throw(ArgumentError("a twisted boundary condition has no device path"))
+    M = num_modes(h.address)
+    # the cosines get_offdiagonal (:99-102) and extended_momentum_transfer_diagonal (excitations.jl:152) evaluate per element
+    return base_desc(6, h.address; u=h.u, v=h.v, t=h.t, kes=h.kes,
+                     ws=[cos(q * 2π / M) for q in 0:M-1], us=[cos(d * (2π / M)) for d in 0:M-1])
+end
+desc(h::HubbardMom1DEP) = base_desc(7, h.address; u=h.u, t=h.t, kes=h.kes, has_potential=true, potential=h.ep)  # HubbardMom1DEP.jl:68-96
 function desc(h::HubbardRealSpace)                                                                  # HubbardRealSpace.jl:163-241
     g = h.geometry
     dims = size(g)

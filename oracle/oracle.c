@@ -48,7 +48,9 @@
 
 enum { ORC_BOSE = 0, ORC_FERMI = 1, ORC_FERMI2C = 2 };
 enum { ORC_HUBBARD_REAL_1D = 0, ORC_HUBBARD_MOM_1D = 1, ORC_HUBBARD_REAL_SPACE = 2,
-       ORC_TRANSCORRELATED_1D = 3, ORC_HUBBARD_REAL_1D_EP = 4, ORC_EXTENDED_HUBBARD_REAL_1D = 5 };
+       ORC_TRANSCORRELATED_1D = 3, ORC_HUBBARD_REAL_1D_EP = 4, ORC_EXTENDED_HUBBARD_REAL_1D = 5,
+       ORC_EXTENDED_HUBBARD_MOM_1D = 6, /* ExtendedHubbardMom1D.jl:37-117 (bosons): ws[q] = cos(q*2pi/M), us[d] = cos(d*(2pi/M)) */
+       ORC_HUBBARD_MOM_1D_EP = 7 };     /* HubbardMom1DEP.jl:68-257: pot[k] = ep[k+1], the momentum-space harmonic potential */
 /* ExtendedHubbardReal1D boundary_condition (ExtendedHubbardReal1D.jl:12-22), stored in orc_ham.fold[0] */
 enum { ORC_BC_PERIODIC = 0, ORC_BC_HARD_WALL = 1, ORC_BC_TWISTED = 2 };
 enum { ORC_STYLE_DETERMINISTIC = 0, ORC_STYLE_INTEGER = 1, ORC_STYLE_SEMISTOCHASTIC = 2,
@@ -252,7 +254,9 @@ double orc_diagonal_onr(const orc_ham *h, const orc_onr *o) {
         }
         return h->u * (double)reg / 2 + h->v * (double)ext;
     }
-    case ORC_HUBBARD_MOM_1D: { /* HubbardMom1D.jl:163-181, excitations.jl:126-160 */
+    case ORC_HUBBARD_MOM_1D: case ORC_EXTENDED_HUBBARD_MOM_1D: case ORC_HUBBARD_MOM_1D_EP: {
+        /* HubbardMom1D.jl:163-181, excitations.jl:126-160; ExtendedHubbardMom1D.jl:85-89 + excitations.jl:145-156;
+         * HubbardMom1DEP.jl:151-166 + excitations.jl:274-279 */
         orc_map ma; build_map(o->n[0], M, &ma);
         if (h->addr_kind == ORC_BOSE) {
             double ke = 0.0;
@@ -262,13 +266,31 @@ double orc_diagonal_onr(const orc_ham *h, const orc_onr *o) {
                 onproduct += (long)ma.occ[i] * (ma.occ[i] - 1);
                 for (int j = 0; j < i; j++) onproduct += 4L * ma.occ[i] * ma.occ[j];
             }
-            return ke + h->u / (2 * M) * (double)onproduct;
+            double value = ke + h->u / (2 * M) * (double)onproduct;
+            if (h->model == ORC_EXTENDED_HUBBARD_MOM_1D) { /* + (v / M) * extended_momentum_transfer_diagonal(map, 2pi / M) */
+                double ext = 0.0;
+                for (int i = 0; i < ma.len; i++) {
+                    ext += (double)((long)ma.occ[i] * (ma.occ[i] - 1));
+                    for (int j = 0; j < i; j++) {
+                        int d = ma.mode[i] - ma.mode[j]; /* cos((mode_j - mode_i) * step) = cos(|d| * step): us[|d|] */
+                        ext += (double)(2L * ma.occ[i] * ma.occ[j]) * (1 + h->us[d]);
+                    }
+                }
+                value += (h->v / M) * ext;
+            } else if (h->model == ORC_HUBBARD_MOM_1D_EP) {
+                long n = 0;
+                for (int i = 0; i < ma.len; i++) n += ma.occ[i];
+                value += (double)n * h->pot[0];
+            }
+            return value;
         } else {
             orc_map mb; build_map(o->n[1], M, &mb);
             double ka = 0.0, kb = 0.0;
             for (int i = 0; i < ma.len; i++) ka += h->kes[ma.mode[i] - 1] * ma.occ[i];
             for (int i = 0; i < mb.len; i++) kb += h->kes[mb.mode[i] - 1] * mb.occ[i];
-            return ka + kb + h->u / (2 * M) * (double)(2 * ma.len * mb.len);
+            double value = ka + kb + h->u / (2 * M) * (double)(2 * ma.len * mb.len);
+            if (h->model == ORC_HUBBARD_MOM_1D_EP) value = value + (double)ma.len * h->pot[0] + (double)mb.len * h->pot[0];
+            return value;
         }
     }
     case ORC_HUBBARD_REAL_SPACE: { /* HubbardRealSpace.jl:18-75,90-106,279-293 */
@@ -317,14 +339,17 @@ long orc_num_offdiagonals_onr(const orc_ham *h, const orc_onr *o) {
     switch (h->model) {
     case ORC_HUBBARD_REAL_1D: case ORC_HUBBARD_REAL_1D_EP: case ORC_EXTENDED_HUBBARD_REAL_1D:
         return 2L * ma.len; /* HubbardReal1D.jl:51-53, HubbardReal1DEP.jl:78-80, ExtendedHubbardReal1D.jl:88-90 */
-    case ORC_HUBBARD_MOM_1D: /* HubbardMom1D.jl:131-144 */
+    case ORC_HUBBARD_MOM_1D: case ORC_EXTENDED_HUBBARD_MOM_1D: case ORC_HUBBARD_MOM_1D_EP: {
+        /* HubbardMom1D.jl:131-144; ExtendedHubbardMom1D.jl:75-83; HubbardMom1DEP.jl:178-186,223-235 */
+        long ep = h->model == ORC_HUBBARD_MOM_1D_EP ? (long)(ma.len + mb.len) * (M - 1) : 0;
         if (h->addr_kind == ORC_BOSE) {
             long s = ma.len, d = 0;
             for (int i = 0; i < ma.len; i++) d += ma.occ[i] > 1;
-            return s * (s - 1) * (M - 2) + d * (M - 1);
+            return s * (s - 1) * (M - 2) + d * (M - 1) + ep;
         } else if (h->addr_kind == ORC_FERMI2C)
-            return (long)h->N[0] * h->N[1] * (M - 1);
+            return (long)h->N[0] * h->N[1] * (M - 1) + ep;
         return 0;
+    }
     case ORC_HUBBARD_REAL_SPACE: /* HubbardRealSpace.jl:309-315,371-374 */
         return (long)(ma.len + mb.len) * 2 * h->ndim;
     case ORC_TRANSCORRELATED_1D: { /* Transcorrelated1D.jl:277-297 */
@@ -416,7 +441,31 @@ double orc_offdiagonal_onr(const orc_ham *h, const orc_onr *in, long chosen, orc
         }
         return -h->t * val;
     }
-    case ORC_HUBBARD_MOM_1D: {
+    case ORC_HUBBARD_MOM_1D: case ORC_EXTENDED_HUBBARD_MOM_1D: case ORC_HUBBARD_MOM_1D_EP: {
+        if (h->model == ORC_HUBBARD_MOM_1D_EP) { /* the external-potential block after the momentum-transfer block */
+            long n_mom;
+            if (h->addr_kind == ORC_BOSE) {
+                long s = ma.len, d = 0;
+                for (int i = 0; i < ma.len; i++) d += ma.occ[i] > 1;
+                n_mom = s * (s - 1) * (M - 2) + d * (M - 1);
+            } else n_mom = (long)ma.len * mb.len * (M - 1);
+            if (chosen > n_mom) { /* momentum_external_potential_excitation, excitations.jl:257-267 */
+                long i = chosen - n_mom;
+                int comp = 0;
+                if (h->addr_kind != ORC_BOSE && i > (long)ma.len * (M - 1)) { i -= (long)ma.len * (M - 1); comp = 1; }
+                const orc_map *mp = comp ? &mb : &ma;
+                long p, q;
+                fldmod1i(i, M - 1, &p, &q);
+                int pmode = mp->mode[p - 1];
+                if (q >= pmode) q += 1;            /* leave out the diagonal term */
+                int k = pmode - (int)q;            /* change in momentum */
+                int km = ((k % M) + M) % M;
+                double factor = h->pot[km];
+                int cre[1] = {(int)q}, des[1] = {pmode};
+                double val = excite(h->addr_kind == ORC_BOSE, out->n[comp], M, cre, des, 1);
+                return val * factor;
+            }
+        }
         if (h->addr_kind == ORC_BOSE) { /* excitations.jl:26-80; HubbardMom1D.jl:182-188 */
             long singlies = ma.len;
             long dbl = chosen - singlies * (singlies - 1) * (M - 2);
@@ -443,6 +492,8 @@ double orc_offdiagonal_onr(const orc_ham *h, const orc_onr *in, long chosen, orc
             dst[0] = mod1i(src[0] + (int)mom_change, M);
             dst[1] = mod1i(src[1] - (int)mom_change, M);
             double val = bose_excite(out->n[0], M, dst, src, 2);
+            if (h->model == ORC_EXTENDED_HUBBARD_MOM_1D) /* ExtendedHubbardMom1D.jl:99-102: q = -mom_change, cos even */
+                return h->u * val / (2 * M) + h->v * h->ws[mom_change] * val / M;
             return h->u / (2 * M) * val;
         } else { /* HubbardMom1D.jl:189-199 */
             int prm[3];

@@ -30,6 +30,7 @@ MAXM = 128
 BOSE, FERMI, FERMI2C = 0, 1, 2
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3
 HUBBARD_REAL_1D_EP, EXTENDED_HUBBARD_REAL_1D = 4, 5
+EXTENDED_HUBBARD_MOM_1D, HUBBARD_MOM_1D_EP = 6, 7
 BC_PERIODIC, BC_HARD_WALL, BC_TWISTED = 0, 1, 2
 STYLE_DETERMINISTIC, STYLE_INTEGER, STYLE_SEMISTOCHASTIC, STYLE_WITH_THRESHOLD = 0, 1, 2, 3
 
@@ -179,6 +180,15 @@ def ep_lattice(M):
     return is_[-k:] + is_[:-k]  # circshift(is, k)
 
 
+def momentum_space_harmonic_potential(M, v):
+    """HubbardMom1DEP.jl:14-31: 1/M * real(fft(v * j^2)) over the shifted lattice, symmetrised."""
+    js = ep_lattice(M)
+    mom = np.fft.fft(np.array([v * j * j for j in js], dtype=float))
+    for i in range(1, M // 2 + 1):
+        mom[M - i] = mom[i]
+    return (1 / M) * np.real(mom)
+
+
 class OracleHam:
     """A Hamiltonian of the oracle.
 
@@ -189,7 +199,8 @@ class OracleHam:
 
     MODELS = {"HubbardReal1D": HUBBARD_REAL_1D, "HubbardMom1D": HUBBARD_MOM_1D,
               "HubbardRealSpace": HUBBARD_REAL_SPACE, "Transcorrelated1D": TRANSCORRELATED_1D,
-              "HubbardReal1DEP": HUBBARD_REAL_1D_EP, "ExtendedHubbardReal1D": EXTENDED_HUBBARD_REAL_1D}
+              "HubbardReal1DEP": HUBBARD_REAL_1D_EP, "ExtendedHubbardReal1D": EXTENDED_HUBBARD_REAL_1D,
+              "ExtendedHubbardMom1D": EXTENDED_HUBBARD_MOM_1D, "HubbardMom1DEP": HUBBARD_MOM_1D_EP}
     KINDS = {"bose": BOSE, "fermi": FERMI, "fermi2c": FERMI2C}
 
     def __init__(self, model, kind, onr, u=1.0, t=1.0, v=1.0, dims=None, fold=None, trap=None,
@@ -231,6 +242,21 @@ class OracleHam:
             ks, kes = mom1d_grid(M, float(t), dispersion)
             for i in range(M):
                 h.ks[i], h.kes[i] = ks[i], kes[i]
+        elif model == "ExtendedHubbardMom1D":  # ExtendedHubbardMom1D.jl:37-57 (boundary_condition = 0)
+            h.u, h.t, h.v = float(u), float(t), float(v)
+            ks, kes = mom1d_grid(M, float(t), dispersion)
+            step = 2 * math.pi / M
+            for i in range(M):
+                h.ks[i], h.kes[i] = ks[i], kes[i]
+                h.ws[i] = math.cos(i * 2 * math.pi / M)   # cos(q * 2pi / M) of get_offdiagonal (:99-102), q = 0 .. M-1
+                h.us[i] = math.cos(i * step)              # cos((mode_j - mode_i) * step) of the diagonal (excitations.jl:152)
+        elif model == "HubbardMom1DEP":  # HubbardMom1DEP.jl:75-96
+            h.u, h.t = float(u), float(t)
+            ks, kes = mom1d_grid(M, float(t), dispersion)
+            ep = momentum_space_harmonic_potential(M, float(v_ho))
+            h.has_pot = 1
+            for i in range(M):
+                h.ks[i], h.kes[i], h.pot[i] = ks[i], kes[i], ep[i]
         elif model == "Transcorrelated1D":
             h.t, h.v, h.cutoff, h.three_body = float(t), float(v), int(cutoff), int(three_body_term)
             ks, kes, ws, us = tc_tables(M, float(t), int(cutoff))

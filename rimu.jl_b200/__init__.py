@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import RimuB200Error, build
 from .addresses import (AddressType, BoseFS, CompositeFS, FermiFS, FermiFS2C, near_uniform, near_uniform_onr,
                         num_modes, num_particles, onr)
-from .hamiltonians import (AbstractHamiltonian, Context, CubicGrid, ExtendedHubbardReal1D, HardwallBoundaries, HubbardMom1D,
+from .hamiltonians import (AbstractHamiltonian, Context, CubicGrid, ExtendedHubbardMom1D, ExtendedHubbardReal1D, HubbardMom1DEP, HardwallBoundaries, HubbardMom1D,
                            HubbardReal1D, HubbardReal1DEP, shift_lattice, shift_lattice_inv,
                            HubbardRealSpace, LadderBoundaries, PeriodicBoundaries, Transcorrelated1D,
                            continuum_dispersion, diagonal_element, dimension, get_context, get_offdiagonal,

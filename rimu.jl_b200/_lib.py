@@ -32,6 +32,7 @@ ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = -1, -2, -3, -4
 ADDR_BOSE, ADDR_FERMI, ADDR_FERMI2C = 0, 1, 2
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3
 HUBBARD_REAL_1D_EP, EXTENDED_HUBBARD_REAL_1D = 4, 5
+EXTENDED_HUBBARD_MOM_1D, HUBBARD_MOM_1D_EP = 6, 7
 BC_PERIODIC, BC_HARD_WALL, BC_TWISTED = 0, 1, 2
 VAL_F64, VAL_I64 = 0, 1
 STYLE_DETERMINISTIC, STYLE_INTEGER, STYLE_SEMISTOCHASTIC, STYLE_WITH_THRESHOLD = 0, 1, 2, 3

@@ -52,7 +52,7 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
         bits = d->num_particles[0] + M - 1;
         if (bits + 1 > 128) return ham_host_fail(img, "BoseFS{%d,%d} needs %d bits; at most 127 supported", d->num_particles[0], M, bits);
         if (model == RIMU_HUBBARD_REAL_1D || model == RIMU_HUBBARD_REAL_1D_EP || model == RIMU_EXTENDED_HUBBARD_REAL_1D) hk = HK_REAL1D_BOSE;
-        else if (model == RIMU_HUBBARD_MOM_1D) hk = HK_MOM1D_BOSE;
+        else if (model == RIMU_HUBBARD_MOM_1D || model == RIMU_EXTENDED_HUBBARD_MOM_1D || model == RIMU_HUBBARD_MOM_1D_EP) hk = HK_MOM1D_BOSE;
         else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_BOSE;
     } else if (kind == RIMU_ADDR_FERMI) {
         if (d->num_components != 1) return ham_host_fail(img, "FermiFS must have one component");
@@ -65,7 +65,7 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
         if (M > 32) return ham_host_fail(img, "two-component fermions with more than 32 modes unsupported");
         if (d->num_particles[0] == M && d->num_particles[1] == M && M == 32)
             return ham_host_fail(img, "completely filled 32-mode two-component address collides with the empty-slot sentinel");
-        if (model == RIMU_HUBBARD_MOM_1D) hk = HK_MOM1D_F2C;
+        if (model == RIMU_HUBBARD_MOM_1D || model == RIMU_HUBBARD_MOM_1D_EP) hk = HK_MOM1D_F2C;
         else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_F2C;
         else if (model == RIMU_TRANSCORRELATED_1D) hk = HK_TC_F2C;
     }
@@ -76,9 +76,9 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
     if (hk == HK_MOM1D_BOSE && M < 3) return ham_host_fail(img, "HubbardMom1D needs at least 3 modes");
     { // the device decoders index off-diagonals with 32-bit arithmetic
         double n1 = d->num_particles[0], n2 = d->num_particles[1], m = M, lmax = 0;
-        if (hk == HK_MOM1D_BOSE) lmax = n1 * (n1 - 1) * (m - 2) + n1 * (m - 1);
+        if (hk == HK_MOM1D_BOSE) lmax = n1 * (n1 - 1) * (m - 2) + 2 * n1 * (m - 1);
         else if (hk == HK_TC_F2C) lmax = n1 * n2 * (m - 1) + (n1 * (n1 - 1) * n2 + n2 * (n2 - 1) * n1) * m * m;
-        else if (hk == HK_MOM1D_F2C) lmax = n1 * n2 * (m - 1);
+        else if (hk == HK_MOM1D_F2C) lmax = n1 * n2 * (m - 1) + (n1 + n2) * (m - 1);
         else lmax = (n1 + n2) * 6;
         if (lmax >= 2147483648.0) return ham_host_fail(img, "more than 2^31 off-diagonals per address are unsupported");
     }
@@ -91,7 +91,9 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
     v.u = d->u; v.t = d->t; v.v = d->v; v.tc0 = d->t_comp[0]; v.tc1 = d->t_comp[1];
     v.u00 = d->u_mat[0]; v.u10 = d->u_mat[1];
     v.u_2m = d->u / (2 * M); v.u_m = d->u / M;
-    v.variant = model == RIMU_HUBBARD_REAL_1D_EP ? 1 : model == RIMU_EXTENDED_HUBBARD_REAL_1D ? 2 : 0;
+    v.variant = model == RIMU_HUBBARD_REAL_1D_EP ? 1 : model == RIMU_EXTENDED_HUBBARD_REAL_1D ? 2
+              : model == RIMU_EXTENDED_HUBBARD_MOM_1D ? 1 : model == RIMU_HUBBARD_MOM_1D_EP ? 2 : 0;
+    v.v_m = d->v / M;
     v.bc = d->boundary_condition;
     if (v.variant == 2 && (v.bc < 0 || v.bc > 2)) return ham_host_fail(img, "invalid boundary condition");
     int nz = 0;

@@ -29,6 +29,9 @@ enum HamKind {
 struct HamDev {
     int hk, M, N0, N1, ndim, nnb, cutoff, three_body, has_pot, umat_zero;
     int variant, bc; // HK_REAL1D_BOSE: 0 HubbardReal1D, 1 HubbardReal1DEP (pot = eps_i), 2 ExtendedHubbardReal1D (v, bc = RIMU_BC_*)
+                     // HK_MOM1D_BOSE / HK_MOM1D_F2C: 0 HubbardMom1D, 1 ExtendedHubbardMom1D (v; ws, us = cosine tables),
+                     //                               2 HubbardMom1DEP (pot = ep, momentum-space harmonic potential)
+    double v_m;      // v / M
     double u, t, v, tc0, tc1, u00, u10;
     double u_2m, u_m; // u / (2M), u / M: the same IEEE divisions the reference evaluates per element, done once on the host
     const double *kes, *ws, *us, *pot; // device tables
@@ -253,11 +256,24 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         // sum n(n-1) + 4 sum_{i>j} n_i n_j with sum n = N and sum n^2 = lin + N
         const int ntot = h.N0;
         const long long onproduct = (long long)lin + 2LL * ((long long)ntot * ntot - lin - ntot);
-        return ke + h.u_2m * (double)onproduct;
+        double value = ke + h.u_2m * (double)onproduct;
+        if (h.variant == 1) { // + (v / M) * extended_momentum_transfer_diagonal(map, 2pi / M)  (excitations.jl:145-156)
+            double ext = 0.0;
+            int mi, ni;
+            for (BoseModes<B> it(x); it.next(mi, ni);) {
+                ext += (double)(ni * (ni - 1));
+                int mj, nj;
+                for (BoseModes<B> jt(x); jt.next(mj, nj) && mj < mi;) ext += (double)(2 * ni * nj) * (1 + h.us[mi - mj]);
+            }
+            value += h.v_m * ext;
+        } else if (h.variant == 2) value += (double)ntot * h.pot[0]; // momentum_external_potential_diagonal (excitations.jl:274-279)
+        return value;
     } else if constexpr (HK == HK_MOM1D_F2C) {
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
         double ka = kes_sum(h.kes, fa), kb = kes_sum(h.kes, fb);
-        return ka + kb + h.u_2m * (double)(2 * __popcll(fa) * __popcll(fb));
+        double value = ka + kb + h.u_2m * (double)(2 * __popcll(fa) * __popcll(fb));
+        if (h.variant == 2) value = value + (double)__popcll(fa) * h.pot[0] + (double)__popcll(fb) * h.pot[0];
+        return value;
     } else if constexpr (HK == HK_RS_BOSE) {
         double interaction = h.umat_zero ? 0.0 : h.u00 * (double)bose_interaction(x) / 2;
         double pot = 0.0;
@@ -305,9 +321,9 @@ template <int HK, class B> DEV long long ham_num_offdiagonals(const HamDev &h, B
         return 2LL * bose_num_occupied(x);
     } else if constexpr (HK == HK_MOM1D_BOSE) {
         long long s = bose_num_occupied(x), d = bose_num_doubly(x);
-        return s * (s - 1) * (M - 2) + d * (M - 1);
+        return s * (s - 1) * (M - 2) + d * (M - 1) + (h.variant == 2 ? s * (M - 1) : 0);
     } else if constexpr (HK == HK_MOM1D_F2C) {
-        return (long long)h.N0 * h.N1 * (M - 1);
+        return (long long)h.N0 * h.N1 * (M - 1) + (h.variant == 2 ? (long long)(h.N0 + h.N1) * (M - 1) : 0);
     } else if constexpr (HK == HK_RS_BOSE) {
         return (long long)bose_num_occupied(x) * h.nnb;
     } else if constexpr (HK == HK_RS_FERMI) {
@@ -344,6 +360,22 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         const int s = bose_num_occupied(x);
         const int ndiff = s * (s - 1) * (M - 2);
         const int ii = (int)i;
+        if (h.variant == 2) { // HubbardMom1DEP: the external-potential block follows the momentum-transfer block
+            const int nmom = ndiff + bose_num_doubly(x) * (M - 1);
+            if (ii >= nmom) { // momentum_external_potential_excitation (excitations.jl:257-267): a^dagger_q a_p, q != p
+                const unsigned e = (unsigned)(ii - nmom), mm1 = (unsigned)(M - 1);
+                const unsigned p = udiv_small(e, mm1);
+                int q = (int)(e - p * mm1) + 1, pmode, np_, poff;
+                bose_kth_occupied(x, (int)p, pmode, np_, poff);
+                if (q >= pmode) q += 1;
+                int k = pmode - q;
+                if (k < 0) k += M;
+                B y = delete_bit(x, poff);
+                const int nq = bose_create(y, q);
+                out = y;
+                return sqrt((double)(np_ * nq)) * h.pot[k];
+            }
+        }
         int src0, src1, off0, off1, n0, n1, mom;
         if (ii >= ndiff) { // both particles from one mode with n >= 2
             const unsigned dbl = (unsigned)(ii - ndiff), mm1 = (unsigned)(M - 1);
@@ -373,9 +405,35 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         value *= bose_create(y, dst1);
         value *= bose_create(y, dst0);
         out = y;
+        if (h.variant == 1) { // ExtendedHubbardMom1D.jl:99-102: u * onproduct / 2M + v * cos(q * 2pi / M) * onproduct / M, q = -mom
+            const double op = sqrt((double)value);
+            return h.u * op / (2 * M) + h.v * h.ws[mom] * op / M;
+        }
         return h.u_2m * sqrt((double)value);
     } else if constexpr (HK == HK_MOM1D_F2C) {
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
+        if (h.variant == 2) { // HubbardMom1DEP.jl:223-257: then N1 (M-1) one-body moves of component a, N2 (M-1) of component b
+            const long long nmom = (long long)h.N0 * h.N1 * (M - 1);
+            if (i >= nmom) {
+                unsigned e = (unsigned)(i - nmom);
+                const unsigned mm1 = (unsigned)(M - 1);
+                const int comp = e >= (unsigned)h.N0 * mm1 ? 1 : 0;
+                if (comp) e -= (unsigned)h.N0 * mm1;
+                u64 f = comp ? fb : fa;
+                const unsigned p = udiv_small(e, mm1);
+                int q = (int)(e - p * mm1) + 1;
+                const int pmode = select_(f, (int)p) + 1;
+                if (q >= pmode) q += 1;
+                int k = pmode - q;
+                if (k < 0) k += M;
+                int cnt = 0;
+                fermi_destroy(f, pmode, cnt);
+                if (!fermi_create(f, q, cnt)) return 0.0;
+                if (comp) fb = f; else fa = f;
+                out = (B)(fa | (fb << M));
+                return parity_sign(cnt) * h.pot[k];
+            }
+        }
         int p, q, mk;
         double val = mom_transfer_2c(M, fa, fb, h.N1, i, true, p, q, mk);
         if (val != 0.0) out = (B)(fa | (fb << M));

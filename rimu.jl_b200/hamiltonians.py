@@ -354,6 +354,77 @@ class HubbardMom1D(AbstractHamiltonian):
         return f"HubbardMom1D({self.address}; u={self.u}, t={self.t})"
 
 
+def _momentum_grid(M, t, dispersion):
+    """ks and kes of the momentum-space models (HubbardMom1D.jl:55-63)"""
+    step = 2 * math.pi / M
+    start = -math.pi * (1 + 1 / M) + step if M % 2 else -math.pi + step
+    ks = np.array([start + i * step for i in range(M)])
+    return ks, np.asarray(dispersion(t, ks), dtype=float)
+
+
+class ExtendedHubbardMom1D(AbstractHamiltonian):
+    """ExtendedHubbardMom1D(address; u, v, t, dispersion) (Hamiltonians/ExtendedHubbardMom1D.jl:37-117): the t-V model in
+    momentum space, bosons, boundary_condition = 0.  The cosines the reference evaluates per element -- cos(q * 2pi / M) in
+    get_offdiagonal, cos((mode_j - mode_i) * (2pi / M)) in the diagonal -- are tabulated by the host with the same expressions
+    and passed through the descriptor, like kes."""
+
+    def __init__(self, address, u=1.0, v=1.0, t=1.0, dispersion=hubbard_dispersion, boundary_condition=0.0):
+        if not isinstance(address, BoseFS):
+            raise TypeError("ExtendedHubbardMom1D on the device path needs a BoseFS address")
+        if boundary_condition != 0.0:
+            raise NotImplementedError("a twisted boundary condition has no device path")
+        self.u, self.v, self.t, self.boundary_condition = float(u), float(v), float(t), 0.0
+        M = address.num_modes
+        if M > _lib.MAX_TABLE_MODES:
+            raise ValueError(f"momentum-space models support at most {_lib.MAX_TABLE_MODES} modes")
+        self.ks, self.kes = _momentum_grid(M, self.t, dispersion)
+        self.desc = _lib.HamDesc()
+        self.desc.model, self.desc.u, self.desc.v, self.desc.t = _lib.EXTENDED_HUBBARD_MOM_1D, self.u, self.v, self.t
+        step = 2 * math.pi / M
+        for i in range(M):
+            self.desc.kes[i] = self.kes[i]
+            self.desc.ws[i] = math.cos(i * 2 * math.pi / M)
+            self.desc.us[i] = math.cos(i * step)
+        self._finish(address)
+
+    def __repr__(self):
+        return f"ExtendedHubbardMom1D({self.address}; u={self.u}, v={self.v}, t={self.t}, boundary_condition={self.boundary_condition})"
+
+
+def momentum_space_harmonic_potential(M, v):
+    """HubbardMom1DEP.jl:14-31: 1/M * real(fft(v j^2)) over the shifted lattice, symmetrised"""
+    js = shift_lattice(range(-(M // 2), -(M // 2) + M))
+    mom = np.fft.fft(np.array([v * j * j for j in js], dtype=float))
+    for i in range(1, M // 2 + 1):
+        mom[M - i] = mom[i]
+    return (1 / M) * np.real(mom)
+
+
+class HubbardMom1DEP(AbstractHamiltonian):
+    """HubbardMom1DEP(address; u, t, v_ho, dispersion) (Hamiltonians/HubbardMom1DEP.jl:68-257): Hubbard chain in momentum space
+    with a harmonic trap; BoseFS or two FermiFS components.  The off-diagonals are the momentum-transfer block of
+    HubbardMom1D followed by the one-body block of the potential (excitations.jl:257-267)."""
+
+    def __init__(self, address, u=1.0, t=1.0, v_ho=1.0, dispersion=hubbard_dispersion):
+        if not isinstance(address, (BoseFS, CompositeFS)):
+            raise TypeError("HubbardMom1DEP needs a BoseFS or FermiFS2C address")
+        self.u, self.t, self.v_ho = float(u), float(t), float(v_ho)
+        M = address.num_modes
+        if M > _lib.MAX_TABLE_MODES:
+            raise ValueError(f"momentum-space models support at most {_lib.MAX_TABLE_MODES} modes")
+        self.ks, self.kes = _momentum_grid(M, self.t, dispersion)
+        self.ep = momentum_space_harmonic_potential(M, self.v_ho)
+        self.desc = _lib.HamDesc()
+        self.desc.model, self.desc.u, self.desc.t, self.desc.has_potential = _lib.HUBBARD_MOM_1D_EP, self.u, self.t, 1
+        for i in range(M):
+            self.desc.kes[i] = self.kes[i]
+            self.desc.potential[i] = self.ep[i]
+        self._finish(address)
+
+    def __repr__(self):
+        return f"HubbardMom1DEP({self.address}; u={self.u}, t={self.t}, v_ho={self.v_ho})"
+
+
 class HubbardRealSpace(AbstractHamiltonian):
     def __init__(self, address, geometry=None, t=None, u=None, v=None):
         C_ = 1 if not isinstance(address, CompositeFS) else 2

@@ -29,6 +29,10 @@ SPECS = {
     "mom1d_bose": ("HubbardMom1D", "bose", (0, 0, 0, 6, 0, 0, 0, 0), dict(u=4.0, t=1.0)),
     "mom1d_bose_20": ("HubbardMom1D", "bose", tuple(20 if i == 9 else 0 for i in range(20)), dict(u=6.0, t=1.0)),  # config 2
     "mom1d_odd": ("HubbardMom1D", "bose", (1, 2, 3, 0, 0), dict(u=1.0, t=1.0)),
+    "ext_mom1d": ("ExtendedHubbardMom1D", "bose", (0, 1, 2, 0, 1, 0), dict(u=1.5, v=2.5, t=1.0)),
+    "ext_mom1d_20": ("ExtendedHubbardMom1D", "bose", tuple(10 if i == 9 else 0 for i in range(20)), dict(u=6.0, v=1.0, t=1.0)),
+    "mom1d_ep": ("HubbardMom1DEP", "bose", (0, 0, 3, 1, 0), dict(u=2.0, t=1.0, v_ho=0.5)),
+    "mom1d_ep_f2c": ("HubbardMom1DEP", "fermi2c", ((0, 1, 1, 0, 0, 0), (0, 0, 1, 0, 1, 0)), dict(u=3.0, t=1.0, v_ho=0.3)),
     "mom1d_f2c": ("HubbardMom1D", "fermi2c", ((1, 1, 0, 0), (0, 0, 1, 1)), dict(u=4.0, t=4 / math.pi ** 2)),
     "rs_bose_1d": ("HubbardRealSpace", "bose", _nu(5, 5), dict(u=1.0, t=1.0, dims=(5,))),
     "rs_bose_2d": ("HubbardRealSpace", "bose", _nu(6, 9), dict(u=2.0, t=1.5, dims=(3, 3))),
@@ -71,6 +75,10 @@ def product_ham(name):
         return R.ExtendedHubbardReal1D(addr, **p)
     if model == "HubbardMom1D":
         return R.HubbardMom1D(addr, **p)
+    if model == "ExtendedHubbardMom1D":
+        return R.ExtendedHubbardMom1D(addr, **p)
+    if model == "HubbardMom1DEP":
+        return R.HubbardMom1DEP(addr, **p)
     if model == "Transcorrelated1D":
         return R.Transcorrelated1D(addr, **p)
     dims, fold, trap = p.pop("dims"), p.pop("fold", None), p.pop("trap", None)

@@ -48,7 +48,7 @@ def test_hamiltonian_elements(built, name):
                     assert tuple(int(x) for x in ko[i]) == ok
 
 
-@pytest.mark.parametrize("name", ["real1d_ep", "ext1d", "ext1d_hw", "real1d_6", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d", "rs_bose_3d_w2",
+@pytest.mark.parametrize("name", ["ext_mom1d", "mom1d_ep", "mom1d_ep_f2c", "real1d_ep", "ext1d", "ext1d_hw", "real1d_6", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d", "rs_bose_3d_w2",
                                   "rs_fermi", "rs_f2c_4x4", "rs_f2c_trap", "tc_7", "tc_8_cut2"])
 def test_deterministic_hv(built, name):
     """mul!(y, H, x) three times from the starting address: keys exact, values 1e-12 relative."""
@@ -70,7 +70,7 @@ def test_deterministic_hv(built, name):
             break
 
 
-@pytest.mark.parametrize("name", ["real1d_ep", "ext1d", "ext1d_hw", "real1d_6", "real1d_10", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d",
+@pytest.mark.parametrize("name", ["ext_mom1d", "ext_mom1d_20", "mom1d_ep", "mom1d_ep_f2c", "real1d_ep", "ext1d", "ext1d_hw", "real1d_6", "real1d_10", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d",
                                   "rs_bose_3d_w2", "rs_f2c_4x4", "tc_7"])
 def test_integer_walkers_bit_exact(built, name):
     """IsStochasticInteger FCIQMC steps: same Philox streams => identical vectors and statistics."""

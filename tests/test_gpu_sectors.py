@@ -15,7 +15,7 @@ from tests.test_gpu_energies import exact_energy
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["real1d_6", "rs_bose_2d", "rs_fermi", "rs_fermi_hw", "rs_f2c_4x4", "rs_f2c_trap", "mom1d_bose", "mom1d_f2c", "ext1d_twisted", "real1d_ep"]
+CASES = ["real1d_6", "rs_bose_2d", "rs_fermi", "rs_fermi_hw", "rs_f2c_4x4", "rs_f2c_trap", "mom1d_bose", "mom1d_f2c", "ext1d_twisted", "real1d_ep", "ext_mom1d", "mom1d_ep", "mom1d_ep_f2c"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -118,7 +118,7 @@ STYLES = {  # name -> (oracle style, integer values?, proj_threshold, plain_h)
 
 
 @pytest.mark.parametrize("style_name", sorted(STYLES))
-@pytest.mark.parametrize("name", ["real1d_10", "real1d_w2", "ext1d_twisted", "real1d_ep", "mom1d_bose", "mom1d_f2c", "rs_bose_2d_hw",
+@pytest.mark.parametrize("name", ["ext_mom1d", "mom1d_ep", "mom1d_ep_f2c", "real1d_10", "real1d_w2", "ext1d_twisted", "real1d_ep", "mom1d_bose", "mom1d_f2c", "rs_bose_2d_hw",
                                   "rs_bose_3d_w2", "rs_f2c_4x4", "tc_7"])
 def test_device_step_arithmetic_matches_oracle_on_the_host(built, emu, name, style_name):
     """Everything ONE parent deposits in a step -- the diagonal death/cloning value and every spawn attempt (Philox draw,

@@ -173,7 +173,7 @@ Pair Symbol ArgumentError RimuB200Error Context GPUHam GPUDVec GPUWorkingMemory 
 IsDeterministic IsStochasticInteger NonInitiator to_key from_key words desc base_desc addr_kind particles components gpu_ham
 make_current table_slots resize_table! grow_exchange! create_vec val_type upload! download similar_empty global_length
 style_params initiator_params compression_threshold step_stats_tuple default_style apply_operator! mul! dot norm pairs
-working_memory last_error num_offdiagonals StochasticStyle zerovector! isa Returns something showerror Vector
+working_memory last_error num_offdiagonals cos StochasticStyle zerovector! isa Returns something showerror Vector
 """.split())
 
 

@@ -557,3 +557,39 @@ def test_golden_fixture_spectra_and_elements():
         assert h.diagonal_element(k) == e["diagonal_element"] and h.num_offdiagonals(k) == e["num_offdiagonals"]
         k2, v2 = h.get_offdiagonal(k, e["get_offdiagonal"]["chosen"])
         assert h.unpack(k2) == tuple(e["get_offdiagonal"]["onr"]) and math.isclose(v2, e["get_offdiagonal"]["value"], rel_tol=1e-15)
+
+
+# --------------------------------------------------------------------------- momentum-space siblings
+def test_hubbard_mom1d_ep_relations_of_the_reference():
+    """test/Hamiltonians.jl:1082-1106: (i) exact_energy(HubbardReal1DEP) == exact_energy(HubbardMom1DEP) for the same
+    parameters; (ii) without a potential the fermionic HubbardMom1DEP matrix IS the HubbardMom1D matrix; (iii) two fermions of
+    opposite spin and two bosons have the same ground-state energy in the trap."""
+    real = orc.OracleHam("HubbardReal1DEP", "bose", (1, 1, 1, 1, 1), u=1.2, t=2.0, v_ho=2.0)
+    mom = orc.OracleHam("HubbardMom1DEP", "bose", (0, 0, 5, 0, 0), u=1.2, t=2.0, v_ho=2.0)
+    assert math.isclose(real.exact_energy(), mom.exact_energy(), rel_tol=1e-10)
+    c = ((0, 1, 0, 1, 0, 0), (0, 0, 1, 0, 0, 0))
+    plain = orc.OracleHam("HubbardMom1D", "fermi2c", c, u=2.0)
+    ep0 = orc.OracleHam("HubbardMom1DEP", "fermi2c", c, u=2.0, v_ho=0.0)
+    # the EP model lists (N1 + N2)(M - 1) more off-diagonals, all with value 0 when v_ho = 0: compare through the full sector
+    b = np.array([plain.sector_unrank(i) for i in range(plain.sector_dim())]).reshape(-1, 1)
+    assert np.array_equal(plain.sparse_matrix(b).toarray(), ep0.sparse_matrix(b).toarray())
+    for disp in ("continuum", "hubbard"):
+        bose = orc.OracleHam("HubbardMom1DEP", "bose", (0, 0, 2, 0, 0), v_ho=1.5, dispersion=disp)
+        fermi = orc.OracleHam("HubbardMom1DEP", "fermi2c", ((0, 0, 1, 0, 0), (0, 0, 1, 0, 0)), v_ho=1.5, dispersion=disp)
+        assert math.isclose(bose.exact_energy(), fermi.exact_energy(), rel_tol=1e-10, abs_tol=1e-12)
+
+
+def test_extended_hubbard_mom1d_spectrum_is_contained_in_the_real_space_one():
+    """test/Hamiltonians.jl:1627-1639 (boundary_condition = 0, bosons): every eigenvalue of ExtendedHubbardMom1D (one momentum
+    sector) is an eigenvalue of ExtendedHubbardReal1D, to 8 digits."""
+    hm = orc.OracleHam("ExtendedHubbardMom1D", "bose", (0, 0, 3, 0, 0, 0))
+    hr = orc.OracleHam("ExtendedHubbardReal1D", "bose", (0, 0, 3, 0, 0, 0))
+    em = np.round(hm.exact_eigenvalues(), 8)
+    er = np.round(hr.exact_eigenvalues(), 8)
+    assert len(em) >= 8 and all(np.any(np.abs(er - x) < 2e-8) for x in em)
+    # the v = 0 limit is HubbardMom1D
+    a = (0, 1, 2, 0, 1, 0)
+    h0 = orc.OracleHam("ExtendedHubbardMom1D", "bose", a, u=1.5, v=0.0, t=1.0)
+    h1 = orc.OracleHam("HubbardMom1D", "bose", a, u=1.5, t=1.0)
+    bs = h1.bfs_basis()
+    assert np.allclose(h0.sparse_matrix(bs).toarray(), h1.sparse_matrix(bs).toarray(), rtol=1e-14, atol=1e-14)
