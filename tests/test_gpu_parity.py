@@ -62,9 +62,22 @@ def test_deterministic_hv(built, name):
         R.mul(y, ph, x)
         ok, ov, st = oh.step(p, ok, ov)
         gk, gv = y.download_sorted()
-        assert np.array_equal(gk, ok), (name, it)
         scale = np.abs(ov).max()
-        assert np.all(np.abs(gv - ov) <= RTOL * np.maximum(np.abs(ov), scale)), (name, it, np.abs(gv - ov).max())
+        if not np.array_equal(gk, ok):
+            # a sum of terms that cancel (the symmetric potential of HubbardMom1DEP with fermion signs) is an exact zero -- no
+            # entry -- in one summation order and a rounding residue in another: such keys may differ, but only with values
+            # below the Float64 tolerance of the product
+            got = {tuple(k): v for k, v in zip(gk.tolist(), gv.tolist())}
+            want = {tuple(k): v for k, v in zip(ok.tolist(), ov.tolist())}
+            for k in set(got) ^ set(want):
+                assert abs(got.get(k, 0.0) - want.get(k, 0.0)) <= RTOL * scale, (name, it, k)
+            common = sorted(set(got) & set(want))
+            gv, ov2 = np.array([got[k] for k in common]), np.array([want[k] for k in common])
+            assert np.all(np.abs(gv - ov2) <= RTOL * np.maximum(np.abs(ov2), scale)), (name, it)
+            # continue from the oracle's vector so that both sides see the same input
+            y = R.GPUDVec(style=R.IsDeterministic(), address_type=x.address_type, ctx=x.ctx).upload(ok, ov)
+        else:
+            assert np.all(np.abs(gv - ov) <= RTOL * np.maximum(np.abs(ov), scale)), (name, it, np.abs(gv - ov).max())
         x = y
         if len(ok) > 20000:
             break
