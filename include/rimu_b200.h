@@ -124,7 +124,10 @@ typedef struct {
      * (|parent value| > threshold) is "initiator", its spawns are "safe", spawns of non-initiators are "unsafe" -- and
      * converted back with from_initiator_value before compression.  Partitioned method only. */
     int32_t initiator_rule;   /* RIMU_INITIATOR_* ; 0 = NonInitiator */
-    int32_t reserved_;
+    int32_t ordered;          /* != 0 (Float64 styles, partitioned method, no initiator rule): order-deterministic summation --
+                               * every address is summed in sorted (address, value) order and the walker number in a fixed
+                               * order, so that a step's result is bit-identical from run to run (audit mode, ~10x slower
+                               * annihilation).  Integer walkers are always exact. */
     double initiator_threshold;
 } rimu_step_params;
 

@@ -442,7 +442,7 @@ struct StepParams                     # == rimu_step_params; asserted against ri
     step::UInt64
     table_slots::UInt64
     initiator_rule::Int32
-    reserved::Int32
+    ordered::Int32
     initiator_threshold::Float64
 end
 struct StepStats                      # == rimu_step_stats; asserted against rimu_sizeof_step_stats()
@@ -486,11 +486,12 @@ mutable struct GPUWorkingMemory{S,I}
     initiator::I
     seed::UInt64
     counter::UInt64
+    ordered::Bool          # order-deterministic Float64 summation (rimu_step_params.ordered): bit-reproducible steps
     last_stats::StepStats
 end
 # pmc_simulation.jl:125; PDWorkingMemory(v) pdworkingmemory.jl:104-108
-working_memory(v::GPUDVec; seed=rand(UInt64)) =
-    GPUWorkingMemory(v.ctx, v.style, v.initiator, UInt64(seed), UInt64(0), StepStats(ntuple(_ -> 0, fieldcount(StepStats))...))
+working_memory(v::GPUDVec; seed=rand(UInt64), ordered=false) =
+    GPUWorkingMemory(v.ctx, v.style, v.initiator, UInt64(seed), UInt64(0), ordered, StepStats(ntuple(_ -> 0, fieldcount(StepStats))...))
 
 initiator_params(::NonInitiator) = (0, 0.0)                                       # initiators.jl:224-236
 initiator_params(i::Initiator) = (1, Float64(i.threshold))                        # :132-160
@@ -533,7 +534,7 @@ function apply_operator!(wm::GPUWorkingMemory, target::GPUDVec, source::GPUDVec,
         (op.hamiltonian, 0, Float64(op.shift), Float64(op.time_step)) : (op, 1, 0.0, 0.0)
     sty, pt, rt, at, ct = style_params(wm.style)
     ir, it = initiator_params(wm.initiator)
-    params = Ref(StepParams(sty, plain, shift, dτ, Float64(boost), pt, rt, at, ct, wm.seed, wm.counter, 0, ir, 0, it))
+    params = Ref(StepParams(sty, plain, shift, dτ, Float64(boost), pt, rt, at, ct, wm.seed, wm.counter, 0, ir, Int32(wm.ordered), it))
     stats = Ref(wm.last_stats)
     gh = gpu_ham(ham, wm.ctx)
     table_retries = 0

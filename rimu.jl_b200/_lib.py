@@ -111,7 +111,7 @@ class StepParams(C.Structure):
         ("proj_threshold", C.c_double), ("rel_threshold", C.c_double), ("abs_threshold", C.c_double),
         ("compress_threshold", C.c_double),
         ("seed", C.c_uint64), ("step", C.c_uint64), ("table_slots", C.c_uint64),
-        ("initiator_rule", C.c_int32), ("reserved_", C.c_int32), ("initiator_threshold", C.c_double),
+        ("initiator_rule", C.c_int32), ("ordered", C.c_int32), ("initiator_threshold", C.c_double),
     ]
 
 

@@ -124,7 +124,7 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->heavy.items); cudaFree(c->bucket_tmp);
     cudaFree(c->spare_keys); cudaFree(c->spare_vals); cudaFree(c->spare_diag);
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
-    cudaFree(c->d_red); cudaFreeHost(c->h_red);
+    cudaFree(c->d_red); cudaFreeHost(c->h_red); cudaFree(c->d_ord);
     cudaGetLastError(); // teardown is best effort (e.g. closing an IPC mapping whose exporter is already gone): never leave a stale error behind
     if (c->live_vecs > 0) { // vectors still point at this context: keep the struct and the stream until the last one goes
         c->dead = 1;
@@ -1218,6 +1218,9 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
     p.k0 = key[0]; p.k1 = key[1];
     p.rank = c->rank; p.nranks = c->nranks;
     p.init_rule = prm->initiator_rule; p.init_thr = prm->initiator_threshold;
+    p.ordered = prm->ordered != 0 && !is_int; // integer sums are exact in any order
+    if (p.ordered && (c->method != RIMU_ANNIHILATE_PARTITION || p.init_rule))
+        return fail(RIMU_ERR_INVALID, "ordered summation needs the partitioned method and no initiator rule");
     if (p.init_rule < 0 || p.init_rule > 3) return fail(RIMU_ERR_INVALID, "unknown initiator rule %d", p.init_rule);
     if (p.init_rule && prm->plain_h == 0 && !(p.init_thr >= 0.0)) return fail(RIMU_ERR_INVALID, "initiator threshold must be >= 0");
     if (p.init_rule && c->method != RIMU_ANNIHILATE_PARTITION)

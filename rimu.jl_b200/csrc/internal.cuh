@@ -133,6 +133,7 @@ struct rimu_ctx {
     char *d_ipc, *h_ipc;     // all-gather scratch for the IPC handles
     alignas(16) char sort_scratch[96];   // SortScratch of sort.cu (opaque here)
     double rec_per_parent;   // running estimate: records appended per parent (sizes the bucket count)
+    double *d_ord; u32 ord_cap; // per-warp partial walker numbers of an ordered merge (fixed-order reduction)
     int rcnt_clean;          // one rank: every fill counter of `part` is zero (the last merge cleared what it consumed)
     u32 ovf_nb; double ovf_expected; // the last bucket count that overflowed and the expected item count it overflowed at:
                              //   choose_buckets stays above it until the vector has shrunk (no flip-flop between a count

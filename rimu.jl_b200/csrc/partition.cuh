@@ -293,7 +293,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
         const double val = (double)vals[it.parent];
         const long long L = ham_num_offdiagonals<HK, B>(h, key);
         const bool exact = it.exact != 0;
-        const bool agg = !exact && L <= ACC_MAX;
+        const bool agg = !exact && L <= ACC_MAX && !p.ordered; // (pre-sums use shared atomics: their order is not reproducible)
         const u64 hkey = hash_bits(key);
         const u32 rlane = deposit_lane(p, false, val); // one parent per tile: one lane
         if (agg) { for (int c = threadIdx.x; c < L; c += SPAWN_NT) acc[c] = 0ull; __syncthreads(); }
@@ -413,9 +413,15 @@ template <u32 BITS> DEV u32 slot_hash(u64 k0, u64 k1) {
 template <u32 N> struct Log2 { static constexpr u32 value = 1 + Log2<N / 2>::value; };
 template <> struct Log2<1> { static constexpr u32 value = 0; };
 
-template <int HK, int W, class VT, int MODE, bool INIT = false>
+// ORD (Float64 steps, audit mode): order-deterministic summation.  The records of a bucket arrive in whatever order the
+// spawn kernels' counter atomics happened to hand out, and the hash-table placement adds duplicates with shared-memory
+// atomics -- both make the last bits of a Float64 sum differ from run to run.  With ORD the bucket's items are SORTED by
+// (address, value bits) with a bitonic network in shared memory (the hash table is not used at all), every address is summed
+// by one thread in that order, and the walker number is reduced in a fixed order as well: the step's result is a pure
+// function of its inputs, bit for bit.  ~10x slower than the hash placement; selected by rimu_step_params.ordered.
+template <int HK, int W, class VT, int MODE, bool INIT = false, bool ORD = false>
 __global__ void __launch_bounds__(PART_NT, PART_MINB)
-merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st) {
+merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st, double *ord_partials = nullptr) {
     typedef typename BitsT<W>::type B;
     constexpr bool is_int = std::is_integral<VT>::value;
     constexpr int CAP = PartCap<W>::value;
@@ -425,7 +431,8 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     constexpr u32 TMASK = 2 * CAP - 1;
     constexpr u32 WLIST = 2 * CAP / NW;  // owner-table entries per warp once the table is dead (>= R * 32 items of a warp)
     constexpr u32 NIL = 0xffffffffu;
-    constexpr u32 NOPARENT = 0x7fffu, IFLAG = 0x8000u; // pidx: parent item index | "initiator lane is non-zero" flag
+    constexpr u32 NOPARENT = 0x3fffu, OWNFLAG = 0x4000u, IFLAG = 0x8000u; // pidx: parent item index | (ORD) "sums its address" | "initiator lane is non-zero"
+    static_assert(CAP < (int)NOPARENT, "item indices must fit below the flags");
     static_assert((2 * CAP & (2 * CAP - 1)) == 0, "table size must be a power of two");
     static_assert(WLIST >= (u32)R * 32, "a warp's list region must hold all of its items");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -442,6 +449,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     __shared__ u64 s_base;
     __shared__ u32 s_arrive;
     __shared__ u32 s_nlist;
+    __shared__ double s_wnorm[NW]; // ORD: per-warp walker number of the current bucket
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
     u32 *wlist = owner + wid * WLIST;
@@ -538,7 +546,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         max_fill = max(max_fill, n);
         nrec_sum += nrec;
         if (sub_over || n > (u32)CAP) { // uniform over the CTA: the host retries with more buckets
-            if (tid == 0) { st->overflow_table = 1; dst.seg_len[b] = 0; dst.seg_start[b] = 0; }
+            if (tid == 0) { st->overflow_table = 1; dst.seg_len[b] = 0; dst.seg_start[b] = 0; if constexpr (ORD) ord_partials[b] = 0.0; }
             if ((u32)tid < nsrc) s_cnt[nn][tid] = pending_cnt;
             if (meta_thread) { s_np[nn] = pending_np; s_p0[nn] = pending_p0; }
             __syncthreads();
@@ -632,12 +640,66 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 svals[i] = cv.b;
                 valid |= 1u << r;
                 ndep++;
-            }
+            } else if constexpr (ORD) svals[i] = 0ull; // (the sort recognises items without a deposit by their zero value)
         }
         if constexpr (!initm) cp_async_wait_all();
         __syncthreads();
-        // ---- placement: claim a slot (CAS) or annihilate into the item that owns this address
         u32 own = 0;
+        if constexpr (ORD) {
+            // ---- ordered annihilation: sort the item indices by (address, value bits), sum every run in that order
+            u32 *idx = owner;
+            u32 P2 = 2;
+            while (P2 < n) P2 <<= 1; // uniform
+            for (u32 s = tid; s < P2; s += PART_NT) idx[s] = (s < n && svals[s] != 0ull) ? s : NIL;
+            __syncthreads();
+            auto same_key = [&](u32 a, u32 b) {
+                bool eq = skeys[a * W] == skeys[b * W];
+                if constexpr (W == 2) eq = eq && skeys[a * W + 1] == skeys[b * W + 1];
+                return eq;
+            };
+            auto less = [&](u32 a, u32 b) { // strict total order; NIL sorts last
+                if (a == NIL) return false;
+                if (b == NIL) return true;
+                if constexpr (W == 2) { if (skeys[a * 2 + 1] != skeys[b * 2 + 1]) return skeys[a * 2 + 1] < skeys[b * 2 + 1]; }
+                if (skeys[a * W] != skeys[b * W]) return skeys[a * W] < skeys[b * W];
+                if (svals[a] != svals[b]) return svals[a] < svals[b];
+                return a < b;
+            };
+            for (u32 k = 2; k <= P2; k <<= 1)
+                for (u32 j = k >> 1; j > 0; j >>= 1) {
+                    for (u32 t = tid; t < P2 / 2; t += PART_NT) {
+                        const u32 i1 = ((t & ~(j - 1u)) << 1) | (t & (j - 1u)), i2 = i1 + j;
+                        const bool up = (i1 & k) == 0u;
+                        const u32 a = idx[i1], b2 = idx[i2];
+                        if (less(b2, a) == up) { idx[i1] = b2; idx[i2] = a; }
+                    }
+                    __syncthreads();
+                }
+            for (u32 s = tid; s < P2; s += PART_NT) {
+                const u32 a = idx[s];
+                if (a == NIL) continue;
+                if (s > 0 && same_key(idx[s - 1], a)) continue; // not the head of its run
+                union { u64 b; VT v; } acc; acc.v = (VT)0;
+                u32 pi = NOPARENT;
+                for (u32 e = s; e < P2; e++) {
+                    const u32 m = idx[e];
+                    if (m == NIL || !same_key(m, a)) break;
+                    union { u64 b; VT v; } cv; cv.b = svals[m];
+                    acc.v += cv.v;
+                    if (m < np) pi = m;
+                }
+                svals[a] = acc.b;
+                pidx[a] = (unsigned short)(pi | OWNFLAG);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r >= rmax) break;
+                if (!((valid >> r) & 1u)) continue;
+                if (pidx[item_of(r)] & OWNFLAG) own |= 1u << r;
+            }
+        } else {
+        // ---- placement: claim a slot (CAS) or annihilate into the item that owns this address
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (r >= rmax) break;
@@ -672,6 +734,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 s = (s + 1) & TMASK;
             }
         }
+        } // !ORD
         __syncthreads(); // every sum is complete; the owner table is dead from here on (reused as per-warp lists)
         // ---- from_initiator_value (initiators.jl:136-138,177-179,201-207; pdworkingmemory.jl:268-270): collapse the lanes
         if (initm) {
@@ -727,6 +790,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         }
         // ---- drop zeros, count survivors
         u32 keep = 0, cnt = 0;
+        double bnorm = 0.0; // ORD: this thread's share of the bucket's walker number
 #pragma unroll
         for (int r = 0; r < R; r++) {
             if (r >= rmax) break;
@@ -736,7 +800,13 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             const VT v = cv.v;
             if (v == (VT)0) continue; // exact zeros are deleted (pdworkingmemory.jl:25-29); so are compressed-away entries
             keep |= 1u << r; cnt++;
-            if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v); else norm1 += fabs((double)v);
+            if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v);
+            else if (ORD) bnorm += fabs((double)v);
+            else norm1 += fabs((double)v);
+        }
+        if constexpr (ORD) { // the bucket's walker number through a fixed tree: lanes, then warps in order -> one entry per BUCKET
+            const double wsum = warp_sum(bnorm);
+            if (lane == 0) s_wnorm[wid] = wsum;
         }
         if (!compressed && !initm) len_before += cnt;
         // ---- survivor scan: warp totals meet in shared memory; the LAST warp to arrive reserves the segment with the one
@@ -760,6 +830,9 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             }
         }
         __syncthreads();
+        if constexpr (ORD) {
+            if (tid == 0) { double s = 0.0; for (int w = 0; w < NW; w++) s += s_wnorm[w]; ord_partials[b] = s; }
+        }
         u32 wbase = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) { u32 t = s_warp[w]; if (w < wid) wbase += t; total += t; }
@@ -822,13 +895,20 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         stat_add(&st->inorm1, inorm1);
         if (MODE == 0) { stat_add(&st->iclones, (i64)clones); stat_add(&st->ideaths, (i64)deaths); stat_add(&st->izombies, (i64)zombies); }
     } else {
-        stat_add(&st->norm1, norm1);
+        if constexpr (!ORD) stat_add(&st->norm1, norm1); // (ORD: one partial per bucket, summed in bucket order afterwards)
         if (MODE == 0) { stat_add(&st->clones, clones); stat_add(&st->deaths, deaths); stat_add(&st->zombies, zombies); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) max_fill = max(max_fill, __shfl_xor_sync(0xffffffffu, max_fill, o));
     if (lane == 0) atomicMax(&st->max_fill, (unsigned long long)max_fill);
     if (tid == 0 && nrec_sum) atomicAdd(&st->records, (u64)nrec_sum);
+}
+
+// sum of the per-warp partial walker numbers of an ordered merge, in index order (one thread: the order IS the point)
+static __global__ void ordered_sum_kernel(const double *__restrict__ partials, u32 n, double *out) {
+    double s = 0.0;
+    for (u32 i = 0; i < n; i++) s += partials[i];
+    *out = s;
 }
 
 // ---------------------------------------------------------------- dot(::FrozenDVec, v): few keys against a big vector

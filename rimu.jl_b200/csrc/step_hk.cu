@@ -94,6 +94,27 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     SegSrc ss{src->keys, (const u64 *)src->vals, seg ? src->seg_start : nullptr, seg ? src->seg_len : nullptr, src_diag};
     SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, dst->diag};
     const int mgrid = (int)(nb < c->merge_grid_cap ? nb : c->merge_grid_cap);
+    if constexpr (!std::is_integral<VT>::value) {
+        if (p.ordered) { // audit mode: sorted, order-deterministic annihilation + fixed-order walker number
+            static bool ord_attr[HK_COUNT][3] = {};
+            if (!ord_attr[HK][W]) {
+                CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
+                ord_attr[HK][W] = true;
+            }
+            const u32 nparts = nb; // one partial walker number per bucket: independent of the launch geometry
+            if (c->ord_cap < nparts) {
+                cudaFree(c->d_ord); c->d_ord = nullptr; c->ord_cap = 0;
+                CUDA_TRY(rimu_malloc(&c->d_ord, (size_t)nparts * sizeof(double)));
+                c->ord_cap = nparts;
+            }
+            merge_kernel<HK, W, VT, 0, false, true><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats, c->d_ord);
+            ordered_sum_kernel<<<1, 1, 0, c->stream>>>(c->d_ord, nparts, &c->d_stats->norm1);
+            CUDA_TRY(cudaGetLastError());
+            c->launches += 2;
+            CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+            return 0;
+        }
+    }
     if (p.init_rule) merge_kernel<HK, W, VT, 0, true><<<mgrid, PART_NT, part_smem_bytes(W) + smem_init, c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     else merge_kernel<HK, W, VT, 0, false><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     CUDA_TRY(cudaGetLastError());

@@ -14,6 +14,7 @@ struct StepDev {
     int rank, nranks;
     int init_rule;      // RIMU_INITIATOR_*: 0 = no initiator lanes
     double init_thr;
+    int ordered;        // order-deterministic Float64 summation (audit mode)
 };
 
 #if defined(__CUDACC__) || defined(RIMU_HOST_EMULATION)

@@ -241,14 +241,15 @@ class WorkingMemory:
     """working_memory(v) (Interfaces/dictvectors.jl:87, pdworkingmemory.jl:295): the context's
     HBM working table plus the Philox stream position (seed, call counter)."""
 
-    def __init__(self, v: GPUDVec, seed: int = 0):
+    def __init__(self, v: GPUDVec, seed: int = 0, ordered: bool = False):
         self.ctx, self.style, self.seed, self.counter = v.ctx, v.style, int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+        self.ordered = bool(ordered)  # order-deterministic Float64 summation (rimu_step_params.ordered): bit-reproducible steps
         self.initiator = v.initiator  # PDWorkingMemory(t).initiator = t.initiator (pdworkingmemory.jl:104-108)
         self.last_stats: _lib.StepStats | None = None
 
 
-def working_memory(v: GPUDVec, seed: int = 0) -> WorkingMemory:
-    return WorkingMemory(v, seed)
+def working_memory(v: GPUDVec, seed: int = 0, ordered: bool = False) -> WorkingMemory:
+    return WorkingMemory(v, seed, ordered)
 
 
 def walkernumber_and_length(v: GPUDVec):
@@ -272,6 +273,7 @@ def apply_operator(wm: WorkingMemory, target: GPUDVec, source: GPUDVec, op, boos
         raise TypeError("operator must be one of the device Hamiltonians or a FirstOrderTransitionOperator "
                         "(custom Julia/Python operators cannot run on the GPU; there is no CPU fallback)")
     p.boost, p.seed, p.step, p.table_slots = float(boost), wm.seed, wm.counter, int(table_slots)
+    p.ordered = int(getattr(wm, "ordered", False))
     rule = getattr(wm, "initiator", None)
     if rule is not None and rule.rule_id:
         p.initiator_rule, p.initiator_threshold = rule.rule_id, float(rule.threshold)

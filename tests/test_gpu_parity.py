@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
 Integer/index work must be bit-exact; Float64 within 1e-12 relative (north_star tolerance)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -438,3 +439,64 @@ def test_vectors_may_outlive_their_context(built):
     y = x.similar()
     R.mul(y, H, x)
     assert math.isclose(y.norm(1), sum(abs(val) for val in y.download()[1]))
+
+
+# --------------------------------------------------------------------------- ordered (order-deterministic) Float64 steps
+@pytest.mark.parametrize("name", ["mom1d_bose", "rs_bose_2d", "rs_f2c_4x4", "real1d_w2"])
+def test_ordered_semistochastic_steps_match_the_oracle_tightly(built, name):
+    """rimu_step_params.ordered: every address is summed in sorted (address, value) order.  The oracle sums in its own
+    (hash-map insertion) order, so the comparison is still a Float64 one -- but at 1e-12 relative, without feeding the device
+    values back into the oracle between steps (the plain mode needs that, because its summation order varies)."""
+    import rimu_b200 as R
+    oh, ph = oracle_ham(name), product_ham(name)
+    seed, dtau = 31, 0.01
+    style = R.IsDynamicSemistochastic()
+    v = R.GPUDVec([(ph.address, 40.0)], style=style)
+    wm = R.working_memory(v, seed=seed, ordered=True)
+    ok, ov = np.array([oh.start_key], dtype=np.uint64).reshape(1, -1), np.array([40.0])
+    shift = oh.diagonal_element(oh.start_key)
+    for step in range(6):
+        out = v.similar()
+        R.apply_operator(wm, out, v, R.FirstOrderTransitionOperator(ph, shift + 1.0, dtau))
+        v = out
+        ok, ov, st = oh.step(orc.make_params(orc.STYLE_SEMISTOCHASTIC, shift=shift + 1.0, dtau=dtau, compress_threshold=1.0,
+                                             key=orc.step_key(seed, step)), ok, ov)
+        gk, gv = v.download_sorted()
+        assert np.array_equal(gk, ok), (name, step)
+        assert np.allclose(gv, ov, rtol=1e-12, atol=0), (name, step, np.abs(gv - ov).max())
+        assert math.isclose(wm.last_stats.norm1, st.norm1, rel_tol=1e-12)
+
+
+def test_ordered_steps_are_bit_reproducible(built):
+    """The same three steps on ~3e5 determinants, run twice on fresh contexts whose merge grids differ (so that buckets meet
+    different CTAs and the spawn kernels' appends interleave differently): with ordered summation the vectors and the walker
+    numbers are identical bit for bit."""
+    import rimu_b200 as R
+    from tests.test_gpu_energies import _grow
+    ph = product_ham("mom1d_bose_20")
+    big = _grow(R, ph, 300_000, R.IsDynamicSemistochastic())
+    keys, vals = big.download()
+    shift = R.diagonal_element(ph, ph.address)
+    runs = []
+    for grid in ("0", "37"):
+        if grid != "0":
+            os.environ["RIMU_B200_MERGE_GRID"] = grid
+        try:
+            ctx = R.Context(1)
+        finally:
+            os.environ.pop("RIMU_B200_MERGE_GRID", None)
+        v = R.GPUDVec(style=R.IsDynamicSemistochastic(), address_type=big.address_type, ctx=ctx)
+        v.assign(keys, vals)
+        wm = R.working_memory(v, seed=5, ordered=True)
+        norms = []
+        for _ in range(3):
+            out = v.similar()
+            R.apply_operator(wm, out, v, R.FirstOrderTransitionOperator(ph, shift, 1e-3))
+            v = out
+            norms.append(wm.last_stats.norm1)
+        runs.append(v.download_sorted() + (norms,))
+        del v, out, wm
+        ctx.close()
+    (k0, v0, n0), (k1, v1, n1) = runs
+    assert np.array_equal(k0, k1) and np.array_equal(v0.view(np.uint64), v1.view(np.uint64))
+    assert n0 == n1

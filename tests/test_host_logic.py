@@ -162,7 +162,7 @@ def test_initiator_rule_keywords(built):
     assert [r.rule_id for r in (R.NonInitiator(), R.Initiator(), R.SimpleInitiator(), R.CoherentInitiator())] == [0, 1, 2, 3]
     assert (_lib.lib().rimu_sizeof_step_params(), _lib.lib().rimu_sizeof_step_stats()) == (C.sizeof(_lib.StepParams), C.sizeof(_lib.StepStats))
     names = [f for f, _ in _lib.StepParams._fields_]
-    assert names[-3:] == ["initiator_rule", "reserved_", "initiator_threshold"]
+    assert names[-3:] == ["initiator_rule", "ordered", "initiator_threshold"]
 
     class FakeHam:
         pass
