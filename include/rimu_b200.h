@@ -21,6 +21,10 @@
  * bit is kept so that the all-ones word pattern can mark empty table slots).
  * FermiFS{N,M}: bit m-1 <-> mode m (bitstring.jl:713-723).  CompositeFS of two FermiFS
  * (FermiFS2C): component c occupies bits [c*M, (c+1)*M), 2M <= 64.
+ * General CompositeFS (multicomponent.jl:10-19; RIMU_ADDR_COMPOSITE, HubbardRealSpace): up to RIMU_MAX_COMPONENTS
+ * BoseFS / FermiFS components over the same M modes, packed side by side from the low bits: component c occupies
+ * bits [off_c, off_c + b_c) with b_c = N_c + M - 1 (BoseFS layout) or M (FermiFS layout) and off_c = b_0 + ... + b_{c-1};
+ * at most 127 bits in total, W = ceil((bits + 1) / 64).  (Julia keeps one BitString per component; the shim concatenates.)
  * Julia's BitString stores chunks most-significant first (bitstring.jl:72-75); the shim
  * reverses chunk order and widens sub-64-bit chunk types.
  * Values are one 8-byte lane: double (RIMU_VAL_F64) or int64 (RIMU_VAL_I64).
@@ -36,6 +40,7 @@ extern "C" {
 
 #define RIMU_MAX_MODES 128
 #define RIMU_MAX_TABLE_MODES 64
+#define RIMU_MAX_COMPONENTS 4
 
 /* status codes */
 enum {
@@ -51,7 +56,8 @@ enum {
     RIMU_ERR_NO_DEVICE = -4
 };
 
-enum { RIMU_ADDR_BOSE = 0, RIMU_ADDR_FERMI = 1, RIMU_ADDR_FERMI2C = 2 };
+enum { RIMU_ADDR_BOSE = 0, RIMU_ADDR_FERMI = 1, RIMU_ADDR_FERMI2C = 2,
+       RIMU_ADDR_COMPOSITE = 3 /* CompositeFS of 2..RIMU_MAX_COMPONENTS BoseFS / FermiFS components (HubbardRealSpace) */ };
 enum { RIMU_HUBBARD_REAL_1D = 0, RIMU_HUBBARD_MOM_1D = 1, RIMU_HUBBARD_REAL_SPACE = 2, RIMU_TRANSCORRELATED_1D = 3,
        RIMU_HUBBARD_REAL_1D_EP = 4,        /* Hamiltonians/HubbardReal1DEP.jl:47-92: potential[] = eps_i, bosons */
        RIMU_EXTENDED_HUBBARD_REAL_1D = 5,  /* Hamiltonians/ExtendedHubbardReal1D.jl:30-135: v = neighbour interaction, bosons */
@@ -86,7 +92,7 @@ typedef struct {
     int32_t model;          /* RIMU_HUBBARD_* / RIMU_TRANSCORRELATED_1D */
     int32_t addr_kind;      /* RIMU_ADDR_* */
     int32_t num_modes;      /* M (per component) */
-    int32_t num_components; /* 1 or 2 */
+    int32_t num_components; /* 1 or 2; 2..RIMU_MAX_COMPONENTS for RIMU_ADDR_COMPOSITE */
     int32_t num_particles[2];
     int32_t ndim;           /* HubbardRealSpace: CubicGrid{D} (geometry.jl:45-54) */
     int32_t dims[3];
@@ -102,6 +108,13 @@ typedef struct {
     double ws[RIMU_MAX_TABLE_MODES];
     double us[RIMU_MAX_TABLE_MODES];
     double potential[2 * RIMU_MAX_MODES]; /* potential[c*M + site] */
+    /* RIMU_ADDR_COMPOSITE only (HubbardRealSpace{C} over a general CompositeFS, HubbardRealSpace.jl:18-75,166-241,340-391):
+     * per-component address kind and particle number, hopping strengths t[c] and the symmetric interaction matrix
+     * u[i + C*j] (column major, C = num_components); num_particles / t_comp / u_mat above are ignored for this kind */
+    int32_t comp_kind[RIMU_MAX_COMPONENTS];      /* RIMU_ADDR_BOSE or RIMU_ADDR_FERMI */
+    int32_t comp_particles[RIMU_MAX_COMPONENTS];
+    double comp_t[RIMU_MAX_COMPONENTS];
+    double comp_u[RIMU_MAX_COMPONENTS * RIMU_MAX_COMPONENTS];
 } rimu_ham_desc;
 
 /* One FCIQMC step = Interfaces.apply_operator!(wm, target, source, op, boost)

@@ -60,7 +60,15 @@ end
 # bit m-1 <-> mode m (bitstring.jl:713-723); two-component FermiFS -- component c in bits [c*M, (c+1)*M).
 words(::Type{<:BoseFS{N,M}}) where {N,M} = cld(N + M, 64)          # B + 1 bits: one spare bit marks empty table slots
 words(::Type{<:FermiFS{N,M}}) where {N,M} = cld(M + 1, 64)
-words(::Type{<:CompositeFS{2,N,M}}) where {N,M} = cld(2M, 64)
+# CompositeFS: two FermiFS components of at most 32 modes are the one-word FermiFS2C layout (RIMU_ADDR_FERMI2C); every other
+# CompositeFS (bosonic or mixed components, 3-4 components, wider fermions) is the general packed layout RIMU_ADDR_COMPOSITE:
+# the components' bit strings side by side from the low bits (multicomponent.jl:10-34 keeps one BitString per component)
+comp_bits(::Type{<:BoseFS{N,M}}) where {N,M} = N + M - 1
+comp_bits(::Type{<:FermiFS{N,M}}) where {N,M} = M
+comp_types(::Type{A}) where {A<:CompositeFS} = fieldtypes(fieldtype(A, :components))
+is_fermi2c(::Type{A}) where {C,N,M,A<:CompositeFS{C,N,M}} = C == 2 && M <= 32 && all(T -> T <: FermiFS, comp_types(A))
+words(::Type{A}) where {C,N,M,A<:CompositeFS{C,N,M}} =
+    is_fermi2c(A) ? cld(2M, 64) : cld(sum(comp_bits, comp_types(A)) + 1, 64)
 words(a::AbstractFockAddress) = words(typeof(a))
 
 function set_bit!(key::Vector{UInt64}, pos::Int)
@@ -88,13 +96,25 @@ function to_key(a::FermiFS{N,M}) where {N,M}
     end
     return key
 end
-function to_key(a::CompositeFS{2,N,M}) where {N,M}
+function to_key(a::CompositeFS{C,N,M}) where {C,N,M}
     key = zeros(UInt64, words(typeof(a)))
-    for (c, comp) in enumerate(a.components)
-        comp isa FermiFS || throw(ArgumentError("only two-component FermiFS addresses have a device layout"))
-        for (m, n) in enumerate(onr(comp))
-            n == 1 && set_bit!(key, (c - 1) * M + m - 1)
+    base = 0
+    for comp in a.components
+        if comp isa FermiFS
+            for (m, n) in enumerate(onr(comp))
+                n == 1 && set_bit!(key, base + m - 1)
+            end
+        else
+            pos = base
+            for n in onr(comp)
+                for _ in 1:n
+                    set_bit!(key, pos)
+                    pos += 1
+                end
+                pos += 1
+            end
         end
+        base += comp_bits(typeof(comp))
     end
     return key
 end
@@ -114,11 +134,29 @@ end
 function from_key(::Type{A}, key::AbstractVector{UInt64}) where {N,M,A<:FermiFS{N,M}}
     return A(ntuple(m -> Int(get_bit(key, m - 1)), M))
 end
-function from_key(::Type{A}, key::AbstractVector{UInt64}) where {N,M,A<:CompositeFS{2,N,M}}
-    T1, T2 = fieldtypes(fieldtype(A, :components))
-    c1 = T1(ntuple(m -> Int(get_bit(key, m - 1)), M))
-    c2 = T2(ntuple(m -> Int(get_bit(key, M + m - 1)), M))
-    return A((c1, c2))
+function component_from_key(::Type{T}, key::AbstractVector{UInt64}, base::Int) where {N,M,T<:FermiFS{N,M}}
+    return T(ntuple(m -> Int(get_bit(key, base + m - 1)), M))
+end
+function component_from_key(::Type{T}, key::AbstractVector{UInt64}, base::Int) where {N,M,T<:BoseFS{N,M}}
+    occ = zeros(Int, M)
+    pos = 0
+    for m in 1:M
+        while pos < N + M - 1 && get_bit(key, base + pos)
+            occ[m] += 1
+            pos += 1
+        end
+        pos += 1
+    end
+    return T(Tuple(occ))
+end
+function from_key(::Type{A}, key::AbstractVector{UInt64}) where {C,N,M,A<:CompositeFS{C,N,M}}
+    base = 0
+    comps = map(comp_types(A)) do T
+        c = component_from_key(T, key, base)
+        base += comp_bits(T)
+        c
+    end
+    return A(comps)
 end
 
 # ---------------------------------------------------------------------------------------------------------------- context
@@ -171,7 +209,7 @@ owner_rank(a::AbstractFockAddress, nranks::Integer) =
     Int(ccall((:rimu_addr_owner, LIB), Cint, (Ptr{UInt64}, Cint, Cint), to_key(a), words(a), nranks))
 
 # ---------------------------------------------------------------------------------------------------------------- Hamiltonians
-const MAX_MODES, MAX_TABLE_MODES = 128, 64
+const MAX_MODES, MAX_TABLE_MODES, MAX_COMPONENTS = 128, 64, 4
 
 struct HamDesc                        # == rimu_ham_desc (include/rimu_b200.h); asserted against rimu_sizeof_ham_desc()
     model::Int32
@@ -195,6 +233,10 @@ struct HamDesc                        # == rimu_ham_desc (include/rimu_b200.h); 
     ws::NTuple{64,Float64}
     us::NTuple{64,Float64}
     potential::NTuple{256,Float64}
+    comp_kind::NTuple{4,Int32}            # RIMU_ADDR_COMPOSITE: kind, particle number, t[c], u[i + C*j] per component
+    comp_particles::NTuple{4,Int32}
+    comp_t::NTuple{4,Float64}
+    comp_u::NTuple{16,Float64}
 end
 
 pad(xs, n) = ntuple(i -> i <= length(xs) ? Float64(xs[i]) : 0.0, n)
@@ -202,19 +244,27 @@ pad3(xs, fill) = ntuple(i -> i <= length(xs) ? Int32(xs[i]) : Int32(fill), 3)
 
 addr_kind(::BoseFS) = Int32(0)
 addr_kind(::FermiFS) = Int32(1)
-addr_kind(::CompositeFS{2}) = Int32(2)
+addr_kind(a::CompositeFS) = is_fermi2c(typeof(a)) ? Int32(2) : Int32(3)
 particles(a::SingleComponentFockAddress) = (Int32(num_particles(a)), Int32(0))
-particles(a::CompositeFS{2}) = (Int32(num_particles(a.components[1])), Int32(num_particles(a.components[2])))
+particles(a::CompositeFS) = is_fermi2c(typeof(a)) ?
+    (Int32(num_particles(a.components[1])), Int32(num_particles(a.components[2]))) : (Int32(0), Int32(0))
+pad4(xs) = ntuple(i -> i <= length(xs) ? Int32(xs[i]) : Int32(0), 4)
+comp_kinds(a::AbstractFockAddress) = pad4(())
+comp_kinds(a::CompositeFS) = pad4([c isa BoseFS ? 0 : 1 for c in a.components])
+comp_particles(a::AbstractFockAddress) = pad4(())
+comp_particles(a::CompositeFS) = pad4([num_particles(c) for c in a.components])
 components(a::SingleComponentFockAddress) = Int32(1)
 components(a::CompositeFS{C}) where {C} = Int32(C)
 
 function base_desc(model, a; ndim=0, dims=(), fold=(), cutoff=0, three_body=false, has_potential=false, bc=0,
-                   u=0.0, t=0.0, v=0.0, t_comp=(0.0, 0.0), u_mat=(0.0, 0.0, 0.0, 0.0), kes=(), ws=(), us=(), potential=())
+                   u=0.0, t=0.0, v=0.0, t_comp=(0.0, 0.0), u_mat=(0.0, 0.0, 0.0, 0.0), kes=(), ws=(), us=(), potential=(),
+                   comp_t=(), comp_u=())
     num_modes(a) <= MAX_MODES || throw(ArgumentError("at most $MAX_MODES modes"))
     return HamDesc(Int32(model), addr_kind(a), Int32(num_modes(a)), components(a), particles(a), Int32(ndim),
                    pad3(dims, 1), pad3(fold, 0), Int32(cutoff), Int32(three_body), Int32(has_potential), Int32(bc),
                    Float64(u), Float64(t), Float64(v), pad(t_comp, 2), pad(u_mat, 4),
-                   pad(kes, MAX_TABLE_MODES), pad(ws, MAX_TABLE_MODES), pad(us, MAX_TABLE_MODES), pad(potential, 2 * MAX_MODES))
+                   pad(kes, MAX_TABLE_MODES), pad(ws, MAX_TABLE_MODES), pad(us, MAX_TABLE_MODES), pad(potential, 2 * MAX_MODES),
+                   comp_kinds(a), comp_particles(a), pad(comp_t, MAX_COMPONENTS), pad(comp_u, MAX_COMPONENTS^2))
 end
 
 const BOUNDARY = Dict(:periodic => 0, :hard_wall => 1, :twisted => 2)
@@ -239,11 +289,17 @@ function desc(h::HubbardRealSpace)                                              
     g = h.geometry
     dims = size(g)
     C = Int(components(h.address))
-    C <= 2 || throw(ArgumentError("at most two components have a device layout"))
+    C <= MAX_COMPONENTS || throw(ArgumentError("at most $MAX_COMPONENTS components have a device layout"))
+    pot = h.potential === nothing ? () : vec(h.potential)               # M x C column major = potential[c*M + site]
+    common = (; ndim=length(dims), dims=dims, fold=Int.(collect(Rimu.Hamiltonians.fold(g))),
+              has_potential=h.potential !== nothing, potential=pot)
+    if h.address isa CompositeFS && !is_fermi2c(typeof(h.address))       # general CompositeFS: u[i + C*j], t[c]
+        sum(comp_bits, comp_types(typeof(h.address))) <= 127 || throw(ArgumentError("addresses beyond 127 bits have no device layout"))
+        umat = h.u === nothing ? () : vec(collect(h.u))
+        return base_desc(2, h.address; common..., comp_t=Tuple(h.t), comp_u=umat)
+    end
     umat = h.u === nothing ? (0.0, 0.0, 0.0, 0.0) : (C == 1 ? (h.u[1, 1], 0.0, 0.0, 0.0) : (h.u[1, 1], h.u[2, 1], h.u[1, 2], h.u[2, 2]))
-    pot = h.potential === nothing ? () : vec(permutedims(h.potential))   # potential[c*M + site]
-    return base_desc(2, h.address; ndim=length(dims), dims=dims, fold=Int.(collect(Rimu.Hamiltonians.fold(g))),
-                     t_comp=Tuple(h.t), u_mat=umat, has_potential=h.potential !== nothing, potential=pot)
+    return base_desc(2, h.address; common..., t_comp=Tuple(h.t), u_mat=umat)
 end
 function desc(h::Transcorrelated1D)                                                                 # Transcorrelated1D.jl:55-89
     h.v_ho == 0 || throw(ArgumentError("Transcorrelated1D with v_ho != 0 has no device path"))

@@ -46,7 +46,9 @@
 
 #define ORC_MAXM 128
 
-enum { ORC_BOSE = 0, ORC_FERMI = 1, ORC_FERMI2C = 2 };
+#define ORC_MAXC 4
+enum { ORC_BOSE = 0, ORC_FERMI = 1, ORC_FERMI2C = 2,
+       ORC_COMPOSITE = 3 }; /* CompositeFS of 2..ORC_MAXC BoseFS / FermiFS components (multicomponent.jl:10-34), HubbardRealSpace */
 enum { ORC_HUBBARD_REAL_1D = 0, ORC_HUBBARD_MOM_1D = 1, ORC_HUBBARD_REAL_SPACE = 2,
        ORC_TRANSCORRELATED_1D = 3, ORC_HUBBARD_REAL_1D_EP = 4, ORC_EXTENDED_HUBBARD_REAL_1D = 5,
        ORC_EXTENDED_HUBBARD_MOM_1D = 6, /* ExtendedHubbardMom1D.jl:37-117 (bosons): ws[q] = cos(q*2pi/M), us[d] = cos(d*(2pi/M)) */
@@ -65,9 +67,13 @@ typedef struct {
     double tc[2], umat[4]; /* umat[i + 2*j] = u[i,j], column major like Julia */
     double ks[ORC_MAXM], kes[ORC_MAXM], ws[ORC_MAXM], us[ORC_MAXM];
     double pot[2 * ORC_MAXM]; /* pot[c*M + site] */
+    /* ORC_COMPOSITE: kind (ORC_BOSE / ORC_FERMI) and particle number of every component, t[c], u[i + ncomp*j] */
+    int32_t ckind[ORC_MAXC], Nc[ORC_MAXC];
+    double tcs[ORC_MAXC], umats[ORC_MAXC * ORC_MAXC];
 } orc_ham;
 
-typedef struct { int n[2][ORC_MAXM]; } orc_onr;
+typedef struct { int n[ORC_MAXC][ORC_MAXM]; } orc_onr;
+static void onr_copy(const orc_ham *h, orc_onr *dst, const orc_onr *src) { memcpy(dst, src, sizeof(int) * ORC_MAXM * h->ncomp); }
 typedef struct { int len; int occ[ORC_MAXM]; int mode[ORC_MAXM]; } orc_map;
 
 /* ------------------------------------------------------------------ helpers */
@@ -126,13 +132,29 @@ static double excite(int kind_is_bose, int *n, int M, const int *cre, const int 
  * Device interchange layout: W little-endian uint64 words, word 0 least significant.
  * BoseFS (bitstring.jl:464-472): mode 1 in the lowest bits, n ones then a 0 separator.
  * FermiFS (bitstring.jl:713-723): bit m-1 <-> mode m.
- * Two fermion components: component c occupies bits [c*M, (c+1)*M). */
+ * Two fermion components: component c occupies bits [c*M, (c+1)*M).
+ * General CompositeFS: the components' bit strings side by side from the low bits (BoseFS: N_c + M - 1 bits, FermiFS: M). */
 static void setbit(uint64_t *w, int pos) { w[pos >> 6] |= (uint64_t)1 << (pos & 63); }
 static int getbit(const uint64_t *w, int pos) { return (int)((w[pos >> 6] >> (pos & 63)) & 1); }
 
 void orc_pack(const orc_ham *h, const orc_onr *o, uint64_t *w) {
     for (int j = 0; j < h->words; j++) w[j] = 0;
-    if (h->addr_kind == ORC_BOSE) {
+    if (h->addr_kind == ORC_COMPOSITE) {
+        int base = 0;
+        for (int c = 0; c < h->ncomp; c++) {
+            if (h->ckind[c] == ORC_BOSE) {
+                int pos = base;
+                for (int m = 0; m < h->M; m++) {
+                    for (int q = 0; q < o->n[c][m]; q++) setbit(w, pos++);
+                    pos++;
+                }
+                base += h->Nc[c] + h->M - 1;
+            } else {
+                for (int m = 0; m < h->M; m++) if (o->n[c][m]) setbit(w, base + m);
+                base += h->M;
+            }
+        }
+    } else if (h->addr_kind == ORC_BOSE) {
         int pos = 0;
         for (int m = 0; m < h->M; m++) {
             for (int q = 0; q < o->n[0][m]; q++) setbit(w, pos++);
@@ -146,8 +168,23 @@ void orc_pack(const orc_ham *h, const orc_onr *o, uint64_t *w) {
 }
 
 void orc_unpack(const orc_ham *h, const uint64_t *w, orc_onr *o) {
-    memset(o, 0, sizeof(*o));
-    if (h->addr_kind == ORC_BOSE) {
+    memset(o, 0, sizeof(int) * ORC_MAXM * h->ncomp);
+    if (h->addr_kind == ORC_COMPOSITE) {
+        int base = 0;
+        for (int c = 0; c < h->ncomp; c++) {
+            if (h->ckind[c] == ORC_BOSE) {
+                int B = h->Nc[c] + h->M - 1, mode = 0;
+                for (int pos = 0; pos < B; pos++) {
+                    if (getbit(w, base + pos)) o->n[c][mode]++;
+                    else mode++;
+                }
+                base += B;
+            } else {
+                for (int m = 0; m < h->M; m++) o->n[c][m] = getbit(w, base + m);
+                base += h->M;
+            }
+        }
+    } else if (h->addr_kind == ORC_BOSE) {
         int B = h->N[0] + h->M - 1, mode = 0;
         for (int pos = 0; pos < B; pos++) {
             if (getbit(w, pos)) o->n[0][mode]++;
@@ -296,6 +333,35 @@ double orc_diagonal_onr(const orc_ham *h, const orc_onr *o) {
     case ORC_HUBBARD_REAL_SPACE: { /* HubbardRealSpace.jl:18-75,90-106,279-293 */
         double interaction = 0.0;
         int C = h->ncomp;
+        if (h->addr_kind == ORC_COMPOSITE) {
+            /* local_interaction(::CompositeFS, u) = _interactions(components, u) (:18-75), recursive:
+             *   _interactions((a, as...), m) = self(a, m[1,1]) + _interaction_col(a, as, m[2:N,1]) + _interactions(as, m[2:N,2:N])
+             *   _interaction_col(a, (b, bs...), (u, us...)) = u * dot(occupied_modes(a), occupied_modes(b)) + _interaction_col(a, bs, us)
+             * self = u * sum n(n-1) / 2 for a BoseFS, 0 for a FermiFS; both recursions bottom out in 0 */
+            double rest = 0.0;
+            for (int i = C - 1; i >= 0; i--) {
+                double row = 0.0;
+                for (int j = C - 1; j > i; j--) {
+                    long dot = 0;
+                    for (int m = 0; m < M; m++) dot += (long)o->n[i][m] * o->n[j][m];
+                    row = h->umats[j + C * i] * (double)dot + row;
+                }
+                double self = h->ckind[i] == ORC_BOSE ? h->umats[i + C * i] * (double)bose_interaction(o->n[i], M) / 2 : 0.0;
+                rest = (self + row) + rest;
+            }
+            interaction = rest;
+            int allz = 1;
+            for (int i = 0; i < C; i++) for (int j = 0; j < C; j++) if (h->umats[i + C * j] != 0.0) allz = 0;
+            if (allz) interaction = 0.0; /* u_mat = iszero(u) ? nothing : ... (:205) */
+            double potc = 0.0;
+            if (h->has_pot)
+                for (int c = 0; c < C; c++) {
+                    double pe = 0.0;
+                    for (int i = 0; i < M; i++) if (o->n[c][i]) pe += o->n[c][i] * h->pot[c * M + i];
+                    potc += pe;
+                }
+            return interaction + potc;
+        }
         if (C == 1) {
             if (h->addr_kind == ORC_BOSE) interaction = h->umat[0] * (double)bose_interaction(o->n[0], M) / 2;
         } else {
@@ -351,6 +417,11 @@ long orc_num_offdiagonals_onr(const orc_ham *h, const orc_onr *o) {
         return 0;
     }
     case ORC_HUBBARD_REAL_SPACE: /* HubbardRealSpace.jl:309-315,371-374 */
+        if (h->addr_kind == ORC_COMPOSITE) {
+            long s = 0;
+            for (int c = 0; c < h->ncomp; c++) { orc_map mc; build_map(o->n[c], M, &mc); s += mc.len; }
+            return s * 2 * h->ndim;
+        }
         return (long)(ma.len + mb.len) * 2 * h->ndim;
     case ORC_TRANSCORRELATED_1D: { /* Transcorrelated1D.jl:277-297 */
         long N1 = ma.len, N2 = mb.len;
@@ -422,7 +493,7 @@ static double tc_three_body(int M, int *na, int *nb, const orc_map *ma, const or
  * When the value is 0 the returned address equals the input (as the reference does). */
 double orc_offdiagonal_onr(const orc_ham *h, const orc_onr *in, long chosen, orc_onr *out) {
     int M = h->M;
-    *out = *in;
+    onr_copy(h, out, in);
     orc_map ma, mb; build_map(in->n[0], M, &ma);
     if (h->ncomp == 2) build_map(in->n[1], M, &mb); else mb.len = 0;
     switch (h->model) {
@@ -504,6 +575,22 @@ double orc_offdiagonal_onr(const orc_ham *h, const orc_onr *in, long chosen, orc
     case ORC_HUBBARD_REAL_SPACE: { /* HubbardRealSpace.jl:316-338,383-391 */
         int nb = 2 * h->ndim, comp = 0;
         long c = chosen;
+        if (h->addr_kind == ORC_COMPOSITE) { /* _getindex over the components' hop lists (:383-391) */
+            orc_map mc;
+            for (comp = 0; ; comp++) {
+                build_map(in->n[comp], M, &mc);
+                if (c <= (long)mc.len * nb || comp == h->ncomp - 1) break;
+                c -= (long)mc.len * nb;
+            }
+            long particle, neigh;
+            fldmod1i(c, nb, &particle, &neigh);
+            int src = mc.mode[particle - 1];
+            int dstsite = neighbor_site(h, src, (int)neigh);
+            if (dstsite == 0) return 0.0;
+            int cre[1] = {dstsite}, des[1] = {src};
+            double val = excite(h->ckind[comp] == ORC_BOSE, out->n[comp], M, cre, des, 1);
+            return -h->tcs[comp] * val;
+        }
         if (c > (long)ma.len * nb) { c -= (long)ma.len * nb; comp = 1; }
         const orc_map *mp = comp ? &mb : &ma;
         long particle, neigh;
@@ -529,13 +616,13 @@ double orc_offdiagonal_onr(const orc_ham *h, const orc_onr *in, long chosen, orc
             int k, l;
             double value = tc_three_body(M, out->n[0], out->n[1], &ma, &mb, chosen - n_mom, &k, &l);
             value *= tc_q_function(h, k, l);
-            if (value == 0.0) *out = *in;
+            if (value == 0.0) onr_copy(h, out, in);
             return value;
         } else if (chosen <= n_mom + n1 + n2) {
             int k, l;
             double value = tc_three_body(M, out->n[1], out->n[0], &mb, &ma, chosen - n_mom - n1, &k, &l);
             value *= tc_q_function(h, k, l);
-            if (value == 0.0) *out = *in;
+            if (value == 0.0) onr_copy(h, out, in);
             return value;
         }
         return NAN;

@@ -27,7 +27,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 MAXM = 128
 
-BOSE, FERMI, FERMI2C = 0, 1, 2
+BOSE, FERMI, FERMI2C, COMPOSITE = 0, 1, 2, 3
+MAXC = 4
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3
 HUBBARD_REAL_1D_EP, EXTENDED_HUBBARD_REAL_1D = 4, 5
 EXTENDED_HUBBARD_MOM_1D, HUBBARD_MOM_1D_EP = 6, 7
@@ -53,6 +54,8 @@ class _Ham(C.Structure):
         ("tc", C.c_double * 2), ("umat", C.c_double * 4),
         ("ks", C.c_double * MAXM), ("kes", C.c_double * MAXM), ("ws", C.c_double * MAXM), ("us", C.c_double * MAXM),
         ("pot", C.c_double * (2 * MAXM)),
+        ("ckind", C.c_int32 * MAXC), ("Nc", C.c_int32 * MAXC),
+        ("tcs", C.c_double * MAXC), ("umats", C.c_double * (MAXC * MAXC)),
     ]
 
 
@@ -193,7 +196,8 @@ class OracleHam:
     """A Hamiltonian of the oracle.
 
     model: 'HubbardReal1D' | 'HubbardMom1D' | 'HubbardRealSpace' | 'Transcorrelated1D'
-    kind:  'bose' | 'fermi' | 'fermi2c'
+    kind:  'bose' | 'fermi' | 'fermi2c' | 'comp:<letters>' -- a general CompositeFS, one letter per component:
+           'b' BoseFS, 'f' FermiFS (e.g. 'comp:bf'); HubbardRealSpace only
     onr:   occupation numbers of the starting address (tuple, or tuple of two tuples)
     """
 
@@ -206,14 +210,23 @@ class OracleHam:
     def __init__(self, model, kind, onr, u=1.0, t=1.0, v=1.0, dims=None, fold=None, trap=None,
                  cutoff=1, three_body_term=True, dispersion="hubbard", v_ho=1.0, boundary_condition="periodic"):
         h = _Ham()
-        h.model, h.addr_kind = self.MODELS[model], self.KINDS[kind]
-        comps = [tuple(onr)] if kind != "fermi2c" else [tuple(onr[0]), tuple(onr[1])]
+        composite = kind.startswith("comp:")
+        h.model, h.addr_kind = self.MODELS[model], COMPOSITE if composite else self.KINDS[kind]
+        comps = [tuple(onr)] if kind in ("bose", "fermi") else [tuple(c) for c in onr]
         M = len(comps[0])
         assert all(len(c) == M for c in comps) and M <= MAXM
         h.M, h.ncomp = M, len(comps)
-        for c, comp in enumerate(comps):
-            h.N[c] = sum(comp)
-        bits = (h.N[0] + M - 1) + 1 if kind == "bose" else M * len(comps)  # bosons keep one spare bit (empty-slot sentinel)
+        if composite:
+            letters = kind[5:]
+            assert model == "HubbardRealSpace" and len(letters) == len(comps) and 2 <= len(comps) <= MAXC
+            bits = 1  # one spare bit (empty-slot sentinel)
+            for c, (letter, comp) in enumerate(zip(letters, comps)):
+                h.ckind[c], h.Nc[c] = {"b": BOSE, "f": FERMI}[letter], sum(comp)
+                bits += sum(comp) + M - 1 if letter == "b" else M
+        else:
+            for c, comp in enumerate(comps):
+                h.N[c] = sum(comp)
+            bits = (h.N[0] + M - 1) + 1 if kind == "bose" else M * len(comps)  # bosons keep one spare bit (empty-slot sentinel)
         h.words = (bits + 63) // 64
         assert h.words <= 2
         self.model, self.kind, self.M, self.W = model, kind, M, h.words
@@ -228,9 +241,15 @@ class OracleHam:
             tt = np.ones(ncomp) * np.asarray(t, dtype=float)
             uu = np.ones((ncomp, ncomp)) * np.asarray(u, dtype=float)
             for c in range(ncomp):
-                h.tc[c] = tt[c]
+                if composite:
+                    h.tcs[c] = tt[c]
+                else:
+                    h.tc[c] = tt[c]
                 for c2 in range(ncomp):
-                    h.umat[c + 2 * c2] = uu[c, c2]
+                    if composite:
+                        h.umats[c + ncomp * c2] = uu[c, c2]
+                    else:
+                        h.umat[c + 2 * c2] = uu[c, c2]
             if trap is not None and np.any(np.asarray(trap) != 0):
                 pot = trap_potential(dims, np.asarray(trap, dtype=float).reshape(ncomp, len(dims)))
                 h.has_pot = 1
@@ -279,7 +298,7 @@ class OracleHam:
 
     # -- codec
     def pack(self, onr):
-        comps = [tuple(onr)] if self.kind != "fermi2c" else [tuple(onr[0]), tuple(onr[1])]
+        comps = [tuple(onr)] if self.kind in ("bose", "fermi") else [tuple(c) for c in onr]
         flat = np.array([x for c in comps for x in c], dtype=np.int32)
         out = np.zeros(self.W, dtype=np.uint64)
         lib().orc_pack_onr(C.byref(self.h), _p(flat, C.c_int32), _p(out, C.c_uint64))
@@ -289,8 +308,8 @@ class OracleHam:
         k = np.array(key, dtype=np.uint64).reshape(self.W)
         out = np.zeros(self.h.ncomp * self.M, dtype=np.int32)
         lib().orc_unpack_onr(C.byref(self.h), _p(k, C.c_uint64), _p(out, C.c_int32))
-        if self.kind == "fermi2c":
-            return (tuple(int(x) for x in out[: self.M]), tuple(int(x) for x in out[self.M:]))
+        if self.kind not in ("bose", "fermi"):
+            return tuple(tuple(int(x) for x in out[c * self.M:(c + 1) * self.M]) for c in range(self.h.ncomp))
         return tuple(int(x) for x in out)
 
     def _key(self, key):

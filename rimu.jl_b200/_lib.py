@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RIMU_B200_LIB") or os.path.join(_HERE, "librimu_b200.
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "sort.cu", "sector.cu", "step_hk.cu"]   # step_hk.cu is compiled once per HamKind (-DRIMU_HK=n), in parallel
 HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh", "internal.cuh", "sector.cuh"]
-NUM_HAM_KINDS = 7
+NUM_HAM_KINDS = 8
 OBJ_DIR = os.environ.get("RIMU_B200_OBJ_DIR") or os.path.join("/tmp", "rimu_b200_build_" + str(os.getuid()))  # objects stay out of the tree
 
 NVCC_FLAGS = [
@@ -29,7 +29,8 @@ MAX_TABLE_MODES = 64
 
 OK, ERR_TABLE_FULL, ERR_VECTOR_FULL, ERR_EXCHANGE_FULL, ERR_WORKMEM = 0, 1, 2, 3, 4
 ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE = -1, -2, -3, -4
-ADDR_BOSE, ADDR_FERMI, ADDR_FERMI2C = 0, 1, 2
+ADDR_BOSE, ADDR_FERMI, ADDR_FERMI2C, ADDR_COMPOSITE = 0, 1, 2, 3
+MAX_COMPONENTS = 4
 HUBBARD_REAL_1D, HUBBARD_MOM_1D, HUBBARD_REAL_SPACE, TRANSCORRELATED_1D = 0, 1, 2, 3
 HUBBARD_REAL_1D_EP, EXTENDED_HUBBARD_REAL_1D = 4, 5
 EXTENDED_HUBBARD_MOM_1D, HUBBARD_MOM_1D_EP = 6, 7
@@ -101,6 +102,8 @@ class HamDesc(C.Structure):
         ("t_comp", C.c_double * 2), ("u_mat", C.c_double * 4),
         ("kes", C.c_double * MAX_TABLE_MODES), ("ws", C.c_double * MAX_TABLE_MODES), ("us", C.c_double * MAX_TABLE_MODES),
         ("potential", C.c_double * (2 * MAX_MODES)),
+        ("comp_kind", C.c_int32 * MAX_COMPONENTS), ("comp_particles", C.c_int32 * MAX_COMPONENTS),
+        ("comp_t", C.c_double * MAX_COMPONENTS), ("comp_u", C.c_double * (MAX_COMPONENTS * MAX_COMPONENTS)),
     ]
 
 

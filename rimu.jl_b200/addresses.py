@@ -19,20 +19,29 @@ class AddressType:
     kind: int                      # _lib.ADDR_*
     num_particles: Tuple[int, ...]
     num_modes: int
+    comp_kinds: Tuple[int, ...] = ()   # ADDR_COMPOSITE: ADDR_BOSE / ADDR_FERMI per component
 
     @property
     def num_components(self):
         return len(self.num_particles)
 
     @property
-    def bits(self):
+    def comp_bits(self):
+        """Bits of every component: N + M - 1 for a BoseFS component, M for a FermiFS component."""
+        M = self.num_modes
         if self.kind == _lib.ADDR_BOSE:
-            return self.num_particles[0] + self.num_modes - 1
-        return self.num_modes * self.num_components
+            return (self.num_particles[0] + M - 1,)
+        if self.kind == _lib.ADDR_COMPOSITE:
+            return tuple(n + M - 1 if k == _lib.ADDR_BOSE else M for k, n in zip(self.comp_kinds, self.num_particles))
+        return (M,) * self.num_components
+
+    @property
+    def bits(self):
+        return sum(self.comp_bits)
 
     @property
     def words(self):
-        b = self.bits + 1 if self.kind == _lib.ADDR_BOSE else self.bits
+        b = self.bits + 1 if self.kind in (_lib.ADDR_BOSE, _lib.ADDR_COMPOSITE) else self.bits
         return (b + 63) // 64
 
     def from_key(self, key):
@@ -49,6 +58,14 @@ class AddressType:
                 else:
                     mode += 1
             return BoseFS(tuple(onr))
+        if self.kind == _lib.ADDR_COMPOSITE:
+            comps, off = [], 0
+            for k, n, b in zip(self.comp_kinds, self.num_particles, self.comp_bits):
+                sub = AddressType(k, (n,), M)
+                xc = (x >> off) & ((1 << b) - 1)
+                comps.append(sub.from_key([(xc >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(max(sub.words, 1))]))
+                off += b
+            return CompositeFS(*comps)
         comps = []
         for c in range(self.num_components):
             comps.append(FermiFS(tuple((x >> (c * M + m)) & 1 for m in range(M))))
@@ -145,13 +162,17 @@ class FermiFS(_SingleComponent):
 
 
 class CompositeFS:
-    """CompositeFS(FermiFS, FermiFS): two fermion components with the same number of modes."""
+    """CompositeFS(components...) (multicomponent.jl:10-34): BoseFS / FermiFS components over the same modes.
+
+    Two FermiFS components of at most 32 modes are the one-word `FermiFS2C` layout every two-component model accepts;
+    anything else (bosonic or mixed components, more than two components, wider fermions) is the general packed layout
+    (`_lib.ADDR_COMPOSITE`, components side by side from the low bits) that `HubbardRealSpace` accepts."""
 
     def __init__(self, *components):
-        if len(components) != 2 or not all(isinstance(c, FermiFS) for c in components):
-            raise ValueError("only CompositeFS(FermiFS, FermiFS) is supported on the device path")
-        if components[0].num_modes != components[1].num_modes:
-            raise ValueError("components must have the same number of modes")
+        if len(components) < 1 or not all(isinstance(c, (BoseFS, FermiFS)) for c in components):
+            raise TypeError("the components of a CompositeFS must be BoseFS or FermiFS addresses")
+        if len({c.num_modes for c in components}) != 1:
+            raise ValueError("all addresses must have the same number of modes")
         self.components = tuple(components)
 
     @property
@@ -167,13 +188,25 @@ class CompositeFS:
         return tuple(c.onr for c in self.components)
 
     @property
+    def is_fermi2c(self):
+        return (len(self.components) == 2 and all(isinstance(c, FermiFS) for c in self.components)
+                and self.num_modes <= 32)
+
+    @property
     def address_type(self):
-        return AddressType(_lib.ADDR_FERMI2C, tuple(c.num_particles for c in self.components), self.num_modes)
+        nps = tuple(c.num_particles for c in self.components)
+        if self.is_fermi2c:
+            return AddressType(_lib.ADDR_FERMI2C, nps, self.num_modes)
+        kinds = tuple(_lib.ADDR_BOSE if isinstance(c, BoseFS) else _lib.ADDR_FERMI for c in self.components)
+        return AddressType(_lib.ADDR_COMPOSITE, nps, self.num_modes, kinds)
 
     def key(self):
-        M = self.num_modes
-        x = self.components[0]._bits() | (self.components[1]._bits() << M)
-        return (x & 0xFFFFFFFFFFFFFFFF,)
+        at = self.address_type
+        x, off = 0, 0
+        for c, b in zip(self.components, at.comp_bits):
+            x |= c._bits() << off
+            off += b
+        return tuple((x >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(at.words))
 
     def __eq__(self, other):
         return isinstance(other, CompositeFS) and self.components == other.components
@@ -182,7 +215,7 @@ class CompositeFS:
         return hash(self.components)
 
     def __repr__(self):
-        return f"CompositeFS({self.components[0]!r}, {self.components[1]!r})"
+        return "CompositeFS(" + ", ".join(repr(c) for c in self.components) + ")"
 
 
 def FermiFS2C(onr_a, onr_b):

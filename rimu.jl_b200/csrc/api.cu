@@ -506,6 +506,7 @@ static const HkOps *hk_ops(const rimu_ham *h) {
     case HK_RS_FERMI: return rimu_hk_ops_4();
     case HK_RS_F2C: return rimu_hk_ops_5();
     case HK_TC_F2C: return rimu_hk_ops_6();
+    case HK_RS_COMP: return rimu_hk_ops_7();
     }
     fail(RIMU_ERR_INVALID, "unknown Hamiltonian kind");
     return nullptr;

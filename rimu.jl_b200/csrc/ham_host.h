@@ -69,6 +69,21 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
         else if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_F2C;
         else if (model == RIMU_TRANSCORRELATED_1D) hk = HK_TC_F2C;
     }
+    else if (kind == RIMU_ADDR_COMPOSITE) { // general CompositeFS: components packed side by side from the low bits
+        const int C = d->num_components;
+        if (C < 2 || C > RIMU_MAX_COMPONENTS) return ham_host_fail(img, "CompositeFS must have 2..%d components", RIMU_MAX_COMPONENTS);
+        for (int c = 0; c < C; c++) {
+            const int n = d->comp_particles[c];
+            if (d->comp_kind[c] == RIMU_ADDR_BOSE) { if (n < 0) return ham_host_fail(img, "negative particle number"); bits += n + M - 1; }
+            else if (d->comp_kind[c] == RIMU_ADDR_FERMI) {
+                if (n < 0 || n > M) return ham_host_fail(img, "FermiFS component with %d particles in %d modes", n, M);
+                if (M > 64) return ham_host_fail(img, "FermiFS components with more than 64 modes unsupported");
+                bits += M;
+            } else return ham_host_fail(img, "components of a CompositeFS must be BoseFS or FermiFS");
+        }
+        if (bits + 1 > 128) return ham_host_fail(img, "CompositeFS needs %d bits; at most 127 supported", bits);
+        if (model == RIMU_HUBBARD_REAL_SPACE) hk = HK_RS_COMP;
+    }
     if (hk < 0)
         return ham_host_fail(img, "model %d is not implemented for address kind %d (no CPU fallback exists)", model, kind);
     if ((hk == HK_MOM1D_BOSE || hk == HK_MOM1D_F2C || hk == HK_TC_F2C) && M > RIMU_MAX_TABLE_MODES)
@@ -79,11 +94,12 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
         if (hk == HK_MOM1D_BOSE) lmax = n1 * (n1 - 1) * (m - 2) + 2 * n1 * (m - 1);
         else if (hk == HK_TC_F2C) lmax = n1 * n2 * (m - 1) + (n1 * (n1 - 1) * n2 + n2 * (n2 - 1) * n1) * m * m;
         else if (hk == HK_MOM1D_F2C) lmax = n1 * n2 * (m - 1) + (n1 + n2) * (m - 1);
+        else if (hk == HK_RS_COMP) { lmax = 0; for (int c = 0; c < d->num_components; c++) lmax += 6.0 * d->comp_particles[c]; }
         else lmax = (n1 + n2) * 6;
         if (lmax >= 2147483648.0) return ham_host_fail(img, "more than 2^31 off-diagonals per address are unsupported");
     }
     img->hk = hk;
-    img->W = (kind == RIMU_ADDR_BOSE) ? ((bits + 1 + 63) / 64) : 1;
+    img->W = (kind == RIMU_ADDR_BOSE || kind == RIMU_ADDR_COMPOSITE) ? ((bits + 1 + 63) / 64) : 1;
     HamDev &v = img->dev;
     memset(&v, 0, sizeof(v));
     v.hk = hk; v.M = M; v.N0 = d->num_particles[0]; v.N1 = d->num_particles[1];
@@ -97,6 +113,22 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
     v.bc = d->boundary_condition;
     if (v.variant == 2 && (v.bc < 0 || v.bc > 2)) return ham_host_fail(img, "invalid boundary condition");
     int nz = 0;
+    if (hk == HK_RS_COMP) {
+        const int C = d->num_components;
+        v.ncomp = C;
+        int off = 0;
+        for (int c = 0; c < C; c++) {
+            v.cbose[c] = d->comp_kind[c] == RIMU_ADDR_BOSE;
+            v.cbits[c] = v.cbose[c] ? d->comp_particles[c] + M - 1 : M;
+            v.coff[c] = off; off += v.cbits[c];
+            v.tcs[c] = d->comp_t[c];
+            for (int c2 = 0; c2 < C; c2++) {
+                v.umat[c + C * c2] = d->comp_u[c + C * c2];
+                nz += d->comp_u[c + C * c2] != 0.0;
+                if (d->comp_u[c + C * c2] != d->comp_u[c2 + C * c]) return ham_host_fail(img, "`u` must be symmetric");
+            }
+        }
+    } else
     for (int i = 0; i < d->num_components * d->num_components; i++) nz += d->u_mat[(i % d->num_components) + 2 * (i / d->num_components)] != 0.0;
     v.umat_zero = nz == 0;
     // tables: kes | ws | us | pot

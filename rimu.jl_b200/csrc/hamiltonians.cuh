@@ -23,8 +23,10 @@ enum HamKind {
     HK_RS_FERMI = 4,
     HK_RS_F2C = 5,
     HK_TC_F2C = 6,
-    HK_COUNT = 7
+    HK_RS_COMP = 7,   // HubbardRealSpace over a general CompositeFS (2..4 BoseFS / FermiFS components, one or two words)
+    HK_COUNT = 8
 };
+#define HAM_MAX_COMP 4
 
 struct HamDev {
     int hk, M, N0, N1, ndim, nnb, cutoff, three_body, has_pot, umat_zero;
@@ -36,6 +38,9 @@ struct HamDev {
     double u_2m, u_m; // u / (2M), u / M: the same IEEE divisions the reference evaluates per element, done once on the host
     const double *kes, *ws, *us, *pot; // device tables
     const unsigned char *nbr;          // HubbardRealSpace: nbr[(site-1)*nnb + dir] = neighbour site (1-based) or 0
+    // HK_RS_COMP: component c is a BoseFS (cbose[c]) or FermiFS bit string of cbits[c] bits at bit offset coff[c]
+    int ncomp, cbose[HAM_MAX_COMP], coff[HAM_MAX_COMP], cbits[HAM_MAX_COMP];
+    double tcs[HAM_MAX_COMP], umat[HAM_MAX_COMP * HAM_MAX_COMP]; // t[c]; u[i + ncomp * j]
 };
 
 #if defined(__CUDACC__) || defined(RIMU_HOST_EMULATION)
@@ -222,6 +227,32 @@ DEV double tc_three_body(int M, u64 &fa, u64 &fb, int N1, int N2, long long i64_
 }
 
 // ---------------------------------------------------------------- the Hamiltonian interface
+// ---------------------------------------------------------------- general CompositeFS (HK_RS_COMP)
+template <class B> DEV B comp_get(const HamDev &h, B x, int c) { return (B)(x >> h.coff[c]) & lowmask<B>(h.cbits[c]); }
+template <class B> DEV B comp_put(const HamDev &h, B x, int c, B xc) {
+    return (x & ~(lowmask<B>(h.cbits[c]) << h.coff[c])) | (xc << h.coff[c]);
+}
+template <class B> DEV int comp_num_occupied(const HamDev &h, B xc, int c) { return h.cbose[c] ? bose_num_occupied(xc) : popc_(xc); }
+// occupation of 0-based mode md in component c
+template <class B> DEV int comp_occupation(const HamDev &h, B xc, int c, int md) {
+    if (!h.cbose[c]) return (int)((u64)(xc >> md) & 1ull);
+    const int off = bose_mode_offset(xc, md + 1);
+    return cto_((B)(xc >> off));
+}
+// dot(occupied_modes(a), occupied_modes(b)) = sum_m n_a(m) n_b(m) (fockaddress.jl:692-719); an exact integer, any order
+template <class B> DEV long long comp_overlap(const HamDev &h, B x, int a, int b) {
+    const B xa = comp_get(h, x, a), xb = comp_get(h, x, b);
+    if (!h.cbose[a] && !h.cbose[b]) return popc_((B)(xa & xb));
+    if (!h.cbose[a]) { // iterate the fermions, look the boson occupation up
+        long long r = 0; u64 f = (u64)xa;
+        while (f) { int md = __ffsll((long long)f) - 1; f &= f - 1; r += comp_occupation(h, xb, b, md); }
+        return r;
+    }
+    long long r = 0; int md, n;
+    for (BoseModes<B> it(xa); it.next(md, n);) r += (long long)n * comp_occupation(h, xb, b, md);
+    return r;
+}
+
 template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
     const int M = h.M;
     if constexpr (HK == HK_REAL1D_BOSE) {
@@ -304,6 +335,31 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
             pot += pe;
         }
         return interaction + pot;
+    } else if constexpr (HK == HK_RS_COMP) {
+        // local_interaction(::CompositeFS, u) = _interactions(components, u) (HubbardRealSpace.jl:18-75):
+        // (self_1 + row_1) + ((self_2 + row_2) + (... + 0.0)), row_i = u[i+1,i] n_i.n_{i+1} + (u[i+2,i] n_i.n_{i+2} + (... + 0))
+        const int C = h.ncomp;
+        double interaction = 0.0;
+        if (!h.umat_zero) {
+            for (int i = C - 1; i >= 0; i--) {
+                const B xi = comp_get(h, x, i);
+                double row = 0.0;
+                for (int j = C - 1; j > i; j--) row = h.umat[j + C * i] * (double)comp_overlap(h, x, i, j) + row;
+                const double self = h.cbose[i] ? h.umat[i + C * i] * (double)bose_interaction(xi) / 2 : 0.0;
+                interaction = (self + row) + interaction;
+            }
+        }
+        double pot = 0.0;
+        if (h.has_pot) { // external_potential(::CompositeFS, pot::Matrix) (:99-106): per component, occupied modes ascending
+            for (int c = 0; c < C; c++) {
+                const B xc = comp_get(h, x, c);
+                double pe = 0.0;
+                if (h.cbose[c]) { int md, n; for (BoseModes<B> it(xc); it.next(md, n);) pe += n * h.pot[c * M + md]; }
+                else { u64 f = (u64)xc; while (f) { int b = __ffsll((long long)f) - 1; f &= f - 1; pe += 1 * h.pot[c * M + b]; } }
+                pot += pe;
+            }
+        }
+        return interaction + pot;
     } else { // HK_TC_F2C
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
         int n1 = __popcll(fa), n2 = __popcll(fb);
@@ -330,6 +386,10 @@ template <int HK, class B> DEV long long ham_num_offdiagonals(const HamDev &h, B
         return (long long)__popcll((u64)x) * h.nnb;
     } else if constexpr (HK == HK_RS_F2C) {
         return (long long)__popcll((u64)x) * h.nnb; // both components
+    } else if constexpr (HK == HK_RS_COMP) {
+        long long s = 0;
+        for (int c = 0; c < h.ncomp; c++) s += comp_num_occupied(h, comp_get(h, x, c), c);
+        return s * h.nnb;
     } else {
         long long N1 = h.N0, N2 = h.N1;
         long long n = N1 * N2 * (M - 1);
@@ -469,6 +529,42 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         if (comp) fb = f; else fa = f;
         out = (HK == HK_RS_F2C) ? (B)(fa | (fb << M)) : (B)fa;
         return -(comp ? h.tc1 : h.tc0) * parity_sign(cnt);
+    } else if constexpr (HK == HK_RS_COMP) {
+        // HubbardRealSpaceOffdiagonals (HubbardRealSpace.jl:340-391): the components' hop lists one after the other
+        int c = 0;
+        B xc = comp_get(h, x, 0);
+        for (;;) {
+            const long long nc = (long long)comp_num_occupied(h, xc, c) * h.nnb;
+            if (i < nc || c == h.ncomp - 1) break;
+            i -= nc; c++;
+            xc = comp_get(h, x, c);
+        }
+        const unsigned ii = (unsigned)i, nnb = (unsigned)h.nnb;
+        const unsigned pq = udiv_small(ii, nnb);
+        const int particle = (int)pq, neigh = (int)(ii - pq * nnb);
+        double value;
+        if (h.cbose[c]) {
+            int mode, ns, off;
+            bose_kth_occupied(xc, particle, mode, ns, off);
+            const int dst = h.nbr[(mode - 1) * h.nnb + neigh];
+            if (dst == 0) return 0.0;
+            B y = delete_bit(xc, off);
+            const int nd = bose_create(y, dst);
+            xc = y;
+            value = sqrt((double)(ns * nd));
+        } else {
+            u64 f = (u64)xc;
+            const int mode = select_(f, particle) + 1;
+            const int dst = h.nbr[(mode - 1) * h.nnb + neigh];
+            if (dst == 0) return 0.0;
+            int cnt = 0;
+            fermi_destroy(f, mode, cnt);
+            if (!fermi_create(f, dst, cnt)) return 0.0;
+            xc = (B)f;
+            value = parity_sign(cnt);
+        }
+        out = comp_put(h, x, c, xc);
+        return -h.tcs[c] * value;
     } else { // HK_TC_F2C
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
         long long N1 = h.N0, N2 = h.N1;

@@ -224,4 +224,5 @@ RIMU_INTERNAL const HkOps *rimu_hk_ops_3();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_4();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_5();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_6();
+RIMU_INTERNAL const HkOps *rimu_hk_ops_7();
 

@@ -108,6 +108,7 @@ __global__ void sector_compact_kernel(const u64 *__restrict__ keys, const double
 extern "C" int rimu_sector_create(rimu_ctx *c, const rimu_ham *h, rimu_sector **out) {
     if (!c || !h || !out) return fail(RIMU_ERR_INVALID, "null argument");
     if (c->W != 1 || h->W != 1) return fail(RIMU_ERR_INVALID, "dense sectors need one-word addresses");
+    if (h->hk == HK_RS_COMP) return fail(RIMU_ERR_INVALID, "dense sectors are numbered for BoseFS, FermiFS and FermiFS2C addresses; use the dictionary vector for a general CompositeFS");
     if (h->hk == HK_TC_F2C) return fail(RIMU_ERR_INVALID, "the dense H*v is a gather over a real symmetric matrix; Transcorrelated1D is not Hermitian");
     TRY(enter_ctx(c));
     const rimu_ham_desc &d = h->desc;

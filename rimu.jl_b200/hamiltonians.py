@@ -148,8 +148,19 @@ class AbstractHamiltonian:
         at = self.address_type
         d = self.desc
         d.addr_kind, d.num_modes, d.num_components = at.kind, at.num_modes, at.num_components
-        for c, n in enumerate(at.num_particles):
-            d.num_particles[c] = n
+        if at.kind == _lib.ADDR_COMPOSITE:
+            if d.model != _lib.HUBBARD_REAL_SPACE:
+                raise TypeError(f"{type(self).__name__} is defined for BoseFS or two-component fermionic (FermiFS2C, at most "
+                                "32 modes) addresses; general CompositeFS addresses are supported by HubbardRealSpace")
+            if at.num_components > _lib.MAX_COMPONENTS:
+                raise ValueError(f"at most {_lib.MAX_COMPONENTS} components are supported on the device path")
+            if at.bits > 127:
+                raise ValueError(f"the address needs {at.bits} bits; at most 127 are supported on the device path")
+            for c, (k, n) in enumerate(zip(at.comp_kinds, at.num_particles)):
+                d.comp_kind[c], d.comp_particles[c] = k, n
+        else:
+            for c, n in enumerate(at.num_particles):
+                d.num_particles[c] = n
         self._handle = None
         self._ctx = None
 
@@ -256,8 +267,9 @@ def dimension(h):
     if at.kind == _lib.ADDR_BOSE:
         return math.comb(at.num_particles[0] + M - 1, at.num_particles[0])
     out = 1
-    for n in at.num_particles:
-        out *= math.comb(M, n)
+    kinds = at.comp_kinds if at.kind == _lib.ADDR_COMPOSITE else (_lib.ADDR_FERMI,) * at.num_components
+    for k, n in zip(kinds, at.num_particles):
+        out *= math.comb(n + M - 1, n) if k == _lib.ADDR_BOSE else math.comb(M, n)
     return out
 
 
@@ -427,7 +439,12 @@ class HubbardMom1DEP(AbstractHamiltonian):
 
 class HubbardRealSpace(AbstractHamiltonian):
     def __init__(self, address, geometry=None, t=None, u=None, v=None):
-        C_ = 1 if not isinstance(address, CompositeFS) else 2
+        C_ = 1 if not isinstance(address, CompositeFS) else len(address.components)
+        if isinstance(address, CompositeFS) and C_ < 2:
+            raise TypeError("a CompositeFS address needs at least two components")  # (MethodError in the reference)
+        general = isinstance(address, CompositeFS) and not address.is_fermi2c
+        if C_ > _lib.MAX_COMPONENTS:
+            raise ValueError(f"at most {_lib.MAX_COMPONENTS} components are supported on the device path")
         M = address.num_modes
         geometry = PeriodicBoundaries(M) if geometry is None else geometry
         D = len(geometry.dims)
@@ -448,9 +465,15 @@ class HubbardRealSpace(AbstractHamiltonian):
         for k in range(D):
             d.dims[k], d.fold[k] = geometry.dims[k], int(geometry.fold[k])
         for c in range(C_):
-            d.t_comp[c] = t[c]
+            if general:
+                d.comp_t[c] = t[c]
+            else:
+                d.t_comp[c] = t[c]
             for c2 in range(C_):
-                d.u_mat[c + 2 * c2] = u[c, c2]
+                if general:
+                    d.comp_u[c + C_ * c2] = u[c, c2]
+                else:
+                    d.u_mat[c + 2 * c2] = u[c, c2]
         if np.any(v != 0):  # HubbardRealSpace.jl:214-227
             d.has_potential = 1
             for site in range(M):

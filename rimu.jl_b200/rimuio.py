@@ -64,6 +64,12 @@ def _components(at: AddressType):
     M = at.num_modes
     if at.kind == _lib.ADDR_BOSE:
         return [(_NAMES[_lib.ADDR_BOSE], at.num_particles[0], M, at.num_particles[0] + M - 1, 0)]
+    if at.kind == _lib.ADDR_COMPOSITE:  # general CompositeFS: the components side by side from the low bits
+        out, shift = [], 0
+        for k, n, b in zip(at.comp_kinds, at.num_particles, at.comp_bits):
+            out.append((_NAMES[k], n, M, b, shift))
+            shift += b
+        return out
     return [(_NAMES[_lib.ADDR_FERMI], n, M, M, c * M) for c, n in enumerate(at.num_particles)]
 
 
@@ -208,13 +214,16 @@ def read_state_file(filename):
     if name == "Rimu.CompositeFS":
         parts = [m.split(":") for m in meta.split(";")]
         comps = [_decode_component(n, mm) for n, mm in parts]
-        if any(c[0] != _lib.ADDR_FERMI for c in comps) or len(comps) != 2:
-            raise ValueError("only two-component fermion addresses have a device layout")
         M = comps[0][2]
-        at = AddressType(_lib.ADDR_FERMI2C, tuple(c[1] for c in comps), M)
+        if len(comps) == 2 and all(c[0] == _lib.ADDR_FERMI for c in comps) and M <= 32:
+            at = AddressType(_lib.ADDR_FERMI2C, tuple(c[1] for c in comps), M)
+        else:
+            if not 2 <= len(comps) <= _lib.MAX_COMPONENTS or sum(c[3] for c in comps) > 127:
+                raise ValueError("this CompositeFS has no device layout (2..4 components, at most 127 bits)")
+            at = AddressType(_lib.ADDR_COMPOSITE, tuple(c[1] for c in comps), M, tuple(c[0] for c in comps))
         lists = [col.field(i) for i in range(len(comps))]
-        shifts = [i * M for i in range(len(comps))]
         bits = [c[3] for c in comps]
+        shifts = [sum(bits[:i]) for i in range(len(comps))]
     else:
         kind, N, M, B = _decode_component(name, meta)
         at = AddressType(kind, (N,), M)

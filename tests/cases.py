@@ -44,6 +44,15 @@ SPECS = {
     "rs_f2c_3up3dn": ("HubbardRealSpace", "fermi2c", (_fermi(16, (1, 6, 11)), _fermi(16, (2, 8, 13))), dict(t=(1.0, 1.0), u=((0.0, 4.0), (4.0, 0.0)), dims=(4, 4))),  # dim 313 600
     "rs_f2c_half": ("HubbardRealSpace", "fermi2c", (_fermi(16, range(1, 9)), _fermi(16, range(5, 13))), dict(t=(1.0, 1.0), u=((0.0, 1.0), (1.0, 0.0)), dims=(4, 4))),  # config 3
     "rs_f2c_trap": ("HubbardRealSpace", "fermi2c", (_fermi(6, (1, 2, 4, 5)), _fermi(6, (2, 3))), dict(t=(1.0, 2.0), u=((0.0, 0.5), (0.5, 0.0)), dims=(6,), trap=((0.1,), (0.2,)))),
+    # general CompositeFS (multicomponent.jl:10-34) on HubbardRealSpace: bosonic, mixed, three components, wide fermions, two words
+    "rs_comp_bb": ("HubbardRealSpace", "comp:bb", ((1, 1, 1, 0, 0, 0), (1, 0, 0, 0, 0, 0)), dict(t=(1.0, 4.0), u=((2.0, 3.0), (3.0, 0.0)), dims=(6,))),  # test/Hamiltonians.jl:329-333
+    "rs_comp_bf": ("HubbardRealSpace", "comp:bf", ((1, 1, 1, 0, 0, 0), (1, 0, 0, 0, 0, 0)), dict(t=(1.0, 4.0), u=((2.0, 3.0), (3.0, 0.0)), dims=(6,))),  # :335-339
+    "rs_comp_fb": ("HubbardRealSpace", "comp:fb", ((1, 0, 0, 0, 0, 0), (1, 1, 1, 0, 0, 0)), dict(t=(4.0, 1.0), u=((0.0, 3.0), (3.0, 2.0)), dims=(6,))),  # :347-351
+    "rs_comp_bb_trap": ("HubbardRealSpace", "comp:bb", ((1, 1, 1, 0, 0, 0), (1, 0, 0, 0, 0, 0)), dict(t=(1.0, 1.0), u=((2.0, 3.0), (3.0, 0.0)), dims=(6,), trap=((1.0,), (4.0,)))),  # :398-403
+    "rs_comp_ffb": ("HubbardRealSpace", "comp:ffb", ((1, 1, 0, 0), (1, 0, 0, 1), (0, 0, 2, 1)), dict(t=(1.0, 2.0, 0.5), u=((0.0, 1.0, 2.0), (1.0, 0.0, 3.0), (2.0, 3.0, 1.5)), dims=(2, 2), fold=(True, False))),
+    "rs_comp_bbb": ("HubbardRealSpace", "comp:bbb", ((1, 0, 0, 0), (1, 0, 0, 0), (1, 0, 0, 0)), dict(t=(1.0, 1.0, 1.0), u=((1.0, 1.0, 1.0), (1.0, 1.0, 1.0), (1.0, 1.0, 1.0)), dims=(4,))),  # :78
+    "rs_comp_ff_wide": ("HubbardRealSpace", "comp:ff", (_fermi(36, (1, 8, 15, 22)), _fermi(36, (2, 8, 30))), dict(t=(1.0, 1.0), u=((0.0, 4.0), (4.0, 0.0)), dims=(6, 6))),  # 72 bits: two words
+    "rs_comp_bf_w2": ("HubbardRealSpace", "comp:bf", (_nu(30, 27), _fermi(27, (1, 5, 9, 14, 20))), dict(t=(1.0, 0.5), u=((1.0, 2.0), (2.0, 0.0)), dims=(3, 3, 3), trap=((0.1, 0.2, 0.3), (0.0, 0.5, 0.0)))),  # 56 + 27 bits
     "tc_7": ("Transcorrelated1D", "fermi2c", (_fermi(7, (3, 5)), _fermi(7, (4,))), dict(t=24.5, v=7.0, cutoff=1, three_body_term=True)),
     "tc_8_cut2": ("Transcorrelated1D", "fermi2c", (_fermi(8, (3, 4, 6)), _fermi(8, (2, 5))), dict(t=1.0, v=1.5, cutoff=2, three_body_term=True)),
     "tc_12": ("Transcorrelated1D", "fermi2c", (_fermi(12, (5, 6, 7)), _fermi(12, (6, 7))), dict(t=1.0, v=1.0, cutoff=1, three_body_term=True)),  # config 5's model, small enough for ED
@@ -65,6 +74,8 @@ def product_ham(name):
         addr = R.BoseFS(onr)
     elif kind == "fermi":
         addr = R.FermiFS(onr)
+    elif kind.startswith("comp:"):
+        addr = R.CompositeFS(*[(R.BoseFS if letter == "b" else R.FermiFS)(c) for letter, c in zip(kind[5:], onr)])
     else:
         addr = R.FermiFS2C(onr[0], onr[1])
     if model == "HubbardReal1D":

@@ -33,6 +33,7 @@ template <class F> static auto dispatch(int hk, int W, F &&f) {
     case HK_RS_BOSE: return W == 1 ? f(std::integral_constant<int, HK_RS_BOSE>(), u64()) : f(std::integral_constant<int, HK_RS_BOSE>(), u128());
     case HK_RS_FERMI: return f(std::integral_constant<int, HK_RS_FERMI>(), u64());
     case HK_RS_F2C: return f(std::integral_constant<int, HK_RS_F2C>(), u64());
+    case HK_RS_COMP: return W == 1 ? f(std::integral_constant<int, HK_RS_COMP>(), u64()) : f(std::integral_constant<int, HK_RS_COMP>(), u128());
     default: return f(std::integral_constant<int, HK_TC_F2C>(), u64());
     }
 }

@@ -35,7 +35,8 @@ def exact_energy(oh):
 
 # --------------------------------------------------------------------------- Lanczos vs ED
 @pytest.mark.parametrize("name", ["real1d_6", "mom1d_bose", "rs_bose_2d", "rs_fermi", "rs_f2c_4x4", "rs_f2c_trap", "mom1d_f2c",
-                                  "rs_f2c_3up3dn", "real1d_ep", "ext1d", "ext1d_twisted", "ext_mom1d", "mom1d_ep", "mom1d_ep_f2c"])
+                                  "rs_f2c_3up3dn", "real1d_ep", "ext1d", "ext1d_twisted", "ext_mom1d", "mom1d_ep", "mom1d_ep_f2c",
+                                  "rs_comp_bb", "rs_comp_bf", "rs_comp_fb", "rs_comp_bb_trap", "rs_comp_ffb"])
 def test_lanczos_ground_state_matches_exact_diagonalization(built, name):
     import rimu_b200 as R
     oh, ph = oracle_ham(name), product_ham(name)

@@ -50,7 +50,8 @@ def test_hamiltonian_elements(built, name):
 
 
 @pytest.mark.parametrize("name", ["ext_mom1d", "mom1d_ep", "mom1d_ep_f2c", "real1d_ep", "ext1d", "ext1d_hw", "real1d_6", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d", "rs_bose_3d_w2",
-                                  "rs_fermi", "rs_f2c_4x4", "rs_f2c_trap", "tc_7", "tc_8_cut2"])
+                                  "rs_fermi", "rs_f2c_4x4", "rs_f2c_trap", "tc_7", "tc_8_cut2",
+                                  "rs_comp_bb", "rs_comp_bf", "rs_comp_bb_trap", "rs_comp_ffb", "rs_comp_ff_wide", "rs_comp_bf_w2"])
 def test_deterministic_hv(built, name):
     """mul!(y, H, x) three times from the starting address: keys exact, values 1e-12 relative."""
     import rimu_b200 as R
@@ -85,7 +86,7 @@ def test_deterministic_hv(built, name):
 
 
 @pytest.mark.parametrize("name", ["ext_mom1d", "ext_mom1d_20", "mom1d_ep", "mom1d_ep_f2c", "real1d_ep", "ext1d", "ext1d_hw", "real1d_6", "real1d_10", "real1d_w2", "mom1d_bose", "mom1d_f2c", "rs_bose_2d",
-                                  "rs_bose_3d_w2", "rs_f2c_4x4", "tc_7"])
+                                  "rs_bose_3d_w2", "rs_f2c_4x4", "tc_7", "rs_comp_bf", "rs_comp_ffb", "rs_comp_bbb", "rs_comp_ff_wide", "rs_comp_bf_w2"])
 def test_integer_walkers_bit_exact(built, name):
     """IsStochasticInteger FCIQMC steps: same Philox streams => identical vectors and statistics."""
     import rimu_b200 as R
@@ -112,7 +113,7 @@ def test_integer_walkers_bit_exact(built, name):
         assert names == ("spawn_attempts", "spawns", "deaths", "clones", "zombies")
 
 
-@pytest.mark.parametrize("name", ["real1d_6", "mom1d_bose", "rs_f2c_4x4", "tc_7"])
+@pytest.mark.parametrize("name", ["real1d_6", "mom1d_bose", "rs_f2c_4x4", "tc_7", "rs_comp_fb", "rs_comp_bf_w2"])
 def test_semistochastic_step(built, name):
     """IsDynamicSemistochastic: exact/inexact branch, late ThresholdCompression.  Random decisions are
     keyed on addresses, so results match the oracle except for Float64 summation order."""

@@ -186,7 +186,8 @@ def test_device_step_arithmetic_matches_oracle_on_the_host(built, emu, name, sty
 def _random_onr(rng, kind, comps, M):
     """random occupation numbers with the particle numbers of `comps` (edge shapes included)"""
     out = []
-    for comp in comps:
+    kinds = ["bose" if letter == "b" else "fermi" for letter in kind[5:]] if kind.startswith("comp:") else [kind] * len(comps)
+    for kind, comp in zip(kinds, comps):
         N = sum(comp)
         if kind == "bose":
             mode = rng.integers(0, 4)
@@ -205,7 +206,8 @@ def _random_onr(rng, kind, comps, M):
 
 
 @pytest.mark.parametrize("name", ["real1d_10", "real1d_w2", "real1d_ep_w2", "ext1d_hw", "mom1d_bose_20", "mom1d_odd", "mom1d_f2c",
-                                  "rs_bose_2d_hw", "rs_bose_3d_w2", "rs_fermi_hw", "rs_f2c_trap", "tc_8_cut2", "tc_32"])
+                                  "rs_bose_2d_hw", "rs_bose_3d_w2", "rs_fermi_hw", "rs_f2c_trap", "tc_8_cut2", "tc_32",
+                                  "rs_comp_bf", "rs_comp_bb_trap", "rs_comp_ffb", "rs_comp_ff_wide", "rs_comp_bf_w2"])
 def test_device_hamiltonian_code_on_random_addresses(built, emu, name):
     """Addresses the BFS walk from the starting address rarely visits: all particles in the first / last mode, random
     fillings, both address widths.  diagonal, count and a spread of off-diagonals, device code (host build) vs oracle."""
@@ -219,7 +221,7 @@ def test_device_hamiltonian_code_on_random_addresses(built, emu, name):
     kind = SPECS[name][1]
     comps = oh.start_onr
     for _ in range(60):
-        onrs = _random_onr(rng, "bose" if kind == "bose" else "fermi", comps, oh.M)
+        onrs = _random_onr(rng, kind if kind == "bose" or kind.startswith("comp:") else "fermi", comps, oh.M)
         key = oh.pack(onrs[0] if len(onrs) == 1 else tuple(onrs))
         kt = tuple(int(x) for x in key) if isinstance(key, (tuple, list)) else tuple(int(x) for x in np.asarray(key, dtype=np.uint64).ravel())
         kin = (C.c_uint64 * 2)(*(list(kt) + [0] * (2 - len(kt))))

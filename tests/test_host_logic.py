@@ -172,3 +172,51 @@ def test_initiator_rule_keywords(built):
     # the oracle uses the same rule numbering
     from oracle import oracle as orc
     assert (orc.NON_INITIATOR, orc.INITIATOR, orc.SIMPLE_INITIATOR, orc.COHERENT_INITIATOR) == (0, 1, 2, 3)
+
+
+def test_general_composite_addresses(built):
+    """CompositeFS beyond two small fermion components (multicomponent.jl:10-34): packed layout == the oracle's, round trip,
+    address-type bookkeeping, and the errors of the constructor / of models that cannot take such an address."""
+    import rimu_b200 as R
+    from tests.cases import SPECS, oracle_ham, product_ham
+    rng = np.random.default_rng(7)
+    for name in [n for n in SPECS if n.startswith("rs_comp_")]:
+        oh, ph = oracle_ham(name), product_ham(name)
+        at = ph.address_type
+        assert at.kind == R._lib.ADDR_COMPOSITE and at.words == oh.W and ph.address.key() == oh.start_key
+        assert at.from_key(ph.address.key()) == ph.address
+        assert R.dimension(ph) == math.prod(
+            math.comb(n + at.num_modes - 1, n) if k == R._lib.ADDR_BOSE else math.comb(at.num_modes, n)
+            for k, n in zip(at.comp_kinds, at.num_particles))
+        # a few random addresses of the same type
+        for _ in range(10):
+            comps = []
+            for k, n in zip(at.comp_kinds, at.num_particles):
+                if k == R._lib.ADDR_BOSE:
+                    comps.append(R.BoseFS(tuple(int(x) for x in np.bincount(rng.integers(0, at.num_modes, size=n), minlength=at.num_modes))))
+                else:
+                    occ = np.zeros(at.num_modes, dtype=int)
+                    occ[rng.choice(at.num_modes, size=n, replace=False)] = 1
+                    comps.append(R.FermiFS(tuple(int(x) for x in occ)))
+            a = R.CompositeFS(*comps)
+            assert a.key() == oh.pack(tuple(c.onr for c in comps)) and at.from_key(a.key()) == a
+    # two fermion components of at most 32 modes stay the one-word FermiFS2C layout; wider ones use the general layout
+    assert R.FermiFS2C((1, 0), (0, 1)).address_type.kind == R._lib.ADDR_FERMI2C
+    wide = R.CompositeFS(R.near_uniform(R.FermiFS, 3, 40), R.near_uniform(R.FermiFS, 2, 40))
+    assert wide.address_type.kind == R._lib.ADDR_COMPOSITE and wide.address_type.words == 2
+    with pytest.raises(ValueError, match="same number of modes"):       # ArgumentError in the reference (multicomponent.jl:27-29)
+        R.CompositeFS(R.BoseFS((1, 1)), R.FermiFS((1, 0, 0)))
+    with pytest.raises(TypeError):
+        R.CompositeFS((1, 0), (0, 1))
+    mixed = R.CompositeFS(R.BoseFS((1, 2, 0)), R.FermiFS((0, 1, 0)))
+    for model in (R.HubbardMom1D, R.Transcorrelated1D, R.HubbardMom1DEP):
+        with pytest.raises(TypeError):
+            model(mixed)
+    with pytest.raises(ValueError, match="127"):
+        R.HubbardRealSpace(R.CompositeFS(R.near_uniform(R.BoseFS, 40, 40), R.near_uniform(R.BoseFS, 40, 40)))
+    with pytest.raises(ValueError, match="components"):
+        R.HubbardRealSpace(R.CompositeFS(*[R.FermiFS((1, 0, 0))] * 5))
+    with pytest.raises(ValueError, match="symmetric"):                   # HubbardRealSpace.jl:188-189
+        R.HubbardRealSpace(mixed, u=[[1, 2], [3, 4]])
+    with pytest.raises(ValueError, match="length 2"):                    # :192-193
+        R.HubbardRealSpace(mixed, t=[1, 2, 3])

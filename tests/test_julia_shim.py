@@ -110,7 +110,7 @@ def c_struct_fields(name):
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     end = re.search(r"\}\s*" + name + r"\s*;", src).start()
     body = src[src.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
-    consts = {"RIMU_MAX_MODES": 128, "RIMU_MAX_TABLE_MODES": 64}
+    consts = {"RIMU_MAX_MODES": 128, "RIMU_MAX_TABLE_MODES": 64, "RIMU_MAX_COMPONENTS": 4}
     fields = []
     for decl in body.split(";"):
         decl = decl.strip()
@@ -166,7 +166,7 @@ def test_mirrored_structs_have_the_c_layout():
 
 
 KNOWN = set("""
-ccall check get joinpath unsafe_string throw print zeros cld enumerate onr set_bit! get_bit ntuple fieldtypes fieldtype Tuple Int
+ccall check get joinpath unsafe_string throw print zeros cld all map sum enumerate onr set_bit! get_bit ntuple fieldtypes fieldtype Tuple Int
 Ref finalizer max min length collect first last reduce vcat view isempty num_modes num_particles Int32 Int64 UInt64 UInt8 Float64
 Float32 Cint pad pad3 size vec permutedims get! rand typeof eltype zero iterate similar copy copy! sizeof fieldcount Dict IdDict
 Pair Symbol ArgumentError RimuB200Error Context GPUHam GPUDVec GPUWorkingMemory HamDesc StepParams StepStats FrozenDVec DVec

@@ -593,3 +593,78 @@ def test_extended_hubbard_mom1d_spectrum_is_contained_in_the_real_space_one():
     h1 = orc.OracleHam("HubbardMom1D", "bose", a, u=1.5, t=1.0)
     bs = h1.bfs_basis()
     assert np.allclose(h0.sparse_matrix(bs).toarray(), h1.sparse_matrix(bs).toarray(), rtol=1e-14, atol=1e-14)
+
+
+# ------------------------------------------------------------------ general CompositeFS on HubbardRealSpace
+def _comp(letters, onr, **kw):
+    return orc.OracleHam("HubbardRealSpace", "comp:" + letters, onr, **kw)
+
+
+def test_composite_two_component_relations_of_the_reference():
+    """test/Hamiltonians.jl:328-360: a single particle is a boson and a fermion at once, so BoseFS x BoseFS,
+    BoseFS x FermiFS and the two swapped orders (t, u permuted accordingly) have the same exact energy."""
+    three, one = (1, 1, 1, 0, 0, 0), (1, 0, 0, 0, 0, 0)
+    e2 = _comp("bb", (three, one), t=(1.0, 4.0), u=((2.0, 3.0), (3.0, 0.0)), dims=(6,)).exact_energy()
+    e3 = _comp("bf", (three, one), t=(1.0, 4.0), u=((2.0, 3.0), (3.0, 0.0)), dims=(6,)).exact_energy()
+    e4 = _comp("bb", (one, three), t=(4.0, 1.0), u=((0.0, 3.0), (3.0, 2.0)), dims=(6,)).exact_energy()
+    e5 = _comp("fb", (one, three), t=(4.0, 1.0), u=((0.0, 3.0), (3.0, 2.0)), dims=(6,)).exact_energy()
+    assert math.isclose(e2, e3, rel_tol=1e-4) and math.isclose(e3, e4, rel_tol=1e-4) and math.isclose(e4, e5, rel_tol=1e-4)
+    # :396-410 the same with a trap: component order does not matter
+    e3t = _comp("bb", (three, one), trap=((1.0,), (4.0,)), u=((2.0, 3.0), (3.0, 0.0)), dims=(6,)).exact_energy()
+    e4t = _comp("bb", (one, three), trap=((4.0,), (1.0,)), u=((0.0, 3.0), (3.0, 2.0)), dims=(6,)).exact_energy()
+    assert math.isclose(e3t, e4t, rel_tol=1e-4)
+
+
+def test_composite_fermions_equal_the_fermifs2c_path():
+    """CompositeFS(FermiFS, FermiFS) in the general packed layout is the same operator as the FermiFS2C path that is pinned by
+    test/Hamiltonians.jl:362-389 (-3 + -6 without interaction): element by element over the whole sector."""
+    a = ((1, 1, 1, 1, 0, 0), (1, 1, 0, 0, 0, 0))
+    for uu in (0.0, 1.0, -1.0):
+        kw = dict(t=(1.0, 2.0), u=((0.0, uu), (uu, 0.0)), dims=(6,))
+        hg, hf = _comp("ff", a, **kw), orc.OracleHam("HubbardRealSpace", "fermi2c", a, **kw)
+        assert hg.W == hf.W == 1  # 12 bits either way, and the same bit layout: the keys coincide
+        basis = hf.bfs_basis(None, 100000)
+        for key in basis:
+            kt = tuple(int(x) for x in np.atleast_1d(key))
+            assert hg.diagonal_element(kt) == hf.diagonal_element(kt)
+            assert hg.offdiagonals(kt) == hf.offdiagonals(kt)
+    assert math.isclose(_comp("ff", a, t=(1.0, 2.0), u=((0.0, 0.0), (0.0, 0.0)), dims=(6,)).exact_energy(), -9.0, rel_tol=1e-4)
+
+
+def test_composite_interaction_and_potential_by_hand():
+    """HubbardRealSpace.jl:18-106 by hand for three components (fermion, fermion, boson) on a 2x2 grid:
+    interaction = u_33/2 sum n(n-1) + sum_{s<t} u_st sum_i n_s(i) n_t(i); potential = sum_c sum_i v_c . x_i^2 n_c(i)."""
+    onr = ((1, 1, 0, 0), (1, 0, 0, 1), (0, 0, 2, 1))
+    u = ((0.0, 1.0, 2.0), (1.0, 0.0, 3.0), (2.0, 3.0, 1.5))
+    h = _comp("ffb", onr, t=(1.0, 2.0, 0.5), u=u, dims=(2, 2), fold=(True, False))
+    # self: 1.5 * (2*1)/2 = 1.5; f1.f2 = 1 (site 1) -> 1.0; f1.b = 0; f2.b = 1 (site 4) -> 3.0
+    assert h.diagonal_element(h.start_key) == 1.5 + 1.0 + 3.0
+    assert h.num_offdiagonals(h.start_key) == (2 + 2 + 2) * 4
+    # hops are listed component by component (:383-391); every hop changes exactly one component
+    for i, (k, v) in enumerate(h.offdiagonals(h.start_key)):
+        if v == 0.0:
+            continue
+        new = h.unpack(k)
+        changed = [c for c in range(3) if new[c] != onr[c]]
+        assert changed == [i // 8]
+        c = i // 8
+        if c < 2:
+            assert abs(v) == (1.0, 2.0)[c]  # fermions: -t * (+-1)
+        else:  # bosons: -t sqrt(n_src (n_dst + 1)) (fockaddress.jl:559-567)
+            (src,) = [j for j in range(4) if new[2][j] == onr[2][j] - 1]
+            (dst,) = [j for j in range(4) if new[2][j] == onr[2][j] + 1]
+            assert v == -0.5 * math.sqrt(onr[2][src] * (onr[2][dst] + 1))
+    ht = _comp("ffb", onr, u=u, dims=(2, 2), trap=((1.0, 0.0), (0.0, 2.0), (0.5, 0.25)))
+    # positions x = (-1, 0) per dimension, column-major sites: site1 (-1,-1), site2 (0,-1), site3 (-1,0), site4 (0,0)
+    pot = (1.0 * 1 + 0.0) + (0.0 + 0.0) + (2.0 * 1 + 0.0) + 2 * (0.5 * 1 + 0.0) + 1 * 0.0
+    assert math.isclose(ht.diagonal_element(ht.start_key), 5.5 + pot, rel_tol=1e-15)
+
+
+def test_composite_pack_roundtrip_two_words():
+    onr = (tuple(2 if i % 3 == 0 else 1 for i in range(27)), fermi_onr(27, (1, 5, 9, 14, 27)))
+    h = _comp("bf", onr, dims=(3, 3, 3))
+    assert h.W == 2 and h.unpack(h.start_key) == onr
+    # component 0 occupies the low N + M - 1 bits in the BoseFS layout, component 1 the next M bits
+    x = h.start_key[0] | (h.start_key[1] << 64)
+    nb = sum(onr[0]) + 27 - 1
+    assert bin(x & ((1 << nb) - 1)).count("1") == sum(onr[0]) and (x >> nb) == sum(1 << m for m in range(27) if onr[1][m])
