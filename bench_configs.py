@@ -113,12 +113,30 @@ def run_stochastic(R, cfg, args, world, rank, dist, torch, peak):
         dist.barrier()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # --device-steps K (one GPU): the timed steps go through rimu_advance in batches of K -- shift update and abort rules on the
+    # device, no host round trip between steps (what `solve` does by default for runs without post-step strategies).  The
+    # trajectory is the same; only the per-phase event times are not recorded.
+    batched = args.device_steps > 1 and world == 1
     e0.record(stream)
-    for _ in range(args.steps):
-        P = len(v)
-        s = one()
-        acc["att"] += s.spawn_attempts; acc["dep"] += s.deposits; acc["P"] += P; acc["U"] += s.local_len; acc["lb"] += s.len_before
-        acc["spawn"] += s.ms_spawn; acc["exch"] += s.ms_exchange; acc["merge"] += s.ms_compact
+    if batched:
+        from rimu_b200 import _lib
+        left = args.steps
+        while left > 0:
+            k = min(args.device_steps, left)
+            P = len(v)
+            v, pv, stats, shifts, done = R.advance(wm, v, pv, H, sp, _lib.SHIFT_DOUBLE_LOG_UPDATE, target_walkers=target,
+                                                   zeta=strat.zeta, xi=strat.xi, nsteps=k)
+            assert done == k, "the run ended inside the timed region"
+            for s in stats:
+                acc["att"] += s.spawn_attempts; acc["dep"] += s.deposits; acc["P"] += P; acc["U"] += s.local_len; acc["lb"] += s.len_before
+                P = s.local_len
+            left -= k
+    else:
+        for _ in range(args.steps):
+            P = len(v)
+            s = one()
+            acc["att"] += s.spawn_attempts; acc["dep"] += s.deposits; acc["P"] += P; acc["U"] += s.local_len; acc["lb"] += s.len_before
+            acc["spawn"] += s.ms_spawn; acc["exch"] += s.ms_exchange; acc["merge"] += s.ms_compact
     e1.record(stream)
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64)
@@ -138,7 +156,8 @@ def run_stochastic(R, cfg, args, world, rank, dist, torch, peak):
             "algorithmic_bytes_per_step_per_gpu": step_bytes, "hbm_gbs": step_bytes / (ms * 1e-3) / 1e9,
             "hbm_frac_of_measured_peak": step_bytes / (ms * 1e-3) / 1e9 / peak, "growth_steps": nsteps, "steps": K,
             "shift": sp.shift, "dtau": cfg["dtau"], "words": W, "buckets_per_gpu": int(s.buckets), "max_bucket_fill": int(s.max_bucket_fill),
-            "sent_records_per_step_per_gpu": int(s.sent_records)}
+            "sent_records_per_step_per_gpu": int(s.sent_records),
+            "driver": f"rimu_advance, batches of {min(args.device_steps, K)} steps" if batched else "rimu_step per step + host shift update"}
 
 
 def run_deterministic(R, cfg, args, world, rank, dist, torch, peak):
@@ -215,6 +234,7 @@ def main():
     ap.add_argument("--growth-seconds", type=float, default=300)
     ap.add_argument("--max-dim", type=float, default=2e8)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--device-steps", type=int, default=1, help="time the steps in batches of K through rimu_advance (one GPU)")
     ap.add_argument("--dictionary-hv", action="store_true", help="config 3 through the dictionary path (records + annihilation)")
     args = ap.parse_args()
     import torch

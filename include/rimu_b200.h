@@ -313,6 +313,38 @@ int rimu_sector_to_vec(rimu_sector *s, const double *d, rimu_vec *v);
 int rimu_step(rimu_ctx *ctx, const rimu_ham *ham, const rimu_step_params *params,
               rimu_vec *src, rimu_vec *dst, rimu_step_stats *stats_out);
 
+/* ---- a batch of steps ------------------------------------------------------
+ * nsteps x { apply_operator!(wm, w, v, FirstOrderTransitionOperator(H, shift, dt)); swap(v, w); update_shift_parameters! }
+ * = the body of advance!(::FCIQMC) (fciqmc.jl:126-181) with the shift strategies of
+ * strategies_and_params/shiftstrategy.jl:77-213 and the abort rules of the reference (dead population, max_length, a strategy
+ * that asks to stop) -- evaluated ON THE DEVICE, so that the kernels of step k+1 are enqueued before step k has finished.
+ * A step of a small problem (the reference's own benchmark sizes, BASELINE config 1) is bound by launch latency and by the
+ * host round trip of the walker number; a batch has neither.  Step k uses the Philox key of (params->seed, params->step + k):
+ * the trajectory is the one nsteps rimu_step calls produce (the device evaluates the same shift formulas; its log() may
+ * differ from the host's in the last bit).  One rank, partitioned method, not ordered: otherwise, and for vectors too
+ * large to profit, the call simply runs step by step.  A chunk of steps that runs out of working memory is rolled back to
+ * its snapshot and repeated step by step, so the call never returns a half-finished state. */
+enum { RIMU_SHIFT_DONT_UPDATE = 0,                     /* shiftstrategy.jl:77-91 (stops once norm >= target_walkers) */
+       RIMU_SHIFT_LOG_UPDATE = 1,                      /* :124-146 */
+       RIMU_SHIFT_LOG_UPDATE_AFTER_TARGET = 2,         /* :100-122 */
+       RIMU_SHIFT_DOUBLE_LOG_UPDATE = 3,               /* :160-181 */
+       RIMU_SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET = 4   /* :190-215 */ };
+typedef struct {
+    int32_t strategy;        /* RIMU_SHIFT_* */
+    int32_t shift_mode;      /* in/out: DefaultShiftParameters.shift_mode (shiftstrategy.jl:32-38) */
+    double target_walkers, zeta, xi;
+    double shift, pnorm;     /* in/out: shift and previous walker number */
+    int64_t max_length;      /* abort when the vector grows beyond this many entries (0 = no limit) */
+} rimu_shift_params;
+/* v: current vector, w: scratch partner of the same type.  params->shift is ignored (sp->shift is the shift).  On return
+ * *steps_done steps were taken (< nsteps only when the run ended: dead population, max_length, DontUpdate target reached --
+ * the state is that of the last step taken, as in the reference), stats_out[k] / shift_out[k] (optional) hold the statistics
+ * of step k and the shift AFTER its update, and *result_in_w tells which vector holds the current state. */
+int rimu_advance(rimu_ctx *ctx, const rimu_ham *ham, const rimu_step_params *params, rimu_shift_params *sp,
+                 rimu_vec *v, rimu_vec *w, int64_t nsteps, rimu_step_stats *stats_out, double *shift_out,
+                 int64_t *steps_done, int32_t *result_in_w);
+int rimu_sizeof_shift_params(void);
+
 /* per-step Philox key derivation, exported so hosts/oracles can reproduce streams */
 void rimu_step_key(uint64_t seed, uint64_t step, uint32_t key_out[2]);
 void rimu_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -534,6 +534,7 @@ function __init__()
     @assert sizeof(HamDesc) == ccall((:rimu_sizeof_ham_desc, LIB), Cint, ())
     @assert sizeof(StepParams) == ccall((:rimu_sizeof_step_params, LIB), Cint, ())
     @assert sizeof(StepStats) == ccall((:rimu_sizeof_step_stats, LIB), Cint, ())
+    @assert sizeof(ShiftParams) == ccall((:rimu_sizeof_shift_params, LIB), Cint, ())
 end
 
 mutable struct GPUWorkingMemory{S,I}
@@ -612,6 +613,51 @@ function apply_operator!(wm::GPUWorkingMemory, target::GPUDVec, source::GPUDVec,
     wm.last_stats = stats[]
     names, values = step_stats_tuple(wm.style, stats[])
     return names, values, wm, target
+end
+
+# ---- a batch of steps: the body of advance!(::FCIQMC) (fciqmc.jl:126-181) x nsteps with the shift update on the device
+struct ShiftParams                    # == rimu_shift_params; asserted against rimu_sizeof_shift_params()
+    strategy::Int32
+    shift_mode::Int32
+    target_walkers::Float64
+    zeta::Float64
+    xi::Float64
+    shift::Float64
+    pnorm::Float64
+    max_length::Int64
+end
+# shiftstrategy.jl:77-215 -> (RIMU_SHIFT_* id, target_walkers, zeta, xi)
+shift_strategy_params(s::Rimu.DontUpdate) = (Int32(0), Float64(s.target_walkers), 0.0, 0.0)
+shift_strategy_params(s::Rimu.LogUpdate) = (Int32(1), 0.0, Float64(s.ζ), 0.0)
+shift_strategy_params(s::Rimu.LogUpdateAfterTargetWalkers) = (Int32(2), Float64(s.target_walkers), Float64(s.ζ), 0.0)
+shift_strategy_params(s::Rimu.DoubleLogUpdate) = (Int32(3), Float64(s.target_walkers), Float64(s.ζ), Float64(s.ξ))
+shift_strategy_params(s::Rimu.DoubleLogUpdateAfterTargetWalkers) = (Int32(4), Float64(s.target_walkers), Float64(s.ζ), Float64(s.ξ))
+shift_strategy_params(s) = throw(ArgumentError("$(typeof(s)) needs the vectors on the host every step: use the step-by-step loop"))
+
+"""
+    advance_steps!(wm, v, pv, hamiltonian, shift_parameters, shift_strategy, nsteps; max_length=0)
+        -> (v, pv, stats::Vector{StepStats}, shifts::Vector{Float64})
+
+`nsteps` iterations of `apply_operator!`, swap and `update_shift_parameters!` in one call (`rimu_advance`); `shift_parameters`
+(Rimu's `DefaultShiftParameters`) is updated in place.  Fewer than `nsteps` entries come back when the run ended.
+"""
+function advance_steps!(wm::GPUWorkingMemory, v::GPUDVec, pv::GPUDVec, ham::AbstractHamiltonian, sp, strategy, nsteps::Integer; max_length::Integer=0)
+    sty, pt, rt, at, ct = style_params(wm.style)
+    ir, it = initiator_params(wm.initiator)
+    params = Ref(StepParams(sty, 0, Float64(sp.shift), Float64(sp.time_step), 1.0, pt, rt, at, ct, wm.seed, wm.counter, 0, ir, Int32(wm.ordered), it))
+    id, target, ζ, ξ = shift_strategy_params(strategy)
+    shp = Ref(ShiftParams(id, Int32(sp.shift_mode), target, ζ, ξ, Float64(sp.shift), Float64(sp.pnorm), Int64(max_length)))
+    stats = Vector{StepStats}(undef, nsteps)
+    shifts = zeros(Float64, nsteps)
+    done, in_w = Ref{Int64}(0), Ref{Int32}(0)
+    check(ccall((:rimu_advance, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{StepParams}, Ptr{ShiftParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{StepStats}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+                wm.ctx.ptr, gpu_ham(ham, wm.ctx).ptr, params, shp, v.ptr, pv.ptr, nsteps, stats, shifts, done, in_w))
+    wm.counter += done[]
+    sp.shift, sp.pnorm, sp.shift_mode = shp[].shift, shp[].pnorm, shp[].shift_mode != 0
+    done[] > 0 && (wm.last_stats = stats[done[]])
+    in_w[] != 0 && ((v, pv) = (pv, v))
+    return v, pv, stats[1:done[]], shifts[1:done[]]
 end
 
 function mul!(y::GPUDVec, op::AbstractHamiltonian, x::GPUDVec, wm=working_memory(x))   # pdvec.jl:810-822

@@ -19,7 +19,7 @@ from .stochasticstyles import (IsDeterministic, IsDynamicSemistochastic, IsStoch
                                IsStochasticWithThreshold, NoCompression, StochasticStyle, ThresholdCompression,
                                default_style, step_stats,
                                CoherentInitiator, Initiator, InitiatorRule, NonInitiator, SimpleInitiator)
-from .dictvectors import (DVec, FirstOrderTransitionOperator, FrozenDVec, GPUDVec, InitiatorDVec, PDVec, WorkingMemory, apply_operator, dot, mul,
+from .dictvectors import (DVec, FirstOrderTransitionOperator, FrozenDVec, GPUDVec, InitiatorDVec, PDVec, WorkingMemory, advance, apply_operator, dot, mul,
                           walkernumber_and_length, working_memory)
 from .fciqmc import (AllOverlaps, DataFrame, DontUpdate, DoubleLogUpdate, DoubleLogUpdateAfterTargetWalkers, GramSchmidt, LogUpdate, ReportDFAndInfo, ReportToFile, load_df,
                      LogUpdateAfterTargetWalkers,

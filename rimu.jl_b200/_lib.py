@@ -137,6 +137,18 @@ class StepStats(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class ShiftParams(C.Structure):
+    """rimu_shift_params: shift strategy + DefaultShiftParameters of rimu_advance"""
+    _fields_ = [
+        ("strategy", C.c_int32), ("shift_mode", C.c_int32),
+        ("target_walkers", C.c_double), ("zeta", C.c_double), ("xi", C.c_double),
+        ("shift", C.c_double), ("pnorm", C.c_double),
+        ("max_length", C.c_int64),
+    ]
+
+
+SHIFT_DONT_UPDATE, SHIFT_LOG_UPDATE, SHIFT_LOG_UPDATE_AFTER_TARGET, SHIFT_DOUBLE_LOG_UPDATE, SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET = range(5)
+
 # every symbol include/rimu_b200.h declares: name -> (restype, argtypes)
 _vp, _u64p, _i64p, _f64p, _u32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_uint32)
 SYMBOLS = {
@@ -210,6 +222,9 @@ SYMBOLS = {
     "rimu_annihilate": (C.c_int, [_vp, _u64p, _vp, C.c_int64, C.c_int]),
     "rimu_annihilate_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "rimu_step": (C.c_int, [_vp, _vp, C.POINTER(StepParams), _vp, _vp, C.POINTER(StepStats)]),
+    "rimu_advance": (C.c_int, [_vp, _vp, C.POINTER(StepParams), C.POINTER(ShiftParams), _vp, _vp, C.c_int64, C.POINTER(StepStats), _f64p,
+                               _i64p, C.POINTER(C.c_int32)]),
+    "rimu_sizeof_shift_params": (C.c_int, []),
     "rimu_step_key": (None, [C.c_uint64, C.c_uint64, _u32p]),
     "rimu_philox4x32_10": (None, [_u32p, _u32p, _u32p]),
 }

@@ -30,6 +30,7 @@ extern "C" int rimu_version(void) { return 100; }
 extern "C" int rimu_sizeof_ham_desc(void) { return (int)sizeof(rimu_ham_desc); }
 extern "C" int rimu_sizeof_step_params(void) { return (int)sizeof(rimu_step_params); }
 extern "C" int rimu_sizeof_step_stats(void) { return (int)sizeof(rimu_step_stats); }
+extern "C" int rimu_sizeof_shift_params(void) { return (int)sizeof(rimu_shift_params); }
 
 // ---------------------------------------------------------------- NCCL (resolved lazily; same soname as torch's bundled copy)
 NcclApi g_nccl;
@@ -125,6 +126,8 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->spare_keys); cudaFree(c->spare_vals); cudaFree(c->spare_diag);
     for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
     cudaFree(c->d_red); cudaFreeHost(c->h_red); cudaFree(c->d_ord);
+    cudaFree(c->d_ring); cudaFreeHost(c->h_ring); cudaFree(c->d_ctl); cudaFreeHost(c->h_ctl); cudaFree(c->d_shiftlog); cudaFreeHost(c->h_shiftlog);
+    cudaFree(c->snap_keys); cudaFree(c->snap_vals); cudaFree(c->snap_diag); cudaFree(c->snap_seg_start); cudaFree(c->snap_seg_len);
     cudaGetLastError(); // teardown is best effort (e.g. closing an IPC mapping whose exporter is already gone): never leave a stale error behind
     if (c->live_vecs > 0) { // vectors still point at this context: keep the struct and the stream until the last one goes
         c->dead = 1;
@@ -1371,3 +1374,218 @@ extern "C" int rimu_step(rimu_ctx *c, const rimu_ham *h, const rimu_step_params 
         return 0;
     }
 }
+
+// ---------------------------------------------------------------- a batch of steps (advance!, fciqmc.jl:126-181)
+// update_shift_parameters! on the host (strategies_and_params/shiftstrategy.jl:77-215): the same formulas as advance_ctl_kernel
+static bool host_shift_update(rimu_shift_params *sp, double dtau, double tnorm, int64_t len) {
+    bool proceed = true;
+    if (len <= 0) return proceed;
+    switch (sp->strategy) {
+    case RIMU_SHIFT_DONT_UPDATE: proceed = tnorm < sp->target_walkers; break;
+    case RIMU_SHIFT_LOG_UPDATE: sp->shift -= sp->zeta / dtau * log(tnorm / sp->pnorm); sp->pnorm = tnorm; break;
+    case RIMU_SHIFT_LOG_UPDATE_AFTER_TARGET:
+        if (sp->shift_mode || tnorm > sp->target_walkers) { sp->shift_mode = 1; sp->shift -= sp->zeta / dtau * log(tnorm / sp->pnorm); }
+        sp->pnorm = tnorm; break;
+    case RIMU_SHIFT_DOUBLE_LOG_UPDATE:
+        sp->shift -= sp->xi / dtau * log(tnorm / sp->target_walkers) + sp->zeta / dtau * log(tnorm / sp->pnorm);
+        sp->pnorm = tnorm; break;
+    default:
+        if (sp->shift_mode || tnorm > sp->target_walkers) {
+            sp->shift_mode = 1;
+            sp->shift -= sp->xi / dtau * log(tnorm / sp->target_walkers) + sp->zeta / dtau * log(tnorm / sp->pnorm);
+        }
+        sp->pnorm = tnorm; break;
+    }
+    return proceed;
+}
+
+static void stats_to_abi(const StatsDev &g, rimu_step_stats *out, u32 nb) {
+    memset(out, 0, sizeof(*out));
+    out->exact_steps = g.exact_steps; out->inexact_steps = g.inexact_steps; out->spawn_attempts = g.spawn_attempts;
+    out->len_before = g.len_before; out->len = g.len;
+    out->spawns = g.spawns; out->deaths = g.deaths; out->clones = g.clones; out->zombies = g.zombies; out->norm1 = g.norm1;
+    out->ispawns = g.ispawns; out->ideaths = g.ideaths; out->iclones = g.iclones; out->izombies = g.izombies; out->inorm1 = g.inorm1;
+    out->local_len = (i64)g.out_count; out->deposits = g.deposits;
+    out->buckets = (int64_t)nb; out->max_bucket_fill = (int64_t)g.max_fill;
+}
+
+static int ensure_advance_buffers(rimu_ctx *c, const rimu_vec *cur) {
+    if (!c->d_ring) {
+        CUDA_TRY(rimu_malloc(&c->d_ring, RIMU_ADVANCE_CHUNK * sizeof(StatsDev)));
+        CUDA_TRY(cudaMallocHost(&c->h_ring, RIMU_ADVANCE_CHUNK * sizeof(StatsDev)));
+        CUDA_TRY(rimu_malloc(&c->d_ctl, sizeof(StepCtl)));
+        CUDA_TRY(cudaMallocHost(&c->h_ctl, 2 * sizeof(StepCtl))); // [0]: upload image, [1]: read-back
+        CUDA_TRY(rimu_malloc(&c->d_shiftlog, 2 * RIMU_ADVANCE_CHUNK * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&c->h_shiftlog, 2 * RIMU_ADVANCE_CHUNK * sizeof(double)));
+    }
+    if (c->snap_cap < (u64)cur->n) {
+        cudaFree(c->snap_keys); cudaFree(c->snap_vals); cudaFree(c->snap_diag);
+        c->snap_keys = c->snap_vals = nullptr; c->snap_diag = nullptr; c->snap_cap = 0;
+        const u64 cap = (u64)cur->n + (u64)cur->n / 2 + 1024;
+        CUDA_TRY(rimu_malloc(&c->snap_keys, cap * c->W * sizeof(u64)));
+        CUDA_TRY(rimu_malloc(&c->snap_vals, cap * sizeof(u64)));
+        CUDA_TRY(rimu_malloc(&c->snap_diag, cap * sizeof(double)));
+        c->snap_cap = cap;
+    }
+    if (c->snap_nb_cap < cur->nb) {
+        cudaFree(c->snap_seg_start); cudaFree(c->snap_seg_len);
+        c->snap_seg_start = nullptr; c->snap_seg_len = nullptr; c->snap_nb_cap = 0;
+        const u64 cap = (u64)cur->nb + cur->nb / 2 + 64;
+        CUDA_TRY(rimu_malloc(&c->snap_seg_start, cap * sizeof(u64)));
+        CUDA_TRY(rimu_malloc(&c->snap_seg_len, cap * sizeof(u32)));
+        c->snap_nb_cap = cap;
+    }
+    return 0;
+}
+
+extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_params *prm, rimu_shift_params *sp, rimu_vec *v, rimu_vec *w,
+                            int64_t nsteps, rimu_step_stats *stats_out, double *shift_out, int64_t *steps_done, int32_t *result_in_w) {
+    if (!c || !h || !prm || !sp || !v || !w || !steps_done || !result_in_w) return fail(RIMU_ERR_INVALID, "null argument");
+    if (sp->strategy < RIMU_SHIFT_DONT_UPDATE || sp->strategy > RIMU_SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET)
+        return fail(RIMU_ERR_INVALID, "unknown shift strategy %d", sp->strategy);
+    if (prm->plain_h) return fail(RIMU_ERR_INVALID, "rimu_advance steps with FirstOrderTransitionOperator (plain_h must be 0)");
+    if (!(prm->time_step > 0.0)) return fail(RIMU_ERR_INVALID, "time_step must be positive");
+    const HkOps *ops = hk_ops(h);
+    if (!ops) return RIMU_ERR_INVALID;
+    const bool is_int = prm->style == RIMU_STYLE_INTEGER;
+    if (v == w) return fail(RIMU_ERR_INVALID, "the two vectors must not alias (Interfaces/dictvectors.jl:115-117)");
+    if (v->ctx != c || w->ctx != c) return fail(RIMU_ERR_INVALID, "vectors belong to another context");
+    if (v->vt != w->vt || is_int != (v->vt == RIMU_VAL_I64))
+        return fail(RIMU_ERR_INVALID, "IsStochasticInteger needs Int64 vectors; the other styles need Float64 vectors");
+    if (prm->style < 0 || prm->style > 3) return fail(RIMU_ERR_INVALID, "unknown stochastic style %d", prm->style);
+    if (is_int && prm->proj_threshold != 0.0) return fail(RIMU_ERR_INVALID, "Thresholding not supported for integer spawns");
+    if (prm->initiator_rule < 0 || prm->initiator_rule > 3) return fail(RIMU_ERR_INVALID, "unknown initiator rule %d", prm->initiator_rule);
+    if (c->detached) return fail(RIMU_ERR_INVALID, "this context was detached from its peers (rimu_comm_detach): no further steps");
+    if (nsteps < 0) return fail(RIMU_ERR_INVALID, "nsteps must not be negative");
+    rimu_vec *cur = v, *oth = w;
+    int64_t done = 0;
+    bool ended = false;
+    *steps_done = 0; *result_in_w = 0;
+    rimu_step_params q = *prm;
+    // one step through rimu_step (validation, sizing, re-segmentation, retries) + the host's shift update
+    auto single = [&]() -> int {
+        q.shift = sp->shift; q.step = prm->step + (uint64_t)done;
+        rimu_step_stats st;
+        TRY(rimu_step(c, h, &q, cur, oth, &st));
+        std::swap(cur, oth);
+        const double tnorm = is_int ? (double)st.inorm1 : st.norm1;
+        const bool proceed = host_shift_update(sp, prm->time_step, tnorm, st.len);
+        if (stats_out) stats_out[done] = st;
+        if (shift_out) shift_out[done] = sp->shift;
+        done++;
+        if (st.len == 0 || (sp->max_length > 0 && st.len > sp->max_length) || !proceed) ended = true;
+        return 0;
+    };
+    while (done < nsteps && !ended) {
+        const bool batchable = c->nranks == 1 && c->method == RIMU_ANNIHILATE_PARTITION && !prm->ordered && cur->nb != 0 && cur->n > 0 &&
+                               (u64)cur->n <= RIMU_ADVANCE_MAX_N && cur->diag && cur->diag_uid == h->uid && nsteps - done >= 2 &&
+                               choose_buckets(c, cur, (double)cur->n) == cur->nb;
+        if (!batchable) { TRY(single()); continue; }
+        // ---- a chunk of K steps, enqueued back to back
+        TRY(enter_ctx(c));
+        const int K = (int)std::min<int64_t>(nsteps - done, RIMU_ADVANCE_CHUNK);
+        const u32 nb = cur->nb;
+        const u32 nlane = prm->initiator_rule ? 3u : 1u;
+        // room: both vectors must hold whatever a step of this chunk produces; sized for twice the current length (a step that
+        // outgrows it stops the chunk, which is then repeated step by step with rimu_step's own growth logic)
+        const u64 want = (u64)cur->n * 2 + 4096;
+        if (cur->cap < want) TRY(rimu_vec_reserve(cur, want));
+        if (oth->cap < want) { oth->n = 0; TRY(rimu_vec_reserve(oth, want)); }
+        TRY(ensure_seg(oth, nb));
+        TRY(ensure_diag(oth));
+        if (!cur->diag || cur->diag_cap < cur->cap) { TRY(single()); continue; } // (cannot happen after a reserve; be safe)
+        TRY(ensure_part(c, nb, nlane));
+        TRY(ensure_heavy(c, std::max(cur->cap, oth->cap)));
+        TRY(ensure_advance_buffers(c, cur));
+        // snapshot of the chunk's source
+        const i64 n0 = cur->n;
+        CUDA_TRY(cudaMemcpyAsync(c->snap_keys, cur->keys, (size_t)n0 * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->snap_vals, cur->vals, (size_t)n0 * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->snap_diag, cur->diag, (size_t)n0 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->snap_seg_start, cur->seg_start, (size_t)nb * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->snap_seg_len, cur->seg_len, (size_t)nb * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
+        const rimu_shift_params sp0 = *sp;
+        rimu_vec *const cur0 = cur;
+        // controller + statistics ring
+        StepCtl &hc = c->h_ctl[0];
+        hc.shift = sp->shift; hc.pnorm = sp->pnorm; hc.shift_mode = sp->shift_mode; hc.stop = 0; hc.steps_done = 0; hc.n = (unsigned long long)n0;
+        CUDA_TRY(cudaMemcpyAsync(c->d_ctl, &hc, sizeof(StepCtl), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_ring, 0, (size_t)K * sizeof(StatsDev), c->stream));
+        if (!c->rcnt_clean) CUDA_TRY(cudaMemsetAsync(c->part.rcnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream));
+        c->rcnt_clean = 0;
+        StepDev p;
+        memset(&p, 0, sizeof(p));
+        p.style = prm->style; p.dtau = prm->time_step; p.boost = prm->boost;
+        p.proj_thr = prm->proj_threshold; p.rel_thr = prm->rel_threshold; p.abs_thr = prm->abs_threshold;
+        p.compress_thr = prm->compress_threshold;
+        p.rank = 0; p.nranks = 1;
+        p.init_rule = prm->initiator_rule; p.init_thr = prm->initiator_threshold;
+        p.ctl = c->d_ctl;
+        AdvanceDev a;
+        a.strategy = sp->strategy; a.is_int = is_int ? 1 : 0; a.target_walkers = sp->target_walkers; a.zeta = sp->zeta; a.xi = sp->xi;
+        a.dtau = prm->time_step; a.max_length = sp->max_length; a.heavy_cap = c->heavy.cap;
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        rimu_vec *src = cur, *dst = oth;
+        for (int k = 0; k < K; k++) {
+            uint32_t key[2];
+            rimu_step_key(prm->seed, prm->step + (uint64_t)done + (uint64_t)k, key);
+            p.k0 = key[0]; p.k1 = key[1];
+            TRY(ops->enqueue(c, h, p, src, dst, is_int, nb, c->d_ring + k));
+            a.dst_cap = dst->cap;
+            advance_ctl_kernel<<<1, 1, 0, c->stream>>>(c->d_ctl, c->d_ring + k, a, c->d_shiftlog + 2 * k);
+            c->launches += 1;
+            std::swap(src, dst);
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->h_ring, c->d_ring, (size_t)K * sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->h_shiftlog, c->d_shiftlog, (size_t)K * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(&c->h_ctl[1], c->d_ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const StepCtl &rc = c->h_ctl[1];
+        if (rc.stop == 2) {
+            // some step of the chunk outgrew the working memory or a vector: back to the snapshot, repeat the chunk step by step
+            // (same seeds and steps: the same trajectory)
+            CUDA_TRY(cudaMemcpyAsync(cur0->keys, c->snap_keys, (size_t)n0 * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(cur0->vals, c->snap_vals, (size_t)n0 * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(cur0->diag, c->snap_diag, (size_t)n0 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(cur0->seg_start, c->snap_seg_start, (size_t)nb * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(cur0->seg_len, c->snap_seg_len, (size_t)nb * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
+            cur = cur0; oth = cur0 == v ? w : v;
+            cur->n = n0; cur->nb = nb; cur->diag_uid = h->uid; cur->version++;
+            oth->n = 0; oth->nb = 0; oth->diag_uid = 0; oth->version++;
+            *sp = sp0;
+            for (int k = 0; k < K && !ended; k++) TRY(single());
+            continue;
+        }
+        const int kd = (int)rc.steps_done; // steps of this chunk that were taken (all of them unless the run ended)
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]);
+        for (int k = 0; k < kd; k++) {
+            if (stats_out) {
+                stats_to_abi(c->h_ring[k], &stats_out[done + k], nb);
+                stats_out[done + k].ms_total = ms / (float)(kd > 0 ? kd : 1);
+            }
+            if (shift_out) shift_out[done + k] = c->h_shiftlog[2 * k];
+        }
+        if (kd > 0) {
+            const StatsDev &last = c->h_ring[kd - 1];
+            if (kd & 1) std::swap(cur, oth);
+            cur->n = (i64)last.out_count; cur->nb = nb; cur->diag_uid = h->uid; cur->version++;
+            oth->version++; // (holds the step before: still a valid segmented vector, but nobody should rely on it)
+            if (kd >= 2) { oth->n = (i64)c->h_ring[kd - 2].out_count; oth->nb = nb; oth->diag_uid = h->uid; }
+            sp->shift = rc.shift; sp->pnorm = rc.pnorm; sp->shift_mode = rc.shift_mode;
+            c->last_dst_uid = cur->uid; c->last_dst_version = cur->version; c->last_g_len = (double)last.len;
+            const double par = kd >= 2 ? (double)c->h_ring[kd - 2].out_count : (double)n0;
+            if (par > 0) c->rec_per_parent = 0.5 * c->rec_per_parent + 0.5 * (double)last.records / par;
+            c->last_max_fill = last.max_fill;
+            c->rcnt_clean = 1; // every merge that ran cleared the counters it consumed; stopped steps appended nothing
+        } else c->rcnt_clean = 1;
+        done += kd;
+        if (rc.stop == 1) ended = true;
+    }
+    *steps_done = done;
+    *result_in_w = cur == w ? 1 : 0;
+    return 0;
+}
+

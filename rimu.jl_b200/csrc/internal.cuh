@@ -142,7 +142,17 @@ struct rimu_ctx {
                              //   vector swaps it into these buffers and keeps the old ones as the next spare (no cudaMalloc,
                              //   no synchronisation when a host-fed vector is re-segmented every step)
     u64 last_max_fill;
+    // rimu_advance (batches of steps without host synchronisation): one statistics block per step of a chunk, the device-resident
+    // controller, the per-step shift log, and a snapshot of the chunk's first source vector (restored when a step of the chunk
+    // ran out of working memory: the chunk is then repeated step by step)
+    StatsDev *d_ring = nullptr, *h_ring = nullptr;
+    StepCtl *d_ctl = nullptr, *h_ctl = nullptr;
+    double *d_shiftlog = nullptr, *h_shiftlog = nullptr;
+    u64 *snap_keys = nullptr, *snap_vals = nullptr, *snap_seg_start = nullptr; double *snap_diag = nullptr; u32 *snap_seg_len = nullptr;
+    u64 snap_cap = 0, snap_nb_cap = 0;
 };
+#define RIMU_ADVANCE_CHUNK 128        /* steps enqueued per host synchronisation */
+#define RIMU_ADVANCE_MAX_N (1u << 21) /* batches pay off while a step is launch/latency bound; beyond this, step by step */
 RIMU_INTERNAL int enter_ctx(rimu_ctx *c);
 struct rimu_ham {
     rimu_ham_desc desc;
@@ -216,6 +226,9 @@ struct HkOps {
     int (*offdiag)(rimu_ctx *c, const rimu_ham *h, const u64 *d_key, i64 first0, i64 count, u64 *d_keys_out, double *d_vals);
     // y = H x over a complete sector in dense (combinadic-rank) indexing: sector.cuh
     int (*sector_mul)(rimu_ctx *c, const rimu_ham *h, const SectorDev *s, const u64 *d_keys, const double *d_x, double *d_y, u64 dim);
+    // batch mode (rimu_advance): enqueue the kernels of ONE partitioned step whose shift / source length / stop flag live in
+    // *p.ctl; statistics go to *st; no events, no memsets, no synchronisation.  The caller has sized every buffer.
+    int (*enqueue)(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, bool is_int, u32 nb, StatsDev *st);
 };
 RIMU_INTERNAL const HkOps *rimu_hk_ops_0();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_1();

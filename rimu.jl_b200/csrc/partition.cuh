@@ -179,6 +179,10 @@ __global__ void __launch_bounds__(SPAWN_NT, SPAWN_MINB)
 spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
                   PartDev pt, ExchangeDev xch, HeavyDev hv, StatsDev *st) {
     typedef typename BitsT<W>::type B;
+    if (p.ctl) { // batch of steps: the source is the previous step's result, its length is known on the device only
+        if (p.ctl->stop) return;
+        n = (i64)p.ctl->n;
+    }
     __shared__ u32 s_off[SPAWN_NT + 1];
     __shared__ u64 s_keys[SPAWN_NT * W];
     __shared__ VT s_vals[SPAWN_NT];
@@ -277,6 +281,7 @@ spawn_heavy_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys
     typedef typename BitsT<W>::type B;
     __shared__ u64 acc[ACC_MAX];
     __shared__ RouteSmem s_route;
+    if (p.ctl && p.ctl->stop) return;
     const u64 packed = *hv.packed;
     const u64 total = packed & 0xffffffffull;
     u64 nitems = packed >> 32;
@@ -445,6 +450,8 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     // only an address's own parent can deposit there
     constexpr bool initm = MODE == 0 && INIT; // separate instantiation: the plain step pays nothing for the lanes
     u64 *sunsafe = reinterpret_cast<u64 *>(pidx + CAP);
+    if (p.ctl && p.ctl->stop) return;         // batch of steps that has ended: leave both vectors as they are
+    const double shift = p.ctl ? p.ctl->shift : p.shift;
     __shared__ u32 s_warp[NW];
     __shared__ u64 s_base;
     __shared__ u32 s_arrive;
@@ -601,7 +608,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                     // diagonal_step! (spawning.jl:73-77) through FirstOrderTransitionOperator (fciqmc.jl:93-96)
                     const double val = (double)pv;
                     const double hd = src.diag ? src.diag[p0 + i] : ham_diagonal<HK, B>(hl, key);
-                    const double d = p.plain_h ? hd : 1 - p.dtau * (hd - p.shift);
+                    const double d = p.plain_h ? hd : 1 - p.dtau * (hd - shift);
                     double rr = 0.0;
                     const double thr = is_int ? 0.0 : p.proj_thr;
                     if (is_int || thr > 0.0) {
@@ -902,6 +909,51 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     for (int o = 16; o > 0; o >>= 1) max_fill = max(max_fill, __shfl_xor_sync(0xffffffffu, max_fill, o));
     if (lane == 0) atomicMax(&st->max_fill, (unsigned long long)max_fill);
     if (tid == 0 && nrec_sum) atomicAdd(&st->records, (u64)nrec_sum);
+}
+
+// ---------------------------------------------------------------- controller of a batch of steps (rimu_advance)
+// After the merge of a step: update_shift_parameters! (strategies_and_params/shiftstrategy.jl:77-213) and the abort rules of
+// advance! (fciqmc.jl:126-181: dead population, max_length, a strategy that asks to stop), evaluated by ONE device thread so
+// that the next step's kernels -- already enqueued -- find their shift, their source length and the stop flag in HBM.
+struct AdvanceDev {
+    int strategy;          // RIMU_SHIFT_*
+    int is_int;
+    double target_walkers, zeta, xi, dtau;
+    long long max_length;  // 0 = no limit
+    u64 dst_cap;           // capacity of the vector this step wrote
+    u64 heavy_cap;
+};
+static __global__ void advance_ctl_kernel(StepCtl *ctl, const StatsDev *st, AdvanceDev a, double *shift_log) {
+    if (ctl->stop) return;
+    if (st->overflow_table || st->out_count > a.dst_cap || (st->heavy_packed >> 32) > a.heavy_cap) { ctl->stop = 2; return; }
+    const double tnorm = a.is_int ? (double)st->inorm1 : st->norm1;
+    const long long len = st->len;
+    bool proceed = true;
+    if (len > 0) {
+        double shift = ctl->shift;
+        const double pnorm = ctl->pnorm;
+        switch (a.strategy) {
+        case 0: proceed = tnorm < a.target_walkers; break;                                   // DontUpdate (pnorm untouched)
+        case 1: shift -= a.zeta / a.dtau * log(tnorm / pnorm); ctl->pnorm = tnorm; break;     // LogUpdate
+        case 2:                                                                               // LogUpdateAfterTargetWalkers
+            if (ctl->shift_mode || tnorm > a.target_walkers) { ctl->shift_mode = 1; shift -= a.zeta / a.dtau * log(tnorm / pnorm); }
+            ctl->pnorm = tnorm; break;
+        case 3:                                                                               // DoubleLogUpdate
+            shift -= a.xi / a.dtau * log(tnorm / a.target_walkers) + a.zeta / a.dtau * log(tnorm / pnorm);
+            ctl->pnorm = tnorm; break;
+        default:                                                                              // DoubleLogUpdateAfterTargetWalkers
+            if (ctl->shift_mode || tnorm > a.target_walkers) {
+                ctl->shift_mode = 1;
+                shift -= a.xi / a.dtau * log(tnorm / a.target_walkers) + a.zeta / a.dtau * log(tnorm / pnorm);
+            }
+            ctl->pnorm = tnorm; break;
+        }
+        ctl->shift = shift;
+    }
+    shift_log[0] = ctl->shift; shift_log[1] = (double)ctl->shift_mode;
+    ctl->n = st->out_count;
+    ctl->steps_done += 1;
+    if (len == 0 || (a.max_length > 0 && len > a.max_length) || !proceed) ctl->stop = 1;
 }
 
 // sum of the per-warp partial walker numbers of an ordered merge, in index order (one thread: the order IS the point)

@@ -124,6 +124,34 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
 }
 
 
+// batch mode: the kernels of one step, nothing else (rimu_advance sized the buffers, cleared the statistics ring and the
+// fill counters, and follows every step with the controller kernel)
+template <int HK, int W, class VT>
+static int step_part_enqueue(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, u32 nb, StatsDev *st) {
+    const size_t smem_init = (size_t)part_cap_items(W) * 8;
+    static bool attr_set[3][2] = {};
+    if (!attr_set[W][std::is_integral<VT>::value]) {
+        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
+        CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(part_smem_bytes(W) + smem_init)));
+        attr_set[W][std::is_integral<VT>::value] = true;
+    }
+    HeavyDev hv = c->heavy;
+    hv.packed = (u64 *)&st->heavy_packed;
+    // the source length is known on the device only: size the grid for the most the source can hold
+    const i64 nchunks = ((i64)src->cap + SPAWN_NT - 1) / SPAWN_NT;
+    const int grid = (int)(nchunks < (i64)c->sm_count * 8 ? nchunks : (i64)c->sm_count * 8);
+    spawn_part_kernel<HK, W, VT><<<grid, SPAWN_NT, 0, c->stream>>>(h->dev, p, src->keys, (const VT *)src->vals, 0, c->part, c->xch, hv, st);
+    spawn_heavy_kernel<HK, W, VT><<<c->sm_count * 4, SPAWN_NT, 0, c->stream>>>(h->dev, p, src->keys, (const VT *)src->vals, c->part, c->xch, hv, st);
+    SegSrc ss{src->keys, (const u64 *)src->vals, src->seg_start, src->seg_len, src->diag};
+    SegDst sd{dst->keys, (u64 *)dst->vals, dst->seg_start, dst->seg_len, dst->cap, dst->diag};
+    const int mgrid = (int)(nb < c->merge_grid_cap ? nb : c->merge_grid_cap);
+    if (p.init_rule) merge_kernel<HK, W, VT, 0, true><<<mgrid, PART_NT, part_smem_bytes(W) + smem_init, c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, st);
+    else merge_kernel<HK, W, VT, 0, false><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, st);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 3;
+    return 0;
+}
+
 #define RIMU_CAT_(a, b) a##b
 #define RIMU_CAT(a, b) RIMU_CAT_(a, b)
 #define HKNAME(x) RIMU_CAT(RIMU_CAT(x, _hk), RIMU_HK)
@@ -150,6 +178,11 @@ static int HKNAME(step_entry)(rimu_ctx *c, const rimu_ham *h, const StepDev &p, 
     if constexpr (HAS_W2) return step_w<2>(c, h, p, src, dst, use_part, is_int, nb, slots, sent);
     return fail(RIMU_ERR_INVALID, "this Hamiltonian kind is compiled for one-word addresses only");
 }
+static int HKNAME(enqueue_entry)(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, bool is_int, u32 nb, StatsDev *st) {
+    if (h->W == 1) return is_int ? step_part_enqueue<HKC, 1, i64>(c, h, p, src, dst, nb, st) : step_part_enqueue<HKC, 1, double>(c, h, p, src, dst, nb, st);
+    if constexpr (HAS_W2) return is_int ? step_part_enqueue<HKC, 2, i64>(c, h, p, src, dst, nb, st) : step_part_enqueue<HKC, 2, double>(c, h, p, src, dst, nb, st);
+    return fail(RIMU_ERR_INVALID, "this Hamiltonian kind is compiled for one-word addresses only");
+}
 static int HKNAME(diag_entry)(rimu_ctx *c, const rimu_ham *h, const u64 *d_keys, i64 n, double *d_out, i64 *d_nod) {
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (h->W == 1) ham_diag_kernel<HKC, 1><<<grid, 256, 0, c->stream>>>(h->dev, d_keys, n, d_out, d_nod);
@@ -172,5 +205,5 @@ static int HKNAME(sector_mul_entry)(rimu_ctx *c, const rimu_ham *h, const Sector
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-static const HkOps HKNAME(OPS) = {HKNAME(step_entry), HKNAME(diag_entry), HKNAME(offdiag_entry), HKNAME(sector_mul_entry)};
+static const HkOps HKNAME(OPS) = {HKNAME(step_entry), HKNAME(diag_entry), HKNAME(offdiag_entry), HKNAME(sector_mul_entry), HKNAME(enqueue_entry)};
 const HkOps *RIMU_CAT(rimu_hk_ops_, RIMU_HK)() { return &HKNAME(OPS); }

@@ -7,6 +7,17 @@
 #include "hamiltonians.cuh"
 #include <type_traits>
 
+// Device-resident controller of a BATCH of steps (rimu_advance): the shift update of every step runs on the GPU, so the host
+// enqueues step k+1 before step k has finished -- nobody waits for the walker number to cross PCIe.  Null in rimu_step.
+struct StepCtl {
+    double shift, pnorm;   // DefaultShiftParameters (shiftstrategy.jl:32-38) after the last finished step
+    int shift_mode;        // ... its shift_mode flag (the *AfterTargetWalkers strategies)
+    int stop;              // 0 running; 1 the run ended after steps_done steps (dead population, max_length, strategy);
+                           // 2 step number steps_done ran out of working memory / vector capacity: every later kernel is a no-op
+    long long steps_done;
+    unsigned long long n;  // entries of the current source vector
+};
+
 struct StepDev {
     int style, plain_h;
     double shift, dtau, boost, proj_thr, rel_thr, abs_thr, compress_thr;
@@ -15,6 +26,7 @@ struct StepDev {
     int init_rule;      // RIMU_INITIATOR_*: 0 = no initiator lanes
     double init_thr;
     int ordered;        // order-deterministic Float64 summation (audit mode)
+    const StepCtl *ctl; // batch mode: shift, source length and the stop flag come from device memory
 };
 
 #if defined(__CUDACC__) || defined(RIMU_HOST_EMULATION)

@@ -303,6 +303,41 @@ def apply_operator(wm: WorkingMemory, target: GPUDVec, source: GPUDVec, op, boos
     return names, values, wm, target
 
 
+def advance(wm: WorkingMemory, v: GPUDVec, pv: GPUDVec, hamiltonian, shift_params, strategy_id, *, target_walkers=0.0, zeta=0.0,
+            xi=0.0, nsteps=1, max_length=0, boost=1.0):
+    """`nsteps` x { apply_operator!(wm, pv, v, FirstOrderTransitionOperator(H, shift, dt)); v, pv = pv, v;
+    update_shift_parameters! } -- the body of advance! (fciqmc.jl:126-181) -- in ONE call: the shift update and the abort
+    rules run on the device, so no step waits for the host (rimu_advance, include/rimu_b200.h).
+    `shift_params` (fciqmc.ShiftParameters) is updated in place.
+    -> (v, pv, stats [StepStats per step taken], shifts [shift after each step's update], steps_done); steps_done < nsteps
+    only when the run ended (dead population, max_length, DontUpdate target reached)."""
+    style = wm.style
+    p = _lib.StepParams()
+    style.fill(p)
+    p.plain_h, p.shift, p.time_step = 0, shift_params.shift, shift_params.time_step
+    p.boost, p.seed, p.step = float(boost), wm.seed, wm.counter
+    p.ordered = int(getattr(wm, "ordered", False))
+    rule = getattr(wm, "initiator", None)
+    if rule is not None and rule.rule_id:
+        p.initiator_rule, p.initiator_threshold = rule.rule_id, float(rule.threshold)
+    sp = _lib.ShiftParams()
+    sp.strategy, sp.shift_mode = int(strategy_id), int(bool(shift_params.shift_mode))
+    sp.target_walkers, sp.zeta, sp.xi = float(target_walkers), float(zeta), float(xi)
+    sp.shift, sp.pnorm, sp.max_length = float(shift_params.shift), float(shift_params.pnorm), int(max_length)
+    stats = (_lib.StepStats * nsteps)()
+    shifts = (C.c_double * nsteps)()
+    done, in_w = C.c_int64(0), C.c_int32(0)
+    _lib.check(_lib.lib().rimu_advance(wm.ctx.handle, hamiltonian.handle, C.byref(p), C.byref(sp), v.handle, pv.handle, nsteps,
+                                      stats, shifts, C.byref(done), C.byref(in_w)))
+    wm.counter += done.value
+    shift_params.shift, shift_params.pnorm, shift_params.shift_mode = sp.shift, sp.pnorm, bool(sp.shift_mode)
+    if done.value:
+        wm.last_stats = stats[done.value - 1]
+    if in_w.value:
+        v, pv = pv, v
+    return v, pv, [stats[k] for k in range(done.value)], [shifts[k] for k in range(done.value)], done.value
+
+
 def mul(y: GPUDVec, op, x: GPUDVec, wm: WorkingMemory | None = None):
     """mul!(y, op, x, w) (pdvec.jl:810-822): deterministic y = op * x.  Dense sector vectors (sectors.py) take the gather path."""
     if hasattr(y, "mul_from"):

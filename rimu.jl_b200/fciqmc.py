@@ -21,7 +21,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from .dictvectors import (FirstOrderTransitionOperator, GPUDVec, WorkingMemory, apply_operator, dot, mul,
+from .dictvectors import (FirstOrderTransitionOperator, GPUDVec, WorkingMemory, advance, apply_operator, dot, mul,
                           walkernumber_and_length)
 from .hamiltonians import AbstractHamiltonian, starting_address
 from .stochasticstyles import IsDeterministic, IsDynamicSemistochastic, StochasticStyle, default_style
@@ -108,6 +108,22 @@ class DoubleLogUpdateAfterTargetWalkers:
             sp.shift -= self.xi / dt * math.log(tnorm / self.target_walkers) + self.zeta / dt * math.log(tnorm / sp.pnorm)
         sp.pnorm = tnorm
         return {"shift": sp.shift, "norm": tnorm, "shift_mode": sp.shift_mode}, True
+
+
+def _device_strategy(strategy):
+    """(RIMU_SHIFT_* id, target_walkers, zeta, xi) of a shift strategy the device controller implements, or None"""
+    t = type(strategy)
+    if t is DontUpdate:
+        return _lib.SHIFT_DONT_UPDATE, strategy.target_walkers, 0.0, 0.0
+    if t is LogUpdate:
+        return _lib.SHIFT_LOG_UPDATE, 0.0, strategy.zeta, 0.0
+    if t is LogUpdateAfterTargetWalkers:
+        return _lib.SHIFT_LOG_UPDATE_AFTER_TARGET, strategy.target_walkers, strategy.zeta, 0.0
+    if t is DoubleLogUpdate:
+        return _lib.SHIFT_DOUBLE_LOG_UPDATE, strategy.target_walkers, strategy.zeta, strategy.xi
+    if t is DoubleLogUpdateAfterTargetWalkers:
+        return _lib.SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET, strategy.target_walkers, strategy.zeta, strategy.xi
+    return None
 
 
 # --------------------------------------------------------------------------- post-step strategies
@@ -358,7 +374,7 @@ class ProjectorMonteCarloProblem:
                  last_step=100, wall_time=math.inf, target_walkers=1000, zeta=0.08, xi=None, shift_strategy=None,
                  post_step_strategy=(), max_length=None, random_seed=True, reporting_interval=1, metadata=None,
                  n_replicas=1, initiator=False, replica_strategy=None, spectral_strategy=None, minimum_size=None,
-                 reporting_strategy=None):
+                 reporting_strategy=None, device_steps=None):
         if int(n_replicas) < 1:
             raise ValueError("n_replicas must be at least 1")
         self.n_replicas = int(n_replicas)  # independent copies of the walker vector, advanced side by side (qmc_states.jl:89-140)
@@ -390,6 +406,12 @@ class ProjectorMonteCarloProblem:
         self.reporting_strategy = reporting_strategy or ReportDFAndInfo(reporting_interval)
         self.reporting_interval = self.reporting_strategy.reporting_interval
         self.metadata = dict(metadata or {})
+        # device_steps: how many steps `solve` hands to the device in one call (rimu_advance: shift update and abort rules on
+        # the GPU, no host round trip between steps).  Applies to single-state runs without post-step strategies on one GPU;
+        # 1 = the plain step-by-step loop.  The report has the same rows either way.
+        if device_steps is None:
+            device_steps = int(os.environ.get("RIMU_B200_DEVICE_STEPS", "64"))
+        self.device_steps = max(1, int(device_steps))
 
 
 class PMCSimulation:
@@ -512,6 +534,59 @@ class PMCSimulation:
         self.modified = True
         return self
 
+    # ---- a batch of steps on the device (rimu_advance): advance! x K without a host round trip
+    def _batch_size(self):
+        p = self.problem
+        if p.device_steps <= 1 or len(self.states) != 1 or p.post_step_strategy or p.replica_strategy is not None:
+            return 0
+        st = self.state
+        if not hasattr(st.v, "handle") or getattr(st.v.ctx, "nranks", 1) != 1 or _device_strategy(p.shift_strategy) is None:
+            return 0
+        return min(p.device_steps, p.last_step - self.step)
+
+    def _advance_batch(self, K):
+        p, st = self.problem, self.state
+        sp = st.shift_parameters
+        sid, target, zeta, xi = _device_strategy(p.shift_strategy)
+        mode = sp.shift_mode
+        v, pv, stats, shifts, done = advance(st.wm, st.v, st.pv, st.hamiltonian, sp, sid, target_walkers=target, zeta=zeta, xi=xi,
+                                             nsteps=K, max_length=p.max_length)
+        st.v, st.pv = v, pv
+        is_int = v.style.val_type == _lib.VAL_I64
+        style = v.style
+        with_len_before = type(getattr(style, "compression", None)).__name__ == "ThresholdCompression"
+        after_target = sid in (_lib.SHIFT_LOG_UPDATE_AFTER_TARGET, _lib.SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET)
+        for k in range(done):
+            self.step += 1
+            s = stats[k]
+            tnorm = float(s.inorm1) if is_int else s.norm1
+            length = s.len
+            proceed = True
+            shift_stats = {"shift": shifts[k], "norm": tnorm}
+            if length > 0:
+                if after_target:
+                    mode = mode or tnorm > target
+                    shift_stats["shift_mode"] = mode
+                if sid == _lib.SHIFT_DONT_UPDATE:
+                    proceed = tnorm < target
+            if self.step % p.reporting_interval == 0:
+                row = {"step": self.step, "len": length}
+                row.update(shift_stats)
+                names, values = style.stat_names, style.stats(s)
+                if with_len_before:
+                    names, values = names + ("len_before",), values + (s.len_before,)
+                row.update(dict(zip(names, values)))
+                for key, val in row.items():
+                    self.report.setdefault(key, []).append(val)
+                if isinstance(p.reporting_strategy, ReportToFile):
+                    p.reporting_strategy.after_step(self.step, self.report, self._report_metadata())
+            if length == 0 or length > p.max_length or not proceed:
+                self.aborted, self.message = True, f"Aborted in step {self.step}."
+        if not self.aborted and self.step >= p.last_step:
+            self.success = True
+        self.modified = True
+        return self
+
     def solve_(self, last_step=None, wall_time=None):
         if last_step is not None:
             self.problem.last_step = last_step
@@ -524,7 +599,11 @@ class PMCSimulation:
             if time.time() - t0 > wt:
                 self.aborted, self.message = True, "Wall time reached."
                 break
-            self.step_()
+            K = self._batch_size()
+            if K >= 2:
+                self._advance_batch(K)
+            else:
+                self.step_()
         self.elapsed_time += time.time() - t0
         if (self.aborted or self.success) and isinstance(self.problem.reporting_strategy, ReportToFile):
             self.problem.reporting_strategy.finalize(self.report, self._report_metadata())

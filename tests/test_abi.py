@@ -34,6 +34,7 @@ def test_struct_layouts(built):
     assert L.rimu_sizeof_ham_desc() == C.sizeof(_lib.HamDesc)
     assert L.rimu_sizeof_step_params() == C.sizeof(_lib.StepParams)
     assert L.rimu_sizeof_step_stats() == C.sizeof(_lib.StepStats)
+    assert L.rimu_sizeof_shift_params() == C.sizeof(_lib.ShiftParams)
 
 
 def test_no_cpu_fallback(built):

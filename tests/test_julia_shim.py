@@ -148,7 +148,8 @@ def jl_struct_fields(name):
 
 
 def test_mirrored_structs_have_the_c_layout():
-    for cname, jname in (("rimu_ham_desc", "HamDesc"), ("rimu_step_params", "StepParams"), ("rimu_step_stats", "StepStats")):
+    for cname, jname in (("rimu_ham_desc", "HamDesc"), ("rimu_step_params", "StepParams"), ("rimu_step_stats", "StepStats"),
+                         ("rimu_shift_params", "ShiftParams")):
         cf, jf = c_struct_fields(cname), jl_struct_fields(jname)
         assert [f[0] for f in cf] == [f[0] for f in jf], (cname, [f[0] for f in cf], [f[0] for f in jf])
         assert [(w, n) for _, w, n in cf] == [(w, n) for _, w, n in jf], cname
@@ -156,7 +157,7 @@ def test_mirrored_structs_have_the_c_layout():
     import rimu_b200 as R
     lib = R._lib.lib()
     for cname, fn in (("rimu_ham_desc", lib.rimu_sizeof_ham_desc), ("rimu_step_params", lib.rimu_sizeof_step_params),
-                      ("rimu_step_stats", lib.rimu_sizeof_step_stats)):
+                      ("rimu_step_stats", lib.rimu_sizeof_step_stats), ("rimu_shift_params", lib.rimu_sizeof_shift_params)):
         size, off = 0, 0
         for _, w, n in c_struct_fields(cname):
             off = (off + w - 1) // w * w
