@@ -1174,12 +1174,22 @@ static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
     int rounds = rounds_env > 0 ? rounds_env : (5 * max_rounds) / 8; // 5 of 8 (measured flat between 5 and 7): room for growth and skew
     if (rounds > max_rounds - 1) rounds = max_rounds - 1;
     if (rounds < 1) rounds = 1;
+    const double expected = parents * (1.0 + c->rec_per_parent) * 1.02 + 64.0;
+    // Small problems: the merge takes as long as the busiest CTA's rounds, and with 5-round buckets a vector of a few thousand
+    // determinants occupies a handful of the GPU's 4 x 148 CTA slots (config 1: 4 buckets, 19 us).  Use as few rounds per bucket
+    // as it takes to give every resident CTA a bucket.  (Identical on every rank: all inputs are.)
+    const int base_rounds = rounds;
+    if (rounds_env <= 0) {
+        const double all_slots = (double)c->sm_count * PART_MINB * PART_NT;
+        int r = (int)ceil(expected / all_slots);
+        if (r < 1) r = 1;
+        if (r < rounds) rounds = r;
+    }
     // `upper` = the largest mean fill whose Poisson spread (1.5 sigma) still fits the rounds.  A fresh segmentation starts at
     // 0.9 * upper, and the bucket count is kept while the mean stays in [0.7, 1] * upper: a growing population is re-segmented
     // every ~5 % of growth (one step that carries the diagonal deposits as records), a steady one sits just below the
     // round boundary, where every round of every bucket is nearly full.
     const double slots = (double)rounds * PART_NT, upper = slots - 1.5 * sqrt(slots);
-    const double expected = parents * (1.0 + c->rec_per_parent) * 1.02 + 64.0;
     // a count that overflowed is not tried again (nor anything within 20 % of it) until the vector has shrunk by a fifth
     double floor_nb = 1.0;
     if (c->ovf_nb) {
@@ -1189,6 +1199,10 @@ static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
     if (src->nb && (double)src->nb >= floor_nb) {
         double fill = expected / src->nb;
         if (fill >= 0.7 * upper && fill <= upper) return src->nb;
+        if (rounds < base_rounds) { // a segmentation made for one round more is kept (no flip-flop where the round count changes)
+            const double s1 = (double)(rounds + 1) * PART_NT, u1 = s1 - 1.5 * sqrt(s1);
+            if (fill >= 0.7 * u1 && fill <= u1) return src->nb;
+        }
         if (c->ovf_nb && fill <= upper && (double)src->nb <= 1.5 * floor_nb) return src->nb; // the retry's count: keep it
     }
     double nb = ceil(expected / (0.9 * upper));
@@ -1543,6 +1557,9 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
         CUDA_TRY(cudaMemcpyAsync(&c->h_ctl[1], c->d_ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const StepCtl &rc = c->h_ctl[1];
+        static const bool dbg = getenv("RIMU_B200_DEBUG_ADVANCE") != nullptr;
+        if (dbg) fprintf(stderr, "[rimu_advance] chunk at step %lld: K=%d nb=%u n0=%lld -> stop=%d steps_done=%lld n=%llu shift=%.17g\n",
+                         (long long)done, K, nb, (long long)n0, rc.stop, rc.steps_done, rc.n, rc.shift);
         if (rc.stop == 2) {
             // some step of the chunk outgrew the working memory or a vector: back to the snapshot, repeat the chunk step by step
             // (same seeds and steps: the same trajectory)

@@ -12,12 +12,12 @@ from tests.cases import oracle_ham, product_ham
 pytestmark = pytest.mark.gpu
 
 
-def _strategy(R, sid, target):
+def _strategy(R, sid, target, zeta=0.08):
     from rimu_b200 import _lib
-    return {_lib.SHIFT_DONT_UPDATE: R.DontUpdate(target), _lib.SHIFT_LOG_UPDATE: R.LogUpdate(0.08),
-            _lib.SHIFT_LOG_UPDATE_AFTER_TARGET: R.LogUpdateAfterTargetWalkers(target, 0.08),
-            _lib.SHIFT_DOUBLE_LOG_UPDATE: R.DoubleLogUpdate(target, 0.08),
-            _lib.SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET: R.DoubleLogUpdateAfterTargetWalkers(target, 0.08)}[sid]
+    return {_lib.SHIFT_DONT_UPDATE: R.DontUpdate(target), _lib.SHIFT_LOG_UPDATE: R.LogUpdate(zeta),
+            _lib.SHIFT_LOG_UPDATE_AFTER_TARGET: R.LogUpdateAfterTargetWalkers(target, zeta),
+            _lib.SHIFT_DOUBLE_LOG_UPDATE: R.DoubleLogUpdate(target, zeta),
+            _lib.SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET: R.DoubleLogUpdateAfterTargetWalkers(target, zeta)}[sid]
 
 
 def _step_by_step(R, ph, style, start, seed, dtau, shift0, strategy, nsteps, max_length=10**9, initiator=None):
@@ -42,12 +42,12 @@ def _step_by_step(R, ph, style, start, seed, dtau, shift0, strategy, nsteps, max
     return v, sp, rows
 
 
-def _batched(R, ph, style, start, seed, dtau, shift0, sid, target, nsteps, max_length=0, initiator=None, calls=1):
+def _batched(R, ph, style, start, seed, dtau, shift0, sid, target, nsteps, max_length=0, initiator=None, calls=1, zeta=0.08):
     v = R.GPUDVec([(ph.address, start)], style=style, initiator=initiator)
     pv = v.similar()
     wm = R.working_memory(v, seed=seed)
     sp = R.ShiftParameters(shift0, v.walkernumber(), dtau)
-    strat = _strategy(R, sid, target)
+    strat = _strategy(R, sid, target, zeta)
     rows, is_int = [], style.val_type == R._lib.VAL_I64
     per_call = -(-nsteps // calls)
     left = nsteps
@@ -131,7 +131,7 @@ def test_batch_rolls_back_when_a_chunk_outgrows_its_memory(built):
     style = R.IsStochasticInteger()
     shift0 = R.diagonal_element(ph, ph.address) + 25.0
     va, spa, ra = _step_by_step(R, ph, style, 20, 7, 0.01, shift0, R.LogUpdate(0.0), 40)
-    vb, spb, rb = _batched(R, ph, style, 20, 7, 0.01, shift0, _lib.SHIFT_LOG_UPDATE, 0.0, 40)
+    vb, spb, rb = _batched(R, ph, style, 20, 7, 0.01, shift0, _lib.SHIFT_LOG_UPDATE, 0.0, 40, zeta=0.0)
     assert ra[-1][0] > 20000  # it did explode
     assert [(a[0], a[1], a[2]) for a in ra] == [(b[0], b[1], b[2]) for b in rb]
     ka, xa = va.download_sorted()
@@ -147,7 +147,7 @@ def test_batch_abort_rules(built):
     style = R.IsStochasticInteger()
     shift0 = R.diagonal_element(ph, ph.address) + 8.0
     va, spa, ra = _step_by_step(R, ph, style, 30, 11, 0.005, shift0, R.LogUpdate(0.0), 300, max_length=600)
-    vb, spb, rb = _batched(R, ph, style, 30, 11, 0.005, shift0, _lib.SHIFT_LOG_UPDATE, 0.0, 300, max_length=600)
+    vb, spb, rb = _batched(R, ph, style, 30, 11, 0.005, shift0, _lib.SHIFT_LOG_UPDATE, 0.0, 300, max_length=600, zeta=0.0)
     assert len(ra) < 300 and ra[-1][0] > 600
     assert [(a[0], a[1], a[2]) for a in ra] == [(b[0], b[1], b[2]) for b in rb]
     ka, xa = va.download_sorted()
