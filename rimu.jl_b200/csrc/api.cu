@@ -1177,10 +1177,10 @@ static u32 choose_buckets(rimu_ctx *c, const rimu_vec *src, double parents) {
     const double expected = parents * (1.0 + c->rec_per_parent) * 1.02 + 64.0;
     // Small problems: the merge takes as long as the busiest CTA's rounds, and with 5-round buckets a vector of a few thousand
     // determinants occupies a handful of the GPU's 4 x 148 CTA slots (config 1: 4 buckets, 19 us).  Use as few rounds per bucket
-    // as it takes to give every resident CTA a bucket.  (Identical on every rank: all inputs are.)
+    // as it takes to give every SM a bucket.  (Identical on every rank: all inputs are.)
     const int base_rounds = rounds;
     if (rounds_env <= 0) {
-        const double all_slots = (double)c->sm_count * PART_MINB * PART_NT;
+        const double all_slots = (double)c->sm_count * PART_NT; // (one CTA per SM: every bucket has a fixed cost -- table clear, barriers)
         int r = (int)ceil(expected / all_slots);
         if (r < 1) r = 1;
         if (r < rounds) rounds = r;
@@ -1535,6 +1535,8 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
         p.rank = 0; p.nranks = 1;
         p.init_rule = prm->initiator_rule; p.init_thr = prm->initiator_threshold;
         p.ctl = c->d_ctl;
+        c->part.ppc = spawn_chunk_parents(n0, c->sm_count);
+        c->adv_grid = (u32)((n0 + n0 / 2) / c->part.ppc + 2); // (a vector that grows beyond this is covered by the kernel's chunk loop)
         AdvanceDev a;
         a.strategy = sp->strategy; a.is_int = is_int ? 1 : 0; a.target_walkers = sp->target_walkers; a.zeta = sp->zeta; a.xi = sp->xi;
         a.dtau = prm->time_step; a.max_length = sp->max_length; a.heavy_cap = c->heavy.cap;

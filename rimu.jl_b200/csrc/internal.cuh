@@ -150,7 +150,14 @@ struct rimu_ctx {
     double *d_shiftlog = nullptr, *h_shiftlog = nullptr;
     u64 *snap_keys = nullptr, *snap_vals = nullptr, *snap_seg_start = nullptr; double *snap_diag = nullptr; u32 *snap_seg_len = nullptr;
     u64 snap_cap = 0, snap_nb_cap = 0;
+    u32 adv_grid = 0;        // spawn grid of the current batch
 };
+// parents per spawn chunk: SPAWN_NT for vectors that fill the GPU anyway; small vectors are cut so that ~every SM gets a chunk
+static inline u32 spawn_chunk_parents(i64 n, int sm_count) {
+    u32 ppc = SPAWN_NT;
+    while (ppc > 32 && (i64)(ppc / 2) * sm_count >= n) ppc /= 2;
+    return ppc;
+}
 #define RIMU_ADVANCE_CHUNK 128        /* steps enqueued per host synchronisation */
 #define RIMU_ADVANCE_MAX_N (1u << 21) /* batches pay off while a step is launch/latency bound; beyond this, step by step */
 RIMU_INTERNAL int enter_ctx(rimu_ctx *c);

@@ -73,6 +73,8 @@ struct PartDev {       // bucket record streams (working memory of the partition
     // (me, lane) of every rank's streams over NVLink while it annihilates -- the transfer overlaps the shared-memory work
     // of the other resident CTAs, there is no exchange pass and no receive pass.
     int direct;
+    u32 ppc;           // parents per spawn chunk (<= SPAWN_NT; set per launch): small vectors are cut into smaller chunks so that
+                       //   the spawn kernel's latency chain runs on every SM instead of a handful of CTAs
     const u64 *peer_rec[RIMU_MAX_RANKS];   // rec of every rank ([this rank] = rec)
     const u32 *peer_rcnt[RIMU_MAX_RANKS];  // rcnt of every rank
 };
@@ -192,17 +194,19 @@ spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys,
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double spawns = 0.0;
     i64 exact_steps = 0, inexact_steps = 0, attempts = 0, nsent = 0;
-    const i64 nchunks = (n + SPAWN_NT - 1) / SPAWN_NT;
+    const i64 PPC = (i64)pt.ppc; // parents per chunk (SPAWN_NT unless the vector is small)
+    const bool has_parent = tid < (int)PPC;
+    const i64 nchunks = (n + PPC - 1) / PPC;
     // the parent of the NEXT chunk is loaded while the current chunk is processed (its HBM latency was the largest
     // single stall of this kernel: 21 % of the samples in profiles/r1_partition_ncu_summary.md)
     B nkey = 0; VT npv = (VT)0;
-    { const i64 j0 = (i64)blockIdx.x * SPAWN_NT + tid; if (j0 < n) { nkey = load_key<W>(keys + j0 * W); npv = vals[j0]; } }
+    { const i64 j0 = (i64)blockIdx.x * PPC + tid; if (has_parent && j0 < n) { nkey = load_key<W>(keys + j0 * W); npv = vals[j0]; } }
     for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        const i64 j = chunk * SPAWN_NT + tid;
+        const i64 j = chunk * PPC + tid;
         const B key = nkey; const VT pv = npv;
-        { const i64 jn = j + (i64)gridDim.x * SPAWN_NT; if (jn < n) { nkey = load_key<W>(keys + jn * W); npv = vals[jn]; } }
+        { const i64 jn = j + (i64)gridDim.x * PPC; if (has_parent && jn < n) { nkey = load_key<W>(keys + jn * W); npv = vals[jn]; } }
         u32 cnt = 0;
-        if (j < n) {
+        if (has_parent && j < n) {
             long long L = ham_num_offdiagonals<HK, B>(h, key);
             u64 c64;
             bool exact = attempts_for(p, (double)pv, L, c64);

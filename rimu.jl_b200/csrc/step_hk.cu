@@ -70,7 +70,8 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
     CUDA_TRY(cudaEventRecord(c->ev[4], c->stream));
     if (n > 0) {
-        const i64 nchunks = (n + SPAWN_NT - 1) / SPAWN_NT;
+        c->part.ppc = spawn_chunk_parents(n, c->sm_count);
+        const i64 nchunks = (n + c->part.ppc - 1) / c->part.ppc;
         const int grid = (int)(nchunks < (i64)c->sm_count * 8 ? nchunks : (i64)c->sm_count * 8);
         spawn_part_kernel<HK, W, VT><<<grid, SPAWN_NT, 0, c->stream>>>(
             h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->xch, c->heavy, c->d_stats);
@@ -137,9 +138,11 @@ static int step_part_enqueue(rimu_ctx *c, const rimu_ham *h, const StepDev &p, r
     }
     HeavyDev hv = c->heavy;
     hv.packed = (u64 *)&st->heavy_packed;
-    // the source length is known on the device only: size the grid for the most the source can hold
-    const i64 nchunks = ((i64)src->cap + SPAWN_NT - 1) / SPAWN_NT;
-    const int grid = (int)(nchunks < (i64)c->sm_count * 8 ? nchunks : (i64)c->sm_count * 8);
+    // the source length is known on the device only: chunk size and grid from the length at the start of the batch (c->part.ppc,
+    // set by rimu_advance); the kernel's chunk loop covers whatever the vector has grown to
+    const i64 nchunks = ((i64)src->cap + c->part.ppc - 1) / c->part.ppc;
+    const i64 want = (i64)c->adv_grid;
+    const int grid = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(nchunks, want), (i64)c->sm_count * 8));
     spawn_part_kernel<HK, W, VT><<<grid, SPAWN_NT, 0, c->stream>>>(h->dev, p, src->keys, (const VT *)src->vals, 0, c->part, c->xch, hv, st);
     spawn_heavy_kernel<HK, W, VT><<<c->sm_count * 4, SPAWN_NT, 0, c->stream>>>(h->dev, p, src->keys, (const VT *)src->vals, c->part, c->xch, hv, st);
     SegSrc ss{src->keys, (const u64 *)src->vals, src->seg_start, src->seg_len, src->diag};
