@@ -336,12 +336,23 @@ typedef struct {
     double shift, pnorm;     /* in/out: shift and previous walker number */
     int64_t max_length;      /* abort when the vector grows beyond this many entries (0 = no limit) */
 } rimu_shift_params;
+/* A frozen projector (FrozenDVec, DictVectors/projectors.jl:141-176): host (key, value) pairs.  rimu_advance evaluates
+ * dot(projector, v) (pdvec.jl:773-779) after every step -- the reports of the ProjectedEnergy / Projector post-step
+ * strategies (strategies_and_params/poststepstrategy.jl:50-121) -- without leaving the device. */
+typedef struct {
+    const uint64_t *keys;    /* n addresses, `words` uint64 each */
+    const double *values;
+    int64_t n;
+} rimu_projector;
+#define RIMU_MAX_PROJECTORS 8
 /* v: current vector, w: scratch partner of the same type.  params->shift is ignored (sp->shift is the shift).  On return
  * *steps_done steps were taken (< nsteps only when the run ended: dead population, max_length, DontUpdate target reached --
  * the state is that of the last step taken, as in the reference), stats_out[k] / shift_out[k] (optional) hold the statistics
- * of step k and the shift AFTER its update, and *result_in_w tells which vector holds the current state. */
+ * of step k and the shift AFTER its update, proj_out[k * nproj + j] = dot(projectors[j], v after step k), and *result_in_w
+ * tells which vector holds the current state. */
 int rimu_advance(rimu_ctx *ctx, const rimu_ham *ham, const rimu_step_params *params, rimu_shift_params *sp,
-                 rimu_vec *v, rimu_vec *w, int64_t nsteps, rimu_step_stats *stats_out, double *shift_out,
+                 rimu_vec *v, rimu_vec *w, int64_t nsteps, const rimu_projector *projectors, int32_t nproj,
+                 rimu_step_stats *stats_out, double *shift_out, double *proj_out,
                  int64_t *steps_done, int32_t *result_in_w);
 int rimu_sizeof_shift_params(void);
 

@@ -634,14 +634,23 @@ shift_strategy_params(s::Rimu.DoubleLogUpdate) = (Int32(3), Float64(s.target_wal
 shift_strategy_params(s::Rimu.DoubleLogUpdateAfterTargetWalkers) = (Int32(4), Float64(s.target_walkers), Float64(s.ζ), Float64(s.ξ))
 shift_strategy_params(s) = throw(ArgumentError("$(typeof(s)) needs the vectors on the host every step: use the step-by-step loop"))
 
+struct ProjectorArg                   # == rimu_projector: host pairs of a FrozenDVec
+    keys::Ptr{UInt64}
+    values::Ptr{Float64}
+    n::Int64
+end
+
 """
-    advance_steps!(wm, v, pv, hamiltonian, shift_parameters, shift_strategy, nsteps; max_length=0)
-        -> (v, pv, stats::Vector{StepStats}, shifts::Vector{Float64})
+    advance_steps!(wm, v, pv, hamiltonian, shift_parameters, shift_strategy, nsteps; max_length=0, projectors=())
+        -> (v, pv, stats::Vector{StepStats}, shifts::Vector{Float64}, dots::Matrix{Float64})
 
 `nsteps` iterations of `apply_operator!`, swap and `update_shift_parameters!` in one call (`rimu_advance`); `shift_parameters`
-(Rimu's `DefaultShiftParameters`) is updated in place.  Fewer than `nsteps` entries come back when the run ended.
+(Rimu's `DefaultShiftParameters`) is updated in place.  `projectors` are `FrozenDVec`s (the frozen `vproj` / `hproj` of
+`ProjectedEnergy`, poststepstrategy.jl:82-121): `dots[j, k]` = `dot(projectors[j], v)` after step `k`, evaluated on the device.
+Fewer than `nsteps` entries come back when the run ended.
 """
-function advance_steps!(wm::GPUWorkingMemory, v::GPUDVec, pv::GPUDVec, ham::AbstractHamiltonian, sp, strategy, nsteps::Integer; max_length::Integer=0)
+function advance_steps!(wm::GPUWorkingMemory, v::GPUDVec, pv::GPUDVec, ham::AbstractHamiltonian, sp, strategy, nsteps::Integer;
+                        max_length::Integer=0, projectors=())
     sty, pt, rt, at, ct = style_params(wm.style)
     ir, it = initiator_params(wm.initiator)
     params = Ref(StepParams(sty, 0, Float64(sp.shift), Float64(sp.time_step), 1.0, pt, rt, at, ct, wm.seed, wm.counter, 0, ir, Int32(wm.ordered), it))
@@ -650,14 +659,22 @@ function advance_steps!(wm::GPUWorkingMemory, v::GPUDVec, pv::GPUDVec, ham::Abst
     stats = Vector{StepStats}(undef, nsteps)
     shifts = zeros(Float64, nsteps)
     done, in_w = Ref{Int64}(0), Ref{Int32}(0)
-    check(ccall((:rimu_advance, LIB), Cint,
-                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{StepParams}, Ptr{ShiftParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{StepStats}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
-                wm.ctx.ptr, gpu_ham(ham, wm.ctx).ptr, params, shp, v.ptr, pv.ptr, nsteps, stats, shifts, done, in_w))
+    nproj = length(projectors)
+    pkeys = [isempty(pairs(f)) ? UInt64[] : reduce(vcat, to_key.(first.(collect(pairs(f))))) for f in projectors]
+    pvals = [Float64.(last.(collect(pairs(f)))) for f in projectors]
+    dots = zeros(Float64, max(nproj, 1), nsteps)                       # column k = step k (C: proj_out[k * nproj + j])
+    GC.@preserve pkeys pvals begin
+        pargs = [ProjectorArg(pointer(pkeys[j]), pointer(pvals[j]), length(pvals[j])) for j in 1:nproj]
+        check(ccall((:rimu_advance, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{StepParams}, Ptr{ShiftParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{ProjectorArg}, Int32,
+                     Ptr{StepStats}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
+                    wm.ctx.ptr, gpu_ham(ham, wm.ctx).ptr, params, shp, v.ptr, pv.ptr, nsteps, pargs, nproj, stats, shifts, dots, done, in_w))
+    end
     wm.counter += done[]
     sp.shift, sp.pnorm, sp.shift_mode = shp[].shift, shp[].pnorm, shp[].shift_mode != 0
     done[] > 0 && (wm.last_stats = stats[done[]])
     in_w[] != 0 && ((v, pv) = (pv, v))
-    return v, pv, stats[1:done[]], shifts[1:done[]]
+    return v, pv, stats[1:done[]], shifts[1:done[]], dots[1:nproj, 1:done[]]
 end
 
 function mul!(y::GPUDVec, op::AbstractHamiltonian, x::GPUDVec, wm=working_memory(x))   # pdvec.jl:810-822

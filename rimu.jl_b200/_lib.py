@@ -147,6 +147,12 @@ class ShiftParams(C.Structure):
     ]
 
 
+class Projector(C.Structure):
+    """rimu_projector: a frozen projector (host pairs) whose dot with the vector rimu_advance reports after every step"""
+    _fields_ = [("keys", C.POINTER(C.c_uint64)), ("values", C.POINTER(C.c_double)), ("n", C.c_int64)]
+
+
+MAX_PROJECTORS = 8
 SHIFT_DONT_UPDATE, SHIFT_LOG_UPDATE, SHIFT_LOG_UPDATE_AFTER_TARGET, SHIFT_DOUBLE_LOG_UPDATE, SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET = range(5)
 
 # every symbol include/rimu_b200.h declares: name -> (restype, argtypes)
@@ -222,8 +228,8 @@ SYMBOLS = {
     "rimu_annihilate": (C.c_int, [_vp, _u64p, _vp, C.c_int64, C.c_int]),
     "rimu_annihilate_device": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.POINTER(C.c_float)]),
     "rimu_step": (C.c_int, [_vp, _vp, C.POINTER(StepParams), _vp, _vp, C.POINTER(StepStats)]),
-    "rimu_advance": (C.c_int, [_vp, _vp, C.POINTER(StepParams), C.POINTER(ShiftParams), _vp, _vp, C.c_int64, C.POINTER(StepStats), _f64p,
-                               _i64p, C.POINTER(C.c_int32)]),
+    "rimu_advance": (C.c_int, [_vp, _vp, C.POINTER(StepParams), C.POINTER(ShiftParams), _vp, _vp, C.c_int64, C.POINTER(Projector), C.c_int32,
+                               C.POINTER(StepStats), _f64p, _f64p, _i64p, C.POINTER(C.c_int32)]),
     "rimu_sizeof_shift_params": (C.c_int, []),
     "rimu_step_key": (None, [C.c_uint64, C.c_uint64, _u32p]),
     "rimu_philox4x32_10": (None, [_u32p, _u32p, _u32p]),

@@ -128,6 +128,7 @@ extern "C" int rimu_ctx_destroy(rimu_ctx *c) {
     cudaFree(c->d_red); cudaFreeHost(c->h_red); cudaFree(c->d_ord);
     cudaFree(c->d_ring); cudaFreeHost(c->h_ring); cudaFree(c->d_ctl); cudaFreeHost(c->h_ctl); cudaFree(c->d_shiftlog); cudaFreeHost(c->h_shiftlog);
     cudaFree(c->snap_keys); cudaFree(c->snap_vals); cudaFree(c->snap_diag); cudaFree(c->snap_seg_start); cudaFree(c->snap_seg_len);
+    cudaFree(c->proj_keys); cudaFree(c->proj_vals); cudaFree(c->d_projlog); cudaFreeHost(c->h_projlog);
     cudaGetLastError(); // teardown is best effort (e.g. closing an IPC mapping whose exporter is already gone): never leave a stale error behind
     if (c->live_vecs > 0) { // vectors still point at this context: keep the struct and the stream until the last one goes
         c->dead = 1;
@@ -1431,6 +1432,8 @@ static int ensure_advance_buffers(rimu_ctx *c, const rimu_vec *cur) {
         CUDA_TRY(cudaMallocHost(&c->h_ctl, 2 * sizeof(StepCtl))); // [0]: upload image, [1]: read-back
         CUDA_TRY(rimu_malloc(&c->d_shiftlog, 2 * RIMU_ADVANCE_CHUNK * sizeof(double)));
         CUDA_TRY(cudaMallocHost(&c->h_shiftlog, 2 * RIMU_ADVANCE_CHUNK * sizeof(double)));
+        CUDA_TRY(rimu_malloc(&c->d_projlog, RIMU_ADVANCE_CHUNK * RIMU_MAX_PROJECTORS * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&c->h_projlog, RIMU_ADVANCE_CHUNK * RIMU_MAX_PROJECTORS * sizeof(double)));
     }
     if (c->snap_cap < (u64)cur->n) {
         cudaFree(c->snap_keys); cudaFree(c->snap_vals); cudaFree(c->snap_diag);
@@ -1453,8 +1456,14 @@ static int ensure_advance_buffers(rimu_ctx *c, const rimu_vec *cur) {
 }
 
 extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_params *prm, rimu_shift_params *sp, rimu_vec *v, rimu_vec *w,
-                            int64_t nsteps, rimu_step_stats *stats_out, double *shift_out, int64_t *steps_done, int32_t *result_in_w) {
+                            int64_t nsteps, const rimu_projector *projectors, int32_t nproj, rimu_step_stats *stats_out, double *shift_out,
+                            double *proj_out, int64_t *steps_done, int32_t *result_in_w) {
     if (!c || !h || !prm || !sp || !v || !w || !steps_done || !result_in_w) return fail(RIMU_ERR_INVALID, "null argument");
+    if (nproj < 0 || nproj > RIMU_MAX_PROJECTORS) return fail(RIMU_ERR_INVALID, "at most %d projectors per call", RIMU_MAX_PROJECTORS);
+    if (nproj > 0 && (!projectors || !proj_out)) return fail(RIMU_ERR_INVALID, "projectors without an output array");
+    for (int j = 0; j < nproj; j++)
+        if (projectors[j].n < 0 || (projectors[j].n > 0 && (!projectors[j].keys || !projectors[j].values)))
+            return fail(RIMU_ERR_INVALID, "projector %d: bad arguments", j);
     if (sp->strategy < RIMU_SHIFT_DONT_UPDATE || sp->strategy > RIMU_SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET)
         return fail(RIMU_ERR_INVALID, "unknown shift strategy %d", sp->strategy);
     if (prm->plain_h) return fail(RIMU_ERR_INVALID, "rimu_advance steps with FirstOrderTransitionOperator (plain_h must be 0)");
@@ -1486,8 +1495,33 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
         const bool proceed = host_shift_update(sp, prm->time_step, tnorm, st.len);
         if (stats_out) stats_out[done] = st;
         if (shift_out) shift_out[done] = sp->shift;
+        for (int j = 0; j < nproj; j++)
+            TRY(rimu_vec_dot_sparse(cur, projectors[j].keys, projectors[j].values, projectors[j].n, &proj_out[done * nproj + j]));
         done++;
         if (st.len == 0 || (sp->max_length > 0 && st.len > sp->max_length) || !proceed) ended = true;
+        return 0;
+    };
+    // the projectors stay on the device for the whole call
+    u64 proj_off[RIMU_MAX_PROJECTORS + 1] = {0};
+    bool proj_resident = false;
+    auto upload_projectors = [&]() -> int {
+        if (proj_resident || nproj == 0) return 0;
+        TRY(enter_ctx(c));
+        for (int j = 0; j < nproj; j++) proj_off[j + 1] = proj_off[j] + (u64)projectors[j].n;
+        const u64 tot = proj_off[nproj];
+        if (tot > c->proj_cap) {
+            cudaFree(c->proj_keys); cudaFree(c->proj_vals); c->proj_keys = nullptr; c->proj_vals = nullptr; c->proj_cap = 0;
+            CUDA_TRY(rimu_malloc(&c->proj_keys, (tot + 64) * c->W * sizeof(u64)));
+            CUDA_TRY(rimu_malloc(&c->proj_vals, (tot + 64) * sizeof(double)));
+            c->proj_cap = tot + 64;
+        }
+        for (int j = 0; j < nproj; j++) {
+            if (!projectors[j].n) continue;
+            CUDA_TRY(cudaMemcpyAsync(c->proj_keys + proj_off[j] * c->W, projectors[j].keys, (size_t)projectors[j].n * c->W * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->proj_vals + proj_off[j], projectors[j].values, (size_t)projectors[j].n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream)); // (pageable host arrays: borrowed for the duration of the call only)
+        proj_resident = true;
         return 0;
     };
     while (done < nsteps && !ended) {
@@ -1511,6 +1545,8 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
         TRY(ensure_part(c, nb, nlane));
         TRY(ensure_heavy(c, std::max(cur->cap, oth->cap)));
         TRY(ensure_advance_buffers(c, cur));
+        TRY(upload_projectors());
+        if (nproj) CUDA_TRY(cudaMemsetAsync(c->d_projlog, 0, (size_t)K * nproj * sizeof(double), c->stream));
         // snapshot of the chunk's source
         const i64 n0 = cur->n;
         CUDA_TRY(cudaMemcpyAsync(c->snap_keys, cur->keys, (size_t)n0 * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
@@ -1551,12 +1587,26 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
             advance_ctl_kernel<<<1, 1, 0, c->stream>>>(c->d_ctl, c->d_ring + k, a, c->d_shiftlog + 2 * k);
             c->launches += 1;
             std::swap(src, dst);
+            for (int j = 0; j < nproj; j++) { // dot(::FrozenDVec, v) on the step's result: per-key lookups in the key's bucket segment
+                const i64 nq = projectors[j].n;
+                if (!nq) continue;
+                const int grid = (int)(nq < (i64)c->sm_count * 8 ? nq : (i64)c->sm_count * 8);
+                TRY(dispatch_wv(c->W, src->vt, [&](auto tag, auto vtag) {
+                    typedef decltype(vtag) VT;
+                    dot_sparse_kernel<decltype(tag)::w, VT><<<grid, RIMU_TPB, 0, c->stream>>>(
+                        c->proj_keys + proj_off[j] * c->W, c->proj_vals + proj_off[j], nq, src->keys, (const VT *)src->vals, 0,
+                        src->seg_start, src->seg_len, nb, 0, 1, c->d_projlog + (size_t)k * nproj + j);
+                    return 0;
+                }));
+                c->launches += 1;
+            }
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(c->ev[3], c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->h_ring, c->d_ring, (size_t)K * sizeof(StatsDev), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->h_shiftlog, c->d_shiftlog, (size_t)K * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemcpyAsync(&c->h_ctl[1], c->d_ctl, sizeof(StepCtl), cudaMemcpyDeviceToHost, c->stream));
+        if (nproj) CUDA_TRY(cudaMemcpyAsync(c->h_projlog, c->d_projlog, (size_t)K * nproj * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         const StepCtl &rc = c->h_ctl[1];
         static const bool dbg = getenv("RIMU_B200_DEBUG_ADVANCE") != nullptr;
@@ -1586,6 +1636,7 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
                 stats_out[done + k].ms_total = ms / (float)(kd > 0 ? kd : 1);
             }
             if (shift_out) shift_out[done + k] = c->h_shiftlog[2 * k];
+            for (int j = 0; j < nproj; j++) proj_out[(done + k) * nproj + j] = c->h_projlog[(size_t)k * nproj + j];
         }
         if (kd > 0) {
             const StatsDev &last = c->h_ring[kd - 1];

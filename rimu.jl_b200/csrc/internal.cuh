@@ -151,6 +151,8 @@ struct rimu_ctx {
     u64 *snap_keys = nullptr, *snap_vals = nullptr, *snap_seg_start = nullptr; double *snap_diag = nullptr; u32 *snap_seg_len = nullptr;
     u64 snap_cap = 0, snap_nb_cap = 0;
     u32 adv_grid = 0;        // spawn grid of the current batch
+    u64 *proj_keys = nullptr; double *proj_vals = nullptr; u64 proj_cap = 0; // frozen projectors of rimu_advance, resident for the call
+    double *d_projlog = nullptr, *h_projlog = nullptr;                        // [RIMU_ADVANCE_CHUNK][RIMU_MAX_PROJECTORS] dots
 };
 // parents per spawn chunk: SPAWN_NT for vectors that fill the GPU anyway; small vectors are cut so that ~every SM gets a chunk
 static inline u32 spawn_chunk_parents(i64 n, int sm_count) {

@@ -304,13 +304,16 @@ def apply_operator(wm: WorkingMemory, target: GPUDVec, source: GPUDVec, op, boos
 
 
 def advance(wm: WorkingMemory, v: GPUDVec, pv: GPUDVec, hamiltonian, shift_params, strategy_id, *, target_walkers=0.0, zeta=0.0,
-            xi=0.0, nsteps=1, max_length=0, boost=1.0):
+            xi=0.0, nsteps=1, max_length=0, boost=1.0, projectors=()):
     """`nsteps` x { apply_operator!(wm, pv, v, FirstOrderTransitionOperator(H, shift, dt)); v, pv = pv, v;
     update_shift_parameters! } -- the body of advance! (fciqmc.jl:126-181) -- in ONE call: the shift update and the abort
     rules run on the device, so no step waits for the host (rimu_advance, include/rimu_b200.h).
     `shift_params` (fciqmc.ShiftParameters) is updated in place.
-    -> (v, pv, stats [StepStats per step taken], shifts [shift after each step's update], steps_done); steps_done < nsteps
-    only when the run ended (dead population, max_length, DontUpdate target reached)."""
+    `projectors`: FrozenDVecs whose dot with the vector is evaluated on the device after every step (the reports of
+    ProjectedEnergy / Projector, poststepstrategy.jl:50-121).
+    -> (v, pv, stats [StepStats per step taken], shifts [shift after each step's update], steps_done) and, with projectors,
+    a sixth element: array [steps_done, len(projectors)] of dots.  steps_done < nsteps only when the run ended (dead
+    population, max_length, DontUpdate target reached)."""
     style = wm.style
     p = _lib.StepParams()
     style.fill(p)
@@ -327,15 +330,23 @@ def advance(wm: WorkingMemory, v: GPUDVec, pv: GPUDVec, hamiltonian, shift_param
     stats = (_lib.StepStats * nsteps)()
     shifts = (C.c_double * nsteps)()
     done, in_w = C.c_int64(0), C.c_int32(0)
+    projectors = list(projectors)
+    nproj = len(projectors)
+    parr = (_lib.Projector * max(nproj, 1))()
+    for j, fr in enumerate(projectors):
+        parr[j].keys, parr[j].values, parr[j].n = fr.keys.ctypes.data_as(_lib._u64p), fr.vals.ctypes.data_as(_lib._f64p), len(fr.vals)
+    pout = np.zeros((nsteps, max(nproj, 1)), dtype=np.float64)
     _lib.check(_lib.lib().rimu_advance(wm.ctx.handle, hamiltonian.handle, C.byref(p), C.byref(sp), v.handle, pv.handle, nsteps,
-                                      stats, shifts, C.byref(done), C.byref(in_w)))
+                                      parr if nproj else None, nproj, stats, shifts, pout.ctypes.data_as(_lib._f64p) if nproj else None,
+                                      C.byref(done), C.byref(in_w)))
     wm.counter += done.value
     shift_params.shift, shift_params.pnorm, shift_params.shift_mode = sp.shift, sp.pnorm, bool(sp.shift_mode)
     if done.value:
         wm.last_stats = stats[done.value - 1]
     if in_w.value:
         v, pv = pv, v
-    return v, pv, [stats[k] for k in range(done.value)], [shifts[k] for k in range(done.value)], done.value
+    out = (v, pv, [stats[k] for k in range(done.value)], [shifts[k] for k in range(done.value)], done.value)
+    return out + (pout[:done.value, :nproj],) if nproj else out
 
 
 def mul(y: GPUDVec, op, x: GPUDVec, wm: WorkingMemory | None = None):

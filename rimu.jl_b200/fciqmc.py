@@ -535,9 +535,23 @@ class PMCSimulation:
         return self
 
     # ---- a batch of steps on the device (rimu_advance): advance! x K without a host round trip
+    def _batch_projectors(self):
+        """[(report name, FrozenDVec)] when every post-step strategy is a frozen projection (ProjectedEnergy of a Hermitian
+        Hamiltonian, Projector) -- those are evaluated inside the device batch; None when some strategy needs the host"""
+        from .dictvectors import FrozenDVec
+        out = []
+        for ps in self.problem.post_step_strategy:
+            if isinstance(ps, ProjectedEnergy) and isinstance(ps.vproj, FrozenDVec) and isinstance(ps.hproj, FrozenDVec):
+                out += [(ps.vproj_name, ps.vproj), (ps.hproj_name, ps.hproj)]
+            elif isinstance(ps, Projector) and isinstance(ps.projector, FrozenDVec):
+                out.append((ps.name, ps.projector))
+            else:
+                return None
+        return out if len(out) <= _lib.MAX_PROJECTORS else None
+
     def _batch_size(self):
         p = self.problem
-        if p.device_steps <= 1 or len(self.states) != 1 or p.post_step_strategy or p.replica_strategy is not None:
+        if p.device_steps <= 1 or len(self.states) != 1 or p.replica_strategy is not None or self._batch_projectors() is None:
             return 0
         st = self.state
         if not hasattr(st.v, "handle") or getattr(st.v.ctx, "nranks", 1) != 1 or _device_strategy(p.shift_strategy) is None:
@@ -549,8 +563,11 @@ class PMCSimulation:
         sp = st.shift_parameters
         sid, target, zeta, xi = _device_strategy(p.shift_strategy)
         mode = sp.shift_mode
-        v, pv, stats, shifts, done = advance(st.wm, st.v, st.pv, st.hamiltonian, sp, sid, target_walkers=target, zeta=zeta, xi=xi,
-                                             nsteps=K, max_length=p.max_length)
+        projs = self._batch_projectors()
+        res = advance(st.wm, st.v, st.pv, st.hamiltonian, sp, sid, target_walkers=target, zeta=zeta, xi=xi,
+                      nsteps=K, max_length=p.max_length, projectors=[fr for _, fr in projs])
+        v, pv, stats, shifts, done = res[:5]
+        pvals = res[5] if projs else None
         st.v, st.pv = v, pv
         is_int = v.style.val_type == _lib.VAL_I64
         style = v.style
@@ -576,6 +593,8 @@ class PMCSimulation:
                 if with_len_before:
                     names, values = names + ("len_before",), values + (s.len_before,)
                 row.update(dict(zip(names, values)))
+                for j, (pname, _) in enumerate(projs):
+                    row[pname] = float(pvals[k, j])
                 for key, val in row.items():
                     self.report.setdefault(key, []).append(val)
                 if isinstance(p.reporting_strategy, ReportToFile):

@@ -185,3 +185,57 @@ def test_solve_reports_the_same_rows_with_and_without_device_batches(built):
     assert list(a.columns) == list(b.columns) and "shift_mode" in a.columns
     assert (a["shift_mode"] == b["shift_mode"]).all() and a["shift_mode"].any() and not a["shift_mode"].all()
     assert (a["len"] == b["len"]).all() and (a["norm"] == b["norm"]).all() and np.allclose(a["shift"], b["shift"], rtol=1e-11)
+
+
+def test_frozen_projections_inside_a_batch(built):
+    """dot(::FrozenDVec, v) after every step of a batch == the host-driven dot after every rimu_step (pdvec.jl:773-779), and
+    `solve` with a ProjectedEnergy report (poststepstrategy.jl:82-121) gives the same vproj / hproj columns either way."""
+    import rimu_b200 as R
+    from rimu_b200 import _lib
+    ph = product_ham("real1d_6")
+    style = R.IsDynamicSemistochastic()
+    ref = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    pe = R.ProjectedEnergy(ph, ref)
+    frozen = [pe.vproj, pe.hproj]
+    shift0, dtau, target = R.diagonal_element(ph, ph.address), 0.004, 300.0
+    # step by step
+    v = R.GPUDVec([(ph.address, 30.0)], style=style)
+    pv = v.similar()
+    wm = R.working_memory(v, seed=21)
+    sp = R.ShiftParameters(shift0, v.walkernumber(), dtau)
+    strat = R.DoubleLogUpdate(target, 0.08)
+    want = []
+    for _ in range(150):
+        R.apply_operator(wm, pv, v, R.FirstOrderTransitionOperator(ph, sp.shift, dtau))
+        v, pv = pv, v
+        strat.update(sp, wm.last_stats.norm1)
+        want.append([fr.dot(v) for fr in frozen])
+    # one call
+    v2 = R.GPUDVec([(ph.address, 30.0)], style=style)
+    pv2 = v2.similar()
+    wm2 = R.working_memory(v2, seed=21)
+    sp2 = R.ShiftParameters(shift0, v2.walkernumber(), dtau)
+    v2, pv2, stats, shifts, done, dots = R.advance(wm2, v2, pv2, ph, sp2, _lib.SHIFT_DOUBLE_LOG_UPDATE, target_walkers=target, zeta=0.08,
+                                                   xi=0.08 ** 2 / 4, nsteps=150, projectors=frozen)
+    assert done == 150 and dots.shape == (150, 2)
+    assert np.allclose(dots, np.array(want), rtol=1e-9, atol=1e-9)
+    assert abs(dots[:, 0]).min() > 0  # the reference determinant stays populated
+    # the driver
+    dfs = []
+    for ds in (1, 40):
+        prob = R.ProjectorMonteCarloProblem(ph, style=style, time_step=dtau, last_step=300, target_walkers=300, random_seed=8,
+                                            post_step_strategy=(R.ProjectedEnergy(ph, ref), R.Projector(ones=ref)), device_steps=ds)
+        sim = R.init(prob)
+        assert (sim._batch_size() >= 2) == (ds > 1)
+        dfs.append(sim.solve_().dataframe())
+    a, b = dfs
+    assert list(a.columns) == list(b.columns) and {"vproj", "hproj", "ones"} <= set(a.columns)
+    for col in a.columns:
+        assert np.allclose(a[col].astype(float), b[col].astype(float), rtol=1e-9, atol=1e-9), col
+    e = R.projected_energy(b, skip=100)
+    assert math.isclose(e.f, oracle_ham("real1d_6").exact_energy(), rel_tol=0.05)
+    # a strategy that needs the host every step (non-Hermitian projected energy: dot(projector, H, v)) is not batched
+    tc = product_ham("tc_7")
+    tref = R.GPUDVec([(tc.address, 1.0)], style=R.IsDeterministic())
+    prob = R.ProjectorMonteCarloProblem(tc, time_step=0.001, last_step=10, post_step_strategy=(R.ProjectedEnergy(tc, tref),))
+    assert R.init(prob)._batch_size() == 0

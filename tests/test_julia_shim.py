@@ -167,7 +167,7 @@ def test_mirrored_structs_have_the_c_layout():
 
 
 KNOWN = set("""
-ccall check get joinpath unsafe_string throw print zeros cld all map sum enumerate onr set_bit! get_bit ntuple fieldtypes fieldtype Tuple Int
+ccall check get joinpath unsafe_string throw print zeros cld all map sum pointer enumerate onr set_bit! get_bit ntuple fieldtypes fieldtype Tuple Int
 Ref finalizer max min length collect first last reduce vcat view isempty num_modes num_particles Int32 Int64 UInt64 UInt8 Float64
 Float32 Cint pad pad3 size vec permutedims get! rand typeof eltype zero iterate similar copy copy! sizeof fieldcount Dict IdDict
 Pair Symbol ArgumentError RimuB200Error Context GPUHam GPUDVec GPUWorkingMemory HamDesc StepParams StepStats FrozenDVec DVec
