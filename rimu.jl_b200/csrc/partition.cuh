@@ -52,11 +52,17 @@
 #ifndef PART_BALANCED_TAIL
 #define PART_BALANCED_TAIL 1
 #endif
+#ifndef PART_ASYNC_PARENTS
+#define PART_ASYNC_PARENTS 1 // merge: parents are staged with cp.async like the records (all loads of a bucket in flight at once)
+#endif
 #define HEAVY_T 1024       // parents with more attempts than this are queued for K2
 #define HEAVY_TILE 8192    // attempts per K2 work item
 #define ACC_MAX 4096       // K2 pre-sums per off-diagonal index when L <= ACC_MAX
 
 template <int W> struct PartCap { static constexpr int value = PART_CAP; };
+#ifdef PART_CAP_W2 // tuning: a smaller bucket for two-word addresses (their items are 34 bytes of shared memory each)
+template <> struct PartCap<2> { static constexpr int value = PART_CAP_W2; };
+#endif
 
 struct PartDev {       // bucket record streams (working memory of the partitioned step)
     u32 nb;            // buckets per rank (identical on all ranks of a step)
@@ -411,6 +417,8 @@ DEV void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
 }
 DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> DEV void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // slot of an address in the bucket's shared-memory table.  The items of a bucket are a pseudo-random subset of the addresses
 // (the bucket is a range of the fmix64 hash), so a multiplicative hash of the folded words spreads them; it costs 3 integer
@@ -579,6 +587,27 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
 #endif
         // ---- stage the spawn records: asynchronous copies straight into the item arrays (no lanes to sort out)
         u32 valid = 0;
+        constexpr bool async_parents = PART_ASYNC_PARENTS && !initm;
+#ifndef PART_RH
+#define PART_RH 4
+#endif
+        constexpr int RH = R < PART_RH ? R : PART_RH; // (parents beyond the first 4 rounds -- more than 1024 per bucket -- read H_aa when they need it)
+        [[maybe_unused]] double hdr[RH];  // async_parents: cached H_aa of this thread's parents, loaded while the copies are in flight
+        if constexpr (async_parents) {
+            // parents first (their own commit group): key and value go global -> shared without passing through registers;
+            // the diagonal step below reads them back once this thread's copies have landed
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r >= rmax) break;
+                const u32 i = item_of(r);
+                if (i >= np) continue;
+                const u64 gp = p0 + i;
+                if constexpr (W == 1) cp_async8(skeys + i, src.keys + gp); else cp_async16(skeys + 2 * i, src.keys + 2 * gp);
+                cp_async8(svals + i, src.vals + gp);
+                if constexpr (MODE == 0) { if (r < RH && src.diag) hdr[r < RH ? r : 0] = src.diag[gp]; }
+            }
+            cp_async_commit();
+        }
         if constexpr (!initm) {
 #pragma unroll
             for (int r = 0; r < R; r++) {
@@ -595,6 +624,7 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
                 ndep++;
             }
         }
+        if constexpr (async_parents) { cp_async_commit(); cp_async_wait_group<1>(); } // this thread's parents have landed; its records may still be in flight
         // ---- stage parents (with the diagonal step); with initiator lanes the records go through registers as well
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -605,13 +635,21 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             B key; VT v;
             u32 ilane = LANE_SAFE;
             if (i < np) {
-                key = load_key<W>(src.keys + (p0 + i) * W);
-                union { u64 b; VT v; } cv; cv.b = src.vals[p0 + i];
+                union { u64 b; VT v; } cv;
+                if constexpr (async_parents) {
+                    if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
+                    cv.b = svals[i];
+                } else {
+                    key = load_key<W>(src.keys + (p0 + i) * W);
+                    cv.b = src.vals[p0 + i];
+                }
                 const VT pv = cv.v;
                 if constexpr (MODE == 0) {
                     // diagonal_step! (spawning.jl:73-77) through FirstOrderTransitionOperator (fciqmc.jl:93-96)
                     const double val = (double)pv;
-                    const double hd = src.diag ? src.diag[p0 + i] : ham_diagonal<HK, B>(hl, key);
+                    double hd;
+                    if constexpr (async_parents) hd = src.diag ? (r < RH ? hdr[r < RH ? r : 0] : src.diag[p0 + i]) : ham_diagonal<HK, B>(hl, key);
+                    else hd = src.diag ? src.diag[p0 + i] : ham_diagonal<HK, B>(hl, key);
                     const double d = p.plain_h ? hd : 1 - p.dtau * (hd - shift);
                     double rr = 0.0;
                     const double thr = is_int ? 0.0 : p.proj_thr;
@@ -644,8 +682,10 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             }
             pidx[i] = (unsigned short)pflag;
             if (v != (VT)0) {
-                skeys[i * W] = (u64)key;
-                if constexpr (W == 2) skeys[i * W + 1] = (u64)(key >> 64);
+                if constexpr (!async_parents) { // (async: the key is where the copy put it)
+                    skeys[i * W] = (u64)key;
+                    if constexpr (W == 2) skeys[i * W + 1] = (u64)(key >> 64);
+                }
                 union { u64 b; VT v; } cv; cv.v = v;
                 if (initm && ilane == LANE_UNSAFE) { sunsafe[i] = cv.b; cv.v = (VT)0; }
                 svals[i] = cv.b;
