@@ -53,7 +53,7 @@
 #define PART_BALANCED_TAIL 1
 #endif
 #ifndef PART_ASYNC_PARENTS
-#define PART_ASYNC_PARENTS 1 // merge: parents are staged with cp.async like the records (all loads of a bucket in flight at once)
+#define PART_ASYNC_PARENTS 0 // (1 after validation on the GPU) merge: parents are staged with cp.async like the records (all loads of a bucket in flight at once)
 #endif
 #define HEAVY_T 1024       // parents with more attempts than this are queued for K2
 #define HEAVY_TILE 8192    // attempts per K2 work item
