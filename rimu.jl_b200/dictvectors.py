@@ -200,6 +200,62 @@ class GPUDVec:
     def __sub__(self, other):
         return self.copy().add_(other, -1.0)
 
+    def __neg__(self):
+        return self.copy().scale_(-1.0)
+
+    def __truediv__(self, alpha):
+        return self.copy().scale_(1.0 / alpha)
+
+    def normalize_(self, p=2):
+        """normalize!(v, p) (abstractdvec.jl:200-256)"""
+        n = self.norm(p)
+        return self.scale_(1.0 / n) if n != 0 else self
+
+    def normalize(self, p=2):
+        return self.copy().normalize_(p)
+
+    # ---- iteration and reductions over the local part (test/DictVectors.jl:193-249).  These take arbitrary host
+    # callables, so they work on a downloaded copy of the (address, value) pairs; nothing on the step path uses them.
+    def keys(self):
+        return [a for a, _ in self.pairs()]
+
+    def values(self):
+        return [x for _, x in self.pairs()]
+
+    def __iter__(self):
+        return iter(self.pairs())
+
+    def __contains__(self, addr):
+        return self[addr] != 0
+
+    def get(self, addr, default=0):
+        x = self[addr]
+        return x if x != 0 else default
+
+    def mapreduce(self, f, op, init=None, over="values"):
+        """mapreduce(f, op, values(v) | keys(v) | pairs(v); init) on the local part"""
+        items = {"values": self.values, "keys": self.keys, "pairs": self.pairs}[over]()
+        import functools
+        mapped = [f(x) for x in items]
+        return functools.reduce(op, mapped) if init is None else functools.reduce(op, mapped, init)
+
+    def sum(self, f=None, over="values"):
+        return self.mapreduce(f or (lambda x: x), lambda a, b: a + b, init=0, over=over)
+
+    def all(self, f, over="values"):
+        return all(f(x) for x in {"values": self.values, "keys": self.keys, "pairs": self.pairs}[over]())
+
+    def any(self, f, over="values"):
+        return any(f(x) for x in {"values": self.values, "keys": self.keys, "pairs": self.pairs}[over]())
+
+    def __eq__(self, other):
+        return isinstance(other, GPUDVec) and self.to_dict() == other.to_dict()
+
+    __hash__ = object.__hash__
+
+    def __repr__(self):
+        return f"GPUDVec{{{type(self.style).__name__}}} with {len(self)} entries on the device"
+
     def freeze(self):
         """freeze(v) (projectors.jl:164): an immutable list of (address, value) pairs on the HOST; its dot with a device
         vector looks every address up in its bucket segment (rimu_vec_dot_sparse) instead of building a hash table."""

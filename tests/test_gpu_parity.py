@@ -227,6 +227,16 @@ def test_vector_interface(built):
     assert vi.walkernumber() == 5.0 and R.walkernumber_and_length(vi) == (5.0, 2)
     vf = R.GPUDVec(style=R.IsDeterministic(), address_type=a.address_type).copy_from(vi)
     assert vf.to_dict() == {a: 3.0, b: -2.0}
+    # iteration / reductions / convenience arithmetic (test/DictVectors.jl:124-150,183-249)
+    u = R.GPUDVec([(a, 3.0), (b, -4.0)], style=R.IsDeterministic())
+    assert sorted(u.values()) == [-4.0, 3.0] and set(u.keys()) == {a, b} and dict(iter(u)) == {a: 3.0, b: -4.0}
+    assert a in u and c not in u and u.get(c, 7) == 7
+    assert u.sum() == -1.0 and u.sum(abs) == 7.0 and u.mapreduce(lambda x: x * x, max) == 16.0
+    assert u.all(lambda x: x != 0) and u.any(lambda x: x < 0) and not u.any(lambda x: x > 3)
+    assert u.all(lambda k: k.num_particles == 6, over="keys")
+    assert math.isclose(u.normalize().norm(2), 1.0) and u.norm(2) == 5.0 and math.isclose(u.normalize(1).norm(1), 1.0)
+    assert (-u).to_dict() == {a: -3.0, b: 4.0} and (u / 2).to_dict() == {a: 1.5, b: -2.0} and (u * 2) == (2 * u)
+    assert u == u.copy() and u != (u + u) and "2 entries" in repr(u)
 
 
 def test_error_behaviour(built):
