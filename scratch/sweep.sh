@@ -1,5 +1,5 @@
 #!/bin/bash
 # usage: scratch/sweep.sh NAME...   -- bench.py once per scratch/variants/lib_NAME.so; prints ms/step and the phase split
 for name in "$@"; do
-  RIMU_B200_LIB=$PWD/scratch/variants/lib_$name.so python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-replicas 1 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['ms_per_step'],4), d['extra']['phase_ms_per_step'])"
+  RIMU_BENCH_SKIP_PREFLIGHT=1 RIMU_B200_LIB=$PWD/scratch/variants/lib_$name.so python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-replicas 1 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$name', round(d['ms_per_step'],4), d['extra']['phase_ms_per_step'])"
 done
