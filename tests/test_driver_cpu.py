@@ -351,3 +351,76 @@ def test_report_to_file_on_the_cpu(built, cpu_device, tmp_path):
     assert not (tmp_path / "none.arrow").exists()
     with pytest.raises(ValueError):
         R.ReportToFile(compress="gzip")
+
+
+def test_device_batches_assemble_the_same_report_on_the_cpu(built, cpu_device, monkeypatch):
+    """`solve(...; device_steps=K)` hands K steps to one `advance` call (rimu_advance on the device) and replays the report rows
+    from the per-step statistics it returns.  Here `advance` is a host loop over the oracle-backed step with the host's own
+    shift strategies, so what is under test is the driver's bookkeeping: same columns and rows as the step-by-step loop --
+    incl. reporting_interval, *AfterTargetWalkers shift_mode, projections, the abort rules and solve!'s continuation."""
+    import rimu_b200 as R
+    from rimu_b200 import _lib, dictvectors, fciqmc
+    oh, ph = cpu_device("real1d_6")
+    calls = []
+
+    def fake_advance(wm, v, pv, ham, sp, sid, *, target_walkers=0.0, zeta=0.0, xi=0.0, nsteps=1, max_length=0, boost=1.0, projectors=()):
+        strat = {_lib.SHIFT_DONT_UPDATE: lambda: R.DontUpdate(target_walkers), _lib.SHIFT_LOG_UPDATE: lambda: R.LogUpdate(zeta),
+                 _lib.SHIFT_LOG_UPDATE_AFTER_TARGET: lambda: R.LogUpdateAfterTargetWalkers(target_walkers, zeta),
+                 _lib.SHIFT_DOUBLE_LOG_UPDATE: lambda: R.DoubleLogUpdate(target_walkers, zeta, xi),
+                 _lib.SHIFT_DOUBLE_LOG_UPDATE_AFTER_TARGET: lambda: R.DoubleLogUpdateAfterTargetWalkers(target_walkers, zeta, xi)}[sid]()
+        calls.append(nsteps)
+        stats, shifts, dots = [], [], []
+        is_int = v.style.val_type == _lib.VAL_I64
+        for _ in range(nsteps):
+            fciqmc.apply_operator(wm, pv, v, R.FirstOrderTransitionOperator(ham, sp.shift, sp.time_step))
+            v, pv = pv, v
+            s = wm.last_stats
+            tnorm = float(s.inorm1) if is_int else s.norm1
+            proceed = True
+            if s.len > 0:
+                _, proceed = strat.update(sp, tnorm)
+            stats.append(s); shifts.append(sp.shift); dots.append([fr.dot(v) for fr in projectors])
+            if s.len == 0 or (max_length and s.len > max_length) or not proceed:
+                break
+        out = (v, pv, stats, shifts, len(stats))
+        return out + (np.array(dots).reshape(len(stats), len(projectors)),) if projectors else out
+
+    monkeypatch.setattr(fciqmc, "advance", fake_advance)
+    monkeypatch.setattr(FakeDVec, "handle", property(lambda self: 1), raising=False)  # "a device vector" for _batch_size
+    monkeypatch.setattr(dictvectors, "FrozenDVec", FakeDVec)  # FakeDVec.freeze() returns a FakeDVec
+
+    def run(ds, **kw):
+        del calls[:]
+        prob = R.ProjectorMonteCarloProblem(ph, start_at=ph.address, random_seed=11, device_steps=ds, **kw)
+        sim = R.solve(prob)
+        return sim, sim.dataframe(), list(calls)
+
+    cases = [dict(style=R.IsDynamicSemistochastic(), time_step=0.002, last_step=230, target_walkers=300, reporting_interval=3),
+             dict(style=R.IsStochasticInteger(), time_step=0.005, last_step=150,
+                  shift_strategy=R.DoubleLogUpdateAfterTargetWalkers(target_walkers=200)),
+             dict(style=R.IsStochasticInteger(), time_step=0.01, last_step=400, target_walkers=5000, max_length=40),          # aborts
+             dict(shift=20.0, shift_strategy=R.DontUpdate(target_walkers=150), time_step=0.01, last_step=2000)]                   # stops
+    for kw in cases:
+        sa, a, ca = run(1, **kw)
+        sb, b, cb = run(64, **kw)
+        assert ca == [] and cb and max(cb) <= 64
+        assert (sa.success, sa.aborted, sa.message, sa.step) == (sb.success, sb.aborted, sb.message, sb.step)
+        assert list(a.columns) == list(b.columns) and len(a) == len(b)
+        for col in a.columns:
+            assert list(a[col]) == list(b[col]), (kw, col)
+    assert sum(cb) >= sb.step  # the DontUpdate run ended inside a batch
+    # projections inside the batch; a strategy that needs the host every step switches batching off
+    ref = R.GPUDVec([(ph.address, 1.0)], style=R.IsDeterministic())
+    kw = dict(style=R.IsDynamicSemistochastic(), time_step=0.002, last_step=100, target_walkers=200)
+    sa, a, _ = run(1, post_step_strategy=(R.ProjectedEnergy(ph, ref), R.Projector(ones=ref)), **kw)
+    sb, b, cb = run(32, post_step_strategy=(R.ProjectedEnergy(ph, ref), R.Projector(ones=ref)), **kw)
+    assert cb == [32, 32, 32, 4] and list(a.columns) == list(b.columns) and {"vproj", "hproj", "ones"} <= set(b.columns)
+    for col in a.columns:
+        assert list(a[col]) == list(b[col]), col
+    sc, c, cc = run(32, post_step_strategy=(R.Timer(),), **kw)
+    assert cc == [] and "time" in c.columns
+    # solve! continues in batches when last_step is raised
+    sim, _, _ = run(50, **kw)
+    del calls[:]
+    R.solve_(sim, last_step=130)
+    assert sim.step == 130 and calls == [30] and len(sim.dataframe()) == 130
