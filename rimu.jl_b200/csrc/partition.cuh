@@ -696,10 +696,10 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         if constexpr (!initm) cp_async_wait_all();
         __syncthreads();
         u32 own = 0;
+        [[maybe_unused]] u32 P2 = 2; // ORD: length of the sorted index array (power of two >= n)
         if constexpr (ORD) {
             // ---- ordered annihilation: sort the item indices by (address, value bits), sum every run in that order
             u32 *idx = owner;
-            u32 P2 = 2;
             while (P2 < n) P2 <<= 1; // uniform
             for (u32 s = tid; s < P2; s += PART_NT) idx[s] = (s < n && svals[s] != 0ull) ? s : NIL;
             __syncthreads();
@@ -808,7 +808,29 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
         // below the threshold into its list so that the Philox draw runs over full warps instead of once per round for the
         // few lanes that need it.  Only this warp touches these entries from here on: __syncwarp is all it takes.
         const bool compressed = !is_int && MODE == 0 && p.compress_thr > 0.0;
-        if constexpr (!is_int && MODE == 0) {
+        if constexpr (ORD && !is_int && MODE == 0) {
+            // audit mode: every thread compresses its own entries in place -- the sorted index array (in the owner table's
+            // memory, where the per-warp lists would go) is still needed for the walker number below
+            if (p.compress_thr > 0.0) { // uniform
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (r >= rmax) break;
+                    if (!((own >> r) & 1u)) continue;
+                    const u32 i = item_of(r);
+                    union { u64 b; double v; } cv; cv.b = svals[i];
+                    if (cv.v == 0.0) continue;
+                    len_before++;
+                    if (fabs(cv.v) >= p.compress_thr) continue;
+                    B key;
+                    if constexpr (W == 1) key = skeys[i]; else key = ((u128)skeys[i * 2 + 1] << 64) | (u128)skeys[i * 2];
+                    const double prob = p.compress_thr == 1.0 ? fabs(cv.v) : fabs(cv.v) / p.compress_thr;
+                    u32 rnd[4];
+                    rng_draw(hash_bits(key), 0, STREAM_COMPRESS, p.k0, p.k1, rnd);
+                    cv.v = (prob > u53(rnd[1], rnd[2])) ? p.compress_thr * sgn_(cv.v) : 0.0;
+                    svals[i] = cv.b;
+                }
+            }
+        } else if constexpr (!is_int && MODE == 0) {
             if (p.compress_thr > 0.0) { // uniform
                 u32 wn = 0;
 #pragma unroll
@@ -852,10 +874,22 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
             if (v == (VT)0) continue; // exact zeros are deleted (pdworkingmemory.jl:25-29); so are compressed-away entries
             keep |= 1u << r; cnt++;
             if (is_int) inorm1 += (i64)(v < (VT)0 ? -v : v);
-            else if (ORD) bnorm += fabs((double)v);
-            else norm1 += fabs((double)v);
+            else if (!ORD) norm1 += fabs((double)v);
         }
-        if constexpr (ORD) { // the bucket's walker number through a fixed tree: lanes, then warps in order -> one entry per BUCKET
+        if constexpr (ORD && !is_int) {
+            // The bucket's walker number in a CANONICAL order.  Which thread owns which survivor depends on where the spawn
+            // kernels' counter atomics happened to put the records, so a sum over "my items" would differ from run to run in its
+            // last bits.  The sorted index array does not: position s holds the s-th smallest (address, value) item whatever the
+            // arrival order was.  Thread t adds the run heads at positions t, t + NT, ... in increasing order, lanes and warps
+            // meet in a fixed tree, buckets are summed in index order afterwards (ordered_sum_kernel).
+            __syncthreads(); // every compressed value is in place
+            const u32 *idx = owner;
+            for (u32 s = tid; s < P2; s += PART_NT) {
+                const u32 a = idx[s];
+                if (a == NIL || !(pidx[a] & OWNFLAG)) continue;
+                union { u64 b; double v; } cv; cv.b = svals[a];
+                bnorm += fabs(cv.v); // (entries that were compressed away add an exact zero)
+            }
             const double wsum = warp_sum(bnorm);
             if (lane == 0) s_wnorm[wid] = wsum;
         }
