@@ -349,7 +349,8 @@ typedef struct {
  * *steps_done steps were taken (< nsteps only when the run ended: dead population, max_length, DontUpdate target reached --
  * the state is that of the last step taken, as in the reference), stats_out[k] / shift_out[k] (optional) hold the statistics
  * of step k and the shift AFTER its update, proj_out[k * nproj + j] = dot(projectors[j], v after step k), and *result_in_w
- * tells which vector holds the current state. */
+ * tells which vector holds the current state.  Both are written on every exit path: after an error (e.g. RIMU_ERR_WORKMEM in
+ * step k) the first *steps_done steps stay taken.  w is scratch: whatever it held is overwritten. */
 int rimu_advance(rimu_ctx *ctx, const rimu_ham *ham, const rimu_step_params *params, rimu_shift_params *sp,
                  rimu_vec *v, rimu_vec *w, int64_t nsteps, const rimu_projector *projectors, int32_t nproj,
                  rimu_step_stats *stats_out, double *shift_out, double *proj_out,

@@ -1524,6 +1524,9 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
         proj_resident = true;
         return 0;
     };
+    // (the loop runs inside a lambda so that *steps_done / *result_in_w describe the state on EVERY exit path: after an error
+    // the steps taken so far stay taken, and the caller must know which vector is current)
+    auto run = [&]() -> int {
     while (done < nsteps && !ended) {
         const bool batchable = c->nranks == 1 && c->method == RIMU_ANNIHILATE_PARTITION && !prm->ordered && cur->nb != 0 && cur->n > 0 &&
                                (u64)cur->n <= RIMU_ADVANCE_MAX_N && cur->diag && cur->diag_uid == h->uid && nsteps - done >= 2 &&
@@ -1654,8 +1657,11 @@ extern "C" int rimu_advance(rimu_ctx *c, const rimu_ham *h, const rimu_step_para
         done += kd;
         if (rc.stop == 1) ended = true;
     }
+    return 0;
+    };
+    const int status = run();
     *steps_done = done;
     *result_in_w = cur == w ? 1 : 0;
-    return 0;
+    return status;
 }
 

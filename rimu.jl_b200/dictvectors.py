@@ -392,13 +392,17 @@ def advance(wm: WorkingMemory, v: GPUDVec, pv: GPUDVec, hamiltonian, shift_param
     for j, fr in enumerate(projectors):
         parr[j].keys, parr[j].values, parr[j].n = fr.keys.ctypes.data_as(_lib._u64p), fr.vals.ctypes.data_as(_lib._f64p), len(fr.vals)
     pout = np.zeros((nsteps, max(nproj, 1)), dtype=np.float64)
-    _lib.check(_lib.lib().rimu_advance(wm.ctx.handle, hamiltonian.handle, C.byref(p), C.byref(sp), v.handle, pv.handle, nsteps,
-                                      parr if nproj else None, nproj, stats, shifts, pout.ctypes.data_as(_lib._f64p) if nproj else None,
-                                      C.byref(done), C.byref(in_w)))
+    status = _lib.lib().rimu_advance(wm.ctx.handle, hamiltonian.handle, C.byref(p), C.byref(sp), v.handle, pv.handle, nsteps,
+                                     parr if nproj else None, nproj, stats, shifts, pout.ctypes.data_as(_lib._f64p) if nproj else None,
+                                     C.byref(done), C.byref(in_w))
+    # the steps taken so far stay taken, also when a later one failed: bring the host's bookkeeping up to date before raising
     wm.counter += done.value
     shift_params.shift, shift_params.pnorm, shift_params.shift_mode = sp.shift, sp.pnorm, bool(sp.shift_mode)
     if done.value:
         wm.last_stats = stats[done.value - 1]
+    if status != 0 and in_w.value:
+        v.handle, pv.handle = pv.handle, v.handle  # no return value on this path: the caller's `v` object stays the current vector
+    _lib.check(status)
     if in_w.value:
         v, pv = pv, v
     out = (v, pv, [stats[k] for k in range(done.value)], [shifts[k] for k in range(done.value)], done.value)
