@@ -665,14 +665,19 @@ function advance_steps!(wm::GPUWorkingMemory, v::GPUDVec, pv::GPUDVec, ham::Abst
     dots = zeros(Float64, max(nproj, 1), nsteps)                       # column k = step k (C: proj_out[k * nproj + j])
     GC.@preserve pkeys pvals begin
         pargs = [ProjectorArg(pointer(pkeys[j]), pointer(pvals[j]), length(pvals[j])) for j in 1:nproj]
-        check(ccall((:rimu_advance, LIB), Cint,
+        status = ccall((:rimu_advance, LIB), Cint,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{StepParams}, Ptr{ShiftParams}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{ProjectorArg}, Int32,
                      Ptr{StepStats}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int32}),
-                    wm.ctx.ptr, gpu_ham(ham, wm.ctx).ptr, params, shp, v.ptr, pv.ptr, nsteps, pargs, nproj, stats, shifts, dots, done, in_w))
+                    wm.ctx.ptr, gpu_ham(ham, wm.ctx).ptr, params, shp, v.ptr, pv.ptr, nsteps, pargs, nproj, stats, shifts, dots, done, in_w)
     end
+    # the steps taken so far stay taken, also when a later one failed: update the host's bookkeeping before raising
     wm.counter += done[]
     sp.shift, sp.pnorm, sp.shift_mode = shp[].shift, shp[].pnorm, shp[].shift_mode != 0
     done[] > 0 && (wm.last_stats = stats[done[]])
+    if status != 0 && in_w[] != 0
+        v.ptr, pv.ptr = pv.ptr, v.ptr                                  # no return value on this path: `v` stays the current vector
+    end
+    check(status)
     in_w[] != 0 && ((v, pv) = (pv, v))
     return v, pv, stats[1:done[]], shifts[1:done[]], dots[1:nproj, 1:done[]]
 end
