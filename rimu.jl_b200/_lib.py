@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RIMU_B200_LIB") or os.path.join(_HERE, "librimu_b200.
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["api.cu", "sort.cu", "sector.cu", "step_hk.cu"]   # step_hk.cu is compiled once per HamKind (-DRIMU_HK=n), in parallel
 HEADERS = ["common.cuh", "hamiltonians.cuh", "kernels.cuh", "partition.cuh", "ham_host.h", "step_math.cuh", "internal.cuh", "sector.cuh"]
-NUM_HAM_KINDS = 8
+NUM_HAM_KINDS = 10
 OBJ_DIR = os.environ.get("RIMU_B200_OBJ_DIR") or os.path.join("/tmp", "rimu_b200_build_" + str(os.getuid()))  # objects stay out of the tree
 
 NVCC_FLAGS = [

@@ -498,7 +498,7 @@ extern "C" int rimu_ham_words(const rimu_ham *h) { return h->W; }
 // per-kind entry points (step_hk.cu)
 static const HkOps *hk_ops(const rimu_ham *h) {
 #ifdef RIMU_TUNE_ONLY_MOM1D // kernel-tuning builds (scratch/): one kind, seconds to compile; never shipped
-    if (h->hk == HK_MOM1D_BOSE && h->W == 1) return rimu_hk_ops_1();
+    if (h->hk == HK_MOM1D_BOSE_PLAIN && h->W == 1) return rimu_hk_ops_9();
     fail(RIMU_ERR_INVALID, "tuning build: only HubbardMom1D/BoseFS one-word addresses are compiled in");
     return nullptr;
 #else
@@ -511,6 +511,8 @@ static const HkOps *hk_ops(const rimu_ham *h) {
     case HK_RS_F2C: return rimu_hk_ops_5();
     case HK_TC_F2C: return rimu_hk_ops_6();
     case HK_RS_COMP: return rimu_hk_ops_7();
+    case HK_REAL1D_BOSE_PLAIN: return rimu_hk_ops_8();
+    case HK_MOM1D_BOSE_PLAIN: return rimu_hk_ops_9();
     }
     fail(RIMU_ERR_INVALID, "unknown Hamiltonian kind");
     return nullptr;

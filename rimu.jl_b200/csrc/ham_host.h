@@ -111,6 +111,11 @@ static inline int ham_build_host(const rimu_ham_desc *d, HamHostImage *img) {
               : model == RIMU_EXTENDED_HUBBARD_MOM_1D ? 1 : model == RIMU_HUBBARD_MOM_1D_EP ? 2 : 0;
     v.v_m = d->v / M;
     v.bc = d->boundary_condition;
+    if (v.variant == 0) { // the plain models get the kernels compiled with the variant folded in
+        if (hk == HK_REAL1D_BOSE) hk = HK_REAL1D_BOSE_PLAIN;
+        else if (hk == HK_MOM1D_BOSE) hk = HK_MOM1D_BOSE_PLAIN;
+        img->hk = hk; v.hk = hk;
+    }
     if (v.variant == 2 && (v.bc < 0 || v.bc > 2)) return ham_host_fail(img, "invalid boundary condition");
     int nz = 0;
     if (hk == HK_RS_COMP) {

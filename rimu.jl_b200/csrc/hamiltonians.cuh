@@ -24,7 +24,16 @@ enum HamKind {
     HK_RS_F2C = 5,
     HK_TC_F2C = 6,
     HK_RS_COMP = 7,   // HubbardRealSpace over a general CompositeFS (2..4 BoseFS / FermiFS components, one or two words)
-    HK_COUNT = 8
+    // "plain" kinds: the code of their base kind with HamDev::variant == 0 known at COMPILE time -- HubbardReal1D and HubbardMom1D
+    // themselves (BASELINE configs 1 and 2).  The variants' branches (EP / Extended models) cost the hot kernels of the plain
+    // models 1.6 % (gpurun_out/r2_sweep_var0.log); ham_build_host picks the plain kind whenever variant == 0.
+    HK_REAL1D_BOSE_PLAIN = 8,
+    HK_MOM1D_BOSE_PLAIN = 9,
+    HK_COUNT = 10
+};
+template <int HKX> struct HkBase {
+    static constexpr int value = HKX == HK_REAL1D_BOSE_PLAIN ? (int)HK_REAL1D_BOSE : HKX == HK_MOM1D_BOSE_PLAIN ? (int)HK_MOM1D_BOSE : HKX;
+    static constexpr bool plain = value != HKX;
 };
 #define HAM_MAX_COMP 4
 
@@ -43,6 +52,13 @@ struct HamDev {
     double tcs[HAM_MAX_COMP], umat[HAM_MAX_COMP * HAM_MAX_COMP]; // t[c]; u[i + ncomp * j]
 };
 
+// the model variant of a kind (see HamDev::variant).  RIMU_TUNE_VARIANT0 (kernel-tuning builds only) compiles the plain models
+// alone, to measure what the variants' branches cost the benchmark configuration.
+#ifdef RIMU_TUNE_VARIANT0
+#define HVARIANT(h) 0
+#else
+#define HVARIANT(h) (HkBase<HKX>::plain ? 0 : (h).variant) /* HKX: the kind the enclosing function was instantiated for */
+#endif
 #if defined(__CUDACC__) || defined(RIMU_HOST_EMULATION)
 // exact x / d for x < 2^21, 0 < d < 2^10 (off-diagonal index decoding): (x + 0.5) / d is at least 0.5/d away from
 // an integer, far more than the float rounding error at these magnitudes, so truncation gives floor(x / d)
@@ -253,11 +269,12 @@ template <class B> DEV long long comp_overlap(const HamDev &h, B x, int a, int b
     return r;
 }
 
-template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
+template <int HKX, class B> DEV double ham_diagonal(const HamDev &h, B x) {
+    constexpr int HK = HkBase<HKX>::value; // (plain kinds run their base kind's code with variant == 0 folded in)
     const int M = h.M;
     if constexpr (HK == HK_REAL1D_BOSE) {
-        if (h.variant == 0) return h.u * (double)bose_interaction(x) / 2;
-        if (h.variant == 1) { // HubbardReal1DEP.jl:82-87: sum over occupied modes (ascending) of u n (n-1) / 2 + eps[mode] n
+        if (HVARIANT(h) == 0) return h.u * (double)bose_interaction(x) / 2;
+        if (HVARIANT(h) == 1) { // HubbardReal1DEP.jl:82-87: sum over occupied modes (ascending) of u n (n-1) / 2 + eps[mode] n
             double s = 0.0; bool first = true;
             int md, n;
             for (BoseModes<B> it(x); it.next(md, n);) {
@@ -288,7 +305,7 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
         const int ntot = h.N0;
         const long long onproduct = (long long)lin + 2LL * ((long long)ntot * ntot - lin - ntot);
         double value = ke + h.u_2m * (double)onproduct;
-        if (h.variant == 1) { // + (v / M) * extended_momentum_transfer_diagonal(map, 2pi / M)  (excitations.jl:145-156)
+        if (HVARIANT(h) == 1) { // + (v / M) * extended_momentum_transfer_diagonal(map, 2pi / M)  (excitations.jl:145-156)
             double ext = 0.0;
             int mi, ni;
             for (BoseModes<B> it(x); it.next(mi, ni);) {
@@ -297,13 +314,13 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
                 for (BoseModes<B> jt(x); jt.next(mj, nj) && mj < mi;) ext += (double)(2 * ni * nj) * (1 + h.us[mi - mj]);
             }
             value += h.v_m * ext;
-        } else if (h.variant == 2) value += (double)ntot * h.pot[0]; // momentum_external_potential_diagonal (excitations.jl:274-279)
+        } else if (HVARIANT(h) == 2) value += (double)ntot * h.pot[0]; // momentum_external_potential_diagonal (excitations.jl:274-279)
         return value;
     } else if constexpr (HK == HK_MOM1D_F2C) {
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
         double ka = kes_sum(h.kes, fa), kb = kes_sum(h.kes, fb);
         double value = ka + kb + h.u_2m * (double)(2 * __popcll(fa) * __popcll(fb));
-        if (h.variant == 2) value = value + (double)__popcll(fa) * h.pot[0] + (double)__popcll(fb) * h.pot[0];
+        if (HVARIANT(h) == 2) value = value + (double)__popcll(fa) * h.pot[0] + (double)__popcll(fb) * h.pot[0];
         return value;
     } else if constexpr (HK == HK_RS_BOSE) {
         double interaction = h.umat_zero ? 0.0 : h.u00 * (double)bose_interaction(x) / 2;
@@ -371,15 +388,16 @@ template <int HK, class B> DEV double ham_diagonal(const HamDev &h, B x) {
     }
 }
 
-template <int HK, class B> DEV long long ham_num_offdiagonals(const HamDev &h, B x) {
+template <int HKX, class B> DEV long long ham_num_offdiagonals(const HamDev &h, B x) {
+    constexpr int HK = HkBase<HKX>::value; // (plain kinds run their base kind's code with variant == 0 folded in)
     const int M = h.M;
     if constexpr (HK == HK_REAL1D_BOSE) {
         return 2LL * bose_num_occupied(x);
     } else if constexpr (HK == HK_MOM1D_BOSE) {
         long long s = bose_num_occupied(x), d = bose_num_doubly(x);
-        return s * (s - 1) * (M - 2) + d * (M - 1) + (h.variant == 2 ? s * (M - 1) : 0);
+        return s * (s - 1) * (M - 2) + d * (M - 1) + (HVARIANT(h) == 2 ? s * (M - 1) : 0);
     } else if constexpr (HK == HK_MOM1D_F2C) {
-        return (long long)h.N0 * h.N1 * (M - 1) + (h.variant == 2 ? (long long)(h.N0 + h.N1) * (M - 1) : 0);
+        return (long long)h.N0 * h.N1 * (M - 1) + (HVARIANT(h) == 2 ? (long long)(h.N0 + h.N1) * (M - 1) : 0);
     } else if constexpr (HK == HK_RS_BOSE) {
         return (long long)bose_num_occupied(x) * h.nnb;
     } else if constexpr (HK == HK_RS_FERMI) {
@@ -399,7 +417,8 @@ template <int HK, class B> DEV long long ham_num_offdiagonals(const HamDev &h, B
 }
 
 // returns H_{out,x} for the i-th (0-based) off-diagonal; out == x whenever the value is 0
-template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long long i, B &out) {
+template <int HKX, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long long i, B &out) {
+    constexpr int HK = HkBase<HKX>::value; // (plain kinds run their base kind's code with variant == 0 folded in)
     const int M = h.M;
     out = x;
     if constexpr (HK == HK_REAL1D_BOSE) {
@@ -410,7 +429,7 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         int nd = bose_create(y, dst);
         out = y;
         double val = sqrt((double)(ns * nd));
-        if (h.variant == 2) { // hopnextneighbour(b, i, boundary_condition) bosefs.jl:355-369
+        if (HVARIANT(h) == 2) { // hopnextneighbour(b, i, boundary_condition) bosefs.jl:355-369
             const bool on_boundary = (i & 1) ? mode == 1 : mode == M;
             if (on_boundary && h.bc == 2) val = -val;
             else if (on_boundary && h.bc == 1) { val = 0.0; out = x; }
@@ -420,7 +439,7 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         const int s = bose_num_occupied(x);
         const int ndiff = s * (s - 1) * (M - 2);
         const int ii = (int)i;
-        if (h.variant == 2) { // HubbardMom1DEP: the external-potential block follows the momentum-transfer block
+        if (HVARIANT(h) == 2) { // HubbardMom1DEP: the external-potential block follows the momentum-transfer block
             const int nmom = ndiff + bose_num_doubly(x) * (M - 1);
             if (ii >= nmom) { // momentum_external_potential_excitation (excitations.jl:257-267): a^dagger_q a_p, q != p
                 const unsigned e = (unsigned)(ii - nmom), mm1 = (unsigned)(M - 1);
@@ -465,14 +484,14 @@ template <int HK, class B> DEV double ham_offdiagonal(const HamDev &h, B x, long
         value *= bose_create(y, dst1);
         value *= bose_create(y, dst0);
         out = y;
-        if (h.variant == 1) { // ExtendedHubbardMom1D.jl:99-102: u * onproduct / 2M + v * cos(q * 2pi / M) * onproduct / M, q = -mom
+        if (HVARIANT(h) == 1) { // ExtendedHubbardMom1D.jl:99-102: u * onproduct / 2M + v * cos(q * 2pi / M) * onproduct / M, q = -mom
             const double op = sqrt((double)value);
             return h.u * op / (2 * M) + h.v * h.ws[mom] * op / M;
         }
         return h.u_2m * sqrt((double)value);
     } else if constexpr (HK == HK_MOM1D_F2C) {
         u64 mask = (1ull << M) - 1, fa = (u64)x & mask, fb = ((u64)x >> M) & mask;
-        if (h.variant == 2) { // HubbardMom1DEP.jl:223-257: then N1 (M-1) one-body moves of component a, N2 (M-1) of component b
+        if (HVARIANT(h) == 2) { // HubbardMom1DEP.jl:223-257: then N1 (M-1) one-body moves of component a, N2 (M-1) of component b
             const long long nmom = (long long)h.N0 * h.N1 * (M - 1);
             if (i >= nmom) {
                 unsigned e = (unsigned)(i - nmom);

@@ -247,4 +247,6 @@ RIMU_INTERNAL const HkOps *rimu_hk_ops_4();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_5();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_6();
 RIMU_INTERNAL const HkOps *rimu_hk_ops_7();
+RIMU_INTERNAL const HkOps *rimu_hk_ops_8();
+RIMU_INTERNAL const HkOps *rimu_hk_ops_9();
 

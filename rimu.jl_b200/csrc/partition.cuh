@@ -503,9 +503,10 @@ merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev 
     if (tid == 0) s_arrive = 0;
     // the kinetic-energy table of the momentum-space models is read once per occupied mode by every H_aa evaluation: keep
     // it in shared memory (29-cycle loads instead of a trip through L1/L2)
-    __shared__ double s_kes[HK == HK_MOM1D_BOSE || HK == HK_MOM1D_F2C || HK == HK_TC_F2C ? 64 : 1];
+    constexpr int BK = HkBase<HK>::value;
+    __shared__ double s_kes[BK == HK_MOM1D_BOSE || BK == HK_MOM1D_F2C || BK == HK_TC_F2C ? 64 : 1];
     HamDev hl = h;
-    if constexpr (HK == HK_MOM1D_BOSE || HK == HK_MOM1D_F2C || HK == HK_TC_F2C) {
+    if constexpr (BK == HK_MOM1D_BOSE || BK == HK_MOM1D_F2C || BK == HK_TC_F2C) {
         if (h.kes && h.M <= 64) {
             if (tid < h.M) s_kes[tid] = h.kes[tid];
             hl.kes = s_kes;

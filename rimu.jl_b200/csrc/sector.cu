@@ -245,12 +245,14 @@ extern "C" int rimu_sector_mul(rimu_sector *s, const double *d_x, double *d_y, f
     switch (s->ham->hk) {
 #ifndef RIMU_TUNE_ONLY_MOM1D
     case HK_REAL1D_BOSE: ops = rimu_hk_ops_0(); break;
+    case HK_REAL1D_BOSE_PLAIN: ops = rimu_hk_ops_8(); break;
     case HK_MOM1D_F2C: ops = rimu_hk_ops_2(); break;
     case HK_RS_BOSE: ops = rimu_hk_ops_3(); break;
     case HK_RS_FERMI: ops = rimu_hk_ops_4(); break;
     case HK_RS_F2C: ops = rimu_hk_ops_5(); break;
-#endif
     case HK_MOM1D_BOSE: ops = rimu_hk_ops_1(); break;
+#endif
+    case HK_MOM1D_BOSE_PLAIN: ops = rimu_hk_ops_9(); break;
     default: return fail(RIMU_ERR_INVALID, "this Hamiltonian kind has no dense H*v");
     }
     CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));

@@ -163,7 +163,8 @@ static constexpr int HKC = RIMU_HK;
 #ifdef RIMU_TUNE_ONLY_MOM1D
 static constexpr bool HAS_W2 = false;
 #else
-static constexpr bool HAS_W2 = HKC == HK_REAL1D_BOSE || HKC == HK_MOM1D_BOSE || HKC == HK_RS_BOSE || HKC == HK_RS_COMP;
+static constexpr int HKB = HkBase<HKC>::value;
+static constexpr bool HAS_W2 = HKB == HK_REAL1D_BOSE || HKB == HK_MOM1D_BOSE || HKB == HK_RS_BOSE || HKB == HK_RS_COMP;
 #endif
 
 template <int W> static int step_w(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu_vec *src, rimu_vec *dst, bool use_part, bool is_int,

@@ -7,5 +7,5 @@ mkdir -p scratch/variants
 python - "$name" "$@" <<'PY'
 import sys, rimu_b200
 name, defs = sys.argv[1], sys.argv[2:]
-print("built", rimu_b200.build(defines=["-DRIMU_TUNE_ONLY_MOM1D"] + defs, out=f"scratch/variants/lib_{name}.so", kinds=[1]))
+print("built", rimu_b200.build(defines=["-DRIMU_TUNE_ONLY_MOM1D"] + defs, out=f"scratch/variants/lib_{name}.so", kinds=[9]))
 PY

@@ -29,6 +29,8 @@ template <class F> static auto dispatch(int hk, int W, F &&f) {
     switch (hk) {
     case HK_REAL1D_BOSE: return W == 1 ? f(std::integral_constant<int, HK_REAL1D_BOSE>(), u64()) : f(std::integral_constant<int, HK_REAL1D_BOSE>(), u128());
     case HK_MOM1D_BOSE: return W == 1 ? f(std::integral_constant<int, HK_MOM1D_BOSE>(), u64()) : f(std::integral_constant<int, HK_MOM1D_BOSE>(), u128());
+    case HK_REAL1D_BOSE_PLAIN: return W == 1 ? f(std::integral_constant<int, HK_REAL1D_BOSE_PLAIN>(), u64()) : f(std::integral_constant<int, HK_REAL1D_BOSE_PLAIN>(), u128());
+    case HK_MOM1D_BOSE_PLAIN: return W == 1 ? f(std::integral_constant<int, HK_MOM1D_BOSE_PLAIN>(), u64()) : f(std::integral_constant<int, HK_MOM1D_BOSE_PLAIN>(), u128());
     case HK_MOM1D_F2C: return f(std::integral_constant<int, HK_MOM1D_F2C>(), u64());
     case HK_RS_BOSE: return W == 1 ? f(std::integral_constant<int, HK_RS_BOSE>(), u64()) : f(std::integral_constant<int, HK_RS_BOSE>(), u128());
     case HK_RS_FERMI: return f(std::integral_constant<int, HK_RS_FERMI>(), u64());
