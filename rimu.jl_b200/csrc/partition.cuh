@@ -55,6 +55,14 @@
 #ifndef PART_ASYNC_PARENTS
 #define PART_ASYNC_PARENTS 0 // (1 after validation on the GPU) merge: parents are staged with cp.async like the records (all loads of a bucket in flight at once)
 #endif
+// kernel-tuning builds only (-DRIMU_TUNE_FIXED_STEP): the step parameters of BASELINE config 2 (IsDynamicSemistochastic with late
+// compression, one rank, no initiator rule, FirstOrderTransitionOperator) as compile-time constants -- measures what the runtime
+// branches on them cost.  Shipping builds copy the parameter struct as it is.
+#ifdef RIMU_TUNE_FIXED_STEP
+#define RIMU_TUNE_FIX_STEP(p, p_in) StepDev p = p_in; p.style = 2; p.plain_h = 0; p.nranks = 1; p.rank = 0; p.init_rule = 0; p.ordered = 0; p.proj_thr = 0.0; p.ctl = nullptr;
+#else
+#define RIMU_TUNE_FIX_STEP(p, p_in) const StepDev &p = p_in;
+#endif
 #define HEAVY_T 1024       // parents with more attempts than this are queued for K2
 #define HEAVY_TILE 8192    // attempts per K2 work item
 #define ACC_MAX 4096       // K2 pre-sums per off-diagonal index when L <= ACC_MAX
@@ -184,9 +192,10 @@ DEV bool route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
 // ---------------------------------------------------------------- K1: spawning, CTA-local work distribution
 template <int HK, int W, class VT>
 __global__ void __launch_bounds__(SPAWN_NT, SPAWN_MINB)
-spawn_part_kernel(const HamDev h, const StepDev p, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
+spawn_part_kernel(const HamDev h, const StepDev p_in, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
                   PartDev pt, ExchangeDev xch, HeavyDev hv, StatsDev *st) {
     typedef typename BitsT<W>::type B;
+    RIMU_TUNE_FIX_STEP(p, p_in)
     if (p.ctl) { // batch of steps: the source is the previous step's result, its length is known on the device only
         if (p.ctl->stop) return;
         n = (i64)p.ctl->n;
@@ -438,8 +447,9 @@ template <> struct Log2<1> { static constexpr u32 value = 0; };
 // function of its inputs, bit for bit.  ~10x slower than the hash placement; selected by rimu_step_params.ordered.
 template <int HK, int W, class VT, int MODE, bool INIT = false, bool ORD = false>
 __global__ void __launch_bounds__(PART_NT, PART_MINB)
-merge_kernel(const HamDev h, const StepDev p, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st, double *ord_partials = nullptr) {
+merge_kernel(const HamDev h, const StepDev p_in, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st, double *ord_partials = nullptr) {
     typedef typename BitsT<W>::type B;
+    RIMU_TUNE_FIX_STEP(p, p_in)
     constexpr bool is_int = std::is_integral<VT>::value;
     constexpr int CAP = PartCap<W>::value;
     constexpr int R = CAP / PART_NT;
