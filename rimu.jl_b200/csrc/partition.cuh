@@ -61,8 +61,24 @@
 #ifdef RIMU_TUNE_FIXED_STEP
 #define RIMU_TUNE_FIX_STEP(p, p_in) StepDev p = p_in; p.style = 2; p.plain_h = 0; p.nranks = 1; p.rank = 0; p.init_rule = 0; p.ordered = 0; p.proj_thr = 0.0; p.ctl = nullptr;
 #else
-#define RIMU_TUNE_FIX_STEP(p, p_in) const StepDev &p = p_in;
+#define RIMU_TUNE_FIX_STEP(p, p_in) const StepDev p = step_view<FS>(p_in);
 #endif
+// FS ("fixed step parameters"): the kernels of the default production run -- IsDynamicSemistochastic with late compression on
+// one GPU through rimu_step, no initiator rule, not ordered -- are instantiated a second time with those parameters as
+// compile-time constants: the branches on style / plain_h / nranks / init_rule / proj_threshold fold away (spawn kernel
+// 60 -> 54 registers).  rimu_step picks the instantiation when the call's parameters match (fixed_step_ok); results are identical.
+template <bool FS> DEV StepDev step_view(const StepDev &in) {
+    StepDev p = in;
+    if constexpr (FS) { p.style = 2; p.plain_h = 0; p.nranks = 1; p.rank = 0; p.init_rule = 0; p.ordered = 0; p.proj_thr = 0.0; p.ctl = nullptr; }
+    return p;
+}
+static inline bool fixed_step_ok(const StepDev &p, bool is_int) {
+#ifdef RIMU_NO_FIXED_STEP
+    (void)p; (void)is_int; return false;
+#else
+    return !is_int && p.style == 2 && !p.plain_h && p.nranks == 1 && !p.init_rule && !p.ordered && p.proj_thr == 0.0 && !p.ctl;
+#endif
+}
 #define HEAVY_T 1024       // parents with more attempts than this are queued for K2
 #define HEAVY_TILE 8192    // attempts per K2 work item
 #define ACC_MAX 4096       // K2 pre-sums per off-diagonal index when L <= ACC_MAX
@@ -190,7 +206,7 @@ DEV bool route_record(const PartDev &pt, const ExchangeDev &x, const StepDev &p,
 }
 
 // ---------------------------------------------------------------- K1: spawning, CTA-local work distribution
-template <int HK, int W, class VT>
+template <int HK, int W, class VT, bool FS = false>
 __global__ void __launch_bounds__(SPAWN_NT, SPAWN_MINB)
 spawn_part_kernel(const HamDev h, const StepDev p_in, const u64 *__restrict__ keys, const VT *__restrict__ vals, i64 n,
                   PartDev pt, ExchangeDev xch, HeavyDev hv, StatsDev *st) {
@@ -445,7 +461,7 @@ template <> struct Log2<1> { static constexpr u32 value = 0; };
 // (address, value bits) with a bitonic network in shared memory (the hash table is not used at all), every address is summed
 // by one thread in that order, and the walker number is reduced in a fixed order as well: the step's result is a pure
 // function of its inputs, bit for bit.  ~10x slower than the hash placement; selected by rimu_step_params.ordered.
-template <int HK, int W, class VT, int MODE, bool INIT = false, bool ORD = false>
+template <int HK, int W, class VT, int MODE, bool INIT = false, bool ORD = false, bool FS = false>
 __global__ void __launch_bounds__(PART_NT, PART_MINB)
 merge_kernel(const HamDev h, const StepDev p_in, SegSrc src, double alpha, PartDev pt, SegDst dst, StatsDev *st, double *ord_partials = nullptr) {
     typedef typename BitsT<W>::type B;

@@ -61,8 +61,11 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
     if (!attr_set[HK][W][std::is_integral<VT>::value]) {
         CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
         CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(part_smem_bytes(W) + smem_init)));
+        if constexpr (!std::is_integral<VT>::value)
+            CUDA_TRY(cudaFuncSetAttribute(merge_kernel<HK, W, VT, 0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_bytes(W)));
         attr_set[HK][W][std::is_integral<VT>::value] = true;
     }
+    const bool fs = fixed_step_ok(p, std::is_integral<VT>::value); // the default production run: kernels with its parameters folded in
     CUDA_TRY(cudaMemsetAsync(c->d_stats, 0, sizeof(StatsDev), c->stream)); // statistics + heavy-parent queue head
     if (!c->rcnt_clean) // fills of every (destination, lane) sub-stream; on one rank the previous merge has already cleared them
         CUDA_TRY(cudaMemsetAsync(c->part.rcnt, 0, (size_t)c->part.nsrc * nb * sizeof(u32), c->stream));
@@ -73,8 +76,17 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
         c->part.ppc = spawn_chunk_parents(n, c->sm_count);
         const i64 nchunks = (n + c->part.ppc - 1) / c->part.ppc;
         const int grid = (int)(nchunks < (i64)c->sm_count * 8 ? nchunks : (i64)c->sm_count * 8);
-        spawn_part_kernel<HK, W, VT><<<grid, SPAWN_NT, 0, c->stream>>>(
-            h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->xch, c->heavy, c->d_stats);
+        bool launched = false;
+        if constexpr (!std::is_integral<VT>::value) {
+            if (fs) {
+                spawn_part_kernel<HK, W, VT, true><<<grid, SPAWN_NT, 0, c->stream>>>(
+                    h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->xch, c->heavy, c->d_stats);
+                launched = true;
+            }
+        }
+        if (!launched)
+            spawn_part_kernel<HK, W, VT><<<grid, SPAWN_NT, 0, c->stream>>>(
+                h->dev, p, src->keys, (const VT *)src->vals, n, c->part, c->xch, c->heavy, c->d_stats);
         spawn_heavy_kernel<HK, W, VT><<<c->sm_count * 4, SPAWN_NT, 0, c->stream>>>(
             h->dev, p, src->keys, (const VT *)src->vals, c->part, c->xch, c->heavy, c->d_stats);
         c->launches += 2;
@@ -116,7 +128,15 @@ static int step_part_once(rimu_ctx *c, const rimu_ham *h, const StepDev &p, rimu
             return 0;
         }
     }
-    if (p.init_rule) merge_kernel<HK, W, VT, 0, true><<<mgrid, PART_NT, part_smem_bytes(W) + smem_init, c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
+    bool merged = false;
+    if constexpr (!std::is_integral<VT>::value) {
+        if (fs) {
+            merge_kernel<HK, W, VT, 0, false, false, true><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
+            merged = true;
+        }
+    }
+    if (merged) {}
+    else if (p.init_rule) merge_kernel<HK, W, VT, 0, true><<<mgrid, PART_NT, part_smem_bytes(W) + smem_init, c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     else merge_kernel<HK, W, VT, 0, false><<<mgrid, PART_NT, part_smem_bytes(W), c->stream>>>(h->dev, p, ss, 1.0, c->part, sd, c->d_stats);
     CUDA_TRY(cudaGetLastError());
     c->launches += 1;
