@@ -1010,10 +1010,10 @@ long orc_step_threaded(const orc_ham *h, const orc_step_params *p, long n, const
         for (int c = 1; c < T; c++) {
             orc_mapv *src = &grid[c * T + r];
             for (size_t s = 0; s < src->cap; s++)
-                if (src->used[s]) {
+                if (src->used[s]) { /* (the unsafe / initiator lanes are all zero unless an initiator rule is on) */
                     mapv_add_lane(&grid[r], src->keys + s * W, src->vals[s], LANE_SAFE);
-                    mapv_add_lane(&grid[r], src->keys + s * W, src->vals_u[s], LANE_UNSAFE);
-                    mapv_add_lane(&grid[r], src->keys + s * W, src->vals_i[s], LANE_INIT);
+                    if (src->vals_u[s].i != 0) mapv_add_lane(&grid[r], src->keys + s * W, src->vals_u[s], LANE_UNSAFE);
+                    if (src->vals_i[s].i != 0) mapv_add_lane(&grid[r], src->keys + s * W, src->vals_i[s], LANE_INIT);
                 }
         }
         rows[r] = (orc_rec *)malloc(sizeof(orc_rec) * (grid[r].count + 1));
